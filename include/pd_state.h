@@ -1,0 +1,131 @@
+/*
+ * pd_state.h -- canonical per-car state record of the batched Car::step path.
+ *
+ * One record = everything the reference keeps between two ticks for ONE car of the
+ * demo-car topology: 7 rigid bodies, 4 tyres with
+ * their 12x3 thermal patch grid, drivetrain / engine / assist state machines, track
+ * locator and scoring state.  On the device the record is stored structure-of-arrays
+ * (word w of env e lives at state[w * n_envs + e], 32-bit words, doubles as lo/hi
+ * word pairs); on the host (snapshot / restore, parity tests, the oracle harness) it is
+ * the flat array of PD_STATE_WORDS 32-bit words laid out by the X-macros below.
+ *
+ * Reference anchors for every group are given next to the list that defines it
+ * (paths relative to the reference tree, src/ProjectD/...).
+ *
+ * Field kinds:  F = float (1 word)   I = int32 (1 word)   D = double (2 words: lo, hi)
+ */
+#ifndef PD_STATE_H
+#define PD_STATE_H
+
+#include <stdint.h>
+
+#define PD_NUM_BODIES   7
+#define PD_BODY_CHASSIS 0  /* Car::body              Car/Car.cpp:38        */
+#define PD_BODY_TANK    1  /* Car::fuelTankBody      Car/Car.cpp:39,49-51  */
+#define PD_BODY_HUB0    2  /* SuspensionStrut::hub   (LF)  SuspensionStrut.cpp:132 */
+#define PD_BODY_STRUT0  3  /* SuspensionStrut::strutBody (LF) SuspensionStrut.cpp:135 */
+#define PD_BODY_HUB1    4  /* (RF) */
+#define PD_BODY_STRUT1  5  /* (RF) */
+#define PD_BODY_AXLE    6  /* Car::rigidAxle         Car/Car.cpp:66, SuspensionAxle.cpp:46 */
+
+#define PD_NUM_WHEELS   4   /* LF, RF, LR, RR (Car/Car.cpp:72) */
+#define PD_THERMAL_STRIPES  3   /* Tyre.cpp:41 thermalModel->init(car, 12, 3) */
+#define PD_THERMAL_ELEMENTS 12
+#define PD_THERMAL_PATCHES  36
+#define PD_MAX_PROBES   10  /* CarState::MaxProbes    Car/CarState.h:48 */
+#define PD_LOOKAHEAD    5   /* CarState::MaxLookAhead Car/CarState.h:51 */
+#define PD_OBS_DIM      24  /* pyprojectd/projectd_env.py:237-275 */
+
+/* ---- rigid body: dxBody pos/q/lvel/avel (ODE 0.16.3 objects; RigidBodyODE.cpp:131-231) ---- */
+#define PD_BODY_FIELDS(X) \
+    X(F, px) X(F, py) X(F, pz) \
+    X(F, qw) X(F, qx) X(F, qy) X(F, qz) \
+    X(F, vx) X(F, vy) X(F, vz) \
+    X(F, wx) X(F, wy) X(F, wz)
+
+/* ---- tyre: TyreStatus (Car/TyreStatus.h:5-45) + Tyre runtime members (Car/Tyre.h:88-106) ---- */
+#define PD_TYRE_FIELDS(X) \
+    X(F, depth) X(F, load) X(F, camberRAD) X(F, slipAngleRAD) X(F, slipRatio) \
+    X(F, angularVelocity) X(F, Fy) X(F, Fx) X(F, Mz) X(I, isLocked) \
+    X(F, slipFactor) X(F, ndSlip) X(F, distToGround) X(F, Dy) X(F, Dx) X(F, D) \
+    X(F, dirtyLevel) X(F, rollingResistence) X(F, thermalInput) X(F, feedbackTorque) \
+    X(F, loadedRadius) X(F, effectiveRadius) X(F, liveRadius) \
+    X(F, pressureStatic) X(F, pressureDynamic) X(D, virtualKM) X(F, inflation) \
+    X(D, flatSpot) X(F, wearMult) \
+    X(F, oldAngularVelocity) X(F, localMX) \
+    X(F, contactX) X(F, contactY) X(F, contactZ) \
+    X(F, normalX) X(F, normalY) X(F, normalZ) \
+    X(I, surfaceId) X(I, hasContact) \
+    X(F, totalHubVelocity) X(F, slidingVelocityX) X(F, slidingVelocityY) \
+    X(F, brakeTorque) X(F, handBrakeTorque) \
+    X(F, suspTravel) X(F, suspDamperSpeed) \
+    /* TyreThermalModel (Car/TyreThermalModel.h:36-49) */ \
+    X(F, coreTemp) X(D, phase) X(F, practicalTemp) X(F, thermalMultD)
+
+/* ---- car-level (Car/Car.h:187-246, AutoClutch.h, AutoBlip.h, AutoShifter.h, GearChanger.h,
+ *      Drivetrain.h:98-145, Engine.h:96-115, ScoringSystem.h:47-66, Track.h:76,79) ---- */
+#define PD_CAR_FIELDS(X) \
+    /* CarControls (Car/CarControls.h:9-20) as last written by the caller / the assists */ \
+    X(F, ctlSteer) X(F, ctlClutch) X(F, ctlBrake) X(F, ctlHandBrake) X(F, ctlGas) \
+    X(I, ctlRequestedGear) X(I, ctlGearUp) X(I, ctlGearDn) X(I, smoothSteer) \
+    X(F, smoothSteerValue) X(F, finalSteerAngleSignal) \
+    X(F, lastVelX) X(F, lastVelY) X(F, lastVelZ) \
+    X(F, accGX) X(F, accGY) X(F, accGZ) \
+    X(D, fuel) X(I, sleepingFrames) X(F, waterT) X(F, speed) \
+    X(I, collisionFlag) X(I, outOfTrackFlag) \
+    /* track locator */ \
+    X(I, nearestTrackPointId) X(I, oldTrackPointId) X(I, splinePointId) \
+    X(F, lastTrackPointTimestamp) X(F, trackLocation) X(F, oldTrackLocation) \
+    X(F, bodyVsTrack) X(F, velocityVsTrack) \
+    X(F, pointCacheX) X(F, pointCacheY) X(F, pointCacheZ) \
+    /* AutoClutch */ \
+    X(F, acSeqTime) X(I, acSeqDone) X(I, acSeqProfile) X(F, acClutchValueSignal) \
+    /* AutoBlip / AutoShifter / GearChanger */ \
+    X(D, blipStartTime) X(F, gasCutoff) X(I, lastGearUp) X(I, lastGearDn) \
+    /* Drivetrain */ \
+    X(I, reqRequest) X(D, reqTimeAcc) X(D, reqTimeout) X(I, reqGear) \
+    X(D, engineVel) X(D, driveVel) X(D, shaftLVel) X(D, shaftRVel) X(D, rootVel) \
+    X(D, locClutch) X(D, lastRatio) X(D, cutOff) \
+    X(I, currentGear) X(I, isGearGrinding) X(I, clutchOpenState) \
+    X(D, validShiftRPMWindow) X(D, currentClutchTorque) \
+    /* Engine */ \
+    X(I, limiterOn) X(F, lifeLeft) X(F, fuelPressure) X(F, gasUsage) X(D, outTorque) \
+    /* ScoringSystem */ \
+    X(I, drifting) X(I, driftExtreme) X(I, driftInvalid) \
+    X(F, currentDriftAngle) X(F, currentSpeedMultiplier) X(F, lastDriftDirection) \
+    X(F, driftStraightTimer) X(F, instantDriftDelta) X(F, instantDrift) X(F, driftPoints) \
+    X(I, driftComboCounter) X(F, stepReward) X(F, totalReward) X(F, prevEpisodeReward) \
+    X(I, oldPointId) X(I, oldSplinePointId) \
+    /* batched-env bookkeeping (no reference counterpart: episode statistics, NaN guard) */ \
+    X(I, episodeSteps) X(I, nanFlag)
+
+/* ---------------------------------------------------------------------------------------- */
+#define PD__W_F 1
+#define PD__W_I 1
+#define PD__W_D 2
+#define PD__COUNT(kind, name) + PD__W_##kind
+
+#define PD_BODY_WORDS   (0 PD_BODY_FIELDS(PD__COUNT))
+#define PD_TYRE_SCALAR_WORDS (0 PD_TYRE_FIELDS(PD__COUNT))
+#define PD_TYRE_WORDS   (PD_TYRE_SCALAR_WORDS + PD_THERMAL_PATCHES)
+#define PD_CAR_SCALAR_WORDS  (0 PD_CAR_FIELDS(PD__COUNT))
+#define PD_CAR_WORDS    (PD_CAR_SCALAR_WORDS + PD_MAX_PROBES + PD_LOOKAHEAD)
+
+/* word offsets of the groups inside one record */
+#define PD_OFF_BODY(b)   ((b) * PD_BODY_WORDS)
+#define PD_OFF_TYRE(w)   (PD_NUM_BODIES * PD_BODY_WORDS + (w) * PD_TYRE_WORDS)
+#define PD_OFF_TYRE_PATCH(w) (PD_OFF_TYRE(w) + PD_TYRE_SCALAR_WORDS)
+#define PD_OFF_CAR       (PD_OFF_TYRE(PD_NUM_WHEELS))
+#define PD_OFF_PROBES    (PD_OFF_CAR + PD_CAR_SCALAR_WORDS)
+#define PD_OFF_LOOKAHEAD (PD_OFF_PROBES + PD_MAX_PROBES)
+#define PD_STATE_WORDS   (PD_OFF_CAR + PD_CAR_WORDS)
+
+/* per-field word offsets inside their group: PD_BODY_o_px, PD_TYRE_o_load, PD_CAR_o_fuel ... */
+#define PD__ENUM_B(kind, name) PD_BODY_o_##name, PD_BODY_e_##name = PD_BODY_o_##name + PD__W_##kind - 1,
+#define PD__ENUM_T(kind, name) PD_TYRE_o_##name, PD_TYRE_e_##name = PD_TYRE_o_##name + PD__W_##kind - 1,
+#define PD__ENUM_C(kind, name) PD_CAR_o_##name,  PD_CAR_e_##name  = PD_CAR_o_##name  + PD__W_##kind - 1,
+enum { PD_BODY_FIELDS(PD__ENUM_B) PD_BODY__end };
+enum { PD_TYRE_FIELDS(PD__ENUM_T) PD_TYRE__end };
+enum { PD_CAR_FIELDS(PD__ENUM_C)  PD_CAR__end };
+
+#endif /* PD_STATE_H */

@@ -1,0 +1,281 @@
+/*
+ * oracle/ode_restate/physics_restate.cpp -- TEST INFRASTRUCTURE (oracle only).
+ *
+ * An IPhysicsEngine back-end (Physics/IPhysicsEngine.h:10-28) for the reference's UNMODIFIED
+ * Car/Sim/Core sources, standing in for Physics/ODE/*.cpp whose third-party dependency (ODE 0.16.3)
+ * is absent from /root/reference.  It replaces Physics/PhysicsFactory.cpp:6-9 and mirrors, call for
+ * call, what the reference's wrappers ask ODE to do:
+ *   bodies      Physics/ODE/RigidBodyODE.cpp:5-270
+ *   joints      Physics/ODE/JointODE.cpp:21-88   (ERP/CFM overrides: only DBall honours them)
+ *   rays        Physics/ODE/PhysicsEngineODE.cpp:168-214, RayCasterODE.cpp:11-28
+ *   world step  Physics/ODE/PhysicsEngineODE.cpp:216-224  -> oder::world_step (ode_core.h)
+ * The arithmetic is in ode_core.h (restated ODE).  Ray-vs-trimesh follows OPCODE's culling
+ * Moller-Trumbore test (OPC_RayTriOverlap.h) and ODE's dCollideRTL contact construction
+ * (collision_trimesh_ray.cpp): t < length, det > 1e-6 with back-face culling, contact normal =
+ * normalised (v1-v0)x(v2-v0) after ODE's g1/g2 swap, minimum depth across meshes.  DEVIATION
+ * (documented): within one mesh the closest stabbed triangle is returned, where ODE
+ * with FirstContact=1 returns the first triangle met by OPCODE's tree walk.
+ * Collision detection between the car colliders and the track (collisionStep,
+ * PhysicsEngineODE.cpp:228-341) is NOT restated yet (deferred); colliders are
+ * accepted and ignored.
+ */
+#include "Physics/PhysicsFactory.h"
+#include "Physics/IPhysicsEngine.h"
+#include "Core/Diag.h"
+#include "ode_core.h"
+#include <cfloat>
+
+namespace D {
+
+using oder::dReal;
+
+struct RestateEngine;
+typedef std::shared_ptr<RestateEngine> RestateEnginePtr;
+
+struct TriMeshR : public ITriMesh {
+    std::vector<TriMeshVertex> vertices;
+    std::vector<TriMeshIndex> indices;
+    void resize(size_t vc, size_t ic) override { vertices.resize(vc); indices.resize(ic); }
+    TriMeshVertex* getVB() override { return vertices.data(); }
+    size_t getVertexCount() override { return vertices.size(); }
+    TriMeshIndex* getIB() override { return indices.data(); }
+    size_t getIndexCount() override { return indices.size(); }
+};
+
+struct CollisionMeshR : public ICollisionObject {
+    ITriMeshPtr trimesh;
+    void* userPointer = nullptr;
+    unsigned long category = 0, mask = 0;
+    bool isDynamic = false;
+    float bbMin[3], bbMax[3];
+    /* spatial index only (plays the role of OPCODE's AABB tree; does not change results):
+       uniform x-z grid of triangle lists */
+    int gnx = 1, gnz = 1; float gcell = 1.0f;
+    std::vector<std::vector<uint32_t>> cells;
+    void buildGrid() {
+        const float target = 4.0f;
+        gnx = std::max(1, std::min(128, (int)ceilf((bbMax[0] - bbMin[0]) / target)));
+        gnz = std::max(1, std::min(128, (int)ceilf((bbMax[2] - bbMin[2]) / target)));
+        cells.assign((size_t)gnx * gnz, {});
+        const TriMeshVertex* vb = trimesh->getVB(); const TriMeshIndex* ib = trimesh->getIB();
+        const size_t nt = trimesh->getIndexCount() / 3;
+        const float sx = gnx / std::max(1e-6f, bbMax[0] - bbMin[0]), sz = gnz / std::max(1e-6f, bbMax[2] - bbMin[2]);
+        for (size_t t = 0; t < nt; ++t) {
+            float x0 = FLT_MAX, x1 = -FLT_MAX, z0 = FLT_MAX, z1 = -FLT_MAX;
+            for (int k = 0; k < 3; ++k) { const TriMeshVertex& v = vb[ib[t * 3 + k]]; x0 = std::min(x0, v.x); x1 = std::max(x1, v.x); z0 = std::min(z0, v.z); z1 = std::max(z1, v.z); }
+            int ix0 = std::max(0, std::min(gnx - 1, (int)floorf((x0 - bbMin[0]) * sx) - 1)), ix1 = std::max(0, std::min(gnx - 1, (int)floorf((x1 - bbMin[0]) * sx) + 1));
+            int iz0 = std::max(0, std::min(gnz - 1, (int)floorf((z0 - bbMin[2]) * sz) - 1)), iz1 = std::max(0, std::min(gnz - 1, (int)floorf((z1 - bbMin[2]) * sz) + 1));
+            for (int iz = iz0; iz <= iz1; ++iz) for (int ix = ix0; ix <= ix1; ++ix) cells[(size_t)iz * gnx + ix].push_back((uint32_t)t);
+        }
+    }
+    void setUserPointer(void* d) override { userPointer = d; }
+    void* getUserPointer() override { return userPointer; }
+    unsigned long getGroup() override { return category; }
+    unsigned long getMask() override { return mask; }
+};
+
+struct RigidBodyR : public IRigidBody {
+    oder::Body b;
+    RestateEngine* core;
+    explicit RigidBodyR(RestateEngine* c) : core(c) {}
+    void setEnabled(bool) override {}
+    bool isEnabled() override { return true; }
+    void setAutoDisable(bool) override {}
+    void stop() override { for (int i = 0; i < 3; ++i) { b.lvel[i] = 0; b.avel[i] = 0; b.facc[i] = 0; b.tacc[i] = 0; } }
+
+    void setMassBox(float m, float x, float y, float z) override { oder::body_set_mass_box(b, m, x, y, z); }
+    float getMass() override { return b.mass; }
+    void setMassExplicitInertia(float, float, float, float) override { SHOULD_NOT_REACH_FATAL; /* not used by the demo car */ }
+    vec3f getLocalInertia() override { return vec3f(b.I[0], b.I[1], b.I[2]); }
+
+    vec3f localToWorld(const vec3f& p) override { dReal r[3]; oder::body_rel_point_pos(b, &p.x, r); return vec3f(r); }
+    vec3f worldToLocal(const vec3f& p) override { dReal r[3]; oder::body_pos_rel_point(b, &p.x, r); return vec3f(r); }
+    vec3f localToWorldNormal(const vec3f& p) override { dReal r[3]; oder::mul0_331(r, b.R, &p.x); return vec3f(r); }
+    vec3f worldToLocalNormal(const vec3f& p) override { dReal r[3]; oder::mul1_331(r, b.R, &p.x); return vec3f(r); }
+
+    void setPosition(const vec3f& pos) override { b.pos[0] = pos.x; b.pos[1] = pos.y; b.pos[2] = pos.z; }
+    vec3f getPosition(float) override { return vec3f(b.pos); }
+    void setRotation(const mat44f& m) override {
+        /* RigidBodyODE.cpp:143-156: r[0]=M11 r[1]=M21 r[2]=M31 / r[4]=M12 ... (ODE rows = mat44f columns) */
+        dReal R[9] = {m.M11, m.M21, m.M31, m.M12, m.M22, m.M32, m.M13, m.M23, m.M33};
+        oder::body_set_rotation(b, R);
+    }
+    mat44f getWorldMatrix(float) override {
+        mat44f m; const dReal* r = b.R;
+        m.M11 = r[0]; m.M12 = r[3]; m.M13 = r[6]; m.M14 = 0;
+        m.M21 = r[1]; m.M22 = r[4]; m.M23 = r[7]; m.M24 = 0;
+        m.M31 = r[2]; m.M32 = r[5]; m.M33 = r[8]; m.M34 = 0;
+        m.M41 = b.pos[0]; m.M42 = b.pos[1]; m.M43 = b.pos[2]; m.M44 = 1.0f;
+        return m;
+    }
+
+    void setVelocity(const vec3f& v) override { b.lvel[0] = v.x; b.lvel[1] = v.y; b.lvel[2] = v.z; }
+    vec3f getVelocity() override { dReal z[3] = {0, 0, 0}, r[3]; oder::body_rel_point_vel(b, z, r); return vec3f(r); }
+    vec3f getLocalVelocity() override { return worldToLocalNormal(getVelocity()); }
+    vec3f getPointVelocity(const vec3f& p) override { dReal r[3]; oder::body_point_vel(b, &p.x, r); return vec3f(r); }
+    vec3f getLocalPointVelocity(const vec3f& p) override { dReal r[3]; oder::body_rel_point_vel(b, &p.x, r); return vec3f(r); }
+
+    void setAngularVelocity(const vec3f& v) override { b.avel[0] = v.x; b.avel[1] = v.y; b.avel[2] = v.z; }
+    vec3f getAngularVelocity() override { return vec3f(b.avel); }
+    vec3f getLocalAngularVelocity() override { return worldToLocalNormal(getAngularVelocity()); }
+
+    void addForceAtPos(const vec3f& f, const vec3f& p) override { oder::body_add_force_at_pos(b, &f.x, &p.x); }
+    void addForceAtLocalPos(const vec3f& f, const vec3f& p) override { oder::body_add_force_at_rel_pos(b, &f.x, &p.x); }
+    void addLocalForce(const vec3f& f) override { dReal z[3] = {0, 0, 0}, fw[3]; oder::mul0_331(fw, b.R, &f.x); oder::body_add_force_at_rel_pos(b, fw, z); }
+    void addLocalForceAtPos(const vec3f& f, const vec3f& p) override { dReal fw[3]; oder::mul0_331(fw, b.R, &f.x); oder::body_add_force_at_pos(b, fw, &p.x); }
+    void addLocalForceAtLocalPos(const vec3f& f, const vec3f& p) override { dReal fw[3]; oder::mul0_331(fw, b.R, &f.x); oder::body_add_force_at_rel_pos(b, fw, &p.x); }
+    void addTorque(const vec3f& t) override { b.tacc[0] += t.x; b.tacc[1] += t.y; b.tacc[2] += t.z; }
+    void addLocalTorque(const vec3f& t) override { dReal tw[3]; oder::mul0_331(tw, b.R, &t.x); b.tacc[0] += tw[0]; b.tacc[1] += tw[1]; b.tacc[2] += tw[2]; }
+
+    void addBoxCollider(const vec3f&, const vec3f&, unsigned int, unsigned int, unsigned long) override {}
+    void addMeshCollider(ITriMeshPtr, const mat44f&, unsigned int, unsigned long, unsigned long) override {}
+};
+
+struct JointR : public IJoint {
+    oder::Joint j;
+    float distance = 0; /* DistanceJointODE::distance */
+    void setERPCFM(float erp, float cfm) override {
+        /* JointODE.cpp:59-75: only Slider and DBall override.  Slider forwards to dJointSetSliderParam
+           (dParamERP is not a limit-motor parameter; dParamCFM only feeds the absent limit/motor row)
+           -> no effect on the 5 slider rows.  DBall: dJointSetDBallParam honours both. */
+        if (j.type == oder::J_DBALL) { if (erp > 0.0f) j.erp = erp; if (cfm > 0.0f) j.cfm = cfm; }
+    }
+    void reseatDistanceJointLocal(const vec3f& p1, const vec3f& p2) override {
+        if (j.type != oder::J_DBALL) return;
+        /* JointODE.cpp:77-88: local -> world -> SetDBallAnchor (world -> local) -> SetDBallDistance */
+        dReal w1[3], w2[3];
+        oder::body_rel_point_pos(*j.b0, &p1.x, w1); oder::body_rel_point_pos(*j.b1, &p2.x, w2);
+        oder::joint_set_dball_anchor1(j, w1); oder::joint_set_dball_anchor2(j, w2);
+        j.targetDistance = distance;
+    }
+};
+
+struct RayCasterR : public IRayCaster {
+    RestateEngine* core; float length;
+    RayCasterR(RestateEngine* c, float l) : core(c), length(l) {}
+    RayCastHit rayCast(const vec3f& pos, const vec3f& dir) override;
+};
+
+struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<RestateEngine> {
+    oder::World world;
+    std::vector<std::shared_ptr<RigidBodyR>> bodies;
+    std::vector<std::shared_ptr<JointR>> joints;
+    std::vector<std::shared_ptr<CollisionMeshR>> staticMeshes;
+    ICollisionCallback* cb = nullptr;
+    unsigned long long rayCount = 0, rayTriTests = 0;
+
+    RestateEngine() {
+        /* PhysicsEngineODE.cpp:23-28 */
+        world.gravity[0] = 0; world.gravity[1] = -9.80665f; world.gravity[2] = 0;
+        world.erp = 0.3f; world.cfm = 1.0e-7f;
+    }
+    oder::Body* B(IRigidBodyPtr rb) { return &std::dynamic_pointer_cast<RigidBodyR>(rb)->b; }
+
+    IRigidBodyPtr createRigidBody() override {
+        auto p = std::make_shared<RigidBodyR>(this);
+        bodies.push_back(p); world.bodies.push_back(&p->b);
+        return p;
+    }
+    std::shared_ptr<JointR> mk(oder::JointType t, IRigidBodyPtr a, IRigidBodyPtr b) {
+        auto p = std::make_shared<JointR>();
+        p->j.type = t; p->j.b0 = B(a); p->j.b1 = B(b);
+        p->j.erp = world.erp; p->j.cfm = world.cfm;  /* joints copy the world defaults at creation */
+        joints.push_back(p); world.joints.push_back(&p->j);
+        return p;
+    }
+    IJointPtr createFixedJoint(IRigidBodyPtr a, IRigidBodyPtr b) override { auto p = mk(oder::J_FIXED, a, b); oder::joint_set_fixed(p->j); return p; }
+    IJointPtr createBallJoint(IRigidBodyPtr a, IRigidBodyPtr b, const vec3f& pos) override { auto p = mk(oder::J_BALL, a, b); oder::joint_set_ball_anchor(p->j, &pos.x); return p; }
+    IJointPtr createSliderJoint(IRigidBodyPtr a, IRigidBodyPtr b, const vec3f& axis) override { auto p = mk(oder::J_SLIDER, a, b); oder::joint_set_slider_axis(p->j, &axis.x); return p; }
+    IJointPtr createDistanceJoint(IRigidBodyPtr a, IRigidBodyPtr b, const vec3f& p1, const vec3f& p2) override {
+        auto p = mk(oder::J_DBALL, a, b);
+        oder::joint_set_dball_anchor1(p->j, &p1.x); oder::joint_set_dball_anchor2(p->j, &p2.x);
+        p->distance = p->j.targetDistance;
+        return p;
+    }
+    IJointPtr createBumpJoint(IRigidBodyPtr, IRigidBodyPtr, const vec3f&, float, float) override { return nullptr; }
+
+    ITriMeshPtr createTriMesh() override { return std::make_shared<TriMeshR>(); }
+    ICollisionObjectPtr createCollider(ITriMeshPtr tm, bool isDynamic, unsigned int, unsigned long category, unsigned long mask) override {
+        auto p = std::make_shared<CollisionMeshR>();
+        p->trimesh = tm; p->category = category; p->mask = mask; p->isDynamic = isDynamic;
+        for (int k = 0; k < 3; ++k) { p->bbMin[k] = FLT_MAX; p->bbMax[k] = -FLT_MAX; }
+        auto* vb = tm->getVB();
+        for (size_t i = 0; i < tm->getVertexCount(); ++i) {
+            const float* v = &vb[i].x;
+            for (int k = 0; k < 3; ++k) { p->bbMin[k] = std::min(p->bbMin[k], v[k]); p->bbMax[k] = std::max(p->bbMax[k], v[k]); }
+        }
+        if (!isDynamic) { p->buildGrid(); staticMeshes.push_back(p); }
+        return p;
+    }
+    IRayCasterPtr createRayCaster(float length) override { return std::make_shared<RayCasterR>(this, length); }
+    void setCollisionCallback(ICollisionCallback* c) override { cb = c; }
+
+    RayCastHit rayCastImpl(const vec3f& o, const vec3f& d, float length) {
+        RayCastHit hit;
+        float best = -1.0f; vec3f bestN; CollisionMeshR* bestMesh = nullptr;
+        float e[3] = {o.x + d.x * length, o.y + d.y * length, o.z + d.z * length};
+        float rmin[3] = {std::min(o.x, e[0]), std::min(o.y, e[1]), std::min(o.z, e[2])};
+        float rmax[3] = {std::max(o.x, e[0]), std::max(o.y, e[1]), std::max(o.z, e[2])};
+        ++rayCount;
+        for (auto& mp : staticMeshes) {
+            CollisionMeshR& m = *mp;
+            if (rmin[0] > m.bbMax[0] || rmax[0] < m.bbMin[0] || rmin[1] > m.bbMax[1] || rmax[1] < m.bbMin[1] || rmin[2] > m.bbMax[2] || rmax[2] < m.bbMin[2]) continue;
+            const TriMeshVertex* vb = m.trimesh->getVB(); const TriMeshIndex* ib = m.trimesh->getIB();
+            float meshBest = -1.0f; vec3f meshN;
+            const float sx = m.gnx / std::max(1e-6f, m.bbMax[0] - m.bbMin[0]), sz = m.gnz / std::max(1e-6f, m.bbMax[2] - m.bbMin[2]);
+            int ix0 = std::max(0, std::min(m.gnx - 1, (int)floorf((rmin[0] - m.bbMin[0]) * sx))), ix1 = std::max(0, std::min(m.gnx - 1, (int)floorf((rmax[0] - m.bbMin[0]) * sx)));
+            int iz0 = std::max(0, std::min(m.gnz - 1, (int)floorf((rmin[2] - m.bbMin[2]) * sz))), iz1 = std::max(0, std::min(m.gnz - 1, (int)floorf((rmax[2] - m.bbMin[2]) * sz)));
+            for (int iz = iz0; iz <= iz1; ++iz) for (int ix = ix0; ix <= ix1; ++ix)
+            for (uint32_t t : m.cells[(size_t)iz * m.gnx + ix]) {
+                const TriMeshVertex& v0 = vb[ib[t * 3]]; const TriMeshVertex& v1 = vb[ib[t * 3 + 1]]; const TriMeshVertex& v2 = vb[ib[t * 3 + 2]];
+                ++rayTriTests;
+                vec3f e1(v1.x - v0.x, v1.y - v0.y, v1.z - v0.z), e2(v2.x - v0.x, v2.y - v0.y, v2.z - v0.z);
+                vec3f pvec = d.cross(e2);
+                float det = e1 * pvec;
+                if (det < 0.000001f) continue;                 /* LOCAL_EPSILON, culling on */
+                vec3f tvec(o.x - v0.x, o.y - v0.y, o.z - v0.z);
+                float u = tvec * pvec;
+                if (u < 0.0f || u > det) continue;
+                vec3f qvec = tvec.cross(e1);
+                float v = d * qvec;
+                if (v < 0.0f || u + v > det) continue;
+                float dist = e2 * qvec;
+                if (dist < 0.0f) continue;
+                dist *= (1.0f / det);
+                if (!(dist < length)) continue;
+                if (meshBest < 0.0f || dist < meshBest) { meshBest = dist; meshN = e1.cross(e2); }
+            }
+            if (meshBest >= 0.0f && (best < 0.0f || best > meshBest)) { best = meshBest; bestN = meshN; bestMesh = &m; }
+        }
+        if (best >= 0.0f) {
+            hit.pos = vec3f(o.x + d.x * best, o.y + d.y * best, o.z + d.z * best);
+            hit.normal = bestN.get_norm();
+            hit.collisionObject = bestMesh;
+            hit.hasContact = true;
+        }
+        return hit;
+    }
+    RayCastHit rayCast(const vec3f& pos, const vec3f& dir, float length) override { return rayCastImpl(pos, dir, length); }
+    RayCastHit rayCast(const vec3f& pos, const vec3f& dir, IRayCasterPtr ray) override {
+        return rayCastImpl(pos, dir, std::dynamic_pointer_cast<RayCasterR>(ray)->length);
+    }
+
+    void step(float dt) override {
+        /* collisionStep (PhysicsEngineODE.cpp:228-244) not restated: see header */
+        oder::world_step(world, dt);
+    }
+};
+
+RayCastHit RayCasterR::rayCast(const vec3f& pos, const vec3f& dir) { return core->rayCastImpl(pos, dir, length); }
+
+std::shared_ptr<IPhysicsEngine> PhysicsFactory::createPhysicsEngine() { return std::make_shared<RestateEngine>(); }
+
+/* harness access (ref_harness.cpp) */
+oder::World* pdref_world(IPhysicsEngine* e) { return &static_cast<RestateEngine*>(e)->world; }
+oder::Body* pdref_body(IRigidBody* rb) { return &static_cast<RigidBodyR*>(rb)->b; }
+oder::Joint* pdref_joint(IJoint* j) { return &static_cast<JointR*>(j)->j; }
+void pdref_ray_stats(IPhysicsEngine* e, unsigned long long* rays, unsigned long long* tris) {
+    auto* r = static_cast<RestateEngine*>(e); *rays = r->rayCount; *tris = r->rayTriTests;
+}
+
+}
