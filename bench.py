@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- car-ticks/sec of the batched Car::step hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path, one process per GPU (torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation on host cores
+
+Workload: N=1 -> BASELINE.json configs[1]: 4096 demo-car envs (ks_toyota_ae86_drift on driftplayground) on one
+B200, randomised synthetic controls resampled every 33 ticks, env-style auto-reset.  N>1 -> configs[2]:
+65536 envs per GPU, sharded by global env id, replicated track BVH, no per-tick collective (weak scaling).
+A "step" is 33 physics ticks (1/333 s each) of every env = one control period.
+
+Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = through the public
+API with host buffers (pinned H2D of actions and D2H of obs/reward/done every tick, as a user of the env does),
+roofline for the dominant kernel (k_tick), cpu_baseline = the oracle timed on this box's host cores.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DT = 1.0 / 333.0
+TICKS_PER_STEP = 33
+METRIC = "car_ticks_per_sec"
+UNIT = "car-ticks/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.idx = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                parts = [x.strip() for x in out.split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(float(parts[0])); self.max_mhz = float(parts[1])
+                    for n, v in zip(names, parts[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set(); self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (reference Car/Sim/Core sources + restated ODE) on host cores
+# ----------------------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """One process = one host core: `sims` reference simulators stepped `ticks` ticks with the bench workload."""
+    wid, sims, ticks, seed = args
+    import numpy as np
+    import pdref
+    rng = np.random.default_rng(seed + wid)
+    S = [pdref.RefSim() for _ in range(sims)]
+    for k, s in enumerate(S):
+        s.teleport_spline(float(rng.uniform(0, 1)))
+    lay = pdref.Layout()
+    o_col = lay.fields["car.collisionFlag"][0]; o_off = lay.fields["car.outOfTrackFlag"][0]
+    t0 = time.perf_counter()
+    for t in range(ticks):
+        if t % TICKS_PER_STEP == 0:
+            acts = rng.uniform(-1, 1, (sims, 2))
+        for k, s in enumerate(S):
+            s.set_controls(steer=float(acts[k, 0]), gas=float(0.1 + 0.9 * (acts[k, 1] + 1) * 0.5))
+            s.step(DT)
+            if t % 8 == 7:  # env-style auto reset (checked sparsely: get_state is harness overhead, not path work)
+                rec = s.state()
+                if rec[o_col] or rec[o_off]:
+                    s.teleport_spline(float(rng.uniform(0, 1)))
+    return sims * ticks, time.perf_counter() - t0
+
+
+def run_reference_cpu(total_sims, ticks, cores):
+    import multiprocessing as mp
+    per = max(1, total_sims // cores)
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, [(w, per, ticks, 1234) for w in range(cores)])
+        wall = time.perf_counter() - t0
+    units = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return units, slowest, wall
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import pdref
+    if not pdref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
+        return
+    cores = os.cpu_count() or 1
+    sims_per_core = 2
+    # warm-up + K steps, each step = 33 ticks of (cores * sims_per_core) reference simulators
+    times = []
+    units = 0
+    for s in range(args.warmup + args.steps):
+        u, slow, wall = run_reference_cpu(cores * sims_per_core, TICKS_PER_STEP * 4, cores)
+        if s >= args.warmup:
+            times.append(slow); units += u
+    total = sum(times)
+    value = units / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] sample: demo car on driftplayground, random controls resampled every 33 ticks, env auto-reset; "
+                               "each step = %d ticks of %d reference simulators (one process per host core)" % (TICKS_PER_STEP * 4, cores * sims_per_core)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "%d sims x %d ticks per step, %d steps; reference Car/Sim/Core sources (g++ -O2) + restated ODE 0.16.3 back-end" % (cores * sims_per_core, TICKS_PER_STEP * 4, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def ours(args):
+    import numpy as np
+    import torch
+    import pdref
+    from projectd_core_b200 import Batch
+    from parity_util import make_env_like
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local if world > 1 else 0)
+    n_envs = args.envs if args.envs else (4096 if world == 1 else 65536)
+    K, W = args.steps, args.warmup
+
+    b = make_env_like(Batch(pdref.BASE_PATH, n_envs=n_envs, device=dev.index))
+    b.set_seed(1234, rank * n_envs)          # RNG keyed by global env id: results do not depend on the sharding
+    b.L.pd_set_tune  # noqa
+    b.teleport_mode(2)                        # random start positions u ~ U[0,1)
+    stream = torch.cuda.ExternalStream(b.stream(), device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(99 + rank)
+    # synthetic controls for every step, resident in HBM before the timed region
+    acts = (torch.rand((W + K, n_envs, 2), device=dev, generator=gen) * 2 - 1).contiguous()
+    rew = torch.zeros(n_envs, device=dev); done = torch.zeros(n_envs, device=dev, dtype=torch.int32)
+    obs = b.obs_tensor()
+    torch.cuda.synchronize()
+
+    def run_steps(lo, hi):
+        for s in range(lo, hi):
+            a = acts[s]
+            for _ in range(TICKS_PER_STEP):
+                b.env_step(a, DT, None, rew, done)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    run_steps(0, W)
+    barrier()
+    l0 = b.launch_count()
+    sampler = ClockSampler(dev.index); sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        run_steps(W, W + K)
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = b.launch_count() - l0
+    if dist is not None:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ticks = K * TICKS_PER_STEP
+    value = world * n_envs * ticks / (ms * 1e-3)
+
+    # ---- dominant kernel (k_tick) alone: CUDA events on the batch's stream around pure tick launches ----
+    with torch.cuda.stream(stream):
+        b.step(DT, 8)
+        k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+        k0.record(stream); b.step(DT, 64); k1.record(stream)
+    torch.cuda.synchronize()
+    tick_ms = k0.elapsed_time(k1) / 64.0
+    words = b.words
+    alg_bytes = n_envs * (2 * words * 4 + 8 + 96 + 8)      # state read + written once, controls in, obs + reward/flags out
+    peak, peak_kind = _peaks()
+    achieved = alg_bytes / (tick_ms * 1e-3) / 1e9
+    # issue-side view (not tensor work): audited ~50 kflop per car-tick against 74 TFLOP/s fp32
+    flop_frac = (n_envs / (tick_ms * 1e-3)) * 50e3 / 74e12
+
+    # ---- end to end through the public API with host buffers ----
+    h_act = torch.empty((n_envs, 2), dtype=torch.float32).pin_memory()
+    h_obs = torch.empty((n_envs, 24), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(n_envs, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(n_envs, dtype=torch.int32).pin_memory()
+    d_act = torch.empty((n_envs, 2), device=dev)
+    acts_host = acts[W:W + min(K, 8)].cpu()
+    e2e_steps = min(K, 8)
+
+    def e2e_tick(a_host):
+        h_act.copy_(a_host)
+        with torch.cuda.stream(stream):
+            d_act.copy_(h_act, non_blocking=True)
+            b.env_step(d_act, DT, None, rew, done)
+            h_obs.copy_(obs, non_blocking=True); h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)
+        stream.synchronize()
+        return float(h_rew[0])
+
+    for _ in range(3):
+        e2e_tick(acts_host[0])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        for _ in range(TICKS_PER_STEP):
+            e2e_tick(acts_host[s])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e_value = world * n_envs * e2e_steps * TICKS_PER_STEP / e2e_s
+
+    # ---- episode statistics: the only collective of the path (once per rollout, never per tick) ----
+    stats = torch.from_numpy(b.env_stats(reset=False)).to(dev)
+    if dist is not None:
+        dist.all_reduce(stats)
+    stats = stats.cpu().tolist()
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and pdref.available():
+        cores = os.cpu_count() or 1
+        units, slow, wall = run_reference_cpu(cores * 2, 999, cores)
+        cpu = {"value": units / slow, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": "%d reference simulators x 999 ticks, one process per core (reference Car/Sim/Core sources, g++ -O2, + restated ODE back-end)" % (cores * 2)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": ("configs[1]: 4096 demo-car envs on 1 B200" if (world == 1 and n_envs == 4096) else "%d demo-car envs per GPU (configs[2] uses 65536)" % n_envs)
+                       + ", ks_toyota_ae86_drift on driftplayground, random controls resampled every 33 ticks, env auto-reset",
+                       "envs_per_gpu": n_envs, "ticks_per_step": TICKS_PER_STEP, "dt": DT,
+                       "l2": "state %.0f MB per tick + inputs regenerated per step; 4096-env state (%.1f MB) is L2-resident by design, see DESIGN.md" % (n_envs * words * 4 / 1e6, n_envs * words * 4 / 1e6),
+                       "parallelism": "env-sharded x%d, no per-tick collective" % world},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TICKS_PER_STEP * n_envs * 8, "d2h_bytes_per_step": TICKS_PER_STEP * n_envs * (96 + 4 + 4),
+                    "note": "per tick: pinned H2D actions, pd_env_step, D2H obs+reward+done, stream sync"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_tick", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_kind, "algorithmic_bytes_per_car_tick": alg_bytes / n_envs, "kernel_ms": tick_ms,
+                         "fp32_issue_frac_of_74TFLOPs_at_50kflop_per_car_tick": flop_frac},
+            "cpu_baseline": cpu,
+            "episode_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None, "mean_length": (stats[2] / stats[0]) if stats[0] else None,
+                              "collisions": stats[3], "offtrack": stats[4], "stuck": stats[5], "lowreward": stats[6], "nan": stats[7]},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: 4096 at N=1, 65536 at N>1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

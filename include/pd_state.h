@@ -36,12 +36,16 @@
 #define PD_LOOKAHEAD    5   /* CarState::MaxLookAhead Car/CarState.h:51 */
 #define PD_OBS_DIM      24  /* pyprojectd/projectd_env.py:237-275 */
 
-/* ---- rigid body: dxBody pos/q/lvel/avel (ODE 0.16.3 objects; RigidBodyODE.cpp:131-231) ---- */
+/* ---- rigid body: dxBody pos/q/R/lvel/avel (ODE 0.16.3 objects; RigidBodyODE.cpp:131-231).
+ *      R is kept beside q exactly as ODE keeps both: after dBodySetRotation (teleports) R is the
+ *      orthogonalised input while q comes from the raw input, and they only re-synchronise at the next
+ *      dxStepBody.  (axx,axy,axz) = body x axis in world = mat44f row 1 = first COLUMN of ODE's R. ---- */
 #define PD_BODY_FIELDS(X) \
     X(F, px) X(F, py) X(F, pz) \
     X(F, qw) X(F, qx) X(F, qy) X(F, qz) \
     X(F, vx) X(F, vy) X(F, vz) \
-    X(F, wx) X(F, wy) X(F, wz)
+    X(F, wx) X(F, wy) X(F, wz) \
+    X(F, axx) X(F, axy) X(F, axz) X(F, ayx) X(F, ayy) X(F, ayz) X(F, azx) X(F, azy) X(F, azz)
 
 /* ---- tyre: TyreStatus (Car/TyreStatus.h:5-45) + Tyre runtime members (Car/Tyre.h:88-106) ---- */
 #define PD_TYRE_FIELDS(X) \
@@ -97,7 +101,9 @@
     X(I, driftComboCounter) X(F, stepReward) X(F, totalReward) X(F, prevEpisodeReward) \
     X(I, oldPointId) X(I, oldSplinePointId) \
     /* batched-env bookkeeping (no reference counterpart: episode statistics, NaN guard) */ \
-    X(I, episodeSteps) X(I, nanFlag)
+    X(I, episodeSteps) X(I, nanFlag) \
+    /* TyreThermalPatch::inputT starts at ambient (TyreThermalModel.cpp:40) and is zero after the first step */ \
+    X(I, thermalPrimed)
 
 /* ---------------------------------------------------------------------------------------- */
 #define PD__W_F 1

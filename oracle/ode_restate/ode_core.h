@@ -151,8 +151,19 @@ inline void body_set_mass_box(Body& b, dReal m, dReal lx, dReal ly, dReal lz) { 
     b.I[1] = m / 12.0f * (lx * lx + lz * lz);
     b.I[2] = m / 12.0f * (lx * lx + ly * ly);
 }
-inline void body_set_rotation(Body& b, const dReal* R) { /* ode.cpp dBodySetRotation */
+/* rotation.cpp dxOrthogonalizeR: Gram-Schmidt on the ROWS of R, third row = row0 x row1 */
+inline void orthogonalize_R(dReal* m) {
+    dReal n0 = dot3(m, m);
+    if (n0 != 1.0f) normalize3(m);
+    dReal proj = dot3(m, m + 3);
+    if (proj != 0) { m[3] -= proj * m[0]; m[4] -= proj * m[1]; m[5] -= proj * m[2]; }
+    dReal n1 = dot3(m + 3, m + 3);
+    if (n1 != 1.0f) normalize3(m + 3);
+    cross3(m + 6, m, m + 3);
+}
+inline void body_set_rotation(Body& b, const dReal* R) { /* ode.cpp dBodySetRotation: R orthogonalised, q from the raw input */
     memcpy(b.R, R, sizeof(dReal) * 9);
+    orthogonalize_R(b.R);
     R_to_q(R, b.q); normalize4(b.q);
 }
 inline void body_rel_point_pos(const Body& b, const dReal* p, dReal* r) { /* dBodyGetRelPointPos */

@@ -143,6 +143,10 @@ void pdref_get_state(void* hv, uint32_t* r) {
         putF(r, o + PD_BODY_o_qw, ob->q[0]); putF(r, o + PD_BODY_o_qx, ob->q[1]); putF(r, o + PD_BODY_o_qy, ob->q[2]); putF(r, o + PD_BODY_o_qz, ob->q[3]);
         putF(r, o + PD_BODY_o_vx, ob->lvel[0]); putF(r, o + PD_BODY_o_vy, ob->lvel[1]); putF(r, o + PD_BODY_o_vz, ob->lvel[2]);
         putF(r, o + PD_BODY_o_wx, ob->avel[0]); putF(r, o + PD_BODY_o_wy, ob->avel[1]); putF(r, o + PD_BODY_o_wz, ob->avel[2]);
+        /* axes = columns of ODE's row-major R */
+        putF(r, o + PD_BODY_o_axx, ob->R[0]); putF(r, o + PD_BODY_o_axy, ob->R[3]); putF(r, o + PD_BODY_o_axz, ob->R[6]);
+        putF(r, o + PD_BODY_o_ayx, ob->R[1]); putF(r, o + PD_BODY_o_ayy, ob->R[4]); putF(r, o + PD_BODY_o_ayz, ob->R[7]);
+        putF(r, o + PD_BODY_o_azx, ob->R[2]); putF(r, o + PD_BODY_o_azy, ob->R[5]); putF(r, o + PD_BODY_o_azz, ob->R[8]);
     }
     for (int w = 0; w < 4; ++w) {
         Tyre* t = c->tyres[w].get(); const TyreStatus& s = t->status; int o = PD_OFF_TYRE(w);
@@ -215,6 +219,8 @@ void pdref_get_state(void* hv, uint32_t* r) {
         CF(driftStraightTimer, sc->driftStraightTimer); CF(instantDriftDelta, sc->instantDriftDelta); CF(instantDrift, sc->instantDrift); CF(driftPoints, sc->driftPoints);
         CI(driftComboCounter, sc->driftComboCounter); CF(stepReward, sc->stepReward); CF(totalReward, sc->totalReward); CF(prevEpisodeReward, sc->prevEpisodeReward);
         CI(oldPointId, sc->oldPointId); CI(oldSplinePointId, sc->oldSplinePointId);
+        CI(episodeSteps, 0); CI(nanFlag, 0);
+        CI(thermalPrimed, c->tyres[0]->thermalModel->patches[5].inputT == 0.0f ? 1 : 0);
         for (size_t i = 0; i < c->probeHits.size() && i < PD_MAX_PROBES; ++i) putF(r, PD_OFF_PROBES + (int)i, c->probeHits[i]);
         for (size_t i = 0; i < c->lookAhead.size() && i < PD_LOOKAHEAD; ++i) putF(r, PD_OFF_LOOKAHEAD + (int)i, c->lookAhead[i]);
 #undef CF
@@ -230,7 +236,9 @@ void pdref_set_state(void* hv, const uint32_t* r) {
         oder::Body* ob = body_of(h, b); int o = PD_OFF_BODY(b);
         for (int k = 0; k < 3; ++k) ob->pos[k] = getF(r, o + PD_BODY_o_px + k);
         for (int k = 0; k < 4; ++k) ob->q[k] = getF(r, o + PD_BODY_o_qw + k);
-        oder::q_to_R(ob->q, ob->R);
+        ob->R[0] = getF(r, o + PD_BODY_o_axx); ob->R[3] = getF(r, o + PD_BODY_o_axy); ob->R[6] = getF(r, o + PD_BODY_o_axz);
+        ob->R[1] = getF(r, o + PD_BODY_o_ayx); ob->R[4] = getF(r, o + PD_BODY_o_ayy); ob->R[7] = getF(r, o + PD_BODY_o_ayz);
+        ob->R[2] = getF(r, o + PD_BODY_o_azx); ob->R[5] = getF(r, o + PD_BODY_o_azy); ob->R[8] = getF(r, o + PD_BODY_o_azz);
         for (int k = 0; k < 3; ++k) { ob->lvel[k] = getF(r, o + PD_BODY_o_vx + k); ob->avel[k] = getF(r, o + PD_BODY_o_wx + k); ob->facc[k] = 0; ob->tacc[k] = 0; }
     }
     for (int w = 0; w < 4; ++w) {
@@ -254,7 +262,7 @@ void pdref_set_state(void* hv, const uint32_t* r) {
         t->thermalModel->coreTemp = TF(coreTemp); t->thermalModel->phase = TD(phase);
         t->thermalModel->practicalTemp = TF(practicalTemp); t->thermalModel->thermalMultD = TF(thermalMultD);
         t->thermalModel->coreTInput = 0;
-        for (int p = 0; p < PD_THERMAL_PATCHES; ++p) { t->thermalModel->patches[p].T = getF(r, PD_OFF_TYRE_PATCH(w) + p); t->thermalModel->patches[p].inputT = 0; }
+        for (int p = 0; p < PD_THERMAL_PATCHES; ++p) { t->thermalModel->patches[p].T = getF(r, PD_OFF_TYRE_PATCH(w) + p); t->thermalModel->patches[p].inputT = getI(r, PD_OFF_CAR + PD_CAR_o_thermalPrimed) ? 0.0f : h->sim->ambientTemperature; }
 #undef TF
 #undef TI
 #undef TD
@@ -371,7 +379,7 @@ void pdref_get_params(void* hv, PdCarParams* P) {
         d.internalCoreTransfer = th->patchData.internalCoreTransfer; d.coolFactorGain = th->patchData.coolFactorGain; d.camberSpreadK = th->camberSpreadK;
         copy_curve(d.performanceCurve, th->performanceCurve);
         d.flatSpotK = t->flatSpotK; d.explosionTemperature = t->explosionTemperature; d.pressureTemperatureGain = t->pressureTemperatureGain;
-        d.pressureStaticDefault = t->compoundDefs[t->currentCompoundIndex]->pressureStatic;
+        d.pressureStaticDefault = t->status.pressureStatic;   /* compound value, possibly re-tuned (SetupManager PRESSURE_xx) */
         d.driven = t->driven ? 1 : 0; d.useLoadForVKM = t->useLoadForVKM ? 1 : 0;
     }
     P->nWings = (int)c->aeroMap->wings.size();

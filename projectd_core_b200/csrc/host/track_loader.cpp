@@ -1,0 +1,265 @@
+/*
+ * track_loader.cpp -- track assets -> GPU-ready arrays.
+ *
+ * surfaces.bin (Sim/Track.cpp:97-149, header Sim/Surface.h:26-45), spline.bin / spline.cache
+ * (Sim/Track.h:13-25, Track.cpp:274-311), cfg/sim.ini [ENVIRONMENT] TRACK_GRIP / [VERTEX_HASH]
+ * (Track.cpp:38-42,217-224), spline.ini CLOSED_LOOP (Track.cpp:155-158), the derived spline data of
+ * Track::initTrackPoints (Track.cpp:178-272) and BSpline3d::init_from_array (Core/Spline3d.cpp:79-162).
+ *
+ * All static meshes (track + wall blobs) go into ONE bounding-volume hierarchy: the reference walks a
+ * dSimpleSpace of 510 geoms per ray (PhysicsEngineODE.cpp:175-176) and keeps the minimum depth, which is
+ * the closest hit over the union of the meshes.
+ */
+#include "pd_host.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace pdh {
+
+#pragma pack(push, 1)
+struct BlobSurfaceHdr {
+    uint32_t magic, numVertices, numIndices, sectorID, collisionCategory;
+    float gripMod, damping, sinHeight, sinLength, granularity, dirtAdditiveK, vibrationGain, vibrationLength, wavPitchSpeed;
+    uint8_t isValidTrack, isPitlane;
+};
+#pragma pack(pop)
+static_assert(sizeof(BlobSurfaceHdr) == 58, "BlobSurface header is 58 bytes packed");
+
+struct V3h { float x, y, z; };
+static inline V3h sub(V3h a, V3h b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline V3h add(V3h a, V3h b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline V3h mulf(V3h a, float f) { return {a.x * f, a.y * f, a.z * f}; }
+static inline V3h divf(V3h a, float f) { return {a.x / f, a.y / f, a.z / f}; }
+static inline float lenh(V3h a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+
+/* ---------------- BVH: top-down, median split on the longest centroid axis, <= 4 triangles per leaf ---------------- */
+namespace {
+struct Builder {
+    const std::vector<float>& v9; const std::vector<int32_t>& surf;
+    std::vector<uint32_t> order; std::vector<float> cx, cy, cz;
+    std::vector<float> tmin, tmax;       /* per-triangle bounds */
+    std::vector<BvhNodeH> nodes;
+    Builder(const std::vector<float>& v, const std::vector<int32_t>& s) : v9(v), surf(s) {}
+    void bounds(uint32_t lo, uint32_t hi, float* mn, float* mx) {
+        for (int k = 0; k < 3; ++k) { mn[k] = 3.4e38f; mx[k] = -3.4e38f; }
+        for (uint32_t i = lo; i < hi; ++i) { uint32_t t = order[i]; for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], tmin[t * 3 + k]); mx[k] = std::max(mx[k], tmax[t * 3 + k]); } }
+    }
+    void build(int nodeIdx, uint32_t lo, uint32_t hi) {
+        float mn[3], mx[3]; bounds(lo, hi, mn, mx);
+        for (int k = 0; k < 3; ++k) {   /* conservative padding: the box test is only a filter */
+            float pad = 1e-4f * std::max(1.0f, std::max(fabsf(mn[k]), fabsf(mx[k])));
+            nodes[nodeIdx].bmin[k] = mn[k] - pad; nodes[nodeIdx].bmax[k] = mx[k] + pad;
+        }
+        const uint32_t n = hi - lo;
+        if (n <= 4) { nodes[nodeIdx].left = (int32_t)lo; nodes[nodeIdx].count = (int32_t)n; return; }
+        float cmn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, cmx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        for (uint32_t i = lo; i < hi; ++i) { uint32_t t = order[i]; float c[3] = {cx[t], cy[t], cz[t]}; for (int k = 0; k < 3; ++k) { cmn[k] = std::min(cmn[k], c[k]); cmx[k] = std::max(cmx[k], c[k]); } }
+        int axis = 0; float ext = cmx[0] - cmn[0];
+        if (cmx[1] - cmn[1] > ext) { axis = 1; ext = cmx[1] - cmn[1]; }
+        if (cmx[2] - cmn[2] > ext) { axis = 2; ext = cmx[2] - cmn[2]; }
+        const std::vector<float>& c = axis == 0 ? cx : axis == 1 ? cy : cz;
+        const uint32_t mid = lo + n / 2;
+        std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](uint32_t a, uint32_t b) { return c[a] < c[b]; });
+        const int left = (int)nodes.size();
+        nodes.push_back(BvhNodeH{}); nodes.push_back(BvhNodeH{});
+        nodes[nodeIdx].left = left; nodes[nodeIdx].count = 0;
+        build(left, lo, mid); build(left + 1, mid, hi);
+    }
+};
+}
+
+void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& surf, TrackModel& out) {
+    const uint32_t nt = (uint32_t)surf.size();
+    Builder B(verts9, surf);
+    B.order.resize(nt); std::iota(B.order.begin(), B.order.end(), 0u);
+    B.cx.resize(nt); B.cy.resize(nt); B.cz.resize(nt); B.tmin.resize(nt * 3); B.tmax.resize(nt * 3);
+    for (uint32_t t = 0; t < nt; ++t) {
+        const float* p = &verts9[(size_t)t * 9];
+        for (int k = 0; k < 3; ++k) {
+            float a = p[k], b = p[3 + k], c = p[6 + k];
+            B.tmin[t * 3 + k] = std::min(a, std::min(b, c)); B.tmax[t * 3 + k] = std::max(a, std::max(b, c));
+        }
+        B.cx[t] = (p[0] + p[3] + p[6]) / 3.0f; B.cy[t] = (p[1] + p[4] + p[7]) / 3.0f; B.cz[t] = (p[2] + p[5] + p[8]) / 3.0f;
+    }
+    B.nodes.reserve(nt); B.nodes.push_back(BvhNodeH{});
+    if (nt > 0) B.build(0, 0, nt);
+    out.nodes = B.nodes;
+    out.tris.resize((size_t)nt * 9); out.triSurf.resize(nt);
+    for (uint32_t i = 0; i < nt; ++i) {
+        const uint32_t t = B.order[i]; const float* p = &verts9[(size_t)t * 9]; float* q = &out.tris[(size_t)i * 9];
+        q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+        q[3] = p[3] - p[0]; q[4] = p[4] - p[1]; q[5] = p[5] - p[2];     /* e1 = v1 - v0 */
+        q[6] = p[6] - p[0]; q[7] = p[7] - p[1]; q[8] = p[8] - p[2];     /* e2 = v2 - v0 */
+        out.triSurf[i] = surf[t];
+    }
+    out.info.nTris = (int32_t)nt; out.info.nNodes = (int32_t)out.nodes.size();
+}
+
+/* BSpline3d::interpolate (Core/Spline3d.cpp:151-160), same operation order */
+static V3h bspline(float u, V3h P0, V3h P1, V3h P2, V3h P3) {
+    V3h point;
+    point = divf(mulf(add(sub(add(mulf(P0, -1.0f), mulf(P1, 3.0f)), mulf(P2, 3.0f)), P3), u * u * u), 6.0f);
+    point = add(point, divf(mulf(add(sub(mulf(P0, 3.0f), mulf(P1, 6.0f)), mulf(P2, 3.0f)), u * u), 6.0f));
+    point = add(point, divf(mulf(add(mulf(P0, -3.0f), mulf(P2, 3.0f)), u), 6.0f));
+    point = add(point, divf(add(add(P0, mulf(P1, 4.0f)), P2), 6.0f));
+    return point;
+}
+
+/* Track::initTrackPoints tail (Track.cpp:207-271) + BSpline3d::init_from_array */
+void finish_track_points(TrackModel& out, bool closedLoop, float cellSize) {
+    const int n = (int)out.fat.size();
+    out.info.nFatPoints = n; out.info.closedLoop = closedLoop ? 1 : 0; out.info.hashCellSize = cellSize;
+    float width = 0.1f, length = 0.1f;
+    out.fatDist.assign(n, 0.0f);
+    std::vector<V3h> pts(n);
+    for (int id = 0; id < n; ++id) {
+        const PdFatPoint& f = out.fat[id];
+        pts[id] = {f.best[0], f.best[1], f.best[2]};
+        const float w = lenh(sub({f.left[0], f.left[1], f.left[2]}, {f.right[0], f.right[1], f.right[2]}));
+        if (width < w) width = w;
+        out.fatDist[id] = length;
+        if (id + 1 < n) { const PdFatPoint& g = out.fat[id + 1]; length += lenh(sub(pts[id], {g.best[0], g.best[1], g.best[2]})); }
+    }
+    out.info.computedTrackWidth = width; out.info.computedTrackLength = length;
+    out.splineXYZ.clear(); out.splineDist.clear();
+    if (n < 4) { out.info.nSplineNodes = 0; out.info.interpolateStep = 0; return; }
+    const int steps = (int)(length / 0.1f) / n;
+    out.info.interpolateStep = steps;
+    std::vector<V3h> nodes;
+    auto add_node = [&](V3h p) {
+        nodes.push_back(p);
+        if (nodes.size() == 1) out.splineDist.push_back(0.0f);
+        else { const size_t k = nodes.size() - 1; out.splineDist.push_back(lenh(sub(nodes[k], nodes[k - 1])) + out.splineDist[k - 1]); }
+    };
+    auto wrap = [&](int id) { return id < n ? id : id - n; };
+    if (!closedLoop) {
+        const float d0 = lenh(sub(pts[1], pts[0])); const V3h n0 = divf(sub(pts[1], pts[0]), d0);
+        for (int i = 0; i < steps; ++i) { float u = (float)i / (float)steps; add_node(add(pts[0], mulf(n0, u * d0))); }
+    }
+    for (int pt = 0; pt + 4 < n; ++pt)
+        for (int i = 0; i < steps; ++i) { float u = (float)i / (float)steps; add_node(bspline(u, pts[pt], pts[pt + 1], pts[pt + 2], pts[pt + 3])); }
+    if (closedLoop) {
+        for (int pt = n - 4; pt < n; ++pt)
+            for (int i = 0; i < steps; ++i) { float u = (float)i / (float)steps; add_node(bspline(u, pts[pt], pts[wrap(pt + 1)], pts[wrap(pt + 2)], pts[wrap(pt + 3)])); }
+    } else {
+        for (int pt = n - 3; pt + 1 < n; ++pt) {
+            const float dx = lenh(sub(pts[pt + 1], pts[pt])); const V3h nx = divf(sub(pts[pt + 1], pts[pt]), dx);
+            for (int i = 0; i < steps; ++i) { float u = (float)i / (float)steps; add_node(add(pts[pt], mulf(nx, u * dx))); }
+        }
+        add_node(pts[n - 1]);
+    }
+    out.splineXYZ.resize(nodes.size() * 3);
+    for (size_t i = 0; i < nodes.size(); ++i) { out.splineXYZ[i * 3] = nodes[i].x; out.splineXYZ[i * 3 + 1] = nodes[i].y; out.splineXYZ[i * 3 + 2] = nodes[i].z; }
+    out.info.nSplineNodes = (int32_t)nodes.size();
+    out.info.computedTrackLength = out.splineDist.empty() ? length : out.splineDist.back();
+}
+
+static std::vector<uint8_t> read_file(const std::string& path) {
+    std::vector<uint8_t> buf;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return buf;
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    buf.resize((size_t)n);
+    if (n > 0 && fread(buf.data(), 1, (size_t)n, f) != (size_t)n) buf.clear();
+    fclose(f);
+    return buf;
+}
+
+void load_track(const std::string& basePathIn, const std::string& name, TrackModel& out) {
+    std::string basePath = basePathIn;
+    if (!basePath.empty() && basePath.back() != '/') basePath += "/";
+    const std::string folder = basePath + "content/tracks/" + name + "/";
+    out = TrackModel(); memset(&out.info, 0, sizeof(out.info));
+    out.info.dynamicGripLevel = 1.0f;
+    float cellSize = 50.0f;
+    {
+        Ini sim(basePath + "cfg/sim.ini");
+        if (sim.ready) { sim.tryGetFloat("ENVIRONMENT", "TRACK_GRIP", out.info.dynamicGripLevel); sim.tryGetFloat("VERTEX_HASH", "CELL_SIZE", cellSize); }
+    }
+    /* surfaces.bin */
+    const std::vector<uint8_t> blob = read_file(folder + "surfaces.bin");
+    if (blob.empty()) throw Error("cannot read " + folder + "surfaces.bin");
+    std::vector<float> verts9; std::vector<int32_t> surf;
+    size_t pos = 0;
+    while (pos + sizeof(BlobSurfaceHdr) <= blob.size()) {
+        BlobSurfaceHdr h; memcpy(&h, &blob[pos], sizeof(h)); pos += sizeof(h);
+        if (h.magic != 0xAABBCCDD) throw Error("surfaces.bin: bad magic");
+        if (!(h.numVertices > 0 && h.numIndices > 0)) throw Error("surfaces.bin: empty blob");
+        const size_t vb = (size_t)h.numVertices * 12, ib = (size_t)h.numIndices * 2;
+        if (pos + vb + ib > blob.size()) throw Error("surfaces.bin: truncated");
+        const float* v = (const float*)&blob[pos]; const uint16_t* idx = (const uint16_t*)&blob[pos + vb];
+        PdSurface s; memset(&s, 0, sizeof(s));
+        s.gripMod = h.gripMod; s.damping = h.damping; s.sinHeight = h.sinHeight; s.sinLength = h.sinLength; s.granularity = h.granularity;
+        s.dirtAdditiveK = h.dirtAdditiveK; s.collisionCategory = h.collisionCategory; s.sectorID = h.sectorID; s.isValidTrack = h.isValidTrack; s.isPitlane = h.isPitlane;
+        const int32_t sid = (int32_t)out.surfaces.size();
+        out.surfaces.push_back(s);
+        std::vector<float> vcopy(v, v + (size_t)h.numVertices * 3);   /* unaligned-safe copy */
+        for (uint32_t t = 0; t + 2 < h.numIndices; t += 3) {
+            for (int k = 0; k < 3; ++k) { uint16_t vi; memcpy(&vi, (const uint8_t*)idx + (size_t)(t + k) * 2, 2); verts9.push_back(vcopy[(size_t)vi * 3]); verts9.push_back(vcopy[(size_t)vi * 3 + 1]); verts9.push_back(vcopy[(size_t)vi * 3 + 2]); }
+            surf.push_back(sid);
+        }
+        pos += vb + ib;
+    }
+    out.info.nSurfaces = (int32_t)out.surfaces.size();
+    build_bvh(verts9, surf, out);
+    /* spline */
+    bool closedLoop = false;
+    { Ini sp(folder + "spline.ini"); if (sp.ready) closedLoop = sp.getInt("SPLINE", "CLOSED_LOOP") != 0; }
+    const std::vector<uint8_t> slim = read_file(folder + "spline.bin");
+    const std::vector<uint8_t> fat = read_file(folder + "spline.cache");
+    const size_t nSlim = slim.size() / 20, nFat = fat.size() / sizeof(PdFatPoint);
+    if (nFat == 0 || nFat != nSlim)
+        throw Error("track '" + name + "': spline.cache missing or stale (regenerating it -- Track::computeFatPoints -- is not part of the hot path yet)");
+    out.fat.resize(nFat); memcpy(out.fat.data(), fat.data(), nFat * sizeof(PdFatPoint));
+    finish_track_points(out, closedLoop, cellSize);
+}
+
+/* Config 4: synthetic closed circuit, flat road strip + verges, tessellated to about `targetTris` triangles. */
+void make_synthetic_track(int targetTris, float lengthMeters, TrackModel& out) {
+    out = TrackModel(); memset(&out.info, 0, sizeof(out.info));
+    out.info.dynamicGripLevel = 0.98f;
+    const float R = lengthMeters / (2.0f * 3.14159265f);
+    const float halfW = 6.0f, verge = 6.0f;
+    const int across = 8;                                  /* quads across: 2 verge + 4 road + 2 verge */
+    int along = std::max(64, targetTris / (across * 2));
+    PdSurface road; memset(&road, 0, sizeof(road)); road.gripMod = 0.97f; road.collisionCategory = 1; road.isValidTrack = 1;
+    PdSurface grass = road; grass.gripMod = 0.8f; grass.isValidTrack = 0; grass.dirtAdditiveK = 0.0f;
+    out.surfaces.push_back(road); out.surfaces.push_back(grass);
+    std::vector<float> verts9; std::vector<int32_t> surf;
+    auto P = [&](int i, int j) {
+        const float a = 2.0f * 3.14159265f * (float)(i % along) / (float)along;
+        const float off = -(halfW + verge) + (2.0f * (halfW + verge)) * (float)j / (float)across;
+        const float r = R * (1.0f + 0.25f * sinf(3.0f * a)) + off;
+        return V3h{r * cosf(a), 2.0f * sinf(2.0f * a), r * sinf(a)};
+    };
+    for (int i = 0; i < along; ++i)
+        for (int j = 0; j < across; ++j) {
+            V3h a = P(i, j), b = P(i + 1, j), c = P(i + 1, j + 1), d = P(i, j + 1);
+            const int32_t s = (j < 2 || j >= across - 2) ? 1 : 0;
+            V3h t1[3] = {a, b, c}, t2[3] = {a, c, d};
+            /* orient so that the geometric normal (v1-v0)x(v2-v0) points up (front face for a downward ray) */
+            auto up = [&](V3h* t) { V3h e1 = sub(t[1], t[0]), e2 = sub(t[2], t[0]); float ny = e1.z * e2.x - e1.x * e2.z; if (ny < 0) std::swap(t[1], t[2]); };
+            up(t1); up(t2);
+            for (auto* t : {t1, t2}) { for (int k = 0; k < 3; ++k) { verts9.push_back(t[k].x); verts9.push_back(t[k].y); verts9.push_back(t[k].z); } surf.push_back(s); }
+        }
+    out.info.nSurfaces = 2;
+    build_bvh(verts9, surf, out);
+    const int nPts = std::max(16, (int)(lengthMeters / 1.5f));
+    out.fat.resize(nPts);
+    for (int i = 0; i < nPts; ++i) {
+        auto C = [&](float a, float off) { const float r = R * (1.0f + 0.25f * sinf(3.0f * a)) + off; return V3h{r * cosf(a), 2.0f * sinf(2.0f * a), r * sinf(a)}; };
+        const float a = 2.0f * 3.14159265f * (float)i / (float)nPts, a2 = 2.0f * 3.14159265f * (float)(i + 1) / (float)nPts;
+        V3h c = C(a, 0), l = C(a, halfW), r = C(a, -halfW), nx = C(a2, 0);
+        V3h f = sub(nx, c); const float fl = lenh(f); f = divf(f, fl);
+        PdFatPoint& p = out.fat[i];
+        p.best[0] = c.x; p.best[1] = c.y; p.best[2] = c.z; p.center[0] = c.x; p.center[1] = c.y; p.center[2] = c.z;
+        p.left[0] = l.x; p.left[1] = l.y; p.left[2] = l.z; p.right[0] = r.x; p.right[1] = r.y; p.right[2] = r.z;
+        p.forwardDir[0] = f.x; p.forwardDir[1] = f.y; p.forwardDir[2] = f.z;
+    }
+    finish_track_points(out, true, 50.0f);
+}
+
+} // namespace pdh

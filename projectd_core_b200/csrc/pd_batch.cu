@@ -1,0 +1,548 @@
+/*
+ * pd_batch.cu -- CUDA kernels (sm_100a) + the C ABI of include/pd_batch.h.
+ *
+ * Kernel map (one thread = one car unless noted):
+ *   k_tick          Simulator::step for every env: Car::step + stepComponents + dWorldStep + postStep
+ *                   (device functions in pd_tick.h / pd_car.h / pd_solver.h / pd_track.h)
+ *   k_teleport      Car::teleportToSpline (reset path)
+ *   k_set_controls / k_set_actions   setCarControls / the env's action mapping
+ *   k_observe       the 24-float observation of pyprojectd/projectd_env.py:237-275
+ *   k_env_done      reward + termination logic of ProjectDEnv.step (projectd_env.py:178-212) + episode stats
+ *   k_raycast       batch rays against the track BVH
+ * State is structure-of-arrays in HBM (include/pd_state.h); car parameters and the track are read-only
+ * device buffers shared by all envs (served from L2/L1 after first touch).
+ * No CPU fallback exists: every entry point that computes launches a kernel or fails.
+ */
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "pd_tick.h"
+#include "host/pd_host.h"
+#include "../../include/pd_batch.h"
+
+using namespace pd;
+
+#define PD_BLOCK 64
+
+/* ------------------------------------------------------------------ kernels ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(PD_BLOCK) k_tick(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mask && !mask[e]) return;
+    SV sv{state, (size_t)n, (size_t)e};
+    car_tick(*P, T, sv, dt, time);
+}
+
+__global__ void k_broadcast(uint32_t* state, int n, const uint32_t* __restrict__ rec) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * PD_STATE_WORDS) return;
+    state[i] = rec[i / n];
+}
+
+__global__ void __launch_bounds__(PD_BLOCK) k_teleport(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int n, const int32_t* __restrict__ mask, const int32_t* __restrict__ pointIds, double time) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mask && !mask[e]) return;
+    SV sv{state, (size_t)n, (size_t)e};
+    car_teleport_to_point(*P, T, sv, pointIds[e], time);
+}
+
+/* counter-based uniform in [0,1): splitmix64 of (seed, global env id, episode counter) */
+__host__ __device__ inline float pd_uniform(uint64_t seed, uint64_t id, uint64_t ctr) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (id * 0x100000001B3ull + ctr + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+/* choose the spline point for a teleport by mode (Car::teleportByMode, Car.cpp:1342-1358) */
+__global__ void k_pick_points(TrackDev T, const uint32_t* __restrict__ state, int n, const int32_t* __restrict__ mask, int mode, const float* __restrict__ distNorm,
+                              uint64_t seed, uint64_t idOffset, uint32_t* __restrict__ episodeCtr, int32_t* __restrict__ pointIds) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mask && !mask[e]) return;
+    float u = 0.0f;
+    if (distNorm) u = distNorm[e];
+    else if (mode == PD_TELEPORT_NEAREST) u = u2f(state[(size_t)(PD_OFF_CAR + PD_CAR_o_trackLocation) * n + e]);
+    else if (mode == PD_TELEPORT_RANDOM) { u = pd_uniform(seed, idOffset + (uint64_t)e, episodeCtr[e]); episodeCtr[e]++; }
+    pointIds[e] = point_id_at_distance(T, u);
+}
+
+__global__ void k_set_controls(uint32_t* state, int n, const float* __restrict__ ctl, const int8_t* __restrict__ gears, int smooth) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    SV sv{state, (size_t)n, (size_t)e};
+    const int o = PD_OFF_CAR;
+    sv.f(o + PD_CAR_o_ctlSteer, ctl[e * 5 + 0]); sv.f(o + PD_CAR_o_ctlClutch, ctl[e * 5 + 1]); sv.f(o + PD_CAR_o_ctlBrake, ctl[e * 5 + 2]);
+    sv.f(o + PD_CAR_o_ctlHandBrake, ctl[e * 5 + 3]); sv.f(o + PD_CAR_o_ctlGas, ctl[e * 5 + 4]);
+    sv.i(o + PD_CAR_o_ctlRequestedGear, gears ? (int)gears[e * 3 + 0] : -1);
+    sv.i(o + PD_CAR_o_ctlGearUp, gears ? (int)gears[e * 3 + 1] : 0);
+    sv.i(o + PD_CAR_o_ctlGearDn, gears ? (int)gears[e * 3 + 2] : 0);
+    sv.i(o + PD_CAR_o_smoothSteer, smooth);
+}
+
+/* projectd_env.py:159-170.  zeroMask: envs that take the reset's zero action [0,0,0] (projectd_env.py:220) */
+__global__ void k_set_actions(uint32_t* state, int n, const float* __restrict__ act, const int32_t* __restrict__ zeroMask) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (zeroMask && !zeroMask[e]) return;
+    SV sv{state, (size_t)n, (size_t)e};
+    const int o = PD_OFF_CAR;
+    const float a0 = zeroMask ? 0.0f : act[e * 2 + 0], a1 = zeroMask ? 0.0f : act[e * 2 + 1];
+    sv.f(o + PD_CAR_o_ctlSteer, a0); sv.f(o + PD_CAR_o_ctlClutch, 0.0f); sv.f(o + PD_CAR_o_ctlBrake, 0.0f); sv.f(o + PD_CAR_o_ctlHandBrake, 0.0f);
+    sv.f(o + PD_CAR_o_ctlGas, linscalef(a1, -1.0f, 1.0f, 0.1f, 1.0f));
+    sv.i(o + PD_CAR_o_ctlRequestedGear, -1); sv.i(o + PD_CAR_o_ctlGearUp, 0); sv.i(o + PD_CAR_o_ctlGearDn, 0); sv.i(o + PD_CAR_o_smoothSteer, 1);
+}
+
+__global__ void k_observe(const uint32_t* state, int n, float* __restrict__ obs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    SV sv{const_cast<uint32_t*>(state), (size_t)n, (size_t)e};
+    float o[PD_OBS_DIM];
+    car_observe(sv, o);
+    for (int k = 0; k < PD_OBS_DIM; ++k) obs[(size_t)e * PD_OBS_DIM + k] = o[k];
+}
+
+__global__ void k_rewards(const uint32_t* state, int n, float* stepReward, float* totalReward, int32_t* flags) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    SV sv{const_cast<uint32_t*>(state), (size_t)n, (size_t)e};
+    if (stepReward) stepReward[e] = sv.f(PD_OFF_CAR + PD_CAR_o_stepReward);
+    if (totalReward) totalReward[e] = sv.f(PD_OFF_CAR + PD_CAR_o_totalReward);
+    if (flags) flags[e] = (sv.i(PD_OFF_CAR + PD_CAR_o_collisionFlag) ? 1 : 0) | (sv.i(PD_OFF_CAR + PD_CAR_o_outOfTrackFlag) ? 2 : 0);
+}
+
+/* ProjectDEnv.step tail (projectd_env.py:178-212): penalties, termination, per-env return; plus episode statistics */
+__global__ void k_env_done(const uint32_t* state, int n, double timeAfter, float* __restrict__ reward, int32_t* __restrict__ done,
+                           float* __restrict__ envReturn, int32_t* __restrict__ envLen, double* __restrict__ stats) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e < n) {
+        SV sv{const_cast<uint32_t*>(state), (size_t)n, (size_t)e};
+        const int o = PD_OFF_CAR;
+        float r = sv.f(o + PD_CAR_o_stepReward);
+        int d = 0;
+        if (sv.i(o + PD_CAR_o_collisionFlag)) { r -= 50.0f; d |= PD_DONE_COLLISION; }
+        if (sv.i(o + PD_CAR_o_outOfTrackFlag)) { r -= 50.0f; d |= PD_DONE_OFFTRACK; }
+        /* dstate.timestamp is the physics time the tick ran at (Car.cpp:808) = timeAfter - dt; the env compares
+           lastTrackPointTimestamp + 5 s against it */
+        const float timestamp = (float)timeAfter;
+        if (sv.f(o + PD_CAR_o_lastTrackPointTimestamp) + 5.0f < timestamp) { r -= 50.0f; d |= PD_DONE_STUCK; }
+        if (sv.i(o + PD_CAR_o_nanFlag)) d |= PD_DONE_NAN;
+        envReturn[e] += r; envLen[e] += 1;
+        if (envReturn[e] < -200.0f) d |= PD_DONE_LOWREWARD;
+        reward[e] = r; done[e] = d;
+        if (d) {
+            s[0] = 1; s[1] = envReturn[e]; s[2] = envLen[e];
+            s[3] = (d & PD_DONE_COLLISION) ? 1 : 0; s[4] = (d & PD_DONE_OFFTRACK) ? 1 : 0; s[5] = (d & PD_DONE_STUCK) ? 1 : 0;
+            s[6] = (d & PD_DONE_LOWREWARD) ? 1 : 0; s[7] = (d & PD_DONE_NAN) ? 1 : 0;
+            envReturn[e] = 0; envLen[e] = 0;
+        }
+    }
+    /* warp-level reduction, one atomic per warp and statistic */
+    for (int k = 0; k < 8; ++k) {
+        double v = s[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&stats[k], v);
+    }
+}
+
+__global__ void k_clear_nan(uint32_t* state, int n, const int32_t* __restrict__ mask) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || !mask[e]) return;
+    state[(size_t)(PD_OFF_CAR + PD_CAR_o_nanFlag) * n + e] = 0;
+}
+
+__global__ void k_raycast(TrackDev T, int n, const float* __restrict__ rays, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = rays + (size_t)i * 7; float* q = out + (size_t)i * 8;
+    const RayHit r = ray_cast(T, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), p[6]);
+    q[0] = (float)r.hit; q[1] = r.pos.x; q[2] = r.pos.y; q[3] = r.pos.z; q[4] = r.normal.x; q[5] = r.normal.y; q[6] = r.normal.z; q[7] = (float)r.surface;
+}
+
+__global__ void k_set_pressure(uint32_t* state, int n, int wheel, float value) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    state[(size_t)(PD_OFF_TYRE(wheel) + PD_TYRE_o_pressureStatic) * n + e] = f2u(value);
+}
+
+/* ------------------------------------------------------------------ host side ------------------------------------------------------------------ */
+/* minimal DLPack ABI (dlpack.h v0.8) */
+typedef struct { int32_t device_type; int32_t device_id; } PdDLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } PdDLDataType;
+typedef struct { void* data; PdDLDevice device; int32_t ndim; PdDLDataType dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset; } PdDLTensor;
+typedef struct PdDLManagedTensor { PdDLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct PdDLManagedTensor*); } PdDLManagedTensor;
+
+#pragma pack(push, 4)
+struct PdCarStateOut {    /* Car/CarState.h:11-56 */
+    int32_t carId, simId; float timestamp;
+    float steer, clutch, brake, handBrake, gas; int8_t isShifterSupported, requestedGearIndex, gearUp, gearDn;
+    int32_t collisionFlag, outOfTrackFlag, trackPointId; float lastTrackPointTimestamp, trackLocation, bodyVsTrack, velocityVsTrack;
+    float engineRPM, speedMS; int32_t gear, gearGrinding;
+    float bodyMatrix[16], bodyPos[3], bodyEuler[3], accG[3], velocity[3], localVelocity[3], angularVelocity[3], localAngularVelocity[3];
+    float hubMatrix[4][16], tyreContacts[4][3], tyreLoad[4], tyreAngularSpeed[4], tyreSlipRatio[4], tyreNdSlip[4];
+    float probes[10], lookAhead[5], stepReward, totalReward;
+};
+#pragma pack(pop)
+static_assert(sizeof(PdCarStateOut) == 664, "CarState is 664 bytes");
+
+struct pd_batch {
+    int n = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    pdh::CarModel car; pdh::TrackModel track;
+    PdCarParams* dP = nullptr; bool paramsDirty = true;
+    TrackDev dev{};
+    std::vector<void*> allocs;
+    uint32_t* dState = nullptr;
+    float* dObs = nullptr; float* dCtl = nullptr; int8_t* dGears = nullptr; float* dAct = nullptr;
+    int32_t* dMask = nullptr; int32_t* dPoints = nullptr; float* dDist = nullptr; uint32_t* dEpisodeCtr = nullptr;
+    float* dReward = nullptr; float* dTotal = nullptr; int32_t* dFlags = nullptr; int32_t* dDone = nullptr;
+    float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
+    double time = 0, lastDt = 0;
+    uint64_t seed = 0, idOffset = 0, launches = 0;
+    std::string err;
+    int64_t dlShape[2] = {0, 0};
+};
+
+static std::string g_createError;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { b->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PD_ERR_CUDA; } } while (0)
+
+template <class T> static int dalloc(pd_batch* b, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 4);
+    if (e != cudaSuccess) { b->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return PD_ERR_CUDA; }
+    b->allocs.push_back(q); *p = (T*)q; return PD_OK;
+}
+template <class T> static int upload(pd_batch* b, const T** p, const std::vector<T>& v) {
+    T* q = nullptr; int rc = dalloc(b, &q, v.size()); if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpyAsync(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, b->stream));
+    *p = q; return PD_OK;
+}
+static inline int grid(int n, int block) { return (n + block - 1) / block; }
+
+static int sync_params(pd_batch* b) {
+    if (!b->paramsDirty) return PD_OK;
+    CK(cudaMemcpyAsync(b->dP, &b->car.P, sizeof(PdCarParams), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));   /* the host copy may change again right after */
+    b->paramsDirty = false; return PD_OK;
+}
+
+static int finish_create(pd_batch* b, int n_envs, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) { b->err = "no CUDA device available (this library has no CPU path)"; return PD_ERR_CUDA; }
+    if (device < 0 || device >= count) { b->err = "bad device ordinal"; return PD_ERR_ARG; }
+    CK(cudaSetDevice(device));
+    b->n = n_envs; b->device = device;
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = dalloc(b, &b->dP, 1))) return rc;
+    { const std::vector<pd::BvhNode>& dummy = *reinterpret_cast<const std::vector<pd::BvhNode>*>(&b->track.nodes); if ((rc = upload(b, &b->dev.nodes, dummy))) return rc; }
+    if ((rc = upload(b, &b->dev.tris, b->track.tris))) return rc;
+    if ((rc = upload(b, &b->dev.triSurf, b->track.triSurf))) return rc;
+    if ((rc = upload(b, &b->dev.surfaces, b->track.surfaces))) return rc;
+    if ((rc = upload(b, &b->dev.fat, b->track.fat))) return rc;
+    if ((rc = upload(b, &b->dev.splineXYZ, b->track.splineXYZ))) return rc;
+    if ((rc = upload(b, &b->dev.splineDist, b->track.splineDist))) return rc;
+    b->dev.info = b->track.info;
+    const size_t n = (size_t)n_envs;
+    if ((rc = dalloc(b, &b->dState, n * PD_STATE_WORDS))) return rc;
+    if ((rc = dalloc(b, &b->dObs, n * PD_OBS_DIM))) return rc;
+    if ((rc = dalloc(b, &b->dCtl, n * 5))) return rc;
+    if ((rc = dalloc(b, &b->dGears, n * 3))) return rc;
+    if ((rc = dalloc(b, &b->dAct, n * 2))) return rc;
+    if ((rc = dalloc(b, &b->dMask, n))) return rc;
+    if ((rc = dalloc(b, &b->dPoints, n))) return rc;
+    if ((rc = dalloc(b, &b->dDist, n))) return rc;
+    if ((rc = dalloc(b, &b->dEpisodeCtr, n))) return rc;
+    if ((rc = dalloc(b, &b->dReward, n))) return rc;
+    if ((rc = dalloc(b, &b->dTotal, n))) return rc;
+    if ((rc = dalloc(b, &b->dFlags, n))) return rc;
+    if ((rc = dalloc(b, &b->dDone, n))) return rc;
+    if ((rc = dalloc(b, &b->dEnvReturn, n))) return rc;
+    if ((rc = dalloc(b, &b->dEnvLen, n))) return rc;
+    if ((rc = dalloc(b, &b->dStats, 8))) return rc;
+    CK(cudaMemsetAsync(b->dEpisodeCtr, 0, n * 4, b->stream));
+    CK(cudaMemsetAsync(b->dEnvReturn, 0, n * 4, b->stream));
+    CK(cudaMemsetAsync(b->dEnvLen, 0, n * 4, b->stream));
+    CK(cudaMemsetAsync(b->dStats, 0, 8 * 8, b->stream));
+    CK(cudaMemsetAsync(b->dObs, 0, n * PD_OBS_DIM * 4, b->stream));
+    /* initial record: built once with the same device functions compiled for the host, then broadcast */
+    std::vector<uint32_t> rec(PD_STATE_WORDS, 0);
+    { SV sv{rec.data(), 1, 0}; car_init_state(b->car.P, sv); }
+    uint32_t* dRec = nullptr; if ((rc = dalloc(b, &dRec, PD_STATE_WORDS))) return rc;
+    CK(cudaMemcpyAsync(dRec, rec.data(), PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream));
+    k_broadcast<<<grid((int)std::min<size_t>(n * PD_STATE_WORDS, 0x7fffffff), 256), 256, 0, b->stream>>>(b->dState, n_envs, dRec); b->launches++;
+    CK(cudaGetLastError());
+    if ((rc = sync_params(b))) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    return PD_OK;
+}
+
+extern "C" {
+
+int pd_create(const char* base_path, const char* track_name, const char* car_model, int n_envs, int device, pd_batch** out) {
+    if (!out || !base_path || !track_name || !car_model || n_envs <= 0) { g_createError = "pd_create: bad argument"; return PD_ERR_ARG; }
+    *out = nullptr;
+    pd_batch* b = new pd_batch();
+    int rc = PD_OK;
+    try { pdh::load_car(base_path, car_model, b->car); pdh::load_track(base_path, track_name, b->track); }
+    catch (const std::exception& ex) { b->err = ex.what(); rc = PD_ERR_IO; }
+    if (rc == PD_OK) rc = finish_create(b, n_envs, device);
+    if (rc != PD_OK) { g_createError = b->err; pd_destroy(b); return rc; }
+    *out = b; return PD_OK;
+}
+
+int pd_create_synthetic(const char* base_path, const char* car_model, int target_tris, float length_m, int n_envs, int device, pd_batch** out) {
+    if (!out || !base_path || !car_model || n_envs <= 0 || target_tris <= 0) { g_createError = "pd_create_synthetic: bad argument"; return PD_ERR_ARG; }
+    *out = nullptr;
+    pd_batch* b = new pd_batch();
+    int rc = PD_OK;
+    try { pdh::load_car(base_path, car_model, b->car); pdh::make_synthetic_track(target_tris, length_m, b->track); }
+    catch (const std::exception& ex) { b->err = ex.what(); rc = PD_ERR_IO; }
+    if (rc == PD_OK) rc = finish_create(b, n_envs, device);
+    if (rc != PD_OK) { g_createError = b->err; pd_destroy(b); return rc; }
+    *out = b; return PD_OK;
+}
+
+void pd_destroy(pd_batch* b) {
+    if (!b) return;
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* p : b->allocs) cudaFree(p);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+const char* pd_last_error(const pd_batch* b) { return b ? b->err.c_str() : g_createError.c_str(); }
+int pd_num_envs(const pd_batch* b) { return b ? b->n : 0; }
+int pd_state_words(void) { return PD_STATE_WORDS; }
+int pd_obs_dim(void) { return PD_OBS_DIM; }
+int pd_car_state_bytes(void) { return (int)sizeof(PdCarStateOut); }
+
+int pd_set_assists(pd_batch* b, int ac, int as, int ab) {
+    if (!b) return PD_ERR_ARG;
+    PdAssists& A = b->car.P.assists;
+    A.acUseAutoOnStart = ac != 0; A.acUseAutoOnChange = ac != 0; A.asIsActive = as != 0; A.blipIsActive = ab != 0;
+    b->paramsDirty = true; return PD_OK;
+}
+int pd_set_tune(pd_batch* b, const char* name, float value) {
+    if (!b || !name) return PD_ERR_ARG;
+    b->car.setTune(name, value); b->paramsDirty = true;
+    static const char* kP[4] = {"PRESSURE_LF", "PRESSURE_RF", "PRESSURE_LR", "PRESSURE_RR"};
+    for (int w = 0; w < 4; ++w) if (!strcmp(name, kP[w])) {   /* the tune writes Tyre::status.pressureStatic of every car */
+        k_set_pressure<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, w, b->car.P.tyre[w].pressureStaticDefault); b->launches++;
+        CK(cudaGetLastError());
+    }
+    return PD_OK;
+}
+int pd_set_scoring_var(pd_batch* b, const char* name, float value) {
+    if (!b || !name) return PD_ERR_ARG;
+    try { b->car.setScoringVar(name, value); } catch (const std::exception& ex) { b->err = ex.what(); return PD_ERR_ARG; }
+    b->paramsDirty = true; return PD_OK;
+}
+float pd_get_scoring_var(const pd_batch* b, const char* name) { return (b && name) ? b->car.getScoringVar(name) : 0.0f; }
+
+int pd_set_controls(pd_batch* b, const float* controls, const int8_t* gears, int smooth, int on_device) {
+    if (!b || !controls) return PD_ERR_ARG;
+    const float* c = controls; const int8_t* g = gears;
+    if (!on_device) {
+        CK(cudaMemcpyAsync(b->dCtl, controls, (size_t)b->n * 5 * 4, cudaMemcpyHostToDevice, b->stream)); c = b->dCtl;
+        if (gears) { CK(cudaMemcpyAsync(b->dGears, gears, (size_t)b->n * 3, cudaMemcpyHostToDevice, b->stream)); g = b->dGears; }
+    }
+    k_set_controls<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, c, g, smooth); b->launches++;
+    CK(cudaGetLastError()); return PD_OK;
+}
+int pd_set_actions(pd_batch* b, const float* actions, int on_device) {
+    if (!b || !actions) return PD_ERR_ARG;
+    const float* a = actions;
+    if (!on_device) { CK(cudaMemcpyAsync(b->dAct, actions, (size_t)b->n * 2 * 4, cudaMemcpyHostToDevice, b->stream)); a = b->dAct; }
+    k_set_actions<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, a, nullptr); b->launches++;
+    CK(cudaGetLastError()); return PD_OK;
+}
+
+int pd_step(pd_batch* b, float dt, int n_ticks) {
+    if (!b || n_ticks < 0) return PD_ERR_ARG;
+    int rc = sync_params(b); if (rc) return rc;
+    for (int t = 0; t < n_ticks; ++t) {
+        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->n, dt, b->time, nullptr); b->launches++;
+        b->time += (double)dt; b->lastDt = dt;
+    }
+    CK(cudaGetLastError()); return PD_OK;
+}
+double pd_get_time(const pd_batch* b) { return b ? b->time : 0.0; }
+int pd_set_time(pd_batch* b, double t) { if (!b) return PD_ERR_ARG; b->time = t; return PD_OK; }
+int pd_set_seed(pd_batch* b, uint64_t seed, uint64_t off) { if (!b) return PD_ERR_ARG; b->seed = seed; b->idOffset = off; return PD_OK; }
+
+static int teleport_common(pd_batch* b, const uint8_t* mask, int mode, const float* dist_norm) {
+    int rc = sync_params(b); if (rc) return rc;
+    const int32_t* dm = nullptr;
+    if (mask) {
+        std::vector<int32_t> m(b->n); for (int i = 0; i < b->n; ++i) m[i] = mask[i] ? 1 : 0;
+        CK(cudaMemcpyAsync(b->dMask, m.data(), (size_t)b->n * 4, cudaMemcpyHostToDevice, b->stream)); CK(cudaStreamSynchronize(b->stream)); dm = b->dMask;
+    }
+    const float* dd = nullptr;
+    if (dist_norm) { CK(cudaMemcpyAsync(b->dDist, dist_norm, (size_t)b->n * 4, cudaMemcpyHostToDevice, b->stream)); dd = b->dDist; }
+    k_pick_points<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dev, b->dState, b->n, dm, mode, dd, b->seed, b->idOffset, b->dEpisodeCtr, b->dPoints); b->launches++;
+    k_teleport<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->n, dm, b->dPoints, b->time); b->launches++;
+    CK(cudaGetLastError()); return PD_OK;
+}
+int pd_teleport_spline(pd_batch* b, const uint8_t* mask, const float* dist_norm) {
+    if (!b) return PD_ERR_ARG;
+    if (!dist_norm) return teleport_common(b, mask, PD_TELEPORT_START, nullptr);
+    return teleport_common(b, mask, PD_TELEPORT_START, dist_norm);
+}
+int pd_teleport_mode(pd_batch* b, const uint8_t* mask, int mode) {
+    if (!b || mode < 0 || mode > 2) return PD_ERR_ARG;
+    return teleport_common(b, mask, mode, nullptr);
+}
+
+int pd_observe(pd_batch* b) {
+    if (!b) return PD_ERR_ARG;
+    k_observe<<<grid(b->n, 128), 128, 0, b->stream>>>(b->dState, b->n, b->dObs); b->launches++;
+    CK(cudaGetLastError()); return PD_OK;
+}
+const float* pd_obs_device_ptr(pd_batch* b) { return b ? b->dObs : nullptr; }
+int pd_get_obs(pd_batch* b, float* out, int to_device) {
+    if (!b || !out) return PD_ERR_ARG;
+    int rc = pd_observe(b); if (rc) return rc;
+    CK(cudaMemcpyAsync(out, b->dObs, (size_t)b->n * PD_OBS_DIM * 4, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, b->stream));
+    if (!to_device) CK(cudaStreamSynchronize(b->stream));
+    return PD_OK;
+}
+static void dl_deleter(PdDLManagedTensor* t) { delete t; }
+void* pd_obs_dlpack(pd_batch* b) {
+    if (!b) return nullptr;
+    PdDLManagedTensor* t = new PdDLManagedTensor();
+    b->dlShape[0] = b->n; b->dlShape[1] = PD_OBS_DIM;
+    t->dl_tensor.data = b->dObs; t->dl_tensor.device.device_type = 2 /* kDLCUDA */; t->dl_tensor.device.device_id = b->device;
+    t->dl_tensor.ndim = 2; t->dl_tensor.dtype.code = 2 /* kDLFloat */; t->dl_tensor.dtype.bits = 32; t->dl_tensor.dtype.lanes = 1;
+    t->dl_tensor.shape = b->dlShape; t->dl_tensor.strides = nullptr; t->dl_tensor.byte_offset = 0;
+    t->manager_ctx = b; t->deleter = dl_deleter;
+    return t;
+}
+int pd_get_rewards(pd_batch* b, float* step_reward, float* total_reward, int32_t* flags) {
+    if (!b) return PD_ERR_ARG;
+    k_rewards<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, b->dReward, b->dTotal, b->dFlags); b->launches++;
+    CK(cudaGetLastError());
+    if (step_reward) CK(cudaMemcpyAsync(step_reward, b->dReward, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (total_reward) CK(cudaMemcpyAsync(total_reward, b->dTotal, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, b->dFlags, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+}
+
+int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev, float* reward_dev, int32_t* done_dev) {
+    if (!b || !actions_dev) return PD_ERR_ARG;
+    int rc = sync_params(b); if (rc) return rc;
+    const int n = b->n;
+    float* rew = reward_dev ? reward_dev : b->dReward; int32_t* done = done_dev ? done_dev : b->dDone;
+    k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, nullptr);
+    k_tick<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, nullptr);
+    k_env_done<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, b->time, rew, done, b->dEnvReturn, b->dEnvLen, b->dStats);
+    b->time += (double)dt; b->lastDt = dt;
+    /* auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) + one zero-action tick */
+    k_pick_points<<<grid(n, 256), 256, 0, b->stream>>>(b->dev, b->dState, n, done, b->car.P.teleportMode, nullptr, b->seed, b->idOffset, b->dEpisodeCtr, b->dPoints);
+    k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, done, b->dPoints, b->time);
+    k_clear_nan<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, done);
+    k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, done);
+    k_tick<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, done);
+    k_observe<<<grid(n, 128), 128, 0, b->stream>>>(b->dState, n, obs_dev ? obs_dev : b->dObs);
+    b->launches += 9;
+    CK(cudaGetLastError()); return PD_OK;
+}
+int pd_env_stats(pd_batch* b, double* out8, int reset) {
+    if (!b || !out8) return PD_ERR_ARG;
+    CK(cudaMemcpyAsync(out8, b->dStats, 64, cudaMemcpyDeviceToHost, b->stream)); CK(cudaStreamSynchronize(b->stream));
+    if (reset) CK(cudaMemsetAsync(b->dStats, 0, 64, b->stream));
+    return PD_OK;
+}
+
+int pd_get_state(pd_batch* b, int env, uint32_t* record) {
+    if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
+    CK(cudaMemcpy2DAsync(record, 4, b->dState + env, (size_t)b->n * 4, 4, PD_STATE_WORDS, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+}
+int pd_set_state(pd_batch* b, int env, const uint32_t* record) {
+    if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
+    CK(cudaMemcpy2DAsync(b->dState + env, (size_t)b->n * 4, record, 4, 4, PD_STATE_WORDS, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+}
+int pd_snapshot(pd_batch* b, uint32_t* host_buf) {
+    if (!b || !host_buf) return PD_ERR_ARG;
+    CK(cudaMemcpyAsync(host_buf, b->dState, (size_t)b->n * PD_STATE_WORDS * 4, cudaMemcpyDeviceToHost, b->stream)); CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+}
+int pd_restore(pd_batch* b, const uint32_t* host_buf) {
+    if (!b || !host_buf) return PD_ERR_ARG;
+    CK(cudaMemcpyAsync(b->dState, host_buf, (size_t)b->n * PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream)); CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+}
+int pd_get_params(const pd_batch* b, PdCarParams* out) { if (!b || !out) return PD_ERR_ARG; *out = b->car.P; return PD_OK; }
+int pd_get_track_info(const pd_batch* b, PdTrackInfo* out) { if (!b || !out) return PD_ERR_ARG; *out = b->track.info; return PD_OK; }
+
+int pd_get_car_state(pd_batch* b, int env, void* outv) {
+    if (!b || !outv) return PD_ERR_ARG;
+    std::vector<uint32_t> rec(PD_STATE_WORDS);
+    int rc = pd_get_state(b, env, rec.data()); if (rc) return rc;
+    SV sv{rec.data(), 1, 0};
+    PdCarStateOut s; memset(&s, 0, sizeof(s));
+    CarS c; load_car(sv, c);
+    Body C; load_body(sv, PD_BODY_CHASSIS, C);
+    s.carId = 0; s.simId = env; s.timestamp = (float)(b->time - b->lastDt);
+    s.steer = c.ctlSteer; s.clutch = c.ctlClutch; s.brake = c.ctlBrake; s.handBrake = c.ctlHandBrake; s.gas = c.ctlGas;
+    s.isShifterSupported = (int8_t)b->car.P.drivetrain.isShifterSupported; s.requestedGearIndex = (int8_t)c.ctlRequestedGear; s.gearUp = (int8_t)c.ctlGearUp; s.gearDn = (int8_t)c.ctlGearDn;
+    s.collisionFlag = c.collisionFlag; s.outOfTrackFlag = c.outOfTrackFlag; s.trackPointId = c.nearestTrackPointId;
+    s.lastTrackPointTimestamp = c.lastTrackPointTimestamp; s.trackLocation = c.trackLocation; s.bodyVsTrack = c.bodyVsTrack; s.velocityVsTrack = c.velocityVsTrack;
+    s.engineRPM = car_engine_rpm(c); s.speedMS = c.speed; s.gear = c.currentGear; s.gearGrinding = c.isGearGrinding ? 1 : 0;
+    auto put_matrix = [](float* m, const Frame& f) {
+        m[0] = f.ax.x; m[1] = f.ax.y; m[2] = f.ax.z; m[3] = 0; m[4] = f.ay.x; m[5] = f.ay.y; m[6] = f.ay.z; m[7] = 0;
+        m[8] = f.az.x; m[9] = f.az.y; m[10] = f.az.z; m[11] = 0; m[12] = f.p.x; m[13] = f.p.y; m[14] = f.p.z; m[15] = 1.0f; };
+    put_matrix(s.bodyMatrix, C.fr);
+    s.bodyPos[0] = C.fr.p.x; s.bodyPos[1] = C.fr.p.y; s.bodyPos[2] = C.fr.p.z;
+    { /* mat44f::getEulerAngles (Core/Math.cpp:60-86) */
+        const float* M = s.bodyMatrix; const float M11 = M[0], M12 = M[1], M21 = M[4], M22 = M[5], M31 = M[8], M32 = M[9], M33 = M[10];
+        float rx = atan2f(-M31, M33); float v7 = 1, v8 = M32;
+        if (v8 > 1.0 || (v7 = -1, v8 < -1.0)) v8 = v7;
+        const float ry = asinf(v8); float v10, v11;
+        if (M12 == 0.0f && M22 == 0.0f) { v11 = M21; v10 = M11; rx = 0.0f; } else { v11 = -M12; v10 = M22; }
+        const float rz = atan2f(v11, v10);
+        s.bodyEuler[0] = ry * -57.295779513082323f; s.bodyEuler[1] = rx * -57.295779513082323f; s.bodyEuler[2] = rz * -57.295779513082323f;
+    }
+    s.accG[0] = c.accGX; s.accG[1] = c.accGY; s.accG[2] = c.accGZ;
+    s.velocity[0] = C.v.x; s.velocity[1] = C.v.y; s.velocity[2] = C.v.z;
+    { const V3 lv = irot(C.fr, C.v), lw = irot(C.fr, C.w); s.localVelocity[0] = lv.x; s.localVelocity[1] = lv.y; s.localVelocity[2] = lv.z; s.localAngularVelocity[0] = lw.x; s.localAngularVelocity[1] = lw.y; s.localAngularVelocity[2] = lw.z; }
+    s.angularVelocity[0] = C.w.x; s.angularVelocity[1] = C.w.y; s.angularVelocity[2] = C.w.z;
+    for (int w = 0; w < 4; ++w) {
+        Frame hf;
+        if (w < 2) { Body H; load_body(sv, PD_BODY_HUB0 + 2 * w, H); hf = strut_hub_frame(b->car.P.strut[w], H); }
+        else { Body A; load_body(sv, PD_BODY_AXLE, A); hf = axle_hub_frame(b->car.P.axle, A, w - 2); }
+        put_matrix(s.hubMatrix[w], hf);
+        const int o = PD_OFF_TYRE(w);
+        s.tyreContacts[w][0] = sv.f(o + PD_TYRE_o_contactX); s.tyreContacts[w][1] = sv.f(o + PD_TYRE_o_contactY); s.tyreContacts[w][2] = sv.f(o + PD_TYRE_o_contactZ);
+        s.tyreLoad[w] = sv.f(o + PD_TYRE_o_load); s.tyreAngularSpeed[w] = sv.f(o + PD_TYRE_o_angularVelocity);
+        s.tyreSlipRatio[w] = sv.f(o + PD_TYRE_o_slipRatio); s.tyreNdSlip[w] = sv.f(o + PD_TYRE_o_ndSlip);
+    }
+    for (int i = 0; i < b->car.P.nProbes && i < 10; ++i) s.probes[i] = c.probes[i];
+    for (int i = 0; i < 5; ++i) s.lookAhead[i] = c.lookAhead[i];
+    s.stepReward = c.stepReward; s.totalReward = c.totalReward;
+    memcpy(outv, &s, sizeof(s)); return PD_OK;
+}
+
+int pd_raycast(pd_batch* b, int n, const float* rays, float* out) {
+    if (!b || n < 0 || !rays || !out) return PD_ERR_ARG;
+    if (n == 0) return PD_OK;
+    float *dr = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&dr, (size_t)n * 7 * 4)); CK(cudaMalloc(&dout, (size_t)n * 8 * 4));
+    cudaMemcpyAsync(dr, rays, (size_t)n * 7 * 4, cudaMemcpyHostToDevice, b->stream);
+    k_raycast<<<grid(n, 128), 128, 0, b->stream>>>(b->dev, n, dr, dout); b->launches++;
+    cudaMemcpyAsync(out, dout, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost, b->stream);
+    cudaError_t e = cudaStreamSynchronize(b->stream);
+    cudaFree(dr); cudaFree(dout);
+    if (e != cudaSuccess) { b->err = cudaGetErrorString(e); return PD_ERR_CUDA; }
+    return PD_OK;
+}
+
+int pd_sync(pd_batch* b) { if (!b) return PD_ERR_ARG; CK(cudaStreamSynchronize(b->stream)); CK(cudaGetLastError()); return PD_OK; }
+void* pd_stream(pd_batch* b) { return b ? (void*)b->stream : nullptr; }
+uint64_t pd_launch_count(const pd_batch* b) { return b ? b->launches : 0; }
+
+} /* extern "C" */

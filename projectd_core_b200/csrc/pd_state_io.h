@@ -1,0 +1,160 @@
+/*
+ * pd_state_io.h -- structure-of-arrays access to the per-car state record (include/pd_state.h).
+ *
+ * Device layout: word w of env e is state[w * n_envs + e].  Consecutive threads (one car each) touch
+ * consecutive 4-byte words of the same row -> every state load / store of a warp is one coalesced
+ * 128-byte transaction.  Doubles are kept as two 32-bit rows (lo, hi) so that rows stay 4-byte wide.
+ */
+#pragma once
+#include "pd_math.h"
+#include "../../include/pd_state.h"
+#include "../../include/pd_params.h"
+#include <string.h>
+
+namespace pd {
+
+PD_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+PD_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+PD_HD double u2d(uint32_t lo, uint32_t hi) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    uint64_t v = ((uint64_t)hi << 32) | lo; double d; memcpy(&d, &v, 8); return d;
+#endif
+}
+PD_HD void d2u(double d, uint32_t& lo, uint32_t& hi) {
+#if defined(__CUDA_ARCH__)
+    lo = (uint32_t)__double2loint(d); hi = (uint32_t)__double2hiint(d);
+#else
+    uint64_t v; memcpy(&v, &d, 8); lo = (uint32_t)v; hi = (uint32_t)(v >> 32);
+#endif
+}
+
+/* view of one env inside the SoA state buffer */
+struct SV {
+    uint32_t* s;
+    size_t n;   /* number of envs (row stride) */
+    size_t e;   /* this env */
+    PD_HD float f(int w) const { return u2f(s[(size_t)w * n + e]); }
+    PD_HD int i(int w) const { return (int)s[(size_t)w * n + e]; }
+    PD_HD double d(int w) const { return u2d(s[(size_t)w * n + e], s[(size_t)(w + 1) * n + e]); }
+    PD_HD void f(int w, float v) const { s[(size_t)w * n + e] = f2u(v); }
+    PD_HD void i(int w, int v) const { s[(size_t)w * n + e] = (uint32_t)v; }
+    PD_HD void d(int w, double v) const { uint32_t lo, hi; d2u(v, lo, hi); s[(size_t)w * n + e] = lo; s[(size_t)(w + 1) * n + e] = hi; }
+};
+
+/* ---- typed mirrors of the X-macro lists ---- */
+#define PD__DECL_F(name) float name;
+#define PD__DECL_I(name) int name;
+#define PD__DECL_D(name) double name;
+#define PD__DECL(kind, name) PD__DECL_##kind(name)
+
+struct TyreS {
+    PD_TYRE_FIELDS(PD__DECL)
+    float T[PD_THERMAL_PATCHES];
+};
+struct CarS {
+    PD_CAR_FIELDS(PD__DECL)
+    float probes[PD_MAX_PROBES];
+    float lookAhead[PD_LOOKAHEAD];
+};
+
+#define PD__LD_F(pre, name) t.name = sv.f(o + pre##name);
+#define PD__LD_I(pre, name) t.name = sv.i(o + pre##name);
+#define PD__LD_D(pre, name) t.name = sv.d(o + pre##name);
+#define PD__ST_F(pre, name) sv.f(o + pre##name, t.name);
+#define PD__ST_I(pre, name) sv.i(o + pre##name, t.name);
+#define PD__ST_D(pre, name) sv.d(o + pre##name, t.name);
+#define PD__LDT(kind, name) PD__LD_##kind(PD_TYRE_o_, name)
+#define PD__STT(kind, name) PD__ST_##kind(PD_TYRE_o_, name)
+#define PD__LDC(kind, name) PD__LD_##kind(PD_CAR_o_, name)
+#define PD__STC(kind, name) PD__ST_##kind(PD_CAR_o_, name)
+
+PD_HD void load_tyre(const SV& sv, int w, TyreS& t) {
+    const int o = PD_OFF_TYRE(w);
+    PD_TYRE_FIELDS(PD__LDT)
+    for (int p = 0; p < PD_THERMAL_PATCHES; ++p) t.T[p] = sv.f(PD_OFF_TYRE_PATCH(w) + p);
+}
+PD_HD void store_tyre(const SV& sv, int w, const TyreS& t) {
+    const int o = PD_OFF_TYRE(w);
+    PD_TYRE_FIELDS(PD__STT)
+    for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, t.T[p]);
+}
+PD_HD void load_car(const SV& sv, CarS& t) {
+    const int o = PD_OFF_CAR;
+    PD_CAR_FIELDS(PD__LDC)
+    for (int p = 0; p < PD_MAX_PROBES; ++p) t.probes[p] = sv.f(PD_OFF_PROBES + p);
+    for (int p = 0; p < PD_LOOKAHEAD; ++p) t.lookAhead[p] = sv.f(PD_OFF_LOOKAHEAD + p);
+}
+PD_HD void store_car(const SV& sv, const CarS& t) {
+    const int o = PD_OFF_CAR;
+    PD_CAR_FIELDS(PD__STC)
+    for (int p = 0; p < PD_MAX_PROBES; ++p) sv.f(PD_OFF_PROBES + p, t.probes[p]);
+    for (int p = 0; p < PD_LOOKAHEAD; ++p) sv.f(PD_OFF_LOOKAHEAD + p, t.lookAhead[p]);
+}
+
+/* rigid body working copy: dxBody state + force / torque accumulators + mass data */
+struct Body {
+    Frame fr;      /* pos + axes (R) */
+    Quat q;
+    V3 v, w;       /* lvel, avel */
+    V3 F, T;       /* facc, tacc */
+    float mass;
+    V3 I;          /* diagonal body-frame inertia */
+};
+PD_HD void load_body(const SV& sv, int b, Body& B) {
+    const int o = PD_OFF_BODY(b);
+    B.fr.p = v3(sv.f(o + PD_BODY_o_px), sv.f(o + PD_BODY_o_py), sv.f(o + PD_BODY_o_pz));
+    B.q.w = sv.f(o + PD_BODY_o_qw); B.q.x = sv.f(o + PD_BODY_o_qx); B.q.y = sv.f(o + PD_BODY_o_qy); B.q.z = sv.f(o + PD_BODY_o_qz);
+    B.fr.ax = v3(sv.f(o + PD_BODY_o_axx), sv.f(o + PD_BODY_o_axy), sv.f(o + PD_BODY_o_axz));
+    B.fr.ay = v3(sv.f(o + PD_BODY_o_ayx), sv.f(o + PD_BODY_o_ayy), sv.f(o + PD_BODY_o_ayz));
+    B.fr.az = v3(sv.f(o + PD_BODY_o_azx), sv.f(o + PD_BODY_o_azy), sv.f(o + PD_BODY_o_azz));
+    B.v = v3(sv.f(o + PD_BODY_o_vx), sv.f(o + PD_BODY_o_vy), sv.f(o + PD_BODY_o_vz));
+    B.w = v3(sv.f(o + PD_BODY_o_wx), sv.f(o + PD_BODY_o_wy), sv.f(o + PD_BODY_o_wz));
+    B.F = v3(0, 0, 0); B.T = v3(0, 0, 0);
+}
+PD_HD void store_body(const SV& sv, int b, const Body& B) {
+    const int o = PD_OFF_BODY(b);
+    sv.f(o + PD_BODY_o_px, B.fr.p.x); sv.f(o + PD_BODY_o_py, B.fr.p.y); sv.f(o + PD_BODY_o_pz, B.fr.p.z);
+    sv.f(o + PD_BODY_o_qw, B.q.w); sv.f(o + PD_BODY_o_qx, B.q.x); sv.f(o + PD_BODY_o_qy, B.q.y); sv.f(o + PD_BODY_o_qz, B.q.z);
+    sv.f(o + PD_BODY_o_vx, B.v.x); sv.f(o + PD_BODY_o_vy, B.v.y); sv.f(o + PD_BODY_o_vz, B.v.z);
+    sv.f(o + PD_BODY_o_wx, B.w.x); sv.f(o + PD_BODY_o_wy, B.w.y); sv.f(o + PD_BODY_o_wz, B.w.z);
+    sv.f(o + PD_BODY_o_axx, B.fr.ax.x); sv.f(o + PD_BODY_o_axy, B.fr.ax.y); sv.f(o + PD_BODY_o_axz, B.fr.ax.z);
+    sv.f(o + PD_BODY_o_ayx, B.fr.ay.x); sv.f(o + PD_BODY_o_ayy, B.fr.ay.y); sv.f(o + PD_BODY_o_ayz, B.fr.ay.z);
+    sv.f(o + PD_BODY_o_azx, B.fr.az.x); sv.f(o + PD_BODY_o_azy, B.fr.az.y); sv.f(o + PD_BODY_o_azz, B.fr.az.z);
+}
+
+/* ---- body force API (RigidBodyODE.cpp:184-270 -> ODE dBody*) ---- */
+PD_HD V3 body_point_vel(const Body& b, V3 p) { return b.v + cross(b.w, p - b.fr.p); }            /* dBodyGetPointVel */
+PD_HD V3 body_rel_point_vel(const Body& b, V3 prel) { return b.v + cross(b.w, rot(b.fr, prel)); } /* dBodyGetRelPointVel */
+PD_HD void add_force_at_pos(Body& b, V3 f, V3 p) { b.F += f; b.T += cross(p - b.fr.p, f); }       /* dBodyAddForceAtPos */
+PD_HD void add_force_at_rel_pos(Body& b, V3 f, V3 prel) { b.F += f; b.T += cross(rot(b.fr, prel), f); }
+PD_HD void add_rel_force_at_rel_pos(Body& b, V3 frel, V3 prel) { add_force_at_rel_pos(b, rot(b.fr, frel), prel); }
+PD_HD void add_torque(Body& b, V3 t) { b.T += t; }
+PD_HD void add_rel_torque(Body& b, V3 t) { b.T += rot(b.fr, t); }
+PD_HD void body_stop(Body& b) { b.v = v3(0, 0, 0); b.w = v3(0, 0, 0); b.F = v3(0, 0, 0); b.T = v3(0, 0, 0); }
+
+/* Core/Curve.cpp:94-115 */
+PD_HD float curve_value(const PdCurve& c, float ref) {
+    if (c.n <= 0) return 0.0f;
+    if (ref <= c.ref[0]) return c.val[0];
+    for (int id = 1; id < c.n; ++id) {
+        if (ref <= c.ref[id])
+            return (((c.val[id] - c.val[id - 1]) * (ref - c.ref[id - 1])) / (c.ref[id] - c.ref[id - 1])) + c.val[id - 1];
+    }
+    return c.val[c.n - 1];
+}
+
+} // namespace pd

@@ -1,0 +1,420 @@
+/*
+ * pd_tick.h -- one full simulator tick for one car: Simulator::step (Sim/Simulator.cpp:168-201) =
+ * stepPreCacheValues + Car::step (Car/Car.cpp:421-553) + stepComponents (:638-681) + dWorldStep +
+ * Car::postStep (:685-713), and the teleport / reset path (Car.cpp:1240-1358).
+ */
+#pragma once
+#include "pd_solver.h"
+
+namespace pd {
+
+PD_HD void set_body_mass(CarCtx& X, const PdCarParams& P) {
+    Body* b = X.b;
+    b[PD_BODY_CHASSIS].mass = P.chassisMass; b[PD_BODY_CHASSIS].I = v3(P.chassisInertia[0], P.chassisInertia[1], P.chassisInertia[2]);
+    b[PD_BODY_TANK].mass = P.tankMass; b[PD_BODY_TANK].I = v3(P.tankInertia[0], P.tankInertia[1], P.tankInertia[2]);
+    for (int s = 0; s < 2; ++s) {
+        b[PD_BODY_HUB0 + 2 * s].mass = P.strut[s].hubMass; b[PD_BODY_HUB0 + 2 * s].I = v3(P.strut[s].hubInertia[0], P.strut[s].hubInertia[1], P.strut[s].hubInertia[2]);
+        b[PD_BODY_STRUT0 + 2 * s].mass = P.strut[s].strutMass; b[PD_BODY_STRUT0 + 2 * s].I = v3(P.strut[s].strutInertia[0], P.strut[s].strutInertia[1], P.strut[s].strutInertia[2]);
+    }
+    b[PD_BODY_AXLE].mass = P.axle.axleMass; b[PD_BODY_AXLE].I = v3(P.axle.axleInertia[0], P.axle.axleInertia[1], P.axle.axleInertia[2]);
+}
+
+/* Car::getBetaRad (Car.cpp:1472-1484) */
+PD_HD float beta_rad(const Body& C) {
+    V3 vel = irot(C.fr, C.v);
+    const float fLen = len(vel);
+    if (fLen != 0.0f) vel.x /= fLen;
+    if (vel.x <= -1.0f || vel.x >= 1.0f) return 1.5707964f;
+    return asinf(vel.x);
+}
+
+/* state of a freshly constructed car (Car::init, Car.cpp:31-223, and the constructors it runs): chassis at the
+ * origin with identity rotation, suspension bodies attached, everything else at its default */
+PD_HDN void car_init_state(const PdCarParams& P, const SV& sv) {
+    for (int w = 0; w < PD_STATE_WORDS; ++w) sv.i(w, 0);
+    CarCtx X; set_body_mass(X, P);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) {
+        Body& b = X.b[i]; b.fr.p = v3(0, 0, 0); b.fr.ax = v3(1, 0, 0); b.fr.ay = v3(0, 1, 0); b.fr.az = v3(0, 0, 1);
+        b.q.w = 1; b.q.x = b.q.y = b.q.z = 0; b.v = v3(0, 0, 0); b.w = v3(0, 0, 0);
+    }
+    Body& C = X.b[PD_BODY_CHASSIS];
+    X.b[PD_BODY_TANK].fr.p = v3(P.fuelTankPos[0], P.fuelTankPos[1], P.fuelTankPos[2]);
+    for (int s = 0; s < 2; ++s) {
+        const PdStrut& S = P.strut[s]; Body& H = X.b[PD_BODY_HUB0 + 2 * s]; Body& B = X.b[PD_BODY_STRUT0 + 2 * s];
+        H.fr.p = to_world(C.fr, v3(S.refPoint[0], S.refPoint[1], S.refPoint[2]));
+        const V3 vCarStrut = to_world(C.fr, v3(S.carStrut[0], S.carStrut[1], S.carStrut[2]));
+        const V3 vTyreStrut = to_world(H.fr, v3(S.tyreStrut[0], S.tyreStrut[1], S.tyreStrut[2]));
+        const V3 vNorm = norm(vTyreStrut - vCarStrut);
+        const V3 vM3 = C.fr.az * -1.0f;
+        const V3 vM3N = cross(vM3, vNorm);
+        const V3 vM3NN = norm(cross(vM3N, vNorm));
+        set_rotation(vM3NN, vM3N * -1.0f, vNorm * -1.0f, B.fr.ax, B.fr.ay, B.fr.az, B.q);
+        B.fr.p = (vNorm * S.strutBodyLength) * 0.5f + vCarStrut;
+    }
+    X.b[PD_BODY_AXLE].fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
+    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, X.b[i]);
+    for (int w = 0; w < PD_NUM_WHEELS; ++w) { /* Tyre::Tyre + setCompound(0) + reset (Tyre.cpp:15-26,343-425) */
+        const int o = PD_OFF_TYRE(w);
+        sv.f(o + PD_TYRE_o_pressureStatic, P.tyre[w].pressureStaticDefault); sv.f(o + PD_TYRE_o_pressureDynamic, P.tyre[w].pressureRef);
+        sv.i(o + PD_TYRE_o_isLocked, 1); sv.f(o + PD_TYRE_o_inflation, 1);
+        sv.i(o + PD_TYRE_o_surfaceId, -1);
+        sv.f(o + PD_TYRE_o_coreTemp, P.ambientTemperature); sv.f(o + PD_TYRE_o_thermalMultD, 1.0f);
+        for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, P.ambientTemperature);
+    }
+    const int o = PD_OFF_CAR;
+    sv.i(o + PD_CAR_o_ctlRequestedGear, -1);
+    sv.d(o + PD_CAR_o_fuel, P.requestedFuel);
+    sv.f(o + PD_CAR_o_pointCacheY, -10000.0f);
+    sv.i(o + PD_CAR_o_acSeqDone, 1);
+    sv.d(o + PD_CAR_o_reqTimeout, 200); sv.i(o + PD_CAR_o_reqGear, -1);
+    sv.d(o + PD_CAR_o_locClutch, 1.0); sv.d(o + PD_CAR_o_lastRatio, -1.0);
+    sv.i(o + PD_CAR_o_currentGear, 1);
+    sv.d(o + PD_CAR_o_validShiftRPMWindow, P.drivetrain.orgRpmWindow);
+    sv.f(o + PD_CAR_o_lifeLeft, 1000.0f); sv.f(o + PD_CAR_o_fuelPressure, 1.0f);
+}
+
+/* teleport: Car::teleportToSpline -> forceRotation + forcePosition (Car.cpp:1325-1340,1275-1308,1240-1273) */
+PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const SV& sv, int pointId, double physicsTime) {
+    CarCtx X; set_body_mass(X, P);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, X.b[i]);
+    load_car(sv, X.c);
+    CarS& c = X.c;
+    const PdFatPoint& pt = T.fat[pointId];
+    Body& C = X.b[PD_BODY_CHASSIS]; Body& Tk = X.b[PD_BODY_TANK];
+    /* forceRotation(heading) */
+    {
+        const V3 heading = v3(pt.forwardDir[0], pt.forwardDir[1], pt.forwardDir[2]);
+        const V3 ihed = heading * -1.0f;
+        const float vM13 = ihed.x, vM11 = -ihed.z, vM12 = 0;
+        const float v6 = sqrtf((vM12 * vM12) + (vM11 * vM11) + (vM13 * vM13));
+        const float s = 1.0f / v6;
+        const V3 ax = v3(vM11 * s, vM12 * s, vM13 * s), ay = v3(0, 1, 0), az = v3(-ihed.x, -ihed.y, -ihed.z);
+        set_rotation(ax, ay, az, C.fr.ax, C.fr.ay, C.fr.az, C.q);
+        Tk.fr.ax = C.fr.ax; Tk.fr.ay = C.fr.ay; Tk.fr.az = C.fr.az; Tk.q = C.q;
+    }
+    /* forcePosition(center) */
+    V3 bodyPos = v3(pt.center[0], pt.center[1], pt.center[2]);
+    {
+        const RayHit hit = ray_cast(T, bodyPos + v3(0, 10, 0), v3(0, -1, 0), 1000.0f);
+        if (hit.hit) bodyPos.y = hit.pos.y;
+        bodyPos.y += (P.baseCarHeight + 0.0f + 0.01f);
+    }
+    /* Car::reset (Car.cpp:385-410) */
+    c.waterT = 60; c.fuel = P.requestedFuel;
+    c.collisionFlag = 0; c.outOfTrackFlag = 0;
+    c.lastTrackPointTimestamp = (float)physicsTime;
+    c.nearestTrackPointId = 0; c.oldTrackPointId = 0; c.splinePointId = 0; c.trackLocation = 0; c.oldTrackLocation = 0;
+    c.prevEpisodeReward = c.totalReward; c.totalReward = 0; c.stepReward = 0; c.oldPointId = 0; c.oldSplinePointId = 0;
+    c.episodeSteps = 0;
+    body_stop(C); C.fr.p = bodyPos;
+    Tk.fr.p = to_world(C.fr, v3(P.fuelTankPos[0], P.fuelTankPos[1], P.fuelTankPos[2]));
+    /* susp->stop(); susp->attach() */
+    for (int s = 0; s < 2; ++s) { /* SuspensionStrut::setPositions (SuspensionStrut.cpp:188-223) */
+        const PdStrut& S = P.strut[s]; Body& H = X.b[PD_BODY_HUB0 + 2 * s]; Body& B = X.b[PD_BODY_STRUT0 + 2 * s];
+        body_stop(H);
+        set_rotation(C.fr.ax, C.fr.ay, C.fr.az, H.fr.ax, H.fr.ay, H.fr.az, H.q);   /* hub->setRotation(mxBody) */
+        H.fr.p = to_world(C.fr, v3(S.refPoint[0], S.refPoint[1], S.refPoint[2]));
+        const V3 vCarStrut = to_world(C.fr, v3(S.carStrut[0], S.carStrut[1], S.carStrut[2]));
+        const V3 vTyreStrut = to_world(H.fr, v3(S.tyreStrut[0], S.tyreStrut[1], S.tyreStrut[2]));
+        const V3 vNorm = norm(vTyreStrut - vCarStrut);
+        const V3 vM3 = C.fr.az * -1.0f;
+        const V3 vM3N = cross(vM3, vNorm);
+        const V3 vM3NN = norm(cross(vM3N, vNorm));
+        set_rotation(vM3NN, vM3N * -1.0f, vNorm * -1.0f, B.fr.ax, B.fr.ay, B.fr.az, B.q);
+        B.fr.p = (vNorm * S.strutBodyLength) * 0.5f + vCarStrut;
+        /* NB SuspensionStrut::stop() stops only the hub; the strut body keeps its velocity (reference behaviour) */
+    }
+    {
+        Body& A = X.b[PD_BODY_AXLE]; body_stop(A);
+        set_rotation(C.fr.ax, C.fr.ay, C.fr.az, A.fr.ax, A.fr.ay, A.fr.az, A.q);
+        A.fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
+    }
+    /* drivetrain->reset() (Drivetrain.cpp:154-167) */
+    c.clutchOpenState = 1; c.rootVel = 0; c.engineVel = 0; c.shaftLVel = 0; c.shaftRVel = 0; c.driveVel = 0;
+    c.reqRequest = 0; c.validShiftRPMWindow = P.drivetrain.orgRpmWindow; c.lifeLeft = 1000.0f;
+    /* tyres reset (Tyre.cpp:393-425) */
+    for (int w = 0; w < PD_NUM_WHEELS; ++w) {
+        const int o = PD_OFF_TYRE(w);
+        sv.f(o + PD_TYRE_o_slipAngleRAD, 0); sv.f(o + PD_TYRE_o_slipRatio, 0); sv.f(o + PD_TYRE_o_angularVelocity, 0);
+        sv.f(o + PD_TYRE_o_Fy, 0); sv.f(o + PD_TYRE_o_Fx, 0); sv.f(o + PD_TYRE_o_Mz, 0); sv.i(o + PD_TYRE_o_isLocked, 1);
+        sv.f(o + PD_TYRE_o_inflation, 1); sv.d(o + PD_TYRE_o_flatSpot, 0);
+        sv.f(o + PD_TYRE_o_dirtyLevel, 0); sv.f(o + PD_TYRE_o_feedbackTorque, 0); sv.d(o + PD_TYRE_o_virtualKM, 0);
+        sv.f(o + PD_TYRE_o_coreTemp, P.ambientTemperature); sv.d(o + PD_TYRE_o_phase, 0);
+        for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, P.ambientTemperature);
+    }
+    /* drivetrain->setCurrentGear(1, true) */
+    c.isGearGrinding = 0; c.currentGear = 1;
+    body_stop(C); body_stop(Tk);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, X.b[i]);
+    store_car(sv, c);
+}
+
+/* the tick */
+PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, float dt, double physicsTime) {
+    CarCtx X; X.dt = dt; X.time = physicsTime;
+    set_body_mass(X, P);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, X.b[i]);
+    load_car(sv, X.c);
+    CarS& c = X.c;
+    Body& C = X.b[PD_BODY_CHASSIS];
+
+    /* ---------------- Simulator::stepCars: stepPreCacheValues + Car::step ---------------- */
+    c.speed = len(C.v);
+    c.collisionFlag = 0; c.outOfTrackFlag = 0;
+    { /* Car.cpp:426-451 (car id 0): DBall ERP by speed; CFM = baseCFM = 1e-7 in both branches */
+        const float fVelSq = sqlen(C.v);
+        X.dballErp = (fVelSq >= 1.0f) ? 0.3f : 0.9f;
+        X.dballCfm = (fVelSq >= 1.0f) ? P.strut[0].baseCFM : 0.0000001f;
+    }
+    c.ctlSteer = tclampf(c.ctlSteer, -1.0f, 1.0f); c.ctlClutch = tclampf(c.ctlClutch, 0.0f, 1.0f); c.ctlBrake = tclampf(c.ctlBrake, 0.0f, 1.0f);
+    c.ctlHandBrake = tclampf(c.ctlHandBrake, 0.0f, 1.0f); c.ctlGas = tclampf(c.ctlGas, 0.0f, 1.0f);
+    {
+        const float target = c.ctlSteer;
+        if (c.smoothSteer) { const float diff = target - c.smoothSteerValue; c.smoothSteerValue += diff * P.scoring[PD_SV_SmoothSteerSpeed] * dt; c.ctlSteer = c.smoothSteerValue; }
+        else c.smoothSteerValue = target;
+    }
+    { /* fuel (Car.cpp:476-489) */
+        const float fRpmAbs = fabsf(engine_rpm(c));
+        const double fNewFuel = c.fuel - (fRpmAbs * dt * c.gasUsage) * (0.0f + 1.0) * P.fuelConsumptionK * 0.001 * P.fuelConsumptionRate;
+        c.fuel = fNewFuel;
+        if (fNewFuel > 0.0f) c.fuelPressure = 1.0f; else { c.fuel = 0; c.fuelPressure = 0; }
+    }
+    {
+        float sig = (P.steerLock * c.ctlSteer) / P.steerRatio;
+        if (!finitef(sig)) sig = 0;
+        c.finalSteerAngleSignal = sig;
+    }
+    bool bAllTyresLoaded = true;
+    for (int w = 0; w < 4; ++w) if (sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_load) <= 0.0f) { bAllTyresLoaded = false; break; }
+    autoclutch_step(P, X);
+    bool sleeping = false;
+    {
+        const float fAngVelSq = sqlen(C.w);
+        if (c.speed >= 0.5f || fAngVelSq >= 1.0f) c.sleepingFrames = 0;
+        else {
+            if (bAllTyresLoaded && (c.ctlGas <= 0.01f || c.ctlClutch <= 0.01f || c.currentGear == 1)) c.sleepingFrames++; else c.sleepingFrames = 0;
+            if (c.sleepingFrames > P.framesToSleep) { body_stop(C); body_stop(X.b[PD_BODY_TANK]); sleeping = true; }
+        }
+    }
+    {
+        const V3 vBodyVel = C.v;
+        const V3 vAccel = (vBodyVel - v3(c.lastVelX, c.lastVelY, c.lastVelZ)) * (1.0f / dt) * 0.10197838f;
+        c.lastVelX = vBodyVel.x; c.lastVelY = vBodyVel.y; c.lastVelZ = vBodyVel.z;
+        const V3 g = irot(C.fr, vAccel);
+        c.accGX = g.x; c.accGY = g.y; c.accGZ = g.z;
+    }
+    { /* stepThermalObjects (Car.cpp:624-634) + ThermalObject::step */
+        const float fRpm = engine_rpm(c);
+        float heat = 0;
+        if (fRpm > (P.engine.minimum * 0.8f)) { const float fLimiter = (float)(int)(P.engine.limiter * P.engine.limiterMultiplier); heat += (((fRpm / fLimiter) * 20.0f) * c.ctlGas) + 85.0f; }
+        const float fOneDivMass = 1.0f / P.waterTmass;
+        const float fCool = 1.0f - (P.waterCoolSpeedK * c.speed);
+        c.waterT += (((((fCool * P.ambientTemperature) - c.waterT) * fOneDivMass) * dt) * P.waterCoolFactor);
+        if (heat != 0.0f) c.waterT += ((((heat - c.waterT) * fOneDivMass) * dt) * P.waterHeatFactor);
+    }
+
+    /* ---------------- stepComponents ---------------- */
+    float brakeT[4], handT[4];
+    brakes_step(P.brakes, c, brakeT, handT);
+    float travel[4], dspeed[4];
+    strut_step(P.strut[0], C, X.b[PD_BODY_HUB0], travel[0], dspeed[0]);
+    strut_step(P.strut[1], C, X.b[PD_BODY_HUB1], travel[1], dspeed[1]);
+    axle_step(P.axle, C, X.b[PD_BODY_AXLE], 0, travel[2], dspeed[2]);
+    axle_step(P.axle, C, X.b[PD_BODY_AXLE], 1, travel[3], dspeed[3]);
+    for (int w = 0; w < 4; ++w) {
+        sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspTravel, travel[w]); sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspDamperSpeed, dspeed[w]);
+    }
+    for (int w = 0; w < 4; ++w) {
+        if (w < 2) { Body& H = X.b[PD_BODY_HUB0 + 2 * w]; const Frame hf = strut_hub_frame(P.strut[w], H); tyre_step(P, T, w, X, sv, H, hf, brakeT[w], handT[w], sleeping); }
+        else { Body& A = X.b[PD_BODY_AXLE]; const Frame hf = axle_hub_frame(P.axle, A, w - 2); tyre_step(P, T, w, X, sv, A, hf, brakeT[w], handT[w], sleeping); }
+    }
+    aero_step(P, C);
+    { /* SteeringSystem::step -> setSteerLengthOffset -> reseatDistanceJointLocal (incl. its local->world->local round trip) */
+        const float steer = -c.finalSteerAngleSignal * P.steerLinearRatio;
+        for (int s = 0; s < 2; ++s) {
+            const PdStrut& S = P.strut[s];
+            const float sx = signf_(S.refPoint[0]);
+            const float offx = 0.0f + steer + (sx * S.toeOutLinear);
+            const V3 carSteer = v3(S.baseCarSteer[0] + offx, S.baseCarSteer[1], S.baseCarSteer[2]);
+            const Body& H = X.b[PD_BODY_HUB0 + 2 * s];
+            X.steerAnchor1[s] = to_local(C.fr, to_world(C.fr, carSteer));
+            X.steerAnchor2[s] = to_local(H.fr, to_world(H.fr, v3(S.tyreSteer[0], S.tyreSteer[1], S.tyreSteer[2])));
+        }
+    }
+    autoblip_step(P, X);
+    autoshift_step(P, X);
+    gearchanger_step(P, X);
+    drivetrain_step(P, X);
+    { /* driven wheels: angular velocity / lock state written by the drivetrain */
+        const int dl = (P.drivetrain.tractionType == 1) ? 0 : 2;
+        for (int w = dl; w < dl + 2; ++w) { sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_angularVelocity, X.wl[w].angularVelocity); sv.i(PD_OFF_TYRE(w) + PD_TYRE_o_isLocked, X.wl[w].isLocked); }
+    }
+    arb_step(P.arbK[0], C, X.b[PD_BODY_HUB0], X.b[PD_BODY_HUB0].fr.p, X.b[PD_BODY_HUB1], X.b[PD_BODY_HUB1].fr.p);
+    {
+        Body& A = X.b[PD_BODY_AXLE];
+        const Frame f0 = axle_hub_frame(P.axle, A, 0), f1 = axle_hub_frame(P.axle, A, 1);
+        arb_step(P.arbK[1], C, A, f0.p, A, f1.p);
+    }
+
+    /* ---------------- physics->step(dt): dWorldStep ---------------- */
+    world_step(P, X);
+
+    /* ---------------- Car::postStep ---------------- */
+    { /* updateTrackLocator (Car.cpp:717-771) */
+        const V3 bodyPos = C.fr.p;
+        const int nFat = T.info.nFatPoints;
+        if (P.nProbes > 0 && nFat > 0) {
+            /* Track::rayCastTrackBounds cache refresh (Track.cpp:505-510): only the first probe can trigger it */
+            const V3 cache = v3(c.pointCacheX, c.pointCacheY, c.pointCacheZ);
+            if (sqlen(cache - bodyPos) > 1.0f * 1.0f) { c.pointCacheX = bodyPos.x; c.pointCacheY = bodyPos.y; c.pointCacheZ = bodyPos.z; }
+        }
+        const V3 cachePos = v3(c.pointCacheX, c.pointCacheY, c.pointCacheZ);
+        const float nearR = (P.nProbes > 0) ? P.probeLength[0] : T.info.hashCellSize;
+        const float nearRSq = nearR * nearR;
+        /* probe rays */
+        float rax = bodyPos.x, raz = bodyPos.z;
+        float rbx[PD_MAX_PROBES], rbz[PD_MAX_PROBES], best[PD_MAX_PROBES];
+        for (int r = 0; r < P.nProbes; ++r) {
+            const V3 rayStart = to_world(C.fr, v3(0, 0, 0));
+            const V3 rayEndL = to_world(C.fr, v3(P.probeDir[r][0], P.probeDir[r][1], P.probeDir[r][2]) * P.probeLength[r]);
+            const V3 dir = norm(rayEndL - rayStart);
+            const V3 rayEnd = rayStart + dir * (P.probeLength[r] * 1.1f);
+            rax = rayStart.x; raz = rayStart.z;
+            rbx[r] = rayEnd.x; rbz[r] = rayEnd.z; best[r] = FLT_MAX;
+        }
+        float bestDistSq = FLT_MAX; int bestPoint = 0;
+        for (int id = 0; id < nFat; ++id) {
+            const PdFatPoint& f = T.fat[id];
+            const V3 loc = v3(f.best[0], f.best[1], f.best[2]);
+            if (!(sqlen(cachePos - loc) < nearRSq)) continue;          /* VertexHash::queryNeighbours filter */
+            { const float dsq = sqlen(loc - bodyPos); if (bestDistSq > dsq) { bestDistSq = dsq; bestPoint = id; } }  /* getPointIdAtLocation */
+            const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
+            for (int r = 0; r < P.nProbes; ++r) {
+                float ix, iz;
+                if (line_intersection(rax, raz, rbx[r], rbz[r], f.left[0], f.left[2], g.left[0], g.left[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
+                if (line_intersection(rax, raz, rbx[r], rbz[r], f.right[0], f.right[2], g.right[0], g.right[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
+            }
+        }
+        for (int r = 0; r < P.nProbes; ++r) c.probes[r] = (best[r] != FLT_MAX) ? best[r] : P.probeLength[r];
+        if (c.nearestTrackPointId != bestPoint) { c.oldTrackPointId = c.nearestTrackPointId; c.nearestTrackPointId = bestPoint; c.lastTrackPointTimestamp = (float)physicsTime; }
+        c.oldTrackLocation = c.trackLocation; c.trackLocation = 0;
+        if (bestPoint >= 0 && bestPoint < nFat) {
+            if (nFat >= 5) { /* getDistanceAlongSplineAtLocation (Track.cpp:609-629) */
+                int prevId = bestPoint - 1; if (prevId < 0) prevId = nFat - 1;
+                int nextId = bestPoint + 1; if (nextId >= nFat) nextId = 0;
+                int prevId2 = prevId - 1; if (prevId2 < 0) prevId2 = nFat - 1;
+                int nextId2 = nextId + 1; if (nextId2 >= nFat) nextId2 = 0;
+                int sid; float sdist;
+                if (spline_nearest(T, bodyPos, prevId2 * T.info.interpolateStep, nextId2 * T.info.interpolateStep, sid, sdist)) {
+                    c.splinePointId = sid; c.trackLocation = tclampf(sdist / T.info.computedTrackLength, 0.0f, 1.0f);
+                }
+            }
+            const V3 bodyFrontDir = norm(C.fr.az);
+            const V3 bodyVelDir = norm(C.v);
+            const PdFatPoint& pt = T.fat[bestPoint];
+            const V3 fwd = v3(pt.forwardDir[0], pt.forwardDir[1], pt.forwardDir[2]);
+            c.bodyVsTrack = dot(bodyFrontDir, fwd);
+            if ((c.speed * 3.6f) > 3.0f) c.velocityVsTrack = dot(bodyVelDir, fwd); else c.velocityVsTrack = 0.0f;
+        }
+    }
+    { /* updateLookAhead (Car.cpp:775-798) */
+        const V3 up = v3(0, 1, 0);
+        const V3 curTrackDir = track_direction_at_distance(T, c.trackLocation);
+        const V3 bodyFrontDir = norm(C.fr.az);
+        const float driveDir = signf_(dot(bodyFrontDir, curTrackDir));
+        for (int i = 0; i < P.lookAheadCount && i < PD_LOOKAHEAD; ++i) {
+            const float distanceNorm = c.trackLocation + ((P.lookAheadStep * (float)(i + 1)) / T.info.computedTrackLength) * driveDir;
+            const V3 dir = track_direction_at_distance(T, distanceNorm);
+            c.lookAhead[i] = atan2f(dot(cross(dir, curTrackDir), up), dot(curTrackDir, dir));
+        }
+    }
+    /* ---- ScoringSystem::step (ScoringSystem.cpp:114-330) ---- */
+    {
+        /* validateDrift */
+        bool bInvalid = true; int nDirty = 0;
+        for (int w = 0; w < 4; ++w) { const int s = X.wl[w].surfaceId; if (s >= 0 && T.surfaces[s].dirtAdditiveK > 0.001f) nDirty++; }
+        if (nDirty <= 2) { if ((c.speed * 3.6f) >= 20.0f) { if (c.currentGear) bInvalid = false; } }
+        if (bInvalid) c.driftInvalid = 1;
+        const float fBeta = fabsf(beta_rad(C));
+        const float fSpeedKmh = c.speed * 3.6f;
+        bool earlyOut = false;
+        if (fSpeedKmh > 20.0f && fBeta > 0.13089749f) {
+            const V3 v = irot(C.fr, C.v);
+            if (!c.drifting) { c.lastDriftDirection = signf_(v.x); c.driftComboCounter = 1; c.driftInvalid = 0; c.instantDrift = 0.0f; }
+            c.currentDriftAngle = fBeta - 0.13089749f;
+            const float fSpeedMult = tclampf((fSpeedKmh - 20.0f) * 0.015384615f, 0.0f, 2.0f);
+            c.currentSpeedMultiplier = fSpeedMult;
+            int nDrifty = 0;
+            for (int w = 0; w < 4; ++w) {
+                const int s = X.wl[w].surfaceId;
+                if (s >= 0 && fabsf(X.wl[w].angularVelocity) > 4.0 && fabsf(X.wl[w].slipRatio) > 0.8f && X.wl[w].load > 10.0 && T.surfaces[s].gripMod >= 0.9f) nDrifty++;
+            }
+            c.driftExtreme = nDrifty > 1;
+            float fDelta = fSpeedMult * c.currentDriftAngle;
+            if (c.driftExtreme) fDelta *= 2.0f;
+            c.instantDriftDelta = fDelta; c.instantDrift += fDelta;
+            if (fabsf(v.x) > 4.0f) {
+                const float fDir = signf_(v.x);
+                if (c.lastDriftDirection != fDir && fBeta > 0.26179498f) { c.instantDrift += 50.0f; c.driftComboCounter++; c.lastDriftDirection = fDir; }
+            }
+            c.drifting = 1; c.driftStraightTimer = 0.0f;
+        }
+        if (c.drifting) {
+            if (fSpeedKmh > 20.0f && fBeta < 0.065448746f) c.driftStraightTimer += dt; else c.driftStraightTimer = 0.0f;
+            if (c.driftInvalid) { c.currentDriftAngle = 0; c.currentSpeedMultiplier = 0; c.driftExtreme = 0; c.drifting = 0; c.instantDrift = 0; c.driftComboCounter = 0; earlyOut = true; }
+            else if (c.driftStraightTimer > 1.0f) { c.driftComboCounter = 0; c.driftPoints += c.instantDrift; c.drifting = 0; c.instantDrift = 0.0f; }
+        }
+        if (!earlyOut && c.driftInvalid) { c.currentDriftAngle = 0; c.currentSpeedMultiplier = 0; c.driftExtreme = 0; c.drifting = 0; c.instantDrift = 0; c.driftComboCounter = 0; }
+    }
+    { /* computeAgentReward (ScoringSystem.cpp:129-248) */
+        const float* SVv = P.scoring;
+        float reward = 0.0f;
+        const float curRpm = car_engine_rpm(c);
+        const float maxRpm = (float)(int)(P.engine.limiter * P.engine.limiterMultiplier);
+        if (c.oldPointId < c.nearestTrackPointId || (c.nearestTrackPointId == 0 && c.oldPointId != c.nearestTrackPointId)) { c.oldPointId = c.nearestTrackPointId; reward += SVv[PD_SV_TravelBonus]; }
+        if (c.oldSplinePointId < c.splinePointId || (c.splinePointId == 0 && c.oldSplinePointId != c.splinePointId)) { c.oldSplinePointId = c.splinePointId; reward += SVv[PD_SV_TravelSplineBonus]; }
+        reward += SVv[PD_SV_DriftBonus] * c.instantDriftDelta;
+        reward += SVv[PD_SV_SpeedBonus] * linscalef(c.speed * 3.6f, SVv[PD_SV_MinBonusSpeed], SVv[PD_SV_MaxBonusSpeed], 0.0f, 1.0f);
+        reward += SVv[PD_SV_ThrottleBonus] * linscalef(c.ctlGas, 0.0f, 1.0f, 0.0f, 1.0f);
+        reward += SVv[PD_SV_EngineRpmBonus] * linscalef(curRpm, 0.0f, maxRpm, 0.0f, 1.0f);
+        if (curRpm < SVv[PD_SV_StallRpm]) reward -= SVv[PD_SV_StallPenalty];
+        if (c.isGearGrinding) reward -= SVv[PD_SV_GearGrindPenalty];
+        if (P.nProbes > 0) {
+            float closest = FLT_MAX;
+            for (int i = 0; i < P.nProbes; ++i) { const float d = c.probes[i]; if (closest > d && d > 0.0f) closest = d; }
+            if (closest < SVv[PD_SV_ApproachDistance]) reward -= SVv[PD_SV_ObstApproachPenalty] * (1.0f - linscalef(closest, SVv[PD_SV_CriticalDistance], SVv[PD_SV_ApproachDistance], 0.0f, 1.0f));
+        }
+        if (c.collisionFlag) reward -= SVv[PD_SV_CollisionPenalty];
+        const int tp = c.nearestTrackPointId;
+        if (tp >= 0 && tp < T.info.nFatPoints) {
+            const PdFatPoint& pt = T.fat[tp];
+            if (len(C.fr.p - v3(pt.center[0], pt.center[1], pt.center[2])) > T.info.computedTrackWidth * SVv[PD_SV_OutOfTrackThreshold]) { c.outOfTrackFlag = 1; reward -= SVv[PD_SV_OffTrackPenalty]; }
+            const float x = c.bodyVsTrack;
+            const float thresh = tclampf(SVv[PD_SV_DirectionThreshold], 0.1f, 1.0f);
+            if (x > thresh) reward += SVv[PD_SV_DirectionBonus] * linscalef(x, thresh, 1.0f, 0.0f, 1.0f);
+            else reward -= SVv[PD_SV_DirectionPenalty] * (1.0f - linscalef(x, -1.0f, thresh, 0.0f, 1.0f));
+        }
+        c.stepReward = reward; c.totalReward += reward;
+    }
+    c.episodeSteps++; c.thermalPrimed = 1;
+    {
+        int bad = 0;
+        for (int i = 0; i < PD_NUM_BODIES; ++i) { const Body& b = X.b[i]; if (!(finitef(b.fr.p.x) && finitef(b.fr.p.y) && finitef(b.fr.p.z) && finitef(b.v.x) && finitef(b.v.y) && finitef(b.v.z) && finitef(b.w.x) && finitef(b.w.y) && finitef(b.w.z) && finitef(b.q.w))) bad = 1; }
+        if (bad) c.nanFlag = 1;
+    }
+    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, X.b[i]);
+    store_car(sv, c);
+}
+
+/* observation vector of pyprojectd/projectd_env.py:237-275 */
+PD_HD void car_observe(const SV& sv, float* obs /* 24, stride 1 */) {
+    Body C; load_body(sv, PD_BODY_CHASSIS, C);
+    const V3 lv = irot(C.fr, C.v), lw = irot(C.fr, C.w);
+    obs[0] = lv.x; obs[1] = lv.y; obs[2] = lv.z; obs[3] = lw.x; obs[4] = lw.y; obs[5] = lw.z;
+    for (int w = 0; w < 4; ++w) obs[6 + w] = sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_ndSlip);
+    obs[10] = sv.f(PD_OFF_CAR + PD_CAR_o_bodyVsTrack); obs[11] = sv.f(PD_OFF_CAR + PD_CAR_o_velocityVsTrack);
+    for (int i = 0; i < 5; ++i) obs[12 + i] = sv.f(PD_OFF_LOOKAHEAD + i);
+    for (int i = 0; i < 7; ++i) obs[17 + i] = sv.f(PD_OFF_PROBES + i);
+}
+
+} // namespace pd

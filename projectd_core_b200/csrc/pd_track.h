@@ -1,0 +1,136 @@
+/*
+ * pd_track.h -- track queries of the hot path: wheel / teleport ray casts against the static track mesh
+ *  and the spline-side queries of Car::postStep (row A10).
+ *
+ * Reference anchors: Physics/ODE/PhysicsEngineODE.cpp:168-214 (ray vs every static geom, min depth),
+ * Physics/ODE/RayCasterODE.cpp:11-15 (first contact, back-face cull), Sim/Track.cpp:497-562
+ * (rayCastTrackBounds), :564-607 (point id / direction at distance), :579-596 (nearest point),
+ * :609-699 (distance along spline), Core/Spline3d.cpp:34-75 (find_nearest_point),
+ * Core/VertexHash.h:45-104 (the 27-cell neighbour query that feeds Track::nearbyPoints).
+ *
+ * Data layout: all triangles of all static meshes (track + wall blobs of surfaces.bin) live in ONE
+ * bounding-volume hierarchy built once on the host (host/bvh_build.cpp).  Leaves hold triangles as
+ * (v0, e1 = v1-v0, e2 = v2-v0) + the index of the blob (= Surface) they came from, so the
+ * Moller-Trumbore test below starts from exactly the edge vectors OPCODE computes.  The whole structure
+ * (driftplayground: 112 411 triangles = 4.5 MB, nodes 1.8 MB) is read-only and far smaller than the
+ * 126 MB L2, so after the first touch every ray is served from L2 / L1.
+ */
+#pragma once
+#include "pd_state_io.h"
+#include <float.h>
+
+namespace pd {
+
+struct BvhNode {          /* 32 bytes */
+    float bmin[3]; int32_t left;    /* inner: left child (right = left + 1); leaf: first triangle */
+    float bmax[3]; int32_t count;   /* 0 = inner node, > 0 = number of triangles in the leaf */
+};
+
+struct TrackDev {
+    const BvhNode* nodes;
+    const float* tris;        /* 9 floats per triangle: v0, e1, e2 (leaf order) */
+    const int32_t* triSurf;   /* surface (blob) index per triangle */
+    const PdSurface* surfaces;
+    const PdFatPoint* fat;
+    const float* splineXYZ;   /* interpolated B-spline nodes */
+    const float* splineDist;  /* cumulative length at node */
+    PdTrackInfo info;
+};
+
+struct RayHit {
+    int hit;        /* hasContact */
+    V3 pos, normal;
+    int surface;
+};
+
+/* Closest front-facing triangle along (o, d) within `length`.
+ * Triangle test = OPCODE RayTriOverlap with culling (det >= 1e-6, 0 <= u <= det, v >= 0, u+v <= det,
+ * t >= 0, t < maxDist); contact = ODE dCollideRTL after the ray/trimesh swap: pos = o + d*t,
+ * normal = normalize(e1 x e2). */
+PD_HDN RayHit ray_cast(const TrackDev& T, V3 o, V3 d, float length) {
+    RayHit h; h.hit = 0; h.surface = -1; h.pos = v3(0, 0, 0); h.normal = v3(0, 0, 0);
+    if (T.info.nNodes <= 0) return h;
+    float best = -1.0f; V3 bestN = v3(0, 0, 0); int bestS = -1;
+    const V3 inv = v3(d.x != 0.0f ? 1.0f / d.x : 0.0f, d.y != 0.0f ? 1.0f / d.y : 0.0f, d.z != 0.0f ? 1.0f / d.z : 0.0f);
+    int stack[48]; int sp = 0; stack[sp++] = 0;
+    while (sp > 0) {
+        const BvhNode nd = T.nodes[stack[--sp]];
+        /* slab test against [0, min(length, best)] */
+        float t0 = 0.0f, t1 = (best >= 0.0f) ? best : length;
+        bool miss = false;
+        if (d.x != 0.0f) { float a = (nd.bmin[0] - o.x) * inv.x, b = (nd.bmax[0] - o.x) * inv.x; t0 = tmaxf(t0, tminf(a, b)); t1 = tminf(t1, tmaxf(a, b)); } else if (o.x < nd.bmin[0] || o.x > nd.bmax[0]) miss = true;
+        if (d.y != 0.0f) { float a = (nd.bmin[1] - o.y) * inv.y, b = (nd.bmax[1] - o.y) * inv.y; t0 = tmaxf(t0, tminf(a, b)); t1 = tminf(t1, tmaxf(a, b)); } else if (o.y < nd.bmin[1] || o.y > nd.bmax[1]) miss = true;
+        if (d.z != 0.0f) { float a = (nd.bmin[2] - o.z) * inv.z, b = (nd.bmax[2] - o.z) * inv.z; t0 = tmaxf(t0, tminf(a, b)); t1 = tminf(t1, tmaxf(a, b)); } else if (o.z < nd.bmin[2] || o.z > nd.bmax[2]) miss = true;
+        if (miss || t0 > t1) continue;
+        if (nd.count == 0) {
+            if (sp + 2 <= 48) { stack[sp++] = nd.left; stack[sp++] = nd.left + 1; }
+            continue;
+        }
+        for (int k = 0; k < nd.count; ++k) {
+            const int t = nd.left + k;
+            const float* p = T.tris + (size_t)t * 9;
+            const V3 v0 = v3(p[0], p[1], p[2]), e1 = v3(p[3], p[4], p[5]), e2 = v3(p[6], p[7], p[8]);
+            const V3 pvec = cross(d, e2);
+            const float det = dot(e1, pvec);
+            if (det < 0.000001f) continue;
+            const V3 tvec = o - v0;
+            const float u = dot(tvec, pvec);
+            if (u < 0.0f || u > det) continue;
+            const V3 qvec = cross(tvec, e1);
+            const float v = dot(d, qvec);
+            if (v < 0.0f || u + v > det) continue;
+            float dist = dot(e2, qvec);
+            if (dist < 0.0f) continue;
+            dist *= (1.0f / det);
+            if (!(dist < length)) continue;
+            if (best < 0.0f || dist < best) { best = dist; bestN = cross(e1, e2); bestS = T.triSurf[t]; }
+        }
+    }
+    if (best >= 0.0f) {
+        h.hit = 1; h.pos = v3(o.x + d.x * best, o.y + d.y * best, o.z + d.z * best);
+        h.normal = norm(bestN); h.surface = bestS;
+    }
+    return h;
+}
+
+/* Track.cpp:469-494 getLineIntersection */
+PD_HD bool line_intersection(float p0x, float p0y, float p1x, float p1y, float p2x, float p2y, float p3x, float p3y, float& ix, float& iy) {
+    float s1x = p1x - p0x, s1y = p1y - p0y, s2x = p3x - p2x, s2y = p3y - p2y;
+    float s = (-s1y * (p0x - p2x) + s1x * (p0y - p2y)) / (-s2x * s1y + s1x * s2y);
+    float t = (s2x * (p0y - p2y) - s2y * (p0x - p2x)) / (-s2x * s1y + s1x * s2y);
+    if (s >= 0 && s <= 1 && t >= 0 && t <= 1) { ix = p0x + (t * s1x); iy = p0y + (t * s1y); return true; }
+    return false;
+}
+
+/* Track::getPointIdAtDistance (Track.cpp:564-577) */
+PD_HD int point_id_at_distance(const TrackDev& T, float distanceNorm) {
+    const int n = T.info.nFatPoints;
+    if (!n) return 0;
+    if (distanceNorm < 0.0f) distanceNorm += 1.0f; else if (distanceNorm > 1.0f) distanceNorm -= 1.0f;
+    return (int)(tclampf(distanceNorm, 0.0f, 1.0f) * (float)(n - 1));
+}
+PD_HD V3 track_direction_at_distance(const TrackDev& T, float distanceNorm) {
+    const int id = point_id_at_distance(T, distanceNorm);
+    if (id < T.info.nFatPoints) { const PdFatPoint& f = T.fat[id]; return v3(f.forwardDir[0], f.forwardDir[1], f.forwardDir[2]); }
+    return v3(0, 0, 0);
+}
+
+/* Spline3d::find_nearest_point (Core/Spline3d.cpp:34-75) restricted as Track.cpp:609-629 calls it */
+PD_HD bool spline_nearest(const TrackDev& T, V3 pos, int seg1, int seg2, int& outId, float& outDist) {
+    int best_id = 0; float best_dist = FLT_MAX, spline_dist = 0; bool found = false;
+    const int np = T.info.nSplineNodes;
+    if (seg1 >= np) seg1 = 0;
+    if (seg2 >= np) seg2 = 0;
+    if (!seg1 && !seg2) seg2 = np;
+    int id = seg1;
+    while (id != seg2) {
+        const float* p = T.splineXYZ + (size_t)id * 3;
+        const float d = sqlen(pos - v3(p[0], p[1], p[2]));
+        if (best_dist >= d) { best_dist = d; best_id = id; spline_dist = T.splineDist[id]; found = true; }
+        ++id; if (id >= np) id = 0;
+    }
+    outId = best_id; outDist = spline_dist;
+    return found;
+}
+
+} // namespace pd

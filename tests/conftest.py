@@ -1,0 +1,80 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_cuda():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The compiled reference (oracle/_ref/libpdref.so + its content copy)."""
+    import pdref
+    if not pdref.available():
+        if os.path.isdir("/root/reference/src/ProjectD"):
+            subprocess.check_call(["make", "-j8"], cwd=os.path.join(ROOT, "oracle"))
+            subprocess.check_call(["make", "content"], cwd=os.path.join(ROOT, "oracle"))
+        else:
+            pytest.skip("oracle/_ref not built and /root/reference absent")
+    return pdref
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    """ctypes handle of tests/hostsim/libpdhostsim.so (device functions compiled for the host, debugging aid)."""
+    import ctypes
+    path = os.path.join(ROOT, "tests", "hostsim", "libpdhostsim.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make"], cwd=os.path.join(ROOT, "tests", "hostsim"))
+    H = ctypes.CDLL(path)
+    vp, cp, f, i, d = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_float, ctypes.c_int, ctypes.c_double
+    H.hs_create.restype = vp; H.hs_create.argtypes = [cp, cp, cp]
+    H.hs_destroy.argtypes = [vp]
+    H.hs_set_tune.argtypes = [vp, cp, f]
+    H.hs_set_scoring_var.argtypes = [vp, cp, f]
+    H.hs_set_assists.argtypes = [vp, i, i, i]
+    H.hs_get_params.argtypes = [vp, vp]
+    H.hs_get_track_info.argtypes = [vp, vp]
+    H.hs_get_spline_nodes.argtypes = [vp, vp, vp]
+    H.hs_tick.argtypes = [vp, vp, f, d]
+    H.hs_teleport_point.argtypes = [vp, vp, i, d]
+    H.hs_point_id_at_distance.argtypes = [vp, f]
+    H.hs_raycast.argtypes = [vp, i, vp, vp]
+    H.hs_sctm_solve.argtypes = [vp, i, i, vp, vp]
+    return H
+
+
+@pytest.fixture(scope="session")
+def hostsim_env(hostsim, oracle):
+    h = hostsim.hs_create(oracle.BASE_PATH.encode(), b"driftplayground", b"ks_toyota_ae86_drift")
+    assert h
+    hostsim.hs_set_assists(h, 1, 1, 1)
+    for k, v in oracle.ENV_TUNES.items():
+        hostsim.hs_set_tune(h, k.encode(), v)
+    for k, v in oracle.ENV_SCORING.items():
+        hostsim.hs_set_scoring_var(h, k.encode(), v)
+    return h

@@ -1,0 +1,60 @@
+/*
+ * tests/hostsim/hostsim.cpp -- DEBUGGING AID, test-only (never shipped, never loaded by the product).
+ *
+ * Compiles the product's device functions (projectd_core_b200/csrc/pd_tick.h, PD_HD = plain inline under
+ * g++) for the host so that the kernels' arithmetic can be single-stepped against the oracle on a box
+ * without a GPU.  The product path is the CUDA library (libpd_b200.so); it has no CPU fallback and does not
+ * link this file.
+ */
+#include "../../projectd_core_b200/csrc/pd_tick.h"
+#include "../../projectd_core_b200/csrc/host/pd_host.h"
+#include <cstdio>
+
+struct HS {
+    pdh::CarModel car;
+    pdh::TrackModel track;
+    pd::TrackDev dev;
+    void bind() {
+        dev.nodes = (const pd::BvhNode*)track.nodes.data(); dev.tris = track.tris.data(); dev.triSurf = track.triSurf.data();
+        dev.surfaces = track.surfaces.data(); dev.fat = track.fat.data(); dev.splineXYZ = track.splineXYZ.data(); dev.splineDist = track.splineDist.data();
+        dev.info = track.info;
+    }
+};
+
+extern "C" {
+void* hs_create(const char* base, const char* track, const char* car) {
+    HS* h = new HS();
+    try { pdh::load_car(base, car, h->car); pdh::load_track(base, track, h->track); h->bind(); }
+    catch (const std::exception& e) { fprintf(stderr, "[hostsim] %s\n", e.what()); delete h; return nullptr; }
+    return h;
+}
+void hs_destroy(void* h) { delete (HS*)h; }
+void hs_set_tune(void* h, const char* name, float v) { ((HS*)h)->car.setTune(name, v); }
+void hs_set_scoring_var(void* h, const char* name, float v) { ((HS*)h)->car.setScoringVar(name, v); }
+void hs_set_assists(void* hv, int ac, int as, int ab) { auto& A = ((HS*)hv)->car.P.assists; A.acUseAutoOnStart = ac; A.acUseAutoOnChange = ac; A.asIsActive = as; A.blipIsActive = ab; }
+int hs_params_bytes() { return (int)sizeof(PdCarParams); }
+void hs_get_params(void* h, PdCarParams* out) { *out = ((HS*)h)->car.P; }
+void hs_set_params(void* h, const PdCarParams* in) { ((HS*)h)->car.P = *in; }
+void hs_get_track_info(void* h, PdTrackInfo* out) { *out = ((HS*)h)->track.info; }
+void hs_get_spline_nodes(void* hv, float* xyz, float* dist) { HS* h = (HS*)hv; memcpy(xyz, h->track.splineXYZ.data(), h->track.splineXYZ.size() * 4); memcpy(dist, h->track.splineDist.data(), h->track.splineDist.size() * 4); }
+void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SV sv{rec, 1, 0}; pd::car_tick(h->car.P, h->dev, sv, dt, time); }
+void hs_teleport_point(void* hv, uint32_t* rec, int pointId, double time) { HS* h = (HS*)hv; pd::SV sv{rec, 1, 0}; pd::car_teleport_to_point(h->car.P, h->dev, sv, pointId, time); }
+int hs_point_id_at_distance(void* hv, float d) { return pd::point_id_at_distance(((HS*)hv)->dev, d); }
+void hs_raycast(void* hv, int n, const float* in, float* out) {
+    HS* h = (HS*)hv;
+    for (int i = 0; i < n; ++i) {
+        const float* p = in + i * 7; float* q = out + i * 8;
+        pd::RayHit r = pd::ray_cast(h->dev, pd::v3(p[0], p[1], p[2]), pd::v3(p[3], p[4], p[5]), p[6]);
+        q[0] = (float)r.hit; q[1] = r.pos.x; q[2] = r.pos.y; q[3] = r.pos.z; q[4] = r.normal.x; q[5] = r.normal.y; q[6] = r.normal.z; q[7] = (float)r.surface;
+    }
+}
+void hs_sctm_solve(void* hv, int wheel, int n, const float* in, float* out) {
+    HS* h = (HS*)hv;
+    for (int i = 0; i < n; ++i) {
+        const float* p = in + i * 9; pd::TmIn t;
+        t.load = p[0]; t.slipAngleRAD = p[1]; t.slipRatio = p[2]; t.camberRAD = p[3]; t.speed = p[4]; t.u = p[5]; t.cpLength = p[6]; t.pressureRatio = p[7]; t.blister = p[8]; t.grain = 0;
+        pd::TmOut o = pd::sctm_solve(h->car.P.tyre[wheel], t);
+        float* q = out + i * 7; q[0] = o.Fy; q[1] = o.Fx; q[2] = o.Mz; q[3] = o.trail; q[4] = o.ndSlip; q[5] = o.Dy; q[6] = o.Dx;
+    }
+}
+}
