@@ -192,6 +192,13 @@ typedef struct PdTrackInfo {
     float computedTrackLength, computedTrackWidth, dynamicGripLevel, hashCellSize;
 } PdTrackInfo;
 
+/* uniform x-z grid over the track's boundary polylines and spline points: an INDEX only (it prunes the
+ * candidates of Track::rayCastTrackBounds / getPointIdAtLocation, it does not change their results) */
+typedef struct PdBoundGrid {
+    float ox, oz, cell, invCell;
+    int32_t nx, nz, pad0, pad1;
+} PdBoundGrid;
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,9 @@ struct TrackModel {
     std::vector<PdFatPoint> fat;
     std::vector<float> fatDist;       /* Track::fatPointDistances */
     std::vector<float> splineXYZ, splineDist;
+    PdBoundGrid grid;
+    std::vector<int32_t> segStart, segItems;   /* CSR per cell: boundary segments, item = id * 2 + side (0 left, 1 right) */
+    std::vector<int32_t> ptStart, ptItems;     /* CSR per cell: fat point ids (by `best`) */
 };
 void load_track(const std::string& basePath, const std::string& name, TrackModel& out);
 /* synthetic track generator for config 4 (large mesh): closed loop of `nPoints` spline points, tessellated */

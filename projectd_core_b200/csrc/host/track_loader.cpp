@@ -108,6 +108,40 @@ static V3h bspline(float u, V3h P0, V3h P1, V3h P2, V3h P3) {
     return point;
 }
 
+/* index over boundary segments and spline points (see PdBoundGrid) */
+static void build_bound_grid(TrackModel& out) {
+    const int n = (int)out.fat.size();
+    PdBoundGrid& G = out.grid; memset(&G, 0, sizeof(G));
+    out.segStart.assign(1, 0); out.segItems.clear(); out.ptStart.assign(1, 0); out.ptItems.clear();
+    if (n == 0) return;
+    float x0 = 3.4e38f, x1 = -3.4e38f, z0 = 3.4e38f, z1 = -3.4e38f;
+    for (const PdFatPoint& f : out.fat)
+        for (const float* p : {f.best, f.left, f.right}) { x0 = std::min(x0, p[0]); x1 = std::max(x1, p[0]); z0 = std::min(z0, p[2]); z1 = std::max(z1, p[2]); }
+    G.cell = 8.0f; G.invCell = 1.0f / G.cell;
+    G.ox = x0 - 2.0f * G.cell; G.oz = z0 - 2.0f * G.cell;
+    G.nx = (int)ceilf((x1 - G.ox) * G.invCell) + 3; G.nz = (int)ceilf((z1 - G.oz) * G.invCell) + 3;
+    const size_t nc = (size_t)G.nx * G.nz;
+    std::vector<std::vector<int32_t>> seg(nc), pts(nc);
+    auto cx = [&](float x) { return std::max(0, std::min(G.nx - 1, (int)floorf((x - G.ox) * G.invCell))); };
+    auto cz = [&](float z) { return std::max(0, std::min(G.nz - 1, (int)floorf((z - G.oz) * G.invCell))); };
+    const float pad = 0.05f;   /* segments are listed in every cell their padded box touches */
+    for (int id = 0; id < n; ++id) {
+        const PdFatPoint& f = out.fat[id]; const PdFatPoint& g = out.fat[id + 1 < n ? id + 1 : 0];
+        for (int side = 0; side < 2; ++side) {
+            const float* a = side ? f.right : f.left; const float* b = side ? g.right : g.left;
+            const int ix0 = cx(std::min(a[0], b[0]) - pad), ix1 = cx(std::max(a[0], b[0]) + pad), iz0 = cz(std::min(a[2], b[2]) - pad), iz1 = cz(std::max(a[2], b[2]) + pad);
+            for (int iz = iz0; iz <= iz1; ++iz) for (int ix = ix0; ix <= ix1; ++ix) seg[(size_t)iz * G.nx + ix].push_back(id * 2 + side);
+        }
+        pts[(size_t)cz(f.best[2]) * G.nx + cx(f.best[0])].push_back(id);
+    }
+    out.segStart.resize(nc + 1); out.ptStart.resize(nc + 1);
+    for (size_t c = 0; c < nc; ++c) {
+        out.segStart[c] = (int32_t)out.segItems.size(); out.segItems.insert(out.segItems.end(), seg[c].begin(), seg[c].end());
+        out.ptStart[c] = (int32_t)out.ptItems.size(); out.ptItems.insert(out.ptItems.end(), pts[c].begin(), pts[c].end());
+    }
+    out.segStart[nc] = (int32_t)out.segItems.size(); out.ptStart[nc] = (int32_t)out.ptItems.size();
+}
+
 /* Track::initTrackPoints tail (Track.cpp:207-271) + BSpline3d::init_from_array */
 void finish_track_points(TrackModel& out, bool closedLoop, float cellSize) {
     const int n = (int)out.fat.size();
@@ -155,6 +189,7 @@ void finish_track_points(TrackModel& out, bool closedLoop, float cellSize) {
     for (size_t i = 0; i < nodes.size(); ++i) { out.splineXYZ[i * 3] = nodes[i].x; out.splineXYZ[i * 3 + 1] = nodes[i].y; out.splineXYZ[i * 3 + 2] = nodes[i].z; }
     out.info.nSplineNodes = (int32_t)nodes.size();
     out.info.computedTrackLength = out.splineDist.empty() ? length : out.splineDist.back();
+    build_bound_grid(out);
 }
 
 static std::vector<uint8_t> read_file(const std::string& path) {

@@ -222,6 +222,8 @@ template <class T> static int upload(pd_batch* b, const T** p, const std::vector
     *p = q; return PD_OK;
 }
 static inline int grid(int n, int block) { return (n + block - 1) / block; }
+/* small batches: one warp per block so that every SM gets work (148 SMs) */
+static inline int tick_block(int n) { return n <= 148 * 64 ? 32 : PD_BLOCK; }
 
 static int sync_params(pd_batch* b) {
     if (!b->paramsDirty) return PD_OK;
@@ -247,6 +249,11 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = upload(b, &b->dev.fat, b->track.fat))) return rc;
     if ((rc = upload(b, &b->dev.splineXYZ, b->track.splineXYZ))) return rc;
     if ((rc = upload(b, &b->dev.splineDist, b->track.splineDist))) return rc;
+    if ((rc = upload(b, &b->dev.segStart, b->track.segStart))) return rc;
+    if ((rc = upload(b, &b->dev.segItems, b->track.segItems))) return rc;
+    if ((rc = upload(b, &b->dev.ptStart, b->track.ptStart))) return rc;
+    if ((rc = upload(b, &b->dev.ptItems, b->track.ptItems))) return rc;
+    b->dev.grid = b->track.grid;
     b->dev.info = b->track.info;
     const size_t n = (size_t)n_envs;
     if ((rc = dalloc(b, &b->dState, n * PD_STATE_WORDS))) return rc;
@@ -366,7 +373,7 @@ int pd_step(pd_batch* b, float dt, int n_ticks) {
     if (!b || n_ticks < 0) return PD_ERR_ARG;
     int rc = sync_params(b); if (rc) return rc;
     for (int t = 0; t < n_ticks; ++t) {
-        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->n, dt, b->time, nullptr); b->launches++;
+        { const int blk = tick_block(b->n); k_tick<<<grid(b->n, blk), blk, 0, b->stream>>>(b->dP, b->dev, b->dState, b->n, dt, b->time, nullptr); b->launches++; }
         b->time += (double)dt; b->lastDt = dt;
     }
     CK(cudaGetLastError()); return PD_OK;
@@ -438,7 +445,7 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     const int n = b->n;
     float* rew = reward_dev ? reward_dev : b->dReward; int32_t* done = done_dev ? done_dev : b->dDone;
     k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, nullptr);
-    k_tick<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, nullptr);
+    k_tick<<<grid(n, tick_block(n)), tick_block(n), 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, nullptr);
     k_env_done<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, b->time, rew, done, b->dEnvReturn, b->dEnvLen, b->dStats);
     b->time += (double)dt; b->lastDt = dt;
     /* auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) + one zero-action tick */
@@ -446,7 +453,7 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, done, b->dPoints, b->time);
     k_clear_nan<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, done);
     k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, done);
-    k_tick<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, done);
+    k_tick<<<grid(n, tick_block(n)), tick_block(n), 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, done);
     k_observe<<<grid(n, 128), 128, 0, b->stream>>>(b->dState, n, obs_dev ? obs_dev : b->dObs);
     b->launches += 9;
     CK(cudaGetLastError()); return PD_OK;

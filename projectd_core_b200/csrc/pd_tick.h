@@ -283,16 +283,24 @@ PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, floa
             rbx[r] = rayEnd.x; rbz[r] = rayEnd.z; best[r] = FLT_MAX;
         }
         float bestDistSq = FLT_MAX; int bestPoint = 0;
-        for (int id = 0; id < nFat; ++id) {
-            const PdFatPoint& f = T.fat[id];
-            const V3 loc = v3(f.best[0], f.best[1], f.best[2]);
-            if (!(sqlen(cachePos - loc) < nearRSq)) continue;          /* VertexHash::queryNeighbours filter */
-            { const float dsq = sqlen(loc - bodyPos); if (bestDistSq > dsq) { bestDistSq = dsq; bestPoint = id; } }  /* getPointIdAtLocation */
-            const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
-            for (int r = 0; r < P.nProbes; ++r) {
-                float ix, iz;
-                if (line_intersection(rax, raz, rbx[r], rbz[r], f.left[0], f.left[2], g.left[0], g.left[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
-                if (line_intersection(rax, raz, rbx[r], rbz[r], f.right[0], f.right[2], g.right[0], g.right[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
+        bool needBrute = false;
+        for (int r = 0; r < P.nProbes; ++r) if (!probe_walk(T, rax, raz, rbx[r], rbz[r], cachePos, nearRSq, best[r])) needBrute = true;
+        const bool haveNearest = nearest_point_grid(T, bodyPos, cachePos, nearRSq, bestPoint);
+        if (needBrute || !haveNearest) {
+            /* exhaustive form of the reference (car far off the indexed area) */
+            bestPoint = 0;
+            for (int r = 0; r < P.nProbes; ++r) best[r] = FLT_MAX;
+            for (int id = 0; id < nFat; ++id) {
+                const PdFatPoint& f = T.fat[id];
+                const V3 loc = v3(f.best[0], f.best[1], f.best[2]);
+                if (!(sqlen(cachePos - loc) < nearRSq)) continue;          /* VertexHash::queryNeighbours filter */
+                { const float dsq = sqlen(loc - bodyPos); if (bestDistSq > dsq) { bestDistSq = dsq; bestPoint = id; } }  /* getPointIdAtLocation */
+                const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
+                for (int r = 0; r < P.nProbes; ++r) {
+                    float ix, iz;
+                    if (line_intersection(rax, raz, rbx[r], rbz[r], f.left[0], f.left[2], g.left[0], g.left[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
+                    if (line_intersection(rax, raz, rbx[r], rbz[r], f.right[0], f.right[2], g.right[0], g.right[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
+                }
             }
         }
         for (int r = 0; r < P.nProbes; ++r) c.probes[r] = (best[r] != FLT_MAX) ? best[r] : P.probeLength[r];

@@ -34,6 +34,9 @@ struct TrackDev {
     const PdFatPoint* fat;
     const float* splineXYZ;   /* interpolated B-spline nodes */
     const float* splineDist;  /* cumulative length at node */
+    const int32_t* segStart; const int32_t* segItems;   /* PdBoundGrid CSR: boundary segments per cell */
+    const int32_t* ptStart; const int32_t* ptItems;     /* PdBoundGrid CSR: spline points per cell */
+    PdBoundGrid grid;
     PdTrackInfo info;
 };
 
@@ -100,6 +103,74 @@ PD_HD bool line_intersection(float p0x, float p0y, float p1x, float p1y, float p
     float t = (s2x * (p0y - p2y) - s2y * (p0x - p2x)) / (-s2x * s1y + s1x * s2y);
     if (s >= 0 && s <= 1 && t >= 0 && t <= 1) { ix = p0x + (t * s1x); iy = p0y + (t * s1y); return true; }
     return false;
+}
+
+/* One probe of Track::rayCastTrackBounds (Track.cpp:497-562): closest intersection of the 2-D segment
+ * A -> B with the left / right boundary polylines of the NEAR points (|best - cachePos|^2 < nearRSq).
+ * The reference tests every near point; here a grid walk (2-D DDA from A) visits only the cells the probe
+ * crosses and stops once the best hit lies before the exit of the current cell.  Every candidate goes
+ * through the same line_intersection arithmetic, so the result equals the exhaustive minimum.
+ * Returns FLT_MAX when nothing is hit; returns false if the walk could not be used (start outside the grid). */
+PD_HDN bool probe_walk(const TrackDev& T, float ax, float az, float bx, float bz, V3 cachePos, float nearRSq, float& bestOut) {
+    const PdBoundGrid& G = T.grid;
+    const int nFat = T.info.nFatPoints;
+    float fx = (ax - G.ox) * G.invCell, fz = (az - G.oz) * G.invCell;
+    int ix = (int)floorf(fx), iz = (int)floorf(fz);
+    if (ix < 0 || iz < 0 || ix >= G.nx || iz >= G.nz) return false;
+    const float dx = bx - ax, dz = bz - az;
+    const float len = sqrtf(dx * dx + dz * dz);
+    const int sx = dx > 0 ? 1 : -1, sz = dz > 0 ? 1 : -1;
+    /* ray parameter (0..1) at which the walk leaves the current cell along x / z */
+    const float tdx = dx != 0.0f ? fabsf(G.cell / dx) : FLT_MAX, tdz = dz != 0.0f ? fabsf(G.cell / dz) : FLT_MAX;
+    float tmx = dx != 0.0f ? ((G.ox + (ix + (sx > 0 ? 1 : 0)) * G.cell) - ax) / dx : FLT_MAX;
+    float tmz = dz != 0.0f ? ((G.oz + (iz + (sz > 0 ? 1 : 0)) * G.cell) - az) / dz : FLT_MAX;
+    float best = FLT_MAX;
+    const float margin = 0.1f;   /* metres: cells are padded by 0.05 m, rounding is far below that */
+    for (int guard = 0; guard < 4096; ++guard) {
+        const int c = iz * G.nx + ix;
+        const int s0 = T.segStart[c], s1 = T.segStart[c + 1];
+        for (int k = s0; k < s1; ++k) {
+            const int item = T.segItems[k]; const int id = item >> 1;
+            const PdFatPoint& f = T.fat[id];
+            if (!(sqlen(cachePos - v3(f.best[0], f.best[1], f.best[2])) < nearRSq)) continue;
+            const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
+            const float* pa = (item & 1) ? f.right : f.left; const float* pb = (item & 1) ? g.right : g.left;
+            float jx, jz;
+            if (line_intersection(ax, az, bx, bz, pa[0], pa[2], pb[0], pb[2], jx, jz)) { const float ex = ax - jx, ez = az - jz; best = tminf(best, sqrtf(ex * ex + ez * ez)); }
+        }
+        const float tExit = tminf(tmx, tmz);
+        if (tExit >= 1.0f) break;                                   /* B lies in this cell */
+        if (best != FLT_MAX && best + margin < tExit * len) break;  /* nothing beyond the exit can be closer */
+        if (tmx < tmz) { ix += sx; tmx += tdx; } else { iz += sz; tmz += tdz; }
+        if (ix < 0 || iz < 0 || ix >= G.nx || iz >= G.nz) break;    /* left the grid: no boundary out there */
+    }
+    bestOut = best;
+    return true;
+}
+
+/* Track::getPointIdAtLocation over the near set (Track.cpp:579-596): ring search in the point grid around
+ * `pos`; falls back (returns false) when no point is found close enough to be provably the nearest. */
+PD_HDN bool nearest_point_grid(const TrackDev& T, V3 pos, V3 cachePos, float nearRSq, int& bestPoint) {
+    const PdBoundGrid& G = T.grid;
+    const int cx = (int)floorf((pos.x - G.ox) * G.invCell), cz = (int)floorf((pos.z - G.oz) * G.invCell);
+    if (cx < 1 || cz < 1 || cx >= G.nx - 1 || cz >= G.nz - 1) return false;
+    float bestDistSq = FLT_MAX; int best = -1;
+    for (int iz = cz - 1; iz <= cz + 1; ++iz)
+        for (int ix = cx - 1; ix <= cx + 1; ++ix) {
+            const int c = iz * G.nx + ix;
+            for (int k = T.ptStart[c]; k < T.ptStart[c + 1]; ++k) {
+                const int id = T.ptItems[k]; const PdFatPoint& f = T.fat[id];
+                const V3 loc = v3(f.best[0], f.best[1], f.best[2]);
+                if (!(sqlen(cachePos - loc) < nearRSq)) continue;
+                const float dsq = sqlen(loc - pos);
+                if (bestDistSq > dsq || (bestDistSq == dsq && id < best)) { bestDistSq = dsq; best = id; }
+            }
+        }
+    /* every point outside the 3x3 block is at least one cell (minus the position's offset in its cell) away in x-z */
+    const float fx = (pos.x - G.ox) - cx * G.cell, fz = (pos.z - G.oz) - cz * G.cell;
+    const float border = tminf(tminf(fx, G.cell - fx), tminf(fz, G.cell - fz)) + G.cell;
+    if (best < 0 || !(bestDistSq < (border - 0.01f) * (border - 0.01f))) return false;
+    bestPoint = best; return true;
 }
 
 /* Track::getPointIdAtDistance (Track.cpp:564-577) */

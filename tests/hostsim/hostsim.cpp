@@ -17,6 +17,7 @@ struct HS {
     void bind() {
         dev.nodes = (const pd::BvhNode*)track.nodes.data(); dev.tris = track.tris.data(); dev.triSurf = track.triSurf.data();
         dev.surfaces = track.surfaces.data(); dev.fat = track.fat.data(); dev.splineXYZ = track.splineXYZ.data(); dev.splineDist = track.splineDist.data();
+        dev.segStart = track.segStart.data(); dev.segItems = track.segItems.data(); dev.ptStart = track.ptStart.data(); dev.ptItems = track.ptItems.data(); dev.grid = track.grid;
         dev.info = track.info;
     }
 };
@@ -46,6 +47,36 @@ void hs_raycast(void* hv, int n, const float* in, float* out) {
         const float* p = in + i * 7; float* q = out + i * 8;
         pd::RayHit r = pd::ray_cast(h->dev, pd::v3(p[0], p[1], p[2]), pd::v3(p[3], p[4], p[5]), p[6]);
         q[0] = (float)r.hit; q[1] = r.pos.x; q[2] = r.pos.y; q[3] = r.pos.z; q[4] = r.normal.x; q[5] = r.normal.y; q[6] = r.normal.z; q[7] = (float)r.surface;
+    }
+}
+/* probes + nearest point: grid-indexed walk vs the reference's exhaustive loop, at arbitrary poses.
+ * in[n][4] = x, y, z, yaw ; walk / brute [n][8] = 7 probe distances + nearest point id */
+void hs_probe_compare(void* hv, int n, const float* in, float* walk, float* brute) {
+    HS* h = (HS*)hv; const pd::TrackDev& T = h->dev; const PdCarParams& P = h->car.P;
+    const int nFat = T.info.nFatPoints;
+    for (int i = 0; i < n; ++i) {
+        const float* p = in + i * 4; const pd::V3 pos = pd::v3(p[0], p[1], p[2]); const float yaw = p[3];
+        const float nearR = P.probeLength[0], nearRSq = nearR * nearR;
+        for (int r = 0; r < P.nProbes; ++r) {
+            const float dx = P.probeDir[r][0] * cosf(yaw) + P.probeDir[r][2] * sinf(yaw), dz = -P.probeDir[r][0] * sinf(yaw) + P.probeDir[r][2] * cosf(yaw);
+            const float bx = pos.x + dx * (P.probeLength[r] * 1.1f), bz = pos.z + dz * (P.probeLength[r] * 1.1f);
+            float w = FLT_MAX; const bool ok = pd::probe_walk(T, pos.x, pos.z, bx, bz, pos, nearRSq, w);
+            float b = FLT_MAX;
+            for (int id = 0; id < nFat; ++id) {
+                const PdFatPoint& f = T.fat[id];
+                if (!(pd::sqlen(pos - pd::v3(f.best[0], f.best[1], f.best[2])) < nearRSq)) continue;
+                const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
+                float ix, iz;
+                if (pd::line_intersection(pos.x, pos.z, bx, bz, f.left[0], f.left[2], g.left[0], g.left[2], ix, iz)) { const float ex = pos.x - ix, ez = pos.z - iz; b = pd::tminf(b, sqrtf(ex * ex + ez * ez)); }
+                if (pd::line_intersection(pos.x, pos.z, bx, bz, f.right[0], f.right[2], g.right[0], g.right[2], ix, iz)) { const float ex = pos.x - ix, ez = pos.z - iz; b = pd::tminf(b, sqrtf(ex * ex + ez * ez)); }
+            }
+            walk[i * 8 + r] = ok ? w : -1.0f; brute[i * 8 + r] = b;
+        }
+        int bp = -1; const bool ok = pd::nearest_point_grid(T, pos, pos, nearRSq, bp);
+        walk[i * 8 + 7] = ok ? (float)bp : -1.0f;
+        float bd = FLT_MAX; int bb = 0;
+        for (int id = 0; id < nFat; ++id) { const PdFatPoint& f = T.fat[id]; const pd::V3 loc = pd::v3(f.best[0], f.best[1], f.best[2]); if (!(pd::sqlen(pos - loc) < nearRSq)) continue; const float d = pd::sqlen(loc - pos); if (bd > d) { bd = d; bb = id; } }
+        brute[i * 8 + 7] = (float)bb;
     }
 }
 void hs_sctm_solve(void* hv, int wheel, int n, const float* in, float* out) {
