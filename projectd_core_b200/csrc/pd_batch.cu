@@ -18,7 +18,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
-#include "pd_tick.h"
+#include "pd_quad.h"
 #include "host/pd_host.h"
 #include "../../include/pd_batch.h"
 
@@ -33,6 +33,29 @@ __global__ void __launch_bounds__(PD_BLOCK) k_tick(const PdCarParams* __restrict
     if (mask && !mask[e]) return;
     SV sv{state, (size_t)n, (size_t)e};
     car_tick(*P, T, sv, dt, time);
+}
+
+/* exchange policy of pd_quad.h on the GPU: shuffles inside the quad, with the quad's own member mask */
+struct QuadShfl {
+    int lane; unsigned mask; int base;
+    __device__ __forceinline__ float get(float v, int src) const { return __shfl_sync(mask, v, base + src); }
+    __device__ __forceinline__ int get(int v, int src) const { return __shfl_sync(mask, v, base + src); }
+    __device__ __forceinline__ V3 get(V3 v, int src) const { return v3(get(v.x, src), get(v.y, src), get(v.z, src)); }
+    __device__ __forceinline__ float sum(float v) const { v += __shfl_xor_sync(mask, v, 1); v += __shfl_xor_sync(mask, v, 2); return v; }
+    __device__ __forceinline__ V3 sum(V3 v) const { return v3(sum(v.x), sum(v.y), sum(v.z)); }
+    __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
+};
+
+/* the tick, four lanes per car: thread t -> env t / 4, lane t % 4 */
+__global__ void __launch_bounds__(64) k_tick_quad(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = t >> 2;
+    if (e >= n) return;                       /* whole quads leave together */
+    if (mask && !mask[e]) return;
+    QuadShfl ex; ex.lane = t & 3; ex.base = (threadIdx.x & 31) & ~3; ex.mask = 0xFu << ex.base;
+    SV sv{state, (size_t)n, (size_t)e};
+    extern __shared__ float pd_smem[];          /* solver scratch: PD_GSCR_WORDS x blockDim, lane-interleaved */
+    car_tick_quad(*P, T, sv, dt, time, ex, pd_smem + threadIdx.x, (int)blockDim.x);
 }
 
 __global__ void k_broadcast(uint32_t* state, int n, const uint32_t* __restrict__ rec) {
@@ -223,7 +246,7 @@ template <class T> static int upload(pd_batch* b, const T** p, const std::vector
 }
 static inline int grid(int n, int block) { return (n + block - 1) / block; }
 /* small batches: one warp per block so that every SM gets work (148 SMs) */
-static inline int tick_block(int n) { return n <= 148 * 64 ? 32 : PD_BLOCK; }
+static inline int tick_block(int n) { return n * 4 <= 148 * 64 ? 32 : 64; }
 
 static int sync_params(pd_batch* b) {
     if (!b->paramsDirty) return PD_OK;
@@ -240,6 +263,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     CK(cudaSetDevice(device));
     b->n = n_envs; b->device = device;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaFuncSetAttribute(k_tick_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * PD_GSCR_WORDS * 4));
     int rc;
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
     { const std::vector<pd::BvhNode>& dummy = *reinterpret_cast<const std::vector<pd::BvhNode>*>(&b->track.nodes); if ((rc = upload(b, &b->dev.nodes, dummy))) return rc; }
@@ -373,7 +397,7 @@ int pd_step(pd_batch* b, float dt, int n_ticks) {
     if (!b || n_ticks < 0) return PD_ERR_ARG;
     int rc = sync_params(b); if (rc) return rc;
     for (int t = 0; t < n_ticks; ++t) {
-        { const int blk = tick_block(b->n); k_tick<<<grid(b->n, blk), blk, 0, b->stream>>>(b->dP, b->dev, b->dState, b->n, dt, b->time, nullptr); b->launches++; }
+        { const int blk = tick_block(b->n); k_tick_quad<<<grid(b->n * 4, blk), blk, (size_t)blk * PD_GSCR_WORDS * 4, b->stream>>>(b->dP, b->dev, b->dState, b->n, dt, b->time, nullptr); b->launches++; }
         b->time += (double)dt; b->lastDt = dt;
     }
     CK(cudaGetLastError()); return PD_OK;
@@ -445,7 +469,7 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     const int n = b->n;
     float* rew = reward_dev ? reward_dev : b->dReward; int32_t* done = done_dev ? done_dev : b->dDone;
     k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, nullptr);
-    k_tick<<<grid(n, tick_block(n)), tick_block(n), 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, nullptr);
+    k_tick_quad<<<grid(n * 4, tick_block(n)), tick_block(n), (size_t)tick_block(n) * PD_GSCR_WORDS * 4, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, nullptr);
     k_env_done<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, b->time, rew, done, b->dEnvReturn, b->dEnvLen, b->dStats);
     b->time += (double)dt; b->lastDt = dt;
     /* auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) + one zero-action tick */
@@ -453,7 +477,7 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, done, b->dPoints, b->time);
     k_clear_nan<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, done);
     k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, done);
-    k_tick<<<grid(n, tick_block(n)), tick_block(n), 0, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, done);
+    k_tick_quad<<<grid(n * 4, tick_block(n)), tick_block(n), (size_t)tick_block(n) * PD_GSCR_WORDS * 4, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, done);
     k_observe<<<grid(n, 128), 128, 0, b->stream>>>(b->dState, n, obs_dev ? obs_dev : b->dObs);
     b->launches += 9;
     CK(cudaGetLastError()); return PD_OK;

@@ -16,14 +16,13 @@ struct WheelLink {
     int isLocked, surfaceId;
 };
 
+/* car-level (non-body) context of one tick; every lane of a car's quad holds an identical copy */
 struct CarCtx {
-    Body b[PD_NUM_BODIES];
     CarS c;
     WheelLink wl[PD_NUM_WHEELS];
     float dt;
     double time;          /* Simulator::physicsTime */
     float dballErp, dballCfm;
-    V3 steerAnchor1[2], steerAnchor2[2];   /* re-seated steer-rod anchors (chassis / hub local) */
 };
 
 PD_HD float engine_rpm(const CarS& c) { return (float)((c.engineVel * 0.15915507) * 60.0); }   /* Drivetrain::getEngineRPM */
@@ -247,7 +246,7 @@ PD_HD TmOut sctm_solve(const PdTyre& P, const TmIn& tmi) {
 
 /* thermal grid neighbours in the reference's connection order (TyreThermalModel.cpp:28-58, buildTyre):
  * patch index p = element + stripe * 12 */
-PD_HD void thermal_step(const PdTyre& P, TyreS& t, float* inputT, float coreTInput, float dt, float angularSpeed, float camberRAD, float ambient, float carSpeed) {
+PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, float in0, float in1, float in2, float coreTInput, float dt, float angularSpeed, float camberRAD, float ambient, float carSpeed) {
     /* TyreThermalModel::step (TyreThermalModel.cpp:60-110) */
     float fPhase = (float)t.phase + (angularSpeed * dt);
     if (fPhase > 100000.0) fPhase = (float)(fPhase - 100000.0); else if (fPhase < 0.0) fPhase = (float)(fPhase + 100000.0);
@@ -259,10 +258,13 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float* inputT, float coreTInp
     const float fPctDt = P.patchCoreTransfer * dt;
     const float kSurf = P.surfaceTransfer * dt;
     const float kPatch = P.patchTransfer * dt;
+    PD_UNROLL
     for (int i = 0; i < PD_THERMAL_STRIPES; ++i) {
+        PD_UNROLL
         for (int j = 0; j < PD_THERMAL_ELEMENTS; ++j) {
             const int p = j + i * PD_THERMAL_ELEMENTS;
-            const float fInputT = inputT[p];
+            /* TyreThermalPatch::inputT: inBase everywhere, plus this tick's injection at element inElem of each stripe */
+            const float fInputT = (j == inElem) ? (inBase + (i == 0 ? in0 : (i == 1 ? in1 : in2))) : inBase;
             float fPatchT = t.T[p];
             if (fInputT <= ambient) fPatchT += ((ambient - fPatchT) * fAmbientFactor);
             else fPatchT += ((fInputT - fPatchT) * kSurf);
@@ -289,7 +291,10 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float* inputT, float coreTInp
         const float fNormCsk = tclampf((camberRAD * P.camberSpreadK), -1.0f, 1.0f);
         const float ph = (float)(t.phase * 0.1591549430964443);
         const int iElemY = ((int)(ph * PD_THERMAL_ELEMENTS)) % PD_THERMAL_ELEMENTS;
-        const float cp = ((((fNormCsk + 1.0f) * t.T[iElemY]) + t.T[iElemY + PD_THERMAL_ELEMENTS]) + ((1.0f - fNormCsk) * t.T[iElemY + 2 * PD_THERMAL_ELEMENTS])) * 0.33333334f;
+        float t0 = 0, t1 = 0, t2 = 0;
+        PD_UNROLL
+        for (int j = 0; j < PD_THERMAL_ELEMENTS; ++j) if (j == iElemY) { t0 = t.T[j]; t1 = t.T[j + PD_THERMAL_ELEMENTS]; t2 = t.T[j + 2 * PD_THERMAL_ELEMENTS]; }
+        const float cp = ((((fNormCsk + 1.0f) * t0) + t1) + ((1.0f - fNormCsk) * t2)) * 0.33333334f;
         const float fPracT = ((cp - coreTemp) * 0.25f) + coreTemp;
         t.practicalTemp = fPracT;
         t.thermalMultD = curve_value(P.performanceCurve, fPracT);
@@ -300,7 +305,7 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float* inputT, float coreTInp
  * updateLockedState/updateAngularSpeed (Tyre.cpp:725-752), stepThermalModel (:766-815), stepGrainBlister
  * (:829-922, consumption rate 0 branch), stepFlatSpot (:924-950).
  * `hubBody` is the body the wheel's forces go to (strut hub or the rigid axle). */
-PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, CarCtx& X, const SV& sv, Body& hubBody, const Frame& hubFrame, float brakeTorqueIn, float handBrakeIn, bool carSleeping) {
+PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, const CarCtx& X, const SV& sv, Body& hubBody, const Frame& hubFrame, Body& C, float brakeTorqueIn, float handBrakeIn, WheelLink& L) {
     const PdTyre& P = PP.tyre[w];
     const float dt = X.dt;
     TyreS t; load_tyre(sv, w, t);
@@ -446,7 +451,8 @@ PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, CarCtx& X
             }
             if (PP.mechanicalDamageRate > 0.0f) { /* stepPuncture (TyreForces.cpp:235-247) */
                 bool expl = false;
-                for (int i = 0; i < 3; ++i) { float s = 0; for (int j = 0; j < 12; ++j) s += t.T[j + i * 12]; if (s / 12.0f > P.explosionTemperature) expl = true; }
+                PD_UNROLL
+                for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) s += t.T[j + i * 12]; if (s / 12.0f > P.explosionTemperature) expl = true; }
                 if (expl) t.inflation = 0;
             }
             t.Mz = tmo.Mz;
@@ -481,7 +487,6 @@ PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, CarCtx& X
             t.ndSlip = tmo.ndSlip; t.D = fStaticDy;
         }
         if (surf.damping > 0.0f) { /* Tyre.cpp:591-602 */
-            Body& C = X.b[PD_BODY_CHASSIS];
             const V3 vForce = C.v * -(C.mass * surf.damping);
             add_force_at_rel_pos(C, vForce, v3(0, 0, 0));
         }
@@ -518,7 +523,6 @@ PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, CarCtx& X
         if (fabsf(t.angularVelocity) < 1.0f) t.angularVelocity *= 0.9f;
         /* stepRotationMatrix only spins the visual wheel matrix: not state of the path */
     }
-    (void)carSleeping;
     if (t.totalHubVelocity < 10.0f) t.slipFactor = fabsf(t.totalHubVelocity * 0.1f) * t.slipFactor;
 
     /* ---- stepThermalModel (Tyre.cpp:766-815) ---- */
@@ -533,22 +537,22 @@ PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, CarCtx& X
             if (fPressureDynamic >= 0.0) fThermalRollingK *= fScale;
             if (P.version < 5) t.thermalInput += (((fThermalRollingK * t.angularVelocity) * t.load) * 0.001f);
             if (P.version >= 6) t.thermalInput += ((((fScale * P.thermalRollingSurfaceK) * t.angularVelocity) * t.load) * 0.001f);
-            float inputT[PD_THERMAL_PATCHES];
-            for (int p = 0; p < PD_THERMAL_PATCHES; ++p) inputT[p] = X.c.thermalPrimed ? 0.0f : PP.ambientTemperature;
+            const float inBase = X.c.thermalPrimed ? 0.0f : PP.ambientTemperature;
+            int inElem; float in0, in1, in2;
             { /* addThermalInput (TyreThermalModel.cpp:147-166), phase BEFORE this tick's update */
                 const float xpos = t.camberRAD, pressureRel = (fPressureDynamic / fIdealPressure) - 1.0f, temp = t.thermalInput;
                 const float fNormXcs = tclampf((xpos * P.camberSpreadK), -1.0f, 1.0f);
                 const float ph = (float)(t.phase * 0.1591549430964443);
-                const int iElemY = ((int)(ph * PD_THERMAL_ELEMENTS)) % PD_THERMAL_ELEMENTS;
+                inElem = ((int)(ph * PD_THERMAL_ELEMENTS)) % PD_THERMAL_ELEMENTS;
                 const float fT = PP.roadTemperature + temp;
                 const float fPr1 = pressureRel * 0.1f, fPr2 = (pressureRel * -0.5f) + 1.0f;
-                inputT[iElemY] += ((((fNormXcs + 1.0f) - (fPr1 * 0.5f)) * fPr2) * fT);
-                inputT[iElemY + PD_THERMAL_ELEMENTS] += (((fPr1 + 1.0f) * fPr2) * fT);
-                inputT[iElemY + 2 * PD_THERMAL_ELEMENTS] += ((((1.0f - fNormXcs) - (fPr1 * 0.5f)) * fPr2) * fT);
+                in0 = ((((fNormXcs + 1.0f) - (fPr1 * 0.5f)) * fPr2) * fT);
+                in1 = (((fPr1 + 1.0f) * fPr2) * fT);
+                in2 = ((((1.0f - fNormXcs) - (fPr1 * 0.5f)) * fPr2) * fT);
             }
             float coreTInput = 0.0f;
             if (P.version >= 5) coreTInput += (((fThermalRollingK * t.angularVelocity) * t.load) * 0.001f);
-            thermal_step(P, t, inputT, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
+            thermal_step(P, t, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
         }
     }
     t.pressureDynamic = ((t.coreTemp - 26.0f) * P.pressureTemperatureGain) + t.pressureStatic;
@@ -564,7 +568,6 @@ PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, CarCtx& X
         }
     }
     store_tyre(sv, w, t);
-    WheelLink& L = X.wl[w];
     L.load = t.load; L.feedbackTorque = t.feedbackTorque; L.angularVelocity = t.angularVelocity;
     L.brakeTorque = t.brakeTorque; L.handBrakeTorque = t.handBrakeTorque; L.ndSlip = t.ndSlip; L.slipRatio = t.slipRatio;
     L.isLocked = t.isLocked; L.surfaceId = t.surfaceId;
@@ -816,7 +819,7 @@ PD_HD double dt_inertia_from_engine(const PdCarParams& PP, double ratio, double 
 
 /* Drivetrain::step + step2WD (Drivetrain.cpp:281-585) for RWD/FWD with LSD or spool.
  * dl / dr index the driven wheels (2,3 for RWD). */
-PD_HDN void drivetrain_step(const PdCarParams& PP, CarCtx& X) {
+PD_HDN float drivetrain_step(const PdCarParams& PP, CarCtx& X) {
     CarS& c = X.c; const PdDrivetrain& D = PP.drivetrain; const float dt = X.dt;
     const int dl = (D.tractionType == 1) ? 0 : 2, dr = dl + 1;
     WheelLink& tl = X.wl[dl]; WheelLink& tr = X.wl[dr];
@@ -912,9 +915,7 @@ PD_HDN void drivetrain_step(const PdCarParams& PP, CarCtx& X) {
     tl.angularVelocity = (float)c.shaftLVel; tr.angularVelocity = (float)c.shaftRVel;
     const float fGearTorque = (float)(c.locClutch * outTorque * curGearRatio);
     /* rear rigid axle: torque reaction about the body / axle local z (Drivetrain.cpp:547-563) */
-    const float fAxleTorq = fGearTorque * PP.axle.torqueReaction;
-    add_rel_torque(X.b[PD_BODY_CHASSIS], v3(0, 0, fAxleTorq));
-    add_rel_torque(X.b[PD_BODY_AXLE], v3(0, 0, -fAxleTorq));
+    return fGearTorque * PP.axle.torqueReaction;   /* +z local on the chassis, -z local on the axle */
 }
 
 } // namespace pd

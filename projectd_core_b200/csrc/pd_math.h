@@ -15,7 +15,9 @@
 #if defined(__CUDACC__)
 #define PD_HD __host__ __device__ __forceinline__
 #define PD_HDN __host__ __device__ __noinline__
+#define PD_UNROLL _Pragma("unroll")
 #else
+#define PD_UNROLL
 #define PD_HD inline
 #define PD_HDN inline
 #endif

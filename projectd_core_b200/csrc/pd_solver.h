@@ -109,152 +109,169 @@ PD_HD void plane_space(V3 n, V3& p, V3& q) {
     }
 }
 
-struct GroupSys {
-    int n, hasB;
-    float JA[PD_GMAX][6], JB[PD_GMAX][6], U[PD_GMAX][6];
-    float c[PD_GMAX], cfm[PD_GMAX];
+/* Scratch of one joint group, addressed with a stride so that the same code runs on
+ *   - shared memory interleaved over the lanes of a block (GPU: element k of lane t at base[k * blockDim + t],
+ *     i.e. every lane owns one bank column -> conflict-free), and
+ *   - a plain local array (host debugging build, stride 1).
+ * Layout (words): JA 11x6 | JB 11x6 | Y 11x7 ([U | r], later L^-1[U | r], column 6 ends as lambda) |
+ * D packed lower 66 (in place: unit-lower L below the diagonal) | dg 11 (cfm per row, then the D diagonal). */
+#define PD_GSCR_WORDS 286
+struct GScr {
+    float* p; int s; int n, hasB;
+    PD_HD float& JA(int i, int k) const { return p[(i * 6 + k) * s]; }
+    PD_HD float& JB(int i, int k) const { return p[(66 + i * 6 + k) * s]; }
+    PD_HD float& Y(int i, int k) const { return p[(132 + i * 7 + k) * s]; }
+    PD_HD float& D(int i, int j) const { return p[(209 + i * (i + 1) / 2 + j) * s]; }   /* j <= i */
+    PD_HD float& dg(int i) const { return p[(275 + i) * s]; }
 };
-struct GroupFac {
-    float L[PD_GMAX * (PD_GMAX - 1) / 2];   /* strict lower triangle of the unit-lower factor, row-major packed */
-    float d[PD_GMAX];                         /* diagonal of D */
-    float Y[PD_GMAX][7];                      /* L^-1 [U | r] */
-};
-PD_HD int tri(int i, int j) { return i * (i - 1) / 2 + j; }   /* j < i */
-
-PD_HD void zero_group(GroupSys& G, int n, int hasB, float cfm) {
+PD_HD void gset6(const GScr& G, int which, int i, V3 l, V3 a) {   /* which: 0 JA, 1 JB, 2 U (= Y cols 0..5) */
+    if (which == 0) { G.JA(i, 0) = l.x; G.JA(i, 1) = l.y; G.JA(i, 2) = l.z; G.JA(i, 3) = a.x; G.JA(i, 4) = a.y; G.JA(i, 5) = a.z; }
+    else if (which == 1) { G.JB(i, 0) = l.x; G.JB(i, 1) = l.y; G.JB(i, 2) = l.z; G.JB(i, 3) = a.x; G.JB(i, 4) = a.y; G.JB(i, 5) = a.z; }
+    else { G.Y(i, 0) = l.x; G.Y(i, 1) = l.y; G.Y(i, 2) = l.z; G.Y(i, 3) = a.x; G.Y(i, 4) = a.y; G.Y(i, 5) = a.z; }
+}
+PD_HD void zero_group(GScr& G, int n, int hasB, float cfm) {
     G.n = n; G.hasB = hasB;
-    for (int i = 0; i < n; ++i) { for (int k = 0; k < 6; ++k) { G.JA[i][k] = 0; G.JB[i][k] = 0; G.U[i][k] = 0; } G.c[i] = 0; G.cfm[i] = cfm; }
+    for (int i = 0; i < n; ++i) { for (int k = 0; k < 6; ++k) { G.JA(i, k) = 0; G.JB(i, k) = 0; G.Y(i, k) = 0; } G.Y(i, 6) = 0; G.dg(i) = cfm; }
+}
+/* dball row between the chassis (body 0 -> U) and an own body (body 1 -> JA); c goes to Y(i,6) */
+PD_HD void grow_dball(const GScr& G, int i, const Body& b0, const Body& b1, V3 anchor1, V3 anchor2, float target, float k, float cfm) {
+    float J0[6], J1[6], c;
+    row_dball(b0, b1, anchor1, anchor2, target, k, J0, J1, c);
+    for (int q = 0; q < 6; ++q) { G.Y(i, q) = J0[q]; G.JA(i, q) = J1[q]; }
+    G.Y(i, 6) = c; G.dg(i) = cfm;
 }
 
-/* group 0: fixed joint tank(b0) <-> chassis(b1)  (fixed.cpp getInfo2: rows 0-2 linear, 3-5 angular) */
-PD_HD void build_tank(const PdCarParams& P, const Body& T, const Body& C, float fps, GroupSys& G) {
+/* group "tank": fixed joint tank(b0) <-> chassis(b1)  (fixed.cpp getInfo2: rows 0-2 linear, 3-5 angular) */
+PD_HD void build_tank(const PdCarParams& P, const Body& T, const Body& C, float fps, GScr& G) {
     zero_group(G, 6, 0, P.worldCFM);
     const V3 ofs = rot(T.fr, v3(P.tankOffset[0], P.tankOffset[1], P.tankOffset[2]));
     /* linear rows: J1l = I, J1a = [ofs]x (rows), J2l = -I */
-    G.JA[0][0] = 1; G.JA[1][1] = 1; G.JA[2][2] = 1;
-    G.JA[0][4] = -ofs.z; G.JA[0][5] = ofs.y; G.JA[1][3] = ofs.z; G.JA[1][5] = -ofs.x; G.JA[2][3] = -ofs.y; G.JA[2][4] = ofs.x;
-    G.U[0][0] = -1; G.U[1][1] = -1; G.U[2][2] = -1;
+    G.JA(0, 0) = 1; G.JA(1, 1) = 1; G.JA(2, 2) = 1;
+    G.JA(0, 4) = -ofs.z; G.JA(0, 5) = ofs.y; G.JA(1, 3) = ofs.z; G.JA(1, 5) = -ofs.x; G.JA(2, 3) = -ofs.y; G.JA(2, 4) = ofs.x;
+    G.Y(0, 0) = -1; G.Y(1, 1) = -1; G.Y(2, 2) = -1;
     const float k = fps * P.worldERP;
-    G.c[0] = k * (C.fr.p.x - T.fr.p.x + ofs.x); G.c[1] = k * (C.fr.p.y - T.fr.p.y + ofs.y); G.c[2] = k * (C.fr.p.z - T.fr.p.z + ofs.z);
-    for (int i = 0; i < 3; ++i) { G.JA[3 + i][3 + i] = 1; G.U[3 + i][3 + i] = -1; }
+    G.Y(0, 6) = k * (C.fr.p.x - T.fr.p.x + ofs.x); G.Y(1, 6) = k * (C.fr.p.y - T.fr.p.y + ofs.y); G.Y(2, 6) = k * (C.fr.p.z - T.fr.p.z + ofs.z);
+    for (int i = 0; i < 3; ++i) { G.JA(3 + i, 3 + i) = 1; G.Y(3 + i, 3 + i) = -1; }
     Quat qrel; qrel.w = P.tankQrel[0]; qrel.x = P.tankQrel[1]; qrel.y = P.tankQrel[2]; qrel.z = P.tankQrel[3];
-    fixed_orientation_c(T, C, qrel, fps * P.worldERP * 2.0f, &G.c[3]);
+    float c3[3]; fixed_orientation_c(T, C, qrel, fps * P.worldERP * 2.0f, c3);
+    G.Y(3, 6) = c3[0]; G.Y(4, 6) = c3[1]; G.Y(5, 6) = c3[2];
 }
 
-/* groups 1,2: strut.  A = hub, B = strut body */
-PD_HD void build_strut(const PdCarParams& P, const PdStrut& S, const Body& C, const Body& H, const Body& B, V3 steerA1, V3 steerA2, float fps, float dballErp, float dballCfm, GroupSys& G) {
+/* groups "strut": A = hub, B = strut body */
+PD_HD void build_strut(const PdCarParams& P, const PdStrut& S, const Body& C, const Body& H, const Body& B, V3 steerA1, V3 steerA2, float fps, float dballErp, float dballCfm, GScr& G) {
     zero_group(G, 11, 1, P.worldCFM);
     for (int l = 0; l < 3; ++l) {
         V3 a1 = v3(S.link[l].anchor1[0], S.link[l].anchor1[1], S.link[l].anchor1[2]);
         V3 a2 = v3(S.link[l].anchor2[0], S.link[l].anchor2[1], S.link[l].anchor2[2]);
         if (l == 2) { a1 = steerA1; a2 = steerA2; }
-        row_dball(C, H, a1, a2, S.link[l].distance, fps * dballErp, G.U[l], G.JA[l], G.c[l]);
-        G.cfm[l] = dballCfm;
+        grow_dball(G, l, C, H, a1, a2, S.link[l].distance, fps * dballErp, dballCfm);
     }
     { /* slider (b0 = strut body, b1 = hub): rows 3..7 */
         Quat qrel; qrel.w = S.sliderQrel[0]; qrel.x = S.sliderQrel[1]; qrel.y = S.sliderQrel[2]; qrel.z = S.sliderQrel[3];
-        for (int i = 0; i < 3; ++i) { G.JB[3 + i][3 + i] = 1; G.JA[3 + i][3 + i] = -1; }
-        fixed_orientation_c(B, H, qrel, fps * P.worldERP * 2.0f, &G.c[3]);
+        for (int i = 0; i < 3; ++i) { G.JB(3 + i, 3 + i) = 1; G.JA(3 + i, 3 + i) = -1; }
+        float c3[3]; fixed_orientation_c(B, H, qrel, fps * P.worldERP * 2.0f, c3);
+        G.Y(3, 6) = c3[0]; G.Y(4, 6) = c3[1]; G.Y(5, 6) = c3[2];
         V3 c = H.fr.p - B.fr.p;
         const V3 ax1 = rot(B.fr, v3(S.sliderAxis1[0], S.sliderAxis1[1], S.sliderAxis1[2]));
         V3 p, q; plane_space(ax1, p, q);
         const V3 cp = cross(c, p) * 0.5f, cq = cross(c, q) * 0.5f;
-        set6(G.JB[6], p, cp); set6(G.JA[6], neg(p), cp);
-        set6(G.JB[7], q, cq); set6(G.JA[7], neg(q), cq);
+        gset6(G, 1, 6, p, cp); gset6(G, 0, 6, neg(p), cp);
+        gset6(G, 1, 7, q, cq); gset6(G, 0, 7, neg(q), cq);
         const V3 ofs = rot(H.fr, v3(S.sliderOffset[0], S.sliderOffset[1], S.sliderOffset[2]));
         c = c + ofs;
         const float k = fps * P.worldERP;
-        G.c[6] = k * dot(p, c); G.c[7] = k * dot(q, c);
+        G.Y(6, 6) = k * dot(p, c); G.Y(7, 6) = k * dot(q, c);
     }
     { /* ball (b0 = chassis, b1 = strut body): rows 8..10 */
         const V3 a1 = rot(C.fr, v3(S.ballAnchor1[0], S.ballAnchor1[1], S.ballAnchor1[2]));
         const V3 a2 = rot(B.fr, v3(S.ballAnchor2[0], S.ballAnchor2[1], S.ballAnchor2[2]));
-        for (int i = 0; i < 3; ++i) { G.U[8 + i][i] = 1; G.JB[8 + i][i] = -1; }
-        G.U[8][4] = a1.z; G.U[8][5] = -a1.y; G.U[9][3] = -a1.z; G.U[9][5] = a1.x; G.U[10][3] = a1.y; G.U[10][4] = -a1.x;
-        G.JB[8][4] = -a2.z; G.JB[8][5] = a2.y; G.JB[9][3] = a2.z; G.JB[9][5] = -a2.x; G.JB[10][3] = -a2.y; G.JB[10][4] = a2.x;
+        for (int i = 0; i < 3; ++i) { G.Y(8 + i, i) = 1; G.JB(8 + i, i) = -1; }
+        G.Y(8, 4) = a1.z; G.Y(8, 5) = -a1.y; G.Y(9, 3) = -a1.z; G.Y(9, 5) = a1.x; G.Y(10, 3) = a1.y; G.Y(10, 4) = -a1.x;
+        G.JB(8, 4) = -a2.z; G.JB(8, 5) = a2.y; G.JB(9, 3) = a2.z; G.JB(9, 5) = -a2.x; G.JB(10, 3) = -a2.y; G.JB(10, 4) = a2.x;
         const float k = fps * P.worldERP;
-        G.c[8] = k * (a2.x + B.fr.p.x - a1.x - C.fr.p.x); G.c[9] = k * (a2.y + B.fr.p.y - a1.y - C.fr.p.y); G.c[10] = k * (a2.z + B.fr.p.z - a1.z - C.fr.p.z);
+        G.Y(8, 6) = k * (a2.x + B.fr.p.x - a1.x - C.fr.p.x); G.Y(9, 6) = k * (a2.y + B.fr.p.y - a1.y - C.fr.p.y); G.Y(10, 6) = k * (a2.z + B.fr.p.z - a1.z - C.fr.p.z);
     }
 }
 
-/* group 3: axle, 5 dball links (b0 = chassis, b1 = axle) */
-PD_HD void build_axle(const PdCarParams& P, const Body& C, const Body& A, float fps, float dballErp, float dballCfm, GroupSys& G) {
+/* group "axle": dball links (b0 = chassis, b1 = axle) */
+PD_HD void build_axle(const PdCarParams& P, const Body& C, const Body& A, float fps, float dballErp, float dballCfm, GScr& G) {
     const int n = P.axle.nLinks;
     zero_group(G, n, 0, dballCfm);
     for (int l = 0; l < n; ++l) {
         const PdDBall& K = P.axle.link[l];
-        row_dball(C, A, v3(K.anchor1[0], K.anchor1[1], K.anchor1[2]), v3(K.anchor2[0], K.anchor2[1], K.anchor2[2]), K.distance, fps * dballErp, G.U[l], G.JA[l], G.c[l]);
+        grow_dball(G, l, C, A, v3(K.anchor1[0], K.anchor1[1], K.anchor1[2]), v3(K.anchor2[0], K.anchor2[1], K.anchor2[2]), K.distance, fps * dballErp, dballCfm);
     }
 }
 
-PD_HD float dot6(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
-PD_HD void jinvm(const float* J, const BodyDyn& d, float* o) {
+PD_HD void jinvm6(const float* J, const BodyDyn& d, float* o) {
     o[0] = J[0] * d.invMass; o[1] = J[1] * d.invMass; o[2] = J[2] * d.invMass;
     const V3 a = sym3_mul(d.invI, v3(J[3], J[4], J[5]));
     o[3] = a.x; o[4] = a.y; o[5] = a.z;
 }
 
-/* factor one group: D = JA MA^-1 JA^T (+ JB MB^-1 JB^T) + cfm/h ; L D L^T ; Y = L^-1 [U | r];
+/* factor one group: D = JA MA^-1 JA^T (+ JB MB^-1 JB^T) + cfm/h ; L D L^T in place ; Y <- L^-1 [U | r];
  * accumulates the chassis Schur complement S (6x6 lower, packed 21) and right-hand side b6. */
-PD_HDN void factor_group(const GroupSys& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, GroupFac& F, float* S21, float* b6) {
+PD_HDN void factor_group(const GScr& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6) {
     const int n = G.n;
-    float Dm[PD_GMAX][PD_GMAX];
     for (int i = 0; i < n; ++i) {
-        float ja[6], jb[6];
-        jinvm(G.JA[i], dA, ja);
-        if (G.hasB) jinvm(G.JB[i], dB, jb);
+        float ra[6], rb[6], ja[6], jb[6];
+        for (int k = 0; k < 6; ++k) { ra[k] = G.JA(i, k); rb[k] = G.hasB ? G.JB(i, k) : 0.0f; }
+        jinvm6(ra, dA, ja);
+        if (G.hasB) jinvm6(rb, dB, jb);
         for (int j = 0; j <= i; ++j) {
-            float s = dot6(ja, G.JA[j]);
-            if (G.hasB) s += dot6(jb, G.JB[j]);
-            Dm[i][j] = s;
+            float s = ja[0] * G.JA(j, 0) + ja[1] * G.JA(j, 1) + ja[2] * G.JA(j, 2) + ja[3] * G.JA(j, 3) + ja[4] * G.JA(j, 4) + ja[5] * G.JA(j, 5);
+            if (G.hasB) s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
+            G.D(i, j) = s;
         }
-        Dm[i][i] += G.cfm[i] * hinv;
+        G.D(i, i) += G.dg(i) * hinv;
         /* r_i = c_i/h - J_i (v/h + M^-1 f) */
-        float s = dot6(G.JA[i], dA.t1) + dot6(G.U[i], dC.t1);
-        if (G.hasB) s += dot6(G.JB[i], dB.t1);
-        F.Y[i][6] = G.c[i] * hinv - s;
-        for (int k = 0; k < 6; ++k) F.Y[i][k] = G.U[i][k];
+        float s = ra[0] * dA.t1[0] + ra[1] * dA.t1[1] + ra[2] * dA.t1[2] + ra[3] * dA.t1[3] + ra[4] * dA.t1[4] + ra[5] * dA.t1[5];
+        s += G.Y(i, 0) * dC.t1[0] + G.Y(i, 1) * dC.t1[1] + G.Y(i, 2) * dC.t1[2] + G.Y(i, 3) * dC.t1[3] + G.Y(i, 4) * dC.t1[4] + G.Y(i, 5) * dC.t1[5];
+        if (G.hasB) s += rb[0] * dB.t1[0] + rb[1] * dB.t1[1] + rb[2] * dB.t1[2] + rb[3] * dB.t1[3] + rb[4] * dB.t1[4] + rb[5] * dB.t1[5];
+        G.Y(i, 6) = G.Y(i, 6) * hinv - s;
     }
-    /* L D L^T, row by row (same recurrence as the oracle's dense factorisation) */
+    /* L D L^T, row by row (same recurrence as the oracle's dense factorisation), in place */
     for (int i = 0; i < n; ++i) {
         for (int j = 0; j < i; ++j) {
-            float s = Dm[i][j];
-            for (int k = 0; k < j; ++k) s -= Dm[i][k] * F.L[tri(j, k)];
-            Dm[i][j] = s;
+            float s = G.D(i, j);
+            for (int k = 0; k < j; ++k) s -= G.D(i, k) * G.D(j, k);    /* D(i,k) = u_k (unscaled), D(j,k) = L_jk */
+            G.D(i, j) = s;
         }
-        float dii = Dm[i][i];
-        for (int j = 0; j < i; ++j) { const float lij = Dm[i][j] / F.d[j]; dii -= Dm[i][j] * lij; F.L[tri(i, j)] = lij; }
-        F.d[i] = dii;
+        float dii = G.D(i, i);
+        for (int j = 0; j < i; ++j) { const float u = G.D(i, j); const float lij = u / G.dg(j); dii -= u * lij; G.D(i, j) = lij; }
+        G.dg(i) = dii;
     }
-    /* forward substitution on 7 right-hand sides */
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < i; ++j) { const float l = F.L[tri(i, j)]; for (int k = 0; k < 7; ++k) F.Y[i][k] -= l * F.Y[j][k]; }
-    /* S += Yu^T D^-1 Yu ; b += Yu^T D^-1 yr */
+    /* forward substitution on the 7 right-hand sides */
     for (int i = 0; i < n; ++i) {
-        const float di = 1.0f / F.d[i];
+        float y[7];
+        for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
+        for (int j = 0; j < i; ++j) { const float l = G.D(i, j); for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(j, k); }
+        for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
+        /* S += Yu^T D^-1 Yu ; b += Yu^T D^-1 yr */
+        const float di = 1.0f / G.dg(i);
         int o = 0;
         for (int a = 0; a < 6; ++a) {
-            const float ya = F.Y[i][a] * di;
-            for (int bb = 0; bb <= a; ++bb) S21[o++] += ya * F.Y[i][bb];
-            b6[a] += ya * F.Y[i][6];
+            const float ya = y[a] * di;
+            for (int bb = 0; bb <= a; ++bb) S21[o++] += ya * y[bb];
+            b6[a] += ya * y[6];
         }
     }
 }
 
 /* lambda_g = L^-T D^-1 (yr - Yu z);  cforce on own bodies = J^T lambda */
-PD_HDN void backsolve_group(const GroupSys& G, const GroupFac& F, const float* z, float* cfA, float* cfB) {
+PD_HDN void backsolve_group(const GScr& G, const float* z, float* cfA, float* cfB) {
     const int n = G.n;
-    float lam[PD_GMAX];
     for (int i = 0; i < n; ++i) {
-        float s = F.Y[i][6];
-        for (int k = 0; k < 6; ++k) s -= F.Y[i][k] * z[k];
-        lam[i] = s / F.d[i];
+        float s = G.Y(i, 6);
+        for (int k = 0; k < 6; ++k) s -= G.Y(i, k) * z[k];
+        G.Y(i, 6) = s / G.dg(i);
     }
-    for (int i = n - 1; i >= 0; --i) { float s = lam[i]; for (int k = i + 1; k < n; ++k) s -= F.L[tri(k, i)] * lam[k]; lam[i] = s; }
+    for (int i = n - 1; i >= 0; --i) { float s = G.Y(i, 6); for (int k = i + 1; k < n; ++k) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
     for (int k = 0; k < 6; ++k) { cfA[k] = 0; cfB[k] = 0; }
     for (int i = 0; i < n; ++i) {
-        for (int k = 0; k < 6; ++k) cfA[k] += G.JA[i][k] * lam[i];
-        if (G.hasB) for (int k = 0; k < 6; ++k) cfB[k] += G.JB[i][k] * lam[i];
+        const float lam = G.Y(i, 6);
+        for (int k = 0; k < 6; ++k) cfA[k] += G.JA(i, k) * lam;
+        if (G.hasB) for (int k = 0; k < 6; ++k) cfB[k] += G.JB(i, k) * lam;
     }
 }
 
@@ -283,71 +300,98 @@ PD_HD void apply_update(Body& b, const BodyDyn& d, const float* cf, float h) {
     b.w += dw;
 }
 
-/* dWorldStep for the car's island */
-PD_HDN void world_step(const PdCarParams& P, CarCtx& X) {
-    const float h = X.dt, hinv = 1.0f / h;
-    BodyDyn dyn[PD_NUM_BODIES];
-    for (int i = 0; i < PD_NUM_BODIES; ++i) {
-        Body& b = X.b[i];
-        const Sym3 I = rot_diag(b.fr, b.I);
-        dyn[i].invI = rot_diag(b.fr, v3(1.0f / b.I.x, 1.0f / b.I.y, 1.0f / b.I.z));
-        dyn[i].invMass = 1.0f / b.mass;
-        b.T += gyro_torque(b, I, h);
-        b.F.y += b.mass * P.gravityY;
-        dyn[i].t1[0] = b.F.x * dyn[i].invMass + b.v.x * hinv; dyn[i].t1[1] = b.F.y * dyn[i].invMass + b.v.y * hinv; dyn[i].t1[2] = b.F.z * dyn[i].invMass + b.v.z * hinv;
-        const V3 a = sym3_mul(dyn[i].invI, b.T);
-        dyn[i].t1[3] = a.x + b.w.x * hinv; dyn[i].t1[4] = a.y + b.w.y * hinv; dyn[i].t1[5] = a.z + b.w.z * hinv;
+/* dxStepIsland stage 0/1 for one body: world inertia, gyroscopic torque, gravity, invM*f + v/h */
+PD_HD void body_dyn(Body& b, float gravityY, float h, BodyDyn& d) {
+    const float hinv = 1.0f / h;
+    const Sym3 I = rot_diag(b.fr, b.I);
+    d.invI = rot_diag(b.fr, v3(1.0f / b.I.x, 1.0f / b.I.y, 1.0f / b.I.z));
+    d.invMass = 1.0f / b.mass;
+    b.T += gyro_torque(b, I, h);
+    b.F.y += b.mass * gravityY;
+    d.t1[0] = b.F.x * d.invMass + b.v.x * hinv; d.t1[1] = b.F.y * d.invMass + b.v.y * hinv; d.t1[2] = b.F.z * d.invMass + b.v.z * hinv;
+    const V3 a = sym3_mul(d.invI, b.T);
+    d.t1[3] = a.x + b.w.x * hinv; d.t1[4] = a.y + b.w.y * hinv; d.t1[5] = a.z + b.w.z * hinv;
+}
+/* S += M_C (mass on the linear diagonal, world inertia on the angular block) */
+PD_HD void schur_add_chassis(float* S21, const Body& C) {
+    const Sym3 Ic = rot_diag(C.fr, C.I);
+    S21[0] += C.mass; S21[2] += C.mass; S21[5] += C.mass;
+    S21[9] += Ic.xx; S21[13] += Ic.xy; S21[14] += Ic.yy; S21[18] += Ic.xz; S21[19] += Ic.yz; S21[20] += Ic.zz;
+}
+/* 6x6 LDL^T solve S z = b (S packed lower, row-major) */
+PD_HD void solve6(const float* S21, const float* b6, float* z) {
+    float Lm[6][6], d[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 6; ++j) {
+            if (j < i) { float s = S21[i * (i + 1) / 2 + j]; for (int k = 0; k < 6; ++k) if (k < j) s -= Lm[i][k] * Lm[j][k] * d[k]; Lm[i][j] = s / d[j]; }
+        }
+        float s = S21[i * (i + 1) / 2 + i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 6; ++k) if (k < i) s -= Lm[i][k] * Lm[i][k] * d[k];
+        d[i] = s;
     }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) { float s = b6[i]; for (int k = 0; k < 6; ++k) if (k < i) s -= Lm[i][k] * z[k]; z[i] = s; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) z[i] /= d[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 5; i >= 0; --i) { float s = z[i]; for (int k = 0; k < 6; ++k) if (k > i) s -= Lm[k][i] * z[k]; z[i] = s; }
+}
+/* chassis: z = M_C^-1 U^T lambda  ->  dv = h (M_C^-1 f + z) */
+PD_HD void chassis_update(Body& Cb, const BodyDyn& d, const float* z, float h) {
+    const float imh = h * d.invMass;
+    Cb.v.x += Cb.F.x * imh + h * z[0]; Cb.v.y += Cb.F.y * imh + h * z[1]; Cb.v.z += Cb.F.z * imh + h * z[2];
+    const V3 dw = sym3_mul(d.invI, v3(Cb.T.x * h, Cb.T.y * h, Cb.T.z * h));
+    Cb.w.x += dw.x + h * z[3]; Cb.w.y += dw.y + h * z[4]; Cb.w.z += dw.z + h * z[5];
+}
+
+/* dWorldStep for the car's island, one thread doing all four groups (host debugging build and reference
+ * for the quad version in pd_quad.h) */
+PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h) {
+    const float hinv = 1.0f / h;
+    BodyDyn dyn[PD_NUM_BODIES];
+    for (int i = 0; i < PD_NUM_BODIES; ++i) body_dyn(b[i], P.gravityY, h, dyn[i]);
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
-    GroupSys G[4]; GroupFac F[4];
-    const Body& C = X.b[PD_BODY_CHASSIS];
-    build_tank(P, X.b[PD_BODY_TANK], C, hinv, G[0]);
-    factor_group(G[0], dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, F[0], S21, b6);
+    float scr[4][PD_GSCR_WORDS]; GScr G[4];
+    for (int g = 0; g < 4; ++g) { G[g].p = scr[g]; G[g].s = 1; }
+    const Body& C = b[PD_BODY_CHASSIS];
+    build_tank(P, b[PD_BODY_TANK], C, hinv, G[0]);
+    factor_group(G[0], dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
     for (int s = 0; s < 2; ++s) {
-        build_strut(P, P.strut[s], C, X.b[PD_BODY_HUB0 + 2 * s], X.b[PD_BODY_STRUT0 + 2 * s], X.steerAnchor1[s], X.steerAnchor2[s], hinv, X.dballErp, X.dballCfm, G[1 + s]);
-        factor_group(G[1 + s], dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, F[1 + s], S21, b6);
+        build_strut(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], hinv, dballErp, dballCfm, G[1 + s]);
+        factor_group(G[1 + s], dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
     }
-    build_axle(P, C, X.b[PD_BODY_AXLE], hinv, X.dballErp, X.dballCfm, G[3]);
-    factor_group(G[3], dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, F[3], S21, b6);
-    /* S += M_C (mass on the linear diagonal, world inertia on the angular block) */
-    {
-        const Sym3 Ic = rot_diag(C.fr, C.I);
-        S21[0] += C.mass; S21[2] += C.mass; S21[5] += C.mass;
-        S21[9] += Ic.xx; S21[13] += Ic.xy; S21[14] += Ic.yy; S21[18] += Ic.xz; S21[19] += Ic.yz; S21[20] += Ic.zz;
-    }
-    /* 6x6 LDL^T solve S z = b */
+    build_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, G[3]);
+    factor_group(G[3], dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
+    schur_add_chassis(S21, C);
     float z[6];
-    {
-        float Lm[6][6], d[6];
-        for (int i = 0; i < 6; ++i) {
-            for (int j = 0; j < i; ++j) { float s = S21[i * (i + 1) / 2 + j]; for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k] * d[k]; Lm[i][j] = s / d[j]; }
-            float s = S21[i * (i + 1) / 2 + i]; for (int k = 0; k < i; ++k) s -= Lm[i][k] * Lm[i][k] * d[k];
-            d[i] = s;
-        }
-        for (int i = 0; i < 6; ++i) { float s = b6[i]; for (int k = 0; k < i; ++k) s -= Lm[i][k] * z[k]; z[i] = s; }
-        for (int i = 0; i < 6; ++i) z[i] /= d[i];
-        for (int i = 5; i >= 0; --i) { float s = z[i]; for (int k = i + 1; k < 6; ++k) s -= Lm[k][i] * z[k]; z[i] = s; }
-    }
-    /* own bodies */
+    solve6(S21, b6, z);
     float cfA[6], cfB[6];
-    backsolve_group(G[0], F[0], z, cfA, cfB); apply_update(X.b[PD_BODY_TANK], dyn[PD_BODY_TANK], cfA, h);
+    backsolve_group(G[0], z, cfA, cfB); apply_update(b[PD_BODY_TANK], dyn[PD_BODY_TANK], cfA, h);
     for (int s = 0; s < 2; ++s) {
-        backsolve_group(G[1 + s], F[1 + s], z, cfA, cfB);
-        apply_update(X.b[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_HUB0 + 2 * s], cfA, h);
-        apply_update(X.b[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], cfB, h);
+        backsolve_group(G[1 + s], z, cfA, cfB);
+        apply_update(b[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_HUB0 + 2 * s], cfA, h);
+        apply_update(b[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], cfB, h);
     }
-    backsolve_group(G[3], F[3], z, cfA, cfB); apply_update(X.b[PD_BODY_AXLE], dyn[PD_BODY_AXLE], cfA, h);
-    /* chassis: z = M_C^-1 U^T lambda  ->  dv = h (M_C^-1 f + z) */
-    {
-        Body& Cb = X.b[PD_BODY_CHASSIS]; const BodyDyn& d = dyn[PD_BODY_CHASSIS];
-        const float imh = h * d.invMass;
-        Cb.v.x += Cb.F.x * imh + h * z[0]; Cb.v.y += Cb.F.y * imh + h * z[1]; Cb.v.z += Cb.F.z * imh + h * z[2];
-        const V3 dw = sym3_mul(d.invI, v3(Cb.T.x * h, Cb.T.y * h, Cb.T.z * h));
-        Cb.w.x += dw.x + h * z[3]; Cb.w.y += dw.y + h * z[4]; Cb.w.z += dw.z + h * z[5];
-    }
-    for (int i = 0; i < PD_NUM_BODIES; ++i) { integrate_body(X.b[i], h); X.b[i].F = v3(0, 0, 0); X.b[i].T = v3(0, 0, 0); }
+    backsolve_group(G[3], z, cfA, cfB); apply_update(b[PD_BODY_AXLE], dyn[PD_BODY_AXLE], cfA, h);
+    chassis_update(b[PD_BODY_CHASSIS], dyn[PD_BODY_CHASSIS], z, h);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) { integrate_body(b[i], h); b[i].F = v3(0, 0, 0); b[i].T = v3(0, 0, 0); }
 }
 
 } // namespace pd

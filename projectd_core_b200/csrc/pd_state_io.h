@@ -47,12 +47,13 @@ struct SV {
     uint32_t* s;
     size_t n;   /* number of envs (row stride) */
     size_t e;   /* this env */
+    bool live = true;   /* false: a padding lane that computes along but must not write */
     PD_HD float f(int w) const { return u2f(s[(size_t)w * n + e]); }
     PD_HD int i(int w) const { return (int)s[(size_t)w * n + e]; }
     PD_HD double d(int w) const { return u2d(s[(size_t)w * n + e], s[(size_t)(w + 1) * n + e]); }
-    PD_HD void f(int w, float v) const { s[(size_t)w * n + e] = f2u(v); }
-    PD_HD void i(int w, int v) const { s[(size_t)w * n + e] = (uint32_t)v; }
-    PD_HD void d(int w, double v) const { uint32_t lo, hi; d2u(v, lo, hi); s[(size_t)w * n + e] = lo; s[(size_t)(w + 1) * n + e] = hi; }
+    PD_HD void f(int w, float v) const { if (live) s[(size_t)w * n + e] = f2u(v); }
+    PD_HD void i(int w, int v) const { if (live) s[(size_t)w * n + e] = (uint32_t)v; }
+    PD_HD void d(int w, double v) const { if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[(size_t)w * n + e] = lo; s[(size_t)(w + 1) * n + e] = hi; }
 };
 
 /* ---- typed mirrors of the X-macro lists ---- */
@@ -85,11 +86,13 @@ struct CarS {
 PD_HD void load_tyre(const SV& sv, int w, TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__LDT)
+    PD_UNROLL
     for (int p = 0; p < PD_THERMAL_PATCHES; ++p) t.T[p] = sv.f(PD_OFF_TYRE_PATCH(w) + p);
 }
 PD_HD void store_tyre(const SV& sv, int w, const TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__STT)
+    PD_UNROLL
     for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, t.T[p]);
 }
 PD_HD void load_car(const SV& sv, CarS& t) {

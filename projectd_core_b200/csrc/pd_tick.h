@@ -8,8 +8,7 @@
 
 namespace pd {
 
-PD_HD void set_body_mass(CarCtx& X, const PdCarParams& P) {
-    Body* b = X.b;
+PD_HD void set_body_mass(Body* b, const PdCarParams& P) {
     b[PD_BODY_CHASSIS].mass = P.chassisMass; b[PD_BODY_CHASSIS].I = v3(P.chassisInertia[0], P.chassisInertia[1], P.chassisInertia[2]);
     b[PD_BODY_TANK].mass = P.tankMass; b[PD_BODY_TANK].I = v3(P.tankInertia[0], P.tankInertia[1], P.tankInertia[2]);
     for (int s = 0; s < 2; ++s) {
@@ -32,15 +31,15 @@ PD_HD float beta_rad(const Body& C) {
  * origin with identity rotation, suspension bodies attached, everything else at its default */
 PD_HDN void car_init_state(const PdCarParams& P, const SV& sv) {
     for (int w = 0; w < PD_STATE_WORDS; ++w) sv.i(w, 0);
-    CarCtx X; set_body_mass(X, P);
+    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
     for (int i = 0; i < PD_NUM_BODIES; ++i) {
-        Body& b = X.b[i]; b.fr.p = v3(0, 0, 0); b.fr.ax = v3(1, 0, 0); b.fr.ay = v3(0, 1, 0); b.fr.az = v3(0, 0, 1);
+        Body& b = bod[i]; b.fr.p = v3(0, 0, 0); b.fr.ax = v3(1, 0, 0); b.fr.ay = v3(0, 1, 0); b.fr.az = v3(0, 0, 1);
         b.q.w = 1; b.q.x = b.q.y = b.q.z = 0; b.v = v3(0, 0, 0); b.w = v3(0, 0, 0);
     }
-    Body& C = X.b[PD_BODY_CHASSIS];
-    X.b[PD_BODY_TANK].fr.p = v3(P.fuelTankPos[0], P.fuelTankPos[1], P.fuelTankPos[2]);
+    Body& C = bod[PD_BODY_CHASSIS];
+    bod[PD_BODY_TANK].fr.p = v3(P.fuelTankPos[0], P.fuelTankPos[1], P.fuelTankPos[2]);
     for (int s = 0; s < 2; ++s) {
-        const PdStrut& S = P.strut[s]; Body& H = X.b[PD_BODY_HUB0 + 2 * s]; Body& B = X.b[PD_BODY_STRUT0 + 2 * s];
+        const PdStrut& S = P.strut[s]; Body& H = bod[PD_BODY_HUB0 + 2 * s]; Body& B = bod[PD_BODY_STRUT0 + 2 * s];
         H.fr.p = to_world(C.fr, v3(S.refPoint[0], S.refPoint[1], S.refPoint[2]));
         const V3 vCarStrut = to_world(C.fr, v3(S.carStrut[0], S.carStrut[1], S.carStrut[2]));
         const V3 vTyreStrut = to_world(H.fr, v3(S.tyreStrut[0], S.tyreStrut[1], S.tyreStrut[2]));
@@ -51,8 +50,8 @@ PD_HDN void car_init_state(const PdCarParams& P, const SV& sv) {
         set_rotation(vM3NN, vM3N * -1.0f, vNorm * -1.0f, B.fr.ax, B.fr.ay, B.fr.az, B.q);
         B.fr.p = (vNorm * S.strutBodyLength) * 0.5f + vCarStrut;
     }
-    X.b[PD_BODY_AXLE].fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
-    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, X.b[i]);
+    bod[PD_BODY_AXLE].fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
+    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, bod[i]);
     for (int w = 0; w < PD_NUM_WHEELS; ++w) { /* Tyre::Tyre + setCompound(0) + reset (Tyre.cpp:15-26,343-425) */
         const int o = PD_OFF_TYRE(w);
         sv.f(o + PD_TYRE_o_pressureStatic, P.tyre[w].pressureStaticDefault); sv.f(o + PD_TYRE_o_pressureDynamic, P.tyre[w].pressureRef);
@@ -75,12 +74,11 @@ PD_HDN void car_init_state(const PdCarParams& P, const SV& sv) {
 
 /* teleport: Car::teleportToSpline -> forceRotation + forcePosition (Car.cpp:1325-1340,1275-1308,1240-1273) */
 PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const SV& sv, int pointId, double physicsTime) {
-    CarCtx X; set_body_mass(X, P);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, X.b[i]);
-    load_car(sv, X.c);
-    CarS& c = X.c;
+    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
+    CarS c; load_car(sv, c);
     const PdFatPoint& pt = T.fat[pointId];
-    Body& C = X.b[PD_BODY_CHASSIS]; Body& Tk = X.b[PD_BODY_TANK];
+    Body& C = bod[PD_BODY_CHASSIS]; Body& Tk = bod[PD_BODY_TANK];
     /* forceRotation(heading) */
     {
         const V3 heading = v3(pt.forwardDir[0], pt.forwardDir[1], pt.forwardDir[2]);
@@ -110,7 +108,7 @@ PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const
     Tk.fr.p = to_world(C.fr, v3(P.fuelTankPos[0], P.fuelTankPos[1], P.fuelTankPos[2]));
     /* susp->stop(); susp->attach() */
     for (int s = 0; s < 2; ++s) { /* SuspensionStrut::setPositions (SuspensionStrut.cpp:188-223) */
-        const PdStrut& S = P.strut[s]; Body& H = X.b[PD_BODY_HUB0 + 2 * s]; Body& B = X.b[PD_BODY_STRUT0 + 2 * s];
+        const PdStrut& S = P.strut[s]; Body& H = bod[PD_BODY_HUB0 + 2 * s]; Body& B = bod[PD_BODY_STRUT0 + 2 * s];
         body_stop(H);
         set_rotation(C.fr.ax, C.fr.ay, C.fr.az, H.fr.ax, H.fr.ay, H.fr.az, H.q);   /* hub->setRotation(mxBody) */
         H.fr.p = to_world(C.fr, v3(S.refPoint[0], S.refPoint[1], S.refPoint[2]));
@@ -125,7 +123,7 @@ PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const
         /* NB SuspensionStrut::stop() stops only the hub; the strut body keeps its velocity (reference behaviour) */
     }
     {
-        Body& A = X.b[PD_BODY_AXLE]; body_stop(A);
+        Body& A = bod[PD_BODY_AXLE]; body_stop(A);
         set_rotation(C.fr.ax, C.fr.ay, C.fr.az, A.fr.ax, A.fr.ay, A.fr.az, A.q);
         A.fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
     }
@@ -145,186 +143,12 @@ PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const
     /* drivetrain->setCurrentGear(1, true) */
     c.isGearGrinding = 0; c.currentGear = 1;
     body_stop(C); body_stop(Tk);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, X.b[i]);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, bod[i]);
     store_car(sv, c);
 }
 
-/* the tick */
-PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, float dt, double physicsTime) {
-    CarCtx X; X.dt = dt; X.time = physicsTime;
-    set_body_mass(X, P);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, X.b[i]);
-    load_car(sv, X.c);
-    CarS& c = X.c;
-    Body& C = X.b[PD_BODY_CHASSIS];
-
-    /* ---------------- Simulator::stepCars: stepPreCacheValues + Car::step ---------------- */
-    c.speed = len(C.v);
-    c.collisionFlag = 0; c.outOfTrackFlag = 0;
-    { /* Car.cpp:426-451 (car id 0): DBall ERP by speed; CFM = baseCFM = 1e-7 in both branches */
-        const float fVelSq = sqlen(C.v);
-        X.dballErp = (fVelSq >= 1.0f) ? 0.3f : 0.9f;
-        X.dballCfm = (fVelSq >= 1.0f) ? P.strut[0].baseCFM : 0.0000001f;
-    }
-    c.ctlSteer = tclampf(c.ctlSteer, -1.0f, 1.0f); c.ctlClutch = tclampf(c.ctlClutch, 0.0f, 1.0f); c.ctlBrake = tclampf(c.ctlBrake, 0.0f, 1.0f);
-    c.ctlHandBrake = tclampf(c.ctlHandBrake, 0.0f, 1.0f); c.ctlGas = tclampf(c.ctlGas, 0.0f, 1.0f);
-    {
-        const float target = c.ctlSteer;
-        if (c.smoothSteer) { const float diff = target - c.smoothSteerValue; c.smoothSteerValue += diff * P.scoring[PD_SV_SmoothSteerSpeed] * dt; c.ctlSteer = c.smoothSteerValue; }
-        else c.smoothSteerValue = target;
-    }
-    { /* fuel (Car.cpp:476-489) */
-        const float fRpmAbs = fabsf(engine_rpm(c));
-        const double fNewFuel = c.fuel - (fRpmAbs * dt * c.gasUsage) * (0.0f + 1.0) * P.fuelConsumptionK * 0.001 * P.fuelConsumptionRate;
-        c.fuel = fNewFuel;
-        if (fNewFuel > 0.0f) c.fuelPressure = 1.0f; else { c.fuel = 0; c.fuelPressure = 0; }
-    }
-    {
-        float sig = (P.steerLock * c.ctlSteer) / P.steerRatio;
-        if (!finitef(sig)) sig = 0;
-        c.finalSteerAngleSignal = sig;
-    }
-    bool bAllTyresLoaded = true;
-    for (int w = 0; w < 4; ++w) if (sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_load) <= 0.0f) { bAllTyresLoaded = false; break; }
-    autoclutch_step(P, X);
-    bool sleeping = false;
-    {
-        const float fAngVelSq = sqlen(C.w);
-        if (c.speed >= 0.5f || fAngVelSq >= 1.0f) c.sleepingFrames = 0;
-        else {
-            if (bAllTyresLoaded && (c.ctlGas <= 0.01f || c.ctlClutch <= 0.01f || c.currentGear == 1)) c.sleepingFrames++; else c.sleepingFrames = 0;
-            if (c.sleepingFrames > P.framesToSleep) { body_stop(C); body_stop(X.b[PD_BODY_TANK]); sleeping = true; }
-        }
-    }
-    {
-        const V3 vBodyVel = C.v;
-        const V3 vAccel = (vBodyVel - v3(c.lastVelX, c.lastVelY, c.lastVelZ)) * (1.0f / dt) * 0.10197838f;
-        c.lastVelX = vBodyVel.x; c.lastVelY = vBodyVel.y; c.lastVelZ = vBodyVel.z;
-        const V3 g = irot(C.fr, vAccel);
-        c.accGX = g.x; c.accGY = g.y; c.accGZ = g.z;
-    }
-    { /* stepThermalObjects (Car.cpp:624-634) + ThermalObject::step */
-        const float fRpm = engine_rpm(c);
-        float heat = 0;
-        if (fRpm > (P.engine.minimum * 0.8f)) { const float fLimiter = (float)(int)(P.engine.limiter * P.engine.limiterMultiplier); heat += (((fRpm / fLimiter) * 20.0f) * c.ctlGas) + 85.0f; }
-        const float fOneDivMass = 1.0f / P.waterTmass;
-        const float fCool = 1.0f - (P.waterCoolSpeedK * c.speed);
-        c.waterT += (((((fCool * P.ambientTemperature) - c.waterT) * fOneDivMass) * dt) * P.waterCoolFactor);
-        if (heat != 0.0f) c.waterT += ((((heat - c.waterT) * fOneDivMass) * dt) * P.waterHeatFactor);
-    }
-
-    /* ---------------- stepComponents ---------------- */
-    float brakeT[4], handT[4];
-    brakes_step(P.brakes, c, brakeT, handT);
-    float travel[4], dspeed[4];
-    strut_step(P.strut[0], C, X.b[PD_BODY_HUB0], travel[0], dspeed[0]);
-    strut_step(P.strut[1], C, X.b[PD_BODY_HUB1], travel[1], dspeed[1]);
-    axle_step(P.axle, C, X.b[PD_BODY_AXLE], 0, travel[2], dspeed[2]);
-    axle_step(P.axle, C, X.b[PD_BODY_AXLE], 1, travel[3], dspeed[3]);
-    for (int w = 0; w < 4; ++w) {
-        sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspTravel, travel[w]); sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspDamperSpeed, dspeed[w]);
-    }
-    for (int w = 0; w < 4; ++w) {
-        if (w < 2) { Body& H = X.b[PD_BODY_HUB0 + 2 * w]; const Frame hf = strut_hub_frame(P.strut[w], H); tyre_step(P, T, w, X, sv, H, hf, brakeT[w], handT[w], sleeping); }
-        else { Body& A = X.b[PD_BODY_AXLE]; const Frame hf = axle_hub_frame(P.axle, A, w - 2); tyre_step(P, T, w, X, sv, A, hf, brakeT[w], handT[w], sleeping); }
-    }
-    aero_step(P, C);
-    { /* SteeringSystem::step -> setSteerLengthOffset -> reseatDistanceJointLocal (incl. its local->world->local round trip) */
-        const float steer = -c.finalSteerAngleSignal * P.steerLinearRatio;
-        for (int s = 0; s < 2; ++s) {
-            const PdStrut& S = P.strut[s];
-            const float sx = signf_(S.refPoint[0]);
-            const float offx = 0.0f + steer + (sx * S.toeOutLinear);
-            const V3 carSteer = v3(S.baseCarSteer[0] + offx, S.baseCarSteer[1], S.baseCarSteer[2]);
-            const Body& H = X.b[PD_BODY_HUB0 + 2 * s];
-            X.steerAnchor1[s] = to_local(C.fr, to_world(C.fr, carSteer));
-            X.steerAnchor2[s] = to_local(H.fr, to_world(H.fr, v3(S.tyreSteer[0], S.tyreSteer[1], S.tyreSteer[2])));
-        }
-    }
-    autoblip_step(P, X);
-    autoshift_step(P, X);
-    gearchanger_step(P, X);
-    drivetrain_step(P, X);
-    { /* driven wheels: angular velocity / lock state written by the drivetrain */
-        const int dl = (P.drivetrain.tractionType == 1) ? 0 : 2;
-        for (int w = dl; w < dl + 2; ++w) { sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_angularVelocity, X.wl[w].angularVelocity); sv.i(PD_OFF_TYRE(w) + PD_TYRE_o_isLocked, X.wl[w].isLocked); }
-    }
-    arb_step(P.arbK[0], C, X.b[PD_BODY_HUB0], X.b[PD_BODY_HUB0].fr.p, X.b[PD_BODY_HUB1], X.b[PD_BODY_HUB1].fr.p);
-    {
-        Body& A = X.b[PD_BODY_AXLE];
-        const Frame f0 = axle_hub_frame(P.axle, A, 0), f1 = axle_hub_frame(P.axle, A, 1);
-        arb_step(P.arbK[1], C, A, f0.p, A, f1.p);
-    }
-
-    /* ---------------- physics->step(dt): dWorldStep ---------------- */
-    world_step(P, X);
-
-    /* ---------------- Car::postStep ---------------- */
-    { /* updateTrackLocator (Car.cpp:717-771) */
-        const V3 bodyPos = C.fr.p;
-        const int nFat = T.info.nFatPoints;
-        if (P.nProbes > 0 && nFat > 0) {
-            /* Track::rayCastTrackBounds cache refresh (Track.cpp:505-510): only the first probe can trigger it */
-            const V3 cache = v3(c.pointCacheX, c.pointCacheY, c.pointCacheZ);
-            if (sqlen(cache - bodyPos) > 1.0f * 1.0f) { c.pointCacheX = bodyPos.x; c.pointCacheY = bodyPos.y; c.pointCacheZ = bodyPos.z; }
-        }
-        const V3 cachePos = v3(c.pointCacheX, c.pointCacheY, c.pointCacheZ);
-        const float nearR = (P.nProbes > 0) ? P.probeLength[0] : T.info.hashCellSize;
-        const float nearRSq = nearR * nearR;
-        /* probe rays */
-        float rax = bodyPos.x, raz = bodyPos.z;
-        float rbx[PD_MAX_PROBES], rbz[PD_MAX_PROBES], best[PD_MAX_PROBES];
-        for (int r = 0; r < P.nProbes; ++r) {
-            const V3 rayStart = to_world(C.fr, v3(0, 0, 0));
-            const V3 rayEndL = to_world(C.fr, v3(P.probeDir[r][0], P.probeDir[r][1], P.probeDir[r][2]) * P.probeLength[r]);
-            const V3 dir = norm(rayEndL - rayStart);
-            const V3 rayEnd = rayStart + dir * (P.probeLength[r] * 1.1f);
-            rax = rayStart.x; raz = rayStart.z;
-            rbx[r] = rayEnd.x; rbz[r] = rayEnd.z; best[r] = FLT_MAX;
-        }
-        float bestDistSq = FLT_MAX; int bestPoint = 0;
-        bool needBrute = false;
-        for (int r = 0; r < P.nProbes; ++r) if (!probe_walk(T, rax, raz, rbx[r], rbz[r], cachePos, nearRSq, best[r])) needBrute = true;
-        const bool haveNearest = nearest_point_grid(T, bodyPos, cachePos, nearRSq, bestPoint);
-        if (needBrute || !haveNearest) {
-            /* exhaustive form of the reference (car far off the indexed area) */
-            bestPoint = 0;
-            for (int r = 0; r < P.nProbes; ++r) best[r] = FLT_MAX;
-            for (int id = 0; id < nFat; ++id) {
-                const PdFatPoint& f = T.fat[id];
-                const V3 loc = v3(f.best[0], f.best[1], f.best[2]);
-                if (!(sqlen(cachePos - loc) < nearRSq)) continue;          /* VertexHash::queryNeighbours filter */
-                { const float dsq = sqlen(loc - bodyPos); if (bestDistSq > dsq) { bestDistSq = dsq; bestPoint = id; } }  /* getPointIdAtLocation */
-                const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
-                for (int r = 0; r < P.nProbes; ++r) {
-                    float ix, iz;
-                    if (line_intersection(rax, raz, rbx[r], rbz[r], f.left[0], f.left[2], g.left[0], g.left[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
-                    if (line_intersection(rax, raz, rbx[r], rbz[r], f.right[0], f.right[2], g.right[0], g.right[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
-                }
-            }
-        }
-        for (int r = 0; r < P.nProbes; ++r) c.probes[r] = (best[r] != FLT_MAX) ? best[r] : P.probeLength[r];
-        if (c.nearestTrackPointId != bestPoint) { c.oldTrackPointId = c.nearestTrackPointId; c.nearestTrackPointId = bestPoint; c.lastTrackPointTimestamp = (float)physicsTime; }
-        c.oldTrackLocation = c.trackLocation; c.trackLocation = 0;
-        if (bestPoint >= 0 && bestPoint < nFat) {
-            if (nFat >= 5) { /* getDistanceAlongSplineAtLocation (Track.cpp:609-629) */
-                int prevId = bestPoint - 1; if (prevId < 0) prevId = nFat - 1;
-                int nextId = bestPoint + 1; if (nextId >= nFat) nextId = 0;
-                int prevId2 = prevId - 1; if (prevId2 < 0) prevId2 = nFat - 1;
-                int nextId2 = nextId + 1; if (nextId2 >= nFat) nextId2 = 0;
-                int sid; float sdist;
-                if (spline_nearest(T, bodyPos, prevId2 * T.info.interpolateStep, nextId2 * T.info.interpolateStep, sid, sdist)) {
-                    c.splinePointId = sid; c.trackLocation = tclampf(sdist / T.info.computedTrackLength, 0.0f, 1.0f);
-                }
-            }
-            const V3 bodyFrontDir = norm(C.fr.az);
-            const V3 bodyVelDir = norm(C.v);
-            const PdFatPoint& pt = T.fat[bestPoint];
-            const V3 fwd = v3(pt.forwardDir[0], pt.forwardDir[1], pt.forwardDir[2]);
-            c.bodyVsTrack = dot(bodyFrontDir, fwd);
-            if ((c.speed * 3.6f) > 3.0f) c.velocityVsTrack = dot(bodyVelDir, fwd); else c.velocityVsTrack = 0.0f;
-        }
-    }
+/* Car::updateLookAhead (Car.cpp:775-798) */
+PD_HD void post_lookahead(const PdCarParams& P, const TrackDev& T, const Body& C, CarS& c) {
     { /* updateLookAhead (Car.cpp:775-798) */
         const V3 up = v3(0, 1, 0);
         const V3 curTrackDir = track_direction_at_distance(T, c.trackLocation);
@@ -336,6 +160,11 @@ PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, floa
             c.lookAhead[i] = atan2f(dot(cross(dir, curTrackDir), up), dot(curTrackDir, dir));
         }
     }
+}
+
+/* ScoringSystem::step = computeDriftScore + computeAgentReward (ScoringSystem.cpp:114-330) */
+PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, CarCtx& X, float dt) {
+    CarS& c = X.c;
     /* ---- ScoringSystem::step (ScoringSystem.cpp:114-330) ---- */
     {
         /* validateDrift */
@@ -404,13 +233,193 @@ PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, floa
         }
         c.stepReward = reward; c.totalReward += reward;
     }
+}
+
+/* the tick */
+PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, float dt, double physicsTime) {
+    CarCtx X; X.dt = dt; X.time = physicsTime;
+    Body bod[PD_NUM_BODIES]; V3 steerAnchor1[2], steerAnchor2[2];
+    set_body_mass(bod, P);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
+    load_car(sv, X.c);
+    CarS& c = X.c;
+    Body& C = bod[PD_BODY_CHASSIS];
+
+    /* ---------------- Simulator::stepCars: stepPreCacheValues + Car::step ---------------- */
+    c.speed = len(C.v);
+    c.collisionFlag = 0; c.outOfTrackFlag = 0;
+    { /* Car.cpp:426-451 (car id 0): DBall ERP by speed; CFM = baseCFM = 1e-7 in both branches */
+        const float fVelSq = sqlen(C.v);
+        X.dballErp = (fVelSq >= 1.0f) ? 0.3f : 0.9f;
+        X.dballCfm = (fVelSq >= 1.0f) ? P.strut[0].baseCFM : 0.0000001f;
+    }
+    c.ctlSteer = tclampf(c.ctlSteer, -1.0f, 1.0f); c.ctlClutch = tclampf(c.ctlClutch, 0.0f, 1.0f); c.ctlBrake = tclampf(c.ctlBrake, 0.0f, 1.0f);
+    c.ctlHandBrake = tclampf(c.ctlHandBrake, 0.0f, 1.0f); c.ctlGas = tclampf(c.ctlGas, 0.0f, 1.0f);
+    {
+        const float target = c.ctlSteer;
+        if (c.smoothSteer) { const float diff = target - c.smoothSteerValue; c.smoothSteerValue += diff * P.scoring[PD_SV_SmoothSteerSpeed] * dt; c.ctlSteer = c.smoothSteerValue; }
+        else c.smoothSteerValue = target;
+    }
+    { /* fuel (Car.cpp:476-489) */
+        const float fRpmAbs = fabsf(engine_rpm(c));
+        const double fNewFuel = c.fuel - (fRpmAbs * dt * c.gasUsage) * (0.0f + 1.0) * P.fuelConsumptionK * 0.001 * P.fuelConsumptionRate;
+        c.fuel = fNewFuel;
+        if (fNewFuel > 0.0f) c.fuelPressure = 1.0f; else { c.fuel = 0; c.fuelPressure = 0; }
+    }
+    {
+        float sig = (P.steerLock * c.ctlSteer) / P.steerRatio;
+        if (!finitef(sig)) sig = 0;
+        c.finalSteerAngleSignal = sig;
+    }
+    bool bAllTyresLoaded = true;
+    for (int w = 0; w < 4; ++w) if (sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_load) <= 0.0f) { bAllTyresLoaded = false; break; }
+    autoclutch_step(P, X);
+    {
+        const float fAngVelSq = sqlen(C.w);
+        if (c.speed >= 0.5f || fAngVelSq >= 1.0f) c.sleepingFrames = 0;
+        else {
+            if (bAllTyresLoaded && (c.ctlGas <= 0.01f || c.ctlClutch <= 0.01f || c.currentGear == 1)) c.sleepingFrames++; else c.sleepingFrames = 0;
+            if (c.sleepingFrames > P.framesToSleep) { body_stop(C); body_stop(bod[PD_BODY_TANK]); }
+        }
+    }
+    {
+        const V3 vBodyVel = C.v;
+        const V3 vAccel = (vBodyVel - v3(c.lastVelX, c.lastVelY, c.lastVelZ)) * (1.0f / dt) * 0.10197838f;
+        c.lastVelX = vBodyVel.x; c.lastVelY = vBodyVel.y; c.lastVelZ = vBodyVel.z;
+        const V3 g = irot(C.fr, vAccel);
+        c.accGX = g.x; c.accGY = g.y; c.accGZ = g.z;
+    }
+    { /* stepThermalObjects (Car.cpp:624-634) + ThermalObject::step */
+        const float fRpm = engine_rpm(c);
+        float heat = 0;
+        if (fRpm > (P.engine.minimum * 0.8f)) { const float fLimiter = (float)(int)(P.engine.limiter * P.engine.limiterMultiplier); heat += (((fRpm / fLimiter) * 20.0f) * c.ctlGas) + 85.0f; }
+        const float fOneDivMass = 1.0f / P.waterTmass;
+        const float fCool = 1.0f - (P.waterCoolSpeedK * c.speed);
+        c.waterT += (((((fCool * P.ambientTemperature) - c.waterT) * fOneDivMass) * dt) * P.waterCoolFactor);
+        if (heat != 0.0f) c.waterT += ((((heat - c.waterT) * fOneDivMass) * dt) * P.waterHeatFactor);
+    }
+
+    /* ---------------- stepComponents ---------------- */
+    float brakeT[4], handT[4];
+    brakes_step(P.brakes, c, brakeT, handT);
+    float travel[4], dspeed[4];
+    strut_step(P.strut[0], C, bod[PD_BODY_HUB0], travel[0], dspeed[0]);
+    strut_step(P.strut[1], C, bod[PD_BODY_HUB1], travel[1], dspeed[1]);
+    axle_step(P.axle, C, bod[PD_BODY_AXLE], 0, travel[2], dspeed[2]);
+    axle_step(P.axle, C, bod[PD_BODY_AXLE], 1, travel[3], dspeed[3]);
+    for (int w = 0; w < 4; ++w) {
+        sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspTravel, travel[w]); sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspDamperSpeed, dspeed[w]);
+    }
+    for (int w = 0; w < 4; ++w) {
+        if (w < 2) { Body& H = bod[PD_BODY_HUB0 + 2 * w]; const Frame hf = strut_hub_frame(P.strut[w], H); tyre_step(P, T, w, X, sv, H, hf, C, brakeT[w], handT[w], X.wl[w]); }
+        else { Body& A = bod[PD_BODY_AXLE]; const Frame hf = axle_hub_frame(P.axle, A, w - 2); tyre_step(P, T, w, X, sv, A, hf, C, brakeT[w], handT[w], X.wl[w]); }
+    }
+    aero_step(P, C);
+    { /* SteeringSystem::step -> setSteerLengthOffset -> reseatDistanceJointLocal (incl. its local->world->local round trip) */
+        const float steer = -c.finalSteerAngleSignal * P.steerLinearRatio;
+        for (int s = 0; s < 2; ++s) {
+            const PdStrut& S = P.strut[s];
+            const float sx = signf_(S.refPoint[0]);
+            const float offx = 0.0f + steer + (sx * S.toeOutLinear);
+            const V3 carSteer = v3(S.baseCarSteer[0] + offx, S.baseCarSteer[1], S.baseCarSteer[2]);
+            const Body& H = bod[PD_BODY_HUB0 + 2 * s];
+            steerAnchor1[s] = to_local(C.fr, to_world(C.fr, carSteer));
+            steerAnchor2[s] = to_local(H.fr, to_world(H.fr, v3(S.tyreSteer[0], S.tyreSteer[1], S.tyreSteer[2])));
+        }
+    }
+    autoblip_step(P, X);
+    autoshift_step(P, X);
+    gearchanger_step(P, X);
+    { const float fAxleTorq = drivetrain_step(P, X); add_rel_torque(C, v3(0, 0, fAxleTorq)); add_rel_torque(bod[PD_BODY_AXLE], v3(0, 0, -fAxleTorq)); }
+    { /* driven wheels: angular velocity / lock state written by the drivetrain */
+        const int dl = (P.drivetrain.tractionType == 1) ? 0 : 2;
+        for (int w = dl; w < dl + 2; ++w) { sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_angularVelocity, X.wl[w].angularVelocity); sv.i(PD_OFF_TYRE(w) + PD_TYRE_o_isLocked, X.wl[w].isLocked); }
+    }
+    arb_step(P.arbK[0], C, bod[PD_BODY_HUB0], bod[PD_BODY_HUB0].fr.p, bod[PD_BODY_HUB1], bod[PD_BODY_HUB1].fr.p);
+    {
+        Body& A = bod[PD_BODY_AXLE];
+        const Frame f0 = axle_hub_frame(P.axle, A, 0), f1 = axle_hub_frame(P.axle, A, 1);
+        arb_step(P.arbK[1], C, A, f0.p, A, f1.p);
+    }
+
+    /* ---------------- physics->step(dt): dWorldStep ---------------- */
+    world_step(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt);
+
+    /* ---------------- Car::postStep ---------------- */
+    { /* updateTrackLocator (Car.cpp:717-771) */
+        const V3 bodyPos = C.fr.p;
+        const int nFat = T.info.nFatPoints;
+        if (P.nProbes > 0 && nFat > 0) {
+            /* Track::rayCastTrackBounds cache refresh (Track.cpp:505-510): only the first probe can trigger it */
+            const V3 cache = v3(c.pointCacheX, c.pointCacheY, c.pointCacheZ);
+            if (sqlen(cache - bodyPos) > 1.0f * 1.0f) { c.pointCacheX = bodyPos.x; c.pointCacheY = bodyPos.y; c.pointCacheZ = bodyPos.z; }
+        }
+        const V3 cachePos = v3(c.pointCacheX, c.pointCacheY, c.pointCacheZ);
+        const float nearR = (P.nProbes > 0) ? P.probeLength[0] : T.info.hashCellSize;
+        const float nearRSq = nearR * nearR;
+        /* probe rays */
+        float rax = bodyPos.x, raz = bodyPos.z;
+        float rbx[PD_MAX_PROBES], rbz[PD_MAX_PROBES], best[PD_MAX_PROBES];
+        for (int r = 0; r < P.nProbes; ++r) {
+            const V3 rayStart = to_world(C.fr, v3(0, 0, 0));
+            const V3 rayEndL = to_world(C.fr, v3(P.probeDir[r][0], P.probeDir[r][1], P.probeDir[r][2]) * P.probeLength[r]);
+            const V3 dir = norm(rayEndL - rayStart);
+            const V3 rayEnd = rayStart + dir * (P.probeLength[r] * 1.1f);
+            rax = rayStart.x; raz = rayStart.z;
+            rbx[r] = rayEnd.x; rbz[r] = rayEnd.z; best[r] = FLT_MAX;
+        }
+        float bestDistSq = FLT_MAX; int bestPoint = 0;
+        bool needBrute = false;
+        for (int r = 0; r < P.nProbes; ++r) if (!probe_walk(T, rax, raz, rbx[r], rbz[r], cachePos, nearRSq, best[r])) needBrute = true;
+        const bool haveNearest = nearest_point_grid(T, bodyPos, cachePos, nearRSq, bestPoint);
+        if (needBrute || !haveNearest) {
+            /* exhaustive form of the reference (car far off the indexed area) */
+            bestPoint = 0;
+            for (int r = 0; r < P.nProbes; ++r) best[r] = FLT_MAX;
+            for (int id = 0; id < nFat; ++id) {
+                const PdFatPoint& f = T.fat[id];
+                const V3 loc = v3(f.best[0], f.best[1], f.best[2]);
+                if (!(sqlen(cachePos - loc) < nearRSq)) continue;          /* VertexHash::queryNeighbours filter */
+                { const float dsq = sqlen(loc - bodyPos); if (bestDistSq > dsq) { bestDistSq = dsq; bestPoint = id; } }  /* getPointIdAtLocation */
+                const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
+                for (int r = 0; r < P.nProbes; ++r) {
+                    float ix, iz;
+                    if (line_intersection(rax, raz, rbx[r], rbz[r], f.left[0], f.left[2], g.left[0], g.left[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
+                    if (line_intersection(rax, raz, rbx[r], rbz[r], f.right[0], f.right[2], g.right[0], g.right[2], ix, iz)) { const float dx = rax - ix, dz = raz - iz; best[r] = tminf(best[r], sqrtf(dx * dx + dz * dz)); }
+                }
+            }
+        }
+        for (int r = 0; r < P.nProbes; ++r) c.probes[r] = (best[r] != FLT_MAX) ? best[r] : P.probeLength[r];
+        if (c.nearestTrackPointId != bestPoint) { c.oldTrackPointId = c.nearestTrackPointId; c.nearestTrackPointId = bestPoint; c.lastTrackPointTimestamp = (float)physicsTime; }
+        c.oldTrackLocation = c.trackLocation; c.trackLocation = 0;
+        if (bestPoint >= 0 && bestPoint < nFat) {
+            if (nFat >= 5) { /* getDistanceAlongSplineAtLocation (Track.cpp:609-629) */
+                int prevId = bestPoint - 1; if (prevId < 0) prevId = nFat - 1;
+                int nextId = bestPoint + 1; if (nextId >= nFat) nextId = 0;
+                int prevId2 = prevId - 1; if (prevId2 < 0) prevId2 = nFat - 1;
+                int nextId2 = nextId + 1; if (nextId2 >= nFat) nextId2 = 0;
+                int sid; float sdist;
+                if (spline_nearest(T, bodyPos, prevId2 * T.info.interpolateStep, nextId2 * T.info.interpolateStep, sid, sdist)) {
+                    c.splinePointId = sid; c.trackLocation = tclampf(sdist / T.info.computedTrackLength, 0.0f, 1.0f);
+                }
+            }
+            const V3 bodyFrontDir = norm(C.fr.az);
+            const V3 bodyVelDir = norm(C.v);
+            const PdFatPoint& pt = T.fat[bestPoint];
+            const V3 fwd = v3(pt.forwardDir[0], pt.forwardDir[1], pt.forwardDir[2]);
+            c.bodyVsTrack = dot(bodyFrontDir, fwd);
+            if ((c.speed * 3.6f) > 3.0f) c.velocityVsTrack = dot(bodyVelDir, fwd); else c.velocityVsTrack = 0.0f;
+        }
+    }
+    post_lookahead(P, T, C, c);
+    post_scoring(P, T, C, X, dt);
     c.episodeSteps++; c.thermalPrimed = 1;
     {
         int bad = 0;
-        for (int i = 0; i < PD_NUM_BODIES; ++i) { const Body& b = X.b[i]; if (!(finitef(b.fr.p.x) && finitef(b.fr.p.y) && finitef(b.fr.p.z) && finitef(b.v.x) && finitef(b.v.y) && finitef(b.v.z) && finitef(b.w.x) && finitef(b.w.y) && finitef(b.w.z) && finitef(b.q.w))) bad = 1; }
+        for (int i = 0; i < PD_NUM_BODIES; ++i) { const Body& b = bod[i]; if (!(finitef(b.fr.p.x) && finitef(b.fr.p.y) && finitef(b.fr.p.z) && finitef(b.v.x) && finitef(b.v.y) && finitef(b.v.z) && finitef(b.w.x) && finitef(b.w.y) && finitef(b.w.z) && finitef(b.q.w))) bad = 1; }
         if (bad) c.nanFlag = 1;
     }
-    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, X.b[i]);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, bod[i]);
     store_car(sv, c);
 }
 

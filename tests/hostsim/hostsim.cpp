@@ -6,7 +6,9 @@
  * without a GPU.  The product path is the CUDA library (libpd_b200.so); it has no CPU fallback and does not
  * link this file.
  */
-#include "../../projectd_core_b200/csrc/pd_tick.h"
+#include "../../projectd_core_b200/csrc/pd_quad.h"
+#include <pthread.h>
+#include <thread>
 #include "../../projectd_core_b200/csrc/host/pd_host.h"
 #include <cstdio>
 
@@ -20,6 +22,21 @@ struct HS {
         dev.segStart = track.segStart.data(); dev.segItems = track.segItems.data(); dev.ptStart = track.ptStart.data(); dev.ptItems = track.ptItems.data(); dev.grid = track.grid;
         dev.info = track.info;
     }
+};
+
+/* host stand-in for the GPU's quad shuffles: the four lanes of a car run as four threads that meet at a barrier */
+struct QuadShared { float slot[4][3]; int islot[4]; pthread_barrier_t bar; };
+struct QuadHost {
+    int lane; QuadShared* sh;
+    void sync() { pthread_barrier_wait(&sh->bar); }
+    float get(float v, int src) { sh->slot[lane][0] = v; sync(); float r = sh->slot[src][0]; sync(); return r; }
+    int get(int v, int src) { sh->islot[lane] = v; sync(); int r = sh->islot[src]; sync(); return r; }
+    pd::V3 get(pd::V3 v, int src) { sh->slot[lane][0] = v.x; sh->slot[lane][1] = v.y; sh->slot[lane][2] = v.z; sync(); pd::V3 r = pd::v3(sh->slot[src][0], sh->slot[src][1], sh->slot[src][2]); sync(); return r; }
+    float sum(float v) { /* the GPU butterfly: (l0+l1)+(l2+l3) */
+        sh->slot[lane][0] = v; sync(); float a = sh->slot[lane][0] + sh->slot[lane ^ 1][0]; sync();
+        sh->slot[lane][0] = a; sync(); float r = sh->slot[lane][0] + sh->slot[lane ^ 2][0]; sync(); return r; }
+    pd::V3 sum(pd::V3 v) { return pd::v3(sum(v.x), sum(v.y), sum(v.z)); }
+    bool all(bool p) { sh->islot[lane] = p ? 1 : 0; sync(); bool r = sh->islot[0] && sh->islot[1] && sh->islot[2] && sh->islot[3]; sync(); return r; }
 };
 
 extern "C" {
@@ -39,6 +56,13 @@ void hs_set_params(void* h, const PdCarParams* in) { ((HS*)h)->car.P = *in; }
 void hs_get_track_info(void* h, PdTrackInfo* out) { *out = ((HS*)h)->track.info; }
 void hs_get_spline_nodes(void* hv, float* xyz, float* dist) { HS* h = (HS*)hv; memcpy(xyz, h->track.splineXYZ.data(), h->track.splineXYZ.size() * 4); memcpy(dist, h->track.splineDist.data(), h->track.splineDist.size() * 4); }
 void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SV sv{rec, 1, 0}; pd::car_tick(h->car.P, h->dev, sv, dt, time); }
+void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
+    HS* h = (HS*)hv; QuadShared sh; pthread_barrier_init(&sh.bar, nullptr, 4);
+    std::thread th[4];
+    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SV sv{rec, 1, 0}; float scr[PD_GSCR_WORDS]; pd::car_tick_quad(h->car.P, h->dev, sv, dt, time, ex, scr, 1); });
+    for (int l = 0; l < 4; ++l) th[l].join();
+    pthread_barrier_destroy(&sh.bar);
+}
 void hs_teleport_point(void* hv, uint32_t* rec, int pointId, double time) { HS* h = (HS*)hv; pd::SV sv{rec, 1, 0}; pd::car_teleport_to_point(h->car.P, h->dev, sv, pointId, time); }
 int hs_point_id_at_distance(void* hv, float d) { return pd::point_id_at_distance(((HS*)hv)->dev, d); }
 void hs_raycast(void* hv, int n, const float* in, float* out) {
