@@ -81,12 +81,15 @@ struct TrackModel {
     std::vector<float> fatDist;       /* Track::fatPointDistances */
     std::vector<float> splineXYZ, splineDist;
     PdBoundGrid grid;
+    PdBoundGrid colGrid;                         /* x-z grid of triangle lists for vertical rays */
+    std::vector<int32_t> colStart, colItems;     /* CSR per cell: triangle indices (leaf order of `tris`) */
     std::vector<int32_t> segStart, segItems;   /* CSR per cell: boundary segments, item = id * 2 + side (0 left, 1 right) */
     std::vector<int32_t> ptStart, ptItems;     /* CSR per cell: fat point ids (by `best`) */
 };
 void load_track(const std::string& basePath, const std::string& name, TrackModel& out);
 /* synthetic track generator for config 4 (large mesh): closed loop of `nPoints` spline points, tessellated */
 void make_synthetic_track(int targetTris, float lengthMeters, TrackModel& out);
+void build_column_grid(TrackModel& out);
 void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& surf, TrackModel& out);
 void finish_track_points(TrackModel& out, bool closedLoop, float cellSize);
 

@@ -96,6 +96,46 @@ void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& sur
         out.triSurf[i] = surf[t];
     }
     out.info.nTris = (int32_t)nt; out.info.nNodes = (int32_t)out.nodes.size();
+    build_column_grid(out);
+}
+
+/* Index for VERTICAL rays (every ray of the hot path is one: wheel rays Tyre.cpp:478-481, the teleport ray
+ * Car.cpp:1243): uniform x-z grid, each cell lists the triangles whose padded x-z box touches it.  The cell
+ * size doubles from 2 m until the lists stay below ~6 entries per triangle and the grid below 4M cells. */
+void build_column_grid(TrackModel& out) {
+    const size_t nt = out.triSurf.size();
+    PdBoundGrid& G = out.colGrid; memset(&G, 0, sizeof(G));
+    out.colStart.assign(1, 0); out.colItems.clear();
+    if (nt == 0) return;
+    float x0 = 3.4e38f, x1 = -3.4e38f, z0 = 3.4e38f, z1 = -3.4e38f;
+    std::vector<float> bx0(nt), bx1(nt), bz0(nt), bz1(nt);
+    for (size_t t = 0; t < nt; ++t) {
+        const float* p = &out.tris[t * 9];
+        const float ax = p[0], az = p[2], bx = p[0] + p[3], bz = p[2] + p[5], cx = p[0] + p[6], cz = p[2] + p[8];
+        bx0[t] = std::min(ax, std::min(bx, cx)) - 1e-3f; bx1[t] = std::max(ax, std::max(bx, cx)) + 1e-3f;
+        bz0[t] = std::min(az, std::min(bz, cz)) - 1e-3f; bz1[t] = std::max(az, std::max(bz, cz)) + 1e-3f;
+        x0 = std::min(x0, bx0[t]); x1 = std::max(x1, bx1[t]); z0 = std::min(z0, bz0[t]); z1 = std::max(z1, bz1[t]);
+    }
+    for (float cell = 2.0f;; cell *= 2.0f) {
+        G.cell = cell; G.invCell = 1.0f / cell; G.ox = x0 - cell; G.oz = z0 - cell;
+        G.nx = (int)ceilf((x1 - G.ox) * G.invCell) + 2; G.nz = (int)ceilf((z1 - G.oz) * G.invCell) + 2;
+        const double cells = (double)G.nx * G.nz;
+        double pairs = 0;
+        for (size_t t = 0; t < nt; ++t) pairs += (double)((int)floorf((bx1[t] - G.ox) * G.invCell) - (int)floorf((bx0[t] - G.ox) * G.invCell) + 1) * ((int)floorf((bz1[t] - G.oz) * G.invCell) - (int)floorf((bz0[t] - G.oz) * G.invCell) + 1);
+        if ((pairs <= 6.0 * nt && cells <= 4.0e6) || cell >= 64.0f) break;
+    }
+    const size_t nc = (size_t)G.nx * G.nz;
+    std::vector<int32_t> count(nc + 1, 0);
+    auto range = [&](size_t t, int& ix0, int& ix1, int& iz0, int& iz1) {
+        ix0 = std::max(0, (int)floorf((bx0[t] - G.ox) * G.invCell)); ix1 = std::min(G.nx - 1, (int)floorf((bx1[t] - G.ox) * G.invCell));
+        iz0 = std::max(0, (int)floorf((bz0[t] - G.oz) * G.invCell)); iz1 = std::min(G.nz - 1, (int)floorf((bz1[t] - G.oz) * G.invCell));
+    };
+    for (size_t t = 0; t < nt; ++t) { int a, b, c, d; range(t, a, b, c, d); for (int iz = c; iz <= d; ++iz) for (int ix = a; ix <= b; ++ix) count[(size_t)iz * G.nx + ix + 1]++; }
+    for (size_t c = 0; c < nc; ++c) count[c + 1] += count[c];
+    out.colStart = count;
+    out.colItems.assign((size_t)count[nc], 0);
+    std::vector<int32_t> fill(count.begin(), count.end() - 1);
+    for (size_t t = 0; t < nt; ++t) { int a, b, c, d; range(t, a, b, c, d); for (int iz = c; iz <= d; ++iz) for (int ix = a; ix <= b; ++ix) out.colItems[(size_t)fill[(size_t)iz * G.nx + ix]++] = (int32_t)t; }
 }
 
 /* BSpline3d::interpolate (Core/Spline3d.cpp:151-160), same operation order */

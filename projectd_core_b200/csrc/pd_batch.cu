@@ -25,14 +25,15 @@
 using namespace pd;
 
 #define PD_BLOCK 64
+#define PD_QBLOCK 64   /* threads per block of the quad kernel = stride of the lane-interleaved solver scratch */
 
 /* ------------------------------------------------------------------ kernels ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(PD_BLOCK) k_tick(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
+__global__ void __launch_bounds__(PD_BLOCK) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (mask && !mask[e]) return;
-    SV sv{state, (size_t)n, (size_t)e};
-    car_tick(*P, T, sv, dt, time);
+    SV sv = sv_tiled(state, (size_t)e);
+    car_tick(P, T, sv, dt, time);
 }
 
 /* exchange policy of pd_quad.h on the GPU: shuffles inside the quad, with the quad's own member mask */
@@ -47,28 +48,28 @@ struct QuadShfl {
 };
 
 /* the tick, four lanes per car: thread t -> env t / 4, lane t % 4 */
-__global__ void __launch_bounds__(64) k_tick_quad(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
+__global__ void __launch_bounds__(64) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = t >> 2;
     if (e >= n) return;                       /* whole quads leave together */
     if (mask && !mask[e]) return;
     QuadShfl ex; ex.lane = t & 3; ex.base = (threadIdx.x & 31) & ~3; ex.mask = 0xFu << ex.base;
-    SV sv{state, (size_t)n, (size_t)e};
+    SV sv = sv_tiled(state, (size_t)e);
     extern __shared__ float pd_smem[];          /* solver scratch: PD_GSCR_WORDS x blockDim, lane-interleaved */
-    car_tick_quad(*P, T, sv, dt, time, ex, pd_smem + threadIdx.x, (int)blockDim.x);
+    car_tick_quad<PD_QBLOCK>(P, T, sv, dt, time, ex, pd_smem + threadIdx.x);
 }
 
 __global__ void k_broadcast(uint32_t* state, int n, const uint32_t* __restrict__ rec) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n * PD_STATE_WORDS) return;
-    state[i] = rec[i / n];
+    if (i >= (size_t)n * PD_STATE_WORDS) return;   /* n = padded env count (multiple of PD_TILE) */
+    state[i] = rec[(i / PD_TILE) % PD_STATE_WORDS];
 }
 
 __global__ void __launch_bounds__(PD_BLOCK) k_teleport(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int n, const int32_t* __restrict__ mask, const int32_t* __restrict__ pointIds, double time) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (mask && !mask[e]) return;
-    SV sv{state, (size_t)n, (size_t)e};
+    SV sv = sv_tiled(state, (size_t)e);
     car_teleport_to_point(*P, T, sv, pointIds[e], time);
 }
 
@@ -87,7 +88,7 @@ __global__ void k_pick_points(TrackDev T, const uint32_t* __restrict__ state, in
     if (mask && !mask[e]) return;
     float u = 0.0f;
     if (distNorm) u = distNorm[e];
-    else if (mode == PD_TELEPORT_NEAREST) u = u2f(state[(size_t)(PD_OFF_CAR + PD_CAR_o_trackLocation) * n + e]);
+    else if (mode == PD_TELEPORT_NEAREST) u = u2f(state[state_index(PD_OFF_CAR + PD_CAR_o_trackLocation, (size_t)e)]);
     else if (mode == PD_TELEPORT_RANDOM) { u = pd_uniform(seed, idOffset + (uint64_t)e, episodeCtr[e]); episodeCtr[e]++; }
     pointIds[e] = point_id_at_distance(T, u);
 }
@@ -95,7 +96,7 @@ __global__ void k_pick_points(TrackDev T, const uint32_t* __restrict__ state, in
 __global__ void k_set_controls(uint32_t* state, int n, const float* __restrict__ ctl, const int8_t* __restrict__ gears, int smooth) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    SV sv{state, (size_t)n, (size_t)e};
+    SV sv = sv_tiled(state, (size_t)e);
     const int o = PD_OFF_CAR;
     sv.f(o + PD_CAR_o_ctlSteer, ctl[e * 5 + 0]); sv.f(o + PD_CAR_o_ctlClutch, ctl[e * 5 + 1]); sv.f(o + PD_CAR_o_ctlBrake, ctl[e * 5 + 2]);
     sv.f(o + PD_CAR_o_ctlHandBrake, ctl[e * 5 + 3]); sv.f(o + PD_CAR_o_ctlGas, ctl[e * 5 + 4]);
@@ -110,7 +111,7 @@ __global__ void k_set_actions(uint32_t* state, int n, const float* __restrict__ 
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (zeroMask && !zeroMask[e]) return;
-    SV sv{state, (size_t)n, (size_t)e};
+    SV sv = sv_tiled(state, (size_t)e);
     const int o = PD_OFF_CAR;
     const float a0 = zeroMask ? 0.0f : act[e * 2 + 0], a1 = zeroMask ? 0.0f : act[e * 2 + 1];
     sv.f(o + PD_CAR_o_ctlSteer, a0); sv.f(o + PD_CAR_o_ctlClutch, 0.0f); sv.f(o + PD_CAR_o_ctlBrake, 0.0f); sv.f(o + PD_CAR_o_ctlHandBrake, 0.0f);
@@ -121,7 +122,7 @@ __global__ void k_set_actions(uint32_t* state, int n, const float* __restrict__ 
 __global__ void k_observe(const uint32_t* state, int n, float* __restrict__ obs) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    SV sv{const_cast<uint32_t*>(state), (size_t)n, (size_t)e};
+    SV sv = sv_tiled(const_cast<uint32_t*>(state), (size_t)e);
     float o[PD_OBS_DIM];
     car_observe(sv, o);
     for (int k = 0; k < PD_OBS_DIM; ++k) obs[(size_t)e * PD_OBS_DIM + k] = o[k];
@@ -130,7 +131,7 @@ __global__ void k_observe(const uint32_t* state, int n, float* __restrict__ obs)
 __global__ void k_rewards(const uint32_t* state, int n, float* stepReward, float* totalReward, int32_t* flags) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    SV sv{const_cast<uint32_t*>(state), (size_t)n, (size_t)e};
+    SV sv = sv_tiled(const_cast<uint32_t*>(state), (size_t)e);
     if (stepReward) stepReward[e] = sv.f(PD_OFF_CAR + PD_CAR_o_stepReward);
     if (totalReward) totalReward[e] = sv.f(PD_OFF_CAR + PD_CAR_o_totalReward);
     if (flags) flags[e] = (sv.i(PD_OFF_CAR + PD_CAR_o_collisionFlag) ? 1 : 0) | (sv.i(PD_OFF_CAR + PD_CAR_o_outOfTrackFlag) ? 2 : 0);
@@ -142,7 +143,7 @@ __global__ void k_env_done(const uint32_t* state, int n, double timeAfter, float
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (e < n) {
-        SV sv{const_cast<uint32_t*>(state), (size_t)n, (size_t)e};
+        SV sv = sv_tiled(const_cast<uint32_t*>(state), (size_t)e);
         const int o = PD_OFF_CAR;
         float r = sv.f(o + PD_CAR_o_stepReward);
         int d = 0;
@@ -174,21 +175,22 @@ __global__ void k_env_done(const uint32_t* state, int n, double timeAfter, float
 __global__ void k_clear_nan(uint32_t* state, int n, const int32_t* __restrict__ mask) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n || !mask[e]) return;
-    state[(size_t)(PD_OFF_CAR + PD_CAR_o_nanFlag) * n + e] = 0;
+    state[state_index(PD_OFF_CAR + PD_CAR_o_nanFlag, (size_t)e)] = 0;
 }
 
 __global__ void k_raycast(TrackDev T, int n, const float* __restrict__ rays, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = rays + (size_t)i * 7; float* q = out + (size_t)i * 8;
-    const RayHit r = ray_cast(T, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), p[6]);
+    const bool down = (p[3] == 0.0f && p[4] == -1.0f && p[5] == 0.0f);
+    const RayHit r = down ? ray_cast_down(T, v3(p[0], p[1], p[2]), p[6]) : ray_cast(T, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), p[6]);
     q[0] = (float)r.hit; q[1] = r.pos.x; q[2] = r.pos.y; q[3] = r.pos.z; q[4] = r.normal.x; q[5] = r.normal.y; q[6] = r.normal.z; q[7] = (float)r.surface;
 }
 
 __global__ void k_set_pressure(uint32_t* state, int n, int wheel, float value) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    state[(size_t)(PD_OFF_TYRE(wheel) + PD_TYRE_o_pressureStatic) * n + e] = f2u(value);
+    state[state_index(PD_OFF_TYRE(wheel) + PD_TYRE_o_pressureStatic, (size_t)e)] = f2u(value);
 }
 
 /* ------------------------------------------------------------------ host side ------------------------------------------------------------------ */
@@ -246,7 +248,10 @@ template <class T> static int upload(pd_batch* b, const T** p, const std::vector
 }
 static inline int grid(int n, int block) { return (n + block - 1) / block; }
 /* small batches: one warp per block so that every SM gets work (148 SMs) */
-static inline int tick_block(int n) { return n * 4 <= 148 * 64 ? 32 : 64; }
+static inline int tick_block(int) { return PD_QBLOCK; }
+/* batches up to PD_QUAD_MAX_ENVS: four lanes per car (latency-bound regime, more warps per car);
+ * larger batches: one thread per car (throughput regime, no redundant scalar work) */
+#define PD_QUAD_MAX_ENVS 16384
 
 static int sync_params(pd_batch* b) {
     if (!b->paramsDirty) return PD_OK;
@@ -278,9 +283,13 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = upload(b, &b->dev.ptStart, b->track.ptStart))) return rc;
     if ((rc = upload(b, &b->dev.ptItems, b->track.ptItems))) return rc;
     b->dev.grid = b->track.grid;
+    if ((rc = upload(b, &b->dev.colStart, b->track.colStart))) return rc;
+    if ((rc = upload(b, &b->dev.colItems, b->track.colItems))) return rc;
+    b->dev.colGrid = b->track.colGrid;
     b->dev.info = b->track.info;
     const size_t n = (size_t)n_envs;
-    if ((rc = dalloc(b, &b->dState, n * PD_STATE_WORDS))) return rc;
+    const size_t nPad = (n + PD_TILE - 1) / PD_TILE * PD_TILE;
+    if ((rc = dalloc(b, &b->dState, nPad * PD_STATE_WORDS))) return rc;
     if ((rc = dalloc(b, &b->dObs, n * PD_OBS_DIM))) return rc;
     if ((rc = dalloc(b, &b->dCtl, n * 5))) return rc;
     if ((rc = dalloc(b, &b->dGears, n * 3))) return rc;
@@ -303,14 +312,21 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     CK(cudaMemsetAsync(b->dObs, 0, n * PD_OBS_DIM * 4, b->stream));
     /* initial record: built once with the same device functions compiled for the host, then broadcast */
     std::vector<uint32_t> rec(PD_STATE_WORDS, 0);
-    { SV sv{rec.data(), 1, 0}; car_init_state(b->car.P, sv); }
+    { SV sv = sv_flat(rec.data()); car_init_state(b->car.P, sv); }
     uint32_t* dRec = nullptr; if ((rc = dalloc(b, &dRec, PD_STATE_WORDS))) return rc;
     CK(cudaMemcpyAsync(dRec, rec.data(), PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream));
-    k_broadcast<<<grid((int)std::min<size_t>(n * PD_STATE_WORDS, 0x7fffffff), 256), 256, 0, b->stream>>>(b->dState, n_envs, dRec); b->launches++;
+    k_broadcast<<<grid((int)std::min<size_t>(nPad * PD_STATE_WORDS, 0x7fffffff), 256), 256, 0, b->stream>>>(b->dState, (int)nPad, dRec); b->launches++;
     CK(cudaGetLastError());
     if ((rc = sync_params(b))) return rc;
     CK(cudaStreamSynchronize(b->stream));
     return PD_OK;
+}
+
+static void launch_tick(pd_batch* b, float dt, const int32_t* mask) {
+    if (b->n <= PD_QUAD_MAX_ENVS)
+        k_tick_quad<<<grid(b->n * 4, PD_QBLOCK), PD_QBLOCK, (size_t)PD_QBLOCK * PD_GSCR_WORDS * 4, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask);
+    else
+        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask);
 }
 
 extern "C" {
@@ -397,7 +413,7 @@ int pd_step(pd_batch* b, float dt, int n_ticks) {
     if (!b || n_ticks < 0) return PD_ERR_ARG;
     int rc = sync_params(b); if (rc) return rc;
     for (int t = 0; t < n_ticks; ++t) {
-        { const int blk = tick_block(b->n); k_tick_quad<<<grid(b->n * 4, blk), blk, (size_t)blk * PD_GSCR_WORDS * 4, b->stream>>>(b->dP, b->dev, b->dState, b->n, dt, b->time, nullptr); b->launches++; }
+        launch_tick(b, dt, nullptr); b->launches++;
         b->time += (double)dt; b->lastDt = dt;
     }
     CK(cudaGetLastError()); return PD_OK;
@@ -469,7 +485,7 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     const int n = b->n;
     float* rew = reward_dev ? reward_dev : b->dReward; int32_t* done = done_dev ? done_dev : b->dDone;
     k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, nullptr);
-    k_tick_quad<<<grid(n * 4, tick_block(n)), tick_block(n), (size_t)tick_block(n) * PD_GSCR_WORDS * 4, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, nullptr);
+    launch_tick(b, dt, nullptr);
     k_env_done<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, b->time, rew, done, b->dEnvReturn, b->dEnvLen, b->dStats);
     b->time += (double)dt; b->lastDt = dt;
     /* auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) + one zero-action tick */
@@ -477,7 +493,7 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, done, b->dPoints, b->time);
     k_clear_nan<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, done);
     k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, done);
-    k_tick_quad<<<grid(n * 4, tick_block(n)), tick_block(n), (size_t)tick_block(n) * PD_GSCR_WORDS * 4, b->stream>>>(b->dP, b->dev, b->dState, n, dt, b->time, done);
+    launch_tick(b, dt, done);
     k_observe<<<grid(n, 128), 128, 0, b->stream>>>(b->dState, n, obs_dev ? obs_dev : b->dObs);
     b->launches += 9;
     CK(cudaGetLastError()); return PD_OK;
@@ -491,21 +507,29 @@ int pd_env_stats(pd_batch* b, double* out8, int reset) {
 
 int pd_get_state(pd_batch* b, int env, uint32_t* record) {
     if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
-    CK(cudaMemcpy2DAsync(record, 4, b->dState + env, (size_t)b->n * 4, 4, PD_STATE_WORDS, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpy2DAsync(record, 4, b->dState + state_index(0, (size_t)env), (size_t)PD_TILE * 4, 4, PD_STATE_WORDS, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream)); return PD_OK;
 }
 int pd_set_state(pd_batch* b, int env, const uint32_t* record) {
     if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
-    CK(cudaMemcpy2DAsync(b->dState + env, (size_t)b->n * 4, record, 4, 4, PD_STATE_WORDS, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpy2DAsync(b->dState + state_index(0, (size_t)env), (size_t)PD_TILE * 4, record, 4, 4, PD_STATE_WORDS, cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream)); return PD_OK;
 }
 int pd_snapshot(pd_batch* b, uint32_t* host_buf) {
     if (!b || !host_buf) return PD_ERR_ARG;
-    CK(cudaMemcpyAsync(host_buf, b->dState, (size_t)b->n * PD_STATE_WORDS * 4, cudaMemcpyDeviceToHost, b->stream)); CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+    const size_t nPad = ((size_t)b->n + PD_TILE - 1) / PD_TILE * PD_TILE;
+    std::vector<uint32_t> tmp(nPad * PD_STATE_WORDS);
+    CK(cudaMemcpyAsync(tmp.data(), b->dState, tmp.size() * 4, cudaMemcpyDeviceToHost, b->stream)); CK(cudaStreamSynchronize(b->stream));
+    for (int w = 0; w < PD_STATE_WORDS; ++w) for (size_t e = 0; e < (size_t)b->n; ++e) host_buf[(size_t)w * b->n + e] = tmp[state_index(w, e)];
+    return PD_OK;
 }
 int pd_restore(pd_batch* b, const uint32_t* host_buf) {
     if (!b || !host_buf) return PD_ERR_ARG;
-    CK(cudaMemcpyAsync(b->dState, host_buf, (size_t)b->n * PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream)); CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+    const size_t nPad = ((size_t)b->n + PD_TILE - 1) / PD_TILE * PD_TILE;
+    std::vector<uint32_t> tmp(nPad * PD_STATE_WORDS);
+    CK(cudaMemcpyAsync(tmp.data(), b->dState, tmp.size() * 4, cudaMemcpyDeviceToHost, b->stream)); CK(cudaStreamSynchronize(b->stream));   /* keeps the padding envs */
+    for (int w = 0; w < PD_STATE_WORDS; ++w) for (size_t e = 0; e < (size_t)b->n; ++e) tmp[state_index(w, e)] = host_buf[(size_t)w * b->n + e];
+    CK(cudaMemcpyAsync(b->dState, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, b->stream)); CK(cudaStreamSynchronize(b->stream)); return PD_OK;
 }
 int pd_get_params(const pd_batch* b, PdCarParams* out) { if (!b || !out) return PD_ERR_ARG; *out = b->car.P; return PD_OK; }
 int pd_get_track_info(const pd_batch* b, PdTrackInfo* out) { if (!b || !out) return PD_ERR_ARG; *out = b->track.info; return PD_OK; }
@@ -514,7 +538,7 @@ int pd_get_car_state(pd_batch* b, int env, void* outv) {
     if (!b || !outv) return PD_ERR_ARG;
     std::vector<uint32_t> rec(PD_STATE_WORDS);
     int rc = pd_get_state(b, env, rec.data()); if (rc) return rc;
-    SV sv{rec.data(), 1, 0};
+    SV sv = sv_flat(rec.data());
     PdCarStateOut s; memset(&s, 0, sizeof(s));
     CarS c; load_car(sv, c);
     Body C; load_body(sv, PD_BODY_CHASSIS, C);

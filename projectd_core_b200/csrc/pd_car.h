@@ -317,7 +317,7 @@ PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, const Car
     const V3 worldPosition = hubFrame.p;
     if (!finitef(t.angularVelocity)) t.angularVelocity = 0;
 
-    const RayHit hit = ray_cast(T, v3(worldPosition.x, worldPosition.y + 2.0f, worldPosition.z), v3(0.0f, -1.0f, 0.0f), 3.0f);
+    const RayHit hit = ray_cast_down(T, v3(worldPosition.x, worldPosition.y + 2.0f, worldPosition.z), 3.0f);
     float gripMod = 0, dirtAdditiveK = 0;
     bool contact = hit.hit && !(hubFrame.ay.y <= 0.35f);
     if (!contact) {

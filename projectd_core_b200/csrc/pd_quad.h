@@ -37,8 +37,8 @@ PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
     }
 }
 
-template <class Ex>
-PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SV& sv, float dt, double physicsTime, Ex& ex, float* scratch, int scratchStride) {
+template <int STRIDE, class Ex>
+PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SV& sv, float dt, double physicsTime, Ex& ex, float* scratch) {
     const int lane = ex.lane;
     const bool front = lane < 2;
     CarCtx X; X.dt = dt; X.time = physicsTime;
@@ -172,7 +172,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SV& sv,
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
-    GScr G; G.p = scratch; G.s = scratchStride;
+    GScr<STRIDE> G; G.p = scratch;
     if (front) build_strut(P, P.strut[lane], C, W, S, steerA1, steerA2, hinv, X.dballErp, X.dballCfm, G);
     else if (lane == 2) build_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G);
     else build_tank(P, S, C, hinv, G);

@@ -109,41 +109,45 @@ PD_HD void plane_space(V3 n, V3& p, V3& q) {
     }
 }
 
-/* Scratch of one joint group, addressed with a stride so that the same code runs on
- *   - shared memory interleaved over the lanes of a block (GPU: element k of lane t at base[k * blockDim + t],
- *     i.e. every lane owns one bank column -> conflict-free), and
+/* Scratch of one joint group, addressed with a COMPILE-TIME stride so that the same code runs on
+ *   - shared memory interleaved over the lanes of a block (GPU: element k of lane t at base[k * blockDim + t]:
+ *     every lane owns one bank column -> conflict-free, and with all loops unrolled every access is an LDS/STS
+ *     with an immediate offset), and
  *   - a plain local array (host debugging build, stride 1).
- * Layout (words): JA 11x6 | JB 11x6 | Y 11x7 ([U | r], later L^-1[U | r], column 6 ends as lambda) |
+ * Every group is padded to PD_GMAX = 11 rows (pad rows: zero Jacobians, unit diagonal) so that the four lanes of
+ * a quad run the same straight-line code whatever their group's real size (11 / 11 / 5 / 6 rows).
+ * Layout (words): JA 11x6 | JB 11x6 | Y 11x7 ([U | c], then [U | r], then L^-1[U | r]; column 6 ends as lambda) |
  * D packed lower 66 (in place: unit-lower L below the diagonal) | dg 11 (cfm per row, then the D diagonal). */
 #define PD_GSCR_WORDS 286
-struct GScr {
-    float* p; int s; int n, hasB;
-    PD_HD float& JA(int i, int k) const { return p[(i * 6 + k) * s]; }
-    PD_HD float& JB(int i, int k) const { return p[(66 + i * 6 + k) * s]; }
-    PD_HD float& Y(int i, int k) const { return p[(132 + i * 7 + k) * s]; }
-    PD_HD float& D(int i, int j) const { return p[(209 + i * (i + 1) / 2 + j) * s]; }   /* j <= i */
-    PD_HD float& dg(int i) const { return p[(275 + i) * s]; }
+template <int S> struct GScr {
+    float* p;
+    PD_HD float& JA(int i, int k) const { return p[(i * 6 + k) * S]; }
+    PD_HD float& JB(int i, int k) const { return p[(66 + i * 6 + k) * S]; }
+    PD_HD float& Y(int i, int k) const { return p[(132 + i * 7 + k) * S]; }
+    PD_HD float& D(int i, int j) const { return p[(209 + i * (i + 1) / 2 + j) * S]; }   /* j <= i */
+    PD_HD float& dg(int i) const { return p[(275 + i) * S]; }
 };
-PD_HD void gset6(const GScr& G, int which, int i, V3 l, V3 a) {   /* which: 0 JA, 1 JB, 2 U (= Y cols 0..5) */
-    if (which == 0) { G.JA(i, 0) = l.x; G.JA(i, 1) = l.y; G.JA(i, 2) = l.z; G.JA(i, 3) = a.x; G.JA(i, 4) = a.y; G.JA(i, 5) = a.z; }
-    else if (which == 1) { G.JB(i, 0) = l.x; G.JB(i, 1) = l.y; G.JB(i, 2) = l.z; G.JB(i, 3) = a.x; G.JB(i, 4) = a.y; G.JB(i, 5) = a.z; }
-    else { G.Y(i, 0) = l.x; G.Y(i, 1) = l.y; G.Y(i, 2) = l.z; G.Y(i, 3) = a.x; G.Y(i, 4) = a.y; G.Y(i, 5) = a.z; }
-}
-PD_HD void zero_group(GScr& G, int n, int hasB, float cfm) {
-    G.n = n; G.hasB = hasB;
-    for (int i = 0; i < n; ++i) { for (int k = 0; k < 6; ++k) { G.JA(i, k) = 0; G.JB(i, k) = 0; G.Y(i, k) = 0; } G.Y(i, 6) = 0; G.dg(i) = cfm; }
+/* all rows zero; pad rows get cfm = h so that their diagonal becomes cfm/h = 1 */
+template <class GS> PD_HD void zero_group(const GS& G, int n, float cfm, float h) {
+    PD_UNROLL
+    for (int i = 0; i < PD_GMAX; ++i) {
+        PD_UNROLL
+        for (int k = 0; k < 6; ++k) { G.JA(i, k) = 0; G.JB(i, k) = 0; G.Y(i, k) = 0; }
+        G.Y(i, 6) = 0; G.dg(i) = (i < n) ? cfm : h;
+    }
 }
 /* dball row between the chassis (body 0 -> U) and an own body (body 1 -> JA); c goes to Y(i,6) */
-PD_HD void grow_dball(const GScr& G, int i, const Body& b0, const Body& b1, V3 anchor1, V3 anchor2, float target, float k, float cfm) {
+template <class GS> PD_HD void grow_dball(const GS& G, int i, const Body& b0, const Body& b1, V3 anchor1, V3 anchor2, float target, float k, float cfm) {
     float J0[6], J1[6], c;
     row_dball(b0, b1, anchor1, anchor2, target, k, J0, J1, c);
+    PD_UNROLL
     for (int q = 0; q < 6; ++q) { G.Y(i, q) = J0[q]; G.JA(i, q) = J1[q]; }
     G.Y(i, 6) = c; G.dg(i) = cfm;
 }
 
 /* group "tank": fixed joint tank(b0) <-> chassis(b1)  (fixed.cpp getInfo2: rows 0-2 linear, 3-5 angular) */
-PD_HD void build_tank(const PdCarParams& P, const Body& T, const Body& C, float fps, GScr& G) {
-    zero_group(G, 6, 0, P.worldCFM);
+template <class GS> PD_HD void build_tank(const PdCarParams& P, const Body& T, const Body& C, float fps, const GS& G) {
+    zero_group(G, 6, P.worldCFM, 1.0f / fps);
     const V3 ofs = rot(T.fr, v3(P.tankOffset[0], P.tankOffset[1], P.tankOffset[2]));
     /* linear rows: J1l = I, J1a = [ofs]x (rows), J2l = -I */
     G.JA(0, 0) = 1; G.JA(1, 1) = 1; G.JA(2, 2) = 1;
@@ -151,15 +155,16 @@ PD_HD void build_tank(const PdCarParams& P, const Body& T, const Body& C, float 
     G.Y(0, 0) = -1; G.Y(1, 1) = -1; G.Y(2, 2) = -1;
     const float k = fps * P.worldERP;
     G.Y(0, 6) = k * (C.fr.p.x - T.fr.p.x + ofs.x); G.Y(1, 6) = k * (C.fr.p.y - T.fr.p.y + ofs.y); G.Y(2, 6) = k * (C.fr.p.z - T.fr.p.z + ofs.z);
-    for (int i = 0; i < 3; ++i) { G.JA(3 + i, 3 + i) = 1; G.Y(3 + i, 3 + i) = -1; }
+    G.JA(3, 3) = 1; G.JA(4, 4) = 1; G.JA(5, 5) = 1; G.Y(3, 3) = -1; G.Y(4, 4) = -1; G.Y(5, 5) = -1;
     Quat qrel; qrel.w = P.tankQrel[0]; qrel.x = P.tankQrel[1]; qrel.y = P.tankQrel[2]; qrel.z = P.tankQrel[3];
     float c3[3]; fixed_orientation_c(T, C, qrel, fps * P.worldERP * 2.0f, c3);
     G.Y(3, 6) = c3[0]; G.Y(4, 6) = c3[1]; G.Y(5, 6) = c3[2];
 }
 
 /* groups "strut": A = hub, B = strut body */
-PD_HD void build_strut(const PdCarParams& P, const PdStrut& S, const Body& C, const Body& H, const Body& B, V3 steerA1, V3 steerA2, float fps, float dballErp, float dballCfm, GScr& G) {
-    zero_group(G, 11, 1, P.worldCFM);
+template <class GS> PD_HD void build_strut(const PdCarParams& P, const PdStrut& S, const Body& C, const Body& H, const Body& B, V3 steerA1, V3 steerA2, float fps, float dballErp, float dballCfm, const GS& G) {
+    zero_group(G, 11, P.worldCFM, 1.0f / fps);
+    PD_UNROLL
     for (int l = 0; l < 3; ++l) {
         V3 a1 = v3(S.link[l].anchor1[0], S.link[l].anchor1[1], S.link[l].anchor1[2]);
         V3 a2 = v3(S.link[l].anchor2[0], S.link[l].anchor2[1], S.link[l].anchor2[2]);
@@ -168,15 +173,17 @@ PD_HD void build_strut(const PdCarParams& P, const PdStrut& S, const Body& C, co
     }
     { /* slider (b0 = strut body, b1 = hub): rows 3..7 */
         Quat qrel; qrel.w = S.sliderQrel[0]; qrel.x = S.sliderQrel[1]; qrel.y = S.sliderQrel[2]; qrel.z = S.sliderQrel[3];
-        for (int i = 0; i < 3; ++i) { G.JB(3 + i, 3 + i) = 1; G.JA(3 + i, 3 + i) = -1; }
+        G.JB(3, 3) = 1; G.JB(4, 4) = 1; G.JB(5, 5) = 1; G.JA(3, 3) = -1; G.JA(4, 4) = -1; G.JA(5, 5) = -1;
         float c3[3]; fixed_orientation_c(B, H, qrel, fps * P.worldERP * 2.0f, c3);
         G.Y(3, 6) = c3[0]; G.Y(4, 6) = c3[1]; G.Y(5, 6) = c3[2];
         V3 c = H.fr.p - B.fr.p;
         const V3 ax1 = rot(B.fr, v3(S.sliderAxis1[0], S.sliderAxis1[1], S.sliderAxis1[2]));
         V3 p, q; plane_space(ax1, p, q);
         const V3 cp = cross(c, p) * 0.5f, cq = cross(c, q) * 0.5f;
-        gset6(G, 1, 6, p, cp); gset6(G, 0, 6, neg(p), cp);
-        gset6(G, 1, 7, q, cq); gset6(G, 0, 7, neg(q), cq);
+        G.JB(6, 0) = p.x; G.JB(6, 1) = p.y; G.JB(6, 2) = p.z; G.JB(6, 3) = cp.x; G.JB(6, 4) = cp.y; G.JB(6, 5) = cp.z;
+        G.JA(6, 0) = -p.x; G.JA(6, 1) = -p.y; G.JA(6, 2) = -p.z; G.JA(6, 3) = cp.x; G.JA(6, 4) = cp.y; G.JA(6, 5) = cp.z;
+        G.JB(7, 0) = q.x; G.JB(7, 1) = q.y; G.JB(7, 2) = q.z; G.JB(7, 3) = cq.x; G.JB(7, 4) = cq.y; G.JB(7, 5) = cq.z;
+        G.JA(7, 0) = -q.x; G.JA(7, 1) = -q.y; G.JA(7, 2) = -q.z; G.JA(7, 3) = cq.x; G.JA(7, 4) = cq.y; G.JA(7, 5) = cq.z;
         const V3 ofs = rot(H.fr, v3(S.sliderOffset[0], S.sliderOffset[1], S.sliderOffset[2]));
         c = c + ofs;
         const float k = fps * P.worldERP;
@@ -185,7 +192,7 @@ PD_HD void build_strut(const PdCarParams& P, const PdStrut& S, const Body& C, co
     { /* ball (b0 = chassis, b1 = strut body): rows 8..10 */
         const V3 a1 = rot(C.fr, v3(S.ballAnchor1[0], S.ballAnchor1[1], S.ballAnchor1[2]));
         const V3 a2 = rot(B.fr, v3(S.ballAnchor2[0], S.ballAnchor2[1], S.ballAnchor2[2]));
-        for (int i = 0; i < 3; ++i) { G.Y(8 + i, i) = 1; G.JB(8 + i, i) = -1; }
+        G.Y(8, 0) = 1; G.Y(9, 1) = 1; G.Y(10, 2) = 1; G.JB(8, 0) = -1; G.JB(9, 1) = -1; G.JB(10, 2) = -1;
         G.Y(8, 4) = a1.z; G.Y(8, 5) = -a1.y; G.Y(9, 3) = -a1.z; G.Y(9, 5) = a1.x; G.Y(10, 3) = a1.y; G.Y(10, 4) = -a1.x;
         G.JB(8, 4) = -a2.z; G.JB(8, 5) = a2.y; G.JB(9, 3) = a2.z; G.JB(9, 5) = -a2.x; G.JB(10, 3) = -a2.y; G.JB(10, 4) = a2.x;
         const float k = fps * P.worldERP;
@@ -194,12 +201,15 @@ PD_HD void build_strut(const PdCarParams& P, const PdStrut& S, const Body& C, co
 }
 
 /* group "axle": dball links (b0 = chassis, b1 = axle) */
-PD_HD void build_axle(const PdCarParams& P, const Body& C, const Body& A, float fps, float dballErp, float dballCfm, GScr& G) {
+template <class GS> PD_HD void build_axle(const PdCarParams& P, const Body& C, const Body& A, float fps, float dballErp, float dballCfm, const GS& G) {
     const int n = P.axle.nLinks;
-    zero_group(G, n, 0, dballCfm);
-    for (int l = 0; l < n; ++l) {
-        const PdDBall& K = P.axle.link[l];
-        grow_dball(G, l, C, A, v3(K.anchor1[0], K.anchor1[1], K.anchor1[2]), v3(K.anchor2[0], K.anchor2[1], K.anchor2[2]), K.distance, fps * dballErp, dballCfm);
+    zero_group(G, n, dballCfm, 1.0f / fps);
+    PD_UNROLL
+    for (int l = 0; l < PD_AXLE_LINKS; ++l) {
+        if (l < n) {
+            const PdDBall& K = P.axle.link[l];
+            grow_dball(G, l, C, A, v3(K.anchor1[0], K.anchor1[1], K.anchor1[2]), v3(K.anchor2[0], K.anchor2[1], K.anchor2[2]), K.distance, fps * dballErp, dballCfm);
+        }
     }
 }
 
@@ -209,70 +219,125 @@ PD_HD void jinvm6(const float* J, const BodyDyn& d, float* o) {
     o[3] = a.x; o[4] = a.y; o[5] = a.z;
 }
 
-/* factor one group: D = JA MA^-1 JA^T (+ JB MB^-1 JB^T) + cfm/h ; L D L^T in place ; Y <- L^-1 [U | r];
+/* factor one group: D = JA MA^-1 JA^T + JB MB^-1 JB^T + cfm/h ; L D L^T in place ; Y <- L^-1 [U | r];
  * accumulates the chassis Schur complement S (6x6 lower, packed 21) and right-hand side b6. */
-PD_HDN void factor_group(const GScr& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6) {
-    const int n = G.n;
-    for (int i = 0; i < n; ++i) {
+template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6) {
+    PD_UNROLL
+    for (int i = 0; i < PD_GMAX; ++i) {
         float ra[6], rb[6], ja[6], jb[6];
-        for (int k = 0; k < 6; ++k) { ra[k] = G.JA(i, k); rb[k] = G.hasB ? G.JB(i, k) : 0.0f; }
+        PD_UNROLL
+        for (int k = 0; k < 6; ++k) { ra[k] = G.JA(i, k); rb[k] = G.JB(i, k); }
         jinvm6(ra, dA, ja);
-        if (G.hasB) jinvm6(rb, dB, jb);
-        for (int j = 0; j <= i; ++j) {
-            float s = ja[0] * G.JA(j, 0) + ja[1] * G.JA(j, 1) + ja[2] * G.JA(j, 2) + ja[3] * G.JA(j, 3) + ja[4] * G.JA(j, 4) + ja[5] * G.JA(j, 5);
-            if (G.hasB) s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
-            G.D(i, j) = s;
+        jinvm6(rb, dB, jb);
+        PD_UNROLL
+        for (int j = 0; j < PD_GMAX; ++j) {
+            if (j <= i) {
+                float s = ja[0] * G.JA(j, 0) + ja[1] * G.JA(j, 1) + ja[2] * G.JA(j, 2) + ja[3] * G.JA(j, 3) + ja[4] * G.JA(j, 4) + ja[5] * G.JA(j, 5);
+                s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
+                G.D(i, j) = s;
+            }
         }
         G.D(i, i) += G.dg(i) * hinv;
         /* r_i = c_i/h - J_i (v/h + M^-1 f) */
         float s = ra[0] * dA.t1[0] + ra[1] * dA.t1[1] + ra[2] * dA.t1[2] + ra[3] * dA.t1[3] + ra[4] * dA.t1[4] + ra[5] * dA.t1[5];
         s += G.Y(i, 0) * dC.t1[0] + G.Y(i, 1) * dC.t1[1] + G.Y(i, 2) * dC.t1[2] + G.Y(i, 3) * dC.t1[3] + G.Y(i, 4) * dC.t1[4] + G.Y(i, 5) * dC.t1[5];
-        if (G.hasB) s += rb[0] * dB.t1[0] + rb[1] * dB.t1[1] + rb[2] * dB.t1[2] + rb[3] * dB.t1[3] + rb[4] * dB.t1[4] + rb[5] * dB.t1[5];
+        s += rb[0] * dB.t1[0] + rb[1] * dB.t1[1] + rb[2] * dB.t1[2] + rb[3] * dB.t1[3] + rb[4] * dB.t1[4] + rb[5] * dB.t1[5];
         G.Y(i, 6) = G.Y(i, 6) * hinv - s;
     }
     /* L D L^T, row by row (same recurrence as the oracle's dense factorisation), in place */
-    for (int i = 0; i < n; ++i) {
-        for (int j = 0; j < i; ++j) {
-            float s = G.D(i, j);
-            for (int k = 0; k < j; ++k) s -= G.D(i, k) * G.D(j, k);    /* D(i,k) = u_k (unscaled), D(j,k) = L_jk */
-            G.D(i, j) = s;
+    PD_UNROLL
+    for (int i = 0; i < PD_GMAX; ++i) {
+        PD_UNROLL
+        for (int j = 0; j < PD_GMAX; ++j) {
+            if (j < i) {
+                float s = G.D(i, j);
+                PD_UNROLL
+                for (int k = 0; k < PD_GMAX; ++k) if (k < j) s -= G.D(i, k) * G.D(j, k);    /* D(i,k) = u_k (unscaled), D(j,k) = L_jk */
+                G.D(i, j) = s;
+            }
         }
         float dii = G.D(i, i);
-        for (int j = 0; j < i; ++j) { const float u = G.D(i, j); const float lij = u / G.dg(j); dii -= u * lij; G.D(i, j) = lij; }
+        PD_UNROLL
+        for (int j = 0; j < PD_GMAX; ++j) if (j < i) { const float u = G.D(i, j); const float lij = u / G.dg(j); dii -= u * lij; G.D(i, j) = lij; }
         G.dg(i) = dii;
     }
     /* forward substitution on the 7 right-hand sides */
-    for (int i = 0; i < n; ++i) {
+    PD_UNROLL
+    for (int i = 0; i < PD_GMAX; ++i) {
         float y[7];
+        PD_UNROLL
         for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
-        for (int j = 0; j < i; ++j) { const float l = G.D(i, j); for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(j, k); }
+        PD_UNROLL
+        for (int j = 0; j < PD_GMAX; ++j) if (j < i) { const float l = G.D(i, j); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(j, k); }
+        PD_UNROLL
         for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
         /* S += Yu^T D^-1 Yu ; b += Yu^T D^-1 yr */
         const float di = 1.0f / G.dg(i);
-        int o = 0;
+        PD_UNROLL
         for (int a = 0; a < 6; ++a) {
             const float ya = y[a] * di;
-            for (int bb = 0; bb <= a; ++bb) S21[o++] += ya * y[bb];
+            PD_UNROLL
+            for (int bb = 0; bb < 6; ++bb) if (bb <= a) S21[a * (a + 1) / 2 + bb] += ya * y[bb];
             b6[a] += ya * y[6];
         }
     }
 }
 
 /* lambda_g = L^-T D^-1 (yr - Yu z);  cforce on own bodies = J^T lambda */
-PD_HDN void backsolve_group(const GScr& G, const float* z, float* cfA, float* cfB) {
-    const int n = G.n;
-    for (int i = 0; i < n; ++i) {
+template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, float* cfA, float* cfB) {
+    PD_UNROLL
+    for (int i = 0; i < PD_GMAX; ++i) {
         float s = G.Y(i, 6);
+        PD_UNROLL
         for (int k = 0; k < 6; ++k) s -= G.Y(i, k) * z[k];
         G.Y(i, 6) = s / G.dg(i);
     }
-    for (int i = n - 1; i >= 0; --i) { float s = G.Y(i, 6); for (int k = i + 1; k < n; ++k) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
+    PD_UNROLL
+    for (int i = PD_GMAX - 1; i >= 0; --i) { float s = G.Y(i, 6); PD_UNROLL for (int k = 0; k < PD_GMAX; ++k) if (k > i) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
+    PD_UNROLL
     for (int k = 0; k < 6; ++k) { cfA[k] = 0; cfB[k] = 0; }
-    for (int i = 0; i < n; ++i) {
+    PD_UNROLL
+    for (int i = 0; i < PD_GMAX; ++i) {
         const float lam = G.Y(i, 6);
-        for (int k = 0; k < 6; ++k) cfA[k] += G.JA(i, k) * lam;
-        if (G.hasB) for (int k = 0; k < 6; ++k) cfB[k] += G.JB(i, k) * lam;
+        PD_UNROLL
+        for (int k = 0; k < 6; ++k) { cfA[k] += G.JA(i, k) * lam; cfB[k] += G.JB(i, k) * lam; }
     }
+}
+
+/* Serial variant of the back-substitution: fold the group into an affine map of the chassis unknown z,
+ *     cforce_A = pA - QA z ,  cforce_B = pB - QB z      (W = L^-T D^-1 [Yu | yr];  p = J^T W[:,6],  Q = J^T W[:,0:6])
+ * so that the group's scratch can be reused by the next group before z is known. */
+template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, float* pB, float* QB) {
+    PD_UNROLL
+    for (int i = 0; i < PD_GMAX; ++i) { const float di = 1.0f / G.dg(i); PD_UNROLL for (int k = 0; k < 7; ++k) G.Y(i, k) *= di; }
+    PD_UNROLL
+    for (int i = PD_GMAX - 1; i >= 0; --i) {
+        float y[7];
+        PD_UNROLL
+        for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
+        PD_UNROLL
+        for (int r = 0; r < PD_GMAX; ++r) if (r > i) { const float l = G.D(r, i); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(r, k); }
+        PD_UNROLL
+        for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
+    }
+    PD_UNROLL
+    for (int a = 0; a < 6; ++a) {
+        float sa = 0, sb = 0;
+        PD_UNROLL
+        for (int i = 0; i < PD_GMAX; ++i) { sa += G.JA(i, a) * G.Y(i, 6); sb += G.JB(i, a) * G.Y(i, 6); }
+        pA[a] = sa; pB[a] = sb;
+        PD_UNROLL
+        for (int k = 0; k < 6; ++k) {
+            float qa = 0, qb = 0;
+            PD_UNROLL
+            for (int i = 0; i < PD_GMAX; ++i) { qa += G.JA(i, a) * G.Y(i, k); qb += G.JB(i, a) * G.Y(i, k); }
+            QA[a * 6 + k] = qa; QB[a * 6 + k] = qb;
+        }
+    }
+}
+PD_HD void unfold(const float* p, const float* Q, const float* z, float* cf) {
+    PD_UNROLL
+    for (int a = 0; a < 6; ++a) { float s = p[a]; PD_UNROLL for (int k = 0; k < 6; ++k) s -= Q[a * 6 + k] * z[k]; cf[a] = s; }
 }
 
 /* util.cpp dxStepBody (finite rotation mode 1, no axis) */
@@ -359,8 +424,8 @@ PD_HD void chassis_update(Body& Cb, const BodyDyn& d, const float* z, float h) {
     Cb.w.x += dw.x + h * z[3]; Cb.w.y += dw.y + h * z[4]; Cb.w.z += dw.z + h * z[5];
 }
 
-/* dWorldStep for the car's island, one thread doing all four groups (host debugging build and reference
- * for the quad version in pd_quad.h) */
+/* dWorldStep for the car's island, one thread doing the four groups one after the other with ONE scratch
+ * (thread-per-car kernel for large batches, and the host debugging build) */
 PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h) {
     const float hinv = 1.0f / h;
     BodyDyn dyn[PD_NUM_BODIES];
@@ -368,28 +433,26 @@ PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, co
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
-    float scr[4][PD_GSCR_WORDS]; GScr G[4];
-    for (int g = 0; g < 4; ++g) { G[g].p = scr[g]; G[g].s = 1; }
+    float scr[PD_GSCR_WORDS]; GScr<1> G; G.p = scr;
+    /* folded groups: [tank | hub0, strut0 | hub1, strut1 | axle] */
+    float pv[6][6], Qv[6][36], pdump[6], Qdump[36];
     const Body& C = b[PD_BODY_CHASSIS];
-    build_tank(P, b[PD_BODY_TANK], C, hinv, G[0]);
-    factor_group(G[0], dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
+    build_tank(P, b[PD_BODY_TANK], C, hinv, G);
+    factor_group(G, dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
+    fold_group(G, pv[0], Qv[0], pdump, Qdump);
     for (int s = 0; s < 2; ++s) {
-        build_strut(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], hinv, dballErp, dballCfm, G[1 + s]);
-        factor_group(G[1 + s], dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
+        build_strut(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], hinv, dballErp, dballCfm, G);
+        factor_group(G, dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
+        fold_group(G, pv[1 + 2 * s], Qv[1 + 2 * s], pv[2 + 2 * s], Qv[2 + 2 * s]);
     }
-    build_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, G[3]);
-    factor_group(G[3], dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
+    build_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, G);
+    factor_group(G, dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
+    fold_group(G, pv[5], Qv[5], pdump, Qdump);
     schur_add_chassis(S21, C);
     float z[6];
     solve6(S21, b6, z);
-    float cfA[6], cfB[6];
-    backsolve_group(G[0], z, cfA, cfB); apply_update(b[PD_BODY_TANK], dyn[PD_BODY_TANK], cfA, h);
-    for (int s = 0; s < 2; ++s) {
-        backsolve_group(G[1 + s], z, cfA, cfB);
-        apply_update(b[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_HUB0 + 2 * s], cfA, h);
-        apply_update(b[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], cfB, h);
-    }
-    backsolve_group(G[3], z, cfA, cfB); apply_update(b[PD_BODY_AXLE], dyn[PD_BODY_AXLE], cfA, h);
+    const int own[6] = {PD_BODY_TANK, PD_BODY_HUB0, PD_BODY_STRUT0, PD_BODY_HUB1, PD_BODY_STRUT1, PD_BODY_AXLE};
+    for (int g = 0; g < 6; ++g) { float cf[6]; unfold(pv[g], Qv[g], z, cf); apply_update(b[own[g]], dyn[own[g]], cf, h); }
     chassis_update(b[PD_BODY_CHASSIS], dyn[PD_BODY_CHASSIS], z, h);
     for (int i = 0; i < PD_NUM_BODIES; ++i) { integrate_body(b[i], h); b[i].F = v3(0, 0, 0); b[i].T = v3(0, 0, 0); }
 }

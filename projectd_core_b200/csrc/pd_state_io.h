@@ -42,19 +42,34 @@ PD_HD void d2u(double d, uint32_t& lo, uint32_t& hi) {
 #endif
 }
 
-/* view of one env inside the SoA state buffer */
+/* View of one env inside the state buffer.
+ * Device layout ("tiled SoA"): envs are grouped in tiles of 32; word w of env e lives at
+ *     state[((e / 32) * PD_STATE_WORDS + w) * 32 + (e % 32)].
+ * A warp's accesses to one word of 32 consecutive envs are one 128-byte line, and -- because the word index
+ * is a compile-time constant almost everywhere -- every access is a load/store with an IMMEDIATE offset from
+ * one per-thread base pointer (no index arithmetic).  Host-side single records (snapshots, the oracle
+ * harness, tests/hostsim) are flat arrays: stride 1. */
+#define PD_TILE 32
 struct SV {
-    uint32_t* s;
-    size_t n;   /* number of envs (row stride) */
-    size_t e;   /* this env */
-    bool live = true;   /* false: a padding lane that computes along but must not write */
-    PD_HD float f(int w) const { return u2f(s[(size_t)w * n + e]); }
-    PD_HD int i(int w) const { return (int)s[(size_t)w * n + e]; }
-    PD_HD double d(int w) const { return u2d(s[(size_t)w * n + e], s[(size_t)(w + 1) * n + e]); }
-    PD_HD void f(int w, float v) const { if (live) s[(size_t)w * n + e] = f2u(v); }
-    PD_HD void i(int w, int v) const { if (live) s[(size_t)w * n + e] = (uint32_t)v; }
-    PD_HD void d(int w, double v) const { if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[(size_t)w * n + e] = lo; s[(size_t)(w + 1) * n + e] = hi; }
+    uint32_t* s;        /* &state[word 0 of this env] */
+    bool live;          /* false: a padding lane that computes along but must not write */
+#if defined(__CUDA_ARCH__)
+    static constexpr int stride = PD_TILE;
+    PD_HD SV(uint32_t* base, int /*stride*/, bool lv = true) : s(base), live(lv) {}
+#else
+    int stride;
+    PD_HD SV(uint32_t* base, int st, bool lv = true) : s(base), live(lv), stride(st) {}
+#endif
+    PD_HD float f(int w) const { return u2f(s[w * stride]); }
+    PD_HD int i(int w) const { return (int)s[w * stride]; }
+    PD_HD double d(int w) const { return u2d(s[w * stride], s[(w + 1) * stride]); }
+    PD_HD void f(int w, float v) const { if (live) s[w * stride] = f2u(v); }
+    PD_HD void i(int w, int v) const { if (live) s[w * stride] = (uint32_t)v; }
+    PD_HD void d(int w, double v) const { if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[w * stride] = lo; s[(w + 1) * stride] = hi; }
 };
+PD_HD size_t state_index(int w, size_t e) { return ((e / PD_TILE) * PD_STATE_WORDS + (size_t)w) * PD_TILE + (e % PD_TILE); }
+PD_HD SV sv_tiled(uint32_t* state, size_t e) { return SV(state + state_index(0, e), PD_TILE); }
+PD_HD SV sv_flat(uint32_t* rec) { return SV(rec, 1); }
 
 /* ---- typed mirrors of the X-macro lists ---- */
 #define PD__DECL_F(name) float name;

@@ -93,7 +93,7 @@ PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const
     /* forcePosition(center) */
     V3 bodyPos = v3(pt.center[0], pt.center[1], pt.center[2]);
     {
-        const RayHit hit = ray_cast(T, bodyPos + v3(0, 10, 0), v3(0, -1, 0), 1000.0f);
+        const RayHit hit = ray_cast_down(T, bodyPos + v3(0, 10, 0), 1000.0f);
         if (hit.hit) bodyPos.y = hit.pos.y;
         bodyPos.y += (P.baseCarHeight + 0.0f + 0.01f);
     }

@@ -37,6 +37,8 @@ struct TrackDev {
     const int32_t* segStart; const int32_t* segItems;   /* PdBoundGrid CSR: boundary segments per cell */
     const int32_t* ptStart; const int32_t* ptItems;     /* PdBoundGrid CSR: spline points per cell */
     PdBoundGrid grid;
+    const int32_t* colStart; const int32_t* colItems;   /* vertical-ray index: triangles per x-z cell */
+    PdBoundGrid colGrid;
     PdTrackInfo info;
 };
 
@@ -91,6 +93,44 @@ PD_HDN RayHit ray_cast(const TrackDev& T, V3 o, V3 d, float length) {
     }
     if (best >= 0.0f) {
         h.hit = 1; h.pos = v3(o.x + d.x * best, o.y + d.y * best, o.z + d.z * best);
+        h.normal = norm(bestN); h.surface = bestS;
+    }
+    return h;
+}
+
+/* The same query for a ray pointing straight down, d = (0,-1,0) -- every ray of the hot path (wheel rays,
+ * teleport ray).  One cell lookup in the column grid replaces the tree walk.  The triangle test is the test
+ * above with the terms that multiply d's zero components dropped: x*0 contributes an exact (signed) zero to
+ * each sum, so det, u, v and t round exactly as in ray_cast and the two functions return identical bits. */
+PD_HDN RayHit ray_cast_down(const TrackDev& T, V3 o, float length) {
+    RayHit h; h.hit = 0; h.surface = -1; h.pos = v3(0, 0, 0); h.normal = v3(0, 0, 0);
+    const PdBoundGrid& G = T.colGrid;
+    const int ix = (int)floorf((o.x - G.ox) * G.invCell), iz = (int)floorf((o.z - G.oz) * G.invCell);
+    if (ix < 0 || iz < 0 || ix >= G.nx || iz >= G.nz) return h;
+    const int c = iz * G.nx + ix;
+    float best = -1.0f; V3 bestN = v3(0, 0, 0); int bestS = -1;
+    const int k0 = T.colStart[c], k1 = T.colStart[c + 1];
+    for (int k = k0; k < k1; ++k) {
+        const int t = T.colItems[k];
+        const float* p = T.tris + (size_t)t * 9;
+        const V3 v0 = v3(p[0], p[1], p[2]), e1 = v3(p[3], p[4], p[5]), e2 = v3(p[6], p[7], p[8]);
+        /* pvec = d x e2 = (-e2.z, 0, e2.x) */
+        const float det = e1.x * (-e2.z) + e1.z * e2.x;
+        if (det < 0.000001f) continue;
+        const V3 tvec = o - v0;
+        const float u = tvec.x * (-e2.z) + tvec.z * e2.x;
+        if (u < 0.0f || u > det) continue;
+        const V3 qvec = cross(tvec, e1);
+        const float v = -qvec.y;
+        if (v < 0.0f || u + v > det) continue;
+        float dist = dot(e2, qvec);
+        if (dist < 0.0f) continue;
+        dist *= (1.0f / det);
+        if (!(dist < length)) continue;
+        if (best < 0.0f || dist < best) { best = dist; bestN = cross(e1, e2); bestS = T.triSurf[t]; }
+    }
+    if (best >= 0.0f) {
+        h.hit = 1; h.pos = v3(o.x + 0.0f * best, o.y + -1.0f * best, o.z + 0.0f * best);
         h.normal = norm(bestN); h.surface = bestS;
     }
     return h;

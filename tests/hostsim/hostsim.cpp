@@ -20,6 +20,7 @@ struct HS {
         dev.nodes = (const pd::BvhNode*)track.nodes.data(); dev.tris = track.tris.data(); dev.triSurf = track.triSurf.data();
         dev.surfaces = track.surfaces.data(); dev.fat = track.fat.data(); dev.splineXYZ = track.splineXYZ.data(); dev.splineDist = track.splineDist.data();
         dev.segStart = track.segStart.data(); dev.segItems = track.segItems.data(); dev.ptStart = track.ptStart.data(); dev.ptItems = track.ptItems.data(); dev.grid = track.grid;
+        dev.colStart = track.colStart.data(); dev.colItems = track.colItems.data(); dev.colGrid = track.colGrid;
         dev.info = track.info;
     }
 };
@@ -55,21 +56,22 @@ void hs_get_params(void* h, PdCarParams* out) { *out = ((HS*)h)->car.P; }
 void hs_set_params(void* h, const PdCarParams* in) { ((HS*)h)->car.P = *in; }
 void hs_get_track_info(void* h, PdTrackInfo* out) { *out = ((HS*)h)->track.info; }
 void hs_get_spline_nodes(void* hv, float* xyz, float* dist) { HS* h = (HS*)hv; memcpy(xyz, h->track.splineXYZ.data(), h->track.splineXYZ.size() * 4); memcpy(dist, h->track.splineDist.data(), h->track.splineDist.size() * 4); }
-void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SV sv{rec, 1, 0}; pd::car_tick(h->car.P, h->dev, sv, dt, time); }
+void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SV sv = pd::sv_flat(rec); pd::car_tick(h->car.P, h->dev, sv, dt, time); }
 void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
     HS* h = (HS*)hv; QuadShared sh; pthread_barrier_init(&sh.bar, nullptr, 4);
     std::thread th[4];
-    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SV sv{rec, 1, 0}; float scr[PD_GSCR_WORDS]; pd::car_tick_quad(h->car.P, h->dev, sv, dt, time, ex, scr, 1); });
+    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SV sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1>(h->car.P, h->dev, sv, dt, time, ex, scr); });
     for (int l = 0; l < 4; ++l) th[l].join();
     pthread_barrier_destroy(&sh.bar);
 }
-void hs_teleport_point(void* hv, uint32_t* rec, int pointId, double time) { HS* h = (HS*)hv; pd::SV sv{rec, 1, 0}; pd::car_teleport_to_point(h->car.P, h->dev, sv, pointId, time); }
+void hs_teleport_point(void* hv, uint32_t* rec, int pointId, double time) { HS* h = (HS*)hv; pd::SV sv = pd::sv_flat(rec); pd::car_teleport_to_point(h->car.P, h->dev, sv, pointId, time); }
 int hs_point_id_at_distance(void* hv, float d) { return pd::point_id_at_distance(((HS*)hv)->dev, d); }
 void hs_raycast(void* hv, int n, const float* in, float* out) {
     HS* h = (HS*)hv;
     for (int i = 0; i < n; ++i) {
         const float* p = in + i * 7; float* q = out + i * 8;
-        pd::RayHit r = pd::ray_cast(h->dev, pd::v3(p[0], p[1], p[2]), pd::v3(p[3], p[4], p[5]), p[6]);
+        const bool down = (p[3] == 0.0f && p[4] == -1.0f && p[5] == 0.0f);
+        pd::RayHit r = down ? pd::ray_cast_down(h->dev, pd::v3(p[0], p[1], p[2]), p[6]) : pd::ray_cast(h->dev, pd::v3(p[0], p[1], p[2]), pd::v3(p[3], p[4], p[5]), p[6]);
         q[0] = (float)r.hit; q[1] = r.pos.x; q[2] = r.pos.y; q[3] = r.pos.z; q[4] = r.normal.x; q[5] = r.normal.y; q[6] = r.normal.z; q[7] = (float)r.surface;
     }
 }
