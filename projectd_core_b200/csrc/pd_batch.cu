@@ -213,6 +213,10 @@ struct PdCarStateOut {    /* Car/CarState.h:11-56 */
 #pragma pack(pop)
 static_assert(sizeof(PdCarStateOut) == 664, "CarState is 664 bytes");
 
+/* batches up to PD_QUAD_MAX_ENVS: four lanes per car (latency-bound regime, more warps per car);
+ * larger batches: one thread per car (throughput regime, no redundant scalar work) */
+#define PD_QUAD_MAX_ENVS 16384
+
 struct pd_batch {
     int n = 0, device = 0;
     cudaStream_t stream = nullptr;
@@ -227,6 +231,7 @@ struct pd_batch {
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     double time = 0, lastDt = 0;
     uint64_t seed = 0, idOffset = 0, launches = 0;
+    int quadMax = PD_QUAD_MAX_ENVS;   /* kernel dispatch threshold; env PD_QUAD_MAX_ENVS overrides (tuning / profiling) */
     std::string err;
     int64_t dlShape[2] = {0, 0};
 };
@@ -249,9 +254,6 @@ template <class T> static int upload(pd_batch* b, const T** p, const std::vector
 static inline int grid(int n, int block) { return (n + block - 1) / block; }
 /* small batches: one warp per block so that every SM gets work (148 SMs) */
 static inline int tick_block(int) { return PD_QBLOCK; }
-/* batches up to PD_QUAD_MAX_ENVS: four lanes per car (latency-bound regime, more warps per car);
- * larger batches: one thread per car (throughput regime, no redundant scalar work) */
-#define PD_QUAD_MAX_ENVS 16384
 
 static int sync_params(pd_batch* b) {
     if (!b->paramsDirty) return PD_OK;
@@ -267,6 +269,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (device < 0 || device >= count) { b->err = "bad device ordinal"; return PD_ERR_ARG; }
     CK(cudaSetDevice(device));
     b->n = n_envs; b->device = device;
+    if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(k_tick_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * PD_GSCR_WORDS * 4));
     int rc;
@@ -323,7 +326,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
 }
 
 static void launch_tick(pd_batch* b, float dt, const int32_t* mask) {
-    if (b->n <= PD_QUAD_MAX_ENVS)
+    if (b->n <= b->quadMax)
         k_tick_quad<<<grid(b->n * 4, PD_QBLOCK), PD_QBLOCK, (size_t)PD_QBLOCK * PD_GSCR_WORDS * 4, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask);
     else
         k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask);

@@ -258,30 +258,30 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, flo
     const float fPctDt = P.patchCoreTransfer * dt;
     const float kSurf = P.surfaceTransfer * dt;
     const float kPatch = P.patchTransfer * dt;
+    /* element loop kept rolled (code size); neighbours are visited in the reference's construction order:
+     * j == 0: up, down, right, wrap(last) ; j > 0: up, left, down, right-or-wrap(first) */
     PD_UNROLL
     for (int i = 0; i < PD_THERMAL_STRIPES; ++i) {
-        PD_UNROLL
+        const float inj = inBase + (i == 0 ? in0 : (i == 1 ? in1 : in2));
+        float* Ti = t.T + i * PD_THERMAL_ELEMENTS;
+        PD_NOUNROLL
         for (int j = 0; j < PD_THERMAL_ELEMENTS; ++j) {
-            const int p = j + i * PD_THERMAL_ELEMENTS;
-            /* TyreThermalPatch::inputT: inBase everywhere, plus this tick's injection at element inElem of each stripe */
-            const float fInputT = (j == inElem) ? (inBase + (i == 0 ? in0 : (i == 1 ? in1 : in2))) : inBase;
-            float fPatchT = t.T[p];
+            const float fInputT = (j == inElem) ? inj : inBase;
+            float fPatchT = Ti[j];
             if (fInputT <= ambient) fPatchT += ((ambient - fPatchT) * fAmbientFactor);
             else fPatchT += ((fInputT - fPatchT) * kSurf);
-            /* connections, in construction order */
-            if (i > 0) fPatchT += (t.T[p - PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
+            if (i > 0) fPatchT += (Ti[j - PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
             if (j == 0) {
-                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (t.T[p + PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
-                fPatchT += (t.T[p + 1] - fPatchT) * kPatch;
-                fPatchT += (t.T[p + PD_THERMAL_ELEMENTS - 1] - fPatchT) * kPatch;
+                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (Ti[PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
+                fPatchT += (Ti[1] - fPatchT) * kPatch;
+                fPatchT += (Ti[PD_THERMAL_ELEMENTS - 1] - fPatchT) * kPatch;
             } else {
-                fPatchT += (t.T[p - 1] - fPatchT) * kPatch;
-                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (t.T[p + PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
-                if (j + 1 < PD_THERMAL_ELEMENTS) fPatchT += (t.T[p + 1] - fPatchT) * kPatch;
-                else fPatchT += (t.T[i * PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
+                fPatchT += (Ti[j - 1] - fPatchT) * kPatch;
+                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (Ti[j + PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
+                fPatchT += (Ti[(j + 1 < PD_THERMAL_ELEMENTS) ? j + 1 : 0] - fPatchT) * kPatch;
             }
             fPatchT += (coreTemp - fPatchT) * fPctDt;
-            t.T[p] = fPatchT;
+            Ti[j] = fPatchT;
             coreTemp += ((fPatchT - coreTemp) * fPctDt);
         }
     }
@@ -292,8 +292,7 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, flo
         const float ph = (float)(t.phase * 0.1591549430964443);
         const int iElemY = ((int)(ph * PD_THERMAL_ELEMENTS)) % PD_THERMAL_ELEMENTS;
         float t0 = 0, t1 = 0, t2 = 0;
-        PD_UNROLL
-        for (int j = 0; j < PD_THERMAL_ELEMENTS; ++j) if (j == iElemY) { t0 = t.T[j]; t1 = t.T[j + PD_THERMAL_ELEMENTS]; t2 = t.T[j + 2 * PD_THERMAL_ELEMENTS]; }
+        if (iElemY >= 0 && iElemY < PD_THERMAL_ELEMENTS) { t0 = t.T[iElemY]; t1 = t.T[iElemY + PD_THERMAL_ELEMENTS]; t2 = t.T[iElemY + 2 * PD_THERMAL_ELEMENTS]; }
         const float cp = ((((fNormCsk + 1.0f) * t0) + t1) + ((1.0f - fNormCsk) * t2)) * 0.33333334f;
         const float fPracT = ((cp - coreTemp) * 0.25f) + coreTemp;
         t.practicalTemp = fPracT;

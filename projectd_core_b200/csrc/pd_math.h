@@ -16,8 +16,12 @@
 #define PD_HD __host__ __device__ __forceinline__
 #define PD_HDN __host__ __device__ __noinline__
 #define PD_UNROLL _Pragma("unroll")
+#define PD_NOUNROLL _Pragma("unroll 1")
+#define PD_UNROLL4 _Pragma("unroll 4")
 #else
 #define PD_UNROLL
+#define PD_UNROLL4
+#define PD_NOUNROLL
 #define PD_HD inline
 #define PD_HDN inline
 #endif

@@ -129,7 +129,7 @@ template <int S> struct GScr {
 };
 /* all rows zero; pad rows get cfm = h so that their diagonal becomes cfm/h = 1 */
 template <class GS> PD_HD void zero_group(const GS& G, int n, float cfm, float h) {
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = 0; i < PD_GMAX; ++i) {
         PD_UNROLL
         for (int k = 0; k < 6; ++k) { G.JA(i, k) = 0; G.JB(i, k) = 0; G.Y(i, k) = 0; }
@@ -220,22 +220,22 @@ PD_HD void jinvm6(const float* J, const BodyDyn& d, float* o) {
 }
 
 /* factor one group: D = JA MA^-1 JA^T + JB MB^-1 JB^T + cfm/h ; L D L^T in place ; Y <- L^-1 [U | r];
- * accumulates the chassis Schur complement S (6x6 lower, packed 21) and right-hand side b6. */
+ * accumulates the chassis Schur complement S (6x6 lower, packed 21) and right-hand side b6.
+ * Row loops are kept ROLLED (compact code: the kernel is instruction-fetch sensitive), the 6- and 7-wide inner
+ * loops are unrolled; every lane runs all PD_GMAX rows (padding rows are identity), so there is no divergence. */
 template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6) {
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = 0; i < PD_GMAX; ++i) {
         float ra[6], rb[6], ja[6], jb[6];
         PD_UNROLL
         for (int k = 0; k < 6; ++k) { ra[k] = G.JA(i, k); rb[k] = G.JB(i, k); }
         jinvm6(ra, dA, ja);
         jinvm6(rb, dB, jb);
-        PD_UNROLL
-        for (int j = 0; j < PD_GMAX; ++j) {
-            if (j <= i) {
-                float s = ja[0] * G.JA(j, 0) + ja[1] * G.JA(j, 1) + ja[2] * G.JA(j, 2) + ja[3] * G.JA(j, 3) + ja[4] * G.JA(j, 4) + ja[5] * G.JA(j, 5);
-                s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
-                G.D(i, j) = s;
-            }
+        PD_NOUNROLL
+        for (int j = 0; j <= i; ++j) {
+            float s = ja[0] * G.JA(j, 0) + ja[1] * G.JA(j, 1) + ja[2] * G.JA(j, 2) + ja[3] * G.JA(j, 3) + ja[4] * G.JA(j, 4) + ja[5] * G.JA(j, 5);
+            s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
+            G.D(i, j) = s;
         }
         G.D(i, i) += G.dg(i) * hinv;
         /* r_i = c_i/h - J_i (v/h + M^-1 f) */
@@ -245,30 +245,28 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
         G.Y(i, 6) = G.Y(i, 6) * hinv - s;
     }
     /* L D L^T, row by row (same recurrence as the oracle's dense factorisation), in place */
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = 0; i < PD_GMAX; ++i) {
-        PD_UNROLL
-        for (int j = 0; j < PD_GMAX; ++j) {
-            if (j < i) {
-                float s = G.D(i, j);
-                PD_UNROLL
-                for (int k = 0; k < PD_GMAX; ++k) if (k < j) s -= G.D(i, k) * G.D(j, k);    /* D(i,k) = u_k (unscaled), D(j,k) = L_jk */
-                G.D(i, j) = s;
-            }
+        PD_NOUNROLL
+        for (int j = 0; j < i; ++j) {
+            float s = G.D(i, j);
+            PD_NOUNROLL
+            for (int k = 0; k < j; ++k) s -= G.D(i, k) * G.D(j, k);    /* D(i,k) = u_k (unscaled), D(j,k) = L_jk */
+            G.D(i, j) = s;
         }
         float dii = G.D(i, i);
-        PD_UNROLL
-        for (int j = 0; j < PD_GMAX; ++j) if (j < i) { const float u = G.D(i, j); const float lij = u / G.dg(j); dii -= u * lij; G.D(i, j) = lij; }
+        PD_NOUNROLL
+        for (int j = 0; j < i; ++j) { const float u = G.D(i, j); const float lij = u / G.dg(j); dii -= u * lij; G.D(i, j) = lij; }
         G.dg(i) = dii;
     }
     /* forward substitution on the 7 right-hand sides */
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = 0; i < PD_GMAX; ++i) {
         float y[7];
         PD_UNROLL
         for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
-        PD_UNROLL
-        for (int j = 0; j < PD_GMAX; ++j) if (j < i) { const float l = G.D(i, j); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(j, k); }
+        PD_NOUNROLL
+        for (int j = 0; j < i; ++j) { const float l = G.D(i, j); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(j, k); }
         PD_UNROLL
         for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
         /* S += Yu^T D^-1 Yu ; b += Yu^T D^-1 yr */
@@ -285,18 +283,18 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
 
 /* lambda_g = L^-T D^-1 (yr - Yu z);  cforce on own bodies = J^T lambda */
 template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, float* cfA, float* cfB) {
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = 0; i < PD_GMAX; ++i) {
         float s = G.Y(i, 6);
         PD_UNROLL
         for (int k = 0; k < 6; ++k) s -= G.Y(i, k) * z[k];
         G.Y(i, 6) = s / G.dg(i);
     }
-    PD_UNROLL
-    for (int i = PD_GMAX - 1; i >= 0; --i) { float s = G.Y(i, 6); PD_UNROLL for (int k = 0; k < PD_GMAX; ++k) if (k > i) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
+    PD_NOUNROLL
+    for (int i = PD_GMAX - 1; i >= 0; --i) { float s = G.Y(i, 6); PD_NOUNROLL for (int k = i + 1; k < PD_GMAX; ++k) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
     PD_UNROLL
     for (int k = 0; k < 6; ++k) { cfA[k] = 0; cfB[k] = 0; }
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = 0; i < PD_GMAX; ++i) {
         const float lam = G.Y(i, 6);
         PD_UNROLL
@@ -308,28 +306,28 @@ template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, flo
  *     cforce_A = pA - QA z ,  cforce_B = pB - QB z      (W = L^-T D^-1 [Yu | yr];  p = J^T W[:,6],  Q = J^T W[:,0:6])
  * so that the group's scratch can be reused by the next group before z is known. */
 template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, float* pB, float* QB) {
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = 0; i < PD_GMAX; ++i) { const float di = 1.0f / G.dg(i); PD_UNROLL for (int k = 0; k < 7; ++k) G.Y(i, k) *= di; }
-    PD_UNROLL
+    PD_NOUNROLL
     for (int i = PD_GMAX - 1; i >= 0; --i) {
         float y[7];
         PD_UNROLL
         for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
-        PD_UNROLL
-        for (int r = 0; r < PD_GMAX; ++r) if (r > i) { const float l = G.D(r, i); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(r, k); }
+        PD_NOUNROLL
+        for (int r = i + 1; r < PD_GMAX; ++r) { const float l = G.D(r, i); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(r, k); }
         PD_UNROLL
         for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
     }
     PD_UNROLL
     for (int a = 0; a < 6; ++a) {
         float sa = 0, sb = 0;
-        PD_UNROLL
+        PD_NOUNROLL
         for (int i = 0; i < PD_GMAX; ++i) { sa += G.JA(i, a) * G.Y(i, 6); sb += G.JB(i, a) * G.Y(i, 6); }
         pA[a] = sa; pB[a] = sb;
         PD_UNROLL
         for (int k = 0; k < 6; ++k) {
             float qa = 0, qb = 0;
-            PD_UNROLL
+            PD_NOUNROLL
             for (int i = 0; i < PD_GMAX; ++i) { qa += G.JA(i, a) * G.Y(i, k); qb += G.JB(i, a) * G.Y(i, k); }
             QA[a * 6 + k] = qa; QB[a * 6 + k] = qb;
         }

@@ -101,13 +101,13 @@ struct CarS {
 PD_HD void load_tyre(const SV& sv, int w, TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__LDT)
-    PD_UNROLL
+    PD_UNROLL4
     for (int p = 0; p < PD_THERMAL_PATCHES; ++p) t.T[p] = sv.f(PD_OFF_TYRE_PATCH(w) + p);
 }
 PD_HD void store_tyre(const SV& sv, int w, const TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__STT)
-    PD_UNROLL
+    PD_UNROLL4
     for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, t.T[p]);
 }
 PD_HD void load_car(const SV& sv, CarS& t) {
