@@ -16,4 +16,6 @@ GPU raises.
 """
 from .binding import Batch, PdError, lib_path, load_library, STATE_WORDS, OBS_DIM  # noqa: F401
 
-__all__ = ["Batch", "PdError", "lib_path", "load_library", "STATE_WORDS", "OBS_DIM"]
+from . import dist  # noqa: F401,E402
+
+__all__ = ["Batch", "PdError", "lib_path", "load_library", "STATE_WORDS", "OBS_DIM", "dist"]

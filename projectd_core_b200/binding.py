@@ -127,6 +127,13 @@ class Batch:
         self.n = n_envs
         self.device = device
         self._obs_tensor = None
+        self._ctl = np.zeros((n_envs, 5), np.float32)
+        self._gears = np.zeros((n_envs, 3), np.int8); self._gears[:, 0] = -1
+
+    def controls_host(self):
+        """Host mirror of the last controls handed over from host memory ([N,5] f32, [N,3] i8); the scalar
+        setCarControls of the PyProjectD mirror edits one row of it."""
+        return self._ctl, self._gears
 
     # -- lifetime -------------------------------------------------------------------------------------
     def close(self):
@@ -170,6 +177,10 @@ class Batch:
             assert controls.shape == (self.n, 5)
             if gears is not None:
                 gears = np.ascontiguousarray(gears, dtype=np.int8)
+                if gears is not self._gears:
+                    self._gears[...] = gears
+            if controls is not self._ctl:
+                self._ctl[...] = controls
         self._ck(self.L.pd_set_controls(self.h, _ptr(controls), _ptr(gears), int(smooth), int(on_dev)))
 
     def set_actions(self, actions):

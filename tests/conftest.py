@@ -61,6 +61,9 @@ def hostsim():
     H.hs_get_track_info.argtypes = [vp, vp]
     H.hs_get_spline_nodes.argtypes = [vp, vp, vp]
     H.hs_tick.argtypes = [vp, vp, f, d]
+    H.hs_tick_quad.argtypes = [vp, vp, f, d]
+    H.hs_probe_compare.argtypes = [vp, i, vp, vp, vp]
+    H.hs_params_bytes.restype = i
     H.hs_teleport_point.argtypes = [vp, vp, i, d]
     H.hs_point_id_at_distance.argtypes = [vp, f]
     H.hs_raycast.argtypes = [vp, i, vp, vp]
@@ -69,12 +72,32 @@ def hostsim():
 
 
 @pytest.fixture(scope="session")
-def hostsim_env(hostsim, oracle):
-    h = hostsim.hs_create(oracle.BASE_PATH.encode(), b"driftplayground", b"ks_toyota_ae86_drift")
+def golden():
+    """Committed golden vectors (tests/golden/demo_golden.npz, written by tests/golden/make_golden.py)."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "demo_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def content_base():
+    """Directory holding cfg/ + content/ of the reference (a copy under oracle/_ref/base, made by `make -C oracle content`)."""
+    import pdref
+    if not os.path.isdir(pdref.BASE_PATH):
+        if os.path.isdir("/root/reference/src/ProjectD"):
+            subprocess.check_call(["make", "content"], cwd=os.path.join(ROOT, "oracle"))
+        else:
+            pytest.skip("no content copy (oracle/_ref/base) and /root/reference absent")
+    return pdref.BASE_PATH
+
+
+@pytest.fixture(scope="session")
+def hostsim_env(hostsim, content_base):
+    import pdref
+    h = hostsim.hs_create(content_base.encode(), b"driftplayground", b"ks_toyota_ae86_drift")
     assert h
     hostsim.hs_set_assists(h, 1, 1, 1)
-    for k, v in oracle.ENV_TUNES.items():
+    for k, v in pdref.ENV_TUNES.items():
         hostsim.hs_set_tune(h, k.encode(), v)
-    for k, v in oracle.ENV_SCORING.items():
+    for k, v in pdref.ENV_SCORING.items():
         hostsim.hs_set_scoring_var(h, k.encode(), v)
     return h

@@ -185,3 +185,61 @@ def test_obs_dlpack_and_env_step(oracle):
     assert np.abs(host[:, 0:3]).max(axis=1).mean() > 0.5, "cars should be moving under full throttle"
     st = b.env_stats()
     assert st[0] >= 0
+
+
+def test_pyprojectd_mirror_matches_reference_car_state(oracle):
+    """The reference's own call sequence (projectd_env.py:118-136,156-171) through the PyProjectD mirror; CarState
+    (664-byte layout of Car/CarState.h) against the reference's getCarState after 120 ticks."""
+    from projectd_core_b200 import pyprojectd as pd
+    sim = pd.createSimulator(oracle.BASE_PATH)
+    assert sim >= 0
+    pd.loadTrack(sim, "driftplayground")
+    car = pd.addCar(sim, "ks_toyota_ae86_drift")
+    assert car == 0
+    pd.teleportCarByMode(sim, car, 0)
+    pd.setCarAutoTeleport(sim, car, False, False, 0)
+    pd.setCarAssists(sim, car, True, True, True)
+    for k, v in oracle.ENV_TUNES.items():
+        pd.setCarTune(sim, car, k, v)
+    for k, v in oracle.ENV_SCORING.items():
+        pd.setScoringVar(sim, car, k, v)
+    r = oracle.RefSim(); r.L.pdref_teleport_mode(r.h, 0)
+    ctl = pd.CarControls(); st = pd.CarState()
+    for t in range(120):
+        ctl.steer = 0.2 * math.sin(t / 40.0); ctl.gas = 0.6
+        pd.setCarControls(sim, car, True, ctl)
+        pd.stepSimulator(sim, DT)
+        r.set_controls(steer=ctl.steer, gas=ctl.gas); r.step()
+    pd.getCarState(sim, car, st)
+    ref = np.zeros(664, np.uint8); r.L.pdref_get_car_state(r.h, ref.ctypes.data)
+    ref = np.frombuffer(ref, dtype=pd.CAR_STATE_DTYPE)[0]
+    assert st.gear == int(ref["gear"]) and st.trackPointId == int(ref["trackPointId"])
+    assert st.collisionFlag == int(ref["collisionFlag"]) and st.outOfTrackFlag == int(ref["outOfTrackFlag"])
+    assert abs(st.speedMS - float(ref["speedMS"])) <= 1e-3 * max(1.0, float(ref["speedMS"]))
+    assert abs(st.engineRPM - float(ref["engineRPM"])) <= 1e-3 * float(ref["engineRPM"])
+    assert np.allclose(list(st.bodyPos), ref["bodyPos"], atol=2e-3)
+    assert np.allclose(list(st.localVelocity), ref["localVelocity"], atol=2e-3)
+    assert np.allclose(st.probes, ref["probes"], atol=5e-3) and np.allclose(st.lookAhead, ref["lookAhead"], atol=1e-4)
+    assert np.allclose(st.tyreLoad, ref["tyreLoad"], rtol=2e-3, atol=1.0)
+    assert np.allclose([st.bodyMatrix.M41, st.bodyMatrix.M42, st.bodyMatrix.M43], ref["bodyMatrix"][12:15], atol=2e-3)
+    pd.destroySimulator(sim)
+
+
+def test_batched_env_reset_step(oracle):
+    import torch
+    from projectd_core_b200.env import BatchedProjectDEnv
+    env = BatchedProjectDEnv(oracle.BASE_PATH, num_envs=1024, device=0, seed=3, teleport_mode=2)
+    obs = env.reset()
+    assert obs.shape == (1024, 24) and obs.is_cuda
+    lo, hi = env.observation_bounds()
+    total = torch.zeros(1024, device="cuda")
+    for t in range(400):
+        a = torch.rand((1024, 2), device="cuda") * 2 - 1
+        obs, rew, term, trunc, _ = env.step(a)
+        total += rew
+    assert torch.isfinite(obs).all() and torch.isfinite(total).all()
+    o = obs.cpu().numpy()
+    assert (o >= lo - 1e-3).all() and (o <= hi + 1e-3).all()
+    st = env.episode_stats()
+    assert st["nan"] == 0
+    env.close()

@@ -1,0 +1,133 @@
+"""CPU-side checks of the product's arithmetic and host logic (no GPU needed).
+
+tests/hostsim compiles the SAME device functions the CUDA kernels are made of (projectd_core_b200/csrc/*.h) with
+g++; it is a debugging aid, not a product path.  Here it is checked against the committed golden vectors of the
+oracle (tests/golden) so that a kernel regression is caught before spending GPU time; the GPU tests proper
+(tests/test_gpu_parity.py) run the CUDA library through the C ABI."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+import pdref
+from parity_util import compare_records
+
+DT = 1.0 / 333.0
+
+
+@pytest.fixture(scope="module")
+def lay():
+    return pdref.Layout()
+
+
+def test_loader_params_equal_reference_init(hostsim, hostsim_env, golden):
+    """car .ini/.lut/.rto parsing + setup spinners + tune re-seat == the reference's own init, byte for byte."""
+    n = hostsim.hs_params_bytes()
+    assert n == golden["params"].size
+    buf = np.zeros(n, np.uint8)
+    hostsim.hs_get_params(hostsim_env, buf.ctypes.data)
+    diff = np.nonzero(buf != golden["params"])[0]
+    assert diff.size == 0, ("parameter block differs at bytes", diff[:16])
+
+
+def test_track_loader_matches_reference(hostsim, hostsim_env, golden):
+    ti = np.zeros(16, np.uint32)
+    hostsim.hs_get_track_info(hostsim_env, ti.ctypes.data)
+    ref = golden["track_info"]
+    assert ti[1] == ref[1] and ti[3] == ref[3] and ti[4] == ref[4]      # nTris, nFatPoints, nSplineNodes
+    assert ti[8] == ref[8]                                              # computedTrackLength (float bits)
+
+
+@pytest.mark.parametrize("variant", ["serial", "quad"])
+def test_single_tick_vs_golden_pairs(hostsim, hostsim_env, golden, lay, variant):
+    """One tick from the oracle's state (controls included) with the kernel arithmetic: ints exact, floats within
+    1e-4 (north-star single-tick tolerance); rare exceedances up to 3e-4 are solver conditioning."""
+    tick = hostsim.hs_tick if variant == "serial" else hostsim.hs_tick_quad
+    worst = 0.0; nbad = 0
+    step = 1 if variant == "serial" else 2
+    idx = range(0, len(golden["pair_before"]), step)
+    for k in idx:
+        rec = golden["pair_before"][k].copy()
+        tick(hostsim_env, rec.ctypes.data, DT, float(golden["pair_time"][k]))
+        bad, w = compare_records(lay, rec, golden["pair_after"][k], tol=1e-4)
+        assert not any(math.isinf(b[3]) for b in bad), (k, [b for b in bad if math.isinf(b[3])][:5])
+        worst = max(worst, w); nbad += bool(bad)
+    assert worst <= 3e-4, worst
+    assert nbad <= max(1, len(idx) // 100), nbad
+
+
+def test_quad_equals_serial_bitwise_mostly(hostsim, hostsim_env, golden, lay):
+    """The 4-lane distribution changes only summation order of the chassis force / Schur terms: <= 2e-6 apart."""
+    for k in range(0, len(golden["pair_before"]), 16):
+        a = golden["pair_before"][k].copy(); b = a.copy()
+        hostsim.hs_tick(hostsim_env, a.ctypes.data, DT, float(golden["pair_time"][k]))
+        hostsim.hs_tick_quad(hostsim_env, b.ctypes.data, DT, float(golden["pair_time"][k]))
+        bad, w = compare_records(lay, b, a, tol=2e-5)
+        assert not bad, (k, bad[:5])
+
+
+def test_teleport_vs_golden(hostsim, hostsim_env, golden, lay):
+    """Car::teleportToSpline + reset (Car.cpp:1325-1340, 385-410) on the device functions."""
+    for u, ref in zip(golden["tele_u"], golden["tele_state"]):
+        rec = golden["tele_state"][0].copy()
+        pid = hostsim.hs_point_id_at_distance(hostsim_env, float(u))
+        hostsim.hs_teleport_point(hostsim_env, rec.ctypes.data, pid, 0.0)
+        bad, w = compare_records(lay, rec, ref, tol=1e-6)
+        assert not bad, (u, bad[:5])
+
+
+def test_raycast_vs_golden(hostsim, hostsim_env, golden):
+    rays = np.ascontiguousarray(golden["rays"]); ref = golden["ray_hits"]
+    out = np.zeros_like(ref)
+    hostsim.hs_raycast(hostsim_env, len(rays), rays.ctypes.data, out.ctypes.data)
+    assert np.array_equal(out[:, 0], ref[:, 0]), "hit flags must match exactly"
+    hit = ref[:, 0] == 1
+    assert hit.sum() > 1000
+    assert np.array_equal(out[hit, 7], ref[hit, 7]), "surface ids must match exactly"
+    assert np.abs(out[hit, 1:7] - ref[hit, 1:7]).max() <= 2e-6
+
+
+def test_sctm_vs_golden(hostsim, hostsim_env, golden):
+    """SCTM::solve (Tyre/SCTM.cpp) restated in pd_car.h: same inputs -> outputs within 2e-6 relative."""
+    x = np.ascontiguousarray(golden["sctm_in"])
+    for w in range(4):
+        y = np.zeros((len(x), 7), np.float32)
+        hostsim.hs_sctm_solve(hostsim_env, w, len(x), x.ctypes.data, y.ctypes.data)
+        ref = golden["sctm_out"][w]
+        err = np.abs(y - ref) / np.maximum(np.abs(ref), 1.0)
+        assert err.max() <= 2e-6, (w, err.max())
+
+
+def test_probe_grid_walk_equals_exhaustive_scan(hostsim, hostsim_env, content_base):
+    """The grid-indexed probe walk / nearest point (pd_track.h) must give the reference's exhaustive-loop results
+    (Track::rayCastTrackBounds Track.cpp:497-562, getPointIdAtLocation :579-596) at arbitrary poses."""
+    fat = np.fromfile(content_base + "/content/tracks/driftplayground/spline.cache", dtype=np.float32).reshape(-1, 15)
+    rng = np.random.default_rng(5)
+    n = 20000
+    idx = rng.integers(0, len(fat), n)
+    poses = np.zeros((n, 4), np.float32)
+    poses[:, 0:3] = fat[idx, 0:3] + rng.uniform(-9, 9, (n, 3)).astype(np.float32) * np.array([1, 0.05, 1], np.float32)
+    poses[:, 3] = rng.uniform(-math.pi, math.pi, n)
+    walk = np.zeros((n, 8), np.float32); brute = np.zeros((n, 8), np.float32)
+    hostsim.hs_probe_compare(hostsim_env, n, poses.ctypes.data, walk.ctypes.data, brute.ctypes.data)
+    ok = walk[:, :7] >= 0     # -1: the walk declined (left the indexed area) and the kernel falls back to the scan
+    assert ok.mean() > 0.99
+    assert np.array_equal(walk[:, :7][ok], brute[:, :7][ok])
+    okp = walk[:, 7] >= 0
+    assert np.array_equal(walk[okp, 7], brute[okp, 7])
+
+
+def test_free_running_1s_vs_golden_trajectory(hostsim, hostsim_env, golden, lay):
+    """configs[0] drive, free running from the teleport state for 250 ticks with the kernel arithmetic vs the
+    oracle's stored record: bounded divergence (5 cm / 0.5 deg, see test_gpu_parity)."""
+    rec = golden["traj_state"][0].copy()
+    t0 = float(golden["traj_time"][0])
+    for t in range(250):
+        lay.set(rec, "car.ctlSteer", 0.3 * math.sin(2 * math.pi * t / 999.0))
+        lay.set(rec, "car.ctlGas", 0.1 + 0.9 * min(1.0, t / 333.0))
+        hostsim.hs_tick(hostsim_env, rec.ctypes.data, DT, t0 + t * DT)
+    ref = golden["traj_state"][1]
+    dp = [lay.get(rec, "chassis." + k) - lay.get(ref, "chassis." + k) for k in ("px", "py", "pz")]
+    assert math.sqrt(sum(d * d for d in dp)) <= 0.05, dp
+    assert lay.get(rec, "car.currentGear") == lay.get(ref, "car.currentGear")
