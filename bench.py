@@ -159,14 +159,11 @@ def ours(args):
     from projectd_core_b200 import Batch
     from parity_util import make_env_like
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from projectd_core_b200 import dist as pdist
+    rank, local, world = pdist.init_from_env("nccl")
     dist = None
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", local if world > 1 else 0)
@@ -174,8 +171,8 @@ def ours(args):
     K, W = args.steps, args.warmup
 
     b = make_env_like(Batch(pdref.BASE_PATH, n_envs=n_envs, device=dev.index))
-    b.set_seed(1234, rank * n_envs)          # RNG keyed by global env id: results do not depend on the sharding
-    b.L.pd_set_tune  # noqa
+    env_offset, _ = pdist.shard_range(world * n_envs, rank, world)
+    b.set_seed(1234, env_offset)             # RNG keyed by global env id: results do not depend on the sharding
     b.teleport_mode(2)                        # random start positions u ~ U[0,1)
     stream = torch.cuda.ExternalStream(b.stream(), device=dev)
     gen = torch.Generator(device=dev); gen.manual_seed(99 + rank)
@@ -210,8 +207,7 @@ def ours(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = b.launch_count() - l0
-    if dist is not None:
-        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ms = pdist.max_over_ranks(ms, dev)
     ticks = K * TICKS_PER_STEP
     value = world * n_envs * ticks / (ms * 1e-3)
 
@@ -228,6 +224,13 @@ def ours(args):
     achieved = alg_bytes / (tick_ms * 1e-3) / 1e9
     # issue-side view (not tensor work): audited ~50 kflop per car-tick against 74 TFLOP/s fp32
     flop_frac = (n_envs / (tick_ms * 1e-3)) * 50e3 / 74e12
+    quad_max = int(os.environ.get("PD_QUAD_MAX_ENVS", "16384"))
+    kernel = "k_tick_quad" if n_envs <= quad_max else "k_tick"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s@%d" % (kernel, n_envs))
+    except Exception:
+        pass
 
     # ---- end to end through the public API with host buffers ----
     h_act = torch.empty((n_envs, 2), dtype=torch.float32).pin_memory()
@@ -256,15 +259,11 @@ def ours(args):
             e2e_tick(acts_host[s])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e_s = pdist.max_over_ranks(e2e_s, dev)
     e2e_value = world * n_envs * e2e_steps * TICKS_PER_STEP / e2e_s
 
     # ---- episode statistics: the only collective of the path (once per rollout, never per tick) ----
-    stats = torch.from_numpy(b.env_stats(reset=False)).to(dev)
-    if dist is not None:
-        dist.all_reduce(stats)
-    stats = stats.cpu().tolist()
+    stats = pdist.reduce_stats(b.env_stats(reset=False), dev).tolist()
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ----
     cpu = None
@@ -282,22 +281,26 @@ def ours(args):
             "config": {"workload": ("configs[1]: 4096 demo-car envs on 1 B200" if (world == 1 and n_envs == 4096) else "%d demo-car envs per GPU (configs[2] uses 65536)" % n_envs)
                        + ", ks_toyota_ae86_drift on driftplayground, random controls resampled every 33 ticks, env auto-reset",
                        "envs_per_gpu": n_envs, "ticks_per_step": TICKS_PER_STEP, "dt": DT,
-                       "l2": "state %.0f MB per tick + inputs regenerated per step; 4096-env state (%.1f MB) is L2-resident by design, see DESIGN.md" % (n_envs * words * 4 / 1e6, n_envs * words * 4 / 1e6),
+                       "l2": ("no flush: the working set is the env state (%.1f MB), read and written every tick; " % (n_envs * words * 4 / 1e6))
+                             + ("it is larger than L2 (126 MB)" if n_envs * words * 4 > 126e6 else "it fits L2 and staying L2-resident between consecutive ticks IS the workload (a simulation steps the same state), see DESIGN.md"),
                        "parallelism": "env-sharded x%d, no per-tick collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TICKS_PER_STEP * n_envs * 8, "d2h_bytes_per_step": TICKS_PER_STEP * n_envs * (96 + 4 + 4),
                     "note": "per tick: pinned H2D actions, pd_env_step, D2H obs+reward+done, stream sync"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_tick", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_kind, "algorithmic_bytes_per_car_tick": alg_bytes / n_envs, "kernel_ms": tick_ms,
                          "fp32_issue_frac_of_74TFLOPs_at_50kflop_per_car_tick": flop_frac},
             "cpu_baseline": cpu,
             "episode_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None, "mean_length": (stats[2] / stats[0]) if stats[0] else None,
                               "collisions": stats[3], "offtrack": stats[4], "stuck": stats[5], "lowreward": stats[6], "nan": stats[7]},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+    b.sync(); b.close()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)      # skip interpreter teardown: torch may destroy the CUDA context before ctypes-held handles are released
 
 
 def main():
