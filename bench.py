@@ -242,12 +242,9 @@ def ours(args):
     e2e_steps = min(K, 8)
 
     def e2e_tick(a_host):
+        # the call a host-side user makes: actions in (pinned) host memory in, obs / reward / done in host memory out
         h_act.copy_(a_host)
-        with torch.cuda.stream(stream):
-            d_act.copy_(h_act, non_blocking=True)
-            b.env_step(d_act, DT, None, rew, done)
-            h_obs.copy_(obs, non_blocking=True); h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)
-        stream.synchronize()
+        b.env_step_host(h_act, DT, h_obs, h_rew, h_done)
         return float(h_rew[0])
 
     for _ in range(3):
@@ -285,7 +282,7 @@ def ours(args):
                              + ("it is larger than L2 (126 MB)" if n_envs * words * 4 > 126e6 else "it fits L2 and staying L2-resident between consecutive ticks IS the workload (a simulation steps the same state), see DESIGN.md"),
                        "parallelism": "env-sharded x%d, no per-tick collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TICKS_PER_STEP * n_envs * 8, "d2h_bytes_per_step": TICKS_PER_STEP * n_envs * (96 + 4 + 4),
-                    "note": "per tick: pinned H2D actions, pd_env_step, D2H obs+reward+done, stream sync"},
+                    "note": "per tick one pd_env_step_host call: pinned H2D actions, step, D2H obs+reward+done, stream sync"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -108,6 +108,11 @@ int pd_get_rewards(pd_batch* b, float* step_reward, float* total_reward, int32_t
  * (teleport by `PD_TELEPORT_*` mode + one zero-action tick, projectd_env.py:216-227) of finished envs.
  * actions / obs / reward / done are DEVICE pointers (obs may be NULL to use the internal buffer). */
 int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev, float* reward_dev, int32_t* done_dev);
+/* The same step for a caller that lives on the host (what ProjectDEnv.step is to a Python user): actions[n_envs][2]
+ * are copied host -> device, obs[n_envs][24] / reward[n_envs] / done[n_envs] device -> host, all on the batch's
+ * stream, one synchronisation at the end.  Pinned (page-locked) host buffers make the copies asynchronous;
+ * pageable ones work too.  obs / reward / done may be NULL. */
+int pd_env_step_host(pd_batch* b, const float* actions_host, float dt, float* obs_host, float* reward_host, int32_t* done_host);
 /* episode statistics accumulated by pd_env_step since the last call: sums over envs, ready for an NCCL
  * all-reduce: {episodes, sum_return, sum_length, collisions, offtrack, stuck, lowreward, nan} as float64[8] */
 int pd_env_stats(pd_batch* b, double* out8, int reset);

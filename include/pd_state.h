@@ -4,10 +4,11 @@
  * One record = everything the reference keeps between two ticks for ONE car of the
  * demo-car topology: 7 rigid bodies, 4 tyres with
  * their 12x3 thermal patch grid, drivetrain / engine / assist state machines, track
- * locator and scoring state.  On the device the record is stored structure-of-arrays
- * (word w of env e lives at state[w * n_envs + e], 32-bit words, doubles as lo/hi
- * word pairs); on the host (snapshot / restore, parity tests, the oracle harness) it is
- * the flat array of PD_STATE_WORDS 32-bit words laid out by the X-macros below.
+ * locator and scoring state.  On the host (get / set state, parity tests, the oracle harness) a record is
+ * the flat array of PD_STATE_WORDS 32-bit words laid out by the X-macros below (doubles = 2 words at an even
+ * word offset).  On the device the library keeps either an array of such records (stride PD_STATE_STRIDE,
+ * staged through shared memory by the 4-lanes-per-car kernel) or a tiled structure-of-arrays (thread-per-car
+ * kernel); see projectd_core_b200/csrc/pd_state_io.h.
  *
  * Reference anchors for every group are given next to the list that defines it
  * (paths relative to the reference tree, src/ProjectD/...).
@@ -49,13 +50,15 @@
 
 /* ---- tyre: TyreStatus (Car/TyreStatus.h:5-45) + Tyre runtime members (Car/Tyre.h:88-106) ---- */
 #define PD_TYRE_FIELDS(X) \
+    /* doubles first: the group starts on an even word, so they are 8-byte aligned in a record */ \
+    X(D, virtualKM) X(D, flatSpot) X(D, phase) \
     X(F, depth) X(F, load) X(F, camberRAD) X(F, slipAngleRAD) X(F, slipRatio) \
     X(F, angularVelocity) X(F, Fy) X(F, Fx) X(F, Mz) X(I, isLocked) \
     X(F, slipFactor) X(F, ndSlip) X(F, distToGround) X(F, Dy) X(F, Dx) X(F, D) \
     X(F, dirtyLevel) X(F, rollingResistence) X(F, thermalInput) X(F, feedbackTorque) \
     X(F, loadedRadius) X(F, effectiveRadius) X(F, liveRadius) \
-    X(F, pressureStatic) X(F, pressureDynamic) X(D, virtualKM) X(F, inflation) \
-    X(D, flatSpot) X(F, wearMult) \
+    X(F, pressureStatic) X(F, pressureDynamic) X(F, inflation) \
+    X(F, wearMult) \
     X(F, oldAngularVelocity) X(F, localMX) \
     X(F, contactX) X(F, contactY) X(F, contactZ) \
     X(F, normalX) X(F, normalY) X(F, normalZ) \
@@ -64,18 +67,24 @@
     X(F, brakeTorque) X(F, handBrakeTorque) \
     X(F, suspTravel) X(F, suspDamperSpeed) \
     /* TyreThermalModel (Car/TyreThermalModel.h:36-49) */ \
-    X(F, coreTemp) X(D, phase) X(F, practicalTemp) X(F, thermalMultD)
+    X(F, coreTemp) X(F, practicalTemp) X(F, thermalMultD) \
+    X(I, tyrePad)   /* keeps the tyre group an even number of words */
 
 /* ---- car-level (Car/Car.h:187-246, AutoClutch.h, AutoBlip.h, AutoShifter.h, GearChanger.h,
  *      Drivetrain.h:98-145, Engine.h:96-115, ScoringSystem.h:47-66, Track.h:76,79) ---- */
 #define PD_CAR_FIELDS(X) \
+    /* doubles first (8-byte aligned inside the record): fuel, AutoBlip, Drivetrain (Drivetrain.h:98-145), Engine */ \
+    X(D, fuel) X(D, blipStartTime) X(D, reqTimeAcc) X(D, reqTimeout) \
+    X(D, engineVel) X(D, driveVel) X(D, shaftLVel) X(D, shaftRVel) X(D, rootVel) \
+    X(D, locClutch) X(D, lastRatio) X(D, cutOff) \
+    X(D, validShiftRPMWindow) X(D, currentClutchTorque) X(D, outTorque) \
     /* CarControls (Car/CarControls.h:9-20) as last written by the caller / the assists */ \
     X(F, ctlSteer) X(F, ctlClutch) X(F, ctlBrake) X(F, ctlHandBrake) X(F, ctlGas) \
     X(I, ctlRequestedGear) X(I, ctlGearUp) X(I, ctlGearDn) X(I, smoothSteer) \
     X(F, smoothSteerValue) X(F, finalSteerAngleSignal) \
     X(F, lastVelX) X(F, lastVelY) X(F, lastVelZ) \
     X(F, accGX) X(F, accGY) X(F, accGZ) \
-    X(D, fuel) X(I, sleepingFrames) X(F, waterT) X(F, speed) \
+    X(I, sleepingFrames) X(F, waterT) X(F, speed) \
     X(I, collisionFlag) X(I, outOfTrackFlag) \
     /* track locator */ \
     X(I, nearestTrackPointId) X(I, oldTrackPointId) X(I, splinePointId) \
@@ -85,15 +94,12 @@
     /* AutoClutch */ \
     X(F, acSeqTime) X(I, acSeqDone) X(I, acSeqProfile) X(F, acClutchValueSignal) \
     /* AutoBlip / AutoShifter / GearChanger */ \
-    X(D, blipStartTime) X(F, gasCutoff) X(I, lastGearUp) X(I, lastGearDn) \
+    X(F, gasCutoff) X(I, lastGearUp) X(I, lastGearDn) \
     /* Drivetrain */ \
-    X(I, reqRequest) X(D, reqTimeAcc) X(D, reqTimeout) X(I, reqGear) \
-    X(D, engineVel) X(D, driveVel) X(D, shaftLVel) X(D, shaftRVel) X(D, rootVel) \
-    X(D, locClutch) X(D, lastRatio) X(D, cutOff) \
+    X(I, reqRequest) X(I, reqGear) \
     X(I, currentGear) X(I, isGearGrinding) X(I, clutchOpenState) \
-    X(D, validShiftRPMWindow) X(D, currentClutchTorque) \
     /* Engine */ \
-    X(I, limiterOn) X(F, lifeLeft) X(F, fuelPressure) X(F, gasUsage) X(D, outTorque) \
+    X(I, limiterOn) X(F, lifeLeft) X(F, fuelPressure) X(F, gasUsage) \
     /* ScoringSystem */ \
     X(I, drifting) X(I, driftExtreme) X(I, driftInvalid) \
     X(F, currentDriftAngle) X(F, currentSpeedMultiplier) X(F, lastDriftDirection) \
@@ -125,6 +131,9 @@
 #define PD_OFF_PROBES    (PD_OFF_CAR + PD_CAR_SCALAR_WORDS)
 #define PD_OFF_LOOKAHEAD (PD_OFF_PROBES + PD_MAX_PROBES)
 #define PD_STATE_WORDS   (PD_OFF_CAR + PD_CAR_WORDS)
+/* record stride of the array-of-records device layout: a multiple of 4 words (16-byte bulk copies) whose value
+ * mod 32 (= 20) spreads the same word of 8 consecutive records over 8 different shared-memory bank groups */
+#define PD_STATE_STRIDE  628
 
 /* per-field word offsets inside their group: PD_BODY_o_px, PD_TYRE_o_load, PD_CAR_o_fuel ... */
 #define PD__ENUM_B(kind, name) PD_BODY_o_##name, PD_BODY_e_##name = PD_BODY_o_##name + PD__W_##kind - 1,

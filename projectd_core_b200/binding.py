@@ -70,6 +70,7 @@ def load_library():
         "pd_obs_device_ptr": (vp, [vp]),
         "pd_get_rewards": (i, [vp, vp, vp, vp]),
         "pd_env_step": (i, [vp, vp, f, vp, vp, vp]),
+        "pd_env_step_host": (i, [vp, vp, f, vp, vp, vp]),
         "pd_env_stats": (i, [vp, vp, i]),
         "pd_get_state": (i, [vp, i, vp]),
         "pd_set_state": (i, [vp, i, vp]),
@@ -195,6 +196,11 @@ class Batch:
 
     def env_step(self, actions_dev, dt=1.0 / 333.0, obs=None, reward=None, done=None):
         self._ck(self.L.pd_env_step(self.h, _ptr(actions_dev), float(dt), _ptr(obs), _ptr(reward), _ptr(done)))
+
+    def env_step_host(self, actions, dt=1.0 / 333.0, obs=None, reward=None, done=None):
+        """One env step for host-resident buffers (numpy arrays or CPU torch tensors, ideally pinned):
+        H2D actions, step, D2H obs / reward / done, one stream sync."""
+        self._ck(self.L.pd_env_step_host(self.h, _ptr(actions), float(dt), _ptr(obs), _ptr(reward), _ptr(done)))
 
     def env_stats(self, reset=True):
         out = np.zeros(8, dtype=np.float64)

@@ -71,10 +71,13 @@ extern const char* const kScoringVarNames[PD_NUM_SCORING_VARS];
 
 /* ---- track ---- */
 struct BvhNodeH { float bmin[3]; int32_t left; float bmax[3]; int32_t count; };
+#ifndef PD_TRI_STRIDE
+#define PD_TRI_STRIDE 12
+#endif
 struct TrackModel {
     PdTrackInfo info;
     std::vector<PdSurface> surfaces;
-    std::vector<float> tris;          /* 9 per triangle, leaf order: v0, e1, e2 */
+    std::vector<float> tris;          /* PD_TRI_STRIDE (12) floats per triangle, leaf order: v0, e1, e2, surface id bits, 0, 0 */
     std::vector<int32_t> triSurf;
     std::vector<BvhNodeH> nodes;
     std::vector<PdFatPoint> fat;
@@ -85,6 +88,8 @@ struct TrackModel {
     std::vector<int32_t> colStart, colItems;     /* CSR per cell: triangle indices (leaf order of `tris`) */
     std::vector<int32_t> segStart, segItems;   /* CSR per cell: boundary segments, item = id * 2 + side (0 left, 1 right) */
     std::vector<int32_t> ptStart, ptItems;     /* CSR per cell: fat point ids (by `best`) */
+    std::vector<float> segRec;                 /* 8 floats per segItems entry: ax, az, bx, bz, best.xyz of the owning point, 0 */
+    std::vector<float> ptRec;                  /* 4 floats per ptItems entry: best.xyz, id (as int bits) */
 };
 void load_track(const std::string& basePath, const std::string& name, TrackModel& out);
 /* synthetic track generator for config 4 (large mesh): closed loop of `nPoints` spline points, tessellated */

@@ -87,13 +87,14 @@ void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& sur
     B.nodes.reserve(nt); B.nodes.push_back(BvhNodeH{});
     if (nt > 0) B.build(0, 0, nt);
     out.nodes = B.nodes;
-    out.tris.resize((size_t)nt * 9); out.triSurf.resize(nt);
+    out.tris.assign((size_t)nt * PD_TRI_STRIDE, 0.0f); out.triSurf.resize(nt);
     for (uint32_t i = 0; i < nt; ++i) {
-        const uint32_t t = B.order[i]; const float* p = &verts9[(size_t)t * 9]; float* q = &out.tris[(size_t)i * 9];
+        const uint32_t t = B.order[i]; const float* p = &verts9[(size_t)t * 9]; float* q = &out.tris[(size_t)i * PD_TRI_STRIDE];
         q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
         q[3] = p[3] - p[0]; q[4] = p[4] - p[1]; q[5] = p[5] - p[2];     /* e1 = v1 - v0 */
         q[6] = p[6] - p[0]; q[7] = p[7] - p[1]; q[8] = p[8] - p[2];     /* e2 = v2 - v0 */
         out.triSurf[i] = surf[t];
+        memcpy(&q[9], &surf[t], 4);                                      /* surface id inline (int bits) */
     }
     out.info.nTris = (int32_t)nt; out.info.nNodes = (int32_t)out.nodes.size();
     build_column_grid(out);
@@ -110,7 +111,7 @@ void build_column_grid(TrackModel& out) {
     float x0 = 3.4e38f, x1 = -3.4e38f, z0 = 3.4e38f, z1 = -3.4e38f;
     std::vector<float> bx0(nt), bx1(nt), bz0(nt), bz1(nt);
     for (size_t t = 0; t < nt; ++t) {
-        const float* p = &out.tris[t * 9];
+        const float* p = &out.tris[t * PD_TRI_STRIDE];
         const float ax = p[0], az = p[2], bx = p[0] + p[3], bz = p[2] + p[5], cx = p[0] + p[6], cz = p[2] + p[8];
         bx0[t] = std::min(ax, std::min(bx, cx)) - 1e-3f; bx1[t] = std::max(ax, std::max(bx, cx)) + 1e-3f;
         bz0[t] = std::min(az, std::min(bz, cz)) - 1e-3f; bz1[t] = std::max(az, std::max(bz, cz)) + 1e-3f;
@@ -180,6 +181,20 @@ static void build_bound_grid(TrackModel& out) {
         out.ptStart[c] = (int32_t)out.ptItems.size(); out.ptItems.insert(out.ptItems.end(), pts[c].begin(), pts[c].end());
     }
     out.segStart[nc] = (int32_t)out.segItems.size(); out.ptStart[nc] = (int32_t)out.ptItems.size();
+    /* the same lists with the data inlined, so that a cell visit is index -> records (no id -> point indirection) */
+    out.segRec.resize(out.segItems.size() * 8); out.ptRec.resize(out.ptItems.size() * 4);
+    for (size_t k = 0; k < out.segItems.size(); ++k) {
+        const int item = out.segItems[k], id = item >> 1;
+        const PdFatPoint& f = out.fat[id]; const PdFatPoint& g = out.fat[id + 1 < n ? id + 1 : 0];
+        const float* a = (item & 1) ? f.right : f.left; const float* b = (item & 1) ? g.right : g.left;
+        float* r = &out.segRec[k * 8];
+        r[0] = a[0]; r[1] = a[2]; r[2] = b[0]; r[3] = b[2]; r[4] = f.best[0]; r[5] = f.best[1]; r[6] = f.best[2]; r[7] = 0.0f;
+    }
+    for (size_t k = 0; k < out.ptItems.size(); ++k) {
+        const int32_t id = out.ptItems[k]; const PdFatPoint& f = out.fat[id];
+        float* r = &out.ptRec[k * 4];
+        r[0] = f.best[0]; r[1] = f.best[1]; r[2] = f.best[2]; memcpy(&r[3], &id, 4);
+    }
 }
 
 /* Track::initTrackPoints tail (Track.cpp:207-271) + BSpline3d::init_from_array */

@@ -7,7 +7,8 @@
  *   k_teleport      Car::teleportToSpline (reset path)
  *   k_set_controls / k_set_actions   setCarControls / the env's action mapping
  *   k_observe       the 24-float observation of pyprojectd/projectd_env.py:237-275
- *   k_env_done      reward + termination logic of ProjectDEnv.step (projectd_env.py:178-212) + episode stats
+ *   env_epilogue    (inside the tick kernels) observation + reward / termination logic of ProjectDEnv.step
+ *                   (projectd_env.py:178-212) + episode statistics
  *   k_raycast       batch rays against the track BVH
  * State is structure-of-arrays in HBM (include/pd_state.h); car parameters and the track are read-only
  * device buffers shared by all envs (served from L2/L1 after first touch).
@@ -26,14 +27,64 @@ using namespace pd;
 
 #define PD_BLOCK 64
 #define PD_QBLOCK 64   /* threads per block of the quad kernel = stride of the lane-interleaved solver scratch */
+#define PD_QCARS (PD_QBLOCK / 4)
 
 /* ------------------------------------------------------------------ kernels ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(PD_BLOCK) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
+/* Optional env-step work fused into the tick kernels (null pointers: skipped).
+ *   act      [n][2]  actions -> controls BEFORE the tick (projectd_env.py:158-170)
+ *   obs      [n][24] observation AFTER the tick (:237-275)
+ *   reward / done / envReturn / envLen / stats: ProjectDEnv.step tail (:178-212) + episode statistics */
+struct EnvIO {
+    const float* act; float* obs;
+    float* reward; int32_t* done; float* envReturn; int32_t* envLen; double* stats;
+    double timeAfter;
+};
+
+template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv, int e, bool on, const EnvIO& io, unsigned warpMask) {
+    if (on && io.obs) {
+        float o[PD_OBS_DIM];
+        car_observe(sv, o);
+        float4* dst = reinterpret_cast<float4*>(io.obs + (size_t)e * PD_OBS_DIM);     /* 96 B per env, 16-byte aligned */
+#pragma unroll
+        for (int k = 0; k < PD_OBS_DIM / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
+    if (!io.reward) return;
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (on) {
+        float r; int d;
+        env_reward_done(sv, io.timeAfter, r, d);
+        const float ret = io.envReturn[e] + r; const int len = io.envLen[e] + 1;
+        if (ret < -200.0f) d |= PD_DONE_LOWREWARD;
+        io.reward[e] = r; io.done[e] = d;
+        if (d) {
+            s[0] = 1; s[1] = ret; s[2] = len;
+            s[3] = (d & PD_DONE_COLLISION) ? 1 : 0; s[4] = (d & PD_DONE_OFFTRACK) ? 1 : 0; s[5] = (d & PD_DONE_STUCK) ? 1 : 0;
+            s[6] = (d & PD_DONE_LOWREWARD) ? 1 : 0; s[7] = (d & PD_DONE_NAN) ? 1 : 0;
+            io.envReturn[e] = 0; io.envLen[e] = 0;
+        } else { io.envReturn[e] = ret; io.envLen[e] = len; }
+    }
+    /* warp-level reduction, one atomic per warp and statistic */
+    const bool any = __any_sync(warpMask, s[0] != 0.0);
+    if (!any) return;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double v = s[k];
+        for (int off = 16; off > 0; off >>= 1) { const double o2 = __shfl_down_sync(warpMask, v, off); if ((threadIdx.x & 31) + off < 32 && ((warpMask >> ((threadIdx.x & 31) + off)) & 1u)) v += o2; }
+        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&io.stats[k], v);
+    }
+}
+
+/* the tick, one thread per car, tiled structure-of-arrays state (batches above the quad threshold) */
+__global__ void __launch_bounds__(PD_BLOCK) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+                                                   const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    if (mask && !mask[e]) return;
-    SV sv = sv_tiled(state, (size_t)e);
-    car_tick(P, T, sv, dt, time);
+    const bool on = e < n && (!mask || mask[e]);
+    SVTile sv = sv_tiled(state, (size_t)(e < n ? e : 0));
+    if (on) {
+        if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
+        car_tick(P, T, sv, dt, time);
+    }
+    env_epilogue(sv, e, on, io, 0xffffffffu);
 }
 
 /* exchange policy of pd_quad.h on the GPU: shuffles inside the quad, with the quad's own member mask */
@@ -45,32 +96,74 @@ struct QuadShfl {
     __device__ __forceinline__ float sum(float v) const { v += __shfl_xor_sync(mask, v, 1); v += __shfl_xor_sync(mask, v, 2); return v; }
     __device__ __forceinline__ V3 sum(V3 v) const { return v3(sum(v.x), sum(v.y), sum(v.z)); }
     __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 
-/* the tick, four lanes per car: thread t -> env t / 4, lane t % 4 */
-__global__ void __launch_bounds__(64) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time, const int32_t* __restrict__ mask) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int e = t >> 2;
-    if (e >= n) return;                       /* whole quads leave together */
-    if (mask && !mask[e]) return;
-    QuadShfl ex; ex.lane = t & 3; ex.base = (threadIdx.x & 31) & ~3; ex.mask = 0xFu << ex.base;
-    SV sv = sv_tiled(state, (size_t)e);
-    extern __shared__ float pd_smem[];          /* solver scratch: PD_GSCR_WORDS x blockDim, lane-interleaved */
-    car_tick_quad<PD_QBLOCK>(P, T, sv, dt, time, ex, pd_smem + threadIdx.x);
+/* ---- bulk asynchronous copies HBM <-> shared memory (the TMA engine's 1-D path: SASS UBLKCP) ---- */
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#define PD_QUAD_SMEM_BYTES (PD_QCARS * PD_STATE_STRIDE * 4 + PD_QBLOCK * PD_GSCR_WORDS * 4 + 16)
+
+/* the tick, four lanes per car, array-of-records state staged through shared memory:
+ * block = 64 threads = 16 cars; ONE bulk copy brings the block's 16 records (40 KB) in, the quads work on the
+ * shared-memory copy (thread t -> car t / 4, lane t % 4), ONE bulk copy writes them back. */
+__global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+                                                         const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
+    extern __shared__ __align__(128) uint32_t pd_smem[];
+    uint32_t* recs = pd_smem;                                                         /* [16][PD_STATE_STRIDE] */
+    float* scratch = reinterpret_cast<float*>(pd_smem + PD_QCARS * PD_STATE_STRIDE);  /* [PD_GSCR_WORDS][64], lane-interleaved */
+    uint64_t* bar = reinterpret_cast<uint64_t*>(pd_smem + PD_QCARS * PD_STATE_STRIDE + PD_QBLOCK * PD_GSCR_WORDS);
+    const int tid = threadIdx.x;
+    const int car0 = blockIdx.x * PD_QCARS;
+    const int ncars = min(PD_QCARS, n - car0);
+    const int car = tid >> 2, e = car0 + car;
+    const bool on = car < ncars && (!mask || mask[e]);
+    if (mask && !__syncthreads_or(on)) return;                 /* reset pass: nothing to do for this block */
+    const uint32_t bytes = (uint32_t)ncars * PD_STATE_STRIDE * 4;
+    uint32_t* gsrc = state + (size_t)car0 * PD_STATE_STRIDE;
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (tid == 0) { mbar_expect_tx(bar, bytes); bulk_g2s(recs, gsrc, bytes, bar); }
+    mbar_wait(bar, 0);
+    uint32_t* rec = recs + car * PD_STATE_STRIDE;
+    SVFlat sv = sv_flat(rec);
+    if (on) {
+        QuadShfl ex; ex.lane = tid & 3; ex.base = (tid & 31) & ~3; ex.mask = 0xFu << ex.base;
+        if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
+        car_tick_quad<PD_QBLOCK>(P, T, sv, dt, time, ex, scratch + tid);
+    }
+    fence_async_smem();                                        /* generic-proxy writes -> visible to the bulk copy engine */
+    __syncthreads();
+    if (tid == 32) { bulk_s2g(gsrc, recs, bytes); }
+    if (tid < 32) {                                            /* warp 0: one thread per car of the block */
+        const int c2 = tid, e2 = car0 + c2;
+        const bool on2 = c2 < ncars && (!mask || mask[e2]);
+        SVFlat sv2 = sv_flat(recs + (c2 < PD_QCARS ? c2 : 0) * PD_STATE_STRIDE);
+        env_epilogue(sv2, e2, on2 && c2 < PD_QCARS, io, 0xffffffffu);
+    }
+    if (tid == 32) bulk_wait_all();                            /* the copy engine has read (and written) everything before the block retires */
 }
 
-__global__ void k_broadcast(uint32_t* state, int n, const uint32_t* __restrict__ rec) {
+/* initial record -> every env (both layouts) */
+__global__ void k_broadcast(uint32_t* state, int layout, size_t nAlloc, const uint32_t* __restrict__ rec) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n * PD_STATE_WORDS) return;   /* n = padded env count (multiple of PD_TILE) */
-    state[i] = rec[(i / PD_TILE) % PD_STATE_WORDS];
-}
-
-__global__ void __launch_bounds__(PD_BLOCK) k_teleport(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int n, const int32_t* __restrict__ mask, const int32_t* __restrict__ pointIds, double time) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    if (mask && !mask[e]) return;
-    SV sv = sv_tiled(state, (size_t)e);
-    car_teleport_to_point(*P, T, sv, pointIds[e], time);
+    if (i >= nAlloc) return;
+    if (layout == PD_LAYOUT_RECORDS) { const int w = (int)(i % PD_STATE_STRIDE); state[i] = w < PD_STATE_WORDS ? rec[w] : 0u; }
+    else state[i] = rec[(i / PD_TILE) % PD_STATE_WORDS];
 }
 
 /* counter-based uniform in [0,1): splitmix64 of (seed, global env id, episode counter) */
@@ -80,23 +173,28 @@ __host__ __device__ inline float pd_uniform(uint64_t seed, uint64_t id, uint64_t
     return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
-/* choose the spline point for a teleport by mode (Car::teleportByMode, Car.cpp:1342-1358) */
-__global__ void k_pick_points(TrackDev T, const uint32_t* __restrict__ state, int n, const int32_t* __restrict__ mask, int mode, const float* __restrict__ distNorm,
-                              uint64_t seed, uint64_t idOffset, uint32_t* __restrict__ episodeCtr, int32_t* __restrict__ pointIds) {
+/* Teleport (reset path): choose the spline point by mode (Car::teleportByMode, Car.cpp:1342-1358)
+ * and re-seat the car there (Car::teleportToSpline); zeroAction: also write the reset's zero action and clear the
+ * NaN guard (auto-reset inside pd_env_step, projectd_env.py:216-227). */
+__global__ void __launch_bounds__(PD_BLOCK) k_teleport(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int layout, int n, const int32_t* __restrict__ mask,
+                                                       int mode, const float* __restrict__ distNorm, uint64_t seed, uint64_t idOffset, uint32_t* __restrict__ episodeCtr,
+                                                       double time, int zeroAction) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (mask && !mask[e]) return;
+    SVR sv = sv_env(layout, state, (size_t)e);
     float u = 0.0f;
     if (distNorm) u = distNorm[e];
-    else if (mode == PD_TELEPORT_NEAREST) u = u2f(state[state_index(PD_OFF_CAR + PD_CAR_o_trackLocation, (size_t)e)]);
+    else if (mode == PD_TELEPORT_NEAREST) u = sv.f(PD_OFF_CAR + PD_CAR_o_trackLocation);
     else if (mode == PD_TELEPORT_RANDOM) { u = pd_uniform(seed, idOffset + (uint64_t)e, episodeCtr[e]); episodeCtr[e]++; }
-    pointIds[e] = point_id_at_distance(T, u);
+    car_teleport_to_point(*P, T, sv, point_id_at_distance(T, u), time);
+    if (zeroAction) { sv.i(PD_OFF_CAR + PD_CAR_o_nanFlag, 0); env_apply_action(sv, 0.0f, 0.0f); }
 }
 
-__global__ void k_set_controls(uint32_t* state, int n, const float* __restrict__ ctl, const int8_t* __restrict__ gears, int smooth) {
+__global__ void k_set_controls(uint32_t* state, int layout, int n, const float* __restrict__ ctl, const int8_t* __restrict__ gears, int smooth) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    SV sv = sv_tiled(state, (size_t)e);
+    SVR sv = sv_env(layout, state, (size_t)e);
     const int o = PD_OFF_CAR;
     sv.f(o + PD_CAR_o_ctlSteer, ctl[e * 5 + 0]); sv.f(o + PD_CAR_o_ctlClutch, ctl[e * 5 + 1]); sv.f(o + PD_CAR_o_ctlBrake, ctl[e * 5 + 2]);
     sv.f(o + PD_CAR_o_ctlHandBrake, ctl[e * 5 + 3]); sv.f(o + PD_CAR_o_ctlGas, ctl[e * 5 + 4]);
@@ -106,76 +204,37 @@ __global__ void k_set_controls(uint32_t* state, int n, const float* __restrict__
     sv.i(o + PD_CAR_o_smoothSteer, smooth);
 }
 
-/* projectd_env.py:159-170.  zeroMask: envs that take the reset's zero action [0,0,0] (projectd_env.py:220) */
-__global__ void k_set_actions(uint32_t* state, int n, const float* __restrict__ act, const int32_t* __restrict__ zeroMask) {
+__global__ void k_set_actions(uint32_t* state, int layout, int n, const float* __restrict__ act) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    if (zeroMask && !zeroMask[e]) return;
-    SV sv = sv_tiled(state, (size_t)e);
-    const int o = PD_OFF_CAR;
-    const float a0 = zeroMask ? 0.0f : act[e * 2 + 0], a1 = zeroMask ? 0.0f : act[e * 2 + 1];
-    sv.f(o + PD_CAR_o_ctlSteer, a0); sv.f(o + PD_CAR_o_ctlClutch, 0.0f); sv.f(o + PD_CAR_o_ctlBrake, 0.0f); sv.f(o + PD_CAR_o_ctlHandBrake, 0.0f);
-    sv.f(o + PD_CAR_o_ctlGas, linscalef(a1, -1.0f, 1.0f, 0.1f, 1.0f));
-    sv.i(o + PD_CAR_o_ctlRequestedGear, -1); sv.i(o + PD_CAR_o_ctlGearUp, 0); sv.i(o + PD_CAR_o_ctlGearDn, 0); sv.i(o + PD_CAR_o_smoothSteer, 1);
+    env_apply_action(sv_env(layout, state, (size_t)e), act[e * 2 + 0], act[e * 2 + 1]);
 }
 
-__global__ void k_observe(const uint32_t* state, int n, float* __restrict__ obs) {
+__global__ void k_observe(const uint32_t* state, int layout, int n, float* __restrict__ obs) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    SV sv = sv_tiled(const_cast<uint32_t*>(state), (size_t)e);
+    SVR sv = sv_env(layout, const_cast<uint32_t*>(state), (size_t)e);
     float o[PD_OBS_DIM];
     car_observe(sv, o);
     for (int k = 0; k < PD_OBS_DIM; ++k) obs[(size_t)e * PD_OBS_DIM + k] = o[k];
 }
 
-__global__ void k_rewards(const uint32_t* state, int n, float* stepReward, float* totalReward, int32_t* flags) {
+__global__ void k_rewards(const uint32_t* state, int layout, int n, float* stepReward, float* totalReward, int32_t* flags) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    SV sv = sv_tiled(const_cast<uint32_t*>(state), (size_t)e);
+    SVR sv = sv_env(layout, const_cast<uint32_t*>(state), (size_t)e);
     if (stepReward) stepReward[e] = sv.f(PD_OFF_CAR + PD_CAR_o_stepReward);
     if (totalReward) totalReward[e] = sv.f(PD_OFF_CAR + PD_CAR_o_totalReward);
     if (flags) flags[e] = (sv.i(PD_OFF_CAR + PD_CAR_o_collisionFlag) ? 1 : 0) | (sv.i(PD_OFF_CAR + PD_CAR_o_outOfTrackFlag) ? 2 : 0);
 }
 
-/* ProjectDEnv.step tail (projectd_env.py:178-212): penalties, termination, per-env return; plus episode statistics */
-__global__ void k_env_done(const uint32_t* state, int n, double timeAfter, float* __restrict__ reward, int32_t* __restrict__ done,
-                           float* __restrict__ envReturn, int32_t* __restrict__ envLen, double* __restrict__ stats) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (e < n) {
-        SV sv = sv_tiled(const_cast<uint32_t*>(state), (size_t)e);
-        const int o = PD_OFF_CAR;
-        float r = sv.f(o + PD_CAR_o_stepReward);
-        int d = 0;
-        if (sv.i(o + PD_CAR_o_collisionFlag)) { r -= 50.0f; d |= PD_DONE_COLLISION; }
-        if (sv.i(o + PD_CAR_o_outOfTrackFlag)) { r -= 50.0f; d |= PD_DONE_OFFTRACK; }
-        /* dstate.timestamp is the physics time the tick ran at (Car.cpp:808) = timeAfter - dt; the env compares
-           lastTrackPointTimestamp + 5 s against it */
-        const float timestamp = (float)timeAfter;
-        if (sv.f(o + PD_CAR_o_lastTrackPointTimestamp) + 5.0f < timestamp) { r -= 50.0f; d |= PD_DONE_STUCK; }
-        if (sv.i(o + PD_CAR_o_nanFlag)) d |= PD_DONE_NAN;
-        envReturn[e] += r; envLen[e] += 1;
-        if (envReturn[e] < -200.0f) d |= PD_DONE_LOWREWARD;
-        reward[e] = r; done[e] = d;
-        if (d) {
-            s[0] = 1; s[1] = envReturn[e]; s[2] = envLen[e];
-            s[3] = (d & PD_DONE_COLLISION) ? 1 : 0; s[4] = (d & PD_DONE_OFFTRACK) ? 1 : 0; s[5] = (d & PD_DONE_STUCK) ? 1 : 0;
-            s[6] = (d & PD_DONE_LOWREWARD) ? 1 : 0; s[7] = (d & PD_DONE_NAN) ? 1 : 0;
-            envReturn[e] = 0; envLen[e] = 0;
-        }
-    }
-    /* warp-level reduction, one atomic per warp and statistic */
-    for (int k = 0; k < 8; ++k) {
-        double v = s[k];
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&stats[k], v);
-    }
-}
-
-__global__ void k_clear_nan(uint32_t* state, int n, const int32_t* __restrict__ mask) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n || !mask[e]) return;
-    state[state_index(PD_OFF_CAR + PD_CAR_o_nanFlag, (size_t)e)] = 0;
+/* host record layout <-> device layout: words [PD_STATE_WORDS][n] on the host side (snapshot / restore) */
+__global__ void k_pack(uint32_t* state, int layout, int n, uint32_t* __restrict__ soa, int toDevice) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * PD_STATE_WORDS) return;
+    const int w = (int)(i / n); const size_t e = i % n;
+    const size_t j = state_index(layout, w, e);
+    if (toDevice) state[j] = soa[i]; else soa[i] = state[j];
 }
 
 __global__ void k_raycast(TrackDev T, int n, const float* __restrict__ rays, float* __restrict__ out) {
@@ -187,10 +246,10 @@ __global__ void k_raycast(TrackDev T, int n, const float* __restrict__ rays, flo
     q[0] = (float)r.hit; q[1] = r.pos.x; q[2] = r.pos.y; q[3] = r.pos.z; q[4] = r.normal.x; q[5] = r.normal.y; q[6] = r.normal.z; q[7] = (float)r.surface;
 }
 
-__global__ void k_set_pressure(uint32_t* state, int n, int wheel, float value) {
+__global__ void k_set_pressure(uint32_t* state, int layout, int n, int wheel, float value) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    state[state_index(PD_OFF_TYRE(wheel) + PD_TYRE_o_pressureStatic, (size_t)e)] = f2u(value);
+    state[state_index(layout, PD_OFF_TYRE(wheel) + PD_TYRE_o_pressureStatic, (size_t)e)] = f2u(value);
 }
 
 /* ------------------------------------------------------------------ host side ------------------------------------------------------------------ */
@@ -231,6 +290,7 @@ struct pd_batch {
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     double time = 0, lastDt = 0;
     uint64_t seed = 0, idOffset = 0, launches = 0;
+    int layout = PD_LAYOUT_TILED;     /* PD_LAYOUT_RECORDS when the 4-lanes-per-car kernel owns the batch */
     int quadMax = PD_QUAD_MAX_ENVS;   /* kernel dispatch threshold; env PD_QUAD_MAX_ENVS overrides (tuning / profiling) */
     std::string err;
     int64_t dlShape[2] = {0, 0};
@@ -271,7 +331,8 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     b->n = n_envs; b->device = device;
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    CK(cudaFuncSetAttribute(k_tick_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * PD_GSCR_WORDS * 4));
+    CK(cudaFuncSetAttribute(k_tick_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES));
+    b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
     int rc;
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
     { const std::vector<pd::BvhNode>& dummy = *reinterpret_cast<const std::vector<pd::BvhNode>*>(&b->track.nodes); if ((rc = upload(b, &b->dev.nodes, dummy))) return rc; }
@@ -285,14 +346,16 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = upload(b, &b->dev.segItems, b->track.segItems))) return rc;
     if ((rc = upload(b, &b->dev.ptStart, b->track.ptStart))) return rc;
     if ((rc = upload(b, &b->dev.ptItems, b->track.ptItems))) return rc;
+    if ((rc = upload(b, &b->dev.segRec, b->track.segRec))) return rc;
+    if ((rc = upload(b, &b->dev.ptRec, b->track.ptRec))) return rc;
     b->dev.grid = b->track.grid;
     if ((rc = upload(b, &b->dev.colStart, b->track.colStart))) return rc;
     if ((rc = upload(b, &b->dev.colItems, b->track.colItems))) return rc;
     b->dev.colGrid = b->track.colGrid;
     b->dev.info = b->track.info;
     const size_t n = (size_t)n_envs;
-    const size_t nPad = (n + PD_TILE - 1) / PD_TILE * PD_TILE;
-    if ((rc = dalloc(b, &b->dState, nPad * PD_STATE_WORDS))) return rc;
+    const size_t nAlloc = state_alloc_words(b->layout, n);
+    if ((rc = dalloc(b, &b->dState, nAlloc))) return rc;
     if ((rc = dalloc(b, &b->dObs, n * PD_OBS_DIM))) return rc;
     if ((rc = dalloc(b, &b->dCtl, n * 5))) return rc;
     if ((rc = dalloc(b, &b->dGears, n * 3))) return rc;
@@ -315,21 +378,22 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     CK(cudaMemsetAsync(b->dObs, 0, n * PD_OBS_DIM * 4, b->stream));
     /* initial record: built once with the same device functions compiled for the host, then broadcast */
     std::vector<uint32_t> rec(PD_STATE_WORDS, 0);
-    { SV sv = sv_flat(rec.data()); car_init_state(b->car.P, sv); }
+    { SVFlat sv = sv_flat(rec.data()); car_init_state(b->car.P, sv); }
     uint32_t* dRec = nullptr; if ((rc = dalloc(b, &dRec, PD_STATE_WORDS))) return rc;
     CK(cudaMemcpyAsync(dRec, rec.data(), PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream));
-    k_broadcast<<<grid((int)std::min<size_t>(nPad * PD_STATE_WORDS, 0x7fffffff), 256), 256, 0, b->stream>>>(b->dState, (int)nPad, dRec); b->launches++;
+    k_broadcast<<<(unsigned)((nAlloc + 255) / 256), 256, 0, b->stream>>>(b->dState, b->layout, nAlloc, dRec); b->launches++;
     CK(cudaGetLastError());
     if ((rc = sync_params(b))) return rc;
     CK(cudaStreamSynchronize(b->stream));
     return PD_OK;
 }
 
-static void launch_tick(pd_batch* b, float dt, const int32_t* mask) {
-    if (b->n <= b->quadMax)
-        k_tick_quad<<<grid(b->n * 4, PD_QBLOCK), PD_QBLOCK, (size_t)PD_QBLOCK * PD_GSCR_WORDS * 4, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask);
+static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO& io) {
+    if (b->layout == PD_LAYOUT_RECORDS)
+        k_tick_quad<<<grid(b->n, PD_QCARS), PD_QBLOCK, PD_QUAD_SMEM_BYTES, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     else
-        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask);
+        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+    b->launches++;
 }
 
 extern "C" {
@@ -382,7 +446,7 @@ int pd_set_tune(pd_batch* b, const char* name, float value) {
     b->car.setTune(name, value); b->paramsDirty = true;
     static const char* kP[4] = {"PRESSURE_LF", "PRESSURE_RF", "PRESSURE_LR", "PRESSURE_RR"};
     for (int w = 0; w < 4; ++w) if (!strcmp(name, kP[w])) {   /* the tune writes Tyre::status.pressureStatic of every car */
-        k_set_pressure<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, w, b->car.P.tyre[w].pressureStaticDefault); b->launches++;
+        k_set_pressure<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, w, b->car.P.tyre[w].pressureStaticDefault); b->launches++;
         CK(cudaGetLastError());
     }
     return PD_OK;
@@ -401,14 +465,14 @@ int pd_set_controls(pd_batch* b, const float* controls, const int8_t* gears, int
         CK(cudaMemcpyAsync(b->dCtl, controls, (size_t)b->n * 5 * 4, cudaMemcpyHostToDevice, b->stream)); c = b->dCtl;
         if (gears) { CK(cudaMemcpyAsync(b->dGears, gears, (size_t)b->n * 3, cudaMemcpyHostToDevice, b->stream)); g = b->dGears; }
     }
-    k_set_controls<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, c, g, smooth); b->launches++;
+    k_set_controls<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, c, g, smooth); b->launches++;
     CK(cudaGetLastError()); return PD_OK;
 }
 int pd_set_actions(pd_batch* b, const float* actions, int on_device) {
     if (!b || !actions) return PD_ERR_ARG;
     const float* a = actions;
     if (!on_device) { CK(cudaMemcpyAsync(b->dAct, actions, (size_t)b->n * 2 * 4, cudaMemcpyHostToDevice, b->stream)); a = b->dAct; }
-    k_set_actions<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, a, nullptr); b->launches++;
+    k_set_actions<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, a); b->launches++;
     CK(cudaGetLastError()); return PD_OK;
 }
 
@@ -416,7 +480,7 @@ int pd_step(pd_batch* b, float dt, int n_ticks) {
     if (!b || n_ticks < 0) return PD_ERR_ARG;
     int rc = sync_params(b); if (rc) return rc;
     for (int t = 0; t < n_ticks; ++t) {
-        launch_tick(b, dt, nullptr); b->launches++;
+        launch_tick(b, dt, nullptr, EnvIO{});
         b->time += (double)dt; b->lastDt = dt;
     }
     CK(cudaGetLastError()); return PD_OK;
@@ -434,8 +498,7 @@ static int teleport_common(pd_batch* b, const uint8_t* mask, int mode, const flo
     }
     const float* dd = nullptr;
     if (dist_norm) { CK(cudaMemcpyAsync(b->dDist, dist_norm, (size_t)b->n * 4, cudaMemcpyHostToDevice, b->stream)); dd = b->dDist; }
-    k_pick_points<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dev, b->dState, b->n, dm, mode, dd, b->seed, b->idOffset, b->dEpisodeCtr, b->dPoints); b->launches++;
-    k_teleport<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->n, dm, b->dPoints, b->time); b->launches++;
+    k_teleport<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, b->n, dm, mode, dd, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 0); b->launches++;
     CK(cudaGetLastError()); return PD_OK;
 }
 int pd_teleport_spline(pd_batch* b, const uint8_t* mask, const float* dist_norm) {
@@ -450,7 +513,7 @@ int pd_teleport_mode(pd_batch* b, const uint8_t* mask, int mode) {
 
 int pd_observe(pd_batch* b) {
     if (!b) return PD_ERR_ARG;
-    k_observe<<<grid(b->n, 128), 128, 0, b->stream>>>(b->dState, b->n, b->dObs); b->launches++;
+    k_observe<<<grid(b->n, 128), 128, 0, b->stream>>>(b->dState, b->layout, b->n, b->dObs); b->launches++;
     CK(cudaGetLastError()); return PD_OK;
 }
 const float* pd_obs_device_ptr(pd_batch* b) { return b ? b->dObs : nullptr; }
@@ -474,7 +537,7 @@ void* pd_obs_dlpack(pd_batch* b) {
 }
 int pd_get_rewards(pd_batch* b, float* step_reward, float* total_reward, int32_t* flags) {
     if (!b) return PD_ERR_ARG;
-    k_rewards<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->n, b->dReward, b->dTotal, b->dFlags); b->launches++;
+    k_rewards<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, b->dReward, b->dTotal, b->dFlags); b->launches++;
     CK(cudaGetLastError());
     if (step_reward) CK(cudaMemcpyAsync(step_reward, b->dReward, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
     if (total_reward) CK(cudaMemcpyAsync(total_reward, b->dTotal, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -487,19 +550,27 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     int rc = sync_params(b); if (rc) return rc;
     const int n = b->n;
     float* rew = reward_dev ? reward_dev : b->dReward; int32_t* done = done_dev ? done_dev : b->dDone;
-    k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, nullptr);
-    launch_tick(b, dt, nullptr);
-    k_env_done<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, b->time, rew, done, b->dEnvReturn, b->dEnvLen, b->dStats);
+    /* 1: actions -> controls, one tick, observation, reward / done / statistics -- one launch */
+    EnvIO io{}; io.act = actions_dev; io.obs = obs_dev ? obs_dev : b->dObs;
+    io.reward = rew; io.done = done; io.envReturn = b->dEnvReturn; io.envLen = b->dEnvLen; io.stats = b->dStats; io.timeAfter = b->time;
+    launch_tick(b, dt, nullptr, io);
     b->time += (double)dt; b->lastDt = dt;
-    /* auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) + one zero-action tick */
-    k_pick_points<<<grid(n, 256), 256, 0, b->stream>>>(b->dev, b->dState, n, done, b->car.P.teleportMode, nullptr, b->seed, b->idOffset, b->dEpisodeCtr, b->dPoints);
-    k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, n, done, b->dPoints, b->time);
-    k_clear_nan<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, done);
-    k_set_actions<<<grid(n, 256), 256, 0, b->stream>>>(b->dState, n, actions_dev, done);
-    launch_tick(b, dt, done);
-    k_observe<<<grid(n, 128), 128, 0, b->stream>>>(b->dState, n, obs_dev ? obs_dev : b->dObs);
-    b->launches += 9;
+    /* 2 + 3: auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) with the reset's zero action,
+       then one tick of those envs only, refreshing their observation */
+    k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, n, done, b->car.P.teleportMode, nullptr, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 1); b->launches++;
+    EnvIO io2{}; io2.obs = io.obs;
+    launch_tick(b, dt, done, io2);
     CK(cudaGetLastError()); return PD_OK;
+}
+int pd_env_step_host(pd_batch* b, const float* actions_host, float dt, float* obs_host, float* reward_host, int32_t* done_host) {
+    if (!b || !actions_host) return PD_ERR_ARG;
+    const size_t n = (size_t)b->n;
+    CK(cudaMemcpyAsync(b->dAct, actions_host, n * 2 * 4, cudaMemcpyHostToDevice, b->stream));
+    int rc = pd_env_step(b, b->dAct, dt, b->dObs, b->dReward, b->dDone); if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, b->dObs, n * PD_OBS_DIM * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, b->dReward, n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (done_host) CK(cudaMemcpyAsync(done_host, b->dDone, n * 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream)); return PD_OK;
 }
 int pd_env_stats(pd_batch* b, double* out8, int reset) {
     if (!b || !out8) return PD_ERR_ARG;
@@ -510,30 +581,34 @@ int pd_env_stats(pd_batch* b, double* out8, int reset) {
 
 int pd_get_state(pd_batch* b, int env, uint32_t* record) {
     if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
-    CK(cudaMemcpy2DAsync(record, 4, b->dState + state_index(0, (size_t)env), (size_t)PD_TILE * 4, 4, PD_STATE_WORDS, cudaMemcpyDeviceToHost, b->stream));
+    if (b->layout == PD_LAYOUT_RECORDS) CK(cudaMemcpyAsync(record, b->dState + (size_t)env * PD_STATE_STRIDE, PD_STATE_WORDS * 4, cudaMemcpyDeviceToHost, b->stream));
+    else CK(cudaMemcpy2DAsync(record, 4, b->dState + state_index_tiled(0, (size_t)env), (size_t)PD_TILE * 4, 4, PD_STATE_WORDS, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream)); return PD_OK;
 }
 int pd_set_state(pd_batch* b, int env, const uint32_t* record) {
     if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
-    CK(cudaMemcpy2DAsync(b->dState + state_index(0, (size_t)env), (size_t)PD_TILE * 4, record, 4, 4, PD_STATE_WORDS, cudaMemcpyHostToDevice, b->stream));
+    if (b->layout == PD_LAYOUT_RECORDS) CK(cudaMemcpyAsync(b->dState + (size_t)env * PD_STATE_STRIDE, record, PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream));
+    else CK(cudaMemcpy2DAsync(b->dState + state_index_tiled(0, (size_t)env), (size_t)PD_TILE * 4, record, 4, 4, PD_STATE_WORDS, cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream)); return PD_OK;
 }
-int pd_snapshot(pd_batch* b, uint32_t* host_buf) {
-    if (!b || !host_buf) return PD_ERR_ARG;
-    const size_t nPad = ((size_t)b->n + PD_TILE - 1) / PD_TILE * PD_TILE;
-    std::vector<uint32_t> tmp(nPad * PD_STATE_WORDS);
-    CK(cudaMemcpyAsync(tmp.data(), b->dState, tmp.size() * 4, cudaMemcpyDeviceToHost, b->stream)); CK(cudaStreamSynchronize(b->stream));
-    for (int w = 0; w < PD_STATE_WORDS; ++w) for (size_t e = 0; e < (size_t)b->n; ++e) host_buf[(size_t)w * b->n + e] = tmp[state_index(w, e)];
-    return PD_OK;
+static int pack_common(pd_batch* b, uint32_t* host_buf, int toDevice) {
+    const size_t words = (size_t)b->n * PD_STATE_WORDS;
+    uint32_t* tmp = nullptr;
+    cudaError_t e = cudaMalloc(&tmp, words * 4);
+    if (e != cudaSuccess) { b->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return PD_ERR_CUDA; }
+    int rc = PD_OK;
+    do {
+        if (toDevice && cudaMemcpyAsync(tmp, host_buf, words * 4, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) { rc = PD_ERR_CUDA; break; }
+        k_pack<<<(unsigned)((words + 255) / 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, tmp, toDevice); b->launches++;
+        if (!toDevice && cudaMemcpyAsync(host_buf, tmp, words * 4, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) { rc = PD_ERR_CUDA; break; }
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = PD_ERR_CUDA;
+    } while (0);
+    if (rc) b->err = std::string("snapshot/restore: ") + cudaGetErrorString(cudaGetLastError());
+    cudaFree(tmp);
+    return rc;
 }
-int pd_restore(pd_batch* b, const uint32_t* host_buf) {
-    if (!b || !host_buf) return PD_ERR_ARG;
-    const size_t nPad = ((size_t)b->n + PD_TILE - 1) / PD_TILE * PD_TILE;
-    std::vector<uint32_t> tmp(nPad * PD_STATE_WORDS);
-    CK(cudaMemcpyAsync(tmp.data(), b->dState, tmp.size() * 4, cudaMemcpyDeviceToHost, b->stream)); CK(cudaStreamSynchronize(b->stream));   /* keeps the padding envs */
-    for (int w = 0; w < PD_STATE_WORDS; ++w) for (size_t e = 0; e < (size_t)b->n; ++e) tmp[state_index(w, e)] = host_buf[(size_t)w * b->n + e];
-    CK(cudaMemcpyAsync(b->dState, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, b->stream)); CK(cudaStreamSynchronize(b->stream)); return PD_OK;
-}
+int pd_snapshot(pd_batch* b, uint32_t* host_buf) { if (!b || !host_buf) return PD_ERR_ARG; return pack_common(b, host_buf, 0); }
+int pd_restore(pd_batch* b, const uint32_t* host_buf) { if (!b || !host_buf) return PD_ERR_ARG; return pack_common(b, const_cast<uint32_t*>(host_buf), 1); }
 int pd_get_params(const pd_batch* b, PdCarParams* out) { if (!b || !out) return PD_ERR_ARG; *out = b->car.P; return PD_OK; }
 int pd_get_track_info(const pd_batch* b, PdTrackInfo* out) { if (!b || !out) return PD_ERR_ARG; *out = b->track.info; return PD_OK; }
 
@@ -541,7 +616,7 @@ int pd_get_car_state(pd_batch* b, int env, void* outv) {
     if (!b || !outv) return PD_ERR_ARG;
     std::vector<uint32_t> rec(PD_STATE_WORDS);
     int rc = pd_get_state(b, env, rec.data()); if (rc) return rc;
-    SV sv = sv_flat(rec.data());
+    SVFlat sv = sv_flat(rec.data());
     PdCarStateOut s; memset(&s, 0, sizeof(s));
     CarS c; load_car(sv, c);
     Body C; load_body(sv, PD_BODY_CHASSIS, C);

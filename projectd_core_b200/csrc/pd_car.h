@@ -304,7 +304,7 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, flo
  * updateLockedState/updateAngularSpeed (Tyre.cpp:725-752), stepThermalModel (:766-815), stepGrainBlister
  * (:829-922, consumption rate 0 branch), stepFlatSpot (:924-950).
  * `hubBody` is the body the wheel's forces go to (strut hub or the rigid axle). */
-PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, const CarCtx& X, const SV& sv, Body& hubBody, const Frame& hubFrame, Body& C, float brakeTorqueIn, float handBrakeIn, WheelLink& L) {
+template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, const CarCtx& X, const SVX& sv, Body& hubBody, const Frame& hubFrame, Body& C, float brakeTorqueIn, float handBrakeIn, WheelLink& L) {
     const PdTyre& P = PP.tyre[w];
     const float dt = X.dt;
     TyreS t; load_tyre(sv, w, t);

@@ -37,8 +37,8 @@ PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
     }
 }
 
-template <int STRIDE, class Ex>
-PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SV& sv, float dt, double physicsTime, Ex& ex, float* scratch) {
+template <int STRIDE, class Ex, class SVX>
+PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch) {
     const int lane = ex.lane;
     const bool front = lane < 2;
     CarCtx X; X.dt = dt; X.time = physicsTime;

@@ -222,10 +222,11 @@ PD_HD void jinvm6(const float* J, const BodyDyn& d, float* o) {
 /* factor one group: D = JA MA^-1 JA^T + JB MB^-1 JB^T + cfm/h ; L D L^T in place ; Y <- L^-1 [U | r];
  * accumulates the chassis Schur complement S (6x6 lower, packed 21) and right-hand side b6.
  * Row loops are kept ROLLED (compact code: the kernel is instruction-fetch sensitive), the 6- and 7-wide inner
- * loops are unrolled; every lane runs all PD_GMAX rows (padding rows are identity), so there is no divergence. */
-template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6) {
+ * loops are unrolled.  n = rows to process: the 4-lanes-per-car kernel runs all PD_GMAX rows on every lane (padding
+ * rows are identity, so there is no divergence); the thread-per-car kernel passes the group's real row count. */
+template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6, const int n = PD_GMAX) {
     PD_NOUNROLL
-    for (int i = 0; i < PD_GMAX; ++i) {
+    for (int i = 0; i < n; ++i) {
         float ra[6], rb[6], ja[6], jb[6];
         PD_UNROLL
         for (int k = 0; k < 6; ++k) { ra[k] = G.JA(i, k); rb[k] = G.JB(i, k); }
@@ -246,7 +247,7 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
     }
     /* L D L^T, row by row (same recurrence as the oracle's dense factorisation), in place */
     PD_NOUNROLL
-    for (int i = 0; i < PD_GMAX; ++i) {
+    for (int i = 0; i < n; ++i) {
         PD_NOUNROLL
         for (int j = 0; j < i; ++j) {
             float s = G.D(i, j);
@@ -261,7 +262,7 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
     }
     /* forward substitution on the 7 right-hand sides */
     PD_NOUNROLL
-    for (int i = 0; i < PD_GMAX; ++i) {
+    for (int i = 0; i < n; ++i) {
         float y[7];
         PD_UNROLL
         for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
@@ -282,20 +283,20 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
 }
 
 /* lambda_g = L^-T D^-1 (yr - Yu z);  cforce on own bodies = J^T lambda */
-template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, float* cfA, float* cfB) {
+template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, float* cfA, float* cfB, const int n = PD_GMAX) {
     PD_NOUNROLL
-    for (int i = 0; i < PD_GMAX; ++i) {
+    for (int i = 0; i < n; ++i) {
         float s = G.Y(i, 6);
         PD_UNROLL
         for (int k = 0; k < 6; ++k) s -= G.Y(i, k) * z[k];
         G.Y(i, 6) = s / G.dg(i);
     }
     PD_NOUNROLL
-    for (int i = PD_GMAX - 1; i >= 0; --i) { float s = G.Y(i, 6); PD_NOUNROLL for (int k = i + 1; k < PD_GMAX; ++k) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
+    for (int i = n - 1; i >= 0; --i) { float s = G.Y(i, 6); PD_NOUNROLL for (int k = i + 1; k < n; ++k) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
     PD_UNROLL
     for (int k = 0; k < 6; ++k) { cfA[k] = 0; cfB[k] = 0; }
     PD_NOUNROLL
-    for (int i = 0; i < PD_GMAX; ++i) {
+    for (int i = 0; i < n; ++i) {
         const float lam = G.Y(i, 6);
         PD_UNROLL
         for (int k = 0; k < 6; ++k) { cfA[k] += G.JA(i, k) * lam; cfB[k] += G.JB(i, k) * lam; }
@@ -305,16 +306,16 @@ template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, flo
 /* Serial variant of the back-substitution: fold the group into an affine map of the chassis unknown z,
  *     cforce_A = pA - QA z ,  cforce_B = pB - QB z      (W = L^-T D^-1 [Yu | yr];  p = J^T W[:,6],  Q = J^T W[:,0:6])
  * so that the group's scratch can be reused by the next group before z is known. */
-template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, float* pB, float* QB) {
+template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, float* pB, float* QB, const int n = PD_GMAX) {
     PD_NOUNROLL
-    for (int i = 0; i < PD_GMAX; ++i) { const float di = 1.0f / G.dg(i); PD_UNROLL for (int k = 0; k < 7; ++k) G.Y(i, k) *= di; }
+    for (int i = 0; i < n; ++i) { const float di = 1.0f / G.dg(i); PD_UNROLL for (int k = 0; k < 7; ++k) G.Y(i, k) *= di; }
     PD_NOUNROLL
-    for (int i = PD_GMAX - 1; i >= 0; --i) {
+    for (int i = n - 1; i >= 0; --i) {
         float y[7];
         PD_UNROLL
         for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
         PD_NOUNROLL
-        for (int r = i + 1; r < PD_GMAX; ++r) { const float l = G.D(r, i); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(r, k); }
+        for (int r = i + 1; r < n; ++r) { const float l = G.D(r, i); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(r, k); }
         PD_UNROLL
         for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
     }
@@ -322,13 +323,13 @@ template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, fl
     for (int a = 0; a < 6; ++a) {
         float sa = 0, sb = 0;
         PD_NOUNROLL
-        for (int i = 0; i < PD_GMAX; ++i) { sa += G.JA(i, a) * G.Y(i, 6); sb += G.JB(i, a) * G.Y(i, 6); }
+        for (int i = 0; i < n; ++i) { sa += G.JA(i, a) * G.Y(i, 6); sb += G.JB(i, a) * G.Y(i, 6); }
         pA[a] = sa; pB[a] = sb;
         PD_UNROLL
         for (int k = 0; k < 6; ++k) {
             float qa = 0, qb = 0;
             PD_NOUNROLL
-            for (int i = 0; i < PD_GMAX; ++i) { qa += G.JA(i, a) * G.Y(i, k); qb += G.JB(i, a) * G.Y(i, k); }
+            for (int i = 0; i < n; ++i) { qa += G.JA(i, a) * G.Y(i, k); qb += G.JB(i, a) * G.Y(i, k); }
             QA[a * 6 + k] = qa; QB[a * 6 + k] = qb;
         }
     }
@@ -436,16 +437,16 @@ PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, co
     float pv[6][6], Qv[6][36], pdump[6], Qdump[36];
     const Body& C = b[PD_BODY_CHASSIS];
     build_tank(P, b[PD_BODY_TANK], C, hinv, G);
-    factor_group(G, dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
-    fold_group(G, pv[0], Qv[0], pdump, Qdump);
+    factor_group(G, dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6, 6);
+    fold_group(G, pv[0], Qv[0], pdump, Qdump, 6);
     for (int s = 0; s < 2; ++s) {
         build_strut(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], hinv, dballErp, dballCfm, G);
         factor_group(G, dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
         fold_group(G, pv[1 + 2 * s], Qv[1 + 2 * s], pv[2 + 2 * s], Qv[2 + 2 * s]);
     }
     build_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, G);
-    factor_group(G, dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
-    fold_group(G, pv[5], Qv[5], pdump, Qdump);
+    factor_group(G, dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6, 5);
+    fold_group(G, pv[5], Qv[5], pdump, Qdump, 5);
     schur_add_chassis(S21, C);
     float z[6];
     solve6(S21, b6, z);

@@ -1,9 +1,5 @@
 /*
- * pd_state_io.h -- structure-of-arrays access to the per-car state record (include/pd_state.h).
- *
- * Device layout: word w of env e is state[w * n_envs + e].  Consecutive threads (one car each) touch
- * consecutive 4-byte words of the same row -> every state load / store of a warp is one coalesced
- * 128-byte transaction.  Doubles are kept as two 32-bit rows (lo, hi) so that rows stay 4-byte wide.
+ * pd_state_io.h -- access to the per-car state record (include/pd_state.h) in its device layouts.
  */
 #pragma once
 #include "pd_math.h"
@@ -42,24 +38,35 @@ PD_HD void d2u(double d, uint32_t& lo, uint32_t& hi) {
 #endif
 }
 
-/* View of one env inside the state buffer.
- * Device layout ("tiled SoA"): envs are grouped in tiles of 32; word w of env e lives at
- *     state[((e / 32) * PD_STATE_WORDS + w) * 32 + (e % 32)].
- * A warp's accesses to one word of 32 consecutive envs are one 128-byte line, and -- because the word index
- * is a compile-time constant almost everywhere -- every access is a load/store with an IMMEDIATE offset from
- * one per-thread base pointer (no index arithmetic).  Host-side single records (snapshots, the oracle
- * harness, tests/hostsim) are flat arrays: stride 1. */
+/* Views of one env inside the state buffer.  Two device layouts exist (chosen per batch at creation):
+ *
+ *  RECORDS ("array of records", 4-lanes-per-car kernel): env e is the contiguous record
+ *      state[e * PD_STATE_STRIDE .. + PD_STATE_WORDS).  A block moves its 16 records between HBM and shared
+ *      memory with ONE bulk async copy each way and works on the shared-memory copy (view stride 1).
+ *  TILED  ("tiled structure of arrays", thread-per-car kernel): envs are grouped in tiles of 32; word w of
+ *      env e lives at state[((e / 32) * PD_STATE_WORDS + w) * 32 + (e % 32)].  A warp's accesses to one word
+ *      of 32 consecutive envs are one 128-byte line and, the word index being a compile-time constant almost
+ *      everywhere, every access is a load/store with an IMMEDIATE offset from one per-thread base pointer.
+ *
+ *  SVT<STRIDE>: view with a compile-time word stride (SVT<1> = one flat record, SVT<PD_TILE> = tiled);
+ *  SVR: view with a run-time stride, for the small kernels that serve both layouts. */
 #define PD_TILE 32
-struct SV {
+enum { PD_LAYOUT_TILED = 0, PD_LAYOUT_RECORDS = 1 };
+template <int STRIDE> struct SVT {
     uint32_t* s;        /* &state[word 0 of this env] */
     bool live;          /* false: a padding lane that computes along but must not write */
-#if defined(__CUDA_ARCH__)
-    static constexpr int stride = PD_TILE;
-    PD_HD SV(uint32_t* base, int /*stride*/, bool lv = true) : s(base), live(lv) {}
-#else
-    int stride;
-    PD_HD SV(uint32_t* base, int st, bool lv = true) : s(base), live(lv), stride(st) {}
-#endif
+    static constexpr int stride = STRIDE;
+    PD_HD SVT(uint32_t* base, bool lv = true) : s(base), live(lv) {}
+    PD_HD float f(int w) const { return u2f(s[w * STRIDE]); }
+    PD_HD int i(int w) const { return (int)s[w * STRIDE]; }
+    PD_HD double d(int w) const { return u2d(s[w * STRIDE], s[(w + 1) * STRIDE]); }
+    PD_HD void f(int w, float v) const { if (live) s[w * STRIDE] = f2u(v); }
+    PD_HD void i(int w, int v) const { if (live) s[w * STRIDE] = (uint32_t)v; }
+    PD_HD void d(int w, double v) const { if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[w * STRIDE] = lo; s[(w + 1) * STRIDE] = hi; }
+};
+struct SVR {
+    uint32_t* s; bool live; int stride;
+    PD_HD SVR(uint32_t* base, int st, bool lv = true) : s(base), live(lv), stride(st) {}
     PD_HD float f(int w) const { return u2f(s[w * stride]); }
     PD_HD int i(int w) const { return (int)s[w * stride]; }
     PD_HD double d(int w) const { return u2d(s[w * stride], s[(w + 1) * stride]); }
@@ -67,9 +74,14 @@ struct SV {
     PD_HD void i(int w, int v) const { if (live) s[w * stride] = (uint32_t)v; }
     PD_HD void d(int w, double v) const { if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[w * stride] = lo; s[(w + 1) * stride] = hi; }
 };
-PD_HD size_t state_index(int w, size_t e) { return ((e / PD_TILE) * PD_STATE_WORDS + (size_t)w) * PD_TILE + (e % PD_TILE); }
-PD_HD SV sv_tiled(uint32_t* state, size_t e) { return SV(state + state_index(0, e), PD_TILE); }
-PD_HD SV sv_flat(uint32_t* rec) { return SV(rec, 1); }
+typedef SVT<PD_TILE> SVTile;
+typedef SVT<1> SVFlat;
+PD_HD size_t state_index_tiled(int w, size_t e) { return ((e / PD_TILE) * PD_STATE_WORDS + (size_t)w) * PD_TILE + (e % PD_TILE); }
+PD_HD size_t state_index(int layout, int w, size_t e) { return layout == PD_LAYOUT_RECORDS ? e * PD_STATE_STRIDE + (size_t)w : state_index_tiled(w, e); }
+PD_HD size_t state_alloc_words(int layout, size_t n) { return layout == PD_LAYOUT_RECORDS ? n * PD_STATE_STRIDE : ((n + PD_TILE - 1) / PD_TILE * PD_TILE) * PD_STATE_WORDS; }
+PD_HD SVTile sv_tiled(uint32_t* state, size_t e) { return SVTile(state + state_index_tiled(0, e)); }
+PD_HD SVFlat sv_flat(uint32_t* rec) { return SVFlat(rec); }
+PD_HD SVR sv_env(int layout, uint32_t* state, size_t e) { return layout == PD_LAYOUT_RECORDS ? SVR(state + e * PD_STATE_STRIDE, 1) : SVR(state + state_index_tiled(0, e), PD_TILE); }
 
 /* ---- typed mirrors of the X-macro lists ---- */
 #define PD__DECL_F(name) float name;
@@ -98,25 +110,25 @@ struct CarS {
 #define PD__LDC(kind, name) PD__LD_##kind(PD_CAR_o_, name)
 #define PD__STC(kind, name) PD__ST_##kind(PD_CAR_o_, name)
 
-PD_HD void load_tyre(const SV& sv, int w, TyreS& t) {
+template <class SVX> PD_HD void load_tyre(const SVX& sv, int w, TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__LDT)
     PD_UNROLL4
     for (int p = 0; p < PD_THERMAL_PATCHES; ++p) t.T[p] = sv.f(PD_OFF_TYRE_PATCH(w) + p);
 }
-PD_HD void store_tyre(const SV& sv, int w, const TyreS& t) {
+template <class SVX> PD_HD void store_tyre(const SVX& sv, int w, const TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__STT)
     PD_UNROLL4
     for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, t.T[p]);
 }
-PD_HD void load_car(const SV& sv, CarS& t) {
+template <class SVX> PD_HD void load_car(const SVX& sv, CarS& t) {
     const int o = PD_OFF_CAR;
     PD_CAR_FIELDS(PD__LDC)
     for (int p = 0; p < PD_MAX_PROBES; ++p) t.probes[p] = sv.f(PD_OFF_PROBES + p);
     for (int p = 0; p < PD_LOOKAHEAD; ++p) t.lookAhead[p] = sv.f(PD_OFF_LOOKAHEAD + p);
 }
-PD_HD void store_car(const SV& sv, const CarS& t) {
+template <class SVX> PD_HD void store_car(const SVX& sv, const CarS& t) {
     const int o = PD_OFF_CAR;
     PD_CAR_FIELDS(PD__STC)
     for (int p = 0; p < PD_MAX_PROBES; ++p) sv.f(PD_OFF_PROBES + p, t.probes[p]);
@@ -132,7 +144,7 @@ struct Body {
     float mass;
     V3 I;          /* diagonal body-frame inertia */
 };
-PD_HD void load_body(const SV& sv, int b, Body& B) {
+template <class SVX> PD_HD void load_body(const SVX& sv, int b, Body& B) {
     const int o = PD_OFF_BODY(b);
     B.fr.p = v3(sv.f(o + PD_BODY_o_px), sv.f(o + PD_BODY_o_py), sv.f(o + PD_BODY_o_pz));
     B.q.w = sv.f(o + PD_BODY_o_qw); B.q.x = sv.f(o + PD_BODY_o_qx); B.q.y = sv.f(o + PD_BODY_o_qy); B.q.z = sv.f(o + PD_BODY_o_qz);
@@ -143,7 +155,7 @@ PD_HD void load_body(const SV& sv, int b, Body& B) {
     B.w = v3(sv.f(o + PD_BODY_o_wx), sv.f(o + PD_BODY_o_wy), sv.f(o + PD_BODY_o_wz));
     B.F = v3(0, 0, 0); B.T = v3(0, 0, 0);
 }
-PD_HD void store_body(const SV& sv, int b, const Body& B) {
+template <class SVX> PD_HD void store_body(const SVX& sv, int b, const Body& B) {
     const int o = PD_OFF_BODY(b);
     sv.f(o + PD_BODY_o_px, B.fr.p.x); sv.f(o + PD_BODY_o_py, B.fr.p.y); sv.f(o + PD_BODY_o_pz, B.fr.p.z);
     sv.f(o + PD_BODY_o_qw, B.q.w); sv.f(o + PD_BODY_o_qx, B.q.x); sv.f(o + PD_BODY_o_qy, B.q.y); sv.f(o + PD_BODY_o_qz, B.q.z);

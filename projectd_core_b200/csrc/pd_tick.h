@@ -29,7 +29,7 @@ PD_HD float beta_rad(const Body& C) {
 
 /* state of a freshly constructed car (Car::init, Car.cpp:31-223, and the constructors it runs): chassis at the
  * origin with identity rotation, suspension bodies attached, everything else at its default */
-PD_HDN void car_init_state(const PdCarParams& P, const SV& sv) {
+template <class SVX> PD_HDN void car_init_state(const PdCarParams& P, const SVX& sv) {
     for (int w = 0; w < PD_STATE_WORDS; ++w) sv.i(w, 0);
     Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
     for (int i = 0; i < PD_NUM_BODIES; ++i) {
@@ -73,7 +73,7 @@ PD_HDN void car_init_state(const PdCarParams& P, const SV& sv) {
 }
 
 /* teleport: Car::teleportToSpline -> forceRotation + forcePosition (Car.cpp:1325-1340,1275-1308,1240-1273) */
-PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const SV& sv, int pointId, double physicsTime) {
+template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const SVX& sv, int pointId, double physicsTime) {
     Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
     for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
     CarS c; load_car(sv, c);
@@ -236,7 +236,7 @@ PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, 
 }
 
 /* the tick */
-PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, float dt, double physicsTime) {
+template <class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime) {
     CarCtx X; X.dt = dt; X.time = physicsTime;
     Body bod[PD_NUM_BODIES]; V3 steerAnchor1[2], steerAnchor2[2];
     set_body_mass(bod, P);
@@ -424,7 +424,7 @@ PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SV& sv, floa
 }
 
 /* observation vector of pyprojectd/projectd_env.py:237-275 */
-PD_HD void car_observe(const SV& sv, float* obs /* 24, stride 1 */) {
+template <class SVX> PD_HD void car_observe(const SVX& sv, float* obs /* 24, stride 1 */) {
     Body C; load_body(sv, PD_BODY_CHASSIS, C);
     const V3 lv = irot(C.fr, C.v), lw = irot(C.fr, C.w);
     obs[0] = lv.x; obs[1] = lv.y; obs[2] = lv.z; obs[3] = lw.x; obs[4] = lw.y; obs[5] = lw.z;
@@ -432,6 +432,28 @@ PD_HD void car_observe(const SV& sv, float* obs /* 24, stride 1 */) {
     obs[10] = sv.f(PD_OFF_CAR + PD_CAR_o_bodyVsTrack); obs[11] = sv.f(PD_OFF_CAR + PD_CAR_o_velocityVsTrack);
     for (int i = 0; i < 5; ++i) obs[12 + i] = sv.f(PD_OFF_LOOKAHEAD + i);
     for (int i = 0; i < 7; ++i) obs[17 + i] = sv.f(PD_OFF_PROBES + i);
+}
+
+/* the env's action mapping (pyprojectd/projectd_env.py:158-170): steer = a0, gas = linscale(a1, -1..1 -> 0.1..1) */
+template <class SVX> PD_HD void env_apply_action(const SVX& sv, float a0, float a1) {
+    const int o = PD_OFF_CAR;
+    sv.f(o + PD_CAR_o_ctlSteer, a0); sv.f(o + PD_CAR_o_ctlClutch, 0.0f); sv.f(o + PD_CAR_o_ctlBrake, 0.0f); sv.f(o + PD_CAR_o_ctlHandBrake, 0.0f);
+    sv.f(o + PD_CAR_o_ctlGas, linscalef(a1, -1.0f, 1.0f, 0.1f, 1.0f));
+    sv.i(o + PD_CAR_o_ctlRequestedGear, -1); sv.i(o + PD_CAR_o_ctlGearUp, 0); sv.i(o + PD_CAR_o_ctlGearDn, 0); sv.i(o + PD_CAR_o_smoothSteer, 1);
+}
+
+/* ProjectDEnv.step tail (projectd_env.py:178-212): reward with the termination penalties and the PD_DONE_* causes
+ * that depend on the car alone (the low-reward cut needs the env's running return and is applied by the caller) */
+template <class SVX> PD_HD void env_reward_done(const SVX& sv, double timeAfter, float& reward, int& done) {
+    const int o = PD_OFF_CAR;
+    float r = sv.f(o + PD_CAR_o_stepReward);
+    int d = 0;
+    if (sv.i(o + PD_CAR_o_collisionFlag)) { r -= 50.0f; d |= 1 /* PD_DONE_COLLISION */; }
+    if (sv.i(o + PD_CAR_o_outOfTrackFlag)) { r -= 50.0f; d |= 2 /* PD_DONE_OFFTRACK */; }
+    /* the env compares lastTrackPointTimestamp + stuck_timeout (5 s) against the state's timestamp */
+    if (sv.f(o + PD_CAR_o_lastTrackPointTimestamp) + 5.0f < (float)timeAfter) { r -= 50.0f; d |= 4 /* PD_DONE_STUCK */; }
+    if (sv.i(o + PD_CAR_o_nanFlag)) d |= 16 /* PD_DONE_NAN */;
+    reward = r; done = d;
 }
 
 } // namespace pd

@@ -26,9 +26,26 @@ struct BvhNode {          /* 32 bytes */
     float bmax[3]; int32_t count;   /* 0 = inner node, > 0 = number of triangles in the leaf */
 };
 
+#ifndef PD_TRI_STRIDE
+#define PD_TRI_STRIDE 12
+#endif
+struct Tri12 { V3 v0, e1, e2; int surf; };
+PD_HD Tri12 load_tri(const float* tris, int t) {
+    Tri12 r;
+#if defined(__CUDA_ARCH__)
+    const float4* q = reinterpret_cast<const float4*>(tris) + 3 * (size_t)t;
+    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    r.v0 = v3(a.x, a.y, a.z); r.e1 = v3(a.w, b.x, b.y); r.e2 = v3(b.z, b.w, c.x); r.surf = __float_as_int(c.y);
+#else
+    const float* p = tris + (size_t)t * PD_TRI_STRIDE;
+    r.v0 = v3(p[0], p[1], p[2]); r.e1 = v3(p[3], p[4], p[5]); r.e2 = v3(p[6], p[7], p[8]); memcpy(&r.surf, &p[9], 4);
+#endif
+    return r;
+}
+
 struct TrackDev {
     const BvhNode* nodes;
-    const float* tris;        /* 9 floats per triangle: v0, e1, e2 (leaf order) */
+    const float* tris;        /* PD_TRI_STRIDE floats (48 B) per triangle, leaf order: v0, e1, e2, surface id bits, 0, 0 */
     const int32_t* triSurf;   /* surface (blob) index per triangle */
     const PdSurface* surfaces;
     const PdFatPoint* fat;
@@ -36,6 +53,8 @@ struct TrackDev {
     const float* splineDist;  /* cumulative length at node */
     const int32_t* segStart; const int32_t* segItems;   /* PdBoundGrid CSR: boundary segments per cell */
     const int32_t* ptStart; const int32_t* ptItems;     /* PdBoundGrid CSR: spline points per cell */
+    const float* segRec;      /* per segItems entry, 32 B: ax, az, bx, bz, owner's best.xyz, 0 */
+    const float* ptRec;       /* per ptItems entry, 16 B: best.xyz, id bits */
     PdBoundGrid grid;
     const int32_t* colStart; const int32_t* colItems;   /* vertical-ray index: triangles per x-z cell */
     PdBoundGrid colGrid;
@@ -73,8 +92,8 @@ PD_HDN RayHit ray_cast(const TrackDev& T, V3 o, V3 d, float length) {
         }
         for (int k = 0; k < nd.count; ++k) {
             const int t = nd.left + k;
-            const float* p = T.tris + (size_t)t * 9;
-            const V3 v0 = v3(p[0], p[1], p[2]), e1 = v3(p[3], p[4], p[5]), e2 = v3(p[6], p[7], p[8]);
+            const Tri12 tr = load_tri(T.tris, t);
+            const V3 v0 = tr.v0, e1 = tr.e1, e2 = tr.e2;
             const V3 pvec = cross(d, e2);
             const float det = dot(e1, pvec);
             if (det < 0.000001f) continue;
@@ -88,7 +107,7 @@ PD_HDN RayHit ray_cast(const TrackDev& T, V3 o, V3 d, float length) {
             if (dist < 0.0f) continue;
             dist *= (1.0f / det);
             if (!(dist < length)) continue;
-            if (best < 0.0f || dist < best) { best = dist; bestN = cross(e1, e2); bestS = T.triSurf[t]; }
+            if (best < 0.0f || dist < best) { best = dist; bestN = cross(e1, e2); bestS = tr.surf; }
         }
     }
     if (best >= 0.0f) {
@@ -110,10 +129,14 @@ PD_HDN RayHit ray_cast_down(const TrackDev& T, V3 o, float length) {
     const int c = iz * G.nx + ix;
     float best = -1.0f; V3 bestN = v3(0, 0, 0); int bestS = -1;
     const int k0 = T.colStart[c], k1 = T.colStart[c + 1];
+    /* two-deep software pipeline: triangle indices are fetched two entries ahead, triangle data one ahead */
+    int tB = (k0 + 1 < k1) ? T.colItems[k0 + 1] : 0;
+    Tri12 cur; if (k0 < k1) cur = load_tri(T.tris, T.colItems[k0]);
     for (int k = k0; k < k1; ++k) {
-        const int t = T.colItems[k];
-        const float* p = T.tris + (size_t)t * 9;
-        const V3 v0 = v3(p[0], p[1], p[2]), e1 = v3(p[3], p[4], p[5]), e2 = v3(p[6], p[7], p[8]);
+        const int tC = (k + 2 < k1) ? T.colItems[k + 2] : 0;
+        Tri12 nxt = cur; if (k + 1 < k1) nxt = load_tri(T.tris, tB);
+        const V3 v0 = cur.v0, e1 = cur.e1, e2 = cur.e2; const int surf = cur.surf;
+        cur = nxt; tB = tC;
         /* pvec = d x e2 = (-e2.z, 0, e2.x) */
         const float det = e1.x * (-e2.z) + e1.z * e2.x;
         if (det < 0.000001f) continue;
@@ -127,7 +150,7 @@ PD_HDN RayHit ray_cast_down(const TrackDev& T, V3 o, float length) {
         if (dist < 0.0f) continue;
         dist *= (1.0f / det);
         if (!(dist < length)) continue;
-        if (best < 0.0f || dist < best) { best = dist; bestN = cross(e1, e2); bestS = T.triSurf[t]; }
+        if (best < 0.0f || dist < best) { best = dist; bestN = cross(e1, e2); bestS = surf; }
     }
     if (best >= 0.0f) {
         h.hit = 1; h.pos = v3(o.x + 0.0f * best, o.y + -1.0f * best, o.z + 0.0f * best);
@@ -143,6 +166,19 @@ PD_HD bool line_intersection(float p0x, float p0y, float p1x, float p1y, float p
     float t = (s2x * (p0y - p2y) - s2y * (p0x - p2x)) / (-s2x * s1y + s1x * s2y);
     if (s >= 0 && s <= 1 && t >= 0 && t <= 1) { ix = p0x + (t * s1x); iy = p0y + (t * s1y); return true; }
     return false;
+}
+
+struct Seg8 { float ax, az, bx, bz, bx0, by0, bz0, pad; };
+PD_HD Seg8 load_seg8(const float* rec, int k) {
+    Seg8 r;
+#if defined(__CUDA_ARCH__)
+    const float4 a = __ldg(reinterpret_cast<const float4*>(rec) + 2 * (size_t)k), b = __ldg(reinterpret_cast<const float4*>(rec) + 2 * (size_t)k + 1);
+    r.ax = a.x; r.az = a.y; r.bx = a.z; r.bz = a.w; r.bx0 = b.x; r.by0 = b.y; r.bz0 = b.z; r.pad = b.w;
+#else
+    const float* p = rec + (size_t)k * 8;
+    r.ax = p[0]; r.az = p[1]; r.bx = p[2]; r.bz = p[3]; r.bx0 = p[4]; r.by0 = p[5]; r.bz0 = p[6]; r.pad = p[7];
+#endif
+    return r;
 }
 
 /* One probe of Track::rayCastTrackBounds (Track.cpp:497-562): closest intersection of the 2-D segment
@@ -169,14 +205,15 @@ PD_HDN bool probe_walk(const TrackDev& T, float ax, float az, float bx, float bz
     for (int guard = 0; guard < 4096; ++guard) {
         const int c = iz * G.nx + ix;
         const int s0 = T.segStart[c], s1 = T.segStart[c + 1];
+        /* records of the cell are contiguous; the next record is fetched while the current one is tested */
+        Seg8 cur; if (s0 < s1) cur = load_seg8(T.segRec, s0);
         for (int k = s0; k < s1; ++k) {
-            const int item = T.segItems[k]; const int id = item >> 1;
-            const PdFatPoint& f = T.fat[id];
-            if (!(sqlen(cachePos - v3(f.best[0], f.best[1], f.best[2])) < nearRSq)) continue;
-            const PdFatPoint& g = T.fat[id + 1 < nFat ? id + 1 : 0];
-            const float* pa = (item & 1) ? f.right : f.left; const float* pb = (item & 1) ? g.right : g.left;
-            float jx, jz;
-            if (line_intersection(ax, az, bx, bz, pa[0], pa[2], pb[0], pb[2], jx, jz)) { const float ex = ax - jx, ez = az - jz; best = tminf(best, sqrtf(ex * ex + ez * ez)); }
+            Seg8 nxt = cur; if (k + 1 < s1) nxt = load_seg8(T.segRec, k + 1);
+            if (sqlen(cachePos - v3(cur.bx0, cur.by0, cur.bz0)) < nearRSq) {
+                float jx, jz;
+                if (line_intersection(ax, az, bx, bz, cur.ax, cur.az, cur.bx, cur.bz, jx, jz)) { const float ex = ax - jx, ez = az - jz; best = tminf(best, sqrtf(ex * ex + ez * ez)); }
+            }
+            cur = nxt;
         }
         const float tExit = tminf(tmx, tmz);
         if (tExit >= 1.0f) break;                                   /* B lies in this cell */
@@ -199,8 +236,13 @@ PD_HDN bool nearest_point_grid(const TrackDev& T, V3 pos, V3 cachePos, float nea
         for (int ix = cx - 1; ix <= cx + 1; ++ix) {
             const int c = iz * G.nx + ix;
             for (int k = T.ptStart[c]; k < T.ptStart[c + 1]; ++k) {
-                const int id = T.ptItems[k]; const PdFatPoint& f = T.fat[id];
-                const V3 loc = v3(f.best[0], f.best[1], f.best[2]);
+#if defined(__CUDA_ARCH__)
+                const float4 r = __ldg(reinterpret_cast<const float4*>(T.ptRec) + k);
+                const V3 loc = v3(r.x, r.y, r.z); const int id = __float_as_int(r.w);
+#else
+                const float* r = T.ptRec + (size_t)k * 4;
+                const V3 loc = v3(r[0], r[1], r[2]); int id; memcpy(&id, &r[3], 4);
+#endif
                 if (!(sqlen(cachePos - loc) < nearRSq)) continue;
                 const float dsq = sqlen(loc - pos);
                 if (bestDistSq > dsq || (bestDistSq == dsq && id < best)) { bestDistSq = dsq; best = id; }

@@ -19,7 +19,7 @@ struct HS {
     void bind() {
         dev.nodes = (const pd::BvhNode*)track.nodes.data(); dev.tris = track.tris.data(); dev.triSurf = track.triSurf.data();
         dev.surfaces = track.surfaces.data(); dev.fat = track.fat.data(); dev.splineXYZ = track.splineXYZ.data(); dev.splineDist = track.splineDist.data();
-        dev.segStart = track.segStart.data(); dev.segItems = track.segItems.data(); dev.ptStart = track.ptStart.data(); dev.ptItems = track.ptItems.data(); dev.grid = track.grid;
+        dev.segStart = track.segStart.data(); dev.segItems = track.segItems.data(); dev.ptStart = track.ptStart.data(); dev.ptItems = track.ptItems.data(); dev.segRec = track.segRec.data(); dev.ptRec = track.ptRec.data(); dev.grid = track.grid;
         dev.colStart = track.colStart.data(); dev.colItems = track.colItems.data(); dev.colGrid = track.colGrid;
         dev.info = track.info;
     }
@@ -56,15 +56,15 @@ void hs_get_params(void* h, PdCarParams* out) { *out = ((HS*)h)->car.P; }
 void hs_set_params(void* h, const PdCarParams* in) { ((HS*)h)->car.P = *in; }
 void hs_get_track_info(void* h, PdTrackInfo* out) { *out = ((HS*)h)->track.info; }
 void hs_get_spline_nodes(void* hv, float* xyz, float* dist) { HS* h = (HS*)hv; memcpy(xyz, h->track.splineXYZ.data(), h->track.splineXYZ.size() * 4); memcpy(dist, h->track.splineDist.data(), h->track.splineDist.size() * 4); }
-void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SV sv = pd::sv_flat(rec); pd::car_tick(h->car.P, h->dev, sv, dt, time); }
+void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); pd::car_tick(h->car.P, h->dev, sv, dt, time); }
 void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
     HS* h = (HS*)hv; QuadShared sh; pthread_barrier_init(&sh.bar, nullptr, 4);
     std::thread th[4];
-    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SV sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1>(h->car.P, h->dev, sv, dt, time, ex, scr); });
+    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SVFlat sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1>(h->car.P, h->dev, sv, dt, time, ex, scr); });
     for (int l = 0; l < 4; ++l) th[l].join();
     pthread_barrier_destroy(&sh.bar);
 }
-void hs_teleport_point(void* hv, uint32_t* rec, int pointId, double time) { HS* h = (HS*)hv; pd::SV sv = pd::sv_flat(rec); pd::car_teleport_to_point(h->car.P, h->dev, sv, pointId, time); }
+void hs_teleport_point(void* hv, uint32_t* rec, int pointId, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); pd::car_teleport_to_point(h->car.P, h->dev, sv, pointId, time); }
 int hs_point_id_at_distance(void* hv, float d) { return pd::point_id_at_distance(((HS*)hv)->dev, d); }
 void hs_raycast(void* hv, int n, const float* in, float* out) {
     HS* h = (HS*)hv;
