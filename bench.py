@@ -224,8 +224,7 @@ def ours(args):
     achieved = alg_bytes / (tick_ms * 1e-3) / 1e9
     # issue-side view (not tensor work): audited ~50 kflop per car-tick against 74 TFLOP/s fp32
     flop_frac = (n_envs / (tick_ms * 1e-3)) * 50e3 / 74e12
-    quad_max = int(os.environ.get("PD_QUAD_MAX_ENVS", "16384"))
-    kernel = "k_tick_quad" if n_envs <= quad_max else "k_tick"
+    kernel = b.tick_kernel()
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s@%d" % (kernel, n_envs))

@@ -133,6 +133,8 @@ int pd_sync(pd_batch* b);
 void* pd_stream(pd_batch* b);                        /* the cudaStream_t every kernel of this batch runs on */
 /* number of kernels launched by this batch since creation (bench.py's gpu_launches) */
 uint64_t pd_launch_count(const pd_batch* b);
+/* name of the tick kernel this batch dispatches to ("k_tick_quad": <= 8192 envs, "k_tick": larger batches) */
+const char* pd_tick_kernel(const pd_batch* b);
 
 #ifdef __cplusplus
 }

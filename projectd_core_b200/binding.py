@@ -19,7 +19,8 @@ class PdError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libpd_b200.so")
+    """The in-tree CUDA library; PD_B200_LIB selects another build of it (kernel A/B experiments)."""
+    return os.environ.get("PD_B200_LIB") or os.path.join(_HERE, "libpd_b200.so")
 
 
 def _header_constant(name):
@@ -71,6 +72,7 @@ def load_library():
         "pd_get_rewards": (i, [vp, vp, vp, vp]),
         "pd_env_step": (i, [vp, vp, f, vp, vp, vp]),
         "pd_env_step_host": (i, [vp, vp, f, vp, vp, vp]),
+        "pd_tick_kernel": (ctypes.c_char_p, [vp]),
         "pd_env_stats": (i, [vp, vp, i]),
         "pd_get_state": (i, [vp, i, vp]),
         "pd_set_state": (i, [vp, i, vp]),
@@ -215,6 +217,9 @@ class Batch:
 
     def sync(self):
         self._ck(self.L.pd_sync(self.h))
+
+    def tick_kernel(self):
+        return self.L.pd_tick_kernel(self.h).decode()
 
     def launch_count(self):
         return int(self.L.pd_launch_count(self.h))

@@ -26,6 +26,9 @@
 using namespace pd;
 
 #define PD_BLOCK 64
+#ifndef PD_SERIAL_SMEM_SCRATCH
+#define PD_SERIAL_SMEM_SCRATCH 0   /* thread-per-car kernel: solver scratch in shared memory (1: 6 warps/SM, measured 2.2 ms @65536) or in local memory (0: 1.16 ms) */
+#endif
 #define PD_QBLOCK 64   /* threads per block of the quad kernel = stride of the lane-interleaved solver scratch */
 #define PD_QCARS (PD_QBLOCK / 4)
 
@@ -80,9 +83,18 @@ __global__ void __launch_bounds__(PD_BLOCK) k_tick(const __grid_constant__ PdCar
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = e < n && (!mask || mask[e]);
     SVTile sv = sv_tiled(state, (size_t)(e < n ? e : 0));
+#if PD_SERIAL_SMEM_SCRATCH
+    extern __shared__ float pd_scr[];          /* solver scratch: PD_GSCR_WORDS x blockDim, lane-interleaved */
+#else
+    float pd_local_scr[PD_GSCR_WORDS];
+#endif
     if (on) {
         if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
-        car_tick(P, T, sv, dt, time);
+#if PD_SERIAL_SMEM_SCRATCH
+        car_tick<PD_BLOCK>(P, T, sv, dt, time, pd_scr + threadIdx.x);
+#else
+        car_tick<1>(P, T, sv, dt, time, pd_local_scr);
+#endif
     }
     env_epilogue(sv, e, on, io, 0xffffffffu);
 }
@@ -274,7 +286,7 @@ static_assert(sizeof(PdCarStateOut) == 664, "CarState is 664 bytes");
 
 /* batches up to PD_QUAD_MAX_ENVS: four lanes per car (latency-bound regime, more warps per car);
  * larger batches: one thread per car (throughput regime, no redundant scalar work) */
-#define PD_QUAD_MAX_ENVS 16384
+#define PD_QUAD_MAX_ENVS 8192
 
 struct pd_batch {
     int n = 0, device = 0;
@@ -332,6 +344,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(k_tick_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_BLOCK * PD_GSCR_WORDS * 4));
     b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
     int rc;
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
@@ -392,7 +405,7 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
     if (b->layout == PD_LAYOUT_RECORDS)
         k_tick_quad<<<grid(b->n, PD_QCARS), PD_QBLOCK, PD_QUAD_SMEM_BYTES, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     else
-        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, PD_SERIAL_SMEM_SCRATCH ? PD_BLOCK * PD_GSCR_WORDS * 4 : 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     b->launches++;
 }
 
@@ -676,6 +689,7 @@ int pd_raycast(pd_batch* b, int n, const float* rays, float* out) {
 
 int pd_sync(pd_batch* b) { if (!b) return PD_ERR_ARG; CK(cudaStreamSynchronize(b->stream)); CK(cudaGetLastError()); return PD_OK; }
 void* pd_stream(pd_batch* b) { return b ? (void*)b->stream : nullptr; }
+const char* pd_tick_kernel(const pd_batch* b) { return !b ? "" : (b->layout == PD_LAYOUT_RECORDS ? "k_tick_quad" : "k_tick"); }
 uint64_t pd_launch_count(const pd_batch* b) { return b ? b->launches : 0; }
 
 } /* extern "C" */

@@ -425,14 +425,14 @@ PD_HD void chassis_update(Body& Cb, const BodyDyn& d, const float* z, float h) {
 
 /* dWorldStep for the car's island, one thread doing the four groups one after the other with ONE scratch
  * (thread-per-car kernel for large batches, and the host debugging build) */
-PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h) {
+template <int STRIDE> PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h, float* scratch) {
     const float hinv = 1.0f / h;
     BodyDyn dyn[PD_NUM_BODIES];
     for (int i = 0; i < PD_NUM_BODIES; ++i) body_dyn(b[i], P.gravityY, h, dyn[i]);
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
-    float scr[PD_GSCR_WORDS]; GScr<1> G; G.p = scr;
+    GScr<STRIDE> G; G.p = scratch;   /* PD_GSCR_WORDS words at stride STRIDE (shared memory, lane-interleaved, or a local array) */
     /* folded groups: [tank | hub0, strut0 | hub1, strut1 | axle] */
     float pv[6][6], Qv[6][36], pdump[6], Qdump[36];
     const Body& C = b[PD_BODY_CHASSIS];

@@ -52,17 +52,26 @@ PD_HD void d2u(double d, uint32_t& lo, uint32_t& hi) {
  *  SVR: view with a run-time stride, for the small kernels that serve both layouts. */
 #define PD_TILE 32
 enum { PD_LAYOUT_TILED = 0, PD_LAYOUT_RECORDS = 1 };
+#if defined(__CUDA_ARCH__)
+/* address-space hints: a tiled view is only ever built over the global state buffer, a stride-1 view on the device
+ * over the shared-memory staging copy (no hint there: nvcc 12.9 miscompiles __builtin_assume(__isShared()) on a pointer
+ * into dynamic shared memory -- the kernel body is dropped); without the hint the accesses inside non-inlined
+ * functions are generic LD/ST */
+#define PD_ASSUME_SPACE(p) do { if (STRIDE != 1) __builtin_assume(__isGlobal(p)); } while (0)
+#else
+#define PD_ASSUME_SPACE(p) do { } while (0)
+#endif
 template <int STRIDE> struct SVT {
     uint32_t* s;        /* &state[word 0 of this env] */
     bool live;          /* false: a padding lane that computes along but must not write */
     static constexpr int stride = STRIDE;
     PD_HD SVT(uint32_t* base, bool lv = true) : s(base), live(lv) {}
-    PD_HD float f(int w) const { return u2f(s[w * STRIDE]); }
-    PD_HD int i(int w) const { return (int)s[w * STRIDE]; }
-    PD_HD double d(int w) const { return u2d(s[w * STRIDE], s[(w + 1) * STRIDE]); }
-    PD_HD void f(int w, float v) const { if (live) s[w * STRIDE] = f2u(v); }
-    PD_HD void i(int w, int v) const { if (live) s[w * STRIDE] = (uint32_t)v; }
-    PD_HD void d(int w, double v) const { if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[w * STRIDE] = lo; s[(w + 1) * STRIDE] = hi; }
+    PD_HD float f(int w) const { PD_ASSUME_SPACE(s); return u2f(s[w * STRIDE]); }
+    PD_HD int i(int w) const { PD_ASSUME_SPACE(s); return (int)s[w * STRIDE]; }
+    PD_HD double d(int w) const { PD_ASSUME_SPACE(s); return u2d(s[w * STRIDE], s[(w + 1) * STRIDE]); }
+    PD_HD void f(int w, float v) const { PD_ASSUME_SPACE(s); if (live) s[w * STRIDE] = f2u(v); }
+    PD_HD void i(int w, int v) const { PD_ASSUME_SPACE(s); if (live) s[w * STRIDE] = (uint32_t)v; }
+    PD_HD void d(int w, double v) const { PD_ASSUME_SPACE(s); if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[w * STRIDE] = lo; s[(w + 1) * STRIDE] = hi; }
 };
 struct SVR {
     uint32_t* s; bool live; int stride;

@@ -236,7 +236,7 @@ PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, 
 }
 
 /* the tick */
-template <class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime) {
+template <int STRIDE, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch) {
     CarCtx X; X.dt = dt; X.time = physicsTime;
     Body bod[PD_NUM_BODIES]; V3 steerAnchor1[2], steerAnchor2[2];
     set_body_mass(bod, P);
@@ -343,7 +343,7 @@ template <class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& 
     }
 
     /* ---------------- physics->step(dt): dWorldStep ---------------- */
-    world_step(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt);
+    world_step<STRIDE>(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, scratch);
 
     /* ---------------- Car::postStep ---------------- */
     { /* updateTrackLocator (Car.cpp:717-771) */

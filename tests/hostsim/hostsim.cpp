@@ -56,7 +56,7 @@ void hs_get_params(void* h, PdCarParams* out) { *out = ((HS*)h)->car.P; }
 void hs_set_params(void* h, const PdCarParams* in) { ((HS*)h)->car.P = *in; }
 void hs_get_track_info(void* h, PdTrackInfo* out) { *out = ((HS*)h)->track.info; }
 void hs_get_spline_nodes(void* hv, float* xyz, float* dist) { HS* h = (HS*)hv; memcpy(xyz, h->track.splineXYZ.data(), h->track.splineXYZ.size() * 4); memcpy(dist, h->track.splineDist.data(), h->track.splineDist.size() * 4); }
-void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); pd::car_tick(h->car.P, h->dev, sv, dt, time); }
+void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick<1>(h->car.P, h->dev, sv, dt, time, scr); }
 void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
     HS* h = (HS*)hv; QuadShared sh; pthread_barrier_init(&sh.bar, nullptr, 4);
     std::thread th[4];

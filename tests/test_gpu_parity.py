@@ -248,7 +248,7 @@ def test_batched_env_reset_step(oracle):
     assert lo.shape == hi.shape == (24,)
     assert (o[:, 10:12] >= -1 - 1e-4).all() and (o[:, 10:12] <= 1 + 1e-4).all()
     assert (np.abs(o[:, 12:17]) <= math.pi + 1e-4).all()
-    assert (o[:, 17:24] >= 0).all() and (o[:, 17:24] <= 50 + 1e-3).all()
+    assert (o[:, 17:24] >= 0).all() and (o[:, 17:24] <= 55 + 1e-3).all()   # rays are cast to 1.1 x probe length (Track.cpp:497-562)
     st = env.episode_stats()
     assert st["nan"] == 0
     env.close()
