@@ -78,7 +78,7 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
 }
 
 /* the tick, one thread per car, tiled structure-of-arrays state (batches above the quad threshold) */
-__global__ void __launch_bounds__(PD_BLOCK) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+__global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                    const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = e < n && (!mask || mask[e]);

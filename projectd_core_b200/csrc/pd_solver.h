@@ -224,25 +224,25 @@ PD_HD void jinvm6(const float* J, const BodyDyn& d, float* o) {
  * Row loops are kept ROLLED (compact code: the kernel is instruction-fetch sensitive), the 6- and 7-wide inner
  * loops are unrolled.  n = rows to process: the 4-lanes-per-car kernel runs all PD_GMAX rows on every lane (padding
  * rows are identity, so there is no divergence); the thread-per-car kernel passes the group's real row count. */
-template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6, const int n = PD_GMAX) {
+template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6, const int n = PD_GMAX, const bool hasB = true) {
     PD_NOUNROLL
     for (int i = 0; i < n; ++i) {
         float ra[6], rb[6], ja[6], jb[6];
         PD_UNROLL
         for (int k = 0; k < 6; ++k) { ra[k] = G.JA(i, k); rb[k] = G.JB(i, k); }
         jinvm6(ra, dA, ja);
-        jinvm6(rb, dB, jb);
+        if (hasB) jinvm6(rb, dB, jb);
         PD_NOUNROLL
         for (int j = 0; j <= i; ++j) {
             float s = ja[0] * G.JA(j, 0) + ja[1] * G.JA(j, 1) + ja[2] * G.JA(j, 2) + ja[3] * G.JA(j, 3) + ja[4] * G.JA(j, 4) + ja[5] * G.JA(j, 5);
-            s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
+            if (hasB) s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
             G.D(i, j) = s;
         }
         G.D(i, i) += G.dg(i) * hinv;
         /* r_i = c_i/h - J_i (v/h + M^-1 f) */
         float s = ra[0] * dA.t1[0] + ra[1] * dA.t1[1] + ra[2] * dA.t1[2] + ra[3] * dA.t1[3] + ra[4] * dA.t1[4] + ra[5] * dA.t1[5];
         s += G.Y(i, 0) * dC.t1[0] + G.Y(i, 1) * dC.t1[1] + G.Y(i, 2) * dC.t1[2] + G.Y(i, 3) * dC.t1[3] + G.Y(i, 4) * dC.t1[4] + G.Y(i, 5) * dC.t1[5];
-        s += rb[0] * dB.t1[0] + rb[1] * dB.t1[1] + rb[2] * dB.t1[2] + rb[3] * dB.t1[3] + rb[4] * dB.t1[4] + rb[5] * dB.t1[5];
+        if (hasB) s += rb[0] * dB.t1[0] + rb[1] * dB.t1[1] + rb[2] * dB.t1[2] + rb[3] * dB.t1[3] + rb[4] * dB.t1[4] + rb[5] * dB.t1[5];
         G.Y(i, 6) = G.Y(i, 6) * hinv - s;
     }
     /* L D L^T, row by row (same recurrence as the oracle's dense factorisation), in place */
@@ -251,12 +251,12 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
         PD_NOUNROLL
         for (int j = 0; j < i; ++j) {
             float s = G.D(i, j);
-            PD_NOUNROLL
+            PD_UNROLL4
             for (int k = 0; k < j; ++k) s -= G.D(i, k) * G.D(j, k);    /* D(i,k) = u_k (unscaled), D(j,k) = L_jk */
             G.D(i, j) = s;
         }
         float dii = G.D(i, i);
-        PD_NOUNROLL
+        PD_UNROLL4
         for (int j = 0; j < i; ++j) { const float u = G.D(i, j); const float lij = u / G.dg(j); dii -= u * lij; G.D(i, j) = lij; }
         G.dg(i) = dii;
     }
@@ -292,7 +292,7 @@ template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, flo
         G.Y(i, 6) = s / G.dg(i);
     }
     PD_NOUNROLL
-    for (int i = n - 1; i >= 0; --i) { float s = G.Y(i, 6); PD_NOUNROLL for (int k = i + 1; k < n; ++k) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
+    for (int i = n - 1; i >= 0; --i) { float s = G.Y(i, 6); PD_UNROLL4 for (int k = i + 1; k < n; ++k) s -= G.D(k, i) * G.Y(k, 6); G.Y(i, 6) = s; }
     PD_UNROLL
     for (int k = 0; k < 6; ++k) { cfA[k] = 0; cfB[k] = 0; }
     PD_NOUNROLL
@@ -306,7 +306,7 @@ template <class GS> PD_HDN void backsolve_group(const GS& G, const float* z, flo
 /* Serial variant of the back-substitution: fold the group into an affine map of the chassis unknown z,
  *     cforce_A = pA - QA z ,  cforce_B = pB - QB z      (W = L^-T D^-1 [Yu | yr];  p = J^T W[:,6],  Q = J^T W[:,0:6])
  * so that the group's scratch can be reused by the next group before z is known. */
-template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, float* pB, float* QB, const int n = PD_GMAX) {
+template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, float* pB, float* QB, const int n = PD_GMAX, const bool hasB = true) {
     PD_NOUNROLL
     for (int i = 0; i < n; ++i) { const float di = 1.0f / G.dg(i); PD_UNROLL for (int k = 0; k < 7; ++k) G.Y(i, k) *= di; }
     PD_NOUNROLL
@@ -319,18 +319,34 @@ template <class GS> PD_HDN void fold_group(const GS& G, float* pA, float* QA, fl
         PD_UNROLL
         for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
     }
-    PD_UNROLL
-    for (int a = 0; a < 6; ++a) {
-        float sa = 0, sb = 0;
-        PD_NOUNROLL
-        for (int i = 0; i < n; ++i) { sa += G.JA(i, a) * G.Y(i, 6); sb += G.JB(i, a) * G.Y(i, 6); }
-        pA[a] = sa; pB[a] = sb;
+    /* p = J^T W[:,6], Q = J^T W[:,0:6]: one pass over the rows with the 2 x 42 sums kept in registers
+     * (each sum still runs over i ascending from 0, as the row-by-row form did) */
+    PD_NOUNROLL
+    for (int body = 0; body < 2; ++body) {
+        float* pOut = body ? pB : pA; float* QOut = body ? QB : QA;
+        float acc[42];
         PD_UNROLL
-        for (int k = 0; k < 6; ++k) {
-            float qa = 0, qb = 0;
+        for (int k = 0; k < 42; ++k) acc[k] = 0;
+        if (body == 0 || hasB) {
             PD_NOUNROLL
-            for (int i = 0; i < n; ++i) { qa += G.JA(i, a) * G.Y(i, k); qb += G.JB(i, a) * G.Y(i, k); }
-            QA[a * 6 + k] = qa; QB[a * 6 + k] = qb;
+            for (int i = 0; i < n; ++i) {
+                float y[7], jr[6];
+                PD_UNROLL
+                for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
+                PD_UNROLL
+                for (int a = 0; a < 6; ++a) jr[a] = body ? G.JB(i, a) : G.JA(i, a);
+                PD_UNROLL
+                for (int a = 0; a < 6; ++a) {
+                    PD_UNROLL
+                    for (int k = 0; k < 7; ++k) acc[a * 7 + k] += jr[a] * y[k];
+                }
+            }
+        }
+        PD_UNROLL
+        for (int a = 0; a < 6; ++a) {
+            pOut[a] = acc[a * 7 + 6];
+            PD_UNROLL
+            for (int k = 0; k < 6; ++k) QOut[a * 6 + k] = acc[a * 7 + k];
         }
     }
 }
@@ -437,16 +453,16 @@ template <int STRIDE> PD_HDN void world_step(const PdCarParams& P, Body* b, cons
     float pv[6][6], Qv[6][36], pdump[6], Qdump[36];
     const Body& C = b[PD_BODY_CHASSIS];
     build_tank(P, b[PD_BODY_TANK], C, hinv, G);
-    factor_group(G, dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6, 6);
-    fold_group(G, pv[0], Qv[0], pdump, Qdump, 6);
+    factor_group(G, dyn[PD_BODY_TANK], dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6, 6, false);
+    fold_group(G, pv[0], Qv[0], pdump, Qdump, 6, false);
     for (int s = 0; s < 2; ++s) {
         build_strut(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], hinv, dballErp, dballCfm, G);
         factor_group(G, dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, S21, b6);
         fold_group(G, pv[1 + 2 * s], Qv[1 + 2 * s], pv[2 + 2 * s], Qv[2 + 2 * s]);
     }
     build_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, G);
-    factor_group(G, dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6, 5);
-    fold_group(G, pv[5], Qv[5], pdump, Qdump, 5);
+    factor_group(G, dyn[PD_BODY_AXLE], dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6, 5, false);
+    fold_group(G, pv[5], Qv[5], pdump, Qdump, 5, false);
     schur_add_chassis(S21, C);
     float z[6];
     solve6(S21, b6, z);
