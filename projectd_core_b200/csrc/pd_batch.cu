@@ -27,7 +27,7 @@ using namespace pd;
 
 #define PD_BLOCK 64
 #ifndef PD_SERIAL_SMEM_SCRATCH
-#define PD_SERIAL_SMEM_SCRATCH 0   /* thread-per-car kernel: solver scratch in shared memory (1: 6 warps/SM, measured 2.2 ms @65536) or in local memory (0: 1.16 ms) */
+#define PD_SERIAL_SMEM_SCRATCH 0   /* thread-per-car kernel: D | dg part of the solver scratch in shared memory (1) or everything in local memory (0); measured equal at 65536 envs (0.884 ms), 0 is 8 % faster at 16384 */
 #endif
 #define PD_QBLOCK 64   /* threads per block of the quad kernel = stride of the lane-interleaved solver scratch */
 #define PD_QCARS (PD_QBLOCK / 4)
@@ -83,17 +83,20 @@ __global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ Pd
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = e < n && (!mask || mask[e]);
     SVTile sv = sv_tiled(state, (size_t)(e < n ? e : 0));
+    /* solver scratch: the rows part (JA | JB | Y, 209 words) in local memory, the D | dg part (77 words, re-read by
+       every phase of the factorisation) in shared memory, lane-interleaved: 19.7 KB per block keeps 8 blocks per SM */
 #if PD_SERIAL_SMEM_SCRATCH
-    extern __shared__ float pd_scr[];          /* solver scratch: PD_GSCR_WORDS x blockDim, lane-interleaved */
+    __shared__ float pd_scrD[PD_GSCR_D_WORDS * PD_BLOCK];
+    float pd_rows[PD_GSCR_ROWS_WORDS];
 #else
-    float pd_local_scr[PD_GSCR_WORDS];
+    float pd_rows[PD_GSCR_WORDS];
 #endif
     if (on) {
         if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
 #if PD_SERIAL_SMEM_SCRATCH
-        car_tick<PD_BLOCK>(P, T, sv, dt, time, pd_scr + threadIdx.x);
+        car_tick<1, PD_BLOCK>(P, T, sv, dt, time, pd_rows, pd_scrD + threadIdx.x);
 #else
-        car_tick<1>(P, T, sv, dt, time, pd_local_scr);
+        car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows + PD_GSCR_ROWS_WORDS);
 #endif
     }
     env_epilogue(sv, e, on, io, 0xffffffffu);
@@ -344,7 +347,6 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(k_tick_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_BLOCK * PD_GSCR_WORDS * 4));
     b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
     int rc;
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
@@ -405,7 +407,7 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
     if (b->layout == PD_LAYOUT_RECORDS)
         k_tick_quad<<<grid(b->n, PD_QCARS), PD_QBLOCK, PD_QUAD_SMEM_BYTES, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     else
-        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, PD_SERIAL_SMEM_SCRATCH ? PD_BLOCK * PD_GSCR_WORDS * 4 : 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     b->launches++;
 }
 

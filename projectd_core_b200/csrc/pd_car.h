@@ -18,11 +18,12 @@ struct WheelLink {
 
 /* car-level (non-body) context of one tick; every lane of a car's quad holds an identical copy */
 struct CarCtx {
-    CarS c;
+    CarS& c;              /* a local copy (tiled state) or the record's car part itself (stride-1 view, in place) */
     WheelLink wl[PD_NUM_WHEELS];
     float dt;
     double time;          /* Simulator::physicsTime */
     float dballErp, dballCfm;
+    PD_HD explicit CarCtx(CarS& cc) : c(cc) {}
 };
 
 PD_HD float engine_rpm(const CarS& c) { return (float)((c.engineVel * 0.15915507) * 60.0); }   /* Drivetrain::getEngineRPM */
@@ -307,7 +308,9 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, flo
 template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev& T, int w, const CarCtx& X, const SVX& sv, Body& hubBody, const Frame& hubFrame, Body& C, float brakeTorqueIn, float handBrakeIn, WheelLink& L) {
     const PdTyre& P = PP.tyre[w];
     const float dt = X.dt;
-    TyreS t; load_tyre(sv, w, t);
+    TyreS tLocal; TyreS* tp = &tLocal;
+    if constexpr (sv_traits<SVX>::in_place) tp = tyre_in_place(sv, w); else load_tyre(sv, w, tLocal);
+    TyreS& t = *tp;
     t.brakeTorque = brakeTorqueIn; t.handBrakeTorque = handBrakeIn;
     t.feedbackTorque = 0; t.Fx = 0; t.Mz = 0; t.slipFactor = 0; t.rollingResistence = 0;
     t.slidingVelocityY = 0; t.slidingVelocityX = 0; t.totalHubVelocity = 0;
@@ -566,7 +569,7 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
             }
         }
     }
-    store_tyre(sv, w, t);
+    if constexpr (!sv_traits<SVX>::in_place) store_tyre(sv, w, t);
     L.load = t.load; L.feedbackTorque = t.feedbackTorque; L.angularVelocity = t.angularVelocity;
     L.brakeTorque = t.brakeTorque; L.handBrakeTorque = t.handBrakeTorque; L.ndSlip = t.ndSlip; L.slipRatio = t.slipRatio;
     L.isLocked = t.isLocked; L.surfaceId = t.surfaceId;

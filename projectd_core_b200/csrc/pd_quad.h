@@ -41,9 +41,15 @@ template <int STRIDE, class Ex, class SVX>
 PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch) {
     const int lane = ex.lane;
     const bool front = lane < 2;
-    CarCtx X; X.dt = dt; X.time = physicsTime;
-    load_car(sv, X.c);
+    /* Car-level state: with a stride-1 view (the shared-memory staging copy) the four lanes work IN PLACE on the
+     * record's car part.  They execute the car-level code converged (ex.sync() below re-joins them after every
+     * lane-dependent section) and from identical inputs, so every store is four identical stores and every
+     * read-modify-write reads before any lane writes.  (tests/hostsim gives each host thread its own record.) */
+    CarS cLocal; CarS* cp = &cLocal;
+    if constexpr (sv_traits<SVX>::in_place) cp = car_in_place(sv); else load_car(sv, cLocal);
+    CarCtx X(*cp); X.dt = dt; X.time = physicsTime;
     CarS& c = X.c;
+    ex.sync();
     Body C, W, S;
     const int wIdx = front ? (PD_BODY_HUB0 + 2 * lane) : PD_BODY_AXLE;
     const int sIdx = front ? (PD_BODY_STRUT0 + 2 * lane) : PD_BODY_TANK;
@@ -132,6 +138,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
         steerA1 = to_local(C.fr, to_world(C.fr, carSteer));
         steerA2 = to_local(W.fr, to_world(W.fr, v3(St.tyreSteer[0], St.tyreSteer[1], St.tyreSteer[2])));
     }
+    ex.sync();
     autoblip_step(P, X);
     autoshift_step(P, X);
     gearchanger_step(P, X);
@@ -172,7 +179,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
-    GScr<STRIDE> G; G.p = scratch;
+    GScr<STRIDE> G; G.bind(scratch);
     if (front) build_strut(P, P.strut[lane], C, W, S, steerA1, steerA2, hinv, X.dballErp, X.dballCfm, G);
     else if (lane == 2) build_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G);
     else build_tank(P, S, C, hinv, G);
@@ -199,6 +206,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     if (lane != 2) store_body(sv, sIdx, S);
 
     /* ---------------- Car::postStep ---------------- */
+    ex.sync();
     {
         const V3 bodyPos = C.fr.p;
         const int nFat = T.info.nFatPoints;
@@ -269,11 +277,13 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
             if ((c.speed * 3.6f) > 3.0f) c.velocityVsTrack = dot(bodyVelDir, fwd); else c.velocityVsTrack = 0.0f;
         }
     }
+    ex.sync();
     post_lookahead(P, T, C, c);
     post_scoring(P, T, C, X, dt);
     c.episodeSteps++; c.thermalPrimed = 1;
     if (bad) c.nanFlag = 1;
-    if (lane == 0) store_car(sv, c);
+    if constexpr (!sv_traits<SVX>::in_place) { if (lane == 0) store_car(sv, c); }
+    ex.sync();
 }
 
 } // namespace pd

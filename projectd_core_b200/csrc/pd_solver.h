@@ -119,13 +119,19 @@ PD_HD void plane_space(V3 n, V3& p, V3& q) {
  * Layout (words): JA 11x6 | JB 11x6 | Y 11x7 ([U | c], then [U | r], then L^-1[U | r]; column 6 ends as lambda) |
  * D packed lower 66 (in place: unit-lower L below the diagonal) | dg 11 (cfm per row, then the D diagonal). */
 #define PD_GSCR_WORDS 286
-template <int S> struct GScr {
-    float* p;
+#define PD_GSCR_ROWS_WORDS 209   /* JA | JB | Y */
+#define PD_GSCR_D_WORDS 77       /* D | dg : the part every phase of the factorisation re-reads */
+/* S: stride of the JA | JB | Y part at p;  SD: stride of the D | dg part at q (the thread-per-car kernel keeps the
+ * first part in local memory, stride 1, and the second in shared memory, lane-interleaved) */
+template <int S, int SD = S> struct GScr {
+    float* p; float* q;
+    PD_HD void bind(float* base) { p = base; q = base + PD_GSCR_ROWS_WORDS * S; }          /* one contiguous scratch */
+    PD_HD void bind(float* rows, float* dpart) { p = rows; q = dpart; }
     PD_HD float& JA(int i, int k) const { return p[(i * 6 + k) * S]; }
     PD_HD float& JB(int i, int k) const { return p[(66 + i * 6 + k) * S]; }
     PD_HD float& Y(int i, int k) const { return p[(132 + i * 7 + k) * S]; }
-    PD_HD float& D(int i, int j) const { return p[(209 + i * (i + 1) / 2 + j) * S]; }   /* j <= i */
-    PD_HD float& dg(int i) const { return p[(275 + i) * S]; }
+    PD_HD float& D(int i, int j) const { return q[(i * (i + 1) / 2 + j) * SD]; }   /* j <= i */
+    PD_HD float& dg(int i) const { return q[(66 + i) * SD]; }
 };
 /* all rows zero; pad rows get cfm = h so that their diagonal becomes cfm/h = 1 */
 template <class GS> PD_HD void zero_group(const GS& G, int n, float cfm, float h) {
@@ -441,14 +447,14 @@ PD_HD void chassis_update(Body& Cb, const BodyDyn& d, const float* z, float h) {
 
 /* dWorldStep for the car's island, one thread doing the four groups one after the other with ONE scratch
  * (thread-per-car kernel for large batches, and the host debugging build) */
-template <int STRIDE> PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h, float* scratch) {
+template <int STRIDE, int STRIDE_D> PD_HDN void world_step(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h, float* scratch, float* scratchD) {
     const float hinv = 1.0f / h;
     BodyDyn dyn[PD_NUM_BODIES];
     for (int i = 0; i < PD_NUM_BODIES; ++i) body_dyn(b[i], P.gravityY, h, dyn[i]);
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
-    GScr<STRIDE> G; G.p = scratch;   /* PD_GSCR_WORDS words at stride STRIDE (shared memory, lane-interleaved, or a local array) */
+    GScr<STRIDE, STRIDE_D> G; G.bind(scratch, scratchD);   /* rows part: PD_GSCR_ROWS_WORDS words at STRIDE; D part: PD_GSCR_D_WORDS at STRIDE_D */
     /* folded groups: [tank | hub0, strut0 | hub1, strut1 | axle] */
     float pv[6][6], Qv[6][36], pdump[6], Qdump[36];
     const Body& C = b[PD_BODY_CHASSIS];

@@ -6,6 +6,7 @@
 #include "../../include/pd_state.h"
 #include "../../include/pd_params.h"
 #include <string.h>
+#include <stddef.h>
 
 namespace pd {
 
@@ -63,25 +64,24 @@ enum { PD_LAYOUT_TILED = 0, PD_LAYOUT_RECORDS = 1 };
 #endif
 template <int STRIDE> struct SVT {
     uint32_t* s;        /* &state[word 0 of this env] */
-    bool live;          /* false: a padding lane that computes along but must not write */
     static constexpr int stride = STRIDE;
-    PD_HD SVT(uint32_t* base, bool lv = true) : s(base), live(lv) {}
+    PD_HD explicit SVT(uint32_t* base) : s(base) {}
     PD_HD float f(int w) const { PD_ASSUME_SPACE(s); return u2f(s[w * STRIDE]); }
     PD_HD int i(int w) const { PD_ASSUME_SPACE(s); return (int)s[w * STRIDE]; }
     PD_HD double d(int w) const { PD_ASSUME_SPACE(s); return u2d(s[w * STRIDE], s[(w + 1) * STRIDE]); }
-    PD_HD void f(int w, float v) const { PD_ASSUME_SPACE(s); if (live) s[w * STRIDE] = f2u(v); }
-    PD_HD void i(int w, int v) const { PD_ASSUME_SPACE(s); if (live) s[w * STRIDE] = (uint32_t)v; }
-    PD_HD void d(int w, double v) const { PD_ASSUME_SPACE(s); if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[w * STRIDE] = lo; s[(w + 1) * STRIDE] = hi; }
+    PD_HD void f(int w, float v) const { PD_ASSUME_SPACE(s); s[w * STRIDE] = f2u(v); }
+    PD_HD void i(int w, int v) const { PD_ASSUME_SPACE(s); s[w * STRIDE] = (uint32_t)v; }
+    PD_HD void d(int w, double v) const { PD_ASSUME_SPACE(s); uint32_t lo, hi; d2u(v, lo, hi); s[w * STRIDE] = lo; s[(w + 1) * STRIDE] = hi; }
 };
 struct SVR {
-    uint32_t* s; bool live; int stride;
-    PD_HD SVR(uint32_t* base, int st, bool lv = true) : s(base), live(lv), stride(st) {}
+    uint32_t* s; int stride;
+    PD_HD SVR(uint32_t* base, int st) : s(base), stride(st) {}
     PD_HD float f(int w) const { return u2f(s[w * stride]); }
     PD_HD int i(int w) const { return (int)s[w * stride]; }
     PD_HD double d(int w) const { return u2d(s[w * stride], s[(w + 1) * stride]); }
-    PD_HD void f(int w, float v) const { if (live) s[w * stride] = f2u(v); }
-    PD_HD void i(int w, int v) const { if (live) s[w * stride] = (uint32_t)v; }
-    PD_HD void d(int w, double v) const { if (!live) return; uint32_t lo, hi; d2u(v, lo, hi); s[w * stride] = lo; s[(w + 1) * stride] = hi; }
+    PD_HD void f(int w, float v) const { s[w * stride] = f2u(v); }
+    PD_HD void i(int w, int v) const { s[w * stride] = (uint32_t)v; }
+    PD_HD void d(int w, double v) const { uint32_t lo, hi; d2u(v, lo, hi); s[w * stride] = lo; s[(w + 1) * stride] = hi; }
 };
 typedef SVT<PD_TILE> SVTile;
 typedef SVT<1> SVFlat;
@@ -107,6 +107,22 @@ struct CarS {
     float probes[PD_MAX_PROBES];
     float lookAhead[PD_LOOKAHEAD];
 };
+
+/* A stride-1 view IS a record in memory with the layout of the typed mirrors (doubles first in each group, groups on
+ * even word offsets, see include/pd_state.h), so its tyre / car parts can be used in place instead of being copied. */
+#define PD__CHK_T(kind, name) static_assert(offsetof(TyreS, name) == 4 * PD_TYRE_o_##name, "TyreS layout != record layout: " #name);
+#define PD__CHK_C(kind, name) static_assert(offsetof(CarS, name) == 4 * PD_CAR_o_##name, "CarS layout != record layout: " #name);
+PD_TYRE_FIELDS(PD__CHK_T)
+PD_CAR_FIELDS(PD__CHK_C)
+static_assert(offsetof(TyreS, T) == 4 * PD_TYRE_SCALAR_WORDS && sizeof(TyreS) == 4 * PD_TYRE_WORDS, "TyreS size");
+static_assert(offsetof(CarS, probes) == 4 * PD_CAR_SCALAR_WORDS && offsetof(CarS, lookAhead) == 4 * (PD_CAR_SCALAR_WORDS + PD_MAX_PROBES), "CarS arrays");
+static_assert(PD_OFF_TYRE(0) % 2 == 0 && PD_TYRE_WORDS % 2 == 0 && PD_OFF_CAR % 2 == 0 && PD_STATE_STRIDE % 2 == 0, "8-byte alignment of the double fields");
+template <class SVX> struct sv_traits { static constexpr bool in_place = false; };
+template <> struct sv_traits<SVT<1> > { static constexpr bool in_place = true; };
+PD_HD TyreS* tyre_in_place(const SVT<1>& sv, int w) { return reinterpret_cast<TyreS*>(sv.s + PD_OFF_TYRE(w)); }
+PD_HD CarS* car_in_place(const SVT<1>& sv) { return reinterpret_cast<CarS*>(sv.s + PD_OFF_CAR); }
+template <class SVX> PD_HD TyreS* tyre_in_place(const SVX&, int) { return nullptr; }
+template <class SVX> PD_HD CarS* car_in_place(const SVX&) { return nullptr; }
 
 #define PD__LD_F(pre, name) t.name = sv.f(o + pre##name);
 #define PD__LD_I(pre, name) t.name = sv.i(o + pre##name);

@@ -236,12 +236,13 @@ PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, 
 }
 
 /* the tick */
-template <int STRIDE, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch) {
-    CarCtx X; X.dt = dt; X.time = physicsTime;
+template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch, float* scratchD) {
+    CarS cLocal; CarS* cp = &cLocal;
+    if constexpr (sv_traits<SVX>::in_place) cp = car_in_place(sv); else load_car(sv, cLocal);
+    CarCtx X(*cp); X.dt = dt; X.time = physicsTime;
     Body bod[PD_NUM_BODIES]; V3 steerAnchor1[2], steerAnchor2[2];
     set_body_mass(bod, P);
     for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
-    load_car(sv, X.c);
     CarS& c = X.c;
     Body& C = bod[PD_BODY_CHASSIS];
 
@@ -343,7 +344,7 @@ template <int STRIDE, class SVX> PD_HDN void car_tick(const PdCarParams& P, cons
     }
 
     /* ---------------- physics->step(dt): dWorldStep ---------------- */
-    world_step<STRIDE>(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, scratch);
+    world_step<STRIDE, STRIDE_D>(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, scratch, scratchD);
 
     /* ---------------- Car::postStep ---------------- */
     { /* updateTrackLocator (Car.cpp:717-771) */
@@ -420,7 +421,7 @@ template <int STRIDE, class SVX> PD_HDN void car_tick(const PdCarParams& P, cons
         if (bad) c.nanFlag = 1;
     }
     for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, bod[i]);
-    store_car(sv, c);
+    if constexpr (!sv_traits<SVX>::in_place) store_car(sv, c);
 }
 
 /* observation vector of pyprojectd/projectd_env.py:237-275 */

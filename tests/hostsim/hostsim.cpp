@@ -8,6 +8,7 @@
  */
 #include "../../projectd_core_b200/csrc/pd_quad.h"
 #include <pthread.h>
+#include <vector>
 #include <thread>
 #include "../../projectd_core_b200/csrc/host/pd_host.h"
 #include <cstdio>
@@ -56,13 +57,24 @@ void hs_get_params(void* h, PdCarParams* out) { *out = ((HS*)h)->car.P; }
 void hs_set_params(void* h, const PdCarParams* in) { ((HS*)h)->car.P = *in; }
 void hs_get_track_info(void* h, PdTrackInfo* out) { *out = ((HS*)h)->track.info; }
 void hs_get_spline_nodes(void* hv, float* xyz, float* dist) { HS* h = (HS*)hv; memcpy(xyz, h->track.splineXYZ.data(), h->track.splineXYZ.size() * 4); memcpy(dist, h->track.splineDist.data(), h->track.splineDist.size() * 4); }
-void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick<1>(h->car.P, h->dev, sv, dt, time, scr); }
+void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick<1, 1>(h->car.P, h->dev, sv, dt, time, scr, scr + PD_GSCR_ROWS_WORDS); }
 void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
+    /* the GPU lanes of a quad share one record and run converged; host threads do not, so every "lane" gets a private
+       copy of the record and the parts each lane owns are merged afterwards:
+       lane 0: chassis, hub0, strut0, tyre 0, car part;  lane 1: hub1, strut1, tyre 1;  lane 2: axle, tyre 2;  lane 3: tank, tyre 3 */
     HS* h = (HS*)hv; QuadShared sh; pthread_barrier_init(&sh.bar, nullptr, 4);
+    std::vector<uint32_t> copy[4];
+    for (int l = 0; l < 4; ++l) copy[l].assign(rec, rec + PD_STATE_WORDS);
     std::thread th[4];
-    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SVFlat sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1>(h->car.P, h->dev, sv, dt, time, ex, scr); });
+    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SVFlat sv = pd::sv_flat(copy[l].data()); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1>(h->car.P, h->dev, sv, dt, time, ex, scr); });
     for (int l = 0; l < 4; ++l) th[l].join();
     pthread_barrier_destroy(&sh.bar);
+    auto take = [&](int lane, int off, int words) { memcpy(rec + off, copy[lane].data() + off, (size_t)words * 4); };
+    take(0, PD_OFF_BODY(PD_BODY_CHASSIS), PD_BODY_WORDS); take(0, PD_OFF_BODY(PD_BODY_HUB0), PD_BODY_WORDS); take(0, PD_OFF_BODY(PD_BODY_STRUT0), PD_BODY_WORDS);
+    take(1, PD_OFF_BODY(PD_BODY_HUB1), PD_BODY_WORDS); take(1, PD_OFF_BODY(PD_BODY_STRUT1), PD_BODY_WORDS);
+    take(2, PD_OFF_BODY(PD_BODY_AXLE), PD_BODY_WORDS); take(3, PD_OFF_BODY(PD_BODY_TANK), PD_BODY_WORDS);
+    for (int l = 0; l < 4; ++l) take(l, PD_OFF_TYRE(l), PD_TYRE_WORDS);
+    take(0, PD_OFF_CAR, PD_CAR_WORDS);
 }
 void hs_teleport_point(void* hv, uint32_t* rec, int pointId, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); pd::car_teleport_to_point(h->car.P, h->dev, sv, pointId, time); }
 int hs_point_id_at_distance(void* hv, float d) { return pd::point_id_at_distance(((HS*)hv)->dev, d); }
