@@ -131,7 +131,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-#define PD_QUAD_SMEM_BYTES (PD_QCARS * PD_STATE_STRIDE * 4 + PD_QBLOCK * PD_GSCR_WORDS * 4 + 16)
+#ifndef PD_QUAD_LOCAL_SCRATCH
+#define PD_QUAD_LOCAL_SCRATCH 0   /* solver scratch of the quad kernel: 0 = shared memory, 1 = local memory, 2 = JA | JB local, Y | D | dg shared */
+#endif
+#define PD_QUAD_SMEM_BYTES (PD_QCARS * PD_STATE_STRIDE * 4 + 16 + (PD_QUAD_LOCAL_SCRATCH == 1 ? 0 : PD_QUAD_LOCAL_SCRATCH == 2 ? PD_QBLOCK * PD_GSCR_D_WORDS * 4 : PD_QBLOCK * PD_GSCR_WORDS * 4))
 
 /* the tick, four lanes per car, array-of-records state staged through shared memory:
  * block = 64 threads = 16 cars; ONE bulk copy brings the block's 16 records (40 KB) in, the quads work on the
@@ -140,8 +143,8 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
                                                          const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     extern __shared__ __align__(128) uint32_t pd_smem[];
     uint32_t* recs = pd_smem;                                                         /* [16][PD_STATE_STRIDE] */
-    float* scratch = reinterpret_cast<float*>(pd_smem + PD_QCARS * PD_STATE_STRIDE);  /* [PD_GSCR_WORDS][64], lane-interleaved */
-    uint64_t* bar = reinterpret_cast<uint64_t*>(pd_smem + PD_QCARS * PD_STATE_STRIDE + PD_QBLOCK * PD_GSCR_WORDS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(pd_smem + PD_QCARS * PD_STATE_STRIDE);
+    float* scratch = reinterpret_cast<float*>(pd_smem + PD_QCARS * PD_STATE_STRIDE + 4);  /* [PD_GSCR_WORDS][64], lane-interleaved */
     const int tid = threadIdx.x;
     const int car0 = blockIdx.x * PD_QCARS;
     const int ncars = min(PD_QCARS, n - car0);
@@ -159,7 +162,15 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
     if (on) {
         QuadShfl ex; ex.lane = tid & 3; ex.base = (tid & 31) & ~3; ex.mask = 0xFu << ex.base;
         if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
-        car_tick_quad<PD_QBLOCK>(P, T, sv, dt, time, ex, scratch + tid);
+#if PD_QUAD_LOCAL_SCRATCH == 1
+        float lscr[PD_GSCR_WORDS];
+        car_tick_quad<1, 1>(P, T, sv, dt, time, ex, lscr, lscr + PD_GSCR_ROWS_WORDS);
+#elif PD_QUAD_LOCAL_SCRATCH == 2
+        float lrows[PD_GSCR_ROWS_WORDS];                     /* JA | JB in local memory, Y | D | dg in shared memory */
+        car_tick_quad<1, PD_QBLOCK>(P, T, sv, dt, time, ex, lrows, scratch + tid);
+#else
+        car_tick_quad<PD_QBLOCK, PD_QBLOCK>(P, T, sv, dt, time, ex, scratch + tid, scratch + PD_GSCR_ROWS_WORDS * PD_QBLOCK + tid);
+#endif
     }
     fence_async_smem();                                        /* generic-proxy writes -> visible to the bulk copy engine */
     __syncthreads();

@@ -31,7 +31,7 @@ PD_HD float car_engine_rpm(const CarS& c) { return ((float)c.engineVel * 0.15915
 
 /* ---- hub frames (ISuspension::getHubWorldMatrix) ---- */
 PD_HD Frame strut_hub_frame(const PdStrut& P, const Body& hub) { /* SuspensionStrut.cpp:360-366 */
-    Frame f; const float s = sinf(P.staticCamber), c = cosf(P.staticCamber);
+    Frame f; const float s = m_sin(P.staticCamber), c = m_cos(P.staticCamber);
     f.ax = v3(c * hub.fr.ax.x + s * hub.fr.ay.x, c * hub.fr.ax.y + s * hub.fr.ay.y, c * hub.fr.ax.z + s * hub.fr.ay.z);
     f.ay = v3(-s * hub.fr.ax.x + c * hub.fr.ay.x, -s * hub.fr.ax.y + c * hub.fr.ay.y, -s * hub.fr.ax.z + c * hub.fr.ay.z);
     f.az = hub.fr.az; f.p = hub.fr.p;
@@ -184,8 +184,8 @@ PD_HD float sctm_pure_fy(const PdTyre& P, float cf, float slip) {
     else fy = (((1.0f - (slip / v6)) * (1.0f - (slip / v6))) * (v5 * slip)) + ((3.0f - ((slip / v6) * 2.0f)) * ((slip / v6) * (slip / v6)));
     return fy;
 }
-PD_HD float sctm_static_dy(const PdTyre& P, float load) { if (load != 0.0f) return (powf(load, P.lsExpY) * P.lsMultY) / load; return 0; }
-PD_HD float sctm_static_dx(const PdTyre& P, float load) { if (load != 0.0) return (powf(load, P.sctmLsExpX) * P.sctmLsMultX) / load; return 0; }
+PD_HD float sctm_static_dy(const PdTyre& P, float load) { if (load != 0.0f) return (m_pow(load, P.lsExpY) * P.lsMultY) / load; return 0; }
+PD_HD float sctm_static_dx(const PdTyre& P, float load) { if (load != 0.0) return (m_pow(load, P.sctmLsExpX) * P.sctmLsMultX) / load; return 0; }
 
 struct TmIn { float load, slipAngleRAD, slipRatio, camberRAD, speed, u, cpLength, grain, blister, pressureRatio; };
 struct TmOut { float Fy, Fx, Mz, trail, ndSlip, Dy, Dx; };
@@ -195,9 +195,9 @@ PD_HD TmOut sctm_solve(const PdTyre& P, const TmIn& tmi) {
     TmOut tmo; tmo.Fy = 0; tmo.Fx = 0; tmo.Mz = 0; tmo.trail = 0; tmo.ndSlip = 0; tmo.Dy = 0; tmo.Dx = 0;
     if (tmi.load <= 0.0f || (tmi.slipAngleRAD == 0.0f && tmi.slipRatio == 0.0f && tmi.camberRAD == 0.0f)) return tmo;
     const float fSlipAngle = tmi.slipAngleRAD;
-    const float fUnk1 = (sinf(tmi.camberRAD) * P.camberGain) + fSlipAngle;
-    const float fUnk1Tan = tanf(fUnk1);
-    const float fSlipAngleSin = sinf(fSlipAngle);
+    const float fUnk1 = (m_sin(tmi.camberRAD) * P.camberGain) + fSlipAngle;
+    const float fUnk1Tan = m_tan(fUnk1);
+    const float fSlipAngleSin = m_sin(fSlipAngle);
     const float fBlister1 = tclampf(tmi.blister * 0.01f, 0.0f, 1.0f);
     const float fBlister2 = (fBlister1 * 0.2f) + 1.0f;
     const float fStaticDy = sctm_static_dy(P, tmi.load);
@@ -215,7 +215,7 @@ PD_HD TmOut sctm_solve(const PdTyre& P, const TmIn& tmi) {
         fUDy += (((fUDy / (fCamberUnk + 1.0f)) - fUDy) * P.dCamberBlend);
     }
     const float fSlipRatio = tmi.slipRatio;
-    const float fSlipAngleCos = cosf(tmi.slipAngleRAD);
+    const float fSlipAngleCos = m_cos(tmi.slipAngleRAD);
     const float fSlipRatioClamped = (fSlipRatio > -0.9999999f ? fSlipRatio : -0.9999999f);
     const float fSpeed = tmi.speed;
     const float a = fSpeed * fSlipAngleSin;
@@ -231,7 +231,7 @@ PD_HD TmOut sctm_solve(const PdTyre& P, const TmIn& tmi) {
     float fSlip;
     const float fCombFactor = P.combinedFactor;
     if (fCombFactor <= 0.0f || fCombFactor == 2.0f) fSlip = sqrtf((fUnk4 * fUnk4) + (fUnk3 * fUnk3));
-    else { const float c34 = powf(fabsf(fUnk4), fCombFactor) + powf(fabsf(fUnk3), fCombFactor); fSlip = powf(c34, 1.0f / fCombFactor); }
+    else { const float c34 = m_pow(fabsf(fUnk4), fCombFactor) + m_pow(fabsf(fUnk3), fCombFactor); fSlip = m_pow(c34, 1.0f / fCombFactor); }
     const float fPureFyDx = sctm_pure_fy(P, fCF * P.cfXmult, fSlip) * fDx;
     const float fPureFyDy = sctm_pure_fy(P, fCF, fSlip);
     tmo.Fy = ((fPureFyDy * fDy) * (fUnk4 / fSlip)) * tmi.load;
@@ -332,8 +332,8 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
         const float fTest = dot(vHitNorm, vWorldM2);
         if (fTest <= 0.96f) {
             float fTestAcos;
-            if (fTest <= -1.0f || fTest >= 1.0f) fTestAcos = 0; else fTestAcos = acosf(fTest);
-            const float fAngle = fTestAcos - acosf(0.96f);
+            if (fTest <= -1.0f || fTest >= 1.0f) fTestAcos = 0; else fTestAcos = m_acos(fTest);
+            const float fAngle = fTestAcos - m_acos(0.96f);
             const V3 vAxis = v3((vWorldM2.z * vHitNorm.y) - (vWorldM2.y * vHitNorm.z), (vWorldM2.x * vHitNorm.z) - (vWorldM2.z * vHitNorm.x), (vWorldM2.y * vHitNorm.x) - (vWorldM2.x * vHitNorm.y));
             const M33 m = axis_angle(norm(vAxis), fAngle);
             vHitNorm = v3((((m.m11 * vHitNorm.x) + (m.m21 * vHitNorm.y)) + (m.m31 * vHitNorm.z)) + 0.0f,
@@ -347,12 +347,12 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
         V3 contactPoint = vHitPos; const V3 contactNormal = vHitNorm;
         if (surf.sinHeight != 0.0f) {
             const float L = surf.sinLength;
-            contactPoint.y -= (((sinf(L * contactPoint.x) * cosf(L * contactPoint.z)) + 1.0f) * surf.sinHeight);
+            contactPoint.y -= (((m_sin(L * contactPoint.x) * m_cos(L * contactPoint.z)) + 1.0f) * surf.sinHeight);
         }
         if (surf.granularity != 0.0f) {
             const float v1[3] = {1.0f, 5.8f, 11.4f}; const float v2[3] = {0.005f, 0.005f, 0.01f};
             const float cx = contactPoint.x, cz = contactPoint.z; float cy = contactPoint.y;
-            for (int id = 0; id < 3; ++id) { const float v = v1[id]; cy = cy + ((((sinf(v * cx) * cosf(v * cz)) + 1.0f) * v2[id]) * -0.6f); }
+            for (int id = 0; id < 3; ++id) { const float v = v1[id]; cy = cy + ((((m_sin(v * cx) * m_cos(v * cz)) + 1.0f) * v2[id]) * -0.6f); }
             contactPoint.y = cy;
         }
         t.contactX = contactPoint.x; t.contactY = contactPoint.y; t.contactZ = contactPoint.z;
@@ -401,7 +401,7 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
             float fSlipRatioTmp = ((fRoadVelocityXAbs == 0.0f) ? 0.0f : (t.slidingVelocityX / fRoadVelocityXAbs));
             { /* calcCamberRAD (TyreUtils.inl:14-21) */
                 const float f = ((hubFrame.ax.y * contactNormal.y) + (hubFrame.ax.x * contactNormal.x)) + (hubFrame.ax.z * contactNormal.z);
-                t.camberRAD = (f <= -1.0f || f >= 1.0f) ? -1.5707964f : -asinf(f);
+                t.camberRAD = (f <= -1.0f || f >= 1.0f) ? -1.5707964f : -m_asin(f);
             }
             t.totalHubVelocity = sqrtf((roadVelocityX * roadVelocityX) + (t.slidingVelocityY * t.slidingVelocityY));
             const float fNdSlip = tclampf(t.ndSlip, 0.0f, 1.0f);
@@ -599,7 +599,7 @@ PD_HD void aero_step(const PdCarParams& PP, Body& C) {
             if (W.isVertical) { fAngleOff = yawAngle; fAxis = lv.x; } else { fAngleOff = aoa; fAxis = lv.y; }
             float cl = curve_value(W.lutAOA_CL, (W.angleMult * W.angle) + fAngleOff) * W.clGain;
             if (lv.z < 0.0f) cl = 0;
-            if (!W.isVertical && W.yawGain != 0.0f) { const float v8 = (sinf(fabsf(yawAngle) * 0.017453f) * W.yawGain) + 1.0f; cl *= tclampf(v8, 0.0f, 1.0f); }
+            if (!W.isVertical && W.yawGain != 0.0f) { const float v8 = (m_sin(fabsf(yawAngle) * 0.017453f) * W.yawGain) + 1.0f; cl *= tclampf(v8, 0.0f, 1.0f); }
             const float fDot = (fAxis * fAxis) + (lv.z * lv.z);
             const float fLift = (((fDot * cl) * PP.airDensity) * W.area) * 0.5f;
             if (fDot != 0.0f) {
@@ -794,7 +794,7 @@ PD_HD void engine_step(const PdCarParams& PP, CarCtx& X, float gasInput, float r
     if (c.fuelPressure > 0.0f) {
         if (rpm >= (float)E.minimum) {
             if (E.overlapGain != 0.0f) {
-                const float fOverlap = sinf((float)X.time * 0.001f * E.overlapFreq * rpm * 0.0003333333333333333f) * 0.5f - 0.5f;
+                const float fOverlap = m_sin((float)X.time * 0.001f * E.overlapFreq * rpm * 0.0003333333333333333f) * 0.5f - 0.5f;
                 outTorque = (fOverlap * fabsf(rpm - E.overlapIdealRPM) * E.overlapGain) + fOutTorq;
             }
         } else if (E.isEngineStallEnabled) outTorque = rpm * -0.01f;
@@ -825,7 +825,7 @@ PD_HDN float drivetrain_step(const PdCarParams& PP, CarCtx& X) {
     CarS& c = X.c; const PdDrivetrain& D = PP.drivetrain; const float dt = X.dt;
     const int dl = (D.tractionType == 1) ? 0 : 2, dr = dl + 1;
     WheelLink& tl = X.wl[dl]; WheelLink& tr = X.wl[dr];
-    c.locClutch = powf(c.ctlClutch, 1.5f);
+    c.locClutch = m_pow(c.ctlClutch, 1.5f);
     c.currentClutchTorque = 0;
     const int iGearRequest = c.reqRequest - 1;
     if ((!iGearRequest || iGearRequest == 1) && (c.reqTimeout < c.reqTimeAcc)) { c.currentGear = c.reqGear; c.reqRequest = 0; }

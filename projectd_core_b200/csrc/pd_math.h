@@ -28,6 +28,17 @@
 
 namespace pd {
 
+/* out-of-line copies of the math-library functions: every inlined call site would carry its own copy of the slow path
+ * (argument reduction etc.), and this kernel is instruction-fetch sensitive */
+PD_HDN float m_sin(float x) { return sinf(x); }
+PD_HDN float m_cos(float x) { return cosf(x); }
+PD_HDN float m_tan(float x) { return tanf(x); }
+PD_HDN float m_pow(float x, float y) { return powf(x, y); }
+PD_HDN float m_acos(float x) { return acosf(x); }
+PD_HDN float m_asin(float x) { return asinf(x); }
+PD_HDN float m_atan2(float y, float x) { return atan2f(y, x); }
+
+
 struct V3 {
     float x, y, z;
 };
@@ -149,7 +160,7 @@ PD_HD Quat qmul2(Quat b, Quat c) {
 /* mat44f::createFromAxisAngle (Core/Math.cpp:88-117) applied to a vector as `v * M` (row vector, no translation) */
 struct M33 { float m11, m12, m13, m21, m22, m23, m31, m32, m33; };
 PD_HD M33 axis_angle(V3 a, float angle) {
-    M33 r; float s = sinf(angle), c = cosf(angle), o = 1.0f - c;
+    M33 r; float s = m_sin(angle), c = m_cos(angle), o = 1.0f - c;
     r.m11 = ((a.x * a.x) * o) + c; r.m22 = ((a.y * a.y) * o) + c; r.m33 = ((a.z * a.z) * o) + c;
     r.m12 = (a.z * s) + (a.y * a.x) * o; r.m23 = (a.x * s) + (a.z * a.y) * o; r.m31 = (a.y * s) + (a.z * a.x) * o;
     r.m13 = (a.z * a.x) * o - (a.y * s); r.m21 = (a.y * a.x) * o - (a.z * s); r.m32 = (a.z * a.y) * o - (a.x * s);

@@ -37,8 +37,8 @@ PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
     }
 }
 
-template <int STRIDE, class Ex, class SVX>
-PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch) {
+template <int STRIDE, int STRIDE_D, class Ex, class SVX>
+PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD) {
     const int lane = ex.lane;
     const bool front = lane < 2;
     /* Car-level state: with a stride-1 view (the shared-memory staging copy) the four lanes work IN PLACE on the
@@ -179,7 +179,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
-    GScr<STRIDE> G; G.bind(scratch);
+    GScr<STRIDE, STRIDE_D> G; G.bind(scratch, scratchD);
     if (front) build_strut(P, P.strut[lane], C, W, S, steerA1, steerA2, hinv, X.dballErp, X.dballCfm, G);
     else if (lane == 2) build_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G);
     else build_tank(P, S, C, hinv, G);

@@ -116,22 +116,22 @@ PD_HD void plane_space(V3 n, V3& p, V3& q) {
  *   - a plain local array (host debugging build, stride 1).
  * Every group is padded to PD_GMAX = 11 rows (pad rows: zero Jacobians, unit diagonal) so that the four lanes of
  * a quad run the same straight-line code whatever their group's real size (11 / 11 / 5 / 6 rows).
- * Layout (words): JA 11x6 | JB 11x6 | Y 11x7 ([U | c], then [U | r], then L^-1[U | r]; column 6 ends as lambda) |
- * D packed lower 66 (in place: unit-lower L below the diagonal) | dg 11 (cfm per row, then the D diagonal). */
+ * Layout (words): rows part JA 11x6 | JB 11x6;  D part Y 11x7 ([U | c], then [U | r], then L^-1[U | r]; column 6 ends
+ * as lambda) | D packed lower 66 (in place: unit-lower L below the diagonal) | dg 11 (cfm per row, then the D diagonal). */
 #define PD_GSCR_WORDS 286
-#define PD_GSCR_ROWS_WORDS 209   /* JA | JB | Y */
-#define PD_GSCR_D_WORDS 77       /* D | dg : the part every phase of the factorisation re-reads */
-/* S: stride of the JA | JB | Y part at p;  SD: stride of the D | dg part at q (the thread-per-car kernel keeps the
- * first part in local memory, stride 1, and the second in shared memory, lane-interleaved) */
+#define PD_GSCR_ROWS_WORDS 132   /* JA | JB : read by the D build and by the final J^T lambda */
+#define PD_GSCR_D_WORDS 154      /* Y | D | dg : what the factorisation and the substitutions work on */
+/* S: stride of the JA | JB part at p;  SD: stride of the Y | D | dg part at q.  The two parts may live in different
+ * memories (e.g. rows in local memory, stride 1, and the rest in shared memory, lane-interleaved). */
 template <int S, int SD = S> struct GScr {
     float* p; float* q;
     PD_HD void bind(float* base) { p = base; q = base + PD_GSCR_ROWS_WORDS * S; }          /* one contiguous scratch */
     PD_HD void bind(float* rows, float* dpart) { p = rows; q = dpart; }
     PD_HD float& JA(int i, int k) const { return p[(i * 6 + k) * S]; }
     PD_HD float& JB(int i, int k) const { return p[(66 + i * 6 + k) * S]; }
-    PD_HD float& Y(int i, int k) const { return p[(132 + i * 7 + k) * S]; }
-    PD_HD float& D(int i, int j) const { return q[(i * (i + 1) / 2 + j) * SD]; }   /* j <= i */
-    PD_HD float& dg(int i) const { return q[(66 + i) * SD]; }
+    PD_HD float& Y(int i, int k) const { return q[(i * 7 + k) * SD]; }
+    PD_HD float& D(int i, int j) const { return q[(77 + i * (i + 1) / 2 + j) * SD]; }   /* j <= i */
+    PD_HD float& dg(int i) const { return q[(143 + i) * SD]; }
 };
 /* all rows zero; pad rows get cfm = h so that their diagonal becomes cfm/h = 1 */
 template <class GS> PD_HD void zero_group(const GS& G, int n, float cfm, float h) {
@@ -367,8 +367,8 @@ PD_HD void integrate_body(Body& b, float h) {
     const float wlen = sqrtf(b.w.x * b.w.x + b.w.y * b.w.y + b.w.z * b.w.z);
     h *= 0.5f;
     const float theta = wlen * h;
-    Quat q; q.w = cosf(theta);
-    const float sinc = (fabsf(theta) < 1.0e-4f) ? 1.0f - theta * theta * 0.166666666666666666667f : sinf(theta) / theta;
+    Quat q; q.w = m_cos(theta);
+    const float sinc = (fabsf(theta) < 1.0e-4f) ? 1.0f - theta * theta * 0.166666666666666666667f : m_sin(theta) / theta;
     const float s = sinc * h;
     q.x = b.w.x * s; q.y = b.w.y * s; q.z = b.w.z * s;
     Quat q2 = qmul0(q, b.q);

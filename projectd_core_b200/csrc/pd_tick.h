@@ -24,7 +24,7 @@ PD_HD float beta_rad(const Body& C) {
     const float fLen = len(vel);
     if (fLen != 0.0f) vel.x /= fLen;
     if (vel.x <= -1.0f || vel.x >= 1.0f) return 1.5707964f;
-    return asinf(vel.x);
+    return m_asin(vel.x);
 }
 
 /* state of a freshly constructed car (Car::init, Car.cpp:31-223, and the constructors it runs): chassis at the
@@ -157,7 +157,7 @@ PD_HD void post_lookahead(const PdCarParams& P, const TrackDev& T, const Body& C
         for (int i = 0; i < P.lookAheadCount && i < PD_LOOKAHEAD; ++i) {
             const float distanceNorm = c.trackLocation + ((P.lookAheadStep * (float)(i + 1)) / T.info.computedTrackLength) * driveDir;
             const V3 dir = track_direction_at_distance(T, distanceNorm);
-            c.lookAhead[i] = atan2f(dot(cross(dir, curTrackDir), up), dot(curTrackDir, dir));
+            c.lookAhead[i] = m_atan2(dot(cross(dir, curTrackDir), up), dot(curTrackDir, dir));
         }
     }
 }

@@ -66,7 +66,7 @@ void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
     std::vector<uint32_t> copy[4];
     for (int l = 0; l < 4; ++l) copy[l].assign(rec, rec + PD_STATE_WORDS);
     std::thread th[4];
-    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SVFlat sv = pd::sv_flat(copy[l].data()); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1>(h->car.P, h->dev, sv, dt, time, ex, scr); });
+    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SVFlat sv = pd::sv_flat(copy[l].data()); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1, 1>(h->car.P, h->dev, sv, dt, time, ex, scr, scr + PD_GSCR_ROWS_WORDS); });
     for (int l = 0; l < 4; ++l) th[l].join();
     pthread_barrier_destroy(&sh.bar);
     auto take = [&](int lane, int off, int words) { memcpy(rec + off, copy[lane].data() + off, (size_t)words * 4); };
