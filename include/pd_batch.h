@@ -45,6 +45,10 @@ typedef struct pd_batch pd_batch;
 #define PD_DONE_LOWREWARD  8
 #define PD_DONE_NAN       16
 
+/* when pd_env_step resets a finished env (see pd_set_autoreset) */
+#define PD_AUTORESET_SAME_STEP 0   /* inside the step that finished it (what SB3's VecEnv does around ProjectDEnv): 3 launches */
+#define PD_AUTORESET_NEXT_STEP 1   /* at the following step, whose action is ignored (gymnasium >= 1.0 VectorEnv): 1 launch */
+
 /* createSimulator + loadTrack + addCar for n_envs environments
  * (PyProjectD.cpp:111-137 createSimulator, :186-203 loadTrack, :219-237 addCar; Simulator::init
  * Sim/Simulator.cpp:22-90, Track::init Sim/Track.cpp:27-50, Car::init Car/Car.cpp:31-223).
@@ -88,7 +92,7 @@ int pd_set_time(pd_batch* b, double t);
  * PD_TELEPORT_RANDOM draws u ~ U[0,1) from a counter-based generator keyed by (seed, global env id) so that
  * results do not depend on how envs are sharded over GPUs (the reference uses the process-global rand()). */
 int pd_teleport_spline(pd_batch* b, const uint8_t* mask, const float* dist_norm);
-int pd_teleport_mode(pd_batch* b, const uint8_t* mask, int mode);
+int pd_teleport_mode(pd_batch* b, const uint8_t* mask, int mode);   /* `mode` also becomes the mode of pd_env_step's automatic resets (ProjectDEnv.teleport_mode, projectd_env.py:39,219) */
 int pd_set_seed(pd_batch* b, uint64_t seed, uint64_t env_id_offset);   /* setSeed (PyProjectD.cpp:50-53) */
 
 /* getCarState (PyProjectD.cpp:319-326): fills one 664-byte CarState (Car/CarState.h:11-56 layout) */
@@ -108,6 +112,13 @@ int pd_get_rewards(pd_batch* b, float* step_reward, float* total_reward, int32_t
  * (teleport by `PD_TELEPORT_*` mode + one zero-action tick, projectd_env.py:216-227) of finished envs.
  * actions / obs / reward / done are DEVICE pointers (obs may be NULL to use the internal buffer). */
 int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev, float* reward_dev, int32_t* done_dev);
+/* Auto-reset convention of pd_env_step.  PD_AUTORESET_SAME_STEP (default): a finished env is teleported and
+ * advanced by the reset's zero-action tick right after the step that finished it; obs then holds the reset
+ * observation (the reference env driven through a same-step auto-resetting vector wrapper).
+ * PD_AUTORESET_NEXT_STEP: the step that finishes an env returns its terminal observation with done != 0; the
+ * NEXT pd_env_step ignores that env's action, performs the reset (teleport + zero-action tick) inside the same
+ * kernel launch as everybody else's tick and returns the reset observation with reward 0 and done 0. */
+int pd_set_autoreset(pd_batch* b, int mode);
 /* The same step for a caller that lives on the host (what ProjectDEnv.step is to a Python user): actions[n_envs][2]
  * are copied host -> device, obs[n_envs][24] / reward[n_envs] / done[n_envs] device -> host, all on the batch's
  * stream, one synchronisation at the end.  Pinned (page-locked) host buffers make the copies asynchronous;
@@ -128,6 +139,10 @@ int pd_get_track_info(const pd_batch* b, PdTrackInfo* out);
 /* batch ray cast against the track BVH (IPhysicsEngine::rayCast, Physics/IPhysicsEngine.h:24):
  * rays[n][7] = origin, direction, length -> out[n][8] = hit, pos, normal, surface index.  Host pointers. */
 int pd_raycast(pd_batch* b, int n, const float* rays, float* out);
+
+/* profiling aid: SM cycles every warp spent in the last full tick launch (batch created with env PD_DEBUG_CLOCKS=1);
+ * returns the number of entries written (0 when disabled) */
+int pd_debug_read_clocks(pd_batch* b, long long* out, int cap);
 
 int pd_sync(pd_batch* b);
 void* pd_stream(pd_batch* b);                        /* the cudaStream_t every kernel of this batch runs on */

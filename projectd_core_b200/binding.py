@@ -74,6 +74,8 @@ def load_library():
         "pd_env_step_host": (i, [vp, vp, f, vp, vp, vp]),
         "pd_tick_kernel": (ctypes.c_char_p, [vp]),
         "pd_env_stats": (i, [vp, vp, i]),
+        "pd_set_autoreset": (i, [vp, i]),
+        "pd_debug_read_clocks": (i, [vp, vp, i]),
         "pd_get_state": (i, [vp, i, vp]),
         "pd_set_state": (i, [vp, i, vp]),
         "pd_snapshot": (i, [vp, vp]),
@@ -203,6 +205,15 @@ class Batch:
         """One env step for host-resident buffers (numpy arrays or CPU torch tensors, ideally pinned):
         H2D actions, step, D2H obs / reward / done, one stream sync."""
         self._ck(self.L.pd_env_step_host(self.h, _ptr(actions), float(dt), _ptr(obs), _ptr(reward), _ptr(done)))
+
+    def set_autoreset(self, mode):
+        """0 = same step (3 launches per env step), 1 = next step (1 launch; gymnasium >= 1.0 VectorEnv convention)."""
+        self._ck(self.L.pd_set_autoreset(self.h, int(mode)))
+
+    def debug_warp_clocks(self):
+        out = np.zeros(self.n // 4 + 64, dtype=np.int64)
+        cnt = self.L.pd_debug_read_clocks(self.h, out.ctypes.data, out.size)
+        return out[:cnt]
 
     def env_stats(self, reset=True):
         out = np.zeros(8, dtype=np.float64)

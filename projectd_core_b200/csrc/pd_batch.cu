@@ -30,7 +30,6 @@ using namespace pd;
 #define PD_SERIAL_SMEM_SCRATCH 0   /* thread-per-car kernel: D | dg part of the solver scratch in shared memory (1) or everything in local memory (0); measured equal at 65536 envs (0.884 ms), 0 is 8 % faster at 16384 */
 #endif
 #define PD_QBLOCK 64   /* threads per block of the quad kernel = stride of the lane-interleaved solver scratch */
-#define PD_QCARS (PD_QBLOCK / 4)
 
 /* ------------------------------------------------------------------ kernels ------------------------------------------------------------------ */
 /* Optional env-step work fused into the tick kernels (null pointers: skipped).
@@ -41,9 +40,31 @@ struct EnvIO {
     const float* act; float* obs;
     float* reward; int32_t* done; float* envReturn; int32_t* envLen; double* stats;
     double timeAfter;
+    /* PD_AUTORESET_NEXT_STEP: an env that finished at step t is reset INSIDE the tick kernel of step t+1
+     * (teleport + the reset's zero-action tick, projectd_env.py:216-227), its action of that step is ignored */
+    int32_t* pending;            /* [n] 1 = finished at the previous step (null: no in-kernel reset) */
+    uint32_t* episodeCtr; uint64_t seed, idOffset; int teleportMode;
+    long long* clk;              /* profiling aid (PD_DEBUG_CLOCKS=1): SM cycles each warp spent in the tick, [blocks * 2]; null otherwise */
 };
 
-template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv, int e, bool on, const EnvIO& io, unsigned warpMask) {
+/* counter-based uniform in [0,1): splitmix64 of (seed, global env id, episode counter) */
+__host__ __device__ inline float pd_uniform(uint64_t seed, uint64_t id, uint64_t ctr) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (id * 0x100000001B3ull + ctr + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+/* the reset of one env inside a tick kernel (one thread): teleportCarByMode + the zero action of ProjectDEnv.reset */
+template <class SVX> __device__ __noinline__ void env_reset_in_kernel(const PdCarParams& P, const TrackDev& T, const SVX& sv, int e, const EnvIO& io, double time) {
+    float u = 0.0f;
+    if (io.teleportMode == PD_TELEPORT_NEAREST) u = sv.f(PD_OFF_CAR + PD_CAR_o_trackLocation);
+    else if (io.teleportMode == PD_TELEPORT_RANDOM) { u = pd_uniform(io.seed, io.idOffset + (uint64_t)e, io.episodeCtr[e]); io.episodeCtr[e]++; }
+    car_teleport_to_point(P, T, sv, point_id_at_distance(T, u), time);
+    sv.i(PD_OFF_CAR + PD_CAR_o_nanFlag, 0);
+    env_apply_action(sv, 0.0f, 0.0f);
+}
+
+template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv, int e, bool on, const EnvIO& io, unsigned warpMask, bool resetNow = false) {
     if (on && io.obs) {
         float o[PD_OBS_DIM];
         car_observe(sv, o);
@@ -53,7 +74,9 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
     }
     if (!io.reward) return;
     double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (on) {
+    if (on && resetNow) {      /* the reset's own step: ProjectDEnv.reset returns the observation only and zeroes the episode counters */
+        io.reward[e] = 0.0f; io.done[e] = 0; io.envReturn[e] = 0; io.envLen[e] = 0; io.pending[e] = 0;
+    } else if (on) {
         float r; int d;
         env_reward_done(sv, io.timeAfter, r, d);
         const float ret = io.envReturn[e] + r; const int len = io.envLen[e] + 1;
@@ -64,6 +87,7 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
             s[3] = (d & PD_DONE_COLLISION) ? 1 : 0; s[4] = (d & PD_DONE_OFFTRACK) ? 1 : 0; s[5] = (d & PD_DONE_STUCK) ? 1 : 0;
             s[6] = (d & PD_DONE_LOWREWARD) ? 1 : 0; s[7] = (d & PD_DONE_NAN) ? 1 : 0;
             io.envReturn[e] = 0; io.envLen[e] = 0;
+            if (io.pending) io.pending[e] = 1;
         } else { io.envReturn[e] = ret; io.envLen[e] = len; }
     }
     /* warp-level reduction, one atomic per warp and statistic */
@@ -80,6 +104,7 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
 /* the tick, one thread per car, tiled structure-of-arrays state (batches above the quad threshold) */
 __global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                    const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
+    const long long clk0 = io.clk ? clock64() : 0;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = e < n && (!mask || mask[e]);
     SVTile sv = sv_tiled(state, (size_t)(e < n ? e : 0));
@@ -91,15 +116,18 @@ __global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ Pd
 #else
     float pd_rows[PD_GSCR_WORDS];
 #endif
+    const bool resetNow = on && io.pending && io.pending[e];
     if (on) {
-        if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
+        if (resetNow) env_reset_in_kernel(P, T, sv, e, io, time);
+        else if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
 #if PD_SERIAL_SMEM_SCRATCH
         car_tick<1, PD_BLOCK>(P, T, sv, dt, time, pd_rows, pd_scrD + threadIdx.x);
 #else
         car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows + PD_GSCR_ROWS_WORDS);
 #endif
     }
-    env_epilogue(sv, e, on, io, 0xffffffffu);
+    if (io.clk && (threadIdx.x & 31) == 0) io.clk[blockIdx.x * (PD_BLOCK / 32) + (threadIdx.x >> 5)] = clock64() - clk0;
+    env_epilogue(sv, e, on, io, 0xffffffffu, resetNow);
 }
 
 /* exchange policy of pd_quad.h on the GPU: shuffles inside the quad, with the quad's own member mask */
@@ -134,22 +162,31 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #ifndef PD_QUAD_LOCAL_SCRATCH
 #define PD_QUAD_LOCAL_SCRATCH 0   /* solver scratch of the quad kernel: 0 = shared memory, 1 = local memory, 2 = JA | JB local, Y | D | dg shared */
 #endif
-#define PD_QUAD_SMEM_BYTES (PD_QCARS * PD_STATE_STRIDE * 4 + 16 + (PD_QUAD_LOCAL_SCRATCH == 1 ? 0 : PD_QUAD_LOCAL_SCRATCH == 2 ? PD_QBLOCK * PD_GSCR_D_WORDS * 4 : PD_QBLOCK * PD_GSCR_WORDS * 4))
+/* shared memory of one block of the quad kernel with CPW cars per warp: 2*CPW records | mbarrier | scratch of 8*CPW lanes */
+#define PD_QUAD_SMEM_BYTES_(CPW) (2 * (CPW) * PD_STATE_STRIDE * 4 + 16 + (PD_QUAD_LOCAL_SCRATCH == 1 ? 0 : PD_QUAD_LOCAL_SCRATCH == 2 ? 8 * (CPW) * PD_GSCR_D_WORDS * 4 : 8 * (CPW) * PD_GSCR_WORDS * 4))
 
 /* the tick, four lanes per car, array-of-records state staged through shared memory:
- * block = 64 threads = 16 cars; ONE bulk copy brings the block's 16 records (40 KB) in, the quads work on the
- * shared-memory copy (thread t -> car t / 4, lane t % 4), ONE bulk copy writes them back. */
+ * block = 64 threads = 2 warps, CPW cars per warp (8: every lane busy, throughput; 4 or 2: half / quarter-filled warps
+ * = more warps per car batch, for batches too small to fill the 592 warp schedulers of a B200 otherwise).
+ * ONE bulk copy brings the block's records in, the quads work on the shared-memory copy, ONE bulk copy writes them back. */
+template <int CPW>
 __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                          const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
+    constexpr int QCARS = 2 * CPW;          /* cars per block */
+    constexpr int QLANES = 8 * CPW;         /* working threads per block = stride of the lane-interleaved solver scratch */
     extern __shared__ __align__(128) uint32_t pd_smem[];
-    uint32_t* recs = pd_smem;                                                         /* [16][PD_STATE_STRIDE] */
-    uint64_t* bar = reinterpret_cast<uint64_t*>(pd_smem + PD_QCARS * PD_STATE_STRIDE);
-    float* scratch = reinterpret_cast<float*>(pd_smem + PD_QCARS * PD_STATE_STRIDE + 4);  /* [PD_GSCR_WORDS][64], lane-interleaved */
+    uint32_t* recs = pd_smem;                                                         /* [QCARS][PD_STATE_STRIDE] */
+    uint64_t* bar = reinterpret_cast<uint64_t*>(pd_smem + QCARS * PD_STATE_STRIDE);
+    float* scratch = reinterpret_cast<float*>(pd_smem + QCARS * PD_STATE_STRIDE + 4);  /* [PD_GSCR_WORDS][QLANES], lane-interleaved */
+    const long long clk0 = io.clk ? clock64() : 0;
     const int tid = threadIdx.x;
-    const int car0 = blockIdx.x * PD_QCARS;
-    const int ncars = min(PD_QCARS, n - car0);
-    const int car = tid >> 2, e = car0 + car;
-    const bool on = car < ncars && (!mask || mask[e]);
+    const int wl = tid & 31, warp = tid >> 5;
+    const bool worker = wl < 4 * CPW;                            /* lanes beyond the warp's cars only help with the block-level steps */
+    const int cid = warp * (4 * CPW) + (worker ? wl : 0);        /* compact index of a working lane */
+    const int car0 = blockIdx.x * QCARS;
+    const int ncars = min(QCARS, n - car0);
+    const int car = cid >> 2, e = car0 + car;
+    const bool on = worker && car < ncars && (!mask || mask[e]);
     if (mask && !__syncthreads_or(on)) return;                 /* reset pass: nothing to do for this block */
     const uint32_t bytes = (uint32_t)ncars * PD_STATE_STRIDE * 4;
     uint32_t* gsrc = state + (size_t)car0 * PD_STATE_STRIDE;
@@ -160,26 +197,29 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
     uint32_t* rec = recs + car * PD_STATE_STRIDE;
     SVFlat sv = sv_flat(rec);
     if (on) {
-        QuadShfl ex; ex.lane = tid & 3; ex.base = (tid & 31) & ~3; ex.mask = 0xFu << ex.base;
-        if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
+        QuadShfl ex; ex.lane = wl & 3; ex.base = wl & ~3; ex.mask = 0xFu << ex.base;
+        if (io.pending && io.pending[e]) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
+        else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
 #if PD_QUAD_LOCAL_SCRATCH == 1
         float lscr[PD_GSCR_WORDS];
         car_tick_quad<1, 1>(P, T, sv, dt, time, ex, lscr, lscr + PD_GSCR_ROWS_WORDS);
 #elif PD_QUAD_LOCAL_SCRATCH == 2
         float lrows[PD_GSCR_ROWS_WORDS];                     /* JA | JB in local memory, Y | D | dg in shared memory */
-        car_tick_quad<1, PD_QBLOCK>(P, T, sv, dt, time, ex, lrows, scratch + tid);
+        car_tick_quad<1, QLANES>(P, T, sv, dt, time, ex, lrows, scratch + cid);
 #else
-        car_tick_quad<PD_QBLOCK, PD_QBLOCK>(P, T, sv, dt, time, ex, scratch + tid, scratch + PD_GSCR_ROWS_WORDS * PD_QBLOCK + tid);
+        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid);
 #endif
     }
+    if (io.clk && wl == 0) io.clk[blockIdx.x * 2 + warp] = clock64() - clk0;
     fence_async_smem();                                        /* generic-proxy writes -> visible to the bulk copy engine */
     __syncthreads();
     if (tid == 32) { bulk_s2g(gsrc, recs, bytes); }
     if (tid < 32) {                                            /* warp 0: one thread per car of the block */
         const int c2 = tid, e2 = car0 + c2;
         const bool on2 = c2 < ncars && (!mask || mask[e2]);
-        SVFlat sv2 = sv_flat(recs + (c2 < PD_QCARS ? c2 : 0) * PD_STATE_STRIDE);
-        env_epilogue(sv2, e2, on2 && c2 < PD_QCARS, io, 0xffffffffu);
+        SVFlat sv2 = sv_flat(recs + (c2 < QCARS ? c2 : 0) * PD_STATE_STRIDE);
+        const bool reset2 = on2 && io.pending && io.pending[e2];     /* read before the epilogue clears it; the quads read it before the block barrier above */
+        env_epilogue(sv2, e2, on2, io, 0xffffffffu, reset2);
     }
     if (tid == 32) bulk_wait_all();                            /* the copy engine has read (and written) everything before the block retires */
 }
@@ -192,22 +232,16 @@ __global__ void k_broadcast(uint32_t* state, int layout, size_t nAlloc, const ui
     else state[i] = rec[(i / PD_TILE) % PD_STATE_WORDS];
 }
 
-/* counter-based uniform in [0,1): splitmix64 of (seed, global env id, episode counter) */
-__host__ __device__ inline float pd_uniform(uint64_t seed, uint64_t id, uint64_t ctr) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (id * 0x100000001B3ull + ctr + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z = z ^ (z >> 31);
-    return (float)(z >> 40) * (1.0f / 16777216.0f);
-}
-
 /* Teleport (reset path): choose the spline point by mode (Car::teleportByMode, Car.cpp:1342-1358)
  * and re-seat the car there (Car::teleportToSpline); zeroAction: also write the reset's zero action and clear the
  * NaN guard (auto-reset inside pd_env_step, projectd_env.py:216-227). */
 __global__ void __launch_bounds__(PD_BLOCK) k_teleport(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int layout, int n, const int32_t* __restrict__ mask,
                                                        int mode, const float* __restrict__ distNorm, uint64_t seed, uint64_t idOffset, uint32_t* __restrict__ episodeCtr,
-                                                       double time, int zeroAction) {
+                                                       double time, int zeroAction, int32_t* __restrict__ pending) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (mask && !mask[e]) return;
+    if (pending) pending[e] = 0;      /* an explicit teleport supersedes a reset that was still due */
     SVR sv = sv_env(layout, state, (size_t)e);
     float u = 0.0f;
     if (distNorm) u = distNorm[e];
@@ -314,9 +348,13 @@ struct pd_batch {
     int32_t* dMask = nullptr; int32_t* dPoints = nullptr; float* dDist = nullptr; uint32_t* dEpisodeCtr = nullptr;
     float* dReward = nullptr; float* dTotal = nullptr; int32_t* dFlags = nullptr; int32_t* dDone = nullptr;
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
+    long long* dClk = nullptr; int nClk = 0;
+    int32_t* dPending = nullptr; int autoreset = PD_AUTORESET_SAME_STEP;
+    int resetMode = PD_TELEPORT_START;   /* ProjectDEnv.teleport_mode: the last pd_teleport_mode() mode, also used by the automatic resets */
     double time = 0, lastDt = 0;
     uint64_t seed = 0, idOffset = 0, launches = 0;
     int layout = PD_LAYOUT_TILED;     /* PD_LAYOUT_RECORDS when the 4-lanes-per-car kernel owns the batch */
+    int quadCpw = 8;                  /* cars per warp of the quad kernel (8 / 4 / 2), chosen at creation from the batch size */
     int quadMax = PD_QUAD_MAX_ENVS;   /* kernel dispatch threshold; env PD_QUAD_MAX_ENVS overrides (tuning / profiling) */
     std::string err;
     int64_t dlShape[2] = {0, 0};
@@ -357,7 +395,14 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     b->n = n_envs; b->device = device;
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    CK(cudaFuncSetAttribute(k_tick_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
+    CK(cudaFuncSetAttribute(k_tick_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
+    CK(cudaFuncSetAttribute(k_tick_quad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(2)));
+    /* cars per warp of the quad kernel: as few as still fit the batch into ONE wave of resident blocks
+       (168 registers x 64 threads -> 6 blocks per SM; shared memory allows 2 / 4 / 8 blocks for 8 / 4 / 2 cars per warp) */
+    { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); const int sms = prop.multiProcessorCount;
+      b->quadCpw = (n_envs <= sms * 6 * 4) ? 2 : (n_envs <= sms * 4 * 8) ? 4 : 8;
+      if (const char* q = getenv("PD_QUAD_CPW")) { const int v = atoi(q); if (v == 2 || v == 4 || v == 8) b->quadCpw = v; } }
     b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
     int rc;
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
@@ -397,6 +442,9 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = dalloc(b, &b->dEnvReturn, n))) return rc;
     if ((rc = dalloc(b, &b->dEnvLen, n))) return rc;
     if ((rc = dalloc(b, &b->dStats, 8))) return rc;
+    if ((rc = dalloc(b, &b->dPending, n))) return rc;
+    CK(cudaMemsetAsync(b->dPending, 0, n * 4, b->stream));
+    if (getenv("PD_DEBUG_CLOCKS")) { b->nClk = (int)(n / 4 + 64); if ((rc = dalloc(b, &b->dClk, (size_t)b->nClk))) return rc; CK(cudaMemsetAsync(b->dClk, 0, (size_t)b->nClk * 8, b->stream)); }
     CK(cudaMemsetAsync(b->dEpisodeCtr, 0, n * 4, b->stream));
     CK(cudaMemsetAsync(b->dEnvReturn, 0, n * 4, b->stream));
     CK(cudaMemsetAsync(b->dEnvLen, 0, n * 4, b->stream));
@@ -414,9 +462,14 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     return PD_OK;
 }
 
-static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO& io) {
+static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO& io_in) {
+    EnvIO io = io_in; io.clk = mask ? nullptr : b->dClk;
     if (b->layout == PD_LAYOUT_RECORDS)
-        k_tick_quad<<<grid(b->n, PD_QCARS), PD_QBLOCK, PD_QUAD_SMEM_BYTES, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+        switch (b->quadCpw) {
+        case 2: k_tick_quad<2><<<grid(b->n, 4), PD_QBLOCK, PD_QUAD_SMEM_BYTES_(2), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        case 4: k_tick_quad<4><<<grid(b->n, 8), PD_QBLOCK, PD_QUAD_SMEM_BYTES_(4), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        default: k_tick_quad<8><<<grid(b->n, 16), PD_QBLOCK, PD_QUAD_SMEM_BYTES_(8), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        }
     else
         k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     b->launches++;
@@ -524,7 +577,7 @@ static int teleport_common(pd_batch* b, const uint8_t* mask, int mode, const flo
     }
     const float* dd = nullptr;
     if (dist_norm) { CK(cudaMemcpyAsync(b->dDist, dist_norm, (size_t)b->n * 4, cudaMemcpyHostToDevice, b->stream)); dd = b->dDist; }
-    k_teleport<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, b->n, dm, mode, dd, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 0); b->launches++;
+    k_teleport<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, b->n, dm, mode, dd, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 0, b->dPending); b->launches++;
     CK(cudaGetLastError()); return PD_OK;
 }
 int pd_teleport_spline(pd_batch* b, const uint8_t* mask, const float* dist_norm) {
@@ -534,6 +587,7 @@ int pd_teleport_spline(pd_batch* b, const uint8_t* mask, const float* dist_norm)
 }
 int pd_teleport_mode(pd_batch* b, const uint8_t* mask, int mode) {
     if (!b || mode < 0 || mode > 2) return PD_ERR_ARG;
+    b->resetMode = mode;
     return teleport_common(b, mask, mode, nullptr);
 }
 
@@ -579,11 +633,18 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     /* 1: actions -> controls, one tick, observation, reward / done / statistics -- one launch */
     EnvIO io{}; io.act = actions_dev; io.obs = obs_dev ? obs_dev : b->dObs;
     io.reward = rew; io.done = done; io.envReturn = b->dEnvReturn; io.envLen = b->dEnvLen; io.stats = b->dStats; io.timeAfter = b->time;
+    if (b->autoreset == PD_AUTORESET_NEXT_STEP) {
+        /* ONE launch per env step: envs that finished at the previous step reset inside this tick kernel */
+        io.pending = b->dPending; io.episodeCtr = b->dEpisodeCtr; io.seed = b->seed; io.idOffset = b->idOffset; io.teleportMode = b->resetMode;
+        launch_tick(b, dt, nullptr, io);
+        b->time += (double)dt; b->lastDt = dt;
+        CK(cudaGetLastError()); return PD_OK;
+    }
     launch_tick(b, dt, nullptr, io);
     b->time += (double)dt; b->lastDt = dt;
     /* 2 + 3: auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) with the reset's zero action,
        then one tick of those envs only, refreshing their observation */
-    k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, n, done, b->car.P.teleportMode, nullptr, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 1); b->launches++;
+    k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, n, done, b->resetMode, nullptr, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 1, nullptr); b->launches++;
     EnvIO io2{}; io2.obs = io.obs;
     launch_tick(b, dt, done, io2);
     CK(cudaGetLastError()); return PD_OK;
@@ -597,6 +658,20 @@ int pd_env_step_host(pd_batch* b, const float* actions_host, float dt, float* ob
     if (reward_host) CK(cudaMemcpyAsync(reward_host, b->dReward, n * 4, cudaMemcpyDeviceToHost, b->stream));
     if (done_host) CK(cudaMemcpyAsync(done_host, b->dDone, n * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+}
+int pd_set_autoreset(pd_batch* b, int mode) {
+    if (!b || (mode != PD_AUTORESET_SAME_STEP && mode != PD_AUTORESET_NEXT_STEP)) return PD_ERR_ARG;
+    b->autoreset = mode;
+    CK(cudaMemsetAsync(b->dPending, 0, (size_t)b->n * 4, b->stream));
+    return PD_OK;
+}
+/* profiling aid: per-warp SM cycles of the last full tick launch (only when the batch was created with PD_DEBUG_CLOCKS=1) */
+int pd_debug_read_clocks(pd_batch* b, long long* out, int cap) {
+    if (!b || !out || !b->dClk) return 0;
+    const int blocks = b->layout == PD_LAYOUT_RECORDS ? grid(b->n, 2 * b->quadCpw) : grid(b->n, PD_BLOCK);
+    int cnt = blocks * 2; if (cnt > cap) cnt = cap; if (cnt > b->nClk) cnt = b->nClk;
+    if (cudaMemcpyAsync(out, b->dClk, (size_t)cnt * 8, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess) return 0;
+    return cnt;
 }
 int pd_env_stats(pd_batch* b, double* out8, int reset) {
     if (!b || !out8) return PD_ERR_ARG;

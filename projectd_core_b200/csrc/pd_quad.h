@@ -234,7 +234,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
             if (!probe_walk(T, rax, raz, rbx[k], rbz[k], cachePos, nearRSq, pr[k])) needBrute = true;
         }
         int bestPoint = 0;
-        const bool haveNearest = nearest_point_grid(T, bodyPos, cachePos, nearRSq, bestPoint);
+        const bool haveNearest = nearest_point_grid_quad(T, bodyPos, cachePos, nearRSq, ex, bestPoint);
         if (!ex.all(!needBrute && haveNearest)) {
             /* exhaustive form of the reference (car far off the indexed area); every lane scans, each for its own probes */
             float bestDistSq = FLT_MAX; bestPoint = 0; pr[0] = FLT_MAX; pr[1] = FLT_MAX;
@@ -265,7 +265,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
                 int prevId2 = prevId - 1; if (prevId2 < 0) prevId2 = nFat - 1;
                 int nextId2 = nextId + 1; if (nextId2 >= nFat) nextId2 = 0;
                 int sid; float sdist;
-                if (spline_nearest(T, bodyPos, prevId2 * T.info.interpolateStep, nextId2 * T.info.interpolateStep, sid, sdist)) {
+                if (spline_nearest_quad(T, bodyPos, prevId2 * T.info.interpolateStep, nextId2 * T.info.interpolateStep, ex, sid, sdist)) {
                     c.splinePointId = sid; c.trackLocation = tclampf(sdist / T.info.computedTrackLength, 0.0f, 1.0f);
                 }
             }

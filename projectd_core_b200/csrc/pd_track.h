@@ -225,34 +225,48 @@ PD_HDN bool probe_walk(const TrackDev& T, float ax, float az, float bx, float bz
     return true;
 }
 
-/* Track::getPointIdAtLocation over the near set (Track.cpp:579-596): ring search in the point grid around
- * `pos`; falls back (returns false) when no point is found close enough to be provably the nearest. */
+/* Track::getPointIdAtLocation over the near set (Track.cpp:579-596): search of the point grid in growing square
+ * blocks of cells around `pos` (3x3, 5x5, 7x7).  A block of radius R proves its best candidate to be the global
+ * nearest as soon as that candidate is closer than the nearest point any cell OUTSIDE the block could hold
+ * (R cells + the position's offset inside its own cell); candidates are ordered by (distance, id), as the
+ * reference's ascending-id scan with a strict `>` orders them.  Cells beyond the grid hold no points.  Returns false
+ * (caller falls back to the exhaustive scan) only when nothing is found within 3 cells. */
+#define PD_NEAREST_MAX_RING 3
+PD_HD void nearest_cell_scan(const TrackDev& T, int c, V3 pos, V3 cachePos, float nearRSq, float& bestDistSq, int& best) {
+    const int k0 = T.ptStart[c], k1 = T.ptStart[c + 1];
+    for (int k = k0; k < k1; ++k) {
+#if defined(__CUDA_ARCH__)
+        const float4 r = __ldg(reinterpret_cast<const float4*>(T.ptRec) + k);
+        const V3 loc = v3(r.x, r.y, r.z); const int id = __float_as_int(r.w);
+#else
+        const float* r = T.ptRec + (size_t)k * 4;
+        const V3 loc = v3(r[0], r[1], r[2]); int id; memcpy(&id, &r[3], 4);
+#endif
+        if (!(sqlen(cachePos - loc) < nearRSq)) continue;
+        const float dsq = sqlen(loc - pos);
+        if (bestDistSq > dsq || (bestDistSq == dsq && id < best)) { bestDistSq = dsq; best = id; }
+    }
+}
 PD_HDN bool nearest_point_grid(const TrackDev& T, V3 pos, V3 cachePos, float nearRSq, int& bestPoint) {
     const PdBoundGrid& G = T.grid;
     const int cx = (int)floorf((pos.x - G.ox) * G.invCell), cz = (int)floorf((pos.z - G.oz) * G.invCell);
-    if (cx < 1 || cz < 1 || cx >= G.nx - 1 || cz >= G.nz - 1) return false;
+    if (cx < 0 || cz < 0 || cx >= G.nx || cz >= G.nz) return false;
+    const float fx = (pos.x - G.ox) - cx * G.cell, fz = (pos.z - G.oz) - cz * G.cell;
+    const float inCell = tminf(tminf(fx, G.cell - fx), tminf(fz, G.cell - fz));
     float bestDistSq = FLT_MAX; int best = -1;
-    for (int iz = cz - 1; iz <= cz + 1; ++iz)
-        for (int ix = cx - 1; ix <= cx + 1; ++ix) {
-            const int c = iz * G.nx + ix;
-            for (int k = T.ptStart[c]; k < T.ptStart[c + 1]; ++k) {
-#if defined(__CUDA_ARCH__)
-                const float4 r = __ldg(reinterpret_cast<const float4*>(T.ptRec) + k);
-                const V3 loc = v3(r.x, r.y, r.z); const int id = __float_as_int(r.w);
-#else
-                const float* r = T.ptRec + (size_t)k * 4;
-                const V3 loc = v3(r[0], r[1], r[2]); int id; memcpy(&id, &r[3], 4);
-#endif
-                if (!(sqlen(cachePos - loc) < nearRSq)) continue;
-                const float dsq = sqlen(loc - pos);
-                if (bestDistSq > dsq || (bestDistSq == dsq && id < best)) { bestDistSq = dsq; best = id; }
+    for (int R = 1; R <= PD_NEAREST_MAX_RING; ++R) {
+        for (int iz = cz - R; iz <= cz + R; ++iz) {
+            if (iz < 0 || iz >= G.nz) continue;
+            for (int ix = cx - R; ix <= cx + R; ++ix) {
+                if (ix < 0 || ix >= G.nx) continue;
+                if (R > 1 && iz > cz - R && iz < cz + R && ix > cx - R && ix < cx + R) continue;   /* inner block: already scanned */
+                nearest_cell_scan(T, iz * G.nx + ix, pos, cachePos, nearRSq, bestDistSq, best);
             }
         }
-    /* every point outside the 3x3 block is at least one cell (minus the position's offset in its cell) away in x-z */
-    const float fx = (pos.x - G.ox) - cx * G.cell, fz = (pos.z - G.oz) - cz * G.cell;
-    const float border = tminf(tminf(fx, G.cell - fx), tminf(fz, G.cell - fz)) + G.cell;
-    if (best < 0 || !(bestDistSq < (border - 0.01f) * (border - 0.01f))) return false;
-    bestPoint = best; return true;
+        const float border = inCell + (float)R * G.cell - 0.01f;
+        if (best >= 0 && bestDistSq < border * border) { bestPoint = best; return true; }
+    }
+    return false;
 }
 
 /* Track::getPointIdAtDistance (Track.cpp:564-577) */
@@ -284,6 +298,66 @@ PD_HD bool spline_nearest(const TrackDev& T, V3 pos, int seg1, int seg2, int& ou
     }
     outId = best_id; outDist = spline_dist;
     return found;
+}
+
+/* ---- the same two searches with the work split over the four lanes of a quad (pd_quad.h) ----
+ * Both return exactly what the sequential forms return: the spline search keeps the LAST minimum in sequence order
+ * (`best_dist >= d`), so lanes take consecutive chunks and ties between lanes go to the later chunk; the point
+ * search orders candidates by (distance, id), which does not depend on the visiting order at all. */
+template <class Ex> PD_HD bool spline_nearest_quad(const TrackDev& T, V3 pos, int seg1, int seg2, Ex& ex, int& outId, float& outDist) {
+    const int np = T.info.nSplineNodes;
+    if (seg1 >= np) seg1 = 0;
+    if (seg2 >= np) seg2 = 0;
+    int cnt = seg2 - seg1; if (cnt < 0) cnt += np;
+    if (!seg1 && !seg2) cnt = np;
+    const int chunk = (cnt + 3) >> 2;
+    const int k0 = ex.lane * chunk, k1 = (k0 + chunk < cnt) ? k0 + chunk : cnt;
+    float bd = FLT_MAX; int bk = -1;
+    int id = seg1 + k0; if (id >= np) id -= np;
+    PD_UNROLL4
+    for (int k = k0; k < k1; ++k) {
+        const float* p = T.splineXYZ + (size_t)id * 3;
+        const float d = sqlen(pos - v3(p[0], p[1], p[2]));
+        if (bd >= d) { bd = d; bk = k; }
+        ++id; if (id >= np) id = 0;
+    }
+    PD_UNROLL
+    for (int off = 1; off <= 2; off <<= 1) {
+        const float od = ex.get(bd, ex.lane ^ off); const int ok = ex.get(bk, ex.lane ^ off);
+        if (ok >= 0 && (bk < 0 || od < bd || (od == bd && ok > bk))) { bd = od; bk = ok; }
+    }
+    if (bk < 0) { outId = 0; outDist = 0; return false; }
+    int best = seg1 + bk; if (best >= np) best -= np;
+    outId = best; outDist = T.splineDist[best];
+    return true;
+}
+
+template <class Ex> PD_HD bool nearest_point_grid_quad(const TrackDev& T, V3 pos, V3 cachePos, float nearRSq, Ex& ex, int& bestPoint) {
+    const PdBoundGrid& G = T.grid;
+    const int cx = (int)floorf((pos.x - G.ox) * G.invCell), cz = (int)floorf((pos.z - G.oz) * G.invCell);
+    if (cx < 0 || cz < 0 || cx >= G.nx || cz >= G.nz) return false;
+    const float fx = (pos.x - G.ox) - cx * G.cell, fz = (pos.z - G.oz) - cz * G.cell;
+    const float inCell = tminf(tminf(fx, G.cell - fx), tminf(fz, G.cell - fz));
+    float bestDistSq = FLT_MAX; int best = -1;
+    for (int R = 1; R <= PD_NEAREST_MAX_RING; ++R) {
+        const int side = 2 * R + 1;
+        for (int cell = ex.lane; cell < side * side; cell += 4) {          /* the block's cells, dealt round-robin to the four lanes */
+            const int dz = cell / side - R, dx = cell % side - R;
+            if (R > 1 && dz > -R && dz < R && dx > -R && dx < R) continue; /* inner block: already scanned */
+            const int iz = cz + dz, ix = cx + dx;
+            if (iz < 0 || iz >= G.nz || ix < 0 || ix >= G.nx) continue;
+            nearest_cell_scan(T, iz * G.nx + ix, pos, cachePos, nearRSq, bestDistSq, best);
+        }
+        float qd = bestDistSq; int qi = best;                               /* quad-wide best so far (own candidates stay per lane) */
+        PD_UNROLL
+        for (int off = 1; off <= 2; off <<= 1) {
+            const float od = ex.get(qd, ex.lane ^ off); const int oi = ex.get(qi, ex.lane ^ off);
+            if (oi >= 0 && (qi < 0 || qd > od || (qd == od && oi < qi))) { qd = od; qi = oi; }
+        }
+        const float border = inCell + (float)R * G.cell - 0.01f;
+        if (qi >= 0 && qd < border * border) { bestPoint = qi; return true; }
+    }
+    return false;
 }
 
 } // namespace pd

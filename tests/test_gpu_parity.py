@@ -271,3 +271,39 @@ def test_env_step_host_equals_device_path(oracle):
     assert np.array_equal(obs_h, c.obs_tensor().cpu().numpy())
     assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy())
     assert np.array_equal(a.snapshot(), c.snapshot())
+
+
+@pytest.mark.parametrize("kernel", ["k_tick_quad", "k_tick"])
+def test_autoreset_next_step_equals_same_step(oracle, kernel, monkeypatch):
+    """PD_AUTORESET_NEXT_STEP (reset inside the next step's single kernel launch) must produce, one step later, exactly
+    the reset observation PD_AUTORESET_SAME_STEP produces (teleport + zero-action tick, projectd_env.py:216-227), with
+    the same done / reward on the finishing step and (0, 0) on the reset step."""
+    import torch
+    monkeypatch.setenv("PD_QUAD_MAX_ENVS", "8192" if kernel == "k_tick_quad" else "0")
+    n = 64
+    a = _batch(oracle, n); a.set_seed(5, 0); a.teleport_spline(np.linspace(0, 0.9, n))
+    c = _batch(oracle, n); c.set_seed(5, 0); c.teleport_spline(np.linspace(0, 0.9, n)); c.set_autoreset(1)
+    assert a.tick_kernel() == kernel and c.tick_kernel() == kernel
+    act = torch.zeros((n, 2), device="cuda"); act[:, 0] = torch.linspace(-1, 1, n, device="cuda"); act[:, 1] = 1.0
+    ra = torch.zeros(n, device="cuda"); da = torch.zeros(n, device="cuda", dtype=torch.int32)
+    rc = torch.zeros(n, device="cuda"); dc = torch.zeros(n, device="cuda", dtype=torch.int32)
+    alive = np.ones(n, bool)            # envs whose two batches are still in lock step (no reset yet)
+    pend = {}                           # env -> reset observation of the same-step batch
+    checked = 0
+    for t in range(1500):
+        a.env_step(act, DT, None, ra, da); c.env_step(act, DT, None, rc, dc)
+        a.sync(); c.sync()                      # the batches run on their own streams
+        oa = a.obs_tensor().cpu().numpy(); oc = c.obs_tensor().cpu().numpy()
+        da_h, dc_h, ra_h, rc_h = da.cpu().numpy(), dc.cpu().numpy(), ra.cpu().numpy(), rc.cpu().numpy()
+        for e, want in list(pend.items()):     # the step after the finishing one
+            assert dc_h[e] == 0 and rc_h[e] == 0.0
+            assert np.array_equal(oc[e], want), "reset observation differs for env %d" % e
+            checked += 1; del pend[e]
+        assert np.array_equal(da_h[alive], dc_h[alive]) and np.array_equal(ra_h[alive], rc_h[alive])
+        for e in np.nonzero(alive & (da_h != 0))[0]:
+            pend[int(e)] = oa[e].copy(); alive[e] = False
+        if not alive.any() and not pend:
+            break
+    assert checked >= n // 4, "too few episodes finished to check (%d)" % checked
+    sa, sc = a.env_stats(), c.env_stats()
+    assert sc[0] >= checked

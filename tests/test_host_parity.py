@@ -107,7 +107,7 @@ def test_probe_grid_walk_equals_exhaustive_scan(hostsim, hostsim_env, content_ba
     n = 20000
     idx = rng.integers(0, len(fat), n)
     poses = np.zeros((n, 4), np.float32)
-    poses[:, 0:3] = fat[idx, 0:3] + rng.uniform(-9, 9, (n, 3)).astype(np.float32) * np.array([1, 0.05, 1], np.float32)
+    poses[:, 0:3] = fat[idx, 0:3] + rng.uniform(-16, 16, (n, 3)).astype(np.float32) * np.array([1, 0.05, 1], np.float32)
     poses[:, 3] = rng.uniform(-math.pi, math.pi, n)
     walk = np.zeros((n, 8), np.float32); brute = np.zeros((n, 8), np.float32)
     hostsim.hs_probe_compare(hostsim_env, n, poses.ctypes.data, walk.ctypes.data, brute.ctypes.data)
@@ -115,6 +115,7 @@ def test_probe_grid_walk_equals_exhaustive_scan(hostsim, hostsim_env, content_ba
     assert ok.mean() > 0.99
     assert np.array_equal(walk[:, :7][ok], brute[:, :7][ok])
     okp = walk[:, 7] >= 0
+    assert okp.mean() > 0.99, "the ring search must cover cars up to 16 m off the line"
     assert np.array_equal(walk[okp, 7], brute[okp, 7])
 
 
