@@ -211,7 +211,7 @@ class Batch:
         self._ck(self.L.pd_set_autoreset(self.h, int(mode)))
 
     def debug_warp_clocks(self):
-        out = np.zeros(self.n // 4 + 64, dtype=np.int64)
+        out = np.zeros(4096 + self.n * 16, dtype=np.int64)
         cnt = self.L.pd_debug_read_clocks(self.h, out.ctypes.data, out.size)
         return out[:cnt]
 

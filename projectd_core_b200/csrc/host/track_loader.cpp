@@ -101,8 +101,29 @@ void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& sur
 }
 
 /* Index for VERTICAL rays (every ray of the hot path is one: wheel rays Tyre.cpp:478-481, the teleport ray
- * Car.cpp:1243): uniform x-z grid, each cell lists the triangles whose padded x-z box touches it.  The cell
- * size doubles from 2 m until the lists stay below ~6 entries per triangle and the grid below 4M cells. */
+ * Car.cpp:1243): uniform x-z grid, each cell lists the triangles whose padded x-z box touches it.
+ * Triangles that no downward ray can hit are left out: the culling test of ray_cast_down rejects a triangle when
+ * det = e1.x * (-e2.z) + e1.z * e2.x < 1e-6, and det does not depend on the ray -- evaluated here with the kernel's
+ * own expression (no contraction), so the lists lose exactly the vertical (walls) and downward-facing triangles and
+ * the hits are unchanged.  Cell size: the smallest of 0.5 / 1 / 2 / 4 ... m whose grid stays below 8M cells and
+ * whose box-overlap count stays below ~24 entries per listed triangle; inside its box a triangle is listed only in
+ * the cells its x-z projection really touches (separating-axis test against the padded cell, in double precision
+ * with a 1 mm margin: conservative, a ray can only hit a triangle whose projection contains the ray's x-z point). */
+static bool tri_touches_cell(const double tx[3], const double tz[3], double cx0, double cz0, double cx1, double cz1) {
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        const double nx = -(tz[j] - tz[i]), nz = tx[j] - tx[i];            /* edge normal */
+        const double nl = std::sqrt(nx * nx + nz * nz);
+        if (nl == 0.0) continue;
+        const double d0 = nx * tx[i] + nz * tz[i], dk = nx * tx[k] + nz * tz[k];
+        const double tmin = std::min(d0, dk), tmax = std::max(d0, dk);     /* the triangle's extent along the normal */
+        const double b0 = nx * cx0 + nz * cz0, b1 = nx * cx1 + nz * cz0, b2 = nx * cx0 + nz * cz1, b3 = nx * cx1 + nz * cz1;
+        const double bmin = std::min(std::min(b0, b1), std::min(b2, b3)), bmax = std::max(std::max(b0, b1), std::max(b2, b3));
+        const double slack = 1e-3 * nl;
+        if (bmin > tmax + slack || bmax < tmin - slack) return false;
+    }
+    return true;
+}
 void build_column_grid(TrackModel& out) {
     const size_t nt = out.triSurf.size();
     PdBoundGrid& G = out.colGrid; memset(&G, 0, sizeof(G));
@@ -110,20 +131,26 @@ void build_column_grid(TrackModel& out) {
     if (nt == 0) return;
     float x0 = 3.4e38f, x1 = -3.4e38f, z0 = 3.4e38f, z1 = -3.4e38f;
     std::vector<float> bx0(nt), bx1(nt), bz0(nt), bz1(nt);
+    std::vector<uint8_t> keep(nt, 0);
+    size_t kept = 0;
     for (size_t t = 0; t < nt; ++t) {
         const float* p = &out.tris[t * PD_TRI_STRIDE];
         const float ax = p[0], az = p[2], bx = p[0] + p[3], bz = p[2] + p[5], cx = p[0] + p[6], cz = p[2] + p[8];
         bx0[t] = std::min(ax, std::min(bx, cx)) - 1e-3f; bx1[t] = std::max(ax, std::max(bx, cx)) + 1e-3f;
         bz0[t] = std::min(az, std::min(bz, cz)) - 1e-3f; bz1[t] = std::max(az, std::max(bz, cz)) + 1e-3f;
         x0 = std::min(x0, bx0[t]); x1 = std::max(x1, bx1[t]); z0 = std::min(z0, bz0[t]); z1 = std::max(z1, bz1[t]);
+        const volatile float e1x = p[3], e1z = p[5], e2x = p[6], e2z = p[8];
+        const volatile float m1 = e1x * (-e2z), m2 = e1z * e2x;
+        const float det = m1 + m2;
+        if (!(det < 0.000001f)) { keep[t] = 1; ++kept; }
     }
-    for (float cell = 2.0f;; cell *= 2.0f) {
+    for (float cell = 0.5f;; cell *= 2.0f) {
         G.cell = cell; G.invCell = 1.0f / cell; G.ox = x0 - cell; G.oz = z0 - cell;
         G.nx = (int)ceilf((x1 - G.ox) * G.invCell) + 2; G.nz = (int)ceilf((z1 - G.oz) * G.invCell) + 2;
         const double cells = (double)G.nx * G.nz;
         double pairs = 0;
-        for (size_t t = 0; t < nt; ++t) pairs += (double)((int)floorf((bx1[t] - G.ox) * G.invCell) - (int)floorf((bx0[t] - G.ox) * G.invCell) + 1) * ((int)floorf((bz1[t] - G.oz) * G.invCell) - (int)floorf((bz0[t] - G.oz) * G.invCell) + 1);
-        if ((pairs <= 6.0 * nt && cells <= 4.0e6) || cell >= 64.0f) break;
+        for (size_t t = 0; t < nt; ++t) if (keep[t]) pairs += (double)((int)floorf((bx1[t] - G.ox) * G.invCell) - (int)floorf((bx0[t] - G.ox) * G.invCell) + 1) * ((int)floorf((bz1[t] - G.oz) * G.invCell) - (int)floorf((bz0[t] - G.oz) * G.invCell) + 1);
+        if ((pairs <= 24.0 * (double)std::max<size_t>(kept, 1) && cells <= 8.0e6) || cell >= 64.0f) break;
     }
     const size_t nc = (size_t)G.nx * G.nz;
     std::vector<int32_t> count(nc + 1, 0);
@@ -131,12 +158,23 @@ void build_column_grid(TrackModel& out) {
         ix0 = std::max(0, (int)floorf((bx0[t] - G.ox) * G.invCell)); ix1 = std::min(G.nx - 1, (int)floorf((bx1[t] - G.ox) * G.invCell));
         iz0 = std::max(0, (int)floorf((bz0[t] - G.oz) * G.invCell)); iz1 = std::min(G.nz - 1, (int)floorf((bz1[t] - G.oz) * G.invCell));
     };
-    for (size_t t = 0; t < nt; ++t) { int a, b, c, d; range(t, a, b, c, d); for (int iz = c; iz <= d; ++iz) for (int ix = a; ix <= b; ++ix) count[(size_t)iz * G.nx + ix + 1]++; }
+    auto touches = [&](size_t t, int ix, int iz) {
+        const float* p = &out.tris[t * PD_TRI_STRIDE];
+        const double tx[3] = {p[0], (double)p[0] + p[3], (double)p[0] + p[6]}, tz[3] = {p[2], (double)p[2] + p[5], (double)p[2] + p[8]};
+        const double cx0 = (double)G.ox + (double)ix * G.cell - 1e-3, cz0 = (double)G.oz + (double)iz * G.cell - 1e-3;
+        return tri_touches_cell(tx, tz, cx0, cz0, cx0 + G.cell + 2e-3, cz0 + G.cell + 2e-3);
+    };
+    for (size_t t = 0; t < nt; ++t) { if (!keep[t]) continue; int a, b, c, d; range(t, a, b, c, d); for (int iz = c; iz <= d; ++iz) for (int ix = a; ix <= b; ++ix) if (touches(t, ix, iz)) count[(size_t)iz * G.nx + ix + 1]++; }
     for (size_t c = 0; c < nc; ++c) count[c + 1] += count[c];
     out.colStart = count;
     out.colItems.assign((size_t)count[nc], 0);
     std::vector<int32_t> fill(count.begin(), count.end() - 1);
-    for (size_t t = 0; t < nt; ++t) { int a, b, c, d; range(t, a, b, c, d); for (int iz = c; iz <= d; ++iz) for (int ix = a; ix <= b; ++ix) out.colItems[(size_t)fill[(size_t)iz * G.nx + ix]++] = (int32_t)t; }
+    for (size_t t = 0; t < nt; ++t) { if (!keep[t]) continue; int a, b, c, d; range(t, a, b, c, d); for (int iz = c; iz <= d; ++iz) for (int ix = a; ix <= b; ++ix) if (touches(t, ix, iz)) out.colItems[(size_t)fill[(size_t)iz * G.nx + ix]++] = (int32_t)t; }
+    if (getenv("PD_TRACK_STATS")) {
+        size_t occ = 0, mx = 0; for (size_t c = 0; c < nc; ++c) { const size_t k = (size_t)(count[c + 1] - count[c]); if (k) { ++occ; mx = std::max(mx, k); } }
+        fprintf(stderr, "[pd] column grid: %zu of %zu triangles can face a downward ray; cell %.2f m, %d x %d cells (%zu occupied), %zu entries, mean %.1f / max %zu per occupied cell\n",
+                kept, nt, G.cell, G.nx, G.nz, occ, out.colItems.size(), occ ? (double)out.colItems.size() / occ : 0.0, mx);
+    }
 }
 
 /* BSpline3d::interpolate (Core/Spline3d.cpp:151-160), same operation order */

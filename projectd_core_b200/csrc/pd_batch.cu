@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ Pd
 /* exchange policy of pd_quad.h on the GPU: shuffles inside the quad, with the quad's own member mask */
 struct QuadShfl {
     int lane; unsigned mask; int base;
+#if defined(PD_PHASE_CLOCKS)
+    long long* ph;
+#endif
     __device__ __forceinline__ float get(float v, int src) const { return __shfl_sync(mask, v, base + src); }
     __device__ __forceinline__ int get(int v, int src) const { return __shfl_sync(mask, v, base + src); }
     __device__ __forceinline__ V3 get(V3 v, int src) const { return v3(get(v.x, src), get(v.y, src), get(v.z, src)); }
@@ -198,6 +201,9 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
     SVFlat sv = sv_flat(rec);
     if (on) {
         QuadShfl ex; ex.lane = wl & 3; ex.base = wl & ~3; ex.mask = 0xFu << ex.base;
+#if defined(PD_PHASE_CLOCKS)
+        ex.ph = (io.clk && wl == 0) ? io.clk + 4096 + (size_t)(blockIdx.x * 2 + warp) * 32 : nullptr;   /* profiling build: 32 stamps per warp after the per-warp totals */
+#endif
         if (io.pending && io.pending[e]) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
         else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
 #if PD_QUAD_LOCAL_SCRATCH == 1
@@ -444,7 +450,11 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = dalloc(b, &b->dStats, 8))) return rc;
     if ((rc = dalloc(b, &b->dPending, n))) return rc;
     CK(cudaMemsetAsync(b->dPending, 0, n * 4, b->stream));
-    if (getenv("PD_DEBUG_CLOCKS")) { b->nClk = (int)(n / 4 + 64); if ((rc = dalloc(b, &b->dClk, (size_t)b->nClk))) return rc; CK(cudaMemsetAsync(b->dClk, 0, (size_t)b->nClk * 8, b->stream)); }
+    if (getenv("PD_DEBUG_CLOCKS")) { b->nClk = (int)(n / 4 + 64);
+#if defined(PD_PHASE_CLOCKS)
+        b->nClk = 4096 + (int)n * 16;
+#endif
+        if ((rc = dalloc(b, &b->dClk, (size_t)b->nClk))) return rc; CK(cudaMemsetAsync(b->dClk, 0, (size_t)b->nClk * 8, b->stream)); }
     CK(cudaMemsetAsync(b->dEpisodeCtr, 0, n * 4, b->stream));
     CK(cudaMemsetAsync(b->dEnvReturn, 0, n * 4, b->stream));
     CK(cudaMemsetAsync(b->dEnvLen, 0, n * 4, b->stream));
@@ -669,7 +679,11 @@ int pd_set_autoreset(pd_batch* b, int mode) {
 int pd_debug_read_clocks(pd_batch* b, long long* out, int cap) {
     if (!b || !out || !b->dClk) return 0;
     const int blocks = b->layout == PD_LAYOUT_RECORDS ? grid(b->n, 2 * b->quadCpw) : grid(b->n, PD_BLOCK);
-    int cnt = blocks * 2; if (cnt > cap) cnt = cap; if (cnt > b->nClk) cnt = b->nClk;
+    int cnt = blocks * 2;
+#if defined(PD_PHASE_CLOCKS)
+    cnt = 4096 + blocks * 2 * 32;
+#endif
+    if (cnt > cap) cnt = cap; if (cnt > b->nClk) cnt = b->nClk;
     if (cudaMemcpyAsync(out, b->dClk, (size_t)cnt * 8, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess) return 0;
     return cnt;
 }

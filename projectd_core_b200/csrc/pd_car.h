@@ -23,8 +23,16 @@ struct CarCtx {
     float dt;
     double time;          /* Simulator::physicsTime */
     float dballErp, dballCfm;
+#if defined(PD_PHASE_CLOCKS)
+    long long* ph = nullptr;   /* profiling build: phase time stamps of this warp (written by its lane 0) */
+#endif
     PD_HD explicit CarCtx(CarS& cc) : c(cc) {}
 };
+#if defined(PD_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define PD_PHASE(X, k) do { if ((X).ph) (X).ph[k] = clock64(); } while (0)
+#else
+#define PD_PHASE(X, k) do { } while (0)
+#endif
 
 PD_HD float engine_rpm(const CarS& c) { return (float)((c.engineVel * 0.15915507) * 60.0); }   /* Drivetrain::getEngineRPM */
 PD_HD float car_engine_rpm(const CarS& c) { return ((float)c.engineVel * 0.15915507f * 60.0f); } /* Car::getEngineRpm */
@@ -320,6 +328,7 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
     if (!finitef(t.angularVelocity)) t.angularVelocity = 0;
 
     const RayHit hit = ray_cast_down(T, v3(worldPosition.x, worldPosition.y + 2.0f, worldPosition.z), 3.0f);
+    PD_PHASE(X, 3);
     float gripMod = 0, dirtAdditiveK = 0;
     bool contact = hit.hit && !(hubFrame.ay.y <= 0.35f);
     if (!contact) {
@@ -527,6 +536,7 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
     }
     if (t.totalHubVelocity < 10.0f) t.slipFactor = fabsf(t.totalHubVelocity * 0.1f) * t.slipFactor;
 
+    PD_PHASE(X, 4);
     /* ---- stepThermalModel (Tyre.cpp:766-815) ---- */
     {
         float fThermalInput = (sqrtf((t.slidingVelocityX * t.slidingVelocityX) + (t.slidingVelocityY * t.slidingVelocityY)) * ((t.D * t.load) * P.thermalFrictionK)) * T.info.dynamicGripLevel;

@@ -49,6 +49,10 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     if constexpr (sv_traits<SVX>::in_place) cp = car_in_place(sv); else load_car(sv, cLocal);
     CarCtx X(*cp); X.dt = dt; X.time = physicsTime;
     CarS& c = X.c;
+#if defined(PD_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    X.ph = ex.ph;
+#endif
+    PD_PHASE(X, 0);
     ex.sync();
     Body C, W, S;
     const int wIdx = front ? (PD_BODY_HUB0 + 2 * lane) : PD_BODY_AXLE;
@@ -113,6 +117,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     /* ---------------- stepComponents: one wheel per lane ---------------- */
     float brakeT[4], handT[4];
     brakes_step(P.brakes, c, brakeT, handT);
+    PD_PHASE(X, 1);
     const float myBrake = front ? brakeT[0] : brakeT[2], myHand = front ? handT[0] : handT[2];
     float travel, dspeed;
     Frame hf;
@@ -120,7 +125,9 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     else { axle_step(P.axle, C, W, lane - 2, travel, dspeed); hf = axle_hub_frame(P.axle, W, lane - 2); }
     sv.f(PD_OFF_TYRE(lane) + PD_TYRE_o_suspTravel, travel); sv.f(PD_OFF_TYRE(lane) + PD_TYRE_o_suspDamperSpeed, dspeed);
     WheelLink my;
+    PD_PHASE(X, 2);
     tyre_step(P, T, lane, X, sv, W, hf, C, myBrake, myHand, my);
+    PD_PHASE(X, 5);
     for (int w = 0; w < 4; ++w) {
         WheelLink& L = X.wl[w];
         L.load = ex.get(my.load, w); L.feedbackTorque = ex.get(my.feedbackTorque, w); L.angularVelocity = ex.get(my.angularVelocity, w);
@@ -139,10 +146,12 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
         steerA2 = to_local(W.fr, to_world(W.fr, v3(St.tyreSteer[0], St.tyreSteer[1], St.tyreSteer[2])));
     }
     ex.sync();
+    PD_PHASE(X, 6);
     autoblip_step(P, X);
     autoshift_step(P, X);
     gearchanger_step(P, X);
     const float fAxleTorq = drivetrain_step(P, X);
+    PD_PHASE(X, 7);
     if (P.tyre[lane].driven) { sv.f(PD_OFF_TYRE(lane) + PD_TYRE_o_angularVelocity, X.wl[lane].angularVelocity); sv.i(PD_OFF_TYRE(lane) + PD_TYRE_o_isLocked, X.wl[lane].isLocked); }
     if (lane == 2) { add_rel_torque(C, v3(0, 0, fAxleTorq)); add_rel_torque(W, v3(0, 0, -fAxleTorq)); }
     { /* anti-roll bars */
@@ -170,6 +179,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     }
 
     /* ---------------- dWorldStep: one joint group per lane ---------------- */
+    PD_PHASE(X, 8);
     const float h = dt, hinv = 1.0f / dt;
     BodyDyn dC, dA, dB;
     body_dyn(C, P.gravityY, h, dC);
@@ -183,12 +193,15 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     if (front) build_strut(P, P.strut[lane], C, W, S, steerA1, steerA2, hinv, X.dballErp, X.dballCfm, G);
     else if (lane == 2) build_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G);
     else build_tank(P, S, C, hinv, G);
+    PD_PHASE(X, 9);
     factor_group(G, dA, dB, dC, hinv, S21, b6);
+    PD_PHASE(X, 10);
     for (int k = 0; k < 21; ++k) S21[k] = ex.sum(S21[k]);
     for (int k = 0; k < 6; ++k) b6[k] = ex.sum(b6[k]);
     schur_add_chassis(S21, C);
     float z[6];
     solve6(S21, b6, z);
+    PD_PHASE(X, 11);
     float cfA[6], cfB[6];
     backsolve_group(G, z, cfA, cfB);
     apply_update(A, dA, cfA, h);
@@ -207,6 +220,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
 
     /* ---------------- Car::postStep ---------------- */
     ex.sync();
+    PD_PHASE(X, 12);
     {
         const V3 bodyPos = C.fr.p;
         const int nFat = T.info.nFatPoints;
@@ -233,8 +247,10 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
             rax = rayStart.x; raz = rayStart.z; rbx[k] = rayEnd.x; rbz[k] = rayEnd.z;
             if (!probe_walk(T, rax, raz, rbx[k], rbz[k], cachePos, nearRSq, pr[k])) needBrute = true;
         }
+        PD_PHASE(X, 13);
         int bestPoint = 0;
         const bool haveNearest = nearest_point_grid_quad(T, bodyPos, cachePos, nearRSq, ex, bestPoint);
+        PD_PHASE(X, 14);
         if (!ex.all(!needBrute && haveNearest)) {
             /* exhaustive form of the reference (car far off the indexed area); every lane scans, each for its own probes */
             float bestDistSq = FLT_MAX; bestPoint = 0; pr[0] = FLT_MAX; pr[1] = FLT_MAX;
@@ -252,6 +268,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
                 }
             }
         }
+        PD_PHASE(X, 15);
         for (int r = 0; r < P.nProbes && r < 8; ++r) {
             const float v = ex.get((r < 4) ? pr[0] : pr[1], r & 3);
             c.probes[r] = (v != FLT_MAX) ? v : P.probeLength[r];
@@ -278,12 +295,14 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
         }
     }
     ex.sync();
+    PD_PHASE(X, 16);
     post_lookahead(P, T, C, c);
     post_scoring(P, T, C, X, dt);
     c.episodeSteps++; c.thermalPrimed = 1;
     if (bad) c.nanFlag = 1;
     if constexpr (!sv_traits<SVX>::in_place) { if (lane == 0) store_car(sv, c); }
     ex.sync();
+    PD_PHASE(X, 17);
 }
 
 } // namespace pd

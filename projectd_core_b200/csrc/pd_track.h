@@ -168,6 +168,22 @@ PD_HD bool line_intersection(float p0x, float p0y, float p1x, float p1y, float p
     return false;
 }
 
+/* Cheap exact pre-filter for line_intersection: true when the full test is KNOWN to fail, decided from the numerators
+ * and the denominator alone (the same three expressions line_intersection divides).  den == 0 makes s, t infinite or
+ * NaN; a numerator of the opposite sign makes the quotient negative; |num| > |den| * (1 + 1e-6) makes it round to
+ * more than 1.  Anything else (including NaNs: every comparison here is then false) goes through the full test. */
+PD_HD bool line_intersection_rejects(float p0x, float p0y, float p1x, float p1y, float p2x, float p2y, float p3x, float p3y) {
+    const float s1x = p1x - p0x, s1y = p1y - p0y, s2x = p3x - p2x, s2y = p3y - p2y;
+    const float den = -s2x * s1y + s1x * s2y;
+    const float ns = -s1y * (p0x - p2x) + s1x * (p0y - p2y);
+    const float nt = s2x * (p0y - p2y) - s2y * (p0x - p2x);
+    if (den == 0.0f) return true;
+    if ((ns < 0.0f && den > 0.0f) || (ns > 0.0f && den < 0.0f)) return true;
+    if ((nt < 0.0f && den > 0.0f) || (nt > 0.0f && den < 0.0f)) return true;
+    const float lim = fabsf(den) * 1.000001f;
+    return fabsf(ns) > lim || fabsf(nt) > lim;
+}
+
 struct Seg8 { float ax, az, bx, bz, bx0, by0, bz0, pad; };
 PD_HD Seg8 load_seg8(const float* rec, int k) {
     Seg8 r;
@@ -211,7 +227,8 @@ PD_HDN bool probe_walk(const TrackDev& T, float ax, float az, float bx, float bz
             Seg8 nxt = cur; if (k + 1 < s1) nxt = load_seg8(T.segRec, k + 1);
             if (sqlen(cachePos - v3(cur.bx0, cur.by0, cur.bz0)) < nearRSq) {
                 float jx, jz;
-                if (line_intersection(ax, az, bx, bz, cur.ax, cur.az, cur.bx, cur.bz, jx, jz)) { const float ex = ax - jx, ez = az - jz; best = tminf(best, sqrtf(ex * ex + ez * ez)); }
+                if (!line_intersection_rejects(ax, az, bx, bz, cur.ax, cur.az, cur.bx, cur.bz) &&
+                    line_intersection(ax, az, bx, bz, cur.ax, cur.az, cur.bx, cur.bz, jx, jz)) { const float ex = ax - jx, ez = az - jz; best = tminf(best, sqrtf(ex * ex + ez * ez)); }
             }
             cur = nxt;
         }
