@@ -145,6 +145,9 @@ enum {
     PD_SV_OffTrackPenalty, PD_SV_GearGrindPenalty, PD_SV_StallPenalty
 };
 
+#define PD_MAX_COLLIDER_VERTS 64
+#define PD_MAX_COLLIDER_TRIS 128
+
 typedef struct PdCarParams {
     /* Car (car.ini) */
     float mass, chassisMass, chassisInertia[3], tankMass, tankInertia[3];
@@ -176,6 +179,17 @@ typedef struct PdCarParams {
     float fuelConsumptionRate, tyreConsumptionRate, mechanicalDamageRate;
     int32_t allowTyreBlankets;
     float gravityY, worldERP, worldCFM;
+    /* colliders of the chassis: the box of colliders.ini [COLLIDER_0] (CarColliderManager.cpp:12-34,
+     * category CAR, collides with TRACK meshes) and the hull mesh of collider.bin (Car.cpp:318-379, collides with WALL
+     * meshes).  Mesh vertices are stored chassis-local, the geom offset (Car::getGraphicsOffsetMatrix at construction:
+     * GRAPHICS_OFFSET, identity rotation) already added. */
+    int32_t hasBoxCollider; float boxCentre[3]; float boxSize[3];
+    int32_t nColliderVerts, nColliderTris;
+    float colliderMin[3], colliderMax[3];                  /* chassis-local bounds of the hull mesh */
+    float colliderVerts[PD_MAX_COLLIDER_VERTS][3];
+    uint8_t colliderTris[PD_MAX_COLLIDER_TRIS][4];         /* vertex indices i0, i1, i2, 0 */
+    float colliderTriBounds[PD_MAX_COLLIDER_TRIS][6];      /* chassis-local box of each hull triangle, grown by 1e-4: min xyz, max xyz (a filter only) */
+    float colliderTriSphere[PD_MAX_COLLIDER_TRIS][4];      /* bounding sphere of each hull triangle: centre xyz, radius grown by 1e-4 (a filter only) */
 } PdCarParams;
 
 /* ---- track (Sim/Track.cpp) ---- */

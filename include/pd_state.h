@@ -109,7 +109,9 @@
     /* batched-env bookkeeping (no reference counterpart: episode statistics, NaN guard) */ \
     X(I, episodeSteps) X(I, nanFlag) \
     /* TyreThermalPatch::inputT starts at ambient (TyreThermalModel.cpp:40) and is zero after the first step */ \
-    X(I, thermalPrimed)
+    X(I, thermalPrimed) \
+    /* PhysicsEngineODE::currentFrame (PhysicsEngineODE.cpp:228-244): collisions against the static meshes are tested on odd frames */ \
+    X(I, physFrame)
 
 /* ---------------------------------------------------------------------------------------- */
 #define PD__W_F 1

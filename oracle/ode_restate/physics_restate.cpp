@@ -15,14 +15,18 @@
  * normalised (v1-v0)x(v2-v0) after ODE's g1/g2 swap, minimum depth across meshes.  DEVIATION
  * (documented): within one mesh the closest stabbed triangle is returned, where ODE
  * with FirstContact=1 returns the first triangle met by OPCODE's tree walk.
- * Collision detection between the car colliders and the track (collisionStep,
- * PhysicsEngineODE.cpp:228-341) is NOT restated yet (deferred); colliders are
- * accepted and ignored.
+ * Collision DETECTION between the car colliders and the track (collisionStep / collisionNearCallback /
+ * onCollision, PhysicsEngineODE.cpp:228-341) is restated in ode_collide.h: frame parity, category / mask
+ * matching, the body-local normal filter of box-vs-trimesh contacts, and the collision callback.  The contact
+ * JOINTS (the response) are not created, and the callback receives a zero normal so that
+ * Car::onCollisionCallback (Car.cpp:921-1044) sets collisionFlag / lastCollisionTime but derives no damage
+ * from a contact normal this restatement does not have for mesh-vs-mesh pairs.
  */
 #include "Physics/PhysicsFactory.h"
 #include "Physics/IPhysicsEngine.h"
 #include "Core/Diag.h"
 #include "ode_core.h"
+#include "ode_collide.h"
 #include <cfloat>
 
 namespace D {
@@ -74,9 +78,14 @@ struct CollisionMeshR : public ICollisionObject {
     unsigned long getMask() override { return mask; }
 };
 
+struct BoxColliderR { vec3f centre, size; unsigned long category, mask; };
+struct MeshColliderR { std::shared_ptr<CollisionMeshR> mesh; float offR[9]; float offP[3]; };   /* geom offset: body-local = offR * v + offP */
+
 struct RigidBodyR : public IRigidBody {
     oder::Body b;
     RestateEngine* core;
+    std::vector<BoxColliderR> boxColliders;
+    std::vector<MeshColliderR> meshColliders;
     explicit RigidBodyR(RestateEngine* c) : core(c) {}
     void setEnabled(bool) override {}
     bool isEnabled() override { return true; }
@@ -127,8 +136,11 @@ struct RigidBodyR : public IRigidBody {
     void addTorque(const vec3f& t) override { b.tacc[0] += t.x; b.tacc[1] += t.y; b.tacc[2] += t.z; }
     void addLocalTorque(const vec3f& t) override { dReal tw[3]; oder::mul0_331(tw, b.R, &t.x); b.tacc[0] += tw[0]; b.tacc[1] += tw[1]; b.tacc[2] += tw[2]; }
 
-    void addBoxCollider(const vec3f&, const vec3f&, unsigned int, unsigned int, unsigned long) override {}
-    void addMeshCollider(ITriMeshPtr, const mat44f&, unsigned int, unsigned long, unsigned long) override {}
+    /* RigidBodyODE.cpp:274-292: dCreateBox(size) attached to the body, offset position = pos, rotation = the body's */
+    void addBoxCollider(const vec3f& pos, const vec3f& size, unsigned int, unsigned int category, unsigned long mask) override {
+        boxColliders.push_back(BoxColliderR{pos, size, (unsigned long)category, mask});
+    }
+    void addMeshCollider(ITriMeshPtr trimesh, const mat44f& offset, unsigned int spaceId, unsigned long category, unsigned long mask) override;
 };
 
 struct JointR : public IJoint {
@@ -260,11 +272,114 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
         return rayCastImpl(pos, dir, std::dynamic_pointer_cast<RayCasterR>(ray)->length);
     }
 
+    /* ---- collisionStep (PhysicsEngineODE.cpp:228-244): odd frames dynamic x static, even frames dynamic x dynamic ---- */
+    unsigned int currentFrame = 0;
+    unsigned long long collisionPairs = 0, localBoundHits = 0;
+    static oder::CV3 toWorld(const oder::Body& b, float x, float y, float z) {
+        return oder::cv((b.R[0] * x + b.R[1] * y + b.R[2] * z) + b.pos[0], (b.R[3] * x + b.R[4] * y + b.R[5] * z) + b.pos[1], (b.R[6] * x + b.R[7] * y + b.R[8] * z) + b.pos[2]);
+    }
+    void fire(RigidBodyR* rb, ICollisionObject* shape0, CollisionMeshR* other, oder::CV3 pos) {
+        /* onCollision (PhysicsEngineODE.cpp:284-341) -> collisionCallback; normal 0: see the header */
+        if (cb) cb->onCollisionCallback(rb, shape0, nullptr, other, vec3f(0, 0, 0), vec3f(pos.x, pos.y, pos.z), 0.0f);
+    }
+    void collideBodyStatic(RigidBodyR* rb) {
+        const oder::Body& b = rb->b;
+        const oder::CV3 A[3] = {oder::cv(b.R[0], b.R[3], b.R[6]), oder::cv(b.R[1], b.R[4], b.R[7]), oder::cv(b.R[2], b.R[5], b.R[8])};
+        for (const BoxColliderR& bx : rb->boxColliders) {
+            const oder::CV3 c = toWorld(b, bx.centre.x, bx.centre.y, bx.centre.z);
+            const float h[3] = {bx.size.x * 0.5f, bx.size.y * 0.5f, bx.size.z * 0.5f};
+            float ext[3];
+            for (int k = 0; k < 3; ++k) ext[k] = h[0] * fabsf(b.R[k * 3 + 0]) + h[1] * fabsf(b.R[k * 3 + 1]) + h[2] * fabsf(b.R[k * 3 + 2]);
+            const float lo[3] = {c.x - ext[0], c.y - ext[1], c.z - ext[2]}, hi[3] = {c.x + ext[0], c.y + ext[1], c.z + ext[2]};
+            for (auto& mp : staticMeshes) {
+                CollisionMeshR& m = *mp;
+                if (!((bx.category & m.mask) && (m.category & bx.mask))) continue;      /* collisionNearCallback bMatch */
+                if (lo[0] > m.bbMax[0] || hi[0] < m.bbMin[0] || lo[1] > m.bbMax[1] || hi[1] < m.bbMin[1] || lo[2] > m.bbMax[2] || hi[2] < m.bbMin[2]) continue;
+                const TriMeshVertex* vb = m.trimesh->getVB(); const TriMeshIndex* ib = m.trimesh->getIB();
+                const size_t nt = m.trimesh->getIndexCount() / 3;
+                for (size_t t = 0; t < nt; ++t) {
+                    const TriMeshVertex& a0 = vb[ib[t * 3]]; const TriMeshVertex& a1 = vb[ib[t * 3 + 1]]; const TriMeshVertex& a2 = vb[ib[t * 3 + 2]];
+                    if (std::min(a0.x, std::min(a1.x, a2.x)) > hi[0] || std::max(a0.x, std::max(a1.x, a2.x)) < lo[0]) continue;
+                    if (std::min(a0.y, std::min(a1.y, a2.y)) > hi[1] || std::max(a0.y, std::max(a1.y, a2.y)) < lo[1]) continue;
+                    if (std::min(a0.z, std::min(a1.z, a2.z)) > hi[2] || std::max(a0.z, std::max(a1.z, a2.z)) < lo[2]) continue;
+                    ++collisionPairs;
+                    oder::CV3 n;
+                    if (!oder::box_tri_contact(c, A, h, oder::cv(a0.x, a0.y, a0.z), oder::cv(a1.x, a1.y, a1.z), oder::cv(a2.x, a2.y, a2.z), n)) continue;
+                    /* box vs trimesh: contacts whose body-local normal y < 0.9 are dropped (PhysicsEngineODE.cpp:309-318) */
+                    const float locY = b.R[1] * n.x + b.R[4] * n.y + b.R[7] * n.z;
+                    if (locY < 0.9f) continue;
+                    if (getenv("PDREF_DEBUG_COLL")) fprintf(stderr, "[oracle] box contact: tri %zu of mesh cat %lu, n=(%g %g %g) locY=%g, tri y=(%g %g %g) box c=(%g %g %g)\n", t, m.category, n.x, n.y, n.z, locY, a0.y, a1.y, a2.y, c.x, c.y, c.z);
+                    fire(rb, nullptr, &m, c);
+                }
+            }
+        }
+        for (const MeshColliderR& mc : rb->meshColliders) {
+            /* mesh vs mesh in the MODEL space of the car's mesh (as OPCODE's tree-vs-tree query works): the hull keeps its
+               body-local vertices (offset applied), every candidate wall triangle is brought into the chassis frame */
+            CollisionMeshR& cm = *mc.mesh;
+            const TriMeshVertex* cvb = cm.trimesh->getVB(); const TriMeshIndex* cib = cm.trimesh->getIB();
+            const size_t nv = cm.trimesh->getVertexCount(), nct = cm.trimesh->getIndexCount() / 3;
+            std::vector<oder::CV3> hl(nv);
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            const float* r = mc.offR;
+            for (size_t i = 0; i < nv; ++i) {
+                hl[i] = oder::cv((r[0] * cvb[i].x + r[1] * cvb[i].y + r[2] * cvb[i].z) + mc.offP[0], (r[3] * cvb[i].x + r[4] * cvb[i].y + r[5] * cvb[i].z) + mc.offP[1], (r[6] * cvb[i].x + r[7] * cvb[i].y + r[8] * cvb[i].z) + mc.offP[2]);
+                const oder::CV3 w = toWorld(b, hl[i].x, hl[i].y, hl[i].z);
+                lo[0] = std::min(lo[0], w.x); hi[0] = std::max(hi[0], w.x); lo[1] = std::min(lo[1], w.y); hi[1] = std::max(hi[1], w.y); lo[2] = std::min(lo[2], w.z); hi[2] = std::max(hi[2], w.z);
+            }
+            auto toLocal = [&](const TriMeshVertex& v) {
+                const float dx = v.x - b.pos[0], dy = v.y - b.pos[1], dz = v.z - b.pos[2];
+                return oder::cv(b.R[0] * dx + b.R[3] * dy + b.R[6] * dz, b.R[1] * dx + b.R[4] * dy + b.R[7] * dz, b.R[2] * dx + b.R[5] * dy + b.R[8] * dz);
+            };
+            for (auto& mp : staticMeshes) {
+                CollisionMeshR& m = *mp;
+                if (!((cm.category & m.mask) && (m.category & cm.mask))) continue;
+                if (lo[0] > m.bbMax[0] || hi[0] < m.bbMin[0] || lo[1] > m.bbMax[1] || hi[1] < m.bbMin[1] || lo[2] > m.bbMax[2] || hi[2] < m.bbMin[2]) continue;
+                const TriMeshVertex* vb = m.trimesh->getVB(); const TriMeshIndex* ib = m.trimesh->getIB();
+                const size_t nt = m.trimesh->getIndexCount() / 3;
+                bool hit = false;
+                for (size_t t = 0; t < nt && !hit; ++t) {
+                    const TriMeshVertex& a0 = vb[ib[t * 3]]; const TriMeshVertex& a1 = vb[ib[t * 3 + 1]]; const TriMeshVertex& a2 = vb[ib[t * 3 + 2]];
+                    if (std::min(a0.x, std::min(a1.x, a2.x)) > hi[0] || std::max(a0.x, std::max(a1.x, a2.x)) < lo[0]) continue;
+                    if (std::min(a0.y, std::min(a1.y, a2.y)) > hi[1] || std::max(a0.y, std::max(a1.y, a2.y)) < lo[1]) continue;
+                    if (std::min(a0.z, std::min(a1.z, a2.z)) > hi[2] || std::max(a0.z, std::max(a1.z, a2.z)) < lo[2]) continue;
+                    const oder::CV3 b0 = toLocal(a0), b1 = toLocal(a1), b2 = toLocal(a2);
+                    if (getenv("PDREF_DEBUG_PAIRS")) { float l0[3] = {std::min(b0.x, std::min(b1.x, b2.x)), std::min(b0.y, std::min(b1.y, b2.y)), std::min(b0.z, std::min(b1.z, b2.z))}, h0[3] = {std::max(b0.x, std::max(b1.x, b2.x)), std::max(b0.y, std::max(b1.y, b2.y)), std::max(b0.z, std::max(b1.z, b2.z))}; float hlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}; for (auto& q : hl) { hlo[0] = std::min(hlo[0], q.x); hhi[0] = std::max(hhi[0], q.x); hlo[1] = std::min(hlo[1], q.y); hhi[1] = std::max(hhi[1], q.y); hlo[2] = std::min(hlo[2], q.z); hhi[2] = std::max(hhi[2], q.z); } if (!(l0[0] > hhi[0] || h0[0] < hlo[0] || l0[1] > hhi[1] || h0[1] < hlo[1] || l0[2] > hhi[2] || h0[2] < hlo[2])) ++localBoundHits; }
+                    for (size_t k = 0; k < nct && !hit; ++k) {
+                        ++collisionPairs;
+                        if (oder::tri_tri(hl[cib[k * 3]], hl[cib[k * 3 + 1]], hl[cib[k * 3 + 2]], b0, b1, b2)) hit = true;
+                    }
+                }
+                if (hit && getenv("PDREF_DEBUG_COLL")) fprintf(stderr, "[oracle] hull contact with mesh cat %lu\n", m.category);
+                if (hit) fire(rb, &cm, &m, oder::cv(b.pos[0], b.pos[1], b.pos[2]));     /* one callback per mesh pair is enough for the flag */
+            }
+        }
+    }
+    void collisionStep() {
+        const unsigned long long pairs0 = collisionPairs;
+        if (currentFrame & 1) { for (auto& rb : bodies) if (!rb->boxColliders.empty() || !rb->meshColliders.empty()) collideBodyStatic(rb.get()); }
+        /* even frames: dynamic x dynamic -- one car per simulator here; its own box and mesh do not match each other's masks */
+        if ((currentFrame & 1) && getenv("PDREF_DEBUG_PAIRS")) { fprintf(stderr, "[oracle] frame %u: %llu narrow-phase pairs %llu inbounds\n", currentFrame, collisionPairs - pairs0, localBoundHits); localBoundHits = 0; }
+        currentFrame++;
+    }
+
     void step(float dt) override {
-        /* collisionStep (PhysicsEngineODE.cpp:228-244) not restated: see header */
+        collisionStep();
         oder::world_step(world, dt);
     }
 };
+
+void RigidBodyR::addMeshCollider(ITriMeshPtr trimesh, const mat44f& offset, unsigned int spaceId, unsigned long category, unsigned long mask) {
+    /* RigidBodyODE.cpp:294-317: dynamic trimesh geom on this body; offset rotation r[0]=M11 r[1]=M21 r[2]=M31 / r[4]=M12 ... (ODE rows =
+       mat44f columns), offset position = the matrix' translation.  The reference passes Car::getGraphicsOffsetMatrix() taken while the
+       chassis sits at the origin with identity rotation (Car.cpp:342, 1407-1424): GRAPHICS_OFFSET and the GRAPHICS_PITCH_ROTATION rotator. */
+    MeshColliderR mc;
+    mc.mesh = std::dynamic_pointer_cast<CollisionMeshR>(core->createCollider(trimesh, true, spaceId, category, mask));
+    const float r[9] = {offset.M11, offset.M21, offset.M31, offset.M12, offset.M22, offset.M32, offset.M13, offset.M23, offset.M33};
+    for (int k = 0; k < 9; ++k) mc.offR[k] = r[k];
+    mc.offP[0] = offset.M41; mc.offP[1] = offset.M42; mc.offP[2] = offset.M43;
+    meshColliders.push_back(mc);
+}
 
 RayCastHit RayCasterR::rayCast(const vec3f& pos, const vec3f& dir) { return core->rayCastImpl(pos, dir, length); }
 
@@ -274,6 +389,18 @@ std::shared_ptr<IPhysicsEngine> PhysicsFactory::createPhysicsEngine() { return s
 oder::World* pdref_world(IPhysicsEngine* e) { return &static_cast<RestateEngine*>(e)->world; }
 oder::Body* pdref_body(IRigidBody* rb) { return &static_cast<RigidBodyR*>(rb)->b; }
 oder::Joint* pdref_joint(IJoint* j) { return &static_cast<JointR*>(j)->j; }
+unsigned int pdref_get_frame(IPhysicsEngine* e) { return static_cast<RestateEngine*>(e)->currentFrame; }
+void pdref_set_frame(IPhysicsEngine* e, unsigned int f) { static_cast<RestateEngine*>(e)->currentFrame = f; }
+/* colliders as the engine received them (for PdCarParams parity) */
+int pdref_body_box(IRigidBody* rb, float* centre3, float* size3) {
+    auto* r = static_cast<RigidBodyR*>(rb); if (r->boxColliders.empty()) return 0;
+    centre3[0] = r->boxColliders[0].centre.x; centre3[1] = r->boxColliders[0].centre.y; centre3[2] = r->boxColliders[0].centre.z;
+    size3[0] = r->boxColliders[0].size.x; size3[1] = r->boxColliders[0].size.y; size3[2] = r->boxColliders[0].size.z; return (int)r->boxColliders.size();
+}
+int pdref_body_mesh(IRigidBody* rb, ITriMesh** mesh, float* offR9, float* off3) {
+    auto* r = static_cast<RigidBodyR*>(rb); if (r->meshColliders.empty()) return 0;
+    *mesh = r->meshColliders[0].mesh->trimesh.get(); for (int k = 0; k < 3; ++k) off3[k] = r->meshColliders[0].offP[k]; for (int k = 0; k < 9; ++k) offR9[k] = r->meshColliders[0].offR[k]; return (int)r->meshColliders.size();
+}
 void pdref_ray_stats(IPhysicsEngine* e, unsigned long long* rays, unsigned long long* tris) {
     auto* r = static_cast<RestateEngine*>(e); *rays = r->rayCount; *tris = r->rayTriTests;
 }

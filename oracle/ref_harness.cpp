@@ -23,6 +23,10 @@ oder::World* pdref_world(IPhysicsEngine* e);
 oder::Body* pdref_body(IRigidBody* rb);
 oder::Joint* pdref_joint(IJoint* j);
 void pdref_ray_stats(IPhysicsEngine* e, unsigned long long* rays, unsigned long long* tris);
+unsigned int pdref_get_frame(IPhysicsEngine* e);
+void pdref_set_frame(IPhysicsEngine* e, unsigned int f);
+int pdref_body_box(IRigidBody* rb, float* centre3, float* size3);
+int pdref_body_mesh(IRigidBody* rb, ITriMesh** mesh, float* offR9, float* off3);
 }
 
 using namespace D;
@@ -221,6 +225,7 @@ void pdref_get_state(void* hv, uint32_t* r) {
         CI(oldPointId, sc->oldPointId); CI(oldSplinePointId, sc->oldSplinePointId);
         CI(episodeSteps, 0); CI(nanFlag, 0);
         CI(thermalPrimed, c->tyres[0]->thermalModel->patches[5].inputT == 0.0f ? 1 : 0);
+        CI(physFrame, (int)pdref_get_frame(h->sim->physics.get()));
         for (size_t i = 0; i < c->probeHits.size() && i < PD_MAX_PROBES; ++i) putF(r, PD_OFF_PROBES + (int)i, c->probeHits[i]);
         for (size_t i = 0; i < c->lookAhead.size() && i < PD_LOOKAHEAD; ++i) putF(r, PD_OFF_LOOKAHEAD + (int)i, c->lookAhead[i]);
 #undef CF
@@ -280,6 +285,7 @@ void pdref_set_state(void* hv, const uint32_t* r) {
         c->lastVelocity = vec3f(CF(lastVelX), CF(lastVelY), CF(lastVelZ)); c->accG = vec3f(CF(accGX), CF(accGY), CF(accGZ));
         c->fuel = CD(fuel); c->sleepingFrames = CI(sleepingFrames); c->water->t = CF(waterT); c->speed.value = CF(speed);
         c->collisionFlag = CI(collisionFlag) != 0; c->outOfTrackFlag = CI(outOfTrackFlag) != 0;
+        pdref_set_frame(h->sim->physics.get(), (unsigned int)CI(physFrame));
         c->nearestTrackPointId = CI(nearestTrackPointId); c->oldTrackPointId = CI(oldTrackPointId); c->splinePointId = CI(splinePointId);
         c->lastTrackPointTimestamp = CF(lastTrackPointTimestamp); c->trackLocation = CF(trackLocation); c->oldTrackLocation = CF(oldTrackLocation);
         c->bodyVsTrack = CF(bodyVsTrack); c->velocityVsTrack = CF(velocityVsTrack);
@@ -429,6 +435,30 @@ void pdref_get_params(void* hv, PdCarParams* P) {
     P->fuelConsumptionRate = sim->fuelConsumptionRate; P->tyreConsumptionRate = sim->tyreConsumptionRate; P->mechanicalDamageRate = sim->mechanicalDamageRate;
     P->allowTyreBlankets = sim->allowTyreBlankets ? 1 : 0;
     { oder::World* w = pdref_world(sim->physics.get()); P->gravityY = w->gravity[1]; P->worldERP = w->erp; P->worldCFM = w->cfm; }
+    { /* colliders exactly as the physics engine received them (CarColliderManager.cpp:32, Car.cpp:377) */
+        P->hasBoxCollider = pdref_body_box(c->body.get(), P->boxCentre, P->boxSize) > 0 ? 1 : 0;
+        ITriMesh* mesh = nullptr; float off[3] = {0, 0, 0}, r[9];
+        if (pdref_body_mesh(c->body.get(), &mesh, r, off) > 0 && mesh) {
+            P->nColliderVerts = (int)mesh->getVertexCount(); P->nColliderTris = (int)(mesh->getIndexCount() / 3);
+            for (int k = 0; k < 3; ++k) { P->colliderMin[k] = 3.4e38f; P->colliderMax[k] = -3.4e38f; }
+            const TriMeshVertex* vb = mesh->getVB(); const TriMeshIndex* ib = mesh->getIB();
+            for (int i = 0; i < P->nColliderVerts && i < PD_MAX_COLLIDER_VERTS; ++i) {
+                const float v[3] = {(r[0] * vb[i].x + r[1] * vb[i].y + r[2] * vb[i].z) + off[0], (r[3] * vb[i].x + r[4] * vb[i].y + r[5] * vb[i].z) + off[1], (r[6] * vb[i].x + r[7] * vb[i].y + r[8] * vb[i].z) + off[2]};
+                for (int k = 0; k < 3; ++k) { P->colliderVerts[i][k] = v[k]; P->colliderMin[k] = std::min(P->colliderMin[k], v[k]); P->colliderMax[k] = std::max(P->colliderMax[k], v[k]); }
+            }
+            for (int t = 0; t < P->nColliderTris && t < PD_MAX_COLLIDER_TRIS; ++t) for (int k = 0; k < 3; ++k) P->colliderTris[t][k] = (uint8_t)ib[t * 3 + k];
+            for (int t = 0; t < P->nColliderTris && t < PD_MAX_COLLIDER_TRIS; ++t) for (int k = 0; k < 3; ++k) {   /* derived filter data of the product's layout */
+                const float a = P->colliderVerts[P->colliderTris[t][0]][k], b = P->colliderVerts[P->colliderTris[t][1]][k], c2 = P->colliderVerts[P->colliderTris[t][2]][k];
+                P->colliderTriBounds[t][k] = std::min(a, std::min(b, c2)) - 1e-4f; P->colliderTriBounds[t][3 + k] = std::max(a, std::max(b, c2)) + 1e-4f;
+            }
+            for (int t = 0; t < P->nColliderTris && t < PD_MAX_COLLIDER_TRIS; ++t) {
+                float cc[3], r2 = 0.0f;
+                for (int k = 0; k < 3; ++k) cc[k] = 0.5f * (P->colliderTriBounds[t][k] + P->colliderTriBounds[t][3 + k]);
+                for (int v = 0; v < 3; ++v) { float d2 = 0.0f; for (int k = 0; k < 3; ++k) { const float d = P->colliderVerts[P->colliderTris[t][v]][k] - cc[k]; d2 += d * d; } r2 = std::max(r2, d2); }
+                P->colliderTriSphere[t][0] = cc[0]; P->colliderTriSphere[t][1] = cc[1]; P->colliderTriSphere[t][2] = cc[2]; P->colliderTriSphere[t][3] = sqrtf(r2) * 1.0001f + 1e-4f;
+            }
+        }
+    }
 }
 
 /* track-level derived data (Track::initTrackPoints, Track.cpp:178-272) for loader parity */
@@ -474,6 +504,8 @@ void pdref_raycast(void* hv, int n, const float* in, float* out) {
         q[7] = hit.hasContact ? (float)surface_index(t, (Surface*)hit.collisionObject->getUserPointer()) : -1.0f;
     }
 }
+unsigned int pdref_frame(void* hv) { return pdref_get_frame(((RefSim*)hv)->sim->physics.get()); }
+void pdref_set_frame_counter(void* hv, unsigned int f) { pdref_set_frame(((RefSim*)hv)->sim->physics.get(), f); }
 void pdref_ray_statistics(void* hv, unsigned long long* rays, unsigned long long* tris) { pdref_ray_stats(((RefSim*)hv)->sim->physics.get(), rays, tris); }
 int pdref_num_rows(void* hv) { return pdref_world(((RefSim*)hv)->sim->physics.get())->last_m; }
 

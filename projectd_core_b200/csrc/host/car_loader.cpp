@@ -19,6 +19,8 @@
  * relative rotations) with a minimal host-side body.  Anything the kernels do not implement is rejected
  * here, loudly, instead of being silently ignored.
  */
+#include <cstdio>
+#include <algorithm>
 #include "pd_host.h"
 #include <algorithm>
 #include <cmath>
@@ -460,6 +462,55 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
     if (fuel == 0.0f) fuel = 30.0f;
     P.requestedFuel = (float)fuel;
     car.getFloat3("FUELTANK", "POSITION", P.fuelTankPos);
+    { /* ---- colliders: CarColliderManager::init (CarColliderManager.cpp:12-34) + Car::loadColliderBlob (Car.cpp:318-379) ---- */
+        Ini col(dataPath + "colliders.ini");
+        if (!col.ready) throw Error("cannot read " + dataPath + "colliders.ini");
+        if (col.hasSection("COLLIDER_0")) { P.hasBoxCollider = 1; col.getFloat3("COLLIDER_0", "CENTRE", P.boxCentre); col.getFloat3("COLLIDER_0", "SIZE", P.boxSize); }
+        if (col.hasSection("COLLIDER_1")) throw Error("cars with more than one box collider are not supported yet");
+        float goff[3]; car.getFloat3("BASIC", "GRAPHICS_OFFSET", goff);
+        /* geom offset = Car::getGraphicsOffsetMatrix() at construction (Car.cpp:1407-1424): translation GRAPHICS_OFFSET, rotation =
+           mat44f::createFromAxisAngle((1,0,0), GRAPHICS_PITCH_ROTATION) (Core/Math.cpp:88-118), handed to ODE transposed
+           (RigidBodyODE.cpp:300-312): local = r * v + offset */
+        const float pitch = (float)(car.getFloat("BASIC", "GRAPHICS_PITCH_ROTATION") * (M_PI / 180.0f));
+        float r[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (pitch != 0.0f) {
+            const float sin_a = sinf(pitch), cos_a = cosf(pitch), om = 1.0f - cos_a;
+            const float ax = 1.0f, ay = 0.0f, az = 0.0f;
+            const float M11 = ((ax * ax) * om) + cos_a, M22 = ((ay * ay) * om) + cos_a, M33 = ((az * az) * om) + cos_a;
+            const float M12 = (az * sin_a) + (ay * ax) * om, M23 = (ax * sin_a) + (az * ay) * om, M31 = (ay * sin_a) + (az * ax) * om;
+            const float M13 = (az * ax) * om - (ay * sin_a), M21 = (ay * ax) * om - (az * sin_a), M32 = (az * ay) * om - (ax * sin_a);
+            const float rr[9] = {M11, M21, M31, M12, M22, M32, M13, M23, M33};
+            for (int k = 0; k < 9; ++k) r[k] = rr[k];
+        }
+        FILE* f = fopen((dataPath + "collider.bin").c_str(), "rb");
+        if (!f) throw Error("cannot read " + dataPath + "collider.bin");
+        uint32_t hdr[3] = {0, 0, 0};
+        bool ok = fread(hdr, 4, 3, f) == 3 && hdr[1] > 0 && hdr[2] > 0 && hdr[1] <= PD_MAX_COLLIDER_VERTS && hdr[2] % 3 == 0 && hdr[2] / 3 <= PD_MAX_COLLIDER_TRIS;
+        std::vector<float> v(ok ? hdr[1] * 3 : 0); std::vector<uint16_t> ix(ok ? hdr[2] : 0);
+        ok = ok && fread(v.data(), 12, hdr[1], f) == hdr[1] && fread(ix.data(), 2, hdr[2], f) == hdr[2];
+        fclose(f);
+        if (!ok) throw Error("collider.bin: malformed or larger than PD_MAX_COLLIDER_VERTS / PD_MAX_COLLIDER_TRIS");
+        P.nColliderVerts = (int32_t)hdr[1]; P.nColliderTris = (int32_t)(hdr[2] / 3);
+        for (int k = 0; k < 3; ++k) { P.colliderMin[k] = 3.4e38f; P.colliderMax[k] = -3.4e38f; }
+        for (int i = 0; i < P.nColliderVerts; ++i) for (int k = 0; k < 3; ++k) {
+            const float x = (r[k * 3 + 0] * v[i * 3 + 0] + r[k * 3 + 1] * v[i * 3 + 1] + r[k * 3 + 2] * v[i * 3 + 2]) + goff[k];
+            P.colliderVerts[i][k] = x; P.colliderMin[k] = std::min(P.colliderMin[k], x); P.colliderMax[k] = std::max(P.colliderMax[k], x);
+        }
+        for (int t = 0; t < P.nColliderTris; ++t) for (int k = 0; k < 3; ++k) {
+            if (ix[t * 3 + k] >= hdr[1]) throw Error("collider.bin: index out of range");
+            P.colliderTris[t][k] = (uint8_t)ix[t * 3 + k];
+        }
+        for (int t = 0; t < P.nColliderTris; ++t) for (int k = 0; k < 3; ++k) {
+            const float a = P.colliderVerts[P.colliderTris[t][0]][k], b = P.colliderVerts[P.colliderTris[t][1]][k], c = P.colliderVerts[P.colliderTris[t][2]][k];
+            P.colliderTriBounds[t][k] = std::min(a, std::min(b, c)) - 1e-4f; P.colliderTriBounds[t][3 + k] = std::max(a, std::max(b, c)) + 1e-4f;
+        }
+        for (int t = 0; t < P.nColliderTris; ++t) {   /* bounding sphere about the box centre */
+            float c[3], r2 = 0.0f;
+            for (int k = 0; k < 3; ++k) c[k] = 0.5f * (P.colliderTriBounds[t][k] + P.colliderTriBounds[t][3 + k]);
+            for (int v = 0; v < 3; ++v) { float d2 = 0.0f; for (int k = 0; k < 3; ++k) { const float d = P.colliderVerts[P.colliderTris[t][v]][k] - c[k]; d2 += d * d; } r2 = std::max(r2, d2); }
+            P.colliderTriSphere[t][0] = c[0]; P.colliderTriSphere[t][1] = c[1]; P.colliderTriSphere[t][2] = c[2]; P.colliderTriSphere[t][3] = sqrtf(r2) * 1.0001f + 1e-4f;
+        }
+    }
     P.framesToSleep = 50;
     P.waterTmass = 20.0f; P.waterCoolSpeedK = 0.002f; P.waterCoolFactor = 0.2f; P.waterHeatFactor = 1.0f;
     /* ---- bodies at construction: chassis at the origin, identity rotation (Car.cpp:38-51) ---- */

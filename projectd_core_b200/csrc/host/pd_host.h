@@ -90,6 +90,12 @@ struct TrackModel {
     std::vector<int32_t> ptStart, ptItems;     /* CSR per cell: fat point ids (by `best`) */
     std::vector<float> segRec;                 /* 8 floats per segItems entry: ax, az, bx, bz, best.xyz of the owning point, 0 */
     std::vector<float> ptRec;                  /* 4 floats per ptItems entry: best.xyz, id (as int bits) */
+    std::vector<float> triRaw;                 /* 9 floats per triangle (leaf order): v0, v1, v2 as stored in surfaces.bin */
+    PdBoundGrid collGrid;                      /* x-z grid over all triangles for collision detection */
+    std::vector<int32_t> collStart, collItems; /* CSR, two lists per cell: [2c] TRACK triangles, [2c+1] WALL triangles */
+    std::vector<float> collRec;                /* per collItems entry, 32 B: box min xyz, triangle index bits, box max xyz, 0; lists sorted by descending ymax */
+    std::vector<float> collCell;               /* per cell, 32 B: track y min / max, wall y min / max, then (int bits) first TRACK entry, first WALL entry, end */
+    std::vector<float> collY;                  /* per cell: y range of its TRACK triangles, y range of its WALL triangles */
 };
 void load_track(const std::string& basePath, const std::string& name, TrackModel& out);
 /* synthetic track generator for config 4 (large mesh): closed loop of `nPoints` spline points, tessellated */

@@ -98,6 +98,76 @@ void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& sur
     }
     out.info.nTris = (int32_t)nt; out.info.nNodes = (int32_t)out.nodes.size();
     build_column_grid(out);
+    /* collision detection (pd_collide.h): the triangles' own vertices (the separating-axis and edge tests start from the
+       vertices, not from the rounded edge vectors of `tris`) and a 2 m x-z grid over ALL triangles, two lists per cell (TRACK, WALL) */
+    out.triRaw.assign((size_t)nt * 9, 0.0f);
+    for (uint32_t i = 0; i < nt; ++i) memcpy(&out.triRaw[(size_t)i * 9], &verts9[(size_t)B.order[i] * 9], 36);
+    {
+        PdBoundGrid& G = out.collGrid; memset(&G, 0, sizeof(G));
+        out.collStart.assign(1, 0); out.collItems.clear();
+        if (nt > 0) {
+            float x0 = 3.4e38f, x1 = -3.4e38f, z0 = 3.4e38f, z1 = -3.4e38f;
+            for (uint32_t i = 0; i < nt; ++i) for (int v = 0; v < 3; ++v) { const float* p = &out.triRaw[(size_t)i * 9 + v * 3]; x0 = std::min(x0, p[0]); x1 = std::max(x1, p[0]); z0 = std::min(z0, p[2]); z1 = std::max(z1, p[2]); }
+            for (float cell = 2.0f;; cell *= 2.0f) {
+                G.cell = cell; G.invCell = 1.0f / cell; G.ox = x0 - cell; G.oz = z0 - cell;
+                G.nx = (int)ceilf((x1 - G.ox) * G.invCell) + 2; G.nz = (int)ceilf((z1 - G.oz) * G.invCell) + 2;
+                if ((double)G.nx * G.nz <= 4.0e6 || cell >= 64.0f) break;
+            }
+            const size_t nc = (size_t)G.nx * G.nz;
+            auto range = [&](uint32_t i, int& a, int& b, int& c, int& d) {
+                const float* p = &out.triRaw[(size_t)i * 9];
+                const float bx0 = std::min(p[0], std::min(p[3], p[6])) - 1e-3f, bx1 = std::max(p[0], std::max(p[3], p[6])) + 1e-3f;
+                const float bz0 = std::min(p[2], std::min(p[5], p[8])) - 1e-3f, bz1 = std::max(p[2], std::max(p[5], p[8])) + 1e-3f;
+                a = std::max(0, (int)floorf((bx0 - G.ox) * G.invCell)); b = std::min(G.nx - 1, (int)floorf((bx1 - G.ox) * G.invCell));
+                c = std::max(0, (int)floorf((bz0 - G.oz) * G.invCell)); d = std::min(G.nz - 1, (int)floorf((bz1 - G.oz) * G.invCell));
+            };
+            auto category = [&](uint32_t i) { const int32_t sid = out.triSurf[i]; return (sid >= 0 && sid < (int32_t)out.surfaces.size()) ? (out.surfaces[sid].collisionCategory & 3u) : 0u; };
+            /* per cell: TRACK triangles first, then WALL triangles (collStart[2c] .. collStart[2c+1] .. collStart[2c+2]), and the
+               height range of each part (collY[4c..]: track min, track max, wall min, wall max) so that a whole cell is skipped
+               when the collider's box does not reach its triangles */
+            std::vector<int32_t> count(2 * nc + 1, 0);
+            out.collY.assign(4 * nc, 0.0f);
+            for (size_t c = 0; c < nc; ++c) { out.collY[4 * c] = 3.4e38f; out.collY[4 * c + 1] = -3.4e38f; out.collY[4 * c + 2] = 3.4e38f; out.collY[4 * c + 3] = -3.4e38f; }
+            for (uint32_t i = 0; i < nt; ++i) {
+                const uint32_t cat = category(i); if (cat != 1u && cat != 2u) continue;
+                const float* p = &out.triRaw[(size_t)i * 9];
+                const float y0 = std::min(p[1], std::min(p[4], p[7])), y1 = std::max(p[1], std::max(p[4], p[7]));
+                int a2, b2, c2, d2; range(i, a2, b2, c2, d2);
+                for (int iz = c2; iz <= d2; ++iz) for (int ix = a2; ix <= b2; ++ix) {
+                    const size_t c = (size_t)iz * G.nx + ix;
+                    count[2 * c + (cat - 1) + 1]++;
+                    float* yr = &out.collY[4 * c + 2 * (cat - 1)]; yr[0] = std::min(yr[0], y0); yr[1] = std::max(yr[1], y1);
+                }
+            }
+            for (size_t c = 0; c < 2 * nc; ++c) count[c + 1] += count[c];
+            out.collStart = count; out.collItems.assign((size_t)count[2 * nc], 0);
+            std::vector<int32_t> fill(count.begin(), count.end() - 1);
+            for (uint32_t i = 0; i < nt; ++i) {
+                const uint32_t cat = category(i); if (cat != 1u && cat != 2u) continue;
+                int a2, b2, c2, d2; range(i, a2, b2, c2, d2);
+                for (int iz = c2; iz <= d2; ++iz) for (int ix = a2; ix <= b2; ++ix) out.collItems[(size_t)fill[2 * ((size_t)iz * G.nx + ix) + (cat - 1)]++] = (int32_t)i;
+            }
+            /* entries carry the triangle's own box, so that most are dismissed without touching the triangle; every list is
+               sorted by descending top (ymax): a collider whose underside is above an entry's top is above all that follow */
+            auto ymax_of = [&](int32_t i) { const float* p = &out.triRaw[(size_t)i * 9]; return std::max(p[1], std::max(p[4], p[7])); };
+            for (size_t l = 0; l < 2 * nc; ++l) std::stable_sort(out.collItems.begin() + count[l], out.collItems.begin() + count[l + 1], [&](int32_t x, int32_t y) { return ymax_of(x) > ymax_of(y); });
+            out.collRec.assign(out.collItems.size() * 8, 0.0f);
+            for (size_t k = 0; k < out.collItems.size(); ++k) {
+                const int32_t i = out.collItems[k]; const float* p = &out.triRaw[(size_t)i * 9]; float* q = &out.collRec[k * 8];
+                for (int d = 0; d < 3; ++d) { q[d] = std::min(p[d], std::min(p[3 + d], p[6 + d])); q[4 + d] = std::max(p[d], std::max(p[3 + d], p[6 + d])); }
+                memcpy(&q[3], &i, 4);
+            }
+            /* one 32-byte header per cell: y ranges of its two lists and their bounds in collRec */
+            out.collCell.assign(nc * 8, 0.0f);
+            for (size_t c = 0; c < nc; ++c) {
+                float* q = &out.collCell[c * 8];
+                q[0] = out.collY[4 * c]; q[1] = out.collY[4 * c + 1]; q[2] = out.collY[4 * c + 2]; q[3] = out.collY[4 * c + 3];
+                const int32_t k[3] = {count[2 * c], count[2 * c + 1], count[2 * c + 2]};
+                memcpy(&q[4], k, 12);
+            }
+            if (getenv("PD_TRACK_STATS")) fprintf(stderr, "[pd] collision grid: cell %.1f m, %d x %d cells, %zu entries\n", G.cell, G.nx, G.nz, out.collItems.size());
+        }
+    }
 }
 
 /* Index for VERTICAL rays (every ray of the hot path is one: wheel rays Tyre.cpp:478-481, the teleport ray

@@ -44,6 +44,7 @@ struct EnvIO {
      * (teleport + the reset's zero-action tick, projectd_env.py:216-227), its action of that step is ignored */
     int32_t* pending;            /* [n] 1 = finished at the previous step (null: no in-kernel reset) */
     uint32_t* episodeCtr; uint64_t seed, idOffset; int teleportMode;
+    const int32_t* collIn;       /* [n] k_collide's answer for this tick's start pose (0 / 1; -1 = test inside the tick); null: test inside the tick */
     long long* clk;              /* profiling aid (PD_DEBUG_CLOCKS=1): SM cycles each warp spent in the tick, [blocks * 2]; null otherwise */
 };
 
@@ -117,13 +118,14 @@ __global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ Pd
     float pd_rows[PD_GSCR_WORDS];
 #endif
     const bool resetNow = on && io.pending && io.pending[e];
+    const int collPre = (on && io.collIn && !resetNow) ? io.collIn[e] : -1;
     if (on) {
         if (resetNow) env_reset_in_kernel(P, T, sv, e, io, time);
         else if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
 #if PD_SERIAL_SMEM_SCRATCH
-        car_tick<1, PD_BLOCK>(P, T, sv, dt, time, pd_rows, pd_scrD + threadIdx.x);
+        car_tick<1, PD_BLOCK>(P, T, sv, dt, time, pd_rows, pd_scrD + threadIdx.x, collPre);
 #else
-        car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows + PD_GSCR_ROWS_WORDS);
+        car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows + PD_GSCR_ROWS_WORDS, collPre);
 #endif
     }
     if (io.clk && (threadIdx.x & 31) == 0) io.clk[blockIdx.x * (PD_BLOCK / 32) + (threadIdx.x >> 5)] = clock64() - clk0;
@@ -204,16 +206,17 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
 #if defined(PD_PHASE_CLOCKS)
         ex.ph = (io.clk && wl == 0) ? io.clk + 4096 + (size_t)(blockIdx.x * 2 + warp) * 32 : nullptr;   /* profiling build: 32 stamps per warp after the per-warp totals */
 #endif
-        if (io.pending && io.pending[e]) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
+        int collPre = io.collIn ? io.collIn[e] : -1;
+        if (io.pending && io.pending[e]) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); collPre = -1; }
         else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
 #if PD_QUAD_LOCAL_SCRATCH == 1
         float lscr[PD_GSCR_WORDS];
-        car_tick_quad<1, 1>(P, T, sv, dt, time, ex, lscr, lscr + PD_GSCR_ROWS_WORDS);
+        car_tick_quad<1, 1>(P, T, sv, dt, time, ex, lscr, lscr + PD_GSCR_ROWS_WORDS, collPre);
 #elif PD_QUAD_LOCAL_SCRATCH == 2
         float lrows[PD_GSCR_ROWS_WORDS];                     /* JA | JB in local memory, Y | D | dg in shared memory */
-        car_tick_quad<1, QLANES>(P, T, sv, dt, time, ex, lrows, scratch + cid);
+        car_tick_quad<1, QLANES>(P, T, sv, dt, time, ex, lrows, scratch + cid, collPre);
 #else
-        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid);
+        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid, collPre);
 #endif
     }
     if (io.clk && wl == 0) io.clk[blockIdx.x * 2 + warp] = clock64() - clk0;
@@ -228,6 +231,28 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
         env_epilogue(sv2, e2, on2, io, 0xffffffffu, reset2);
     }
     if (tid == 32) bulk_wait_all();                            /* the copy engine has read (and written) everything before the block retires */
+}
+
+/* Collision detection for the coming tick, ONE WARP PER CAR: the cells of the car's footprint are dealt to
+ * 4 groups of 8 lanes, the entries of a cell's lists to the 8 lanes of a group (pd_collide.h), the 32 answers are OR-ed.
+ * Runs ahead of the tick kernel on the same stream, on the tick's start pose (the pose collisionStep sees,
+ * PhysicsEngineODE.cpp:216-224); envs on an even physics frame answer 0 at once, envs about to be reset inside the tick
+ * kernel answer -1 (their pose changes first: the tick kernel tests them itself). */
+#define PD_COLLIDE_BLOCK 128
+__global__ void __launch_bounds__(PD_COLLIDE_BLOCK) k_collide(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, const uint32_t* __restrict__ state, int layout, int n,
+                                                              const int32_t* __restrict__ pending, int32_t* __restrict__ collOut, long long* __restrict__ dbg) {
+    const long long clk0 = dbg ? clock64() : 0;
+    const int e = (blockIdx.x * PD_COLLIDE_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= n) return;
+    SVR sv = sv_env(layout, const_cast<uint32_t*>(state), (size_t)e);
+    if (!(sv.i(PD_OFF_CAR + PD_CAR_o_physFrame) & 1)) { if (lane == 0) collOut[e] = 0; return; }
+    if (pending && pending[e]) { if (lane == 0) collOut[e] = -1; return; }
+    Body C; load_body(sv, PD_BODY_CHASSIS, C);
+    int stats[4] = {0, 0, 0, 0};
+    __shared__ __align__(16) float hullS[(PD_COLLIDE_BLOCK / 32) * PD_HULLS_WORDS];
+    const bool any = car_collide_warp(P, T, C, lane, hullS + (threadIdx.x >> 5) * PD_HULLS_WORDS, dbg ? stats : nullptr);
+    if (lane == 0) collOut[e] = any ? 1 : 0;
+    if (dbg && lane == 0) { dbg[4096 + (size_t)n * 12 + (size_t)e * 4] = clock64() - clk0; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 1] = ((long long)stats[0] << 32) | (unsigned)stats[1]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 2] = ((long long)stats[2] << 32) | (unsigned)stats[3]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 3] = any; }
 }
 
 /* initial record -> every env (both layouts) */
@@ -355,6 +380,8 @@ struct pd_batch {
     float* dReward = nullptr; float* dTotal = nullptr; int32_t* dFlags = nullptr; int32_t* dDone = nullptr;
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     long long* dClk = nullptr; int nClk = 0;
+    int32_t* dColl = nullptr;         /* k_collide's answers for the coming tick */
+    long long frameKnown = 0;         /* physics frame shared by all envs, or -1 when states were set individually (then k_collide runs every tick) */
     int32_t* dPending = nullptr; int autoreset = PD_AUTORESET_SAME_STEP;
     int resetMode = PD_TELEPORT_START;   /* ProjectDEnv.teleport_mode: the last pd_teleport_mode() mode, also used by the automatic resets */
     double time = 0, lastDt = 0;
@@ -429,6 +456,12 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = upload(b, &b->dev.colStart, b->track.colStart))) return rc;
     if ((rc = upload(b, &b->dev.colItems, b->track.colItems))) return rc;
     b->dev.colGrid = b->track.colGrid;
+    if ((rc = upload(b, &b->dev.triRaw, b->track.triRaw))) return rc;
+    if ((rc = upload(b, &b->dev.collStart, b->track.collStart))) return rc;
+    if ((rc = upload(b, &b->dev.collItems, b->track.collItems))) return rc;
+    if ((rc = upload(b, &b->dev.collCell, b->track.collCell))) return rc;
+    if ((rc = upload(b, &b->dev.collRec, b->track.collRec))) return rc;
+    b->dev.collGrid = b->track.collGrid;
     b->dev.info = b->track.info;
     const size_t n = (size_t)n_envs;
     const size_t nAlloc = state_alloc_words(b->layout, n);
@@ -449,6 +482,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = dalloc(b, &b->dEnvLen, n))) return rc;
     if ((rc = dalloc(b, &b->dStats, 8))) return rc;
     if ((rc = dalloc(b, &b->dPending, n))) return rc;
+    if ((rc = dalloc(b, &b->dColl, n))) return rc;
     CK(cudaMemsetAsync(b->dPending, 0, n * 4, b->stream));
     if (getenv("PD_DEBUG_CLOCKS")) { b->nClk = (int)(n / 4 + 64);
 #if defined(PD_PHASE_CLOCKS)
@@ -474,6 +508,14 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
 
 static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO& io_in) {
     EnvIO io = io_in; io.clk = mask ? nullptr : b->dClk;
+    if (!mask) {
+        /* collision detection runs ahead of the tick as its own launch (a warp per car) on odd physics frames */
+        if (b->frameKnown < 0 || (b->frameKnown & 1)) {
+            k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr); b->launches++;
+            io.collIn = b->dColl;
+        }
+        if (b->frameKnown >= 0) b->frameKnown++;
+    } else b->frameKnown = -1;          /* a masked tick advances only some envs: frames are no longer in lock step */
     if (b->layout == PD_LAYOUT_RECORDS)
         switch (b->quadCpw) {
         case 2: k_tick_quad<2><<<grid(b->n, 4), PD_QBLOCK, PD_QUAD_SMEM_BYTES_(2), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
@@ -681,7 +723,7 @@ int pd_debug_read_clocks(pd_batch* b, long long* out, int cap) {
     const int blocks = b->layout == PD_LAYOUT_RECORDS ? grid(b->n, 2 * b->quadCpw) : grid(b->n, PD_BLOCK);
     int cnt = blocks * 2;
 #if defined(PD_PHASE_CLOCKS)
-    cnt = 4096 + blocks * 2 * 32;
+    cnt = b->nClk; (void)blocks;
 #endif
     if (cnt > cap) cnt = cap; if (cnt > b->nClk) cnt = b->nClk;
     if (cudaMemcpyAsync(out, b->dClk, (size_t)cnt * 8, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess) return 0;
@@ -702,6 +744,7 @@ int pd_get_state(pd_batch* b, int env, uint32_t* record) {
 }
 int pd_set_state(pd_batch* b, int env, const uint32_t* record) {
     if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
+    b->frameKnown = -1;
     if (b->layout == PD_LAYOUT_RECORDS) CK(cudaMemcpyAsync(b->dState + (size_t)env * PD_STATE_STRIDE, record, PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream));
     else CK(cudaMemcpy2DAsync(b->dState + state_index_tiled(0, (size_t)env), (size_t)PD_TILE * 4, record, 4, 4, PD_STATE_WORDS, cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream)); return PD_OK;
@@ -723,7 +766,7 @@ static int pack_common(pd_batch* b, uint32_t* host_buf, int toDevice) {
     return rc;
 }
 int pd_snapshot(pd_batch* b, uint32_t* host_buf) { if (!b || !host_buf) return PD_ERR_ARG; return pack_common(b, host_buf, 0); }
-int pd_restore(pd_batch* b, const uint32_t* host_buf) { if (!b || !host_buf) return PD_ERR_ARG; return pack_common(b, const_cast<uint32_t*>(host_buf), 1); }
+int pd_restore(pd_batch* b, const uint32_t* host_buf) { if (!b || !host_buf) return PD_ERR_ARG; b->frameKnown = -1; return pack_common(b, const_cast<uint32_t*>(host_buf), 1); }
 int pd_get_params(const pd_batch* b, PdCarParams* out) { if (!b || !out) return PD_ERR_ARG; *out = b->car.P; return PD_OK; }
 int pd_get_track_info(const pd_batch* b, PdTrackInfo* out) { if (!b || !out) return PD_ERR_ARG; *out = b->track.info; return PD_OK; }
 

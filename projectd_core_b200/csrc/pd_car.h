@@ -588,8 +588,10 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
 /* ================================ aero ================================ */
 /* AeroMap::step -> Wing::step / addDrag / addLift (AeroMap.cpp:83-96, Wing.cpp:71-204); wind is zero
  * (Simulator::stepWind is compiled out, Simulator.cpp:203-224) so getGroundWindVector contributes 0 */
-PD_HD void aero_step(const PdCarParams& PP, Body& C) {
-    for (int i = 0; i < PP.nWings; ++i) {
+/* wings first, first + step, ...: the quad kernel gives each lane its own wings (their forces meet in the quad-wide
+ * sum of the chassis force), the thread-per-car kernel passes (0, 1) */
+PD_HD void aero_step(const PdCarParams& PP, Body& C, int first = 0, int step = 1) {
+    for (int i = first; i < PP.nWings; i += step) {
         const PdWing& W = PP.wing[i];
         const V3 pos = v3(W.position[0], W.position[1], W.position[2]);
         const V3 vWorldVel = body_rel_point_vel(C, pos);

@@ -38,7 +38,7 @@ PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
 }
 
 template <int STRIDE, int STRIDE_D, class Ex, class SVX>
-PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD) {
+PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD, int collPre = -1) {
     const int lane = ex.lane;
     const bool front = lane < 2;
     /* Car-level state: with a stride-1 view (the shared-memory staging copy) the four lanes work IN PLACE on the
@@ -134,7 +134,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
         L.brakeTorque = ex.get(my.brakeTorque, w); L.handBrakeTorque = ex.get(my.handBrakeTorque, w); L.ndSlip = ex.get(my.ndSlip, w);
         L.slipRatio = ex.get(my.slipRatio, w); L.isLocked = ex.get(my.isLocked, w); L.surfaceId = ex.get(my.surfaceId, w);
     }
-    if (lane == 0) aero_step(P, C);
+    if (lane == 0) aero_step(P, C);          /* all wings on one lane: the chassis force is then accumulated in the reference's order (a per-lane split is ~2 % faster but re-associates the sum, and the 1 s free-running divergence test is sensitive to that) */
     V3 steerA1 = v3(0, 0, 0), steerA2 = v3(0, 0, 0);
     if (front) { /* SteeringSystem::step */
         const float steer = -c.finalSteerAngleSignal * P.steerLinearRatio;
@@ -178,6 +178,14 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
         if (lane == 2) { W.F += f3; W.T += t3; }
     }
 
+    /* ---------------- collisionStep (odd frames): the cell lists are dealt to the four lanes, any hit sets the flag ---------------- */
+    if (c.physFrame & 1) {
+        bool hitAny;
+        if (collPre >= 0) hitAny = collPre != 0;          /* answered by k_collide for this tick's start pose */
+        else { const bool hit = car_collide(P, T, C, lane, 4); hitAny = !ex.all(!hit); }
+        if (hitAny) c.collisionFlag = 1;
+    }
+    c.physFrame++;
     /* ---------------- dWorldStep: one joint group per lane ---------------- */
     PD_PHASE(X, 8);
     const float h = dt, hinv = 1.0f / dt;
@@ -296,7 +304,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     }
     ex.sync();
     PD_PHASE(X, 16);
-    post_lookahead(P, T, C, c);
+    post_lookahead_quad(P, T, C, c, ex);
     post_scoring(P, T, C, X, dt);
     c.episodeSteps++; c.thermalPrimed = 1;
     if (bad) c.nanFlag = 1;

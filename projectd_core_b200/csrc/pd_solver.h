@@ -231,25 +231,52 @@ PD_HD void jinvm6(const float* J, const BodyDyn& d, float* o) {
  * loops are unrolled.  n = rows to process: the 4-lanes-per-car kernel runs all PD_GMAX rows on every lane (padding
  * rows are identity, so there is no divergence); the thread-per-car kernel passes the group's real row count. */
 template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6, const int n = PD_GMAX, const bool hasB = true) {
+    /* D build, TWO rows per pass: rows i and i+1 share every load of the rows j <= i they are multiplied with
+     * (half the scratch reads, two independent sums in flight); each sum runs over the same terms in the same order
+     * as a row-at-a-time build, so the result is bit-identical to it. */
     PD_NOUNROLL
-    for (int i = 0; i < n; ++i) {
-        float ra[6], rb[6], ja[6], jb[6];
+    for (int i = 0; i < n; i += 2) {
+        const bool two = i + 1 < n;
+        const int i1 = two ? i + 1 : i;
+        float ra0[6], rb0[6], ja0[6], jb0[6], ra1[6], rb1[6], ja1[6], jb1[6];
         PD_UNROLL
-        for (int k = 0; k < 6; ++k) { ra[k] = G.JA(i, k); rb[k] = G.JB(i, k); }
-        jinvm6(ra, dA, ja);
-        if (hasB) jinvm6(rb, dB, jb);
+        for (int k = 0; k < 6; ++k) { ra0[k] = G.JA(i, k); rb0[k] = G.JB(i, k); ra1[k] = G.JA(i1, k); rb1[k] = G.JB(i1, k); }
+        jinvm6(ra0, dA, ja0); jinvm6(ra1, dA, ja1);
+        if (hasB) { jinvm6(rb0, dB, jb0); jinvm6(rb1, dB, jb1); }
         PD_NOUNROLL
         for (int j = 0; j <= i; ++j) {
-            float s = ja[0] * G.JA(j, 0) + ja[1] * G.JA(j, 1) + ja[2] * G.JA(j, 2) + ja[3] * G.JA(j, 3) + ja[4] * G.JA(j, 4) + ja[5] * G.JA(j, 5);
-            if (hasB) s += jb[0] * G.JB(j, 0) + jb[1] * G.JB(j, 1) + jb[2] * G.JB(j, 2) + jb[3] * G.JB(j, 3) + jb[4] * G.JB(j, 4) + jb[5] * G.JB(j, 5);
-            G.D(i, j) = s;
+            float a[6], b[6];
+            PD_UNROLL
+            for (int k = 0; k < 6; ++k) { a[k] = G.JA(j, k); if (hasB) b[k] = G.JB(j, k); }
+            float s0 = ja0[0] * a[0] + ja0[1] * a[1] + ja0[2] * a[2] + ja0[3] * a[3] + ja0[4] * a[4] + ja0[5] * a[5];
+            float s1 = ja1[0] * a[0] + ja1[1] * a[1] + ja1[2] * a[2] + ja1[3] * a[3] + ja1[4] * a[4] + ja1[5] * a[5];
+            if (hasB) {
+                s0 += jb0[0] * b[0] + jb0[1] * b[1] + jb0[2] * b[2] + jb0[3] * b[3] + jb0[4] * b[4] + jb0[5] * b[5];
+                s1 += jb1[0] * b[0] + jb1[1] * b[1] + jb1[2] * b[2] + jb1[3] * b[3] + jb1[4] * b[4] + jb1[5] * b[5];
+            }
+            G.D(i, j) = s0;
+            if (two) G.D(i1, j) = s1;
         }
         G.D(i, i) += G.dg(i) * hinv;
+        if (two) {      /* the second row's own diagonal entry */
+            float s1 = ja1[0] * ra1[0] + ja1[1] * ra1[1] + ja1[2] * ra1[2] + ja1[3] * ra1[3] + ja1[4] * ra1[4] + ja1[5] * ra1[5];
+            if (hasB) s1 += jb1[0] * rb1[0] + jb1[1] * rb1[1] + jb1[2] * rb1[2] + jb1[3] * rb1[3] + jb1[4] * rb1[4] + jb1[5] * rb1[5];
+            G.D(i1, i1) = s1;
+            G.D(i1, i1) += G.dg(i1) * hinv;
+        }
         /* r_i = c_i/h - J_i (v/h + M^-1 f) */
-        float s = ra[0] * dA.t1[0] + ra[1] * dA.t1[1] + ra[2] * dA.t1[2] + ra[3] * dA.t1[3] + ra[4] * dA.t1[4] + ra[5] * dA.t1[5];
-        s += G.Y(i, 0) * dC.t1[0] + G.Y(i, 1) * dC.t1[1] + G.Y(i, 2) * dC.t1[2] + G.Y(i, 3) * dC.t1[3] + G.Y(i, 4) * dC.t1[4] + G.Y(i, 5) * dC.t1[5];
-        if (hasB) s += rb[0] * dB.t1[0] + rb[1] * dB.t1[1] + rb[2] * dB.t1[2] + rb[3] * dB.t1[3] + rb[4] * dB.t1[4] + rb[5] * dB.t1[5];
-        G.Y(i, 6) = G.Y(i, 6) * hinv - s;
+        {
+            float s = ra0[0] * dA.t1[0] + ra0[1] * dA.t1[1] + ra0[2] * dA.t1[2] + ra0[3] * dA.t1[3] + ra0[4] * dA.t1[4] + ra0[5] * dA.t1[5];
+            s += G.Y(i, 0) * dC.t1[0] + G.Y(i, 1) * dC.t1[1] + G.Y(i, 2) * dC.t1[2] + G.Y(i, 3) * dC.t1[3] + G.Y(i, 4) * dC.t1[4] + G.Y(i, 5) * dC.t1[5];
+            if (hasB) s += rb0[0] * dB.t1[0] + rb0[1] * dB.t1[1] + rb0[2] * dB.t1[2] + rb0[3] * dB.t1[3] + rb0[4] * dB.t1[4] + rb0[5] * dB.t1[5];
+            G.Y(i, 6) = G.Y(i, 6) * hinv - s;
+        }
+        if (two) {
+            float s = ra1[0] * dA.t1[0] + ra1[1] * dA.t1[1] + ra1[2] * dA.t1[2] + ra1[3] * dA.t1[3] + ra1[4] * dA.t1[4] + ra1[5] * dA.t1[5];
+            s += G.Y(i1, 0) * dC.t1[0] + G.Y(i1, 1) * dC.t1[1] + G.Y(i1, 2) * dC.t1[2] + G.Y(i1, 3) * dC.t1[3] + G.Y(i1, 4) * dC.t1[4] + G.Y(i1, 5) * dC.t1[5];
+            if (hasB) s += rb1[0] * dB.t1[0] + rb1[1] * dB.t1[1] + rb1[2] * dB.t1[2] + rb1[3] * dB.t1[3] + rb1[4] * dB.t1[4] + rb1[5] * dB.t1[5];
+            G.Y(i1, 6) = G.Y(i1, 6) * hinv - s;
+        }
     }
     /* L D L^T, row by row (same recurrence as the oracle's dense factorisation), in place */
     PD_NOUNROLL
@@ -266,24 +293,46 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
         for (int j = 0; j < i; ++j) { const float u = G.D(i, j); const float lij = u / G.dg(j); dii -= u * lij; G.D(i, j) = lij; }
         G.dg(i) = dii;
     }
-    /* forward substitution on the 7 right-hand sides */
+    /* forward substitution on the 7 right-hand sides, two rows per pass (shared loads of the rows above, same
+     * subtraction order per row as the row-at-a-time form: bit-identical) */
     PD_NOUNROLL
-    for (int i = 0; i < n; ++i) {
-        float y[7];
+    for (int i = 0; i < n; i += 2) {
+        const bool two = i + 1 < n;
+        const int i1 = two ? i + 1 : i;
+        float y0[7], y1[7];
         PD_UNROLL
-        for (int k = 0; k < 7; ++k) y[k] = G.Y(i, k);
+        for (int k = 0; k < 7; ++k) { y0[k] = G.Y(i, k); y1[k] = G.Y(i1, k); }
         PD_NOUNROLL
-        for (int j = 0; j < i; ++j) { const float l = G.D(i, j); PD_UNROLL for (int k = 0; k < 7; ++k) y[k] -= l * G.Y(j, k); }
-        PD_UNROLL
-        for (int k = 0; k < 7; ++k) G.Y(i, k) = y[k];
-        /* S += Yu^T D^-1 Yu ; b += Yu^T D^-1 yr */
-        const float di = 1.0f / G.dg(i);
-        PD_UNROLL
-        for (int a = 0; a < 6; ++a) {
-            const float ya = y[a] * di;
+        for (int j = 0; j < i; ++j) {
+            const float l0 = G.D(i, j), l1 = G.D(i1, j);
             PD_UNROLL
-            for (int bb = 0; bb < 6; ++bb) if (bb <= a) S21[a * (a + 1) / 2 + bb] += ya * y[bb];
-            b6[a] += ya * y[6];
+            for (int k = 0; k < 7; ++k) { const float yj = G.Y(j, k); y0[k] -= l0 * yj; y1[k] -= l1 * yj; }
+        }
+        PD_UNROLL
+        for (int k = 0; k < 7; ++k) G.Y(i, k) = y0[k];
+        /* S += Yu^T D^-1 Yu ; b += Yu^T D^-1 yr */
+        {
+            const float di = 1.0f / G.dg(i);
+            PD_UNROLL
+            for (int a = 0; a < 6; ++a) {
+                const float ya = y0[a] * di;
+                PD_UNROLL
+                for (int bb = 0; bb < 6; ++bb) if (bb <= a) S21[a * (a + 1) / 2 + bb] += ya * y0[bb];
+                b6[a] += ya * y0[6];
+            }
+        }
+        if (two) {
+            const float l = G.D(i1, i);
+            PD_UNROLL
+            for (int k = 0; k < 7; ++k) { y1[k] -= l * y0[k]; G.Y(i1, k) = y1[k]; }
+            const float di = 1.0f / G.dg(i1);
+            PD_UNROLL
+            for (int a = 0; a < 6; ++a) {
+                const float ya = y1[a] * di;
+                PD_UNROLL
+                for (int bb = 0; bb < 6; ++bb) if (bb <= a) S21[a * (a + 1) / 2 + bb] += ya * y1[bb];
+                b6[a] += ya * y1[6];
+            }
         }
     }
 }

@@ -5,6 +5,7 @@
  */
 #pragma once
 #include "pd_solver.h"
+#include "pd_collide.h"
 
 namespace pd {
 
@@ -162,6 +163,24 @@ PD_HD void post_lookahead(const PdCarParams& P, const TrackDev& T, const Body& C
     }
 }
 
+/* the same, look-ahead points dealt to the four lanes of a quad (point i on lane i & 3), results exchanged */
+template <class Ex> PD_HD void post_lookahead_quad(const PdCarParams& P, const TrackDev& T, const Body& C, CarS& c, Ex& ex) {
+    const V3 up = v3(0, 1, 0);
+    const V3 curTrackDir = track_direction_at_distance(T, c.trackLocation);
+    const V3 bodyFrontDir = norm(C.fr.az);
+    const float driveDir = signf_(dot(bodyFrontDir, curTrackDir));
+    const int cnt = (P.lookAheadCount < PD_LOOKAHEAD) ? P.lookAheadCount : PD_LOOKAHEAD;
+    float mine[2] = {0, 0};
+    for (int k = 0; k < 2; ++k) {
+        const int i = ex.lane + 4 * k;
+        if (i >= cnt) continue;
+        const float distanceNorm = c.trackLocation + ((P.lookAheadStep * (float)(i + 1)) / T.info.computedTrackLength) * driveDir;
+        const V3 dir = track_direction_at_distance(T, distanceNorm);
+        mine[k] = m_atan2(dot(cross(dir, curTrackDir), up), dot(curTrackDir, dir));
+    }
+    for (int i = 0; i < cnt; ++i) c.lookAhead[i] = ex.get((i < 4) ? mine[0] : mine[1], i & 3);
+}
+
 /* ScoringSystem::step = computeDriftScore + computeAgentReward (ScoringSystem.cpp:114-330) */
 PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, CarCtx& X, float dt) {
     CarS& c = X.c;
@@ -236,7 +255,7 @@ PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, 
 }
 
 /* the tick */
-template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch, float* scratchD) {
+template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch, float* scratchD, int collPre = -1) {
     CarS cLocal; CarS* cp = &cLocal;
     if constexpr (sv_traits<SVX>::in_place) cp = car_in_place(sv); else load_car(sv, cLocal);
     CarCtx X(*cp); X.dt = dt; X.time = physicsTime;
@@ -343,7 +362,10 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
         arb_step(P.arbK[1], C, A, f0.p, A, f1.p);
     }
 
-    /* ---------------- physics->step(dt): dWorldStep ---------------- */
+    /* ---------------- physics->step(dt): collisionStep (odd frames: car vs static meshes), then dWorldStep ---------------- */
+    /* collPre: the answer of k_collide for this tick's start pose (0 / 1), or -1 = not computed: test here */
+    if (c.physFrame & 1) { if (collPre >= 0 ? (collPre != 0) : car_collide(P, T, C, 0, 1)) c.collisionFlag = 1; }
+    c.physFrame++;
     world_step<STRIDE, STRIDE_D>(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, scratch, scratchD);
 
     /* ---------------- Car::postStep ---------------- */

@@ -58,6 +58,11 @@ struct TrackDev {
     PdBoundGrid grid;
     const int32_t* colStart; const int32_t* colItems;   /* vertical-ray index: triangles per x-z cell */
     PdBoundGrid colGrid;
+    const float* triRaw;      /* 9 floats per triangle: v0, v1, v2 (collision detection, pd_collide.h) */
+    const int32_t* collStart; const int32_t* collItems;  /* collision grid CSR, two lists per cell: TRACK triangles, WALL triangles */
+    const float* collRec;     /* per entry, 32 B: box min xyz, triangle index bits | box max xyz, 0 (lists sorted by descending ymax) */
+    const float* collCell;    /* per cell, 32 B: track y min / max, wall y min / max | first TRACK entry, first WALL entry, end (int bits), 0 */
+    PdBoundGrid collGrid;
     PdTrackInfo info;
 };
 

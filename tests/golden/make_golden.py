@@ -12,6 +12,8 @@ pyprojectd/projectd_env.py:118-136):
   tele_u/state                  teleportCarToSpline(u) states
   rays/ray_hits                 world rays vs the track trimesh
   sctm_in/out                   SCTM::solve inputs -> outputs for the 4 tyres
+  coll_before/coll_flag         collision detection: driving states with the whole car translated (towards
+                                walls / into the ground), physics frame odd -> Car::collisionFlag after one Simulator::step
 """
 import math
 import os
@@ -104,6 +106,33 @@ def main():
     for w in range(4):
         r.L.pdref_sctm_solve(r.h, w, m, x.ctypes.data, y[w].ctypes.data)
     out["sctm_in"] = x; out["sctm_out"] = y
+
+    # ---- collisions: whole-car translations of driving states; the flag after ONE step on an odd physics frame ----
+    lay = pdref.Layout()
+    bodies = ["chassis", "tank", "hub0", "strut0", "hub1", "strut1", "axle"]
+    cb, cf, ct = [], [], []
+    s = pdref.RefSim()
+    for case in range(600):
+        if case % 20 == 0:
+            s.teleport_spline(float(rng.uniform(0, 1)))
+            for t in range(int(rng.integers(5, 250))):
+                s.set_controls(steer=float(rng.uniform(-0.3, 0.3)), gas=0.8); s.step(DT)
+            base = s.state().copy(); tbase = s.time()
+        rec = base.copy()
+        dx, dz = rng.uniform(-9, 9, 2)
+        dy = 0.0 if rng.random() < 0.4 else float(rng.uniform(-0.3, 0.02))
+        if case % 5 == 0:
+            dx = dz = 0.0
+        for b in bodies:
+            lay.set(rec, b + ".px", lay.get(rec, b + ".px") + dx); lay.set(rec, b + ".py", lay.get(rec, b + ".py") + dy); lay.set(rec, b + ".pz", lay.get(rec, b + ".pz") + dz)
+        lay.set(rec, "car.physFrame", 1 + 2 * int(rng.integers(0, 50)))
+        s.set_state(rec); s.set_time(tbase)
+        cb.append(s.state().copy()); ct.append(tbase)
+        s.step(DT)
+        cf.append(lay.get(s.state(), "car.collisionFlag"))
+    s.close()
+    out["coll_before"] = np.stack(cb); out["coll_time"] = np.array(ct, np.float64); out["coll_flag"] = np.array(cf, np.int32)
+    print("collision cases: %d of %d flagged" % (int(np.sum(cf)), len(cf)))
 
     path = os.path.join(HERE, "demo_golden.npz")
     np.savez_compressed(path, **out)

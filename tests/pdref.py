@@ -57,6 +57,8 @@ def lib():
         L.pdref_sctm_solve.argtypes = [vp, i, i, vp, vp]
         L.pdref_raycast.argtypes = [vp, i, vp, vp]
         L.pdref_num_rows.argtypes = [vp]
+        L.pdref_frame.restype = ctypes.c_uint; L.pdref_frame.argtypes = [vp]
+        L.pdref_set_frame_counter.argtypes = [vp, ctypes.c_uint]
         _lib = L
     return _lib
 
@@ -105,6 +107,13 @@ class RefSim:
 
     def set_time(self, t):
         self.L.pdref_set_time(self.h, t)
+
+    def frame(self):
+        """PhysicsEngineODE::currentFrame: collisions against the static meshes are tested on odd frames only."""
+        return int(self.L.pdref_frame(self.h))
+
+    def set_frame(self, f):
+        self.L.pdref_set_frame_counter(self.h, int(f))
 
     def teleport_spline(self, u):
         self.L.pdref_teleport_spline(self.h, u)

@@ -307,3 +307,40 @@ def test_autoreset_next_step_equals_same_step(oracle, kernel, monkeypatch):
     assert checked >= n // 4, "too few episodes finished to check (%d)" % checked
     sa, sc = a.env_stats(), c.env_stats()
     assert sc[0] >= checked
+
+
+@pytest.mark.parametrize("kernel", ["k_tick_quad", "k_tick"])
+def test_collision_flag_matches_oracle(oracle, lay, golden, kernel, monkeypatch):
+    """SURVEY.md A14 on the GPU: collisionFlag after one tick on an odd physics frame for the golden collision cases
+    (whole car translated towards walls / into the ground) and for fresh random cases checked against the oracle live."""
+    monkeypatch.setenv("PD_QUAD_MAX_ENVS", "8192" if kernel == "k_tick_quad" else "0")
+    flags = golden["coll_flag"]; n = len(flags)
+    b = _batch(oracle, n)
+    assert b.tick_kernel() == kernel
+    b.restore(np.ascontiguousarray(golden["coll_before"].T)); b.set_time(float(golden["coll_time"][0]))
+    b.step(DT, 1)
+    out = b.snapshot()
+    off = lay.fields["car.collisionFlag"][0]
+    got = out[off].view(np.int32)
+    assert np.array_equal(got, flags), np.nonzero(got != flags)[0][:10]
+    # live cases: yawed cars near walls
+    rng = np.random.default_rng(11)
+    r = oracle.RefSim()
+    recs, want = [], []
+    bodies = ["chassis", "tank", "hub0", "strut0", "hub1", "strut1", "axle"]
+    for case in range(64):
+        r.teleport_spline(float(rng.uniform(0, 1)))
+        for t in range(30):
+            r.set_controls(steer=float(rng.uniform(-1, 1)), gas=1.0); r.step()
+        rec = r.state().copy()
+        dx, dz = rng.uniform(-8, 8, 2)
+        for bd in bodies:
+            lay.set(rec, bd + ".px", lay.get(rec, bd + ".px") + dx); lay.set(rec, bd + ".pz", lay.get(rec, bd + ".pz") + dz)
+        lay.set(rec, "car.physFrame", 1)
+        r.set_state(rec); recs.append(r.state().copy()); r.step()
+        want.append(lay.get(r.state(), "car.collisionFlag"))
+    b2 = _batch(oracle, 64)
+    b2.restore(np.ascontiguousarray(np.stack(recs).T)); b2.set_time(r.time() - DT)
+    b2.step(DT, 1)
+    got2 = b2.snapshot()[off].view(np.int32)
+    assert np.array_equal(got2, np.array(want, np.int32))

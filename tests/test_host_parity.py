@@ -132,3 +132,30 @@ def test_free_running_1s_vs_golden_trajectory(hostsim, hostsim_env, golden, lay)
     dp = [lay.get(rec, "chassis." + k) - lay.get(ref, "chassis." + k) for k in ("px", "py", "pz")]
     assert math.sqrt(sum(d * d for d in dp)) <= 0.05, dp
     assert lay.get(rec, "car.currentGear") == lay.get(ref, "car.currentGear")
+
+
+@pytest.mark.parametrize("variant", ["serial", "quad"])
+def test_collision_flag_vs_golden(hostsim, hostsim_env, golden, lay, variant):
+    """SURVEY.md A14: Car::collisionFlag after one tick on an odd physics frame, for driving states with the whole car
+    translated towards walls / into the ground (floor box vs TRACK meshes with the body-local normal filter, hull mesh
+    vs WALL meshes): the flag must equal the oracle's on every case."""
+    tick = hostsim.hs_tick if variant == "serial" else hostsim.hs_tick_quad
+    flags = golden["coll_flag"]
+    assert 0.1 < flags.mean() < 0.9
+    wrong = []
+    for k in range(0, len(flags), 1 if variant == "serial" else 3):
+        rec = golden["coll_before"][k].copy()
+        tick(hostsim_env, rec.ctypes.data, DT, float(golden["coll_time"][k]))
+        if lay.get(rec, "car.collisionFlag") != int(flags[k]):
+            wrong.append(k)
+    assert not wrong, wrong[:10]
+
+
+def test_no_collision_check_on_even_frames(hostsim, hostsim_env, golden, lay):
+    """PhysicsEngineODE::collisionStep tests the static meshes on odd frames only (PhysicsEngineODE.cpp:230-236)."""
+    ks = np.nonzero(golden["coll_flag"])[0][:20]
+    for k in ks:
+        rec = golden["coll_before"][k].copy()
+        lay.set(rec, "car.physFrame", 2)
+        hostsim.hs_tick(hostsim_env, rec.ctypes.data, DT, float(golden["coll_time"][k]))
+        assert lay.get(rec, "car.collisionFlag") == 0 and lay.get(rec, "car.physFrame") == 3

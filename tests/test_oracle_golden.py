@@ -14,10 +14,10 @@ DT = 1.0 / 333.0
 
 
 def test_golden_file_shape(golden):
-    lay_words = 627
+    lay_words = 628
     assert golden["traj_state"].shape == (41, lay_words)
     assert golden["pair_before"].shape == golden["pair_after"].shape and golden["pair_before"].shape[1] == lay_words
-    assert golden["params"].size == 7008
+    assert golden["params"].size == 13464
 
 
 def test_spline_cache_known_answers_oracle(oracle):
@@ -85,3 +85,12 @@ def test_restated_solver_constraint_properties(oracle, golden):
     # tank is fixed to the chassis: identical orientation
     dq = [lay.get(s, "tank.q" + k) - lay.get(s, "chassis.q" + k) for k in "wxyz"]
     assert max(abs(x) for x in dq) < 1e-4
+
+
+def test_oracle_reproduces_golden_collision_flags(oracle, golden):
+    lay = oracle.Layout()
+    r = oracle.RefSim()
+    for k in range(0, len(golden["coll_flag"]), 2):
+        r.set_state(golden["coll_before"][k]); r.set_time(float(golden["coll_time"][k]))
+        r.step(DT)
+        assert lay.get(r.state(), "car.collisionFlag") == int(golden["coll_flag"][k]), k

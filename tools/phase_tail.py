@@ -17,11 +17,11 @@ gen = torch.Generator(device=dev); gen.manual_seed(5)
 rew = torch.zeros(n, device=dev); done = torch.zeros(n, device=dev, dtype=torch.int32)
 names = ["load+prologue", "suspension", "ray cast", "tyre forces", "thermal", "exchange+aero+steer", "assists+drivetrain", "arb+force sums",
          "build rows", "factor", "schur+solve6", "backsolve+integrate+store", "probes", "nearest point", "(brute)", "probe exchange+spline+locator", "lookahead+scoring"]
-for t in range(pre + 3):
+for t in range(pre + 4):
     if t % 33 == 0:
         a = (torch.rand((n, 2), device=dev, generator=gen) * 2 - 1).contiguous(); torch.cuda.synchronize()
     b.env_step(a, 1.0 / 333.0, None, rew, done)
-    if t in (100, pre, pre + 2):
+    if t in (101, pre, pre + 1, pre + 3):
         c = b.debug_warp_clocks()
         nw = int((c[:4096] > 0).sum())
         tot = c[:nw].astype(np.float64)
