@@ -57,7 +57,7 @@ struct CollisionMeshR : public ICollisionObject {
     int gnx = 1, gnz = 1; float gcell = 1.0f;
     std::vector<std::vector<uint32_t>> cells;
     void buildGrid() {
-        const float target = 4.0f;
+        const float target = 1.5f;
         gnx = std::max(1, std::min(128, (int)ceilf((bbMax[0] - bbMin[0]) / target)));
         gnz = std::max(1, std::min(128, (int)ceilf((bbMax[2] - bbMin[2]) / target)));
         cells.assign((size_t)gnx * gnz, {});
@@ -77,6 +77,8 @@ struct CollisionMeshR : public ICollisionObject {
     unsigned long getGroup() override { return category; }
     unsigned long getMask() override { return mask; }
 };
+
+static const bool kDebugColl = getenv("PDREF_DEBUG_COLL") != nullptr, kDebugPairs = getenv("PDREF_DEBUG_PAIRS") != nullptr;
 
 struct BoxColliderR { vec3f centre, size; unsigned long category, mask; };
 struct MeshColliderR { std::shared_ptr<CollisionMeshR> mesh; float offR[9]; float offP[3]; };   /* geom offset: body-local = offR * v + offP */
@@ -282,6 +284,18 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
         /* onCollision (PhysicsEngineODE.cpp:284-341) -> collisionCallback; normal 0: see the header */
         if (cb) cb->onCollisionCallback(rb, shape0, nullptr, other, vec3f(0, 0, 0), vec3f(pos.x, pos.y, pos.z), 0.0f);
     }
+    /* candidate triangles of a static mesh near the world box [lo, hi]: the mesh's x-z grid (a spatial index only, it plays
+       the role of OPCODE's tree), every triangle once */
+    std::vector<uint32_t> cand;
+    std::vector<oder::CV3> hl;
+    void gather(CollisionMeshR& m, const float* lo, const float* hi) {
+        cand.clear();
+        const float sx = m.gnx / std::max(1e-6f, m.bbMax[0] - m.bbMin[0]), sz = m.gnz / std::max(1e-6f, m.bbMax[2] - m.bbMin[2]);
+        const int ix0 = std::max(0, std::min(m.gnx - 1, (int)floorf((lo[0] - m.bbMin[0]) * sx))), ix1 = std::max(0, std::min(m.gnx - 1, (int)floorf((hi[0] - m.bbMin[0]) * sx)));
+        const int iz0 = std::max(0, std::min(m.gnz - 1, (int)floorf((lo[2] - m.bbMin[2]) * sz))), iz1 = std::max(0, std::min(m.gnz - 1, (int)floorf((hi[2] - m.bbMin[2]) * sz)));
+        for (int iz = iz0; iz <= iz1; ++iz) for (int ix = ix0; ix <= ix1; ++ix) for (uint32_t t : m.cells[(size_t)iz * m.gnx + ix]) cand.push_back(t);
+        std::sort(cand.begin(), cand.end()); cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+    }
     void collideBodyStatic(RigidBodyR* rb) {
         const oder::Body& b = rb->b;
         const oder::CV3 A[3] = {oder::cv(b.R[0], b.R[3], b.R[6]), oder::cv(b.R[1], b.R[4], b.R[7]), oder::cv(b.R[2], b.R[5], b.R[8])};
@@ -296,8 +310,8 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
                 if (!((bx.category & m.mask) && (m.category & bx.mask))) continue;      /* collisionNearCallback bMatch */
                 if (lo[0] > m.bbMax[0] || hi[0] < m.bbMin[0] || lo[1] > m.bbMax[1] || hi[1] < m.bbMin[1] || lo[2] > m.bbMax[2] || hi[2] < m.bbMin[2]) continue;
                 const TriMeshVertex* vb = m.trimesh->getVB(); const TriMeshIndex* ib = m.trimesh->getIB();
-                const size_t nt = m.trimesh->getIndexCount() / 3;
-                for (size_t t = 0; t < nt; ++t) {
+                gather(m, lo, hi);
+                for (uint32_t t : cand) {
                     const TriMeshVertex& a0 = vb[ib[t * 3]]; const TriMeshVertex& a1 = vb[ib[t * 3 + 1]]; const TriMeshVertex& a2 = vb[ib[t * 3 + 2]];
                     if (std::min(a0.x, std::min(a1.x, a2.x)) > hi[0] || std::max(a0.x, std::max(a1.x, a2.x)) < lo[0]) continue;
                     if (std::min(a0.y, std::min(a1.y, a2.y)) > hi[1] || std::max(a0.y, std::max(a1.y, a2.y)) < lo[1]) continue;
@@ -308,7 +322,7 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
                     /* box vs trimesh: contacts whose body-local normal y < 0.9 are dropped (PhysicsEngineODE.cpp:309-318) */
                     const float locY = b.R[1] * n.x + b.R[4] * n.y + b.R[7] * n.z;
                     if (locY < 0.9f) continue;
-                    if (getenv("PDREF_DEBUG_COLL")) fprintf(stderr, "[oracle] box contact: tri %zu of mesh cat %lu, n=(%g %g %g) locY=%g, tri y=(%g %g %g) box c=(%g %g %g)\n", t, m.category, n.x, n.y, n.z, locY, a0.y, a1.y, a2.y, c.x, c.y, c.z);
+                    if (kDebugColl) fprintf(stderr, "[oracle] box contact: tri %zu of mesh cat %lu, n=(%g %g %g) locY=%g, tri y=(%g %g %g) box c=(%g %g %g)\n", t, m.category, n.x, n.y, n.z, locY, a0.y, a1.y, a2.y, c.x, c.y, c.z);
                     fire(rb, nullptr, &m, c);
                 }
             }
@@ -319,7 +333,7 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
             CollisionMeshR& cm = *mc.mesh;
             const TriMeshVertex* cvb = cm.trimesh->getVB(); const TriMeshIndex* cib = cm.trimesh->getIB();
             const size_t nv = cm.trimesh->getVertexCount(), nct = cm.trimesh->getIndexCount() / 3;
-            std::vector<oder::CV3> hl(nv);
+            hl.resize(nv);
             float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
             const float* r = mc.offR;
             for (size_t i = 0; i < nv; ++i) {
@@ -336,21 +350,22 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
                 if (!((cm.category & m.mask) && (m.category & cm.mask))) continue;
                 if (lo[0] > m.bbMax[0] || hi[0] < m.bbMin[0] || lo[1] > m.bbMax[1] || hi[1] < m.bbMin[1] || lo[2] > m.bbMax[2] || hi[2] < m.bbMin[2]) continue;
                 const TriMeshVertex* vb = m.trimesh->getVB(); const TriMeshIndex* ib = m.trimesh->getIB();
-                const size_t nt = m.trimesh->getIndexCount() / 3;
+                gather(m, lo, hi);
                 bool hit = false;
-                for (size_t t = 0; t < nt && !hit; ++t) {
+                for (uint32_t t : cand) {
+                    if (hit) break;
                     const TriMeshVertex& a0 = vb[ib[t * 3]]; const TriMeshVertex& a1 = vb[ib[t * 3 + 1]]; const TriMeshVertex& a2 = vb[ib[t * 3 + 2]];
                     if (std::min(a0.x, std::min(a1.x, a2.x)) > hi[0] || std::max(a0.x, std::max(a1.x, a2.x)) < lo[0]) continue;
                     if (std::min(a0.y, std::min(a1.y, a2.y)) > hi[1] || std::max(a0.y, std::max(a1.y, a2.y)) < lo[1]) continue;
                     if (std::min(a0.z, std::min(a1.z, a2.z)) > hi[2] || std::max(a0.z, std::max(a1.z, a2.z)) < lo[2]) continue;
                     const oder::CV3 b0 = toLocal(a0), b1 = toLocal(a1), b2 = toLocal(a2);
-                    if (getenv("PDREF_DEBUG_PAIRS")) { float l0[3] = {std::min(b0.x, std::min(b1.x, b2.x)), std::min(b0.y, std::min(b1.y, b2.y)), std::min(b0.z, std::min(b1.z, b2.z))}, h0[3] = {std::max(b0.x, std::max(b1.x, b2.x)), std::max(b0.y, std::max(b1.y, b2.y)), std::max(b0.z, std::max(b1.z, b2.z))}; float hlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}; for (auto& q : hl) { hlo[0] = std::min(hlo[0], q.x); hhi[0] = std::max(hhi[0], q.x); hlo[1] = std::min(hlo[1], q.y); hhi[1] = std::max(hhi[1], q.y); hlo[2] = std::min(hlo[2], q.z); hhi[2] = std::max(hhi[2], q.z); } if (!(l0[0] > hhi[0] || h0[0] < hlo[0] || l0[1] > hhi[1] || h0[1] < hlo[1] || l0[2] > hhi[2] || h0[2] < hlo[2])) ++localBoundHits; }
+                    if (kDebugPairs) { float l0[3] = {std::min(b0.x, std::min(b1.x, b2.x)), std::min(b0.y, std::min(b1.y, b2.y)), std::min(b0.z, std::min(b1.z, b2.z))}, h0[3] = {std::max(b0.x, std::max(b1.x, b2.x)), std::max(b0.y, std::max(b1.y, b2.y)), std::max(b0.z, std::max(b1.z, b2.z))}; float hlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}; for (auto& q : hl) { hlo[0] = std::min(hlo[0], q.x); hhi[0] = std::max(hhi[0], q.x); hlo[1] = std::min(hlo[1], q.y); hhi[1] = std::max(hhi[1], q.y); hlo[2] = std::min(hlo[2], q.z); hhi[2] = std::max(hhi[2], q.z); } if (!(l0[0] > hhi[0] || h0[0] < hlo[0] || l0[1] > hhi[1] || h0[1] < hlo[1] || l0[2] > hhi[2] || h0[2] < hlo[2])) ++localBoundHits; }
                     for (size_t k = 0; k < nct && !hit; ++k) {
                         ++collisionPairs;
                         if (oder::tri_tri(hl[cib[k * 3]], hl[cib[k * 3 + 1]], hl[cib[k * 3 + 2]], b0, b1, b2)) hit = true;
                     }
                 }
-                if (hit && getenv("PDREF_DEBUG_COLL")) fprintf(stderr, "[oracle] hull contact with mesh cat %lu\n", m.category);
+                if (hit && kDebugColl) fprintf(stderr, "[oracle] hull contact with mesh cat %lu\n", m.category);
                 if (hit) fire(rb, &cm, &m, oder::cv(b.pos[0], b.pos[1], b.pos[2]));     /* one callback per mesh pair is enough for the flag */
             }
         }
@@ -359,7 +374,7 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
         const unsigned long long pairs0 = collisionPairs;
         if (currentFrame & 1) { for (auto& rb : bodies) if (!rb->boxColliders.empty() || !rb->meshColliders.empty()) collideBodyStatic(rb.get()); }
         /* even frames: dynamic x dynamic -- one car per simulator here; its own box and mesh do not match each other's masks */
-        if ((currentFrame & 1) && getenv("PDREF_DEBUG_PAIRS")) { fprintf(stderr, "[oracle] frame %u: %llu narrow-phase pairs %llu inbounds\n", currentFrame, collisionPairs - pairs0, localBoundHits); localBoundHits = 0; }
+        if ((currentFrame & 1) && kDebugPairs) { fprintf(stderr, "[oracle] frame %u: %llu narrow-phase pairs %llu inbounds\n", currentFrame, collisionPairs - pairs0, localBoundHits); localBoundHits = 0; }
         currentFrame++;
     }
 

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ Pd
     float pd_rows[PD_GSCR_WORDS];
 #endif
     const bool resetNow = on && io.pending && io.pending[e];
-    const int collPre = (on && io.collIn && !resetNow) ? io.collIn[e] : -1;
+    const int collPre = (on && io.collIn) ? io.collIn[e] : -1;
     if (on) {
         if (resetNow) env_reset_in_kernel(P, T, sv, e, io, time);
         else if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
         ex.ph = (io.clk && wl == 0) ? io.clk + 4096 + (size_t)(blockIdx.x * 2 + warp) * 32 : nullptr;   /* profiling build: 32 stamps per warp after the per-warp totals */
 #endif
         int collPre = io.collIn ? io.collIn[e] : -1;
-        if (io.pending && io.pending[e]) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); collPre = -1; }
+        if (io.pending && io.pending[e]) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
         else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
 #if PD_QUAD_LOCAL_SCRATCH == 1
         float lscr[PD_GSCR_WORDS];
@@ -236,23 +236,31 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
 /* Collision detection for the coming tick, ONE WARP PER CAR: the cells of the car's footprint are dealt to
  * 4 groups of 8 lanes, the entries of a cell's lists to the 8 lanes of a group (pd_collide.h), the 32 answers are OR-ed.
  * Runs ahead of the tick kernel on the same stream, on the tick's start pose (the pose collisionStep sees,
- * PhysicsEngineODE.cpp:216-224); envs on an even physics frame answer 0 at once, envs about to be reset inside the tick
- * kernel answer -1 (their pose changes first: the tick kernel tests them itself). */
+ * PhysicsEngineODE.cpp:216-224); envs on an even physics frame answer 0 at once; for envs about to be reset inside the tick
+ * kernel the pose is the one the teleport will produce. */
 #define PD_COLLIDE_BLOCK 128
 __global__ void __launch_bounds__(PD_COLLIDE_BLOCK) k_collide(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, const uint32_t* __restrict__ state, int layout, int n,
-                                                              const int32_t* __restrict__ pending, int32_t* __restrict__ collOut, long long* __restrict__ dbg) {
+                                                              const int32_t* __restrict__ pending, int32_t* __restrict__ collOut, long long* __restrict__ dbg,
+                                                              int teleportMode, uint64_t seed, uint64_t idOffset, const uint32_t* __restrict__ episodeCtr) {
     const long long clk0 = dbg ? clock64() : 0;
     const int e = (blockIdx.x * PD_COLLIDE_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= n) return;
     SVR sv = sv_env(layout, const_cast<uint32_t*>(state), (size_t)e);
     if (!(sv.i(PD_OFF_CAR + PD_CAR_o_physFrame) & 1)) { if (lane == 0) collOut[e] = 0; return; }
-    if (pending && pending[e]) { if (lane == 0) collOut[e] = -1; return; }
     Body C; load_body(sv, PD_BODY_CHASSIS, C);
-    int stats[4] = {0, 0, 0, 0};
+    if (pending && pending[e]) {
+        /* this env is reset inside the coming tick kernel, BEFORE its collision step: test the pose the teleport will give it
+           (same spline point: the episode counter is only read here, the tick kernel advances it) */
+        float u = 0.0f;
+        if (teleportMode == PD_TELEPORT_NEAREST) u = sv.f(PD_OFF_CAR + PD_CAR_o_trackLocation);
+        else if (teleportMode == PD_TELEPORT_RANDOM) u = pd_uniform(seed, idOffset + (uint64_t)e, episodeCtr[e]);
+        Quat q; teleport_chassis_pose(P, T, point_id_at_distance(T, u), C.fr.ax, C.fr.ay, C.fr.az, q, C.fr.p);
+    }
+    int stats[6] = {0, 0, 0, 0, 0, 0};
     __shared__ __align__(16) float hullS[(PD_COLLIDE_BLOCK / 32) * PD_HULLS_WORDS];
     const bool any = car_collide_warp(P, T, C, lane, hullS + (threadIdx.x >> 5) * PD_HULLS_WORDS, dbg ? stats : nullptr);
     if (lane == 0) collOut[e] = any ? 1 : 0;
-    if (dbg && lane == 0) { dbg[4096 + (size_t)n * 12 + (size_t)e * 4] = clock64() - clk0; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 1] = ((long long)stats[0] << 32) | (unsigned)stats[1]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 2] = ((long long)stats[2] << 32) | (unsigned)stats[3]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 3] = any; }
+    if (dbg && lane == 0) { dbg[4096 + (size_t)n * 12 + (size_t)e * 4] = clock64() - clk0; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 1] = ((long long)stats[0] << 32) | (unsigned)stats[1]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 2] = ((long long)stats[2] << 32) | (unsigned)stats[3]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 3] = (long long)any | ((long long)stats[4] << 8) | ((long long)stats[5] << 36); }
 }
 
 /* initial record -> every env (both layouts) */
@@ -380,6 +388,7 @@ struct pd_batch {
     float* dReward = nullptr; float* dTotal = nullptr; int32_t* dFlags = nullptr; int32_t* dDone = nullptr;
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     long long* dClk = nullptr; int nClk = 0;
+    bool zeroCopy = true; const void* zcKey[4] = {nullptr, nullptr, nullptr, nullptr}; void* zcDev[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* dColl = nullptr;         /* k_collide's answers for the coming tick */
     long long frameKnown = 0;         /* physics frame shared by all envs, or -1 when states were set individually (then k_collide runs every tick) */
     int32_t* dPending = nullptr; int autoreset = PD_AUTORESET_SAME_STEP;
@@ -427,6 +436,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     CK(cudaSetDevice(device));
     b->n = n_envs; b->device = device;
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
+    if (const char* q = getenv("PD_E2E_ZEROCOPY")) b->zeroCopy = atoi(q) != 0;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
     CK(cudaFuncSetAttribute(k_tick_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
@@ -511,7 +521,8 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
     if (!mask) {
         /* collision detection runs ahead of the tick as its own launch (a warp per car) on odd physics frames */
         if (b->frameKnown < 0 || (b->frameKnown & 1)) {
-            k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr); b->launches++;
+            k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr,
+                                                                                                      io.teleportMode, io.seed, io.idOffset, io.episodeCtr); b->launches++;
             io.collIn = b->dColl;
         }
         if (b->frameKnown >= 0) b->frameKnown++;
@@ -701,9 +712,30 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     launch_tick(b, dt, done, io2);
     CK(cudaGetLastError()); return PD_OK;
 }
+/* device alias of a page-locked, mapped host buffer (what cudaHostAlloc / torch's pin_memory() hand out on a UVA system), or
+ * null when `p` is pageable memory */
+static void* mapped_alias(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
 int pd_env_step_host(pd_batch* b, const float* actions_host, float dt, float* obs_host, float* reward_host, int32_t* done_host) {
     if (!b || !actions_host) return PD_ERR_ARG;
     const size_t n = (size_t)b->n;
+    /* zero-copy path: with the one-launch step (next-step auto-reset) and page-locked host buffers the tick kernel reads the
+       actions from, and writes observation / reward / done to, the caller's memory directly over PCIe -- no staging copies, one
+       launch (two on odd physics frames) and one stream synchronisation per step.  PD_E2E_ZEROCOPY=0 disables it. */
+    if (b->autoreset == PD_AUTORESET_NEXT_STEP && b->zeroCopy && obs_host && reward_host && done_host) {
+        if (b->zcKey[0] != actions_host || b->zcKey[1] != obs_host || b->zcKey[2] != reward_host || b->zcKey[3] != done_host) {
+            b->zcKey[0] = actions_host; b->zcKey[1] = obs_host; b->zcKey[2] = reward_host; b->zcKey[3] = done_host;
+            for (int i = 0; i < 4; ++i) b->zcDev[i] = mapped_alias(b->zcKey[i]);
+        }
+        if (b->zcDev[0] && b->zcDev[1] && b->zcDev[2] && b->zcDev[3]) {
+            int rc = pd_env_step(b, (const float*)b->zcDev[0], dt, (float*)b->zcDev[1], (float*)b->zcDev[2], (int32_t*)b->zcDev[3]); if (rc) return rc;
+            CK(cudaStreamSynchronize(b->stream)); return PD_OK;
+        }
+    }
     CK(cudaMemcpyAsync(b->dAct, actions_host, n * 2 * 4, cudaMemcpyHostToDevice, b->stream));
     int rc = pd_env_step(b, b->dAct, dt, b->dObs, b->dReward, b->dDone); if (rc) return rc;
     if (obs_host) CK(cudaMemcpyAsync(obs_host, b->dObs, n * PD_OBS_DIM * 4, cudaMemcpyDeviceToHost, b->stream));

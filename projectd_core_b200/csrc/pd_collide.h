@@ -90,6 +90,14 @@ PD_HD bool seg_tri(V3 p, V3 q, V3 v0, V3 e1, V3 e2) {
     const float t = dot(e2, qvec) * inv;
     return t >= 0.0f && t <= 1.0f;
 }
+/* filter: true when triangle b lies wholly on one side of triangle a's plane, by more than 0.1 mm -- then no edge of
+ * either can cross the other */
+PD_HD bool tri_plane_separates(V3 a0, V3 a1, V3 a2, V3 b0, V3 b1, V3 b2) {
+    const V3 n = cross(a1 - a0, a2 - a0);
+    const float d = dot(n, a0), margin = 1e-4f * sqrtf(dot(n, n));
+    const float s0 = dot(n, b0) - d, s1 = dot(n, b1) - d, s2 = dot(n, b2) - d;
+    return (s0 > margin && s1 > margin && s2 > margin) || (s0 < -margin && s1 < -margin && s2 < -margin);
+}
 PD_HDN bool tri_tri(V3 a0, V3 a1, V3 a2, V3 b0, V3 b1, V3 b2) {
     const V3 ae1 = a1 - a0, ae2 = a2 - a0, be1 = b1 - b0, be2 = b2 - b0;
     return seg_tri(a0, a1, b0, be1, be2) || seg_tri(a1, a2, b0, be1, be2) || seg_tri(a2, a0, b0, be1, be2) ||
@@ -273,6 +281,7 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
                         if ((s0 > margin && s1 > margin && s2 > margin) || (s0 < -margin && s1 < -margin && s2 < -margin)) continue;
                         const float* tb = P.colliderTriBounds[j];
                         if (lo.x > tb[3] || hi.x < tb[0] || lo.y > tb[4] || hi.y < tb[1] || lo.z > tb[5] || hi.z < tb[2]) continue;
+                        if (tri_plane_separates(a0, a1, a2, b0, b1, b2)) continue;
                         if (tri_tri(a0, a1, a2, b0, b1, b2)) return true;
                     }
                   }
@@ -368,7 +377,9 @@ __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackD
                     }
                     const unsigned candMask = __ballot_sync(FULL, cand);
                     if (stats && lane == 0) stats[3] += __popc(candMask);
+                    const long long tc0 = stats ? clock64() : 0;
                     if (candMask) {
+                        const long long ts0 = stats ? clock64() : 0;
                         if (!staged) {      /* first survivor of this car: the hull's filter data and vertices move to this warp's shared memory */
                             for (int i = lane; i < PD_MAX_COLLIDER_TRIS; i += 32) {
                                 PD_UNROLL for (int q = 0; q < 4; ++q) hullS[PD_HULLS_SPHERE + i * 4 + q] = P.colliderTriSphere[i][q];
@@ -378,6 +389,7 @@ __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackD
                             for (int i = lane; i < PD_MAX_COLLIDER_VERTS; i += 32) { PD_UNROLL for (int q = 0; q < 3; ++q) hullS[PD_HULLS_VERTS + i * 3 + q] = P.colliderVerts[i][q]; }
                             __syncwarp(FULL);
                             staged = true;
+                            if (stats && lane == 0) stats[5] += (int)((clock64() - ts0) >> 4);
                         }
                         /* every lane takes its own survivor through the hull's triangles (up to 32 wall triangles at once) */
                         bool hit = false;
@@ -398,11 +410,13 @@ __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackD
                                 const V3 a0 = v3(p0[0], p0[1], p0[2]), a1 = v3(p1[0], p1[1], p1[2]), a2 = v3(p2[0], p2[1], p2[2]);
                                 const float s0 = dot(nW, a0) - dW, s1 = dot(nW, a1) - dW, s2 = dot(nW, a2) - dW;
                                 if ((s0 > margin && s1 > margin && s2 > margin) || (s0 < -margin && s1 < -margin && s2 < -margin)) continue;
+                                if (tri_plane_separates(a0, a1, a2, b0, b1, b2)) continue;
                                 if (tri_tri(a0, a1, a2, b0, b1, b2)) { hit = true; break; }
                             }
                         }
                         if (__any_sync(FULL, hit)) return true;
                     }
+                    if (stats && lane == 0) stats[4] += (int)((clock64() - tc0) >> 4);
                     if (__all_sync(FULL, below)) break;
                 }
             }

@@ -73,14 +73,10 @@ template <class SVX> PD_HDN void car_init_state(const PdCarParams& P, const SVX&
     sv.f(o + PD_CAR_o_lifeLeft, 1000.0f); sv.f(o + PD_CAR_o_fuelPressure, 1.0f);
 }
 
-/* teleport: Car::teleportToSpline -> forceRotation + forcePosition (Car.cpp:1325-1340,1275-1308,1240-1273) */
-template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const SVX& sv, int pointId, double physicsTime) {
-    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
-    CarS c; load_car(sv, c);
+/* where Car::teleportToSpline puts the chassis: forceRotation(heading of the spline point) + forcePosition(its centre, dropped
+ * onto the ground by one ray from 10 m above) (Car.cpp:1325-1340,1275-1308,1240-1273) */
+PD_HD void teleport_chassis_pose(const PdCarParams& P, const TrackDev& T, int pointId, V3& oax, V3& oay, V3& oaz, Quat& q, V3& pos) {
     const PdFatPoint& pt = T.fat[pointId];
-    Body& C = bod[PD_BODY_CHASSIS]; Body& Tk = bod[PD_BODY_TANK];
-    /* forceRotation(heading) */
     {
         const V3 heading = v3(pt.forwardDir[0], pt.forwardDir[1], pt.forwardDir[2]);
         const V3 ihed = heading * -1.0f;
@@ -88,16 +84,26 @@ template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, con
         const float v6 = sqrtf((vM12 * vM12) + (vM11 * vM11) + (vM13 * vM13));
         const float s = 1.0f / v6;
         const V3 ax = v3(vM11 * s, vM12 * s, vM13 * s), ay = v3(0, 1, 0), az = v3(-ihed.x, -ihed.y, -ihed.z);
-        set_rotation(ax, ay, az, C.fr.ax, C.fr.ay, C.fr.az, C.q);
-        Tk.fr.ax = C.fr.ax; Tk.fr.ay = C.fr.ay; Tk.fr.az = C.fr.az; Tk.q = C.q;
+        set_rotation(ax, ay, az, oax, oay, oaz, q);
     }
-    /* forcePosition(center) */
     V3 bodyPos = v3(pt.center[0], pt.center[1], pt.center[2]);
     {
         const RayHit hit = ray_cast_down(T, bodyPos + v3(0, 10, 0), 1000.0f);
         if (hit.hit) bodyPos.y = hit.pos.y;
         bodyPos.y += (P.baseCarHeight + 0.0f + 0.01f);
     }
+    pos = bodyPos;
+}
+
+/* teleport: Car::teleportToSpline -> forceRotation + forcePosition (Car.cpp:1325-1340,1275-1308,1240-1273) */
+template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const SVX& sv, int pointId, double physicsTime) {
+    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
+    CarS c; load_car(sv, c);
+    Body& C = bod[PD_BODY_CHASSIS]; Body& Tk = bod[PD_BODY_TANK];
+    V3 bodyPos;
+    teleport_chassis_pose(P, T, pointId, C.fr.ax, C.fr.ay, C.fr.az, C.q, bodyPos);
+    Tk.fr.ax = C.fr.ax; Tk.fr.ay = C.fr.ay; Tk.fr.az = C.fr.az; Tk.q = C.q;
     /* Car::reset (Car.cpp:385-410) */
     c.waterT = 60; c.fuel = P.requestedFuel;
     c.collisionFlag = 0; c.outOfTrackFlag = 0;

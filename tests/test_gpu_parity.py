@@ -344,3 +344,22 @@ def test_collision_flag_matches_oracle(oracle, lay, golden, kernel, monkeypatch)
     b2.step(DT, 1)
     got2 = b2.snapshot()[off].view(np.int32)
     assert np.array_equal(got2, np.array(want, np.int32))
+
+
+def test_env_step_host_zero_copy_equals_device_path(oracle):
+    """pd_env_step_host with page-locked host buffers and the one-launch step: the kernel reads the actions from and writes
+    obs / reward / done to the caller's pinned memory directly; results must equal the device-buffer path bit for bit."""
+    import torch
+    n = 256
+    a = _batch(oracle, n); a.set_seed(5, 0); a.teleport_mode(2); a.set_autoreset(1)
+    c = _batch(oracle, n); c.set_seed(5, 0); c.teleport_mode(2); c.set_autoreset(1)
+    h_act = torch.empty((n, 2), dtype=torch.float32).pin_memory(); h_obs = torch.zeros((n, 24), dtype=torch.float32).pin_memory()
+    h_rew = torch.zeros(n, dtype=torch.float32).pin_memory(); h_done = torch.zeros(n, dtype=torch.int32).pin_memory()
+    rew_d = torch.zeros(n, device="cuda"); done_d = torch.zeros(n, device="cuda", dtype=torch.int32)
+    gen = torch.Generator(); gen.manual_seed(3)
+    for t in range(80):
+        h_act.copy_(torch.rand((n, 2), generator=gen) * 2 - 1)
+        a.env_step_host(h_act, DT, h_obs, h_rew, h_done)
+        c.env_step(h_act.cuda(), DT, None, rew_d, done_d); c.sync()
+        assert torch.equal(h_obs, c.obs_tensor().cpu()) and torch.equal(h_rew, rew_d.cpu()) and torch.equal(h_done, done_d.cpu()), t
+    assert np.array_equal(a.snapshot(), c.snapshot())

@@ -28,4 +28,5 @@ for e in np.argsort(-cyc)[:12]:
     r = before[:, e]
     ncell, tr = d[e, 1] >> 32, d[e, 1] & 0xffffffff; wr, cand = d[e, 2] >> 32, d[e, 2] & 0xffffffff
     pos = [lay.get(r, "chassis.p" + k) for k in "xyz"]; v = np.linalg.norm([lay.get(r, "chassis.v" + k) for k in "xyz"])
-    print("env %d: %.0f kcycles, cells %d, track rounds %d, wall rounds %d, candidates %d, hit %d | pos %.1f %.1f %.1f v %.1f frame %d oot %d" % (e, cyc[e] / 1e3, ncell, tr, wr, cand, d[e, 3], pos[0], pos[1], pos[2], v, lay.get(r, "car.physFrame"), lay.get(r, "car.outOfTrackFlag")))
+    hullc = ((int(d[e, 3]) >> 8) & 0xfffffff) * 16 / 1e3; stagec = (int(d[e, 3]) >> 36) * 16 / 1e3
+    print("env %d: %.0f kcycles (hull loops %.0f k, of which staging %.0f k), cells %d, track rounds %d, wall rounds %d, candidates %d, hit %d | pos %.1f %.1f %.1f v %.1f frame %d oot %d" % (e, cyc[e] / 1e3, hullc, stagec, ncell, tr, wr, cand, int(d[e, 3]) & 1, pos[0], pos[1], pos[2], v, lay.get(r, "car.physFrame"), lay.get(r, "car.outOfTrackFlag")))
