@@ -170,7 +170,7 @@ def ours(args):
     n_envs = args.envs if args.envs else (4096 if world == 1 else 65536)
     K, W = args.steps, args.warmup
 
-    b = make_env_like(Batch(pdref.BASE_PATH, n_envs=n_envs, device=dev.index))
+    b = make_env_like(Batch(pdref.BASE_PATH, n_envs=n_envs, device=dev.index, synthetic_tris=args.synthetic_tris))
     env_offset, _ = pdist.shard_range(world * n_envs, rank, world)
     b.set_seed(1234, env_offset)             # RNG keyed by global env id: results do not depend on the sharding
     b.teleport_mode(2)                        # random start positions u ~ U[0,1)
@@ -290,14 +290,14 @@ def ours(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("configs[1]: 4096 demo-car envs on 1 B200" if (world == 1 and n_envs == 4096) else "%d demo-car envs per GPU (configs[2] uses 65536)" % n_envs)
-                       + ", ks_toyota_ae86_drift on driftplayground, random controls resampled every 33 ticks, env auto-reset (next-step convention: a finished env resets inside the next step's launch); "
+                       + (", ks_toyota_ae86_drift on driftplayground" if not args.synthetic_tris else ", ks_toyota_ae86_drift on a generated 20.8 km circuit of ~%d triangles (configs[3])" % args.synthetic_tris) + ", random controls resampled every 33 ticks, env auto-reset (next-step convention: a finished env resets inside the next step's launch); "
                          "measured in the rollout's steady state after %d untimed pre-roll ticks" % args.preroll,
                        "envs_per_gpu": n_envs, "ticks_per_step": TICKS_PER_STEP, "dt": DT,
                        "l2": ("no flush: the working set is the env state (%.1f MB), read and written every tick; " % (n_envs * words * 4 / 1e6))
                              + ("it is larger than L2 (126 MB)" if n_envs * words * 4 > 126e6 else "it fits L2 and staying L2-resident between consecutive ticks IS the workload (a simulation steps the same state), see DESIGN.md"),
                        "parallelism": "env-sharded x%d, no per-tick collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TICKS_PER_STEP * n_envs * 8, "d2h_bytes_per_step": TICKS_PER_STEP * n_envs * (96 + 4 + 4),
-                    "note": "per tick one pd_env_step_host call: pinned H2D actions, step, D2H obs+reward+done, stream sync"},
+                    "note": "per tick one pd_env_step_host call with pinned host buffers: the tick kernel reads the actions from and writes obs / reward / done to host memory directly (zero-copy over PCIe), then one stream sync"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -323,6 +323,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: 4096 at N=1, 65536 at N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--synthetic-tris", type=int, default=0, help="BASELINE configs[3]: generated 20.8 km circuit of about this many triangles instead of driftplayground")
     ap.add_argument("--preroll", type=int, default=1998, help="untimed ticks before the warm-up (brings the rollout to its steady state)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

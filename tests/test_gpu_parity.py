@@ -363,3 +363,34 @@ def test_env_step_host_zero_copy_equals_device_path(oracle):
         c.env_step(h_act.cuda(), DT, None, rew_d, done_d); c.sync()
         assert torch.equal(h_obs, c.obs_tensor().cpu()) and torch.equal(h_rew, rew_d.cpu()) and torch.equal(h_done, done_d.cpu()), t
     assert np.array_equal(a.snapshot(), c.snapshot())
+
+
+def test_synthetic_large_track_config4(oracle):
+    """BASELINE configs[3]: a generated ~1 M-triangle circuit (20.8 km).  The vertical-ray column grid must agree with the BVH
+    on it, and a batch must drive on it (finite state, cars moving, no false collisions on the open circuit)."""
+    import torch
+    from projectd_core_b200 import Batch
+    n = 256
+    b = make_env_like(Batch(oracle.BASE_PATH, n_envs=n, device=0, synthetic_tris=1000000))
+    ti = b.track_info()
+    assert 900000 <= ti["nTris"] <= 1100000 and ti["nFatPoints"] > 10000
+    b.set_seed(3, 0); b.teleport_mode(2); b.set_autoreset(1); b.sync()
+    st = b.snapshot()
+    lay = oracle.Layout()
+    px = st[lay.fields["chassis.px"][0]].view(np.float32); py = st[lay.fields["chassis.py"][0]].view(np.float32); pz = st[lay.fields["chassis.pz"][0]].view(np.float32)
+    rays = np.zeros((n, 7), np.float32); rays[:, 0] = px; rays[:, 1] = py + 5; rays[:, 2] = pz; rays[:, 4] = -1; rays[:, 6] = 50
+    down = b.raycast(rays)
+    tilt = rays.copy(); tilt[:, 3] = 1e-6; tilt[:, 4] = -1.0                     # not exactly vertical -> BVH traversal
+    tilt[:, 3:6] /= np.linalg.norm(tilt[:, 3:6], axis=1, keepdims=True)
+    gen = b.raycast(tilt)
+    assert down[:, 0].all() and np.array_equal(down[:, 0], gen[:, 0]) and np.array_equal(down[:, 7], gen[:, 7])
+    assert np.abs(down[:, 1:4] - gen[:, 1:4]).max() < 1e-3
+    act = torch.zeros((n, 2), device="cuda"); act[:, 1] = 1.0
+    rew = torch.zeros(n, device="cuda"); done = torch.zeros(n, device="cuda", dtype=torch.int32)
+    for t in range(900):
+        b.env_step(act, DT, None, rew, done)
+    b.sync()
+    obs = b.obs_tensor().cpu().numpy()
+    assert np.isfinite(obs).all() and np.abs(obs[:, 0:3]).max(axis=1).mean() > 0.5, "cars should be moving under full throttle"
+    s = b.env_stats()
+    assert s[3] == 0 and s[7] == 0, "no collisions / NaNs expected on the open generated circuit"
