@@ -175,7 +175,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
  * = more warps per car batch, for batches too small to fill the 592 warp schedulers of a B200 otherwise).
  * ONE bulk copy brings the block's records in, the quads work on the shared-memory copy, ONE bulk copy writes them back. */
 template <int CPW>
-__global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+__global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                          const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     constexpr int QCARS = 2 * CPW;          /* cars per block */
     constexpr int QLANES = 8 * CPW;         /* working threads per block = stride of the lane-interleaved solver scratch */
@@ -201,25 +201,62 @@ __global__ void __launch_bounds__(PD_QBLOCK) k_tick_quad(const __grid_constant__
     mbar_wait(bar, 0);
     uint32_t* rec = recs + car * PD_STATE_STRIDE;
     SVFlat sv = sv_flat(rec);
-    if (on) {
-        QuadShfl ex; ex.lane = wl & 3; ex.base = wl & ~3; ex.mask = 0xFu << ex.base;
+    const bool resetNow = on && io.pending && io.pending[e];
+    QuadShfl ex; ex.lane = wl & 3; ex.base = wl & ~3; ex.mask = 0xFu << ex.base;
 #if defined(PD_PHASE_CLOCKS)
-        ex.ph = (io.clk && wl == 0) ? io.clk + 4096 + (size_t)(blockIdx.x * 2 + warp) * 32 : nullptr;   /* profiling build: 32 stamps per warp after the per-warp totals */
+    ex.ph = (io.clk && wl == 0 && warp < 2) ? io.clk + 4096 + (size_t)(blockIdx.x * 2 + warp) * 32 : nullptr;   /* profiling build: 32 stamps per warp after the per-warp totals */
 #endif
-        int collPre = io.collIn ? io.collIn[e] : -1;
-        if (io.pending && io.pending[e]) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
+    if (on) {
+        if (ex.lane == 0) rec[PD_OFF_TYRE(0) + PD_TYRE_o_tyrePad] = 0u;      /* the collision warp's mailbox (a pad word of the record) starts empty */
+        if (resetNow) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
         else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
+    }
+    /* A third warp, when launched (blockDim 96: full ticks without k_collide's answer), is the block's COLLISION WARP: it
+     * takes the start poses of the block's cars (after a reset's teleport, before anything moves) into registers and tests the
+     * cars on an odd physics frame one after the other with all 32 lanes (car_collide_warp) while the two tick warps run the
+     * tick; the answer is posted in a pad word of the car's record, where the quad picks it up just before the scoring. */
+    const bool haveCollWarp = blockDim.x > PD_QBLOCK && !io.collIn;
+    const int collSlot = PD_OFF_TYRE(0) + PD_TYRE_o_tyrePad;
+    if (haveCollWarp) {
+        __syncthreads();
+        float fr[12]; int need = 0;
+        if (warp == 2) {
+            if (wl < ncars && (!mask || mask[car0 + wl])) {
+                SVFlat svc = sv_flat(recs + wl * PD_STATE_STRIDE);
+                Body Cc; load_body(svc, PD_BODY_CHASSIS, Cc);
+                fr[0] = Cc.fr.p.x; fr[1] = Cc.fr.p.y; fr[2] = Cc.fr.p.z; fr[3] = Cc.fr.ax.x; fr[4] = Cc.fr.ax.y; fr[5] = Cc.fr.ax.z;
+                fr[6] = Cc.fr.ay.x; fr[7] = Cc.fr.ay.y; fr[8] = Cc.fr.ay.z; fr[9] = Cc.fr.az.x; fr[10] = Cc.fr.az.y; fr[11] = Cc.fr.az.z;
+                need = svc.i(PD_OFF_CAR + PD_CAR_o_physFrame) & 1;
+            } else { PD_UNROLL for (int q = 0; q < 12; ++q) fr[q] = 0.0f; }
+        }
+        __syncthreads();      /* poses and frame parities are in the collision warp's registers: the tick may start changing the records */
+        if (warp == 2) {
+            for (int k = 0; k < ncars; ++k) {
+                if (!__shfl_sync(0xffffffffu, need, k)) continue;
+                Body Cc;
+                Cc.fr.p = v3(__shfl_sync(0xffffffffu, fr[0], k), __shfl_sync(0xffffffffu, fr[1], k), __shfl_sync(0xffffffffu, fr[2], k));
+                Cc.fr.ax = v3(__shfl_sync(0xffffffffu, fr[3], k), __shfl_sync(0xffffffffu, fr[4], k), __shfl_sync(0xffffffffu, fr[5], k));
+                Cc.fr.ay = v3(__shfl_sync(0xffffffffu, fr[6], k), __shfl_sync(0xffffffffu, fr[7], k), __shfl_sync(0xffffffffu, fr[8], k));
+                Cc.fr.az = v3(__shfl_sync(0xffffffffu, fr[9], k), __shfl_sync(0xffffffffu, fr[10], k), __shfl_sync(0xffffffffu, fr[11], k));
+                const bool hit = car_collide_warp<false>(P, T, Cc, wl, nullptr);
+                if (wl == 0) { *reinterpret_cast<volatile uint32_t*>(recs + k * PD_STATE_STRIDE + collSlot) = hit ? 2u : 1u; __threadfence_block(); }
+            }
+        }
+    }
+    if (on) {
+        const int collPre = io.collIn ? io.collIn[e] : -1;
+        volatile uint32_t* collWait = haveCollWarp ? reinterpret_cast<volatile uint32_t*>(rec + collSlot) : nullptr;
 #if PD_QUAD_LOCAL_SCRATCH == 1
         float lscr[PD_GSCR_WORDS];
-        car_tick_quad<1, 1>(P, T, sv, dt, time, ex, lscr, lscr + PD_GSCR_ROWS_WORDS, collPre);
+        car_tick_quad<1, 1>(P, T, sv, dt, time, ex, lscr, lscr + PD_GSCR_ROWS_WORDS, collPre, collWait);
 #elif PD_QUAD_LOCAL_SCRATCH == 2
         float lrows[PD_GSCR_ROWS_WORDS];                     /* JA | JB in local memory, Y | D | dg in shared memory */
-        car_tick_quad<1, QLANES>(P, T, sv, dt, time, ex, lrows, scratch + cid, collPre);
+        car_tick_quad<1, QLANES>(P, T, sv, dt, time, ex, lrows, scratch + cid, collPre, collWait);
 #else
-        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid, collPre);
+        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid, collPre, collWait);
 #endif
     }
-    if (io.clk && wl == 0) io.clk[blockIdx.x * 2 + warp] = clock64() - clk0;
+    if (io.clk && wl == 0 && warp < 2) io.clk[blockIdx.x * 2 + warp] = clock64() - clk0;
     fence_async_smem();                                        /* generic-proxy writes -> visible to the bulk copy engine */
     __syncthreads();
     if (tid == 32) { bulk_s2g(gsrc, recs, bytes); }
@@ -258,7 +295,7 @@ __global__ void __launch_bounds__(PD_COLLIDE_BLOCK) k_collide(const __grid_const
     }
     int stats[6] = {0, 0, 0, 0, 0, 0};
     __shared__ __align__(16) float hullS[(PD_COLLIDE_BLOCK / 32) * PD_HULLS_WORDS];
-    const bool any = car_collide_warp(P, T, C, lane, hullS + (threadIdx.x >> 5) * PD_HULLS_WORDS, dbg ? stats : nullptr);
+    const bool any = car_collide_warp<true>(P, T, C, lane, hullS + (threadIdx.x >> 5) * PD_HULLS_WORDS, dbg ? stats : nullptr);
     if (lane == 0) collOut[e] = any ? 1 : 0;
     if (dbg && lane == 0) { dbg[4096 + (size_t)n * 12 + (size_t)e * 4] = clock64() - clk0; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 1] = ((long long)stats[0] << 32) | (unsigned)stats[1]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 2] = ((long long)stats[2] << 32) | (unsigned)stats[3]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 3] = (long long)any | ((long long)stats[4] << 8) | ((long long)stats[5] << 36); }
 }
@@ -388,6 +425,7 @@ struct pd_batch {
     float* dReward = nullptr; float* dTotal = nullptr; int32_t* dFlags = nullptr; int32_t* dDone = nullptr;
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     long long* dClk = nullptr; int nClk = 0;
+    bool collWarp = true;             /* quad kernel: collision warp inside the tick kernel (env PD_COLL_WARP=0: k_collide ahead of it instead) */
     bool zeroCopy = true; const void* zcKey[4] = {nullptr, nullptr, nullptr, nullptr}; void* zcDev[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* dColl = nullptr;         /* k_collide's answers for the coming tick */
     long long frameKnown = 0;         /* physics frame shared by all envs, or -1 when states were set individually (then k_collide runs every tick) */
@@ -437,6 +475,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     b->n = n_envs; b->device = device;
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     if (const char* q = getenv("PD_E2E_ZEROCOPY")) b->zeroCopy = atoi(q) != 0;
+    if (const char* q = getenv("PD_COLL_WARP")) b->collWarp = atoi(q) != 0;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
     CK(cudaFuncSetAttribute(k_tick_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
@@ -518,22 +557,27 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
 
 static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO& io_in) {
     EnvIO io = io_in; io.clk = mask ? nullptr : b->dClk;
+    bool collWarp = false;
     if (!mask) {
-        /* collision detection runs ahead of the tick as its own launch (a warp per car) on odd physics frames */
-        if (b->frameKnown < 0 || (b->frameKnown & 1)) {
+        /* collision detection (odd physics frames): the quad kernel brings its own collision warp per block; the thread-per-car
+           kernel is preceded by k_collide (a warp per car) on the same stream */
+        const bool oddPossible = b->frameKnown < 0 || (b->frameKnown & 1);
+        if (oddPossible && b->layout == PD_LAYOUT_RECORDS && b->collWarp) collWarp = true;
+        else if (oddPossible) {
             k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr,
                                                                                                       io.teleportMode, io.seed, io.idOffset, io.episodeCtr); b->launches++;
             io.collIn = b->dColl;
         }
         if (b->frameKnown >= 0) b->frameKnown++;
     } else b->frameKnown = -1;          /* a masked tick advances only some envs: frames are no longer in lock step */
-    if (b->layout == PD_LAYOUT_RECORDS)
+    if (b->layout == PD_LAYOUT_RECORDS) {
+        const int threads = collWarp ? PD_QBLOCK + 32 : PD_QBLOCK;
         switch (b->quadCpw) {
-        case 2: k_tick_quad<2><<<grid(b->n, 4), PD_QBLOCK, PD_QUAD_SMEM_BYTES_(2), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
-        case 4: k_tick_quad<4><<<grid(b->n, 8), PD_QBLOCK, PD_QUAD_SMEM_BYTES_(4), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
-        default: k_tick_quad<8><<<grid(b->n, 16), PD_QBLOCK, PD_QUAD_SMEM_BYTES_(8), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        case 2: k_tick_quad<2><<<grid(b->n, 4), threads, PD_QUAD_SMEM_BYTES_(2), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        case 4: k_tick_quad<4><<<grid(b->n, 8), threads, PD_QUAD_SMEM_BYTES_(4), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        default: k_tick_quad<8><<<grid(b->n, 16), threads, PD_QUAD_SMEM_BYTES_(8), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
         }
-    else
+    } else
         k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     b->launches++;
 }

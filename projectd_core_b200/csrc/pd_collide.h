@@ -296,13 +296,14 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
 /* The same answer, computed by the 32 lanes of ONE WARP for one car (k_collide).  The warp walks the cells of the car's
  * footprint together (all cell headers arrive in one round trip: lane i fetches cell i), the entries of a cell's lists are
  * dealt to the 32 lanes, and every lane takes its own surviving wall triangle through the hull's triangles, whose filter
- * data (bounding spheres, boxes) and vertices are staged in the warp's shared memory the first time a survivor appears. */
+ * data (bounding spheres, boxes) and vertices are staged in the warp's shared memory the first time a survivor appears
+ * (hullS; a caller without room for it passes null and the data is read from the kernel parameters). */
 #define PD_HULLS_SPHERE 0
 #define PD_HULLS_BOUNDS (PD_HULLS_SPHERE + PD_MAX_COLLIDER_TRIS * 4)
 #define PD_HULLS_TRIS   (PD_HULLS_BOUNDS + PD_MAX_COLLIDER_TRIS * 6)
 #define PD_HULLS_VERTS  (PD_HULLS_TRIS + PD_MAX_COLLIDER_TRIS)
 #define PD_HULLS_WORDS  (PD_HULLS_VERTS + PD_MAX_COLLIDER_VERTS * 3)      /* 1600 words = 6.4 KB per warp */
-__device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackDev& T, const Body& C, int lane, float* hullS, int* stats = nullptr) {
+template <bool SMEM> __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackDev& T, const Body& C, int lane, float* hullS, int* stats = nullptr) {
     const unsigned FULL = 0xffffffffu;
     bool staged = false;
     const PdBoundGrid& G = T.collGrid;
@@ -380,7 +381,7 @@ __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackD
                     const long long tc0 = stats ? clock64() : 0;
                     if (candMask) {
                         const long long ts0 = stats ? clock64() : 0;
-                        if (!staged) {      /* first survivor of this car: the hull's filter data and vertices move to this warp's shared memory */
+                        if (SMEM && !staged) {      /* first survivor of this car: the hull's filter data and vertices move to this warp's shared memory */
                             for (int i = lane; i < PD_MAX_COLLIDER_TRIS; i += 32) {
                                 PD_UNROLL for (int q = 0; q < 4; ++q) hullS[PD_HULLS_SPHERE + i * 4 + q] = P.colliderTriSphere[i][q];
                                 PD_UNROLL for (int q = 0; q < 6; ++q) hullS[PD_HULLS_BOUNDS + i * 6 + q] = P.colliderTriBounds[i][q];
@@ -400,14 +401,24 @@ __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackD
                             const float nlen = sqrtf(dot(nW, nW)), dW = dot(nW, b0), margin = 1e-4f * nlen;
                             PD_NOUNROLL
                             for (int j = 0; j < P.nColliderTris; ++j) {
-                                const float4 sp = *reinterpret_cast<const float4*>(hullS + PD_HULLS_SPHERE + j * 4);
+                                float4 sp;
+                                if (SMEM) sp = *reinterpret_cast<const float4*>(hullS + PD_HULLS_SPHERE + j * 4);
+                                else sp = make_float4(P.colliderTriSphere[j][0], P.colliderTriSphere[j][1], P.colliderTriSphere[j][2], P.colliderTriSphere[j][3]);   /* constant bank, uniform index */
                                 const float sd = nW.x * sp.x + nW.y * sp.y + nW.z * sp.z - dW;
                                 if (fabsf(sd) > sp.w * nlen + margin) continue;
-                                const float* tb = hullS + PD_HULLS_BOUNDS + j * 6;
+                                float tb[6];
+                                if (SMEM) { PD_UNROLL for (int q = 0; q < 6; ++q) tb[q] = hullS[PD_HULLS_BOUNDS + j * 6 + q]; }
+                                else { PD_UNROLL for (int q = 0; q < 6; ++q) tb[q] = P.colliderTriBounds[j][q]; }
                                 if (lo.x > tb[3] || hi.x < tb[0] || lo.y > tb[4] || hi.y < tb[1] || lo.z > tb[5] || hi.z < tb[2]) continue;
-                                const int tri = __float_as_int(hullS[PD_HULLS_TRIS + j]);
-                                const float* p0 = hullS + PD_HULLS_VERTS + (tri & 255) * 3; const float* p1 = hullS + PD_HULLS_VERTS + ((tri >> 8) & 255) * 3; const float* p2 = hullS + PD_HULLS_VERTS + ((tri >> 16) & 255) * 3;
-                                const V3 a0 = v3(p0[0], p0[1], p0[2]), a1 = v3(p1[0], p1[1], p1[2]), a2 = v3(p2[0], p2[1], p2[2]);
+                                V3 a0, a1, a2;
+                                if (SMEM) {
+                                    const int tri = __float_as_int(hullS[PD_HULLS_TRIS + j]);
+                                    const float* p0 = hullS + PD_HULLS_VERTS + (tri & 255) * 3; const float* p1 = hullS + PD_HULLS_VERTS + ((tri >> 8) & 255) * 3; const float* p2 = hullS + PD_HULLS_VERTS + ((tri >> 16) & 255) * 3;
+                                    a0 = v3(p0[0], p0[1], p0[2]); a1 = v3(p1[0], p1[1], p1[2]); a2 = v3(p2[0], p2[1], p2[2]);
+                                } else {
+                                    const int i0 = P.colliderTris[j][0], i1 = P.colliderTris[j][1], i2 = P.colliderTris[j][2];
+                                    a0 = v3(P.colliderVerts[i0][0], P.colliderVerts[i0][1], P.colliderVerts[i0][2]); a1 = v3(P.colliderVerts[i1][0], P.colliderVerts[i1][1], P.colliderVerts[i1][2]); a2 = v3(P.colliderVerts[i2][0], P.colliderVerts[i2][1], P.colliderVerts[i2][2]);
+                                }
                                 const float s0 = dot(nW, a0) - dW, s1 = dot(nW, a1) - dW, s2 = dot(nW, a2) - dW;
                                 if ((s0 > margin && s1 > margin && s2 > margin) || (s0 < -margin && s1 < -margin && s2 < -margin)) continue;
                                 if (tri_plane_separates(a0, a1, a2, b0, b1, b2)) continue;

@@ -38,7 +38,7 @@ PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
 }
 
 template <int STRIDE, int STRIDE_D, class Ex, class SVX>
-PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD, int collPre = -1) {
+PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD, int collPre = -1, volatile uint32_t* collWait = nullptr) {
     const int lane = ex.lane;
     const bool front = lane < 2;
     /* Car-level state: with a stride-1 view (the shared-memory staging copy) the four lanes work IN PLACE on the
@@ -179,11 +179,13 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     }
 
     /* ---------------- collisionStep (odd frames): the cell lists are dealt to the four lanes, any hit sets the flag ---------------- */
+    /* three ways to the answer: k_collide ran ahead (collPre 0 / 1); the block's collision warp is working on it right now and
+       posts it in shared memory (collWait: picked up just before the scoring, the only consumer); or the quad tests here */
+    bool collDeferred = false;
     if (c.physFrame & 1) {
-        bool hitAny;
-        if (collPre >= 0) hitAny = collPre != 0;          /* answered by k_collide for this tick's start pose */
-        else { const bool hit = car_collide(P, T, C, lane, 4); hitAny = !ex.all(!hit); }
-        if (hitAny) c.collisionFlag = 1;
+        if (collPre >= 0) { if (collPre != 0) c.collisionFlag = 1; }
+        else if (collWait) collDeferred = true;
+        else { const bool hit = car_collide(P, T, C, lane, 4); if (!ex.all(!hit)) c.collisionFlag = 1; }
     }
     c.physFrame++;
     /* ---------------- dWorldStep: one joint group per lane ---------------- */
@@ -304,6 +306,14 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     }
     ex.sync();
     PD_PHASE(X, 16);
+    if (collDeferred) {
+        uint32_t v = 0;
+        for (int spins = 0; spins < (1 << 26) && (v = *collWait) == 0u; ++spins) { }     /* 1 = clear, 2 = contact (posted by the collision warp of this block) */
+        ex.sync();
+        if (v == 2u) c.collisionFlag = 1;
+        if (lane == 0) *collWait = 0u;                 /* the slot is a pad word of the record: back to 0 before it is stored */
+        ex.sync();
+    }
     post_lookahead_quad(P, T, C, c, ex);
     post_scoring(P, T, C, X, dt);
     c.episodeSteps++; c.thermalPrimed = 1;
