@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------------
 def _ref_worker(args):
     """One process = one host core: `sims` reference simulators stepped `ticks` ticks with the bench workload."""
-    wid, sims, ticks, seed = args
+    wid, sims, ticks, seed, preroll = args
     import numpy as np
     import pdref
     rng = np.random.default_rng(seed + wid)
@@ -91,8 +91,10 @@ def _ref_worker(args):
     lay = pdref.Layout()
     o_col = lay.fields["car.collisionFlag"][0]; o_off = lay.fields["car.outOfTrackFlag"][0]
     t0 = time.perf_counter()
-    for t in range(ticks):
-        if t % TICKS_PER_STEP == 0:
+    for t in range(-preroll, ticks):
+        if t == 0:
+            t0 = time.perf_counter()      # the pre-roll (cars leave the grid, reach speed, episodes start ending) is not timed
+        if t % TICKS_PER_STEP == 0 or t == -preroll:
             acts = rng.uniform(-1, 1, (sims, 2))
         for k, s in enumerate(S):
             s.set_controls(steer=float(acts[k, 0]), gas=float(0.1 + 0.9 * (acts[k, 1] + 1) * 0.5))
@@ -104,12 +106,12 @@ def _ref_worker(args):
     return sims * ticks, time.perf_counter() - t0
 
 
-def run_reference_cpu(total_sims, ticks, cores):
+def run_reference_cpu(total_sims, ticks, cores, preroll=666):
     import multiprocessing as mp
     per = max(1, total_sims // cores)
     with mp.get_context("fork").Pool(cores) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_ref_worker, [(w, per, ticks, 1234) for w in range(cores)])
+        res = pool.map(_ref_worker, [(w, per, ticks, 1234, preroll) for w in range(cores)])
         wall = time.perf_counter() - t0
     units = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
@@ -140,9 +142,9 @@ def reference_arm(args):
         "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1] sample: demo car on driftplayground, random controls resampled every 33 ticks, env auto-reset; "
-                               "each step = %d ticks of %d reference simulators (one process per host core)" % (TICKS_PER_STEP * 4, cores * sims_per_core)},
+                               "each step = %d ticks of %d reference simulators (one process per host core) after 666 untimed pre-roll ticks" % (TICKS_PER_STEP * 4, cores * sims_per_core)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": "%d sims x %d ticks per step, %d steps; reference Car/Sim/Core sources (g++ -O2) + restated ODE 0.16.3 back-end" % (cores * sims_per_core, TICKS_PER_STEP * 4, args.steps)},
+                         "sample": "%d sims x %d ticks per step (after 666 untimed pre-roll ticks), %d steps; reference Car/Sim/Core sources (g++ -O2) + restated ODE 0.16.3 back-end" % (cores * sims_per_core, TICKS_PER_STEP * 4, args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -282,7 +284,7 @@ def ours(args):
         cores = os.cpu_count() or 1
         units, slow, wall = run_reference_cpu(cores * 2, 999, cores)
         cpu = {"value": units / slow, "unit": UNIT, "cores": cores, "kind": "reference",
-               "sample": "%d reference simulators x 999 ticks, one process per core (reference Car/Sim/Core sources, g++ -O2, + restated ODE back-end)" % (cores * 2)}
+               "sample": "%d reference simulators x 999 ticks after 666 untimed pre-roll ticks, one process per core (reference Car/Sim/Core sources, g++ -O2, + restated ODE back-end)" % (cores * 2)}
 
     if rank == 0:
         line = {
