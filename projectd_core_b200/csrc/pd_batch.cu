@@ -511,6 +511,17 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = upload(b, &b->dev.collCell, b->track.collCell))) return rc;
     if ((rc = upload(b, &b->dev.collRec, b->track.collRec))) return rc;
     b->dev.collGrid = b->track.collGrid;
+    {   /* the hull's tables in car_collide_warp's layout */
+        std::vector<float> ht(PD_HULLS_WORDS, 0.0f); const PdCarParams& Pc = b->car.P;
+        for (int i = 0; i < PD_MAX_COLLIDER_TRIS; ++i) {
+            for (int q = 0; q < 4; ++q) ht[PD_HULLS_SPHERE + i * 4 + q] = Pc.colliderTriSphere[i][q];
+            for (int q = 0; q < 6; ++q) ht[PD_HULLS_BOUNDS + i * 6 + q] = Pc.colliderTriBounds[i][q];
+            const int32_t tri = (int)Pc.colliderTris[i][0] | ((int)Pc.colliderTris[i][1] << 8) | ((int)Pc.colliderTris[i][2] << 16);
+            memcpy(&ht[PD_HULLS_TRIS + i], &tri, 4);
+        }
+        for (int i = 0; i < PD_MAX_COLLIDER_VERTS; ++i) for (int q = 0; q < 3; ++q) ht[PD_HULLS_VERTS + i * 3 + q] = Pc.colliderVerts[i][q];
+        if ((rc = upload(b, &b->dev.hullTables, ht))) return rc;
+    }
     b->dev.info = b->track.info;
     const size_t n = (size_t)n_envs;
     const size_t nAlloc = state_alloc_words(b->layout, n);

@@ -328,6 +328,82 @@ template <bool SMEM> __device__ __noinline__ bool car_collide_warp(const PdCarPa
     if (iz1 - iz0 > 8) iz1 = iz0 + 8;
     const int wx = ix1 - ix0 + 1, ncell = wx * (iz1 - iz0 + 1);
     if (stats && lane == 0) stats[0] = ncell;
+    /* parked survivors of the wall lists (one per lane, chassis frame) and their narrow phase */
+    bool pend = false; V3 pb0 = v3(0, 0, 0), pb1 = pb0, pb2 = pb0;
+    auto narrow = [&]() -> bool {
+        const long long tc0 = stats ? clock64() : 0;
+                        const long long ts0 = stats ? clock64() : 0;
+                        if (SMEM && !staged) {      /* first survivor of this car: the hull's filter data and vertices move to this warp's shared memory */
+                            for (int i = lane; i < PD_MAX_COLLIDER_TRIS; i += 32) {
+                                PD_UNROLL for (int q = 0; q < 4; ++q) hullS[PD_HULLS_SPHERE + i * 4 + q] = P.colliderTriSphere[i][q];
+                                PD_UNROLL for (int q = 0; q < 6; ++q) hullS[PD_HULLS_BOUNDS + i * 6 + q] = P.colliderTriBounds[i][q];
+                                hullS[PD_HULLS_TRIS + i] = __int_as_float((int)P.colliderTris[i][0] | ((int)P.colliderTris[i][1] << 8) | ((int)P.colliderTris[i][2] << 16));
+                            }
+                            for (int i = lane; i < PD_MAX_COLLIDER_VERTS; i += 32) { PD_UNROLL for (int q = 0; q < 3; ++q) hullS[PD_HULLS_VERTS + i * 3 + q] = P.colliderVerts[i][q]; }
+                            __syncwarp(FULL);
+                            staged = true;
+                            if (stats && lane == 0) stats[5] += (int)((clock64() - ts0) >> 4);
+                        }
+                        /* Narrow phase in two passes.  Pass 1: every lane takes its own survivor through the hull's triangles with the
+                         * cheap filters only (bounding sphere vs the wall triangle's plane, box vs box) and records the hull triangles
+                         * that remain as a bit mask -- the same instructions on every lane.  Pass 2: the surviving (wall triangle, hull
+                         * triangle) PAIRS of the whole warp are dealt evenly to the 32 lanes, so the expensive plane / edge tests run
+                         * ceil(pairs / 32) times instead of once per hull triangle any lane still cared about. */
+                        unsigned pm[PD_MAX_COLLIDER_TRIS / 32];
+                        PD_UNROLL for (int q = 0; q < PD_MAX_COLLIDER_TRIS / 32; ++q) pm[q] = 0u;
+                        if (pend) {
+                            const V3 lo = v3(fminf(pb0.x, fminf(pb1.x, pb2.x)), fminf(pb0.y, fminf(pb1.y, pb2.y)), fminf(pb0.z, fminf(pb1.z, pb2.z)));
+                            const V3 hi = v3(fmaxf(pb0.x, fmaxf(pb1.x, pb2.x)), fmaxf(pb0.y, fmaxf(pb1.y, pb2.y)), fmaxf(pb0.z, fmaxf(pb1.z, pb2.z)));
+                            const V3 nW = cross(pb1 - pb0, pb2 - pb0);
+                            const float nlen = sqrtf(dot(nW, nW)), dW = dot(nW, pb0), margin = 1e-4f * nlen;
+                            PD_NOUNROLL
+                            for (int j = 0; j < P.nColliderTris; ++j) {
+                                float4 sp;
+                                if (SMEM) sp = *reinterpret_cast<const float4*>(hullS + PD_HULLS_SPHERE + j * 4);
+                                else sp = make_float4(P.colliderTriSphere[j][0], P.colliderTriSphere[j][1], P.colliderTriSphere[j][2], P.colliderTriSphere[j][3]);   /* constant bank, uniform index */
+                                const float sd = nW.x * sp.x + nW.y * sp.y + nW.z * sp.z - dW;
+                                if (fabsf(sd) > sp.w * nlen + margin) continue;
+                                float tb[6];
+                                if (SMEM) { PD_UNROLL for (int q = 0; q < 6; ++q) tb[q] = hullS[PD_HULLS_BOUNDS + j * 6 + q]; }
+                                else { PD_UNROLL for (int q = 0; q < 6; ++q) tb[q] = P.colliderTriBounds[j][q]; }
+                                if (lo.x > tb[3] || hi.x < tb[0] || lo.y > tb[4] || hi.y < tb[1] || lo.z > tb[5] || hi.z < tb[2]) continue;
+                                PD_UNROLL for (int q = 0; q < PD_MAX_COLLIDER_TRIS / 32; ++q) if ((j >> 5) == q) pm[q] |= 1u << (j & 31);
+                            }
+                        }
+                        int cnt = 0;
+                        PD_UNROLL for (int q = 0; q < PD_MAX_COLLIDER_TRIS / 32; ++q) cnt += __popc(pm[q]);
+                        int incl = cnt;                                  /* inclusive prefix sum of the pair counts over the lanes */
+                        PD_UNROLL for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+                        const int total = __shfl_sync(FULL, incl, 31);
+                        bool hit = false;
+                        for (int base = 0; base < total; base += 32) {
+                            const int pidx = base + lane; const bool live = pidx < total;
+                            const int pq = live ? pidx : total - 1;
+                            int c = 0;                                   /* owner lane: the first one whose inclusive count exceeds pq */
+                            PD_UNROLL for (int step = 16; step >= 1; step >>= 1) { const int v = __shfl_sync(FULL, incl, c + step - 1); if (v <= pq) c += step; }
+                            const int k = pq - (__shfl_sync(FULL, incl, c) - __shfl_sync(FULL, cnt, c));      /* k-th surviving hull triangle of that lane */
+                            int j = 0, kk = k; bool found = false;
+                            PD_UNROLL
+                            for (int q = 0; q < PD_MAX_COLLIDER_TRIS / 32; ++q) {
+                                const unsigned mq = __shfl_sync(FULL, pm[q], c); const int pc = __popc(mq);
+                                if (!found) { if (kk < pc) { j = q * 32 + (int)__fns(mq, 0, kk + 1); found = true; } else kk -= pc; }
+                            }
+                            const V3 w0 = v3(__shfl_sync(FULL, pb0.x, c), __shfl_sync(FULL, pb0.y, c), __shfl_sync(FULL, pb0.z, c));
+                            const V3 w1 = v3(__shfl_sync(FULL, pb1.x, c), __shfl_sync(FULL, pb1.y, c), __shfl_sync(FULL, pb1.z, c));
+                            const V3 w2 = v3(__shfl_sync(FULL, pb2.x, c), __shfl_sync(FULL, pb2.y, c), __shfl_sync(FULL, pb2.z, c));
+                            if (live && found) {
+                                const float* tbl = SMEM ? hullS : T.hullTables;      /* per-lane hull triangle: shared memory, or the read-only global copy */
+                                const int tri = __float_as_int(tbl[PD_HULLS_TRIS + j]);
+                                const float* p0 = tbl + PD_HULLS_VERTS + (tri & 255) * 3; const float* p1 = tbl + PD_HULLS_VERTS + ((tri >> 8) & 255) * 3; const float* p2 = tbl + PD_HULLS_VERTS + ((tri >> 16) & 255) * 3;
+                                const V3 a0 = v3(p0[0], p0[1], p0[2]), a1 = v3(p1[0], p1[1], p1[2]), a2 = v3(p2[0], p2[1], p2[2]);
+                                if (!tri_plane_separates(w0, w1, w2, a0, a1, a2) && !tri_plane_separates(a0, a1, a2, w0, w1, w2) && tri_tri(a0, a1, a2, w0, w1, w2)) hit = true;
+                            }
+                            if (__any_sync(FULL, hit)) break;
+                        }
+        pend = false;
+        if (stats && lane == 0) stats[4] += (int)((clock64() - tc0) >> 4);
+        return __any_sync(FULL, hit);
+    };
     for (int cbase = 0; cbase < ncell; cbase += 32) {
         /* lane i fetches the header of cell cbase + i */
         float4 hy = make_float4(3.4e38f, -3.4e38f, 3.4e38f, -3.4e38f), hk = make_float4(0, 0, 0, 0);
@@ -378,61 +454,26 @@ template <bool SMEM> __device__ __noinline__ bool car_collide_warp(const PdCarPa
                     }
                     const unsigned candMask = __ballot_sync(FULL, cand);
                     if (stats && lane == 0) stats[3] += __popc(candMask);
-                    const long long tc0 = stats ? clock64() : 0;
+                    /* survivors are parked, one per lane, until a full warp of them has gathered (or the walk ends): the narrow
+                       phase then runs with every lane busy instead of once per round with a few */
                     if (candMask) {
-                        const long long ts0 = stats ? clock64() : 0;
-                        if (SMEM && !staged) {      /* first survivor of this car: the hull's filter data and vertices move to this warp's shared memory */
-                            for (int i = lane; i < PD_MAX_COLLIDER_TRIS; i += 32) {
-                                PD_UNROLL for (int q = 0; q < 4; ++q) hullS[PD_HULLS_SPHERE + i * 4 + q] = P.colliderTriSphere[i][q];
-                                PD_UNROLL for (int q = 0; q < 6; ++q) hullS[PD_HULLS_BOUNDS + i * 6 + q] = P.colliderTriBounds[i][q];
-                                hullS[PD_HULLS_TRIS + i] = __int_as_float((int)P.colliderTris[i][0] | ((int)P.colliderTris[i][1] << 8) | ((int)P.colliderTris[i][2] << 16));
-                            }
-                            for (int i = lane; i < PD_MAX_COLLIDER_VERTS; i += 32) { PD_UNROLL for (int q = 0; q < 3; ++q) hullS[PD_HULLS_VERTS + i * 3 + q] = P.colliderVerts[i][q]; }
-                            __syncwarp(FULL);
-                            staged = true;
-                            if (stats && lane == 0) stats[5] += (int)((clock64() - ts0) >> 4);
-                        }
-                        /* every lane takes its own survivor through the hull's triangles (up to 32 wall triangles at once) */
-                        bool hit = false;
-                        if (cand) {
-                            const V3 lo = v3(fminf(b0.x, fminf(b1.x, b2.x)), fminf(b0.y, fminf(b1.y, b2.y)), fminf(b0.z, fminf(b1.z, b2.z)));
-                            const V3 hi = v3(fmaxf(b0.x, fmaxf(b1.x, b2.x)), fmaxf(b0.y, fmaxf(b1.y, b2.y)), fmaxf(b0.z, fmaxf(b1.z, b2.z)));
-                            const V3 nW = cross(b1 - b0, b2 - b0);
-                            const float nlen = sqrtf(dot(nW, nW)), dW = dot(nW, b0), margin = 1e-4f * nlen;
-                            PD_NOUNROLL
-                            for (int j = 0; j < P.nColliderTris; ++j) {
-                                float4 sp;
-                                if (SMEM) sp = *reinterpret_cast<const float4*>(hullS + PD_HULLS_SPHERE + j * 4);
-                                else sp = make_float4(P.colliderTriSphere[j][0], P.colliderTriSphere[j][1], P.colliderTriSphere[j][2], P.colliderTriSphere[j][3]);   /* constant bank, uniform index */
-                                const float sd = nW.x * sp.x + nW.y * sp.y + nW.z * sp.z - dW;
-                                if (fabsf(sd) > sp.w * nlen + margin) continue;
-                                float tb[6];
-                                if (SMEM) { PD_UNROLL for (int q = 0; q < 6; ++q) tb[q] = hullS[PD_HULLS_BOUNDS + j * 6 + q]; }
-                                else { PD_UNROLL for (int q = 0; q < 6; ++q) tb[q] = P.colliderTriBounds[j][q]; }
-                                if (lo.x > tb[3] || hi.x < tb[0] || lo.y > tb[4] || hi.y < tb[1] || lo.z > tb[5] || hi.z < tb[2]) continue;
-                                V3 a0, a1, a2;
-                                if (SMEM) {
-                                    const int tri = __float_as_int(hullS[PD_HULLS_TRIS + j]);
-                                    const float* p0 = hullS + PD_HULLS_VERTS + (tri & 255) * 3; const float* p1 = hullS + PD_HULLS_VERTS + ((tri >> 8) & 255) * 3; const float* p2 = hullS + PD_HULLS_VERTS + ((tri >> 16) & 255) * 3;
-                                    a0 = v3(p0[0], p0[1], p0[2]); a1 = v3(p1[0], p1[1], p1[2]); a2 = v3(p2[0], p2[1], p2[2]);
-                                } else {
-                                    const int i0 = P.colliderTris[j][0], i1 = P.colliderTris[j][1], i2 = P.colliderTris[j][2];
-                                    a0 = v3(P.colliderVerts[i0][0], P.colliderVerts[i0][1], P.colliderVerts[i0][2]); a1 = v3(P.colliderVerts[i1][0], P.colliderVerts[i1][1], P.colliderVerts[i1][2]); a2 = v3(P.colliderVerts[i2][0], P.colliderVerts[i2][1], P.colliderVerts[i2][2]);
-                                }
-                                const float s0 = dot(nW, a0) - dW, s1 = dot(nW, a1) - dW, s2 = dot(nW, a2) - dW;
-                                if ((s0 > margin && s1 > margin && s2 > margin) || (s0 < -margin && s1 < -margin && s2 < -margin)) continue;
-                                if (tri_plane_separates(a0, a1, a2, b0, b1, b2)) continue;
-                                if (tri_tri(a0, a1, a2, b0, b1, b2)) { hit = true; break; }
-                            }
-                        }
-                        if (__any_sync(FULL, hit)) return true;
+                        const unsigned freeMask = ~__ballot_sync(FULL, pend);
+                        if (__popc(candMask) > __popc(freeMask)) { if (narrow()) return true; }
+                        const unsigned freeNow = ~__ballot_sync(FULL, pend);
+                        const int rank = __popc(freeNow & ((1u << lane) - 1u));          /* this lane's rank among the free lanes */
+                        const bool take = !pend && rank < __popc(candMask);
+                        const int src = take ? (int)__fns(candMask, 0, rank + 1) : lane;
+                        const V3 n0 = v3(__shfl_sync(FULL, b0.x, src), __shfl_sync(FULL, b0.y, src), __shfl_sync(FULL, b0.z, src));
+                        const V3 n1 = v3(__shfl_sync(FULL, b1.x, src), __shfl_sync(FULL, b1.y, src), __shfl_sync(FULL, b1.z, src));
+                        const V3 n2 = v3(__shfl_sync(FULL, b2.x, src), __shfl_sync(FULL, b2.y, src), __shfl_sync(FULL, b2.z, src));
+                        if (take) { pb0 = n0; pb1 = n1; pb2 = n2; pend = true; }
                     }
-                    if (stats && lane == 0) stats[4] += (int)((clock64() - tc0) >> 4);
                     if (__all_sync(FULL, below)) break;
                 }
             }
         }
     }
+    if (__any_sync(FULL, pend)) { if (narrow()) return true; }
     return false;
 }
 #endif

@@ -63,6 +63,7 @@ struct TrackDev {
     const float* collRec;     /* per entry, 32 B: box min xyz, triangle index bits | box max xyz, 0 (lists sorted by descending ymax) */
     const float* collCell;    /* per cell, 32 B: track y min / max, wall y min / max | first TRACK entry, first WALL entry, end (int bits), 0 */
     PdBoundGrid collGrid;
+    const float* hullTables;  /* the car hull's triangle / vertex tables in car_collide_warp's layout (PD_HULLS_*): read-only global copy */
     PdTrackInfo info;
 };
 
