@@ -103,7 +103,10 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
 }
 
 /* the tick, one thread per car, tiled structure-of-arrays state (batches above the quad threshold) */
-__global__ void __launch_bounds__(PD_BLOCK, 8) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+#ifndef PD_SERIAL_MINBLOCKS
+#define PD_SERIAL_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                    const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     const long long clk0 = io.clk ? clock64() : 0;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,6 +428,7 @@ struct pd_batch {
     float* dReward = nullptr; float* dTotal = nullptr; int32_t* dFlags = nullptr; int32_t* dDone = nullptr;
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     long long* dClk = nullptr; int nClk = 0;
+    int serialSmemPad = 0;            /* tuning knob (env PD_SERIAL_SMEM_PAD, bytes): unused dynamic shared memory per block of k_tick, caps the resident blocks per SM */
     bool collWarp = true;             /* quad kernel: collision warp inside the tick kernel (env PD_COLL_WARP=0: k_collide ahead of it instead) */
     bool zeroCopy = true; const void* zcKey[4] = {nullptr, nullptr, nullptr, nullptr}; void* zcDev[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* dColl = nullptr;         /* k_collide's answers for the coming tick */
@@ -476,6 +480,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     if (const char* q = getenv("PD_E2E_ZEROCOPY")) b->zeroCopy = atoi(q) != 0;
     if (const char* q = getenv("PD_COLL_WARP")) b->collWarp = atoi(q) != 0;
+    if (const char* q = getenv("PD_SERIAL_SMEM_PAD")) { b->serialSmemPad = atoi(q); cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); }
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
     CK(cudaFuncSetAttribute(k_tick_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
@@ -589,7 +594,7 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
         default: k_tick_quad<8><<<grid(b->n, 16), threads, PD_QUAD_SMEM_BYTES_(8), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
         }
     } else
-        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
     b->launches++;
 }
 
