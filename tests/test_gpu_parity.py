@@ -394,3 +394,22 @@ def test_synthetic_large_track_config4(oracle):
     assert np.isfinite(obs).all() and np.abs(obs[:, 0:3]).max(axis=1).mean() > 0.5, "cars should be moving under full throttle"
     s = b.env_stats()
     assert s[3] == 0 and s[7] == 0, "no collisions / NaNs expected on the open generated circuit"
+
+
+@pytest.mark.parametrize("n", [1, 5, 37])
+def test_ragged_batch_sizes_match_full_batch(oracle, n):
+    """Batch sizes that do not fill a block / a warp / a quad group: every env of an n-env batch must end in exactly the state
+    the same env reaches inside a 64-env batch (same start point, same actions; collision frames included)."""
+    import torch
+    us = np.linspace(0.05, 0.95, 64).astype(np.float32)
+    full = _batch(oracle, 64); full.set_seed(9, 0); full.teleport_spline(us); full.set_autoreset(1)
+    part = _batch(oracle, n); part.set_seed(9, 0); part.teleport_spline(us[:n]); part.set_autoreset(1)
+    act = torch.zeros((64, 2), device="cuda"); act[:, 0] = torch.linspace(-0.6, 0.6, 64, device="cuda"); act[:, 1] = 0.8
+    rf = torch.zeros(64, device="cuda"); df = torch.zeros(64, device="cuda", dtype=torch.int32)
+    rp = torch.zeros(n, device="cuda"); dp = torch.zeros(n, device="cuda", dtype=torch.int32)
+    for t in range(300):
+        full.env_step(act, DT, None, rf, df); part.env_step(act[:n].contiguous(), DT, None, rp, dp)
+    full.sync(); part.sync()
+    assert np.array_equal(full.snapshot()[:, :n], part.snapshot())
+    assert torch.equal(rf[:n].cpu(), rp.cpu()) and torch.equal(df[:n].cpu(), dp.cpu())
+    assert torch.equal(full.obs_tensor()[:n].cpu(), part.obs_tensor().cpu())
