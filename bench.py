@@ -281,10 +281,14 @@ def ours(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and pdref.available():
-        cores = os.cpu_count() or 1
-        units, slow, wall = run_reference_cpu(cores * 2, 999, cores)
-        cpu = {"value": units / slow, "unit": UNIT, "cores": cores, "kind": "reference",
-               "sample": "%d reference simulators x 999 ticks after 666 untimed pre-roll ticks, one process per core (reference Car/Sim/Core sources, g++ -O2, + restated ODE back-end)" % (cores * 2)}
+        # in a fresh interpreter (this process holds a CUDA context and pinned buffers; workers forked from it ran ~3x slower)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "12", "--warmup", "1"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600).stdout.strip().splitlines()
+            ref = json.loads(out[-1])
+            cpu = ref.get("cpu_baseline")
+        except Exception as ex:  # the baseline is a reported figure, not part of the measurement
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference", "sample": "failed: %s" % ex}
 
     if rank == 0:
         line = {
