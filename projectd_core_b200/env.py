@@ -41,6 +41,8 @@ class BatchedProjectDEnv:
     stuck_timeout = 5.0
 
     teleport_mode = 0   # 0:Start, 1:Nearest, 2:Random
+    autoreset_mode = 0  # 0: a finished env is reset inside the step that finished it (SB3-style VecEnv, 3 launches per step);
+                        # 1: at the following step, whose action is ignored (gymnasium >= 1.0 VectorEnv; 1 launch per step)
     min_gas = 0.1
     max_gas = 1.0
 
@@ -69,6 +71,7 @@ class BatchedProjectDEnv:
         b = self.batch
         b.set_seed(seed, env_id_offset)
         b.teleport_mode(self.teleport_mode)                                    # projectd_env.py:123
+        b.set_autoreset(self.autoreset_mode)
         b.set_assists(self.auto_clutch, self.auto_shift, self.auto_blip)        # :125
         for name, value in self.car_tunes.get(self.car_model, {}).items():      # :127-129
             b.set_tune(name, value)

@@ -232,7 +232,7 @@ def test_pyprojectd_mirror_matches_reference_car_state(oracle):
 def test_batched_env_reset_step(oracle):
     import torch
     from projectd_core_b200.env import BatchedProjectDEnv
-    env = BatchedProjectDEnv(oracle.BASE_PATH, num_envs=1024, device=0, seed=3, teleport_mode=2)
+    env = BatchedProjectDEnv(oracle.BASE_PATH, num_envs=1024, device=0, seed=3, teleport_mode=2, autoreset_mode=1)
     obs = env.reset()
     assert obs.shape == (1024, 24) and obs.is_cuda
     lo, hi = env.observation_bounds()
