@@ -138,6 +138,12 @@ __global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __
 /* exchange policy of pd_quad.h on the GPU: shuffles inside the quad, with the quad's own member mask */
 struct QuadShfl {
     int lane; unsigned mask; int base;
+    /* helper lanes: when a warp holds at most 4 cars, a second quad per car (lane + 4*CPW) runs the same tick on the same data and
+       takes half of the work of the sections that split cleanly (half = 0 main / 1 helper, nhalf = 1 or 2); peer() swaps a value
+       with the twin lane, mask8 covers both quads */
+    int half, nhalf, off; unsigned mask8;
+    __device__ __forceinline__ float peer(float v) const { return nhalf == 2 ? __shfl_xor_sync(mask8, v, off) : v; }
+    __device__ __forceinline__ int peer(int v) const { return nhalf == 2 ? __shfl_xor_sync(mask8, v, off) : v; }
 #if defined(PD_PHASE_CLOCKS)
     long long* ph;
 #endif
@@ -147,7 +153,7 @@ struct QuadShfl {
     __device__ __forceinline__ float sum(float v) const { v += __shfl_xor_sync(mask, v, 1); v += __shfl_xor_sync(mask, v, 2); return v; }
     __device__ __forceinline__ V3 sum(V3 v) const { return v3(sum(v.x), sum(v.y), sum(v.z)); }
     __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask8); }
 };
 
 /* ---- bulk asynchronous copies HBM <-> shared memory (the TMA engine's 1-D path: SASS UBLKCP) ---- */
@@ -189,8 +195,9 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(const __grid_const
     const long long clk0 = io.clk ? clock64() : 0;
     const int tid = threadIdx.x;
     const int wl = tid & 31, warp = tid >> 5;
-    const bool worker = wl < 4 * CPW;                            /* lanes beyond the warp's cars only help with the block-level steps */
-    const int cid = warp * (4 * CPW) + (worker ? wl : 0);        /* compact index of a working lane */
+    constexpr bool HELP = (8 * CPW <= 32);                       /* room for a helper quad per car in the same warp */
+    const bool worker = wl < (HELP ? 8 * CPW : 4 * CPW);         /* lanes beyond the warp's cars (and their helpers) only help with the block-level steps */
+    const int cid = warp * (4 * CPW) + (worker ? (wl % (4 * CPW)) : 0);   /* compact index of a working lane (a helper shares its main lane's) */
     const int car0 = blockIdx.x * QCARS;
     const int ncars = min(QCARS, n - car0);
     const int car = cid >> 2, e = car0 + car;
@@ -206,12 +213,14 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(const __grid_const
     SVFlat sv = sv_flat(rec);
     const bool resetNow = on && io.pending && io.pending[e];
     QuadShfl ex; ex.lane = wl & 3; ex.base = wl & ~3; ex.mask = 0xFu << ex.base;
+    ex.off = 4 * CPW; ex.nhalf = HELP ? 2 : 1; ex.half = (HELP && wl >= 4 * CPW) ? 1 : 0;
+    ex.mask8 = HELP ? (ex.mask | (ex.half ? (ex.mask >> ex.off) : (ex.mask << ex.off))) : ex.mask;
 #if defined(PD_PHASE_CLOCKS)
     ex.ph = (io.clk && wl == 0 && warp < 2) ? io.clk + 4096 + (size_t)(blockIdx.x * 2 + warp) * 32 : nullptr;   /* profiling build: 32 stamps per warp after the per-warp totals */
 #endif
     if (on) {
         if (ex.lane == 0) rec[PD_OFF_TYRE(0) + PD_TYRE_o_tyrePad] = 0u;      /* the collision warp's mailbox (a pad word of the record) starts empty */
-        if (resetNow) { if (ex.lane == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
+        if (resetNow) { if (ex.lane == 0 && ex.half == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
         else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
     }
     /* A third warp, when launched (blockDim 96: full ticks without k_collide's answer), is the block's COLLISION WARP: it

@@ -204,7 +204,10 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     else if (lane == 2) build_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G);
     else build_tank(P, S, C, hinv, G);
     PD_PHASE(X, 9);
-    factor_group(G, dA, dB, dC, hinv, S21, b6);
+    ex.sync();
+    build_D(G, dA, dB, dC, hinv, PD_GMAX, true, ex.half, ex.nhalf);     /* a helper quad builds every other row pair */
+    ex.sync();
+    factor_group(G, dA, dB, dC, hinv, S21, b6, PD_GMAX, true, true);
     PD_PHASE(X, 10);
     for (int k = 0; k < 21; ++k) S21[k] = ex.sum(S21[k]);
     for (int k = 0; k < 6; ++k) b6[k] = ex.sum(b6[k]);
@@ -255,7 +258,22 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
             const V3 dir = norm(rayEndL - rayStart);
             const V3 rayEnd = rayStart + dir * (P.probeLength[r] * 1.1f);
             rax = rayStart.x; raz = rayStart.z; rbx[k] = rayEnd.x; rbz[k] = rayEnd.z;
+            if (ex.nhalf == 2) continue;                            /* with a helper quad the walks happen below, one per twin lane */
             if (!probe_walk(T, rax, raz, rbx[k], rbz[k], cachePos, nearRSq, pr[k])) needBrute = true;
+        }
+        if (ex.nhalf == 2) {
+            /* the main lane walks probe `lane`, its twin probe `lane + 4` -- at the SAME call site, so the two walks run side by side */
+            const int kk = ex.half;
+            const bool have = kk ? mine[1] : mine[0];
+            const float bx = kk ? rbx[1] : rbx[0], bz = kk ? rbz[1] : rbz[0];
+            float best = FLT_MAX;
+            if (have) { if (!probe_walk(T, rax, raz, bx, bz, cachePos, nearRSq, best)) needBrute = true; }
+            if (kk) pr[1] = best; else pr[0] = best;
+        }
+        if (ex.nhalf == 2) {
+            const float o0 = ex.peer(pr[0]), o1 = ex.peer(pr[1]); const int ob = ex.peer(needBrute ? 1 : 0);
+            if (ex.half == 1) pr[0] = o0; else pr[1] = o1;
+            needBrute = needBrute || ob != 0;
         }
         PD_PHASE(X, 13);
         int bestPoint = 0;

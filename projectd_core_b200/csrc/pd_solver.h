@@ -230,12 +230,14 @@ PD_HD void jinvm6(const float* J, const BodyDyn& d, float* o) {
  * Row loops are kept ROLLED (compact code: the kernel is instruction-fetch sensitive), the 6- and 7-wide inner
  * loops are unrolled.  n = rows to process: the 4-lanes-per-car kernel runs all PD_GMAX rows on every lane (padding
  * rows are identity, so there is no divergence); the thread-per-car kernel passes the group's real row count. */
-template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6, const int n = PD_GMAX, const bool hasB = true) {
+/* D = JA MA^-1 JA^T + JB MB^-1 JB^T + cfm/h and the right-hand side r, row pairs first, first + step, ... (step = 2 when a helper
+ * lane takes every other pair: the two callers write disjoint entries of the shared scratch and must synchronise afterwards) */
+template <class GS> PD_HDN void build_D(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, const int n = PD_GMAX, const bool hasB = true, const int first = 0, const int step = 1) {
     /* D build, TWO rows per pass: rows i and i+1 share every load of the rows j <= i they are multiplied with
      * (half the scratch reads, two independent sums in flight); each sum runs over the same terms in the same order
      * as a row-at-a-time build, so the result is bit-identical to it. */
     PD_NOUNROLL
-    for (int i = 0; i < n; i += 2) {
+    for (int i = 2 * first; i < n; i += 2 * step) {
         const bool two = i + 1 < n;
         const int i1 = two ? i + 1 : i;
         float ra0[6], rb0[6], ja0[6], jb0[6], ra1[6], rb1[6], ja1[6], jb1[6];
@@ -278,6 +280,10 @@ template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, con
             G.Y(i1, 6) = G.Y(i1, 6) * hinv - s;
         }
     }
+}
+
+template <class GS> PD_HDN void factor_group(const GS& G, const BodyDyn& dA, const BodyDyn& dB, const BodyDyn& dC, float hinv, float* S21, float* b6, const int n = PD_GMAX, const bool hasB = true, const bool dBuilt = false) {
+    if (!dBuilt) build_D(G, dA, dB, dC, hinv, n, hasB);
     /* L D L^T, row by row (same recurrence as the oracle's dense factorisation), in place */
     PD_NOUNROLL
     for (int i = 0; i < n; ++i) {

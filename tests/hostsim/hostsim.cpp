@@ -31,6 +31,9 @@ struct HS {
 struct QuadShared { float slot[4][3]; int islot[4]; pthread_barrier_t bar; };
 struct QuadHost {
     int lane; QuadShared* sh;
+    int half = 0, nhalf = 1;
+    float peer(float v) { return v; }
+    int peer(int v) { return v; }
     void sync() { pthread_barrier_wait(&sh->bar); }
     float get(float v, int src) { sh->slot[lane][0] = v; sync(); float r = sh->slot[src][0]; sync(); return r; }
     int get(int v, int src) { sh->islot[lane] = v; sync(); int r = sh->islot[src]; sync(); return r; }
