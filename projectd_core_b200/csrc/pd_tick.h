@@ -180,9 +180,22 @@ template <class Ex> PD_HD void post_lookahead_quad(const PdCarParams& P, const T
     for (int k = 0; k < 2; ++k) {
         const int i = ex.lane + 4 * k;
         if (i >= cnt) continue;
+        if (ex.nhalf == 2) continue;                   /* with a helper quad the twins take one point each (below) */
         const float distanceNorm = c.trackLocation + ((P.lookAheadStep * (float)(i + 1)) / T.info.computedTrackLength) * driveDir;
         const V3 dir = track_direction_at_distance(T, distanceNorm);
         mine[k] = m_atan2(dot(cross(dir, curTrackDir), up), dot(curTrackDir, dir));
+    }
+    if (ex.nhalf == 2) {
+        /* both twins run the same code on their own point (lane and lane + 4), then swap */
+        const int i = ex.lane + 4 * ex.half;
+        float v = 0.0f;
+        if (i < cnt) {
+            const float distanceNorm = c.trackLocation + ((P.lookAheadStep * (float)(i + 1)) / T.info.computedTrackLength) * driveDir;
+            const V3 dir = track_direction_at_distance(T, distanceNorm);
+            v = m_atan2(dot(cross(dir, curTrackDir), up), dot(curTrackDir, dir));
+        }
+        const float o = ex.peer(v);
+        mine[0] = ex.half ? o : v; mine[1] = ex.half ? v : o;
     }
     for (int i = 0; i < cnt; ++i) c.lookAhead[i] = ex.get((i < 4) ? mine[0] : mine[1], i & 3);
 }

@@ -333,8 +333,10 @@ template <class Ex> PD_HD bool spline_nearest_quad(const TrackDev& T, V3 pos, in
     if (seg2 >= np) seg2 = 0;
     int cnt = seg2 - seg1; if (cnt < 0) cnt += np;
     if (!seg1 && !seg2) cnt = np;
-    const int chunk = (cnt + 3) >> 2;
-    const int k0 = ex.lane * chunk, k1 = (k0 + chunk < cnt) ? k0 + chunk : cnt;
+    const int parts = 4 * ex.nhalf, part = ex.lane + 4 * ex.half;      /* a helper quad doubles the number of chunks; chunks stay in sequence order */
+    const int chunk = (cnt + parts - 1) / parts;
+    int k0 = part * chunk; if (k0 > cnt) k0 = cnt;
+    const int k1 = (k0 + chunk < cnt) ? k0 + chunk : cnt;
     float bd = FLT_MAX; int bk = -1;
     int id = seg1 + k0; if (id >= np) id -= np;
     PD_UNROLL4
@@ -347,6 +349,10 @@ template <class Ex> PD_HD bool spline_nearest_quad(const TrackDev& T, V3 pos, in
     PD_UNROLL
     for (int off = 1; off <= 2; off <<= 1) {
         const float od = ex.get(bd, ex.lane ^ off); const int ok = ex.get(bk, ex.lane ^ off);
+        if (ok >= 0 && (bk < 0 || od < bd || (od == bd && ok > bk))) { bd = od; bk = ok; }
+    }
+    if (ex.nhalf == 2) {
+        const float od = ex.peer(bd); const int ok = ex.peer(bk);
         if (ok >= 0 && (bk < 0 || od < bd || (od == bd && ok > bk))) { bd = od; bk = ok; }
     }
     if (bk < 0) { outId = 0; outDist = 0; return false; }
@@ -364,7 +370,7 @@ template <class Ex> PD_HD bool nearest_point_grid_quad(const TrackDev& T, V3 pos
     float bestDistSq = FLT_MAX; int best = -1;
     for (int R = 1; R <= PD_NEAREST_MAX_RING; ++R) {
         const int side = 2 * R + 1;
-        for (int cell = ex.lane; cell < side * side; cell += 4) {          /* the block's cells, dealt round-robin to the four lanes */
+        for (int cell = ex.lane + 4 * ex.half; cell < side * side; cell += 4 * ex.nhalf) {          /* the block's cells, dealt round-robin to the lanes (a helper quad doubles them) */
             const int dz = cell / side - R, dx = cell % side - R;
             if (R > 1 && dz > -R && dz < R && dx > -R && dx < R) continue; /* inner block: already scanned */
             const int iz = cz + dz, ix = cx + dx;
@@ -375,6 +381,10 @@ template <class Ex> PD_HD bool nearest_point_grid_quad(const TrackDev& T, V3 pos
         PD_UNROLL
         for (int off = 1; off <= 2; off <<= 1) {
             const float od = ex.get(qd, ex.lane ^ off); const int oi = ex.get(qi, ex.lane ^ off);
+            if (oi >= 0 && (qi < 0 || qd > od || (qd == od && oi < qi))) { qd = od; qi = oi; }
+        }
+        if (ex.nhalf == 2) {
+            const float od = ex.peer(qd); const int oi = ex.peer(qi);
             if (oi >= 0 && (qi < 0 || qd > od || (qd == od && oi < qi))) { qd = od; qi = oi; }
         }
         const float border = inCell + (float)R * G.cell - 0.01f;
