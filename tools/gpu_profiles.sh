@@ -5,4 +5,4 @@ timeout 400 $NCU -k regex:k_tick_quad -s 2300 -c 1 -f -o gpurun_out/r01_quad_v10
 timeout 400 $NCU -k regex:k_tick_quad -s 2301 -c 1 -f -o gpurun_out/r01_quad_v10_4096_odd python tools/prof_env.py 4096 2400 > gpurun_out/y_ncu2.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 2050 -c 200 --csv --log-file gpurun_out/r01_launches_v10_4096.csv python tools/prof_env.py 4096 2300 > gpurun_out/y_ncu3.log 2>&1
 timeout 200 python tools/phase_tail.py 4096 2000 > gpurun_out/y_phase.log 2>&1
-bash tools/gpu_job_final.sh
+bash tools/gpu_round_end.sh
