@@ -24,7 +24,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DT = 1.0 / 333.0
 TICKS_PER_STEP = 33
@@ -83,7 +82,7 @@ def _ref_worker(args):
     """One process = one host core: `sims` reference simulators stepped `ticks` ticks with the bench workload."""
     wid, sims, ticks, seed, preroll = args
     import numpy as np
-    import pdref
+    pdref = _oracle()
     rng = np.random.default_rng(seed + wid)
     S = [pdref.RefSim() for _ in range(sims)]
     for k, s in enumerate(S):
@@ -106,6 +105,14 @@ def _ref_worker(args):
     return sims * ticks, time.perf_counter() - t0
 
 
+def _oracle():
+    """ctypes wrapper of oracle/_ref/libpdref.so -- the ONLY oracle use of this file: the reference arm / cpu_baseline."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pdref", os.path.join(ROOT, "oracle", "pdref.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
 def run_reference_cpu(total_sims, ticks, cores, preroll=666):
     import multiprocessing as mp
     per = max(1, total_sims // cores)
@@ -122,7 +129,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import pdref
+    pdref = _oracle()
     if not pdref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
         return
@@ -157,9 +164,9 @@ def reference_arm(args):
 def ours(args):
     import numpy as np
     import torch
-    import pdref
     from projectd_core_b200 import Batch
-    from parity_util import make_env_like
+    from projectd_core_b200.assets import default_base
+    from projectd_core_b200.env import configure_like_env
 
     from projectd_core_b200 import dist as pdist
     rank, local, world = pdist.init_from_env("nccl")
@@ -172,7 +179,7 @@ def ours(args):
     n_envs = args.envs if args.envs else (4096 if world == 1 else 65536)
     K, W = args.steps, args.warmup
 
-    b = make_env_like(Batch(pdref.BASE_PATH, n_envs=n_envs, device=dev.index, synthetic_tris=args.synthetic_tris))
+    b = configure_like_env(Batch(default_base(), n_envs=n_envs, device=dev.index, synthetic_tris=args.synthetic_tris))
     env_offset, _ = pdist.shard_range(world * n_envs, rank, world)
     b.set_seed(1234, env_offset)             # RNG keyed by global env id: results do not depend on the sharding
     b.teleport_mode(2)                        # random start positions u ~ U[0,1)
@@ -280,7 +287,7 @@ def ours(args):
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and pdref.available():
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpdref.so")):
         # in a fresh interpreter (this process holds a CUDA context and pinned buffers; workers forked from it ran ~3x slower)
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "12", "--warmup", "1"],
@@ -316,9 +323,11 @@ def ours(args):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+    # orderly teardown (no os._exit: the driver's exit hook records which native libraries this process loaded): drop every
+    # torch handle that aliases the batch's buffers, release the batch, then let the interpreter exit normally
+    del obs, evs, e0, e1, stream
     b.sync(); b.close()
-    sys.stdout.flush(); sys.stderr.flush()
-    os._exit(0)      # skip interpreter teardown: torch may destroy the CUDA context before ctypes-held handles are released
+    torch.cuda.synchronize()
 
 
 def main():

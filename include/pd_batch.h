@@ -150,6 +150,8 @@ void* pd_stream(pd_batch* b);                        /* the cudaStream_t every k
 uint64_t pd_launch_count(const pd_batch* b);
 /* name of the tick kernel this batch dispatches to ("k_tick_quad": <= 8192 envs, "k_tick": larger batches) */
 const char* pd_tick_kernel(const pd_batch* b);
+/* the exact kernel instance: "k_tick_quad<2>" / "<4>" / "<8>" (cars per warp) or "k_tick"; the parity tests run on every one */
+const char* pd_tick_kernel_instance(const pd_batch* b);
 
 #ifdef __cplusplus
 }

@@ -6,9 +6,9 @@ import os
 import re
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # oracle/ sits at the repo root
 LIB_PATH = os.path.join(ROOT, "oracle", "_ref", "libpdref.so")
-BASE_PATH = os.path.join(ROOT, "oracle", "_ref", "base")
+BASE_PATH = os.path.join(ROOT, "assets", "_base")   # content copy made by `make -C oracle content` (git-ignored, travels to the GPU box)
 
 ENV_TUNES = {  # pyprojectd/projectd_env.py:83-94
     "FRONT_BIAS": 55.0, "DIFF_POWER": 30.0, "DIFF_COAST": 30.0, "FINAL_RATIO": 5.0,

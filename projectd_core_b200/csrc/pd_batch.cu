@@ -936,6 +936,11 @@ int pd_raycast(pd_batch* b, int n, const float* rays, float* out) {
 int pd_sync(pd_batch* b) { if (!b) return PD_ERR_ARG; CK(cudaStreamSynchronize(b->stream)); CK(cudaGetLastError()); return PD_OK; }
 void* pd_stream(pd_batch* b) { return b ? (void*)b->stream : nullptr; }
 const char* pd_tick_kernel(const pd_batch* b) { return !b ? "" : (b->layout == PD_LAYOUT_RECORDS ? "k_tick_quad" : "k_tick"); }
+const char* pd_tick_kernel_instance(const pd_batch* b) {
+    if (!b) return "";
+    if (b->layout != PD_LAYOUT_RECORDS) return "k_tick";
+    return b->quadCpw == 2 ? "k_tick_quad<2>" : b->quadCpw == 4 ? "k_tick_quad<4>" : "k_tick_quad<8>";
+}
 uint64_t pd_launch_count(const pd_batch* b) { return b ? b->launches : 0; }
 
 } /* extern "C" */

@@ -18,6 +18,17 @@ from .binding import Batch, OBS_DIM
 from . import dist as pdist
 
 
+def configure_like_env(batch, car_model="ks_toyota_ae86_drift", auto_clutch=True, auto_shift=True, auto_blip=True):
+    """Configure a Batch the way ProjectDEnv.__init__ configures its simulator (projectd_env.py:118-136): assists, the
+    car's tune table, the scoring variables."""
+    batch.set_assists(auto_clutch, auto_shift, auto_blip)
+    for name, value in BatchedProjectDEnv.car_tunes.get(car_model, {}).items():
+        batch.set_tune(name, value)
+    for name, value in BatchedProjectDEnv.scoring_vars.items():
+        batch.set_scoring_var(name, value)
+    return batch
+
+
 class BatchedProjectDEnv:
     sim_dt = 1.0 / 333.0
     track_name = "driftplayground"

@@ -85,3 +85,126 @@ def scripted_controls(t, phase=0.0, gas_scale=1.0):
     gas = (0.1 + 0.9 * min(1.0, t / 333.0)) * gas_scale
     steer = 0.3 * math.sin(2 * math.pi * t / 999.0 + phase)
     return steer, gas
+
+
+def centering_steer(lay, rec, gain=1.5):
+    """Keeps a car on the road: steer against the difference of the two 25-degree probes (state of the last tick)."""
+    p1 = lay.get(rec, "car.probe1"); p2 = lay.get(rec, "car.probe2")
+    return max(-1.0, min(1.0, -gain * (p1 - p2) / (p1 + p2 + 1e-3)))
+
+
+def drive_controls(t, i, lay=None, rec=None):
+    """Scripted drive i at tick t -> keyword arguments of RefSim.set_controls.
+      kind 0 (i % 64 in 0..15)  config-1 style throttle ramp + steering sine from the grid (the round-1 drives);
+      kind 1 (16..31) from a rolling start (see drive_start_states): handbrake turns and brake-to-lock at speed;
+      kind 2 (32..47) from the grid: reverse-gear launch through the sequential shifter, brake to a standstill and wait
+                      (sleep counter), forward again;
+      kind 3 (48..63) from a rolling start: first gear held on the rev limiter, then full steering lock at speed (the car
+                      leaves the tarmac: grass / sand / kerb surfaces).
+    rec = the oracle's state before the tick (for the road-keeping steering of the rolling drives)."""
+    steer, gas = scripted_controls(t, phase=0.7 * i, gas_scale=0.4 + 0.6 * ((i % 4) / 3.0))
+    c = dict(steer=steer, gas=gas, brake=0.0, hand_brake=0.0, clutch=0.0, req_gear=-1, gear_up=0, gear_dn=0)
+    kind = (i // 16) % 4
+    if i % 5 == 4 and 400 < t < 450:
+        c["brake"] = 0.6
+    if kind in (1, 3) and rec is not None:
+        c["steer"] = centering_steer(lay, rec); c["gas"] = 1.0 if lay.get(rec, "car.speed") < 22 else 0.3
+    if kind == 1:
+        if 60 <= t % 300 < 130:
+            c["hand_brake"] = 1.0; c["steer"] = 0.8 if i % 2 else -0.8
+        if 180 <= t % 300 < 250:
+            c["brake"] = 1.0; c["gas"] = 0.0
+    elif kind == 2:
+        if t < 6:
+            c["gear_dn"] = 1 if t % 2 == 0 else 0; c["gas"] = 0.0
+        elif t < 180:
+            c["gas"] = 0.7
+        elif t < 420:
+            c["gas"] = 0.0; c["brake"] = 0.9
+        elif t < 430:
+            c["gear_up"] = 1 if t % 2 == 0 else 0; c["gas"] = 0.0
+    elif kind == 3:
+        c["gas"] = 1.0
+        if t < 150:
+            c["req_gear"] = 2
+        if t > 200 + 10 * (i % 16):
+            c["steer"] = 1.0 if i % 2 else -1.0
+    return c
+
+
+_START_CACHE = {}
+# spline points of yamanashi_short whose left verge (2.5 m beyond the boundary) is SAND (DAMPING 0.1, DIRT_ADDITIVE 1, SIN_HEIGHT 0.04)
+_SAND_POINTS = {"yamanashi_short": [444, 448, 452, 456, 460, 464]}
+
+
+def place_beside_track(oracle_mod, lay, r, track, pid, side=0, extra=2.5):
+    """Stand the car of RefSim r on the verge: the grid pose at spline point pid, translated sideways past the track boundary
+    (side 0 = left) by `extra` metres and vertically by the ground-height difference (two oracle rays)."""
+    fat = np.fromfile(oracle_mod.BASE_PATH + "/content/tracks/%s/spline.cache" % track, dtype=np.float32).reshape(-1, 15)
+    best = fat[pid, 0:3]; edge = fat[pid, 3:6] if side == 0 else fat[pid, 6:9]
+    d = (edge - best).astype(np.float64); d[1] = 0; w = float(np.linalg.norm(d)); d /= max(w, 1e-6)
+    off = d * (w + extra)
+    rays = np.zeros((2, 7), np.float32); rays[:, 4] = -1; rays[:, 6] = 20
+    rays[0, 0:3] = best + np.array([0, 5, 0], np.float32); rays[1, 0:3] = best + off.astype(np.float32) + np.array([0, 5, 0], np.float32)
+    out = np.zeros((2, 8), np.float32); r.L.pdref_raycast(r.h, 2, rays.ctypes.data, out.ctypes.data)
+    assert out[0, 0] and out[1, 0], "no ground beside spline point %d" % pid
+    dy = float(out[1, 2] - out[0, 2]) + 0.02
+    r.teleport_spline(pid / len(fat))
+    rec = r.state().copy()
+    for bd in _BODIES:
+        lay.set(rec, bd + ".px", lay.get(rec, bd + ".px") + float(off[0])); lay.set(rec, bd + ".pz", lay.get(rec, bd + ".pz") + float(off[2]))
+        lay.set(rec, bd + ".py", lay.get(rec, bd + ".py") + dy)
+    r.set_state(rec)
+
+
+def drive_start_states(oracle_mod, lay, track, n, preroll=1200):
+    """Start records of the n scripted drives on `track` (cached per session): kinds 0 / 2 stand on the grid at their spline
+    position; kinds 1 / 3 have been driven `preroll` ticks by the oracle under the road-keeping steering (10-16 m/s, 3rd gear)."""
+    key = (track, n, preroll)
+    if key in _START_CACHE:
+        return _START_CACHE[key]
+    out = []
+    for i in range(n):
+        r = oracle_mod.RefSim(track=track)
+        r.teleport_spline((i % 16) / 16 + (i // 16) * 0.013)
+        sand = _SAND_POINTS.get(track, [])
+        if (i // 16) % 4 == 3 and (i % 16) < len(sand):
+            place_beside_track(oracle_mod, lay, r, track, sand[i % 16])          # these drives start on the verge
+        elif (i // 16) % 4 in (1, 3):
+            for t in range(preroll):
+                rec = r.state()
+                r.set_controls(steer=centering_steer(lay, rec), gas=1.0 if lay.get(rec, "car.speed") < 22 else 0.3)
+                r.step()
+        out.append((r.state().copy(), r.time(), r.frame()))
+        r.close()
+    _START_CACHE[key] = out
+    return out
+
+
+def coverage_marks(lay, rec, seen):
+    """Which of the rarely visited regions of the state space the (oracle) record `rec` is in."""
+    g = lambda n: lay.get(rec, n)
+    gear = g("car.currentGear")
+    if gear == 0 and abs(g("car.speed")) > 1.0:
+        seen.add("reverse")
+    if gear >= 3:
+        seen.add("gear>=3")
+    if g("car.ctlHandBrake") > 0.5 and g("car.speed") > 3.0:
+        seen.add("handbrake")
+    if g("car.limiterOn"):
+        seen.add("limiter")
+    if g("car.sleepingFrames") > 50:
+        seen.add("sleeping")
+    if g("car.isGearGrinding"):
+        seen.add("grinding")
+    for w in range(4):
+        if g("tyre%d.isLocked" % w) and g("car.speed") > 3.0:
+            seen.add("locked_wheel_at_speed")
+        s = g("tyre%d.surfaceId" % w)
+        if s > 0 and g("tyre%d.hasContact" % w):
+            seen.add("surface%d" % s)
+        if not g("tyre%d.hasContact" % w):
+            seen.add("wheel_airborne")
+        if g("tyre%d.dirtyLevel" % w) > 0:
+            seen.add("dirty_tyre")
+    return seen

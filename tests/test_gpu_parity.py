@@ -5,7 +5,7 @@ import math
 import numpy as np
 import pytest
 
-from parity_util import compare_records, make_env_like, scripted_controls
+from parity_util import compare_records, coverage_marks, drive_controls, drive_start_states, make_env_like, scripted_controls
 
 pytestmark = pytest.mark.gpu
 DT = 1.0 / 333.0
@@ -85,49 +85,93 @@ def test_spline_cache_known_answers(oracle):
     assert np.abs(out[:, 1:4] - fat[:, 0:3]).max() <= 1e-4
 
 
-@pytest.mark.parametrize("n_envs,ticks", [(16, 700)])
-def test_single_tick_parity_identical_states(oracle, lay, n_envs, ticks):
-    """For every tick of 16 scripted drives (different start points, steering phases, throttle): load the
-    oracle's state into the GPU batch, advance ONE tick on the GPU and in the oracle, compare all state fields.
-    Flags / FSM ints exact, floats within tol (see parity_util)."""
-    b = _batch(oracle, n_envs)
-    refs = [oracle.RefSim() for _ in range(n_envs)]
-    for i, r in enumerate(refs):
-        r.teleport_spline(i / n_envs)
-    worst = 0.0; nbad = 0; examples = []
+# every tick-kernel instance the dispatcher can pick (pd_batch.cu finish_create / launch_tick): the quad kernel at 2 / 4 / 8 cars
+# per warp (helper quads at 2 and 4; 4 is what BASELINE configs[1] = 4096 envs runs, 8 serves 4097..8192 envs) and the
+# thread-per-car kernel (what configs[2] = 65536 envs per GPU runs)
+KERNELS = {
+    "k_tick_quad<2>": {"PD_QUAD_MAX_ENVS": "8192", "PD_QUAD_CPW": "2"},
+    "k_tick_quad<4>": {"PD_QUAD_MAX_ENVS": "8192", "PD_QUAD_CPW": "4"},
+    "k_tick_quad<8>": {"PD_QUAD_MAX_ENVS": "8192", "PD_QUAD_CPW": "8"},
+    "k_tick": {"PD_QUAD_MAX_ENVS": "0"},
+}
+
+
+def _select_kernel(monkeypatch, kernel):
+    for k, v in KERNELS[kernel].items():
+        monkeypatch.setenv(k, v)
+
+
+def _single_tick_parity(oracle, lay, b, track, n_envs, ticks, want):
+    starts = drive_start_states(oracle, lay, track, n_envs)
+    refs = [oracle.RefSim(track=track) for _ in range(n_envs)]
+    for r, (rec, tm, fr) in zip(refs, starts):
+        r.set_state(rec); r.set_time(0.0)
+    worst = 0.0; nbad = 0; examples = []; seen = set()
+    recs = [r.state() for r in refs]
     for t in range(ticks):
         for i, r in enumerate(refs):
-            steer, gas = scripted_controls(t, phase=0.7 * i, gas_scale=0.4 + 0.6 * ((i % 4) / 3.0))
-            brake = 0.6 if (i % 5 == 4 and 400 < t < 450) else 0.0
-            r.set_controls(steer=steer, gas=gas, brake=brake)
+            r.set_controls(**drive_controls(t, i, lay, recs[i]))
         b.restore(np.stack([r.state() for r in refs], axis=1))
         b.set_time(refs[0].time())
         b.step(DT, 1)
         out = b.snapshot()
         for i, r in enumerate(refs):
             r.step()
-            bad, w = compare_records(lay, out[:, i], r.state(), tol=1e-4)
+            ref = recs[i] = r.state()
+            bad, w = compare_records(lay, out[:, i], ref, tol=1e-4)
             worst = max(worst, w if np.isfinite(w) else 0.0)
             if bad:
                 nbad += 1
                 if len(examples) < 10:
                     examples.append((t, i, bad[:4]))
-    # exactness of ints is absolute; float exceedances of 1e-4 must stay below 3e-4 and be rare (solver conditioning)
+            coverage_marks(lay, ref, seen)
+    # exactness of ints is absolute; float exceedances of 1e-4 must stay below 3e-4 and be rare (solver conditioning, DESIGN.md §6)
     int_bad = [e for e in examples if any(math.isinf(x[3]) for x in e[2])]
     assert not int_bad, int_bad
     assert worst <= 3e-4, (worst, examples)
     assert nbad <= ticks * n_envs * 0.001, (nbad, examples)
+    # the drives must really have reached the state space they were written for
+    assert want <= seen, sorted(want - seen)
 
 
-def test_free_running_trajectory_divergence_1s(oracle, lay):
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_single_tick_parity_identical_states(oracle, lay, kernel, monkeypatch):
+    """For every tick of 64 scripted drives (parity_util.drive_controls: grid launches, handbrake turns / brake-to-lock at
+    speed, reverse gear, standstill with the sleep counter, rev limiter, leaving the tarmac): load the oracle's state into the
+    GPU batch, advance ONE tick on the GPU and in the oracle, compare all state fields.  Flags / FSM ints exact, floats within
+    the rule of parity_util (north star: 1e-4 relative).  Run on EVERY tick-kernel instance, with blocks / tiles / helper
+    quads filled."""
+    _select_kernel(monkeypatch, kernel)
+    b = _batch(oracle, 64)
+    assert b.tick_kernel_instance() == kernel
+    _single_tick_parity(oracle, lay, b, "driftplayground", 64, 500,
+                        {"reverse", "handbrake", "locked_wheel_at_speed", "limiter", "sleeping", "gear>=3"})
+
+
+@pytest.mark.parametrize("kernel", ["k_tick_quad<4>", "k_tick"])
+def test_single_tick_parity_offtrack_surfaces(oracle, lay, kernel, monkeypatch):
+    """The same on yamanashi_short, whose grass (SIN_HEIGHT 0.03 / SIN_LENGTH 0.5) and sand (DAMPING 0.1, DIRT_ADDITIVE 1,
+    SIN_HEIGHT 0.04) exercise the surface branches of Tyre::step / addGroundContact / stepDirtyLevel (Tyre.cpp:558-602,
+    TyreForces.cpp:212-233) that driftplayground's plain surfaces never reach."""
+    _select_kernel(monkeypatch, kernel)
+    from projectd_core_b200 import Batch
+    b = make_env_like(Batch(oracle.BASE_PATH, track="yamanashi_short", n_envs=64, device=0))
+    assert b.tick_kernel_instance() == kernel
+    _single_tick_parity(oracle, lay, b, "yamanashi_short", 64, 450, {"dirty_tyre", "gear>=3"})
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_free_running_trajectory_divergence_1s(oracle, lay, kernel, monkeypatch):
     """333 ticks (1 s) free running from the same start with the same controls: bounded divergence.
     The drive is a full-throttle first-gear launch of a drift car with sinusoidal steering, i.e. tyres at
     saturation, where round-off differences grow quickly; bound: 5 cm / 0.5 deg after 1 s (measured worst on
     B200: 1.6 cm), gear state identical."""
-    n = 8
+    _select_kernel(monkeypatch, kernel)
+    n = 64
     b = _batch(oracle, n)
+    assert b.tick_kernel_instance() == kernel
     refs = [oracle.RefSim() for _ in range(n)]
-    us = np.array([i / n for i in range(n)], np.float32)
+    us = np.array([(i % 8) / 8 + (i // 8) * 0.007 for i in range(n)], np.float32)
     for i, r in enumerate(refs):
         r.teleport_spline(float(us[i]))
     b.teleport_spline(us)

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.environ["PD_DEBUG_CLOCKS"] = "1"
 os.environ["PD_B200_LIB"] = os.path.join(ROOT, "projectd_core_b200", "libpd_b200_dbg.so")
 import numpy as np, torch
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import pdref
 from projectd_core_b200 import Batch
 from parity_util import make_env_like

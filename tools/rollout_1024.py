@@ -3,7 +3,7 @@ The policy is a torch op on the env's own observation tensor: no host round trip
 import sys, os, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import pdref
 from projectd_core_b200.env import BatchedProjectDEnv
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
