@@ -69,6 +69,10 @@ int pd_car_state_bytes(void);                       /* sizeof(CarState) = 664 (C
 int pd_set_assists(pd_batch* b, int auto_clutch, int auto_shift, int auto_blip);
 /* setCarTune (PyProjectD.cpp:328-335 -> SetupManager::setTune, Car/SetupManager.cpp:283-288) */
 int pd_set_tune(pd_batch* b, const char* name, float value);
+/* setCarRawTune (PyProjectD.cpp:337-344 -> SetupManager::setRawTune, :276-281): the raw value, no spinner clamp / multiplier.
+ * Both return PD_ERR_UNSUPPORTED for a variable the reference registers but this build cannot honour (rear per-wheel suspension
+ * tunes: the rigid axle keeps one parameter set; AWD differentials; turbos); names the reference does not know are ignored as there. */
+int pd_set_raw_tune(pd_batch* b, const char* name, float value);
 /* setScoringVar / getScoringVar (PyProjectD.cpp:346-363; process-global ScoringConfig in the reference) */
 int pd_set_scoring_var(pd_batch* b, const char* name, float value);
 float pd_get_scoring_var(const pd_batch* b, const char* name);
@@ -107,6 +111,23 @@ const float* pd_obs_device_ptr(pd_batch* b);
 /* stepReward[n_envs] f32 and flags[n_envs] i32 (bit0 collisionFlag, bit1 outOfTrackFlag) */
 int pd_get_rewards(pd_batch* b, float* step_reward, float* total_reward, int32_t* flags);
 
+/* The env-level knobs of ProjectDEnv (pyprojectd/projectd_env.py:27-53) that pd_env_step / pd_set_actions apply inside the kernels.
+ * Defaults = the reference's class attributes. */
+typedef struct PdEnvConfig {
+    float min_gas, max_gas;                       /* gas = linscale(a1, -1..1 -> min_gas..max_gas)                 (:52-53,160) */
+    float terminate_hit_penalty, terminate_off_track_penalty, terminate_stuck_penalty;               /* (:42-44) */
+    float terminate_low_reward, stuck_timeout;                                                      /* (:46-47) */
+    int32_t terminate_on_hit, terminate_off_track, terminate_when_stuck;                            /* (:38-40) */
+    int32_t smooth_controls;                      /* the `smooth` argument of setCarControls                       (:27,168) */
+    float clutch;                                 /* controls.clutch sent with every action: 0, or 1.0 when auto_clutch is off (:162-163) */
+    int32_t requested_gear;                       /* controls.requestedGearIndex: -1 sequential, or 2 when auto_shift is off  (:165-166) */
+} PdEnvConfig;
+int pd_set_env_config(pd_batch* b, const PdEnvConfig* cfg);
+int pd_get_env_config(const pd_batch* b, PdEnvConfig* out);
+/* ProjectDEnv.reset's bookkeeping (projectd_env.py:224-227): zero the running episode return / length of every env (mask NULL)
+ * or of the masked envs, after the reset's own step */
+int pd_env_reset_counters(pd_batch* b, const uint8_t* mask);
+
 /* One vectorised ProjectDEnv.step (pyprojectd/projectd_env.py:157-212) for all envs: set actions, one tick,
  * observations, reward with the env's termination penalties, done flags, and automatic reset
  * (teleport by `PD_TELEPORT_*` mode + one zero-action tick, projectd_env.py:216-227) of finished envs.
@@ -144,6 +165,12 @@ int pd_raycast(pd_batch* b, int n, const float* rays, float* out);
  * returns the number of entries written (0 when disabled) */
 int pd_debug_read_clocks(pd_batch* b, long long* out, int cap);
 
+/* sizeof(PdCarParams) of this build (size the buffer of pd_get_params from it) */
+int pd_params_bytes(void);
+/* Make every later kernel / copy of this batch run on `stream` (a cudaStream_t of the batch's device; NULL = back to the batch's own
+ * non-blocking stream).  The previous stream is synchronised first.  With the caller's stream the batch's work is ordered with the
+ * caller's own kernels (e.g. the torch ops that produce the actions and consume the observations) without events. */
+int pd_set_stream(pd_batch* b, void* stream);
 int pd_sync(pd_batch* b);
 void* pd_stream(pd_batch* b);                        /* the cudaStream_t every kernel of this batch runs on */
 /* number of kernels launched by this batch since creation (bench.py's gpu_launches) */

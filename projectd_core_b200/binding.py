@@ -54,6 +54,12 @@ def load_library():
         "pd_car_state_bytes": (i, []),
         "pd_set_assists": (i, [vp, i, i, i]),
         "pd_set_tune": (i, [vp, cp, f]),
+        "pd_set_raw_tune": (i, [vp, cp, f]),
+        "pd_set_env_config": (i, [vp, vp]),
+        "pd_get_env_config": (i, [vp, vp]),
+        "pd_env_reset_counters": (i, [vp, vp]),
+        "pd_params_bytes": (i, []),
+        "pd_set_stream": (i, [vp, vp]),
         "pd_set_scoring_var": (i, [vp, cp, f]),
         "pd_get_scoring_var": (f, [vp, cp]),
         "pd_set_controls": (i, [vp, vp, vp, i, i]),
@@ -109,6 +115,15 @@ def _ptr(a):
     return a
 
 
+class EnvConfig(ctypes.Structure):
+    """PdEnvConfig of include/pd_batch.h: the ProjectDEnv knobs the kernels apply (projectd_env.py:27-53)."""
+    _fields_ = [("min_gas", ctypes.c_float), ("max_gas", ctypes.c_float),
+                ("terminate_hit_penalty", ctypes.c_float), ("terminate_off_track_penalty", ctypes.c_float), ("terminate_stuck_penalty", ctypes.c_float),
+                ("terminate_low_reward", ctypes.c_float), ("stuck_timeout", ctypes.c_float),
+                ("terminate_on_hit", ctypes.c_int32), ("terminate_off_track", ctypes.c_int32), ("terminate_when_stuck", ctypes.c_int32),
+                ("smooth_controls", ctypes.c_int32), ("clutch", ctypes.c_float), ("requested_gear", ctypes.c_int32)]
+
+
 class Batch:
     """N reference simulators with one car each, advanced together on one GPU.
 
@@ -143,6 +158,7 @@ class Batch:
 
     # -- lifetime -------------------------------------------------------------------------------------
     def close(self):
+        self._obs_tensor = None          # the DLPack alias must not outlive the buffer it points at
         if getattr(self, "h", None):
             self.L.pd_destroy(self.h)
             self.h = None
@@ -164,6 +180,32 @@ class Batch:
 
     def set_tune(self, name, value):
         self._ck(self.L.pd_set_tune(self.h, name.encode(), float(value)))
+
+    def set_raw_tune(self, name, value):
+        self._ck(self.L.pd_set_raw_tune(self.h, name.encode(), float(value)))
+
+    def env_config(self):
+        c = EnvConfig()
+        self._ck(self.L.pd_get_env_config(self.h, ctypes.byref(c)))
+        return c
+
+    def set_env_config(self, **kw):
+        """Update fields of the batch's PdEnvConfig (names as in ProjectDEnv: min_gas, terminate_hit_penalty, ...)."""
+        c = self.env_config()
+        for k, v in kw.items():
+            if not hasattr(c, k):
+                raise TypeError("unknown env config field %r" % k)
+            setattr(c, k, v)
+        self._ck(self.L.pd_set_env_config(self.h, ctypes.byref(c)))
+        return c
+
+    def env_reset_counters(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._ck(self.L.pd_env_reset_counters(self.h, _ptr(m)))
+
+    def set_stream(self, stream_ptr):
+        """Run this batch's kernels on the given cudaStream_t (int / None = the batch's own stream)."""
+        self._ck(self.L.pd_set_stream(self.h, ctypes.c_void_p(stream_ptr) if stream_ptr else None))
 
     def set_scoring_var(self, name, value):
         self._ck(self.L.pd_set_scoring_var(self.h, name.encode(), float(value)))
@@ -310,9 +352,7 @@ class Batch:
         self._ck(self.L.pd_restore(self.h, buf.ctypes.data))
 
     def params_bytes(self):
-        import struct  # noqa: F401
-        n = 16384
-        buf = np.zeros(n, dtype=np.uint8)
+        buf = np.zeros(self.L.pd_params_bytes(), dtype=np.uint8)
         self._ck(self.L.pd_get_params(self.h, buf.ctypes.data))
         return buf
 

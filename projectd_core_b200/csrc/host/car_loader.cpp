@@ -575,6 +575,21 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
     addD("FINAL_RATIO", 1.0, &P.drivetrain.finalRatio);
     addF("ARB_FRONT", 1.0, &P.arbK[0]); addF("ARB_REAR", 1.0, &P.arbK[1]);
     addF("ENGINE_LIMITER", 0.01, &P.engine.limiterMultiplier);
+    for (int i = 0; i < P.drivetrain.nGears && i < PD_MAX_GEARS; ++i) { static char nm[PD_MAX_GEARS][32]; snprintf(nm[i], sizeof(nm[i]), "INTERNAL_GEAR_%d", i); addD(nm[i], 1.0, &P.drivetrain.gears[i]); }
+    {   /* front struts: the per-wheel variables of SetupManager.cpp:62-83 */
+        static const char* kSide[2] = {"LF", "RF"}; static const double kSign[2] = {-1, 1};
+        static char nm[2][11][40];
+        for (int w = 0; w < 2; ++w) {
+            PdStrut& S = P.strut[w]; int q = 0;
+            auto reg = [&](const char* base, double mult, float* ptr) { snprintf(nm[w][q], sizeof(nm[w][q]), "%s_%s", base, kSide[w]); addF(nm[w][q], mult, ptr); ++q; };
+            reg("DAMP_FAST_BUMP", 1.0, &S.damper.bumpFast); reg("DAMP_BUMP", 1.0, &S.damper.bumpSlow);
+            reg("DAMP_FAST_REBOUND", 1.0, &S.damper.reboundFast); reg("DAMP_REBOUND", 1.0, &S.damper.reboundSlow);
+            reg("BUMP_STOP_RATE", 1000.0, &S.bumpStopRate); reg("SPRING_RATE", 1000.0, &S.k); reg("PROGRESSIVE_SPRING_RATE", 1000.0, &S.progressiveK);
+            reg("ROD_LENGTH", 0.0001, &S.rodLength); reg("CAMBER", 0.0017453292 * kSign[w], &S.staticCamber);
+            reg("TOE_OUT", 0.00001, &S.toeOutLinear); reg("PACKER_RANGE", 0.001, &S.packerRange);
+        }
+    }
+    for (int i = 0; i < P.nWings && i < PD_MAX_WINGS; ++i) { static char nm[PD_MAX_WINGS][16]; snprintf(nm[i], sizeof(nm[i]), "WING_%d", i); addF(nm[i], 1.0, &P.wing[i].angle); }
     /* PRESSURE_xx tune status.pressureStatic (per-env state): handled by the batch through pressureStaticDefault */
     addF("PRESSURE_LF", 1.0, &P.tyre[0].pressureStaticDefault); addF("PRESSURE_RF", 1.0, &P.tyre[1].pressureStaticDefault);
     addF("PRESSURE_LR", 1.0, &P.tyre[2].pressureStaticDefault); addF("PRESSURE_RR", 1.0, &P.tyre[3].pressureStaticDefault);
@@ -614,7 +629,30 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
 static inline float trunc_f(float x) { return (float)(int)x; }
 
 /* SetupVar::setTune = getSpinner + clamp + setValue (SetupManager.cpp:283-399) */
+/* variables the reference registers (SetupManager.cpp:18-135) that point at state this build keeps per AXLE, not per wheel, or
+ * at components the demo-car kernels do not have (AWD differentials, turbos): setting them must fail loudly, not silently */
+static bool known_but_unsupported(const std::string& name) {
+    static const char* kPrefix[] = {"FRONT_DIFF_", "REAR_DIFF_", "CENTER_DIFF_", "AWD_FRONT_TORQUE_DISTRIBUTION", "TURBO_", nullptr};
+    for (int i = 0; kPrefix[i]; ++i) if (name.compare(0, strlen(kPrefix[i]), kPrefix[i]) == 0) return true;
+    static const char* kWheel[] = {"DAMP_FAST_BUMP_", "DAMP_BUMP_", "DAMP_FAST_REBOUND_", "DAMP_REBOUND_", "BUMP_STOP_RATE_", "SPRING_RATE_", "PROGRESSIVE_SPRING_RATE_",
+                                   "ROD_LENGTH_", "CAMBER_", "TOE_OUT_", "PACKER_RANGE_", nullptr};
+    for (int i = 0; kWheel[i]; ++i) {
+        const size_t n = strlen(kWheel[i]);
+        if (name.size() == n + 2 && name.compare(0, n, kWheel[i]) == 0 && (name.compare(n, 2, "LR") == 0 || name.compare(n, 2, "RR") == 0)) return true;
+    }
+    return false;
+}
+/* SetupVar::setRaw: the value as is, no spinner clamp / multiplier (SetupManager.cpp:276-281) */
+void CarModel::setRawTune(const std::string& name, float v) {
+    for (auto& var : setupVars) {
+        if (var.name != name) continue;
+        if (var.fvalue) *var.fvalue = v; else if (var.dvalue) *var.dvalue = v;
+        return;
+    }
+    if (known_but_unsupported(name)) throw Error("setup variable '" + name + "' exists in the reference but is not supported by this build (per-wheel rear-axle / AWD / turbo tune)");
+}
 void CarModel::setTune(const std::string& name, float v) {
+    if (known_but_unsupported(name)) throw Error("setup variable '" + name + "' exists in the reference but is not supported by this build (per-wheel rear-axle / AWD / turbo tune)");
     for (auto& var : setupVars) {
         if (var.name != name) continue;
         float smin = 0, smax = 0;

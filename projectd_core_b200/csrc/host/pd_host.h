@@ -61,7 +61,8 @@ struct CarModel {
     PdCarParams P;
     std::vector<SetupVar> setupVars;
     std::string dataPath;
-    void setTune(const std::string& name, float value);     /* SetupManager::setTune */
+    void setTune(const std::string& name, float value);     /* SetupManager::setTune; throws for reference variables this build does not support */
+    void setRawTune(const std::string& name, float value);  /* SetupManager::setRawTune */
     void setScoringVar(const std::string& name, float value);
     float getScoringVar(const std::string& name) const;
 };

@@ -45,6 +45,7 @@ struct EnvIO {
     int32_t* pending;            /* [n] 1 = finished at the previous step (null: no in-kernel reset) */
     uint32_t* episodeCtr; uint64_t seed, idOffset; int teleportMode;
     const int32_t* collIn;       /* [n] k_collide's answer for this tick's start pose (0 / 1; -1 = test inside the tick); null: test inside the tick */
+    PdEnvConfig cfg;             /* ProjectDEnv's knobs (gas range, penalties, termination switches, clutch / gear overrides) */
     long long* clk;              /* profiling aid (PD_DEBUG_CLOCKS=1): SM cycles each warp spent in the tick, [blocks * 2]; null otherwise */
 };
 
@@ -62,7 +63,7 @@ template <class SVX> __device__ __noinline__ void env_reset_in_kernel(const PdCa
     else if (io.teleportMode == PD_TELEPORT_RANDOM) { u = pd_uniform(io.seed, io.idOffset + (uint64_t)e, io.episodeCtr[e]); io.episodeCtr[e]++; }
     car_teleport_to_point(P, T, sv, point_id_at_distance(T, u), time);
     sv.i(PD_OFF_CAR + PD_CAR_o_nanFlag, 0);
-    env_apply_action(sv, 0.0f, 0.0f);
+    env_apply_action(sv, 0.0f, 0.0f, io.cfg);
 }
 
 template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv, int e, bool on, const EnvIO& io, unsigned warpMask, bool resetNow = false) {
@@ -79,9 +80,9 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
         io.reward[e] = 0.0f; io.done[e] = 0; io.envReturn[e] = 0; io.envLen[e] = 0; io.pending[e] = 0;
     } else if (on) {
         float r; int d;
-        env_reward_done(sv, io.timeAfter, r, d);
+        env_reward_done(sv, io.timeAfter, io.cfg, r, d);
         const float ret = io.envReturn[e] + r; const int len = io.envLen[e] + 1;
-        if (ret < -200.0f) d |= PD_DONE_LOWREWARD;
+        if (ret < io.cfg.terminate_low_reward) d |= PD_DONE_LOWREWARD;
         io.reward[e] = r; io.done[e] = d;
         if (d) {
             s[0] = 1; s[1] = ret; s[2] = len;
@@ -114,7 +115,9 @@ __global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __
     SVTile sv = sv_tiled(state, (size_t)(e < n ? e : 0));
     /* solver scratch: the rows part (JA | JB | Y, 209 words) in local memory, the D | dg part (77 words, re-read by
        every phase of the factorisation) in shared memory, lane-interleaved: 19.7 KB per block keeps 8 blocks per SM */
-#if PD_SERIAL_SMEM_SCRATCH
+#if PD_SOLVER2
+    float* pd_rows = nullptr;      /* register-resident solver (pd_solver2.h): no scratch */
+#elif PD_SERIAL_SMEM_SCRATCH
     __shared__ float pd_scrD[PD_GSCR_D_WORDS * PD_BLOCK];
     float pd_rows[PD_GSCR_ROWS_WORDS];
 #else
@@ -124,8 +127,10 @@ __global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __
     const int collPre = (on && io.collIn) ? io.collIn[e] : -1;
     if (on) {
         if (resetNow) env_reset_in_kernel(P, T, sv, e, io, time);
-        else if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]);
-#if PD_SERIAL_SMEM_SCRATCH
+        else if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1], io.cfg);
+#if PD_SOLVER2
+        car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows, collPre);
+#elif PD_SERIAL_SMEM_SCRATCH
         car_tick<1, PD_BLOCK>(P, T, sv, dt, time, pd_rows, pd_scrD + threadIdx.x, collPre);
 #else
         car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows + PD_GSCR_ROWS_WORDS, collPre);
@@ -177,7 +182,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #define PD_QUAD_LOCAL_SCRATCH 0   /* solver scratch of the quad kernel: 0 = shared memory, 1 = local memory, 2 = JA | JB local, Y | D | dg shared */
 #endif
 /* shared memory of one block of the quad kernel with CPW cars per warp: 2*CPW records | mbarrier | scratch of 8*CPW lanes */
-#define PD_QUAD_SMEM_BYTES_(CPW) (2 * (CPW) * PD_STATE_STRIDE * 4 + 16 + (PD_QUAD_LOCAL_SCRATCH == 1 ? 0 : PD_QUAD_LOCAL_SCRATCH == 2 ? 8 * (CPW) * PD_GSCR_D_WORDS * 4 : 8 * (CPW) * PD_GSCR_WORDS * 4))
+#define PD_QUAD_SMEM_BYTES_(CPW) (2 * (CPW) * PD_STATE_STRIDE * 4 + 16 + ((PD_SOLVER2 || PD_QUAD_LOCAL_SCRATCH == 1) ? 0 : PD_QUAD_LOCAL_SCRATCH == 2 ? 8 * (CPW) * PD_GSCR_D_WORDS * 4 : 8 * (CPW) * PD_GSCR_WORDS * 4))
 
 /* the tick, four lanes per car, array-of-records state staged through shared memory:
  * block = 64 threads = 2 warps, CPW cars per warp (8: every lane busy, throughput; 4 or 2: half / quarter-filled warps
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(const __grid_const
     if (on) {
         if (ex.lane == 0) rec[PD_OFF_TYRE(0) + PD_TYRE_o_tyrePad] = 0u;      /* the collision warp's mailbox (a pad word of the record) starts empty */
         if (resetNow) { if (ex.lane == 0 && ex.half == 0) env_reset_in_kernel(P, T, sv, e, io, time); ex.sync(); }
-        else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1]); ex.sync(); }   /* four identical writes */
+        else if (io.act) { env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1], io.cfg); ex.sync(); }   /* four identical writes */
     }
     /* A third warp, when launched (blockDim 96: full ticks without k_collide's answer), is the block's COLLISION WARP: it
      * takes the start poses of the block's cars (after a reset's teleport, before anything moves) into registers and tests the
@@ -325,7 +330,7 @@ __global__ void k_broadcast(uint32_t* state, int layout, size_t nAlloc, const ui
  * NaN guard (auto-reset inside pd_env_step, projectd_env.py:216-227). */
 __global__ void __launch_bounds__(PD_BLOCK) k_teleport(const PdCarParams* __restrict__ P, TrackDev T, uint32_t* state, int layout, int n, const int32_t* __restrict__ mask,
                                                        int mode, const float* __restrict__ distNorm, uint64_t seed, uint64_t idOffset, uint32_t* __restrict__ episodeCtr,
-                                                       double time, int zeroAction, int32_t* __restrict__ pending) {
+                                                       double time, int zeroAction, int32_t* __restrict__ pending, PdEnvConfig cfg) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (mask && !mask[e]) return;
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(PD_BLOCK) k_teleport(const PdCarParams* __rest
     else if (mode == PD_TELEPORT_NEAREST) u = sv.f(PD_OFF_CAR + PD_CAR_o_trackLocation);
     else if (mode == PD_TELEPORT_RANDOM) { u = pd_uniform(seed, idOffset + (uint64_t)e, episodeCtr[e]); episodeCtr[e]++; }
     car_teleport_to_point(*P, T, sv, point_id_at_distance(T, u), time);
-    if (zeroAction) { sv.i(PD_OFF_CAR + PD_CAR_o_nanFlag, 0); env_apply_action(sv, 0.0f, 0.0f); }
+    if (zeroAction) { sv.i(PD_OFF_CAR + PD_CAR_o_nanFlag, 0); env_apply_action(sv, 0.0f, 0.0f, cfg); }
 }
 
 __global__ void k_set_controls(uint32_t* state, int layout, int n, const float* __restrict__ ctl, const int8_t* __restrict__ gears, int smooth) {
@@ -352,10 +357,15 @@ __global__ void k_set_controls(uint32_t* state, int layout, int n, const float* 
     sv.i(o + PD_CAR_o_smoothSteer, smooth);
 }
 
-__global__ void k_set_actions(uint32_t* state, int layout, int n, const float* __restrict__ act) {
+__global__ void k_set_actions(uint32_t* state, int layout, int n, const float* __restrict__ act, PdEnvConfig cfg) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    env_apply_action(sv_env(layout, state, (size_t)e), act[e * 2 + 0], act[e * 2 + 1]);
+    env_apply_action(sv_env(layout, state, (size_t)e), act[e * 2 + 0], act[e * 2 + 1], cfg);
+}
+__global__ void k_zero_counters(int n, const int32_t* __restrict__ mask, float* envReturn, int32_t* envLen) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || (mask && !mask[e])) return;
+    envReturn[e] = 0.0f; envLen[e] = 0;
 }
 
 __global__ void k_observe(const uint32_t* state, int layout, int n, float* __restrict__ obs) {
@@ -426,7 +436,8 @@ static_assert(sizeof(PdCarStateOut) == 664, "CarState is 664 bytes");
 
 struct pd_batch {
     int n = 0, device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, ownStream = nullptr;
+    PdEnvConfig envCfg{0.1f, 1.0f, 50.0f, 50.0f, 50.0f, -200.0f, 5.0f, 1, 1, 1, 1, 0.0f, -1};   /* projectd_env.py:27-53 */
     pdh::CarModel car; pdh::TrackModel track;
     PdCarParams* dP = nullptr; bool paramsDirty = true;
     TrackDev dev{};
@@ -455,6 +466,8 @@ struct pd_batch {
 
 static std::string g_createError;
 
+/* every ABI entry that touches the device makes the batch's device current first (the caller's current device may have changed) */
+#define ENTER(b) do { if (cudaSetDevice((b)->device) != cudaSuccess) { (b)->err = "cudaSetDevice failed"; return PD_ERR_CUDA; } } while (0)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { b->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PD_ERR_CUDA; } } while (0)
 
 template <class T> static int dalloc(pd_batch* b, T** p, size_t count) {
@@ -490,7 +503,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_E2E_ZEROCOPY")) b->zeroCopy = atoi(q) != 0;
     if (const char* q = getenv("PD_COLL_WARP")) b->collWarp = atoi(q) != 0;
     if (const char* q = getenv("PD_SERIAL_SMEM_PAD")) { b->serialSmemPad = atoi(q); cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); }
-    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->ownStream = b->stream;
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
     CK(cudaFuncSetAttribute(k_tick_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
     CK(cudaFuncSetAttribute(k_tick_quad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(2)));
@@ -581,7 +594,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
 }
 
 static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO& io_in) {
-    EnvIO io = io_in; io.clk = mask ? nullptr : b->dClk;
+    EnvIO io = io_in; io.clk = mask ? nullptr : b->dClk; io.cfg = b->envCfg;
     bool collWarp = false;
     if (!mask) {
         /* collision detection (odd physics frames): the quad kernel brings its own collision warp per block; the thread-per-car
@@ -635,9 +648,10 @@ int pd_create_synthetic(const char* base_path, const char* car_model, int target
 
 void pd_destroy(pd_batch* b) {
     if (!b) return;
+    cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (void* p : b->allocs) cudaFree(p);
-    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->ownStream) cudaStreamDestroy(b->ownStream);
     delete b;
 }
 const char* pd_last_error(const pd_batch* b) { return b ? b->err.c_str() : g_createError.c_str(); }
@@ -652,14 +666,43 @@ int pd_set_assists(pd_batch* b, int ac, int as, int ab) {
     A.acUseAutoOnStart = ac != 0; A.acUseAutoOnChange = ac != 0; A.asIsActive = as != 0; A.blipIsActive = ab != 0;
     b->paramsDirty = true; return PD_OK;
 }
-int pd_set_tune(pd_batch* b, const char* name, float value) {
+static int tune_common(pd_batch* b, const char* name, float value, bool raw) {
     if (!b || !name) return PD_ERR_ARG;
-    b->car.setTune(name, value); b->paramsDirty = true;
+    ENTER(b);
+    try { if (raw) b->car.setRawTune(name, value); else b->car.setTune(name, value); } catch (const std::exception& ex) { b->err = ex.what(); return PD_ERR_UNSUPPORTED; }
+    b->paramsDirty = true;
     static const char* kP[4] = {"PRESSURE_LF", "PRESSURE_RF", "PRESSURE_LR", "PRESSURE_RR"};
     for (int w = 0; w < 4; ++w) if (!strcmp(name, kP[w])) {   /* the tune writes Tyre::status.pressureStatic of every car */
         k_set_pressure<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, w, b->car.P.tyre[w].pressureStaticDefault); b->launches++;
         CK(cudaGetLastError());
     }
+    return PD_OK;
+}
+int pd_set_tune(pd_batch* b, const char* name, float value) { return tune_common(b, name, value, false); }
+int pd_set_raw_tune(pd_batch* b, const char* name, float value) { return tune_common(b, name, value, true); }
+int pd_set_env_config(pd_batch* b, const PdEnvConfig* cfg) {
+    if (!b || !cfg) return PD_ERR_ARG;
+    if (!(cfg->max_gas >= cfg->min_gas) || cfg->stuck_timeout < 0.0f) { b->err = "pd_set_env_config: bad gas range / stuck timeout"; return PD_ERR_ARG; }
+    b->envCfg = *cfg; return PD_OK;
+}
+int pd_get_env_config(const pd_batch* b, PdEnvConfig* out) { if (!b || !out) return PD_ERR_ARG; *out = b->envCfg; return PD_OK; }
+int pd_env_reset_counters(pd_batch* b, const uint8_t* mask) {
+    if (!b) return PD_ERR_ARG;
+    ENTER(b);
+    const int32_t* dm = nullptr;
+    if (mask) {
+        std::vector<int32_t> m(b->n); for (int i = 0; i < b->n; ++i) m[i] = mask[i] ? 1 : 0;
+        CK(cudaMemcpyAsync(b->dMask, m.data(), (size_t)b->n * 4, cudaMemcpyHostToDevice, b->stream)); CK(cudaStreamSynchronize(b->stream)); dm = b->dMask;
+    }
+    k_zero_counters<<<grid(b->n, 256), 256, 0, b->stream>>>(b->n, dm, b->dEnvReturn, b->dEnvLen); b->launches++;
+    CK(cudaGetLastError()); return PD_OK;
+}
+int pd_params_bytes(void) { return (int)sizeof(PdCarParams); }
+int pd_set_stream(pd_batch* b, void* stream) {
+    if (!b) return PD_ERR_ARG;
+    ENTER(b);
+    CK(cudaStreamSynchronize(b->stream));
+    b->stream = stream ? (cudaStream_t)stream : b->ownStream;
     return PD_OK;
 }
 int pd_set_scoring_var(pd_batch* b, const char* name, float value) {
@@ -683,7 +726,7 @@ int pd_set_actions(pd_batch* b, const float* actions, int on_device) {
     if (!b || !actions) return PD_ERR_ARG;
     const float* a = actions;
     if (!on_device) { CK(cudaMemcpyAsync(b->dAct, actions, (size_t)b->n * 2 * 4, cudaMemcpyHostToDevice, b->stream)); a = b->dAct; }
-    k_set_actions<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, a); b->launches++;
+    k_set_actions<<<grid(b->n, 256), 256, 0, b->stream>>>(b->dState, b->layout, b->n, a, b->envCfg); b->launches++;
     CK(cudaGetLastError()); return PD_OK;
 }
 
@@ -709,7 +752,7 @@ static int teleport_common(pd_batch* b, const uint8_t* mask, int mode, const flo
     }
     const float* dd = nullptr;
     if (dist_norm) { CK(cudaMemcpyAsync(b->dDist, dist_norm, (size_t)b->n * 4, cudaMemcpyHostToDevice, b->stream)); dd = b->dDist; }
-    k_teleport<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, b->n, dm, mode, dd, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 0, b->dPending); b->launches++;
+    k_teleport<<<grid(b->n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, b->n, dm, mode, dd, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 0, b->dPending, b->envCfg); b->launches++;
     CK(cudaGetLastError()); return PD_OK;
 }
 int pd_teleport_spline(pd_batch* b, const uint8_t* mask, const float* dist_norm) {
@@ -776,7 +819,7 @@ int pd_env_step(pd_batch* b, const float* actions_dev, float dt, float* obs_dev,
     b->time += (double)dt; b->lastDt = dt;
     /* 2 + 3: auto-reset of finished envs: teleport (env.teleport_mode, projectd_env.py:39) with the reset's zero action,
        then one tick of those envs only, refreshing their observation */
-    k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, n, done, b->resetMode, nullptr, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 1, nullptr); b->launches++;
+    k_teleport<<<grid(n, PD_BLOCK), PD_BLOCK, 0, b->stream>>>(b->dP, b->dev, b->dState, b->layout, n, done, b->resetMode, nullptr, b->seed, b->idOffset, b->dEpisodeCtr, b->time, 1, nullptr, b->envCfg); b->launches++;
     EnvIO io2{}; io2.obs = io.obs;
     launch_tick(b, dt, done, io2);
     CK(cudaGetLastError()); return PD_OK;

@@ -199,6 +199,28 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
+#if PD_SOLVER2
+    /* one group per lane, register-resident (pd_solver2.h): lanes 0 / 1 the strut groups, lanes 2 / 3 the single-body groups
+       (axle, tank) through one shared code path */
+    float GR[PD_GSYS_WORDS];
+    StrutSys GS; GS.R = GR; SingleSys G1; G1.R = GR;
+    if (front) strut_factor(P, P.strut[lane], C, W, S, steerA1, steerA2, dA, dB, dC, hinv, X.dballErp, X.dballCfm, GS, S21, b6);
+    else {
+        float cfm[6];
+        if (lane == 2) single_rows_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G1, cfm); else single_rows_tank(P, S, C, hinv, G1, cfm);
+        single_factor(G1, cfm, dA, dC, hinv, S21, b6);
+    }
+    PD_PHASE(X, 9);
+    PD_PHASE(X, 10);
+    for (int k = 0; k < 21; ++k) S21[k] = ex.sum(S21[k]);
+    for (int k = 0; k < 6; ++k) b6[k] = ex.sum(b6[k]);
+    schur_add_chassis(S21, C);
+    float z[6];
+    solve6(S21, b6, z);
+    PD_PHASE(X, 11);
+    float cfA[6], cfB[6];
+    if (front) strut_backsolve(GS, z, cfA, cfB); else single_backsolve(G1, z, cfA);
+#else
     GScr<STRIDE, STRIDE_D> G; G.bind(scratch, scratchD);
     if (front) build_strut(P, P.strut[lane], C, W, S, steerA1, steerA2, hinv, X.dballErp, X.dballCfm, G);
     else if (lane == 2) build_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G);
@@ -217,6 +239,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     PD_PHASE(X, 11);
     float cfA[6], cfB[6];
     backsolve_group(G, z, cfA, cfB);
+#endif
     apply_update(A, dA, cfA, h);
     if (front) apply_update(S, dB, cfB, h);
     chassis_update(C, dC, z, h);

@@ -4,8 +4,9 @@
  * Car::postStep (:685-713), and the teleport / reset path (Car.cpp:1240-1358).
  */
 #pragma once
-#include "pd_solver.h"
+#include "pd_solver2.h"
 #include "pd_collide.h"
+#include "../../include/pd_batch.h"
 
 namespace pd {
 
@@ -385,7 +386,11 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
     /* collPre: the answer of k_collide for this tick's start pose (0 / 1), or -1 = not computed: test here */
     if (c.physFrame & 1) { if (collPre >= 0 ? (collPre != 0) : car_collide(P, T, C, 0, 1)) c.collisionFlag = 1; }
     c.physFrame++;
+#if PD_SOLVER2
+    world_step2(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt);
+#else
     world_step<STRIDE, STRIDE_D>(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, scratch, scratchD);
+#endif
 
     /* ---------------- Car::postStep ---------------- */
     { /* updateTrackLocator (Car.cpp:717-771) */
@@ -476,24 +481,25 @@ template <class SVX> PD_HD void car_observe(const SVX& sv, float* obs /* 24, str
     for (int i = 0; i < 7; ++i) obs[17 + i] = sv.f(PD_OFF_PROBES + i);
 }
 
-/* the env's action mapping (pyprojectd/projectd_env.py:158-170): steer = a0, gas = linscale(a1, -1..1 -> 0.1..1) */
-template <class SVX> PD_HD void env_apply_action(const SVX& sv, float a0, float a1) {
+/* the env's action mapping (pyprojectd/projectd_env.py:158-170): steer = a0, gas = linscale(a1, -1..1 -> min_gas..max_gas),
+ * clutch = 1.0 when auto_clutch is off, requestedGearIndex = 2 when auto_shift is off, `smooth` = smooth_controls */
+template <class SVX> PD_HD void env_apply_action(const SVX& sv, float a0, float a1, const PdEnvConfig& cfg) {
     const int o = PD_OFF_CAR;
-    sv.f(o + PD_CAR_o_ctlSteer, a0); sv.f(o + PD_CAR_o_ctlClutch, 0.0f); sv.f(o + PD_CAR_o_ctlBrake, 0.0f); sv.f(o + PD_CAR_o_ctlHandBrake, 0.0f);
-    sv.f(o + PD_CAR_o_ctlGas, linscalef(a1, -1.0f, 1.0f, 0.1f, 1.0f));
-    sv.i(o + PD_CAR_o_ctlRequestedGear, -1); sv.i(o + PD_CAR_o_ctlGearUp, 0); sv.i(o + PD_CAR_o_ctlGearDn, 0); sv.i(o + PD_CAR_o_smoothSteer, 1);
+    sv.f(o + PD_CAR_o_ctlSteer, a0); sv.f(o + PD_CAR_o_ctlClutch, cfg.clutch); sv.f(o + PD_CAR_o_ctlBrake, 0.0f); sv.f(o + PD_CAR_o_ctlHandBrake, 0.0f);
+    sv.f(o + PD_CAR_o_ctlGas, linscalef(a1, -1.0f, 1.0f, cfg.min_gas, cfg.max_gas));
+    sv.i(o + PD_CAR_o_ctlRequestedGear, cfg.requested_gear); sv.i(o + PD_CAR_o_ctlGearUp, 0); sv.i(o + PD_CAR_o_ctlGearDn, 0); sv.i(o + PD_CAR_o_smoothSteer, cfg.smooth_controls ? 1 : 0);
 }
 
 /* ProjectDEnv.step tail (projectd_env.py:178-212): reward with the termination penalties and the PD_DONE_* causes
  * that depend on the car alone (the low-reward cut needs the env's running return and is applied by the caller) */
-template <class SVX> PD_HD void env_reward_done(const SVX& sv, double timeAfter, float& reward, int& done) {
+template <class SVX> PD_HD void env_reward_done(const SVX& sv, double timeAfter, const PdEnvConfig& cfg, float& reward, int& done) {
     const int o = PD_OFF_CAR;
     float r = sv.f(o + PD_CAR_o_stepReward);
     int d = 0;
-    if (sv.i(o + PD_CAR_o_collisionFlag)) { r -= 50.0f; d |= 1 /* PD_DONE_COLLISION */; }
-    if (sv.i(o + PD_CAR_o_outOfTrackFlag)) { r -= 50.0f; d |= 2 /* PD_DONE_OFFTRACK */; }
-    /* the env compares lastTrackPointTimestamp + stuck_timeout (5 s) against the state's timestamp */
-    if (sv.f(o + PD_CAR_o_lastTrackPointTimestamp) + 5.0f < (float)timeAfter) { r -= 50.0f; d |= 4 /* PD_DONE_STUCK */; }
+    if (cfg.terminate_on_hit && sv.i(o + PD_CAR_o_collisionFlag)) { r -= cfg.terminate_hit_penalty; d |= 1 /* PD_DONE_COLLISION */; }
+    if (cfg.terminate_off_track && sv.i(o + PD_CAR_o_outOfTrackFlag)) { r -= cfg.terminate_off_track_penalty; d |= 2 /* PD_DONE_OFFTRACK */; }
+    /* the env compares lastTrackPointTimestamp + stuck_timeout against the state's timestamp */
+    if (cfg.terminate_when_stuck && sv.f(o + PD_CAR_o_lastTrackPointTimestamp) + cfg.stuck_timeout < (float)timeAfter) { r -= cfg.terminate_stuck_penalty; d |= 4 /* PD_DONE_STUCK */; }
     if (sv.i(o + PD_CAR_o_nanFlag)) d |= 16 /* PD_DONE_NAN */;
     reward = r; done = d;
 }

@@ -45,6 +45,10 @@ class BatchedProjectDEnv:
     range_lookAhead = math.pi
     range_probe = 50
 
+    terminate_on_hit = True
+    terminate_off_track = True
+    terminate_when_stuck = True
+
     terminate_hit_penalty = 50.0
     terminate_off_track_penalty = 50.0
     terminate_stuck_penalty = 50.0
@@ -88,8 +92,19 @@ class BatchedProjectDEnv:
             b.set_tune(name, value)
         for name, value in self.scoring_vars.items():                           # :131-132
             b.set_scoring_var(name, value)
+        # the env-level knobs live in the kernels (PdEnvConfig): gas range, penalties, termination switches, the clutch / gear
+        # overrides of projectd_env.py:162-166 -- every attribute above is live, none is a dead knob
+        b.set_env_config(min_gas=self.min_gas, max_gas=self.max_gas, terminate_hit_penalty=self.terminate_hit_penalty,
+                         terminate_off_track_penalty=self.terminate_off_track_penalty, terminate_stuck_penalty=self.terminate_stuck_penalty,
+                         terminate_low_reward=self.terminate_low_reward, stuck_timeout=self.stuck_timeout,
+                         terminate_on_hit=int(self.terminate_on_hit), terminate_off_track=int(self.terminate_off_track),
+                         terminate_when_stuck=int(self.terminate_when_stuck), smooth_controls=int(self.smooth_controls),
+                         clutch=0.0 if self.auto_clutch else 1.0, requested_gear=-1 if self.auto_shift else 2)
         import torch
         self.device = torch.device("cuda", device)
+        # stream ordering: the batch launches on its own non-blocking stream; every step makes that stream wait for the caller's
+        # current stream (the producer of `actions`) and the caller's stream wait for the tick (before obs / reward / done are read)
+        self._stream = torch.cuda.ExternalStream(b.stream(), device=self.device)
         self.obs = b.obs_tensor()                                               # [N,24] view of the library's buffer
         self.reward = torch.zeros(self.num_envs, device=self.device)
         self.done = torch.zeros(self.num_envs, device=self.device, dtype=torch.int32)
@@ -111,9 +126,14 @@ class BatchedProjectDEnv:
     # ---- gym-style API, vectorised ----
     def reset(self):
         """Teleports every env by `teleport_mode` and advances one zero-action tick (projectd_env.py:218-230)."""
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(cur)
         self.batch.teleport_mode(self.teleport_mode)
         self.batch.env_step(self._zero_action, self.sim_dt, None, self.reward, self.done)
+        self.batch.env_reset_counters()            # total_reward = 0 after the reset's own step (projectd_env.py:224-227)
         self.batch.env_stats(reset=True)
+        cur.wait_stream(self._stream)
         self.step_id = 0
         return self.obs
 
@@ -126,7 +146,11 @@ class BatchedProjectDEnv:
         actions = actions.to(torch.float32).contiguous()
         if actions.shape != (self.num_envs, 2):
             raise ValueError("actions must be [num_envs, 2]")
+        cur = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(cur)              # the tick kernel reads `actions` only after the caller's stream has produced them
+        actions.record_stream(self._stream)        # ... and their memory is not recycled while the kernel may still read it
         self.batch.env_step(actions, self.sim_dt, None, self.reward, self.done)
+        cur.wait_stream(self._stream)              # obs / reward / done are complete before anything on the caller's stream reads them
         self.step_id += 1
         return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), {}
 
@@ -139,4 +163,5 @@ class BatchedProjectDEnv:
         return pdist.summarize(s)
 
     def close(self):
+        self.obs = None                            # alias of the batch's observation buffer: gone with the batch
         self.batch.close()

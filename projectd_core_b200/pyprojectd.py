@@ -287,7 +287,12 @@ def setCarTune(simId, carId, name, value):
         b.set_tune(str(name), float(value))
 
 
-setCarRawTune = setCarTune
+@_guard
+def setCarRawTune(simId, carId, name, value):
+    """PyProjectD.cpp:337-344 -> SetupManager::setRawTune: the raw value, no spinner clamp / multiplier."""
+    b = _batch(simId, carId)
+    if b is not None:
+        b.set_raw_tune(str(name), float(value))
 
 
 @_guard

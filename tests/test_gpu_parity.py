@@ -457,3 +457,158 @@ def test_ragged_batch_sizes_match_full_batch(oracle, n):
     assert np.array_equal(full.snapshot()[:, :n], part.snapshot())
     assert torch.equal(rf[:n].cpu(), rp.cpu()) and torch.equal(df[:n].cpu(), dp.cpu())
     assert torch.equal(full.obs_tensor()[:n].cpu(), part.obs_tensor().cpu())
+
+
+@pytest.mark.parametrize("kernel", ["k_tick_quad<4>", "k_tick"])
+def test_car_state_and_obs_identical_state(oracle, lay, kernel, monkeypatch):
+    """SURVEY.md A12 from IDENTICAL states: one tick from the oracle's state, then the 664-byte CarState (Car/CarState.h:11-56,
+    Car::updateCarState Car.cpp:802-865) and the env's 24 observations (projectd_env.py:237-275) against the reference's own
+    getCarState: ints exact, floats within 1e-4 of the field's scale (vectors against their norm; matrices: rotation entries
+    against 1, the translation row against the tick's displacement scale), every field compared -- hubMatrix, tyreNdSlip and
+    localAngularVelocity included."""
+    _select_kernel(monkeypatch, kernel)
+    from projectd_core_b200.pyprojectd import CAR_STATE_DTYPE
+    n = 32
+    b = _batch(oracle, n)
+    assert b.tick_kernel_instance() == kernel
+    starts = drive_start_states(oracle, lay, "driftplayground", 64)
+    pick = [i for i in range(64) if (i // 16) % 4 in (1, 3)][:n]          # the rolling starts (10-16 m/s)
+    refs = [oracle.RefSim() for _ in range(n)]
+    for r, i in zip(refs, pick):
+        r.set_state(starts[i][0]); r.set_time(0.0)
+    recs = [r.state() for r in refs]
+    obs = b.obs_tensor()
+    worst = 0.0
+    for t in range(120):
+        for k, r in enumerate(refs):
+            r.set_controls(**drive_controls(t, pick[k], lay, recs[k]))
+        b.restore(np.stack([r.state() for r in refs], axis=1)); b.set_time(refs[0].time())
+        b.step(DT, 1); b.observe(); b.sync()
+        o = obs.cpu().numpy()
+        for k, r in enumerate(refs):
+            r.step(); recs[k] = r.state()
+            if t % 4 != k % 4:
+                continue
+            want = np.zeros(664, np.uint8); r.L.pdref_get_car_state(r.h, want.ctypes.data)
+            want = np.frombuffer(want, dtype=CAR_STATE_DTYPE)[0]
+            got = np.frombuffer(b.car_state_bytes(k), dtype=CAR_STATE_DTYPE)[0]
+            for name in CAR_STATE_DTYPE.names:
+                if name in ("carId", "simId"):
+                    continue
+                g, w = got[name], want[name]
+                if name == "controls":
+                    for cn in g.dtype.names:
+                        if cn == "isShifterSupported":
+                            continue
+                        assert abs(float(g[cn]) - float(w[cn])) <= 1e-6, (name, cn, g[cn], w[cn])
+                    continue
+                if np.issubdtype(g.dtype, np.integer):
+                    assert np.array_equal(g, w), (t, k, name, g, w)
+                    continue
+                g = np.asarray(g, np.float64); w = np.asarray(w, np.float64)
+                if name in ("bodyMatrix", "hubMatrix"):
+                    gm = g.reshape(-1, 16); wm = w.reshape(-1, 16)
+                    err = max(np.abs(gm[:, :12] - wm[:, :12]).max(), np.abs(gm[:, 12:15] - wm[:, 12:15]).max() / 10.0)   # positions: 1e-3 m in world coordinates of ~100 m (fp32 ulp 8e-6)
+                elif name in ("bodyPos", "tyreContacts"):
+                    err = np.abs(g - w).max() / 10.0
+                elif g.ndim and name not in ("probes", "lookAhead", "tyreLoad", "tyreAngularSpeed", "tyreSlipRatio", "tyreNdSlip"):
+                    err = np.abs(g - w).max() / max(float(np.linalg.norm(w)), 1.0)
+                else:
+                    err = (np.abs(g - w) / np.maximum(np.abs(w), 1.0)).max()
+                worst = max(worst, float(err))
+                assert err <= 3e-4, (t, k, name, g, w)
+            ref_obs = np.concatenate([want["localVelocity"], want["localAngularVelocity"], want["tyreNdSlip"], [want["bodyVsTrack"], want["velocityVsTrack"]],
+                                      want["lookAhead"], want["probes"][:7]]).astype(np.float64)
+            sc = np.maximum(np.abs(ref_obs), 1.0)
+            sc[0:3] = max(np.linalg.norm(ref_obs[0:3]), 1.0); sc[3:6] = max(np.linalg.norm(ref_obs[3:6]), 1.0)
+            assert (np.abs(o[k] - ref_obs) / sc).max() <= 3e-4, (t, k, o[k], ref_obs)
+    assert worst > 0.0
+
+
+def test_env_config_knobs_are_live(oracle):
+    """PdEnvConfig (ProjectDEnv's class attributes, projectd_env.py:27-53) reaches the kernels: gas range, termination switches,
+    penalties, the clutch / gear overrides of auto_clutch / auto_shift off."""
+    import torch
+    from projectd_core_b200.env import BatchedProjectDEnv
+    n = 64
+    act = torch.zeros((n, 2), device="cuda"); act[:, 1] = -1.0          # a1 = -1 -> gas = min_gas
+    lay = oracle.Layout(); o_gas = lay.fields["car.ctlGas"][0]; o_cl = lay.fields["car.ctlClutch"][0]; o_rg = lay.fields["car.ctlRequestedGear"][0]
+    env = BatchedProjectDEnv(oracle.BASE_PATH, num_envs=n, device=0, min_gas=0.25, max_gas=0.75, auto_clutch=False, auto_shift=False,
+                             terminate_when_stuck=True, stuck_timeout=0.05, terminate_stuck_penalty=7.0, autoreset_mode=1)
+    env.reset()
+    env.step(act); torch.cuda.synchronize()
+    st = env.batch.snapshot()
+    assert np.allclose(st[o_gas].view(np.float32), 0.25) and np.allclose(st[o_cl].view(np.float32), 1.0) and (st[o_rg].view(np.int32) == 2).all()
+    act[:, 1] = 1.0
+    env.step(act); torch.cuda.synchronize()
+    assert np.allclose(env.batch.snapshot()[o_gas].view(np.float32), 0.75)
+    # stuck after 0.05 s without reaching a new track point: every env terminates with the configured penalty
+    done_any = torch.zeros(n, dtype=torch.bool, device="cuda"); pen = None
+    act[:, 1] = -1.0
+    for t in range(40):
+        obs, rew, term, trunc, _ = env.step(act)
+        if pen is None and bool(term.any()):
+            pen = float(rew[term].max())
+        done_any |= term
+    assert bool(done_any.all()) and pen is not None and pen <= -7.0 + 0.2
+    env.close()
+    # with the switch off nothing terminates for being stuck
+    env = BatchedProjectDEnv(oracle.BASE_PATH, num_envs=n, device=0, terminate_when_stuck=False, stuck_timeout=0.05)
+    env.reset()
+    act[:, 1] = -1.0
+    seen = False
+    for t in range(60):
+        obs, rew, term, trunc, _ = env.step(act)
+        seen |= bool(term.any())
+    assert not seen
+    env.close()
+
+
+def test_env_step_is_ordered_with_callers_stream(oracle):
+    """BatchedProjectDEnv.step on torch's default stream: actions produced just before the call and results consumed right after
+    it, with no synchronisation by the caller, must equal a fully synchronised run (stream ordering)."""
+    import torch
+    from projectd_core_b200.env import BatchedProjectDEnv
+    n = 512
+    outs = []
+    for sync in (False, True):
+        env = BatchedProjectDEnv(oracle.BASE_PATH, num_envs=n, device=0, seed=11, teleport_mode=2, autoreset_mode=1)
+        env.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(4)
+        tot = torch.zeros(n, device="cuda"); nd = torch.zeros(n, device="cuda"); acc = torch.zeros((n, 24), device="cuda")
+        big = torch.empty((2048, 2048), device="cuda")
+        for t in range(200):
+            big.normal_(generator=g)                                        # work in flight on the caller's stream
+            a = torch.tanh((big[:n, :2] * 0.7)).contiguous()               # actions produced by that work, then dropped
+            if sync:
+                torch.cuda.synchronize()
+            obs, rew, term, trunc, _ = env.step(a)
+            del a
+            if sync:
+                torch.cuda.synchronize()
+            tot += rew; nd += term; acc += obs
+        torch.cuda.synchronize()
+        outs.append((tot.cpu().numpy(), nd.cpu().numpy(), acc.cpu().numpy(), env.batch.snapshot()))
+        env.close()
+    for x, y in zip(outs[0], outs[1]):
+        assert np.array_equal(x, y)
+
+
+def test_tunes_raw_and_unsupported(oracle):
+    """setCarTune clamps / scales through the spinner, setCarRawTune writes the raw value (SetupManager.cpp:276-288,394-399);
+    per-wheel front suspension tunes are live; reference variables this build cannot honour fail loudly."""
+    from projectd_core_b200 import Batch, PdError
+    b = Batch(oracle.BASE_PATH, n_envs=2, device=0)
+    r = oracle.RefSim(env_setup=False)
+    for name, val in (("FRONT_BIAS", 55.0), ("SPRING_RATE_LF", 30.0), ("DAMP_BUMP_RF", 2500.0), ("CAMBER_LF", -20.0), ("TOE_OUT_RF", 12.0),
+                      ("ROD_LENGTH_LF", 50.0), ("ARB_FRONT", 12000.0), ("INTERNAL_GEAR_2", 3.2), ("WING_1", 3.0)):
+        b.set_tune(name, val); r.L.pdref_set_tune(r.h, name.encode(), val)
+    ref = r.params_bytes(); mine = b.params_bytes()[: len(ref)]
+    assert np.array_equal(mine, ref), np.nonzero(mine != ref)[0][:20]
+    b3 = Batch(oracle.BASE_PATH, n_envs=2, device=0); b3.set_raw_tune("FRONT_BIAS", 0.61)
+    b4 = Batch(oracle.BASE_PATH, n_envs=2, device=0); b4.set_tune("FRONT_BIAS", 61.0)
+    assert np.array_equal(b3.params_bytes(), b4.params_bytes())
+    for name in ("SPRING_RATE_LR", "DAMP_REBOUND_RR", "TURBO_0", "CENTER_DIFF_POWER"):
+        with pytest.raises(PdError):
+            b.set_tune(name, 1.0)
+    b.set_tune("NO_SUCH_VARIABLE", 1.0)        # unknown to the reference as well: ignored there, ignored here
