@@ -84,7 +84,8 @@ struct TrackModel {
     std::vector<PdFatPoint> fat;
     std::vector<float> fatDist;       /* Track::fatPointDistances */
     std::vector<float> splineXYZ, splineDist;
-    PdBoundGrid grid;
+    PdBoundGrid grid;                            /* 8 m cells: spline points (nearest-point search) */
+    PdBoundGrid segGrid;                         /* 2 m cells (coarser on very large tracks): boundary segments (probes) */
     PdBoundGrid colGrid;                         /* x-z grid of triangle lists for vertical rays */
     std::vector<int32_t> colStart, colItems;     /* CSR per cell: triangle indices (leaf order of `tris`) */
     std::vector<int32_t> segStart, segItems;   /* CSR per cell: boundary segments, item = id * 2 + side (0 left, 1 right) */

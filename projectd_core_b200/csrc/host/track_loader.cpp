@@ -261,34 +261,53 @@ static V3h bspline(float u, V3h P0, V3h P1, V3h P2, V3h P3) {
 static void build_bound_grid(TrackModel& out) {
     const int n = (int)out.fat.size();
     PdBoundGrid& G = out.grid; memset(&G, 0, sizeof(G));
+    PdBoundGrid& S = out.segGrid; memset(&S, 0, sizeof(S));
     out.segStart.assign(1, 0); out.segItems.clear(); out.ptStart.assign(1, 0); out.ptItems.clear();
     if (n == 0) return;
     float x0 = 3.4e38f, x1 = -3.4e38f, z0 = 3.4e38f, z1 = -3.4e38f;
     for (const PdFatPoint& f : out.fat)
         for (const float* p : {f.best, f.left, f.right}) { x0 = std::min(x0, p[0]); x1 = std::max(x1, p[0]); z0 = std::min(z0, p[2]); z1 = std::max(z1, p[2]); }
-    G.cell = 8.0f; G.invCell = 1.0f / G.cell;
-    G.ox = x0 - 2.0f * G.cell; G.oz = z0 - 2.0f * G.cell;
-    G.nx = (int)ceilf((x1 - G.ox) * G.invCell) + 3; G.nz = (int)ceilf((z1 - G.oz) * G.invCell) + 3;
-    const size_t nc = (size_t)G.nx * G.nz;
-    std::vector<std::vector<int32_t>> seg(nc), pts(nc);
-    auto cx = [&](float x) { return std::max(0, std::min(G.nx - 1, (int)floorf((x - G.ox) * G.invCell))); };
-    auto cz = [&](float z) { return std::max(0, std::min(G.nz - 1, (int)floorf((z - G.oz) * G.invCell))); };
+    auto shape = [&](PdBoundGrid& g, float cell) {
+        g.cell = cell; g.invCell = 1.0f / cell;
+        const float m = std::max(2.0f * cell, 16.0f);          /* indexed margin around the track: cars further out fall back to the exhaustive scan */
+        g.ox = x0 - m; g.oz = z0 - m;
+        g.nx = (int)ceilf((x1 + m - g.ox) * g.invCell) + 1; g.nz = (int)ceilf((z1 + m - g.oz) * g.invCell) + 1;
+    };
+    /* point grid and segment grid: 8 m cells.  (Measured on B200: 2 m segment cells -- an empty corridor between the boundary
+       polylines, 4x fewer segment tests -- made the probes SLOWER, 47 k instead of 36 k cycles per tick: a probe walk is a chain
+       of dependent L2 loads, one per cell, and the finer grid quadruples the chain.)  Cells grow for very large tracks so that
+       the index stays within a few million entries. */
+    shape(G, 8.0f);
+    { float cell = 8.0f; shape(S, cell); while ((size_t)S.nx * S.nz > (size_t)4 << 20) { cell *= 1.5f; shape(S, cell); } }
+    const size_t nc = (size_t)G.nx * G.nz, ncs = (size_t)S.nx * S.nz;
+    std::vector<std::vector<int32_t>> seg(ncs), pts(nc);
+    auto cx = [&](const PdBoundGrid& g, float x) { return std::max(0, std::min(g.nx - 1, (int)floorf((x - g.ox) * g.invCell))); };
+    auto cz = [&](const PdBoundGrid& g, float z) { return std::max(0, std::min(g.nz - 1, (int)floorf((z - g.oz) * g.invCell))); };
     const float pad = 0.05f;   /* segments are listed in every cell their padded box touches */
     for (int id = 0; id < n; ++id) {
         const PdFatPoint& f = out.fat[id]; const PdFatPoint& g = out.fat[id + 1 < n ? id + 1 : 0];
         for (int side = 0; side < 2; ++side) {
             const float* a = side ? f.right : f.left; const float* b = side ? g.right : g.left;
-            const int ix0 = cx(std::min(a[0], b[0]) - pad), ix1 = cx(std::max(a[0], b[0]) + pad), iz0 = cz(std::min(a[2], b[2]) - pad), iz1 = cz(std::max(a[2], b[2]) + pad);
-            for (int iz = iz0; iz <= iz1; ++iz) for (int ix = ix0; ix <= ix1; ++ix) seg[(size_t)iz * G.nx + ix].push_back(id * 2 + side);
+            const int ix0 = cx(S, std::min(a[0], b[0]) - pad), ix1 = cx(S, std::max(a[0], b[0]) + pad), iz0 = cz(S, std::min(a[2], b[2]) - pad), iz1 = cz(S, std::max(a[2], b[2]) + pad);
+            for (int iz = iz0; iz <= iz1; ++iz) for (int ix = ix0; ix <= ix1; ++ix) {
+                /* long segments (closing segment of an open track, coarse splines): keep only the cells the padded segment really crosses */
+                if ((ix1 - ix0) + (iz1 - iz0) > 2) {
+                    const float bx0 = S.ox + ix * S.cell - pad, bx1 = bx0 + S.cell + 2 * pad, bz0 = S.oz + iz * S.cell - pad, bz1 = bz0 + S.cell + 2 * pad;
+                    const float dx = b[0] - a[0], dz = b[2] - a[2];
+                    float t0 = 0.0f, t1 = 1.0f; bool hit = true;
+                    auto clip = [&](float p, float q) { if (p == 0.0f) { if (q < 0.0f) hit = false; return; } const float r = q / p; if (p < 0.0f) { if (r > t1) hit = false; else if (r > t0) t0 = r; } else { if (r < t0) hit = false; else if (r < t1) t1 = r; } };
+                    clip(-dx, a[0] - bx0); if (hit) clip(dx, bx1 - a[0]); if (hit) clip(-dz, a[2] - bz0); if (hit) clip(dz, bz1 - a[2]);
+                    if (!hit) continue;
+                }
+                seg[(size_t)iz * S.nx + ix].push_back(id * 2 + side);
+            }
         }
-        pts[(size_t)cz(f.best[2]) * G.nx + cx(f.best[0])].push_back(id);
+        pts[(size_t)cz(G, f.best[2]) * G.nx + cx(G, f.best[0])].push_back(id);
     }
-    out.segStart.resize(nc + 1); out.ptStart.resize(nc + 1);
-    for (size_t c = 0; c < nc; ++c) {
-        out.segStart[c] = (int32_t)out.segItems.size(); out.segItems.insert(out.segItems.end(), seg[c].begin(), seg[c].end());
-        out.ptStart[c] = (int32_t)out.ptItems.size(); out.ptItems.insert(out.ptItems.end(), pts[c].begin(), pts[c].end());
-    }
-    out.segStart[nc] = (int32_t)out.segItems.size(); out.ptStart[nc] = (int32_t)out.ptItems.size();
+    out.segStart.resize(ncs + 1); out.ptStart.resize(nc + 1);
+    for (size_t c = 0; c < ncs; ++c) { out.segStart[c] = (int32_t)out.segItems.size(); out.segItems.insert(out.segItems.end(), seg[c].begin(), seg[c].end()); }
+    for (size_t c = 0; c < nc; ++c) { out.ptStart[c] = (int32_t)out.ptItems.size(); out.ptItems.insert(out.ptItems.end(), pts[c].begin(), pts[c].end()); }
+    out.segStart[ncs] = (int32_t)out.segItems.size(); out.ptStart[nc] = (int32_t)out.ptItems.size();
     /* the same lists with the data inlined, so that a cell visit is index -> records (no id -> point indirection) */
     out.segRec.resize(out.segItems.size() * 8); out.ptRec.resize(out.ptItems.size() * 4);
     for (size_t k = 0; k < out.segItems.size(); ++k) {

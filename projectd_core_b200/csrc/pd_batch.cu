@@ -528,7 +528,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = upload(b, &b->dev.ptItems, b->track.ptItems))) return rc;
     if ((rc = upload(b, &b->dev.segRec, b->track.segRec))) return rc;
     if ((rc = upload(b, &b->dev.ptRec, b->track.ptRec))) return rc;
-    b->dev.grid = b->track.grid;
+    b->dev.grid = b->track.grid; b->dev.segGrid = b->track.segGrid;
     if ((rc = upload(b, &b->dev.colStart, b->track.colStart))) return rc;
     if ((rc = upload(b, &b->dev.colItems, b->track.colItems))) return rc;
     b->dev.colGrid = b->track.colGrid;

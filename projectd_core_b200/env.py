@@ -148,9 +148,12 @@ class BatchedProjectDEnv:
             raise ValueError("actions must be [num_envs, 2]")
         cur = torch.cuda.current_stream(self.device)
         self._stream.wait_stream(cur)              # the tick kernel reads `actions` only after the caller's stream has produced them
-        actions.record_stream(self._stream)        # ... and their memory is not recycled while the kernel may still read it
         self.batch.env_step(actions, self.sim_dt, None, self.reward, self.done)
-        cur.wait_stream(self._stream)              # obs / reward / done are complete before anything on the caller's stream reads them
+        # obs / reward / done are complete before anything on the caller's stream reads them -- and the memory of `actions` is
+        # not recycled under the kernel either: the caching allocator hands a freed block to later work of the caller's stream
+        # only, all of which is ordered after this wait (no record_stream: it would make the allocator touch the batch's stream
+        # after close() has destroyed it)
+        cur.wait_stream(self._stream)
         self.step_id += 1
         return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), {}
 

@@ -61,7 +61,7 @@ class CarControls:
 
     def __init__(self):
         self.steer = 0.0; self.clutch = 0.0; self.brake = 0.0; self.handBrake = 0.0; self.gas = 0.0
-        self.isShifterSupported = 0; self.requestedGearIndex = -1; self.gearUp = 0; self.gearDn = 0
+        self.isShifterSupported = 1; self.requestedGearIndex = -1; self.gearUp = 0; self.gearDn = 0
 
 
 _CTRL_DTYPE = np.dtype([("steer", "<f4"), ("clutch", "<f4"), ("brake", "<f4"), ("handBrake", "<f4"), ("gas", "<f4"),
@@ -316,7 +316,7 @@ def setCarControls(simId, carId, smooth, controls):
         return
     ctl, gears = b.controls_host()
     ctl[carId] = (controls.steer, controls.clutch, controls.brake, controls.handBrake, controls.gas)
-    gears[carId] = (controls.requestedGearIndex if controls.isShifterSupported else -1, controls.gearUp, controls.gearDn)
+    gears[carId] = (controls.requestedGearIndex, controls.gearUp, controls.gearDn)     # the struct is copied as is (PyProjectD.cpp:297-305)
     b.set_controls(ctl, gears, smooth=bool(smooth))
 
 
