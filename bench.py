@@ -79,30 +79,34 @@ class ClockSampler(threading.Thread):
 # reference arm / cpu_baseline: the oracle (reference Car/Sim/Core sources + restated ODE) on host cores
 # ----------------------------------------------------------------------------------------------------------------
 def _ref_worker(args):
-    """One process = one host core: `sims` reference simulators stepped `ticks` ticks with the bench workload."""
+    """One process = one host core: `sims` reference simulators stepped `ticks` ticks with the bench workload.  The whole loop
+    (controls, Simulator::step, the env's reset rule) runs inside oracle/_ref/libpdref.so (pdref_bench_loop): the figure carries
+    no Python / ctypes time."""
     wid, sims, ticks, seed, preroll = args
-    import numpy as np
+    import ctypes
     pdref = _oracle()
-    rng = np.random.default_rng(seed + wid)
+    L = pdref.lib()
+    L.pdref_bench_loop.restype = ctypes.c_double
+    L.pdref_bench_loop.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_void_p]
     S = [pdref.RefSim() for _ in range(sims)]
     for k, s in enumerate(S):
-        s.teleport_spline(float(rng.uniform(0, 1)))
-    lay = pdref.Layout()
-    o_col = lay.fields["car.collisionFlag"][0]; o_off = lay.fields["car.outOfTrackFlag"][0]
-    t0 = time.perf_counter()
-    for t in range(-preroll, ticks):
-        if t == 0:
-            t0 = time.perf_counter()      # the pre-roll (cars leave the grid, reach speed, episodes start ending) is not timed
-        if t % TICKS_PER_STEP == 0 or t == -preroll:
-            acts = rng.uniform(-1, 1, (sims, 2))
-        for k, s in enumerate(S):
-            s.set_controls(steer=float(acts[k, 0]), gas=float(0.1 + 0.9 * (acts[k, 1] + 1) * 0.5))
-            s.step(DT)
-            if True:        # env-style auto reset, checked every tick as ProjectDEnv.step does (the state read is ~2 us of harness work)
-                rec = s.state()
-                if rec[o_col] or rec[o_off]:
-                    s.teleport_spline(float(rng.uniform(0, 1)))
-    return sims * ticks, time.perf_counter() - t0
+        s.set_collision_response(False)          # the env terminates on hit (terminate_on_hit): detection only, as our arm runs it
+        s.teleport_spline(((wid * 7919 + k * 104729) % 1000) / 1000.0)
+    arr = (ctypes.c_void_p * sims)(*[s.h for s in S])
+    resets = ctypes.c_longlong(0)
+    secs = L.pdref_bench_loop(arr, sims, ticks, preroll, seed + wid, ctypes.byref(resets))
+    return sims * ticks, secs
+
+
+def _physical_cores():
+    try:
+        sibs = set()
+        for c in os.sched_getaffinity(0):
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c) as f:
+                sibs.add(f.read().strip())
+        return len(sibs) or None
+    except Exception:
+        return None
 
 
 def _oracle():
@@ -133,7 +137,8 @@ def reference_arm(args):
     if not pdref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
         return
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)      # one process per usable hardware thread
+    physical = _physical_cores()
     sims_per_core = 2
     # warm-up + K steps, each step = 33 ticks of (cores * sims_per_core) reference simulators
     times = []
@@ -151,7 +156,8 @@ def reference_arm(args):
         "config": {"workload": "configs[1] sample: demo car on driftplayground, random controls resampled every 33 ticks, env auto-reset; "
                                "each step = %d ticks of %d reference simulators (one process per host core) after 666 untimed pre-roll ticks" % (TICKS_PER_STEP * 4, cores * sims_per_core)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": "%d sims x %d ticks per step (after 666 untimed pre-roll ticks), %d steps; reference Car/Sim/Core sources (g++ -O2) + restated ODE 0.16.3 back-end" % (cores * sims_per_core, TICKS_PER_STEP * 4, args.steps)},
+                         "physical_cores": physical,
+                         "sample": "%d sims x %d ticks per step (after 666 untimed pre-roll ticks), %d steps, one process per hardware thread (%d threads on %s physical cores), the whole loop inside the C++ library (no Python per tick); reference Car/Sim/Core sources (g++ -O2) + restated ODE 0.16.3 back-end, collision detection without response (the env terminates on hit)" % (cores * sims_per_core, TICKS_PER_STEP * 4, args.steps, cores, physical)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

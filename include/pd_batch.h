@@ -56,6 +56,11 @@ typedef struct pd_batch pd_batch;
 int pd_create(const char* base_path, const char* track_name, const char* car_model, int n_envs, int device, pd_batch** out);
 /* same, but the track is a generated closed circuit of about `target_tris` triangles (BASELINE.json config 4) */
 int pd_create_synthetic(const char* base_path, const char* car_model, int target_tris, float length_m, int n_envs, int device, pd_batch** out);
+/* Track::computeFatPoints + computeSideLocation (Sim/Track.cpp:366-467) as batch ray casting on the GPU: regenerates the content of
+ * spline.cache (15 floats per spline point: best, left, right, center, forwardDir) from spline.bin + surfaces.bin, ignoring any
+ * cache on disk.  Returns the number of points (out holds min(points, cap_points)) or a negative PD_ERR_*.  pd_create does the same
+ * by itself when a track has no usable spline.cache. */
+int pd_compute_fat_points(const char* base_path, const char* track_name, int device, float* out, int cap_points);
 /* destroySimulator (PyProjectD.cpp:139-149) */
 void pd_destroy(pd_batch* b);
 const char* pd_last_error(const pd_batch* b);      /* b may be NULL: error of the last failed pd_create */
@@ -165,6 +170,13 @@ int pd_raycast(pd_batch* b, int n, const float* rays, float* out);
  * returns the number of entries written (0 when disabled) */
 int pd_debug_read_clocks(pd_batch* b, long long* out, int cap);
 
+/* Collision RESPONSE (PhysicsEngineODE::onCollision, Physics/ODE/PhysicsEngineODE.cpp:284-341): when on (default),
+ * a car that touches the static world on an odd physics frame gets contact joints (normal row + friction pyramid) that act in that
+ * frame's solve and the next one, as the reference's two-frame contact groups do.  Off: contacts only raise collisionFlag (what an
+ * env that terminates on hit needs; the detection then runs inside the tick kernel and costs no extra launch). */
+int pd_set_collision_response(pd_batch* b, int on);
+/* live contact joints of one env: out[i][8] = position, normal, depth, kind (0 floor box vs TRACK, 1 hull vs WALL); returns their number */
+int pd_get_contacts(pd_batch* b, int env, float* out, int max_contacts);
 /* sizeof(PdCarParams) of this build (size the buffer of pd_get_params from it) */
 int pd_params_bytes(void);
 /* Make every later kernel / copy of this batch run on `stream` (a cudaStream_t of the batch's device; NULL = back to the batch's own

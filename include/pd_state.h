@@ -111,7 +111,10 @@
     /* TyreThermalPatch::inputT starts at ambient (TyreThermalModel.cpp:40) and is zero after the first step */ \
     X(I, thermalPrimed) \
     /* PhysicsEngineODE::currentFrame (PhysicsEngineODE.cpp:228-244): collisions against the static meshes are tested on odd frames */ \
-    X(I, physFrame)
+    X(I, physFrame) \
+    /* Car::damageZoneLevel[5] (Car.h:204; front, rear, left, right, max): raised by wall contacts in Car::onCollisionCallback \
+     * (Car.cpp:980-999), read by ScoringSystem::validateDrift (a tick with new damage invalidates the drift); + 1 pad word */ \
+    X(F, damageZone0) X(F, damageZone1) X(F, damageZone2) X(F, damageZone3) X(F, damageZone4) X(I, carPad)
 
 /* ---------------------------------------------------------------------------------------- */
 #define PD__W_F 1
@@ -135,7 +138,7 @@
 #define PD_STATE_WORDS   (PD_OFF_CAR + PD_CAR_WORDS)
 /* record stride of the array-of-records device layout: a multiple of 4 words (16-byte bulk copies) whose value
  * mod 32 (= 20) spreads the same word of 8 consecutive records over 8 different shared-memory bank groups */
-#define PD_STATE_STRIDE  628
+#define PD_STATE_STRIDE  636
 
 /* per-field word offsets inside their group: PD_BODY_o_px, PD_TYRE_o_load, PD_CAR_o_fuel ... */
 #define PD__ENUM_B(kind, name) PD_BODY_o_##name, PD_BODY_e_##name = PD_BODY_o_##name + PD__W_##kind - 1,

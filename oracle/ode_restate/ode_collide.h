@@ -15,7 +15,21 @@
  * least depth wins, edge axes only when 1.5 x depth is still smaller (the bias of _cldTestEdge); the reported normal
  * points from the triangle towards the box.  mesh vs mesh: a pair of triangles touches when an edge of either crosses
  * the other (the edge / triangle clipping both ODE trimesh-trimesh colliders are built on); coplanar overlap is not
- * detected.  Contact positions, depths and the contact-joint response are NOT restated.
+ * detected.
+ *
+ * Contact GENERATION (positions, normals, depths) -- ODE's own generators (the clipping of collision_trimesh_box.cpp, the
+ * OPCODE pair walk of collision_trimesh_trimesh.cpp) cannot be restated from memory to the vertex, and nothing in the reference
+ * pins them, so the contacts handed to the contact joints are defined HERE, as simply as the physics allows, and the product
+ * follows this definition (pd_contacts.h):
+ *   floor box vs an accepted TRACK triangle (SAT overlap + body-local normal filter): every box corner that lies BELOW the
+ *     triangle's plane and whose projection falls inside the triangle is a contact (position = the corner, normal = the
+ *     triangle's unit normal towards the box, depth = distance below the plane); per corner the deepest triangle wins; when no
+ *     corner qualifies for any accepted triangle, one contact at the box's support corner along the SAT normal of the deepest
+ *     accepted triangle with the SAT depth.
+ *   hull mesh vs a WALL triangle that at least one hull triangle crosses: every hull VERTEX that lies behind the wall triangle's
+ *     plane (seen from the chassis origin) by less than 0.5 m and projects inside it is a contact (position = the vertex, normal
+ *     = the wall's unit normal towards the chassis, depth = distance behind the plane); per vertex the deepest triangle wins.
+ *   At most 4 floor and 4 wall contacts per car, the deepest first (ties: lower corner / vertex index).
  */
 #pragma once
 #include <cmath>
@@ -45,7 +59,7 @@ static inline bool sat_axis(CV3 L, const float p[3], float r, float bias, float&
 
 /* box: centre c, world axes A[3] (unit), half sizes h[3]; triangle v0 v1 v2.  Returns true when they overlap and
  * writes the contact normal (unit, pointing from the triangle towards the box). */
-static inline bool box_tri_contact(CV3 c, const CV3 A[3], const float h[3], CV3 v0, CV3 v1, CV3 v2, CV3& nOut) {
+static inline bool box_tri_contact(CV3 c, const CV3 A[3], const float h[3], CV3 v0, CV3 v1, CV3 v2, CV3& nOut, float* depthOut = nullptr) {
     const CV3 E[3] = {csub(v1, v0), csub(v2, v1), csub(v0, v2)};
     const CV3 P[3] = {csub(v0, c), csub(v1, c), csub(v2, c)};
     const CV3 N = ccross(E[0], csub(v2, v0));
@@ -70,7 +84,44 @@ static inline bool box_tri_contact(CV3 c, const CV3 A[3], const float h[3], CV3 
         if (!sat_axis(L, p, r, 1.5f, bestDepth, bestN)) return false;
     }
     nOut = bestN;
+    if (depthOut) *depthOut = bestDepth;
     return true;
+}
+
+/* is the projection of p onto the plane of (v0, v1, v2) along its normal inside the triangle?  (edge functions on the
+ * UNNORMALISED normal N = (v1 - v0) x (v2 - v0); boundary counts as inside) */
+static inline bool projects_inside(CV3 p, CV3 v0, CV3 v1, CV3 v2, CV3 N) {
+    const float d0 = cdot(ccross(csub(v1, v0), csub(p, v0)), N);
+    const float d1 = cdot(ccross(csub(v2, v1), csub(p, v1)), N);
+    const float d2 = cdot(ccross(csub(v0, v2), csub(p, v2)), N);
+    return d0 >= 0.0f && d1 >= 0.0f && d2 >= 0.0f;
+}
+
+struct ContactPoint { CV3 pos, normal; float depth; int kind; };     /* kind 0: floor box vs TRACK (mode 28700), 1: hull vs WALL (mode 28692) */
+
+/* candidate for slot `key` (box corner / hull vertex): deeper wins; ties by larger normal.y, then .x, then .z */
+static inline void contact_offer(ContactPoint* slot, bool* used, int key, CV3 pos, CV3 n, float depth, int kind) {
+    ContactPoint& c = slot[key];
+    bool take = !used[key];
+    if (!take) {
+        if (depth > c.depth) take = true;
+        else if (depth == c.depth) {
+            if (n.y > c.normal.y) take = true;
+            else if (n.y == c.normal.y && (n.x > c.normal.x || (n.x == c.normal.x && n.z > c.normal.z))) take = true;
+        }
+    }
+    if (take) { c.pos = pos; c.normal = n; c.depth = depth; c.kind = kind; used[key] = true; }
+}
+/* the `maxOut` deepest used slots, deepest first, ties by lower key */
+static inline int contact_select(const ContactPoint* slot, const bool* used, int nSlots, ContactPoint* out, int maxOut) {
+    int n = 0; bool taken[64] = {false};
+    for (int r = 0; r < maxOut; ++r) {
+        int best = -1;
+        for (int k = 0; k < nSlots; ++k) if (used[k] && !taken[k] && (best < 0 || slot[k].depth > slot[best].depth)) best = k;
+        if (best < 0) break;
+        taken[best] = true; out[n++] = slot[best];
+    }
+    return n;
 }
 
 /* segment p -> q against triangle (v0, e1, e2), both faces */

@@ -49,11 +49,24 @@ struct Joint {
     int rows() const { return type == J_FIXED ? 6 : type == J_BALL ? 3 : type == J_SLIDER ? 5 : 1; }
 };
 
+/* dxJointContact between a body and the static world (dJointAttach(j, body, 0)): geometry fixed at creation
+ * (ode/src/joints/contact.cpp getInfo2); surface parameters of PhysicsEngineODE::onCollision (PhysicsEngineODE.cpp:299-322) */
+struct ContactJoint {
+    Body* b0 = nullptr;
+    dReal pos[3], normal[3], depth;
+    dReal mu, bounce, soft_cfm, soft_erp;      /* soft_erp < 0: world ERP (mode without dContactSoftERP) */
+};
+
 struct World {
     dReal gravity[3] = {0, 0, 0};
     dReal erp = 0.2f, cfm = 1e-5f;
+    dReal contactMaxCorrectingVel = 3.0f, contactSurfaceLayer = 0.0f;     /* PhysicsEngineODE.cpp:26-27 */
     std::vector<Body*> bodies;
     std::vector<Joint*> joints;
+    std::vector<ContactJoint> contacts;          /* the joints of both contact groups that are alive in this step */
+    int pgsIterations = 50;
+    bool keepSystem = false;                     /* tests: keep A (before factoring) and rhs of the last step's bilateral block */
+    std::vector<dReal> lastA, lastRhs;
     /* diagnostics of the last step */
     int last_m = 0;
     std::vector<dReal> last_lambda;
@@ -221,7 +234,35 @@ inline void joint_set_dball_anchor1(Joint& j, const dReal* p) { body_pos_rel_poi
 inline void joint_set_dball_anchor2(Joint& j, const dReal* p) { body_pos_rel_point(*j.b1, p, j.anchor2); j.targetDistance = dball_current_distance(j); }
 
 /* ---------------- constraint rows ---------------- */
-struct Row { dReal J1[6], J2[6], c, cfm; int b0, b1; };
+struct Row { dReal J1[6], J2[6], c, cfm; int b0, b1; dReal lo, hi; int findex; };   /* lo / hi / findex: contact rows only (bilateral rows: unbounded) */
+
+/* contact.cpp getInfo2 for a contact whose second body is the static world: row 0 the normal (lo 0, soft ERP / CFM, bounce,
+ * push-out capped by ContactMaxCorrectingVel), rows 1-2 the friction directions of dPlaneSpace(normal) with dContactApprox1
+ * (bounds = +-mu x normal force, findex = row 0); returns 3 */
+inline int contact_get_rows(const World& w, const ContactJoint& cj, dReal fps, Row* r, int firstRow) {
+    const Body& b = *cj.b0;
+    for (int i = 0; i < 3; ++i) { memset(&r[i], 0, sizeof(Row)); r[i].b0 = b.index; r[i].b1 = b.index; r[i].cfm = w.cfm; r[i].findex = -1; }
+    dReal c1[3] = {cj.pos[0] - b.pos[0], cj.pos[1] - b.pos[1], cj.pos[2] - b.pos[2]};
+    const dReal* n = cj.normal;
+    for (int k = 0; k < 3; ++k) r[0].J1[k] = n[k];
+    cross3(r[0].J1 + 3, c1, n);
+    const dReal erp = cj.soft_erp >= 0 ? cj.soft_erp : w.erp;
+    const dReal k = fps * erp;
+    dReal depth = cj.depth - w.contactSurfaceLayer; if (depth < 0) depth = 0;
+    r[0].cfm = cj.soft_cfm;
+    dReal c = k * depth;
+    if (c > w.contactMaxCorrectingVel) c = w.contactMaxCorrectingVel;
+    {   /* bounce (bounce_vel = 0: the struct is zero-initialised by the reference) */
+        const dReal outgoing = dot3(r[0].J1, b.lvel) + dot3(r[0].J1 + 3, b.avel);
+        if (-outgoing > 0) { const dReal newc = -cj.bounce * outgoing; if (newc > c) c = newc; }
+    }
+    r[0].c = c; r[0].lo = 0; r[0].hi = 3.4e38f;
+    dReal t1[3], t2[3]; plane_space(n, t1, t2);
+    for (int k3 = 0; k3 < 3; ++k3) { r[1].J1[k3] = t1[k3]; r[2].J1[k3] = t2[k3]; }
+    cross3(r[1].J1 + 3, c1, t1); cross3(r[2].J1 + 3, c1, t2);
+    r[1].lo = -cj.mu; r[1].hi = cj.mu; r[1].findex = firstRow; r[2].lo = -cj.mu; r[2].hi = cj.mu; r[2].findex = firstRow;
+    return 3;
+}
 
 inline void set_fixed_orientation(const Joint& j, dReal fps, dReal erp, Row* r) { /* joint.cpp setFixedOrientation */
     for (int i = 0; i < 3; ++i) { r[i].J1[3 + i] = 1; r[i].J2[3 + i] = -1; }
@@ -368,9 +409,12 @@ inline void world_step(World& w, dReal h) {
         for (int k = 0; k < 3; ++k) b.facc[k] += b.mass * w.gravity[k];
     }
     /* rows */
-    int m = 0; for (Joint* j : w.joints) m += j->rows();
+    int mb = 0; for (Joint* j : w.joints) mb += j->rows();           /* bilateral (unbounded) rows first, as dSolveLCP orders them */
+    const int mc = 3 * (int)w.contacts.size();
+    const int m = mb + mc;
     std::vector<Row> rows(m);
-    { int o = 0; for (Joint* j : w.joints) o += joint_get_rows(w, *j, hinv, &rows[o]); }
+    { int o = 0; for (Joint* j : w.joints) { const int n = joint_get_rows(w, *j, hinv, &rows[o]); for (int i = 0; i < n; ++i) { rows[o + i].lo = -3.4e38f; rows[o + i].hi = 3.4e38f; rows[o + i].findex = -1; } o += n; }
+      for (const ContactJoint& cj : w.contacts) o += contact_get_rows(w, cj, hinv, &rows[o], o); }
     w.last_m = m;
     std::vector<dReal> lambda(m, 0.0f);
     if (m > 0) {
@@ -392,9 +436,9 @@ inline void world_step(World& w, dReal h) {
                 dReal s = 0;
                 const dReal* a0 = &JiM[i * 12]; const dReal* a1 = &JiM[i * 12 + 6];
                 if (ri.b0 == rj.b0) for (int k = 0; k < 6; ++k) s += a0[k] * rj.J1[k];
-                if (ri.b0 == rj.b1) for (int k = 0; k < 6; ++k) s += a0[k] * rj.J2[k];
-                if (ri.b1 == rj.b0) for (int k = 0; k < 6; ++k) s += a1[k] * rj.J1[k];
-                if (ri.b1 == rj.b1) for (int k = 0; k < 6; ++k) s += a1[k] * rj.J2[k];
+                if (ri.b0 == rj.b1 && rj.b1 != rj.b0) for (int k = 0; k < 6; ++k) s += a0[k] * rj.J2[k];
+                if (ri.b1 == rj.b0 && ri.b1 != ri.b0) for (int k = 0; k < 6; ++k) s += a1[k] * rj.J1[k];
+                if (ri.b1 == rj.b1 && ri.b1 != ri.b0 && rj.b1 != rj.b0) for (int k = 0; k < 6; ++k) s += a1[k] * rj.J2[k];
                 A[(size_t)i * m + j] = s;
             }
         for (int i = 0; i < m; ++i) A[(size_t)i * m + i] += rows[i].cfm * hinv;
@@ -410,13 +454,24 @@ inline void world_step(World& w, dReal h) {
         for (int i = 0; i < m; ++i) {
             const Row& r = rows[i]; dReal s = 0;
             for (int k = 0; k < 6; ++k) s += r.J1[k] * tmp1[r.b0 * 6 + k];
-            for (int k = 0; k < 6; ++k) s += r.J2[k] * tmp1[r.b1 * 6 + k];
+            if (r.b1 != r.b0) for (int k = 0; k < 6; ++k) s += r.J2[k] * tmp1[r.b1 * 6 + k];
             rhs[i] = r.c * hinv - s;
         }
         /* LDL^T factor + solve (fastldlt.c semantics: unit-lower L and diagonal D, row by row:
            solve L(0:i,0:i) u = A(i,0:i), then L_ij = u_j / D_j and D_i = A_ii - sum_j u_j L_ij) */
-        std::vector<dReal> d(m);
-        for (int i = 0; i < m; ++i) {
+        /* with contact rows: dSolveLCP factors the unbounded block first; the bounded rows then see the Schur complement
+           A_cc - A_cb A_bb^-1 A_bc.  ODE continues with Dantzig pivoting; here the small bounded system is solved by projected
+           Gauss-Seidel (a fixed number of sweeps in row order, friction bounds +-mu x the current normal force), see the header
+           of ode_collide.h: the contact path is this repository's own definition. */
+        if (w.keepSystem) { w.lastA.assign((size_t)mb * mb, 0.0f); for (int i = 0; i < mb; ++i) for (int j = 0; j <= i; ++j) { w.lastA[(size_t)i * mb + j] = A[(size_t)i * m + j]; w.lastA[(size_t)j * mb + i] = A[(size_t)i * m + j]; } w.lastRhs.assign(rhs.begin(), rhs.begin() + mb); }
+        std::vector<dReal> Acc, rc;
+        if (mc > 0) { Acc.assign((size_t)mc * mc, 0.0f); rc.assign(mc, 0.0f);
+            for (int i = 0; i < mc; ++i) { for (int j = 0; j <= i; ++j) { Acc[(size_t)i * mc + j] = A[(size_t)(mb + i) * m + mb + j]; Acc[(size_t)j * mc + i] = Acc[(size_t)i * mc + j]; } rc[i] = rhs[mb + i]; } }
+        std::vector<dReal> Acb;
+        if (mc > 0) { Acb.assign((size_t)mc * mb, 0.0f); for (int i = 0; i < mc; ++i) for (int j = 0; j < mb; ++j) Acb[(size_t)i * mb + j] = A[(size_t)(mb + i) * m + j]; }
+        const int mfull = m; (void)mfull;
+        std::vector<dReal> d(mb);
+        for (int i = 0; i < mb; ++i) {
             dReal* Ai = &A[(size_t)i * m];
             for (int j = 0; j < i; ++j) {
                 const dReal* Aj = &A[(size_t)j * m];
@@ -432,16 +487,46 @@ inline void world_step(World& w, dReal h) {
             }
             d[i] = dii;
         }
-        for (int i = 0; i < m; ++i) { dReal s = rhs[i]; for (int k = 0; k < i; ++k) s -= A[(size_t)i * m + k] * lambda[k]; lambda[i] = s; }
-        for (int i = 0; i < m; ++i) lambda[i] /= d[i];
-        for (int i = m - 1; i >= 0; --i) { dReal s = lambda[i]; for (int k = i + 1; k < m; ++k) s -= A[(size_t)k * m + i] * lambda[k]; lambda[i] = s; }
+        auto solve_b = [&](std::vector<dReal>& x) {          /* x <- A_bb^-1 x with the factor above */
+            for (int i = 0; i < mb; ++i) { dReal s = x[i]; for (int k = 0; k < i; ++k) s -= A[(size_t)i * m + k] * x[k]; x[i] = s; }
+            for (int i = 0; i < mb; ++i) x[i] /= d[i];
+            for (int i = mb - 1; i >= 0; --i) { dReal s = x[i]; for (int k = i + 1; k < mb; ++k) s -= A[(size_t)k * m + i] * x[k]; x[i] = s; }
+        };
+        std::vector<dReal> xb(rhs.begin(), rhs.begin() + mb);
+        solve_b(xb);                                         /* A_bb^-1 rhs_b */
+        if (mc > 0) {
+            /* Schur complement onto the contact rows */
+            std::vector<dReal> col(mb);
+            for (int j = 0; j < mc; ++j) {
+                for (int k = 0; k < mb; ++k) col[k] = Acb[(size_t)j * mb + k];     /* A_bc(:, j) = A_cb(j, :)^T */
+                solve_b(col);
+                for (int i = 0; i < mc; ++i) { dReal s = 0; for (int k = 0; k < mb; ++k) s += Acb[(size_t)i * mb + k] * col[k]; Acc[(size_t)i * mc + j] -= s; }
+            }
+            for (int i = 0; i < mc; ++i) { dReal s = 0; for (int k = 0; k < mb; ++k) s += Acb[(size_t)i * mb + k] * xb[k]; rc[i] -= s; }
+            std::vector<dReal> lc(mc, 0.0f);
+            for (int it = 0; it < w.pgsIterations; ++it)
+                for (int i = 0; i < mc; ++i) {
+                    const Row& r = rows[mb + i];
+                    dReal s = rc[i]; for (int k = 0; k < mc; ++k) s -= Acc[(size_t)i * mc + k] * lc[k];
+                    dReal v = lc[i] + s / Acc[(size_t)i * mc + i];
+                    dReal lo = r.lo, hi = r.hi;
+                    if (r.findex >= 0) { const dReal fn = lc[r.findex - mb]; hi = r.hi * fn; lo = -hi; }
+                    if (v < lo) v = lo; if (v > hi) v = hi;
+                    lc[i] = v;
+                }
+            /* lambda_b = A_bb^-1 (rhs_b - A_bc lambda_c) */
+            for (int k = 0; k < mb; ++k) { dReal s = rhs[k]; for (int i = 0; i < mc; ++i) s -= Acb[(size_t)i * mb + k] * lc[i]; xb[k] = s; }
+            solve_b(xb);
+            for (int i = 0; i < mc; ++i) lambda[mb + i] = lc[i];
+        }
+        for (int i = 0; i < mb; ++i) lambda[i] = xb[i];
     }
     w.last_lambda = lambda;
     /* cforce = J^T lambda ; velocity update ; position update */
     std::vector<dReal> cf(nb * 6, 0.0f);
     for (int i = 0; i < m; ++i) {
         const Row& r = rows[i];
-        for (int k = 0; k < 6; ++k) { cf[r.b0 * 6 + k] += r.J1[k] * lambda[i]; cf[r.b1 * 6 + k] += r.J2[k] * lambda[i]; }
+        for (int k = 0; k < 6; ++k) { cf[r.b0 * 6 + k] += r.J1[k] * lambda[i]; if (r.b1 != r.b0) cf[r.b1 * 6 + k] += r.J2[k] * lambda[i]; }
     }
     for (int i = 0; i < nb; ++i) {
         Body& b = *w.bodies[i];

@@ -296,6 +296,20 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
         for (int iz = iz0; iz <= iz1; ++iz) for (int ix = ix0; ix <= ix1; ++ix) for (uint32_t t : m.cells[(size_t)iz * m.gnx + ix]) cand.push_back(t);
         std::sort(cand.begin(), cand.end()); cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
     }
+    /* ---- contact generation (definition: header of ode_collide.h) + contact joints (PhysicsEngineODE.cpp:284-341) ---- */
+    bool responseEnabled = true;
+    std::vector<oder::ContactJoint> contactGroupDynamic;      /* created on odd frames, alive for that frame and the next one */
+    void addContacts(RigidBodyR* rb, const oder::ContactPoint* cp, int n, ICollisionObject* shape0, CollisionMeshR* other) {
+        for (int i = 0; i < n; ++i) {
+            oder::ContactJoint cj; cj.b0 = &rb->b;
+            cj.pos[0] = cp[i].pos.x; cj.pos[1] = cp[i].pos.y; cj.pos[2] = cp[i].pos.z;
+            cj.normal[0] = cp[i].normal.x; cj.normal[1] = cp[i].normal.y; cj.normal[2] = cp[i].normal.z; cj.depth = cp[i].depth;
+            if (cp[i].kind == 0) { cj.mu = 0.1f; cj.bounce = 0.0f; cj.soft_cfm = 0.000952380942f; cj.soft_erp = 0.714285731f; }   /* box <-> trimesh: mode 28700 */
+            else { cj.mu = 0.25f; cj.bounce = 0.01f; cj.soft_cfm = 0.0001f; cj.soft_erp = -1.0f; }                                /* anything else: mode 28692 */
+            contactGroupDynamic.push_back(cj);
+            if (cb) cb->onCollisionCallback(rb, shape0, nullptr, other, vec3f(cj.normal[0], cj.normal[1], cj.normal[2]), vec3f(cj.pos[0], cj.pos[1], cj.pos[2]), cj.depth);
+        }
+    }
     void collideBodyStatic(RigidBodyR* rb) {
         const oder::Body& b = rb->b;
         const oder::CV3 A[3] = {oder::cv(b.R[0], b.R[3], b.R[6]), oder::cv(b.R[1], b.R[4], b.R[7]), oder::cv(b.R[2], b.R[5], b.R[8])};
@@ -305,6 +319,13 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
             float ext[3];
             for (int k = 0; k < 3; ++k) ext[k] = h[0] * fabsf(b.R[k * 3 + 0]) + h[1] * fabsf(b.R[k * 3 + 1]) + h[2] * fabsf(b.R[k * 3 + 2]);
             const float lo[3] = {c.x - ext[0], c.y - ext[1], c.z - ext[2]}, hi[3] = {c.x + ext[0], c.y + ext[1], c.z + ext[2]};
+            oder::CV3 corner[8];
+            for (int k = 0; k < 8; ++k) {
+                const float sx = (k & 1) ? 1.0f : -1.0f, sy = (k & 2) ? 1.0f : -1.0f, sz = (k & 4) ? 1.0f : -1.0f;
+                corner[k] = toWorld(b, bx.centre.x + sx * h[0], bx.centre.y + sy * h[1], bx.centre.z + sz * h[2]);
+            }
+            oder::ContactPoint slot[8]; bool used[8] = {false, false, false, false, false, false, false, false};
+            bool anyAccepted = false; float fbDepth = -1.0f; oder::CV3 fbN = oder::cv(0, 0, 0); CollisionMeshR* firstMesh = nullptr;
             for (auto& mp : staticMeshes) {
                 CollisionMeshR& m = *mp;
                 if (!((bx.category & m.mask) && (m.category & bx.mask))) continue;      /* collisionNearCallback bMatch */
@@ -317,14 +338,42 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
                     if (std::min(a0.y, std::min(a1.y, a2.y)) > hi[1] || std::max(a0.y, std::max(a1.y, a2.y)) < lo[1]) continue;
                     if (std::min(a0.z, std::min(a1.z, a2.z)) > hi[2] || std::max(a0.z, std::max(a1.z, a2.z)) < lo[2]) continue;
                     ++collisionPairs;
-                    oder::CV3 n;
-                    if (!oder::box_tri_contact(c, A, h, oder::cv(a0.x, a0.y, a0.z), oder::cv(a1.x, a1.y, a1.z), oder::cv(a2.x, a2.y, a2.z), n)) continue;
+                    oder::CV3 n; float satDepth = 0.0f;
+                    const oder::CV3 t0 = oder::cv(a0.x, a0.y, a0.z), t1 = oder::cv(a1.x, a1.y, a1.z), t2 = oder::cv(a2.x, a2.y, a2.z);
+                    if (!oder::box_tri_contact(c, A, h, t0, t1, t2, n, &satDepth)) continue;
                     /* box vs trimesh: contacts whose body-local normal y < 0.9 are dropped (PhysicsEngineODE.cpp:309-318) */
                     const float locY = b.R[1] * n.x + b.R[4] * n.y + b.R[7] * n.z;
                     if (locY < 0.9f) continue;
                     if (kDebugColl) fprintf(stderr, "[oracle] box contact: tri %zu of mesh cat %lu, n=(%g %g %g) locY=%g, tri y=(%g %g %g) box c=(%g %g %g)\n", t, m.category, n.x, n.y, n.z, locY, a0.y, a1.y, a2.y, c.x, c.y, c.z);
                     fire(rb, nullptr, &m, c);
+                    if (!responseEnabled) continue;
+                    /* contact candidates of this accepted triangle: box corners below its plane, inside its prism */
+                    if (!firstMesh) firstMesh = &m;
+                    anyAccepted = true;
+                    if (satDepth > fbDepth || (satDepth == fbDepth && (n.y > fbN.y || (n.y == fbN.y && (n.x > fbN.x || (n.x == fbN.x && n.z > fbN.z)))))) { fbDepth = satDepth; fbN = n; }
+                    oder::CV3 N = oder::ccross(oder::csub(t1, t0), oder::csub(t2, t0));
+                    const float len = sqrtf(oder::cdot(N, N));
+                    if (!(len > 1e-12f)) continue;
+                    const float inv = 1.0f / len;
+                    oder::CV3 nt = oder::cv(N.x * inv, N.y * inv, N.z * inv);
+                    if (oder::cdot(nt, n) < 0.0f) nt = oder::cv(-nt.x, -nt.y, -nt.z);          /* towards the box */
+                    for (int k = 0; k < 8; ++k) {
+                        const float sdist = oder::cdot(oder::csub(corner[k], t0), nt);
+                        if (!(sdist < 0.0f)) continue;
+                        if (!oder::projects_inside(corner[k], t0, t1, t2, N)) continue;
+                        oder::contact_offer(slot, used, k, corner[k], nt, -sdist, 0);
+                    }
                 }
+            }
+            if (responseEnabled && anyAccepted) {
+                oder::ContactPoint out[4];
+                int nOut = oder::contact_select(slot, used, 8, out, 4);
+                if (nOut == 0) {       /* no corner qualified: one contact at the support corner of the deepest accepted triangle */
+                    int bestK = 0; float bestS = 3.4e38f;
+                    for (int k = 0; k < 8; ++k) { const float sdot = oder::cdot(corner[k], fbN); if (sdot < bestS) { bestS = sdot; bestK = k; } }
+                    out[0].pos = corner[bestK]; out[0].normal = fbN; out[0].depth = fbDepth; out[0].kind = 0; nOut = 1;
+                }
+                addContacts(rb, out, nOut, nullptr, firstMesh);
             }
         }
         for (const MeshColliderR& mc : rb->meshColliders) {
@@ -345,6 +394,8 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
                 const float dx = v.x - b.pos[0], dy = v.y - b.pos[1], dz = v.z - b.pos[2];
                 return oder::cv(b.R[0] * dx + b.R[3] * dy + b.R[6] * dz, b.R[1] * dx + b.R[4] * dy + b.R[7] * dz, b.R[2] * dx + b.R[5] * dy + b.R[8] * dz);
             };
+            std::vector<oder::ContactPoint> vslot(nv); std::vector<char> vusedC(nv, 0);
+            CollisionMeshR* firstWall = nullptr;
             for (auto& mp : staticMeshes) {
                 CollisionMeshR& m = *mp;
                 if (!((cm.category & m.mask) && (m.category & cm.mask))) continue;
@@ -353,26 +404,55 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
                 gather(m, lo, hi);
                 bool hit = false;
                 for (uint32_t t : cand) {
-                    if (hit) break;
+                    if (hit && !responseEnabled) break;
                     const TriMeshVertex& a0 = vb[ib[t * 3]]; const TriMeshVertex& a1 = vb[ib[t * 3 + 1]]; const TriMeshVertex& a2 = vb[ib[t * 3 + 2]];
                     if (std::min(a0.x, std::min(a1.x, a2.x)) > hi[0] || std::max(a0.x, std::max(a1.x, a2.x)) < lo[0]) continue;
                     if (std::min(a0.y, std::min(a1.y, a2.y)) > hi[1] || std::max(a0.y, std::max(a1.y, a2.y)) < lo[1]) continue;
                     if (std::min(a0.z, std::min(a1.z, a2.z)) > hi[2] || std::max(a0.z, std::max(a1.z, a2.z)) < lo[2]) continue;
                     const oder::CV3 b0 = toLocal(a0), b1 = toLocal(a1), b2 = toLocal(a2);
                     if (kDebugPairs) { float l0[3] = {std::min(b0.x, std::min(b1.x, b2.x)), std::min(b0.y, std::min(b1.y, b2.y)), std::min(b0.z, std::min(b1.z, b2.z))}, h0[3] = {std::max(b0.x, std::max(b1.x, b2.x)), std::max(b0.y, std::max(b1.y, b2.y)), std::max(b0.z, std::max(b1.z, b2.z))}; float hlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}; for (auto& q : hl) { hlo[0] = std::min(hlo[0], q.x); hhi[0] = std::max(hhi[0], q.x); hlo[1] = std::min(hlo[1], q.y); hhi[1] = std::max(hhi[1], q.y); hlo[2] = std::min(hlo[2], q.z); hhi[2] = std::max(hhi[2], q.z); } if (!(l0[0] > hhi[0] || h0[0] < hlo[0] || l0[1] > hhi[1] || h0[1] < hlo[1] || l0[2] > hhi[2] || h0[2] < hlo[2])) ++localBoundHits; }
-                    for (size_t k = 0; k < nct && !hit; ++k) {
+                    bool triHit = false;
+                    for (size_t k = 0; k < nct && !triHit; ++k) {
                         ++collisionPairs;
-                        if (oder::tri_tri(hl[cib[k * 3]], hl[cib[k * 3 + 1]], hl[cib[k * 3 + 2]], b0, b1, b2)) hit = true;
+                        if (oder::tri_tri(hl[cib[k * 3]], hl[cib[k * 3 + 1]], hl[cib[k * 3 + 2]], b0, b1, b2)) triHit = true;
+                    }
+                    if (!triHit) continue;
+                    hit = true;
+                    if (!responseEnabled) continue;
+                    if (!firstWall) firstWall = &m;
+                    /* contact candidates of this wall triangle, in the chassis frame (the hull's model space): hull vertices behind its
+                       plane (seen from the chassis origin) by less than 0.5 m, inside its prism */
+                    oder::CV3 N = oder::ccross(oder::csub(b1, b0), oder::csub(b2, b0));
+                    const float len = sqrtf(oder::cdot(N, N));
+                    if (!(len > 1e-12f)) continue;
+                    const float inv = 1.0f / len;
+                    oder::CV3 nl = oder::cv(N.x * inv, N.y * inv, N.z * inv);
+                    if (oder::cdot(oder::csub(oder::cv(0, 0, 0), b0), nl) < 0.0f) nl = oder::cv(-nl.x, -nl.y, -nl.z);      /* towards the chassis origin */
+                    for (size_t j = 0; j < nv; ++j) {
+                        const float sdist = oder::cdot(oder::csub(hl[j], b0), nl);
+                        if (!(sdist < 0.0f) || !(sdist > -0.5f)) continue;
+                        if (!oder::projects_inside(hl[j], b0, b1, b2, N)) continue;
+                        const oder::CV3 pw = toWorld(b, hl[j].x, hl[j].y, hl[j].z);
+                        const oder::CV3 nw = oder::cv(b.R[0] * nl.x + b.R[1] * nl.y + b.R[2] * nl.z, b.R[3] * nl.x + b.R[4] * nl.y + b.R[5] * nl.z, b.R[6] * nl.x + b.R[7] * nl.y + b.R[8] * nl.z);
+                        bool u = vusedC[j] != 0;
+                        oder::contact_offer(&vslot[j], &u, 0, pw, nw, -sdist, 1);
+                        vusedC[j] = u ? 1 : 0;
                     }
                 }
                 if (hit && kDebugColl) fprintf(stderr, "[oracle] hull contact with mesh cat %lu\n", m.category);
                 if (hit) fire(rb, &cm, &m, oder::cv(b.pos[0], b.pos[1], b.pos[2]));     /* one callback per mesh pair is enough for the flag */
             }
+            if (responseEnabled && firstWall) {
+                bool usedArr[64]; for (size_t j = 0; j < 64; ++j) usedArr[j] = j < nv && vusedC[j] != 0;
+                oder::ContactPoint out[4];
+                const int nOut = oder::contact_select(vslot.data(), usedArr, (int)std::min<size_t>(nv, 64), out, 4);
+                addContacts(rb, out, nOut, &cm, firstWall);
+            }
         }
     }
     void collisionStep() {
         const unsigned long long pairs0 = collisionPairs;
-        if (currentFrame & 1) { for (auto& rb : bodies) if (!rb->boxColliders.empty() || !rb->meshColliders.empty()) collideBodyStatic(rb.get()); }
+        if (currentFrame & 1) { contactGroupDynamic.clear(); for (auto& rb : bodies) if (!rb->boxColliders.empty() || !rb->meshColliders.empty()) collideBodyStatic(rb.get()); }
         /* even frames: dynamic x dynamic -- one car per simulator here; its own box and mesh do not match each other's masks */
         if ((currentFrame & 1) && kDebugPairs) { fprintf(stderr, "[oracle] frame %u: %llu narrow-phase pairs %llu inbounds\n", currentFrame, collisionPairs - pairs0, localBoundHits); localBoundHits = 0; }
         currentFrame++;
@@ -380,6 +460,7 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
 
     void step(float dt) override {
         collisionStep();
+        world.contacts = contactGroupDynamic;       /* both frames of the group's life (PhysicsEngineODE.cpp:228-244) */
         oder::world_step(world, dt);
     }
 };
@@ -406,6 +487,14 @@ oder::Body* pdref_body(IRigidBody* rb) { return &static_cast<RigidBodyR*>(rb)->b
 oder::Joint* pdref_joint(IJoint* j) { return &static_cast<JointR*>(j)->j; }
 unsigned int pdref_get_frame(IPhysicsEngine* e) { return static_cast<RestateEngine*>(e)->currentFrame; }
 void pdref_set_frame(IPhysicsEngine* e, unsigned int f) { static_cast<RestateEngine*>(e)->currentFrame = f; }
+/* contact joints alive after the last step (tests): n x {pos3, normal3, depth, kind}; clearing them = what a state restore implies */
+int pdref_engine_contacts(IPhysicsEngine* e, float* out8, int cap) {
+    auto* r = static_cast<RestateEngine*>(e); int n = 0;
+    for (const oder::ContactJoint& c : r->contactGroupDynamic) { if (n >= cap) break; float* o = out8 + n * 8; o[0] = c.pos[0]; o[1] = c.pos[1]; o[2] = c.pos[2]; o[3] = c.normal[0]; o[4] = c.normal[1]; o[5] = c.normal[2]; o[6] = c.depth; o[7] = c.soft_erp >= 0 ? 0.0f : 1.0f; ++n; }
+    return (int)r->contactGroupDynamic.size();
+}
+void pdref_engine_clear_contacts(IPhysicsEngine* e) { static_cast<RestateEngine*>(e)->contactGroupDynamic.clear(); }
+void pdref_engine_set_response(IPhysicsEngine* e, int on) { static_cast<RestateEngine*>(e)->responseEnabled = on != 0; if (!on) static_cast<RestateEngine*>(e)->contactGroupDynamic.clear(); }
 /* colliders as the engine received them (for PdCarParams parity) */
 int pdref_body_box(IRigidBody* rb, float* centre3, float* size3) {
     auto* r = static_cast<RigidBodyR*>(rb); if (r->boxColliders.empty()) return 0;

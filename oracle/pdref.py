@@ -57,6 +57,8 @@ def lib():
         L.pdref_sctm_solve.argtypes = [vp, i, i, vp, vp]
         L.pdref_raycast.argtypes = [vp, i, vp, vp]
         L.pdref_num_rows.argtypes = [vp]
+        L.pdref_contacts.argtypes = [vp, vp, i]
+        L.pdref_set_collision_response.argtypes = [vp, i]
         L.pdref_frame.restype = ctypes.c_uint; L.pdref_frame.argtypes = [vp]
         L.pdref_set_frame_counter.argtypes = [vp, ctypes.c_uint]
         _lib = L
@@ -107,6 +109,15 @@ class RefSim:
 
     def set_time(self, t):
         self.L.pdref_set_time(self.h, t)
+
+    def contacts(self):
+        """Contact joints alive after the last step: array [k, 8] = position, normal, depth, kind (0 floor / 1 wall)."""
+        buf = np.zeros((16, 8), np.float32)
+        k = self.L.pdref_contacts(self.h, buf.ctypes.data, 16)
+        return buf[:min(k, 16)]
+
+    def set_collision_response(self, on=True):
+        self.L.pdref_set_collision_response(self.h, int(bool(on)))
 
     def frame(self):
         """PhysicsEngineODE::currentFrame: collisions against the static meshes are tested on odd frames only."""

@@ -9,6 +9,7 @@
  * reference legs.  It also exports the full per-car state in the pd_state.h record layout and the
  * car parameters in the pd_params.h layout so that the CUDA path can be compared field by field.
  */
+#include <time.h>
 #include "Sim/Simulator.h"
 #include "Sim/Track.h"
 #include "Car/CarImpl.h"
@@ -25,6 +26,9 @@ oder::Joint* pdref_joint(IJoint* j);
 void pdref_ray_stats(IPhysicsEngine* e, unsigned long long* rays, unsigned long long* tris);
 unsigned int pdref_get_frame(IPhysicsEngine* e);
 void pdref_set_frame(IPhysicsEngine* e, unsigned int f);
+int pdref_engine_contacts(IPhysicsEngine* e, float* out8, int cap);
+void pdref_engine_clear_contacts(IPhysicsEngine* e);
+void pdref_engine_set_response(IPhysicsEngine* e, int on);
 int pdref_body_box(IRigidBody* rb, float* centre3, float* size3);
 int pdref_body_mesh(IRigidBody* rb, ITriMesh** mesh, float* offR9, float* off3);
 }
@@ -226,6 +230,7 @@ void pdref_get_state(void* hv, uint32_t* r) {
         CI(episodeSteps, 0); CI(nanFlag, 0);
         CI(thermalPrimed, c->tyres[0]->thermalModel->patches[5].inputT == 0.0f ? 1 : 0);
         CI(physFrame, (int)pdref_get_frame(h->sim->physics.get()));
+        CF(damageZone0, c->damageZoneLevel[0]); CF(damageZone1, c->damageZoneLevel[1]); CF(damageZone2, c->damageZoneLevel[2]); CF(damageZone3, c->damageZoneLevel[3]); CF(damageZone4, c->damageZoneLevel[4]);
         for (size_t i = 0; i < c->probeHits.size() && i < PD_MAX_PROBES; ++i) putF(r, PD_OFF_PROBES + (int)i, c->probeHits[i]);
         for (size_t i = 0; i < c->lookAhead.size() && i < PD_LOOKAHEAD; ++i) putF(r, PD_OFF_LOOKAHEAD + (int)i, c->lookAhead[i]);
 #undef CF
@@ -237,6 +242,7 @@ void pdref_get_state(void* hv, uint32_t* r) {
 /* Inverse of pdref_get_state: overwrite the live reference objects with a record ("identical states in"). */
 void pdref_set_state(void* hv, const uint32_t* r) {
     RefSim* h = (RefSim*)hv; Car* c = h->car; Track* trk = c->track;
+    pdref_engine_clear_contacts(h->sim->physics.get());     /* contact joints are not part of the record: a restored state has none alive */
     for (int b = 0; b < PD_NUM_BODIES; ++b) {
         oder::Body* ob = body_of(h, b); int o = PD_OFF_BODY(b);
         for (int k = 0; k < 3; ++k) ob->pos[k] = getF(r, o + PD_BODY_o_px + k);
@@ -286,6 +292,8 @@ void pdref_set_state(void* hv, const uint32_t* r) {
         c->fuel = CD(fuel); c->sleepingFrames = CI(sleepingFrames); c->water->t = CF(waterT); c->speed.value = CF(speed);
         c->collisionFlag = CI(collisionFlag) != 0; c->outOfTrackFlag = CI(outOfTrackFlag) != 0;
         pdref_set_frame(h->sim->physics.get(), (unsigned int)CI(physFrame));
+        c->damageZoneLevel[0] = CF(damageZone0); c->damageZoneLevel[1] = CF(damageZone1); c->damageZoneLevel[2] = CF(damageZone2); c->damageZoneLevel[3] = CF(damageZone3); c->damageZoneLevel[4] = CF(damageZone4);
+        for (int i = 0; i < 5; ++i) c->oldDamageZoneLevel[i] = c->damageZoneLevel[i];        /* Car::postStep leaves them equal (Car.cpp:706-707) */
         c->nearestTrackPointId = CI(nearestTrackPointId); c->oldTrackPointId = CI(oldTrackPointId); c->splinePointId = CI(splinePointId);
         c->lastTrackPointTimestamp = CF(lastTrackPointTimestamp); c->trackLocation = CF(trackLocation); c->oldTrackLocation = CF(oldTrackLocation);
         c->bodyVsTrack = CF(bodyVsTrack); c->velocityVsTrack = CF(velocityVsTrack);
@@ -504,6 +512,107 @@ void pdref_raycast(void* hv, int n, const float* in, float* out) {
         q[7] = hit.hasContact ? (float)surface_index(t, (Surface*)hit.collisionObject->getUserPointer()) : -1.0f;
     }
 }
+/* ---- independent pins of the ODE restatement: quantities that do not depend on how the restatement is written ---- */
+/* largest constraint violation |C(q)| over the car's joints after the last step: ball / fixed anchors apart (m), dball length error
+ * (m), slider: offset across the axis (m); out3 = {max linear error, max dball error, number of joints} */
+void pdref_constraint_errors(void* hv, double* out3) {
+    oder::World* w = pdref_world(((RefSim*)hv)->sim->physics.get());
+    double lin = 0, db = 0;
+    for (oder::Joint* j : w->joints) {
+        const oder::Body& b0 = *j->b0; const oder::Body& b1 = *j->b1;
+        if (j->type == oder::J_BALL) {
+            float g1[3], g2[3]; oder::body_rel_point_pos(b0, j->anchor1, g1); oder::body_rel_point_pos(b1, j->anchor2, g2);
+            const double e = sqrt((double)(g1[0] - g2[0]) * (g1[0] - g2[0]) + (double)(g1[1] - g2[1]) * (g1[1] - g2[1]) + (double)(g1[2] - g2[2]) * (g1[2] - g2[2]));
+            if (e > lin) lin = e;
+        } else if (j->type == oder::J_DBALL) {
+            const double e = fabs((double)oder::dball_current_distance(*j) - (double)j->targetDistance);
+            if (e > db) db = e;
+        } else if (j->type == oder::J_FIXED) {
+            float ofs[3]; oder::mul0_331(ofs, b0.R, j->offset);
+            const double ex = b1.pos[0] - b0.pos[0] + ofs[0], ey = b1.pos[1] - b0.pos[1] + ofs[1], ez = b1.pos[2] - b0.pos[2] + ofs[2];
+            const double e = sqrt(ex * ex + ey * ey + ez * ez);
+            if (e > lin) lin = e;
+        } else if (j->type == oder::J_SLIDER) {
+            float ax1[3], p[3], q[3], ofs[3]; oder::mul0_331(ax1, b0.R, j->axis1); oder::plane_space(ax1, p, q); oder::mul0_331(ofs, b1.R, j->offset);
+            const float c[3] = {b1.pos[0] - b0.pos[0] + ofs[0], b1.pos[1] - b0.pos[1] + ofs[1], b1.pos[2] - b0.pos[2] + ofs[2]};
+            const double e = sqrt((double)oder::dot3(p, c) * oder::dot3(p, c) + (double)oder::dot3(q, c) * oder::dot3(q, c));
+            if (e > lin) lin = e;
+        }
+    }
+    out3[0] = lin; out3[1] = db; out3[2] = (double)w->joints.size();
+}
+/* the last step's bilateral system (A before factoring, rhs) solved again in DOUBLE precision by Gaussian elimination with partial
+ * pivoting, against the single-precision lambda the restated LDL^T produced: out2 = {max |lambda32 - lambda64| / max |lambda64|, rows} */
+void pdref_keep_system(void* hv, int on) { pdref_world(((RefSim*)hv)->sim->physics.get())->keepSystem = on != 0; }
+void pdref_resolve_fp64(void* hv, double* out2) {
+    oder::World* w = pdref_world(((RefSim*)hv)->sim->physics.get());
+    const int m = (int)w->lastRhs.size();
+    out2[0] = -1; out2[1] = m;
+    if (m == 0 || (int)w->last_lambda.size() < m) return;
+    std::vector<double> A((size_t)m * m), x(m);
+    for (size_t k = 0; k < A.size(); ++k) A[k] = w->lastA[k];
+    for (int i = 0; i < m; ++i) x[i] = w->lastRhs[i];
+    for (int c = 0; c < m; ++c) {
+        int piv = c; for (int r = c + 1; r < m; ++r) if (fabs(A[(size_t)r * m + c]) > fabs(A[(size_t)piv * m + c])) piv = r;
+        if (piv != c) { for (int k = 0; k < m; ++k) std::swap(A[(size_t)c * m + k], A[(size_t)piv * m + k]); std::swap(x[c], x[piv]); }
+        const double d = A[(size_t)c * m + c];
+        for (int r = c + 1; r < m; ++r) { const double f = A[(size_t)r * m + c] / d; if (f == 0) continue; for (int k = c; k < m; ++k) A[(size_t)r * m + k] -= f * A[(size_t)c * m + k]; x[r] -= f * x[c]; }
+    }
+    for (int r = m - 1; r >= 0; --r) { double sacc = x[r]; for (int k = r + 1; k < m; ++k) sacc -= A[(size_t)r * m + k] * x[k]; x[r] = sacc / A[(size_t)r * m + r]; }
+    double num = 0, den = 0;
+    for (int i = 0; i < m; ++i) { num = std::max(num, fabs((double)w->last_lambda[i] - x[i])); den = std::max(den, fabs(x[i])); }
+    out2[0] = den > 0 ? num / den : 0;
+}
+/* a free rigid body (no joints, no gravity) tumbling about a non-principal axis, stepped by the restated dxStepIsland / dxStepBody:
+ * relative drift of the angular momentum's magnitude, of the kinetic energy and of the linear momentum after `steps` steps */
+void pdref_free_body_drift(int steps, double h, double* out3) {
+    oder::World w; w.gravity[0] = w.gravity[1] = w.gravity[2] = 0;
+    oder::Body b; oder::body_set_mass_box(b, 837.4f, 1.40f, 1.35f, 4.70f);          /* the demo car's chassis (car.ini [BASIC]) */
+    b.avel[0] = 0.7f; b.avel[1] = 1.1f; b.avel[2] = -0.4f; b.lvel[0] = 3.0f; b.lvel[1] = 0.5f; b.lvel[2] = -12.0f;
+    w.bodies.push_back(&b);
+    auto momentum = [&](double* L, double& E) {
+        float Iw[9], inv[9]; oder::world_inertia(b, Iw, inv);
+        for (int i = 0; i < 3; ++i) L[i] = (double)Iw[i * 3] * b.avel[0] + (double)Iw[i * 3 + 1] * b.avel[1] + (double)Iw[i * 3 + 2] * b.avel[2];
+        E = 0.5 * (L[0] * b.avel[0] + L[1] * b.avel[1] + L[2] * b.avel[2]);
+    };
+    double L0[3], E0; momentum(L0, E0);
+    const double p0[3] = {b.lvel[0], b.lvel[1], b.lvel[2]};
+    for (int s = 0; s < steps; ++s) oder::world_step(w, (float)h);
+    double L1[3], E1; momentum(L1, E1);
+    const double n0 = sqrt(L0[0] * L0[0] + L0[1] * L0[1] + L0[2] * L0[2]), n1 = sqrt(L1[0] * L1[0] + L1[1] * L1[1] + L1[2] * L1[2]);
+    out3[0] = fabs(n1 - n0) / n0; out3[1] = fabs(E1 - E0) / E0;
+    out3[2] = sqrt((b.lvel[0] - p0[0]) * (b.lvel[0] - p0[0]) + (b.lvel[1] - p0[1]) * (b.lvel[1] - p0[1]) + (b.lvel[2] - p0[2]) * (b.lvel[2] - p0[2]));
+}
+
+/* The bench workload (bench.py: configs[1] sample) for `nsims` simulators, entirely on this side of the FFI, so that the CPU
+ * figure carries no Python / ctypes time: random actions resampled every 33 ticks (xorshift, seeded), setCarControls +
+ * stepSimulator per tick, env-style auto reset on collisionFlag / outOfTrackFlag (teleportToSpline(u), u random).  `preroll`
+ * untimed ticks first.  Returns the seconds spent in the `ticks` timed ticks. */
+double pdref_bench_loop(void** hv, int nsims, int ticks, int preroll, unsigned int seed, long long* resets_out) {
+    unsigned long long st = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)seed * 0xD1B54A32D192ED03ull);
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (float)((st >> 40) & 0xFFFFFF) * (1.0f / 16777216.0f); };
+    std::vector<float> steer((size_t)nsims, 0.0f), gas((size_t)nsims, 0.5f);
+    long long resets = 0;
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = -preroll; t < ticks; ++t) {
+        if (t == 0) clock_gettime(CLOCK_MONOTONIC, &t0);
+        if ((t + preroll) % 33 == 0) for (int i = 0; i < nsims; ++i) { steer[(size_t)i] = rnd() * 2.0f - 1.0f; gas[(size_t)i] = 0.1f + 0.9f * rnd(); }
+        for (int i = 0; i < nsims; ++i) {
+            RefSim* h = (RefSim*)hv[i]; Car* c = h->car;
+            CarControls k; k.steer = steer[(size_t)i]; k.gas = gas[(size_t)i]; k.isShifterSupported = c->controls.isShifterSupported;
+            c->controls = k; c->smoothSteer = true;
+            Simulator* s = h->sim.get();
+            s->step(1.0f / 333.0f, s->physicsTime, s->gameTime);
+            s->physicsTime += 1.0 / 333.0; s->gameTime += 1.0 / 333.0;
+            if (c->collisionFlag || c->outOfTrackFlag) { c->teleportToSpline(rnd()); ++resets; }
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (resets_out) *resets_out = resets;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+int pdref_contacts(void* hv, float* out8, int cap) { return pdref_engine_contacts(((RefSim*)hv)->sim->physics.get(), out8, cap); }
+void pdref_set_collision_response(void* hv, int on) { pdref_engine_set_response(((RefSim*)hv)->sim->physics.get(), on); }
 unsigned int pdref_frame(void* hv) { return pdref_get_frame(((RefSim*)hv)->sim->physics.get()); }
 void pdref_set_frame_counter(void* hv, unsigned int f) { pdref_set_frame(((RefSim*)hv)->sim->physics.get(), f); }
 void pdref_ray_statistics(void* hv, unsigned long long* rays, unsigned long long* tris) { pdref_ray_stats(((RefSim*)hv)->sim->physics.get(), rays, tris); }

@@ -47,6 +47,7 @@ def load_library():
         "pd_create": (i, [cp, cp, cp, i, i, ctypes.POINTER(vp)]),
         "pd_create_synthetic": (i, [cp, cp, i, f, i, i, ctypes.POINTER(vp)]),
         "pd_destroy": (None, [vp]),
+        "pd_compute_fat_points": (i, [cp, cp, i, vp, i]),
         "pd_last_error": (cp, [vp]),
         "pd_num_envs": (i, [vp]),
         "pd_state_words": (i, []),
@@ -59,6 +60,8 @@ def load_library():
         "pd_get_env_config": (i, [vp, vp]),
         "pd_env_reset_counters": (i, [vp, vp]),
         "pd_params_bytes": (i, []),
+        "pd_set_collision_response": (i, [vp, i]),
+        "pd_get_contacts": (i, [vp, i, vp, i]),
         "pd_set_stream": (i, [vp, vp]),
         "pd_set_scoring_var": (i, [vp, cp, f]),
         "pd_get_scoring_var": (f, [vp, cp]),
@@ -103,6 +106,17 @@ def load_library():
 
 
 STATE_WORDS = None
+
+
+def compute_fat_points(base_path, track, device=0, max_points=200000):
+    """Track::computeFatPoints on the GPU: the content of spline.cache, [n, 15] float32 (best, left, right, center, forwardDir)."""
+    L = load_library()
+    out = np.zeros((max_points, 15), np.float32)
+    n = L.pd_compute_fat_points(os.fspath(base_path).encode(), track.encode(), int(device), out.ctypes.data, max_points)
+    if n < 0:
+        msg = L.pd_last_error(None)
+        raise PdError("pd_compute_fat_points failed (%d): %s" % (n, msg.decode() if msg else "?"))
+    return out[:n].copy()
 
 
 def _ptr(a):
@@ -202,6 +216,18 @@ class Batch:
     def env_reset_counters(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         self._ck(self.L.pd_env_reset_counters(self.h, _ptr(m)))
+
+    def set_collision_response(self, on=True):
+        """Contact joints from collisions enter the solve (default) / collisions only raise collisionFlag."""
+        self._ck(self.L.pd_set_collision_response(self.h, int(bool(on))))
+
+    def contacts(self, env=0):
+        """Live contact joints of one env: array [k, 8] = position, normal, depth, kind."""
+        out = np.zeros((8, 8), np.float32)
+        k = self.L.pd_get_contacts(self.h, int(env), out.ctypes.data, 8)
+        if k < 0:
+            raise PdError("pd_get_contacts failed")
+        return out[:k]
 
     def set_stream(self, stream_ptr):
         """Run this batch's kernels on the given cudaStream_t (int / None = the batch's own stream)."""

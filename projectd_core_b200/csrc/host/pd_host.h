@@ -75,8 +75,18 @@ struct BvhNodeH { float bmin[3]; int32_t left; float bmax[3]; int32_t count; };
 #ifndef PD_TRI_STRIDE
 #define PD_TRI_STRIDE 12
 #endif
+/* Track::computeFatPoints' configuration (Sim/Track.h:83-89, spline.ini [SPLINE], Track.cpp:180-205) */
+struct TraceConfig {
+    int32_t traceSides = 0;
+    float rayOffsetY = 20.0f, rayLength = 100.0f, sideMax = 10.0f, diffHeightMax = 0.01f, diffGripMax = 0.1f, step = 0.01f;
+    int32_t nBadSectors = 0; uint32_t badSectors[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
 struct TrackModel {
     PdTrackInfo info;
+    std::vector<float> slim;          /* spline.bin: 5 floats per point {best.xyz, sides[2]} (Sim/Track.h:13-17) */
+    TraceConfig trace;
+    bool needFat = false;             /* spline.cache missing / stale / ignored on request: `fat` must be computed (on the GPU) before finish_track_points */
+    bool closedLoop = false; float hashCellSize = 50.0f;
     std::vector<PdSurface> surfaces;
     std::vector<float> tris;          /* PD_TRI_STRIDE (12) floats per triangle, leaf order: v0, e1, e2, surface id bits, 0, 0 */
     std::vector<int32_t> triSurf;
@@ -99,7 +109,8 @@ struct TrackModel {
     std::vector<float> collCell;               /* per cell, 32 B: track y min / max, wall y min / max, then (int bits) first TRACK entry, first WALL entry, end */
     std::vector<float> collY;                  /* per cell: y range of its TRACK triangles, y range of its WALL triangles */
 };
-void load_track(const std::string& basePath, const std::string& name, TrackModel& out);
+/* recomputeFat: ignore spline.cache and leave `fat` to be regenerated (TrackModel::needFat) */
+void load_track(const std::string& basePath, const std::string& name, TrackModel& out, bool recomputeFat = false);
 /* synthetic track generator for config 4 (large mesh): closed loop of `nPoints` spline points, tessellated */
 void make_synthetic_track(int targetTris, float lengthMeters, TrackModel& out);
 void build_column_grid(TrackModel& out);

@@ -385,7 +385,7 @@ static std::vector<uint8_t> read_file(const std::string& path) {
     return buf;
 }
 
-void load_track(const std::string& basePathIn, const std::string& name, TrackModel& out) {
+void load_track(const std::string& basePathIn, const std::string& name, TrackModel& out, bool recomputeFat) {
     std::string basePath = basePathIn;
     if (!basePath.empty() && basePath.back() != '/') basePath += "/";
     const std::string folder = basePath + "content/tracks/" + name + "/";
@@ -424,12 +424,31 @@ void load_track(const std::string& basePathIn, const std::string& name, TrackMod
     build_bvh(verts9, surf, out);
     /* spline */
     bool closedLoop = false;
-    { Ini sp(folder + "spline.ini"); if (sp.ready) closedLoop = sp.getInt("SPLINE", "CLOSED_LOOP") != 0; }
+    {   /* Track::initTrackPoints (Track.cpp:178-205) */
+        Ini sp(folder + "spline.ini");
+        if (sp.ready) {
+            closedLoop = sp.getInt("SPLINE", "CLOSED_LOOP") != 0;
+            TraceConfig& tc = out.trace;
+            int ts = 0; if (sp.tryGetInt("SPLINE", "TRACE_SIDES", ts)) tc.traceSides = ts != 0;
+            sp.tryGetFloat("SPLINE", "TRACE_RAY_OFFSET_Y", tc.rayOffsetY); sp.tryGetFloat("SPLINE", "TRACE_RAY_LENGTH", tc.rayLength);
+            sp.tryGetFloat("SPLINE", "TRACE_SIDE_MAX", tc.sideMax); sp.tryGetFloat("SPLINE", "TRACE_DIFF_HEIGHT_MAX", tc.diffHeightMax);
+            sp.tryGetFloat("SPLINE", "TRACE_DIFF_GRIP_MAX", tc.diffGripMax); sp.tryGetFloat("SPLINE", "TRACE_STEP", tc.step);
+            std::string list;
+            if (sp.tryGetString("SPLINE", "TRACE_BAD_SECTORS", list)) for (const std::string& tok : split(list, "|")) if (!tok.empty() && tc.nBadSectors < 8) tc.badSectors[tc.nBadSectors++] = (uint32_t)stoi_ref(tok);
+        }
+    }
+    out.closedLoop = closedLoop; out.hashCellSize = cellSize;
     const std::vector<uint8_t> slim = read_file(folder + "spline.bin");
     const std::vector<uint8_t> fat = read_file(folder + "spline.cache");
     const size_t nSlim = slim.size() / 20, nFat = fat.size() / sizeof(PdFatPoint);
-    if (nFat == 0 || nFat != nSlim)
-        throw Error("track '" + name + "': spline.cache missing or stale (regenerating it -- Track::computeFatPoints -- is not part of the hot path yet)");
+    out.slim.resize(nSlim * 5); if (nSlim) memcpy(out.slim.data(), slim.data(), nSlim * 20);
+    if (recomputeFat || nFat == 0 || nFat != nSlim) {
+        /* Track::computeFatPoints (Track.cpp:366-433) is batch ray casting: it runs on the GPU (pd_batch.cu k_fat_points) once the
+           triangle index is on the device; the point grids are built afterwards (finish_track_points) */
+        if (nSlim == 0) throw Error("track '" + name + "': neither spline.cache nor spline.bin");
+        out.needFat = true; out.fat.clear();
+        return;
+    }
     out.fat.resize(nFat); memcpy(out.fat.data(), fat.data(), nFat * sizeof(PdFatPoint));
     finish_track_points(out, closedLoop, cellSize);
 }

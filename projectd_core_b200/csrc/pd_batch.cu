@@ -45,6 +45,7 @@ struct EnvIO {
     int32_t* pending;            /* [n] 1 = finished at the previous step (null: no in-kernel reset) */
     uint32_t* episodeCtr; uint64_t seed, idOffset; int teleportMode;
     const int32_t* collIn;       /* [n] k_collide's answer for this tick's start pose (0 / 1; -1 = test inside the tick); null: test inside the tick */
+    const float* contacts;       /* [n][PD_CONTACT_WORDS] live contact joints per env (collision response on), or null */
     PdEnvConfig cfg;             /* ProjectDEnv's knobs (gas range, penalties, termination switches, clutch / gear overrides) */
     long long* clk;              /* profiling aid (PD_DEBUG_CLOCKS=1): SM cycles each warp spent in the tick, [blocks * 2]; null otherwise */
 };
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __
         if (resetNow) env_reset_in_kernel(P, T, sv, e, io, time);
         else if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1], io.cfg);
 #if PD_SOLVER2
-        car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows, collPre);
+        car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows, collPre, io.contacts ? io.contacts + (size_t)e * PD_CONTACT_WORDS : nullptr);
 #elif PD_SERIAL_SMEM_SCRATCH
         car_tick<1, PD_BLOCK>(P, T, sv, dt, time, pd_rows, pd_scrD + threadIdx.x, collPre);
 #else
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(const __grid_const
         float lrows[PD_GSCR_ROWS_WORDS];                     /* JA | JB in local memory, Y | D | dg in shared memory */
         car_tick_quad<1, QLANES>(P, T, sv, dt, time, ex, lrows, scratch + cid, collPre, collWait);
 #else
-        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid, collPre, collWait);
+        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid, collPre, collWait, io.contacts ? io.contacts + (size_t)e * PD_CONTACT_WORDS : nullptr);
 #endif
     }
     if (io.clk && wl == 0 && warp < 2) io.clk[blockIdx.x * 2 + warp] = clock64() - clk0;
@@ -315,6 +316,29 @@ __global__ void __launch_bounds__(PD_COLLIDE_BLOCK) k_collide(const __grid_const
     const bool any = car_collide_warp<true>(P, T, C, lane, hullS + (threadIdx.x >> 5) * PD_HULLS_WORDS, dbg ? stats : nullptr);
     if (lane == 0) collOut[e] = any ? 1 : 0;
     if (dbg && lane == 0) { dbg[4096 + (size_t)n * 12 + (size_t)e * 4] = clock64() - clk0; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 1] = ((long long)stats[0] << 32) | (unsigned)stats[1]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 2] = ((long long)stats[2] << 32) | (unsigned)stats[3]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 3] = (long long)any | ((long long)stats[4] << 8) | ((long long)stats[5] << 36); }
+}
+
+/* Collision response: the contact joints of this odd frame (PhysicsEngineODE.cpp:230-236: the frame's contact group is emptied, then
+ * refilled).  One warp per car, after k_collide on the same stream; cars on an even frame keep the joints of the previous frame,
+ * cars without contact get an empty set, cars WITH contact (rare) run the generator of pd_contacts.h on the same start pose
+ * k_collide tested. */
+__global__ void __launch_bounds__(PD_COLLIDE_BLOCK) k_contacts(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, const uint32_t* __restrict__ state, int layout, int n,
+                                                               const int32_t* __restrict__ pending, const int32_t* __restrict__ collIn, float* __restrict__ contOut,
+                                                               int teleportMode, uint64_t seed, uint64_t idOffset, const uint32_t* __restrict__ episodeCtr) {
+    const int e = (blockIdx.x * PD_COLLIDE_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= n) return;
+    SVR sv = sv_env(layout, const_cast<uint32_t*>(state), (size_t)e);
+    if (!(sv.i(PD_OFF_CAR + PD_CAR_o_physFrame) & 1)) return;
+    float* co = contOut + (size_t)e * PD_CONTACT_WORDS;
+    if (!collIn[e]) { if (lane == 0) reinterpret_cast<int*>(co)[0] = 0; return; }
+    Body C; load_body(sv, PD_BODY_CHASSIS, C);
+    if (pending && pending[e]) {
+        float u = 0.0f;
+        if (teleportMode == PD_TELEPORT_NEAREST) u = sv.f(PD_OFF_CAR + PD_CAR_o_trackLocation);
+        else if (teleportMode == PD_TELEPORT_RANDOM) u = pd_uniform(seed, idOffset + (uint64_t)e, episodeCtr[e]);
+        Quat q; teleport_chassis_pose(P, T, point_id_at_distance(T, u), C.fr.ax, C.fr.ay, C.fr.az, q, C.fr.p);
+    }
+    car_contacts_warp(P, T, C, lane, co);
 }
 
 /* initial record -> every env (both layouts) */
@@ -404,6 +428,53 @@ __global__ void k_raycast(TrackDev T, int n, const float* __restrict__ rays, flo
     q[0] = (float)r.hit; q[1] = r.pos.x; q[2] = r.pos.y; q[3] = r.pos.z; q[4] = r.normal.x; q[5] = r.normal.y; q[6] = r.normal.z; q[7] = (float)r.surface;
 }
 
+/* Track::computeFatPoints + computeSideLocation (Sim/Track.cpp:366-467), one thread per (spline point, side): the down ray that
+ * drops the point onto the road, then either the two side rays at the stored half widths or the side TRACE -- rays from the
+ * point's ray origin towards positions stepping outwards by `step`, each accepted only while the surface stays valid track of the
+ * same category, height and grip continuous with the previous accepted hit and not in a bad sector; the first rejected hit ends
+ * the walk.  Each walk is sequential by definition (it depends on its previous hit); the batch is parallel over points and sides. */
+struct FatCfg { int traceSides; float offY, rayLen, sideMax, diffH, diffGrip, step; int nBad; uint32_t bad[8]; };
+__global__ void k_fat_points(TrackDev T, int n, const float* __restrict__ slim, FatCfg cfg, float* __restrict__ fat /* [n][15] */) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid >> 1, side = tid & 1;
+    if (i >= n) return;
+    const float* sp = slim + (size_t)i * 5;
+    float* f = fat + (size_t)i * 15;
+    const V3 best0 = v3(sp[0], sp[1], sp[2]);
+    const V3 rayOff = v3(0.0f, cfg.offY, 0.0f);
+    const V3 rayStart = best0 + rayOff;
+    const RayHit hit = ray_cast_down(T, rayStart, cfg.rayLen);
+    if (!hit.hit) { if (side == 0) for (int k = 0; k < 15; ++k) f[k] = 0.0f; return; }
+    V3 fwd = v3(0, 0, 0);
+    if (i + 1 < n) fwd = norm(v3(slim[(size_t)(i + 1) * 5], slim[(size_t)(i + 1) * 5 + 1], slim[(size_t)(i + 1) * 5 + 2]) - best0);
+    else if (i > 0) fwd = norm(best0 - v3(slim[(size_t)(i - 1) * 5], slim[(size_t)(i - 1) * 5 + 1], slim[(size_t)(i - 1) * 5 + 2]));
+    const V3 leftDir = norm(cross(fwd, v3(0.0f, -1.0f, 0.0f)));
+    const V3 dir = side == 0 ? leftDir : leftDir * -1.0f;
+    V3 result;
+    if (!cfg.traceSides) {
+        result = hit.pos + dir * sp[3 + side];
+        const RayHit h2 = ray_cast_down(T, result + rayOff, cfg.rayLen);
+        if (h2.hit) result = h2.pos;
+    } else {
+        const PdSurface& s0 = T.surfaces[hit.surface];
+        result = hit.pos; V3 prevHit = hit.pos; float prevGrip = s0.gripMod;
+        const int numSteps = (int)(cfg.sideMax / cfg.step);
+        for (int traceId = 1; traceId < numSteps; ++traceId) {
+            const V3 rayEnd = hit.pos + dir * ((float)traceId * cfg.step);
+            const V3 rayN = norm(rayEnd - rayStart);
+            const RayHit h2 = ray_cast(T, rayStart, rayN, cfg.rayLen);
+            if (!h2.hit) continue;
+            const PdSurface& s2 = T.surfaces[h2.surface];
+            bool bad = false;
+            for (int q = 0; q < cfg.nBad; ++q) if (cfg.bad[q] == s2.sectorID) bad = true;
+            if (s2.isValidTrack && s2.collisionCategory == s0.collisionCategory && fabsf(h2.pos.y - prevHit.y) < cfg.diffH && fabsf(s2.gripMod - prevGrip) < cfg.diffGrip && !bad) { result = h2.pos; prevHit = h2.pos; prevGrip = s2.gripMod; }
+            else break;
+        }
+    }
+    if (side == 0) { f[0] = hit.pos.x; f[1] = hit.pos.y; f[2] = hit.pos.z; f[3] = result.x; f[4] = result.y; f[5] = result.z; f[12] = fwd.x; f[13] = fwd.y; f[14] = fwd.z; }
+    else { f[6] = result.x; f[7] = result.y; f[8] = result.z; }
+}
+
 __global__ void k_set_pressure(uint32_t* state, int layout, int n, int wheel, float value) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -452,6 +523,8 @@ struct pd_batch {
     bool collWarp = true;             /* quad kernel: collision warp inside the tick kernel (env PD_COLL_WARP=0: k_collide ahead of it instead) */
     bool zeroCopy = true; const void* zcKey[4] = {nullptr, nullptr, nullptr, nullptr}; void* zcDev[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* dColl = nullptr;         /* k_collide's answers for the coming tick */
+    float* dContacts = nullptr;       /* [n][PD_CONTACT_WORDS] contact joints alive per env (collision response) */
+    bool response = true;             /* A14 response: contact joints from collisions enter the solve (pd_set_collision_response) */
     long long frameKnown = 0;         /* physics frame shared by all envs, or -1 when states were set individually (then k_collide runs every tick) */
     int32_t* dPending = nullptr; int autoreset = PD_AUTORESET_SAME_STEP;
     int resetMode = PD_TELEPORT_START;   /* ProjectDEnv.teleport_mode: the last pd_teleport_mode() mode, also used by the automatic resets */
@@ -492,6 +565,41 @@ static int sync_params(pd_batch* b) {
     b->paramsDirty = false; return PD_OK;
 }
 
+/* Track::computeFatPoints on the device: needs only the ray structures of the track (BVH, triangles, surfaces, column grid), which
+ * are uploaded into temporaries here; fills track.fat and builds the point grids (pdh::finish_track_points). */
+static int fat_points_on_device(pdh::TrackModel& track, cudaStream_t stream, std::string& err) {
+    const int n = (int)(track.slim.size() / 5);
+    if (n <= 0) { err = "no spline points"; return PD_ERR_IO; }
+    TrackDev T{}; std::vector<void*> tmp;
+    auto up = [&](const void* src, size_t bytes) -> void* { void* q = nullptr; if (cudaMalloc(&q, bytes ? bytes : 4) != cudaSuccess) return nullptr; tmp.push_back(q); if (bytes && src) cudaMemcpyAsync(q, src, bytes, cudaMemcpyHostToDevice, stream); return q; };
+    T.nodes = (const BvhNode*)up(track.nodes.data(), track.nodes.size() * sizeof(pdh::BvhNodeH));
+    T.tris = (const float*)up(track.tris.data(), track.tris.size() * 4);
+    T.triSurf = (const int32_t*)up(track.triSurf.data(), track.triSurf.size() * 4);
+    T.surfaces = (const PdSurface*)up(track.surfaces.data(), track.surfaces.size() * sizeof(PdSurface));
+    T.colStart = (const int32_t*)up(track.colStart.data(), track.colStart.size() * 4);
+    T.colItems = (const int32_t*)up(track.colItems.data(), track.colItems.size() * 4);
+    T.colGrid = track.colGrid; T.info = track.info;
+    float* dSlim = (float*)up(track.slim.data(), track.slim.size() * 4);
+    float* dFat = (float*)up(nullptr, (size_t)n * 15 * 4);
+    int rc = PD_OK;
+    if (!T.nodes || !T.tris || !T.triSurf || !T.surfaces || !T.colStart || !T.colItems || !dSlim || !dFat) { err = "cudaMalloc failed (fat points)"; rc = PD_ERR_CUDA; }
+    if (rc == PD_OK) {
+        FatCfg cfg{}; const pdh::TraceConfig& tc = track.trace;
+        cfg.traceSides = tc.traceSides; cfg.offY = tc.rayOffsetY; cfg.rayLen = tc.rayLength; cfg.sideMax = tc.sideMax; cfg.diffH = tc.diffHeightMax; cfg.diffGrip = tc.diffGripMax; cfg.step = tc.step;
+        cfg.nBad = tc.nBadSectors; for (int q = 0; q < 8; ++q) cfg.bad[q] = tc.badSectors[q];
+        cudaMemsetAsync(dFat, 0, (size_t)n * 15 * 4, stream);
+        k_fat_points<<<(2 * n + 63) / 64, 64, 0, stream>>>(T, n, dSlim, cfg, dFat);
+        track.fat.resize((size_t)n);
+        if (cudaMemcpyAsync(track.fat.data(), dFat, (size_t)n * 15 * 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { err = std::string("k_fat_points: ") + cudaGetErrorString(cudaGetLastError()); rc = PD_ERR_CUDA; }
+    }
+    for (void* q : tmp) cudaFree(q);
+    if (rc != PD_OK) return rc;
+    for (PdFatPoint& p : track.fat) for (int k = 0; k < 3; ++k) p.center[k] = (p.left[k] + p.right[k]) * 0.5f;     /* fat.center = (left + right) * 0.5 (Track.cpp:430) */
+    track.needFat = false;
+    try { pdh::finish_track_points(track, track.closedLoop, track.hashCellSize); } catch (const std::exception& ex) { err = ex.what(); return PD_ERR_IO; }
+    return PD_OK;
+}
+
 static int finish_create(pd_batch* b, int n_envs, int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -514,6 +622,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
       if (const char* q = getenv("PD_QUAD_CPW")) { const int v = atoi(q); if (v == 2 || v == 4 || v == 8) b->quadCpw = v; } }
     b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
     int rc;
+    if (b->track.needFat) { b->launches++; if ((rc = fat_points_on_device(b->track, b->stream, b->err))) return rc; }      /* no usable spline.cache: Track::computeFatPoints, on the GPU */
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
     { const std::vector<pd::BvhNode>& dummy = *reinterpret_cast<const std::vector<pd::BvhNode>*>(&b->track.nodes); if ((rc = upload(b, &b->dev.nodes, dummy))) return rc; }
     if ((rc = upload(b, &b->dev.tris, b->track.tris))) return rc;
@@ -570,6 +679,8 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = dalloc(b, &b->dStats, 8))) return rc;
     if ((rc = dalloc(b, &b->dPending, n))) return rc;
     if ((rc = dalloc(b, &b->dColl, n))) return rc;
+    if ((rc = dalloc(b, &b->dContacts, n * PD_CONTACT_WORDS))) return rc;
+    CK(cudaMemsetAsync(b->dContacts, 0, n * PD_CONTACT_WORDS * 4, b->stream));
     CK(cudaMemsetAsync(b->dPending, 0, n * 4, b->stream));
     if (getenv("PD_DEBUG_CLOCKS")) { b->nClk = (int)(n / 4 + 64);
 #if defined(PD_PHASE_CLOCKS)
@@ -600,14 +711,19 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
         /* collision detection (odd physics frames): the quad kernel brings its own collision warp per block; the thread-per-car
            kernel is preceded by k_collide (a warp per car) on the same stream */
         const bool oddPossible = b->frameKnown < 0 || (b->frameKnown & 1);
-        if (oddPossible && b->layout == PD_LAYOUT_RECORDS && b->collWarp) collWarp = true;
+        /* with the collision response on, k_collide also GENERATES the contact joints of cars that touch something (it knows the
+           start pose, resets included); the tick kernels pick the live joints up at the solve */
+        if (oddPossible && b->layout == PD_LAYOUT_RECORDS && b->collWarp && !b->response) collWarp = true;
         else if (oddPossible) {
             k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr,
                                                                                                       io.teleportMode, io.seed, io.idOffset, io.episodeCtr); b->launches++;
             io.collIn = b->dColl;
+            if (b->response) { k_contacts<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, b->dContacts,
+                                                                                                                        io.teleportMode, io.seed, io.idOffset, io.episodeCtr); b->launches++; }
         }
+        if (b->response) io.contacts = b->dContacts;
         if (b->frameKnown >= 0) b->frameKnown++;
-    } else b->frameKnown = -1;          /* a masked tick advances only some envs: frames are no longer in lock step */
+    } else { b->frameKnown = -1; if (b->response) io.contacts = b->dContacts; }          /* a masked tick advances only some envs: frames are no longer in lock step */
     if (b->layout == PD_LAYOUT_RECORDS) {
         const int threads = collWarp ? PD_QBLOCK + 32 : PD_QBLOCK;
         switch (b->quadCpw) {
@@ -632,6 +748,22 @@ int pd_create(const char* base_path, const char* track_name, const char* car_mod
     if (rc == PD_OK) rc = finish_create(b, n_envs, device);
     if (rc != PD_OK) { g_createError = b->err; pd_destroy(b); return rc; }
     *out = b; return PD_OK;
+}
+
+int pd_compute_fat_points(const char* base_path, const char* track_name, int device, float* out, int cap_points) {
+    if (!base_path || !track_name || !out || cap_points < 0) { g_createError = "pd_compute_fat_points: bad argument"; return PD_ERR_ARG; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { g_createError = "no CUDA device available (this library has no CPU path)"; return PD_ERR_CUDA; }
+    if (device < 0 || device >= count || cudaSetDevice(device) != cudaSuccess) { g_createError = "bad device ordinal"; return PD_ERR_ARG; }
+    pdh::TrackModel track;
+    try { pdh::load_track(base_path, track_name, track, true); } catch (const std::exception& ex) { g_createError = ex.what(); return PD_ERR_IO; }
+    cudaStream_t st; if (cudaStreamCreate(&st) != cudaSuccess) { g_createError = "cudaStreamCreate failed"; return PD_ERR_CUDA; }
+    std::string err; const int rc = fat_points_on_device(track, st, err);
+    cudaStreamDestroy(st);
+    if (rc != PD_OK) { g_createError = err; return rc; }
+    const int n = (int)track.fat.size();
+    memcpy(out, track.fat.data(), (size_t)(n < cap_points ? n : cap_points) * sizeof(PdFatPoint));
+    return n;
 }
 
 int pd_create_synthetic(const char* base_path, const char* car_model, int target_tris, float length_m, int n_envs, int device, pd_batch** out) {
@@ -698,6 +830,23 @@ int pd_env_reset_counters(pd_batch* b, const uint8_t* mask) {
     CK(cudaGetLastError()); return PD_OK;
 }
 int pd_params_bytes(void) { return (int)sizeof(PdCarParams); }
+int pd_set_collision_response(pd_batch* b, int on) {
+    if (!b) return PD_ERR_ARG;
+    ENTER(b);
+    b->response = on != 0;
+    CK(cudaMemsetAsync(b->dContacts, 0, (size_t)b->n * PD_CONTACT_WORDS * 4, b->stream));
+    return PD_OK;
+}
+int pd_get_contacts(pd_batch* b, int env, float* out, int max_contacts) {
+    if (!b || !out || env < 0 || env >= b->n || max_contacts < 0) return -1;
+    ENTER(b);
+    float rec[PD_CONTACT_WORDS];
+    if (cudaMemcpyAsync(rec, b->dContacts + (size_t)env * PD_CONTACT_WORDS, sizeof(rec), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess) return -1;
+    int n; memcpy(&n, rec, 4);
+    if (n < 0) n = 0; if (n > PD_MAX_CONTACTS) n = PD_MAX_CONTACTS;
+    for (int i = 0; i < n && i < max_contacts; ++i) memcpy(out + i * 8, rec + 1 + i * 8, 32);
+    return n;
+}
 int pd_set_stream(pd_batch* b, void* stream) {
     if (!b) return PD_ERR_ARG;
     ENTER(b);
@@ -889,6 +1038,7 @@ int pd_get_state(pd_batch* b, int env, uint32_t* record) {
 int pd_set_state(pd_batch* b, int env, const uint32_t* record) {
     if (!b || !record || env < 0 || env >= b->n) return PD_ERR_ARG;
     b->frameKnown = -1;
+    CK(cudaMemsetAsync(b->dContacts + (size_t)env * PD_CONTACT_WORDS, 0, PD_CONTACT_WORDS * 4, b->stream));   /* contact joints are not part of the record */
     if (b->layout == PD_LAYOUT_RECORDS) CK(cudaMemcpyAsync(b->dState + (size_t)env * PD_STATE_STRIDE, record, PD_STATE_WORDS * 4, cudaMemcpyHostToDevice, b->stream));
     else CK(cudaMemcpy2DAsync(b->dState + state_index_tiled(0, (size_t)env), (size_t)PD_TILE * 4, record, 4, 4, PD_STATE_WORDS, cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream)); return PD_OK;
@@ -910,7 +1060,12 @@ static int pack_common(pd_batch* b, uint32_t* host_buf, int toDevice) {
     return rc;
 }
 int pd_snapshot(pd_batch* b, uint32_t* host_buf) { if (!b || !host_buf) return PD_ERR_ARG; return pack_common(b, host_buf, 0); }
-int pd_restore(pd_batch* b, const uint32_t* host_buf) { if (!b || !host_buf) return PD_ERR_ARG; b->frameKnown = -1; return pack_common(b, const_cast<uint32_t*>(host_buf), 1); }
+int pd_restore(pd_batch* b, const uint32_t* host_buf) {
+    if (!b || !host_buf) return PD_ERR_ARG;
+    b->frameKnown = -1;
+    CK(cudaMemsetAsync(b->dContacts, 0, (size_t)b->n * PD_CONTACT_WORDS * 4, b->stream));      /* contact joints are not part of the record: a restored state has none alive */
+    return pack_common(b, const_cast<uint32_t*>(host_buf), 1);
+}
 int pd_get_params(const pd_batch* b, PdCarParams* out) { if (!b || !out) return PD_ERR_ARG; *out = b->car.P; return PD_OK; }
 int pd_get_track_info(const pd_batch* b, PdTrackInfo* out) { if (!b || !out) return PD_ERR_ARG; *out = b->track.info; return PD_OK; }
 

@@ -26,6 +26,7 @@ struct CarCtx {
 #if defined(PD_PHASE_CLOCKS)
     long long* ph = nullptr;   /* profiling build: phase time stamps of this warp (written by its lane 0) */
 #endif
+    bool newDamage = false;      /* a damage zone rose during this tick's collision callbacks */
     PD_HD explicit CarCtx(CarS& cc) : c(cc) {}
 };
 #if defined(PD_PHASE_CLOCKS) && defined(__CUDA_ARCH__)

@@ -9,8 +9,7 @@
  *   hull mesh  (collider.bin,   category CAR, mask WALL)   vs  WALL triangles: a triangle pair touches when an edge
  *       of either crosses the other
  * Tested on odd physics frames only (PhysicsEngineODE.cpp:230-236; even frames are dynamic-vs-dynamic, and there is
- * one car per env).  The contact joints (the response) are not built: the env terminates the episode on the flag
- * (projectd_env.py:186-189); DESIGN.md lists this as the remaining part of A14 / N3.
+ * one car per env).  The response (contact generation + contact joints) lives in pd_contacts.h.
  *
  * Hull vs wall is evaluated in the chassis frame (the hull's model space, as OPCODE's mesh-vs-mesh query does): the
  * hull keeps its chassis-local vertices, each candidate wall triangle is transformed into that frame.
@@ -43,7 +42,7 @@ PD_HD bool sat_axis(V3 L, float p0, float p1, float p2, float r, float bias, flo
 }
 
 /* box (centre c, unit axes A0 A1 A2, half sizes h) against triangle v0 v1 v2; nOut = contact normal (triangle -> box) */
-PD_HDN bool box_tri_contact(V3 c, V3 A0, V3 A1, V3 A2, V3 h, V3 v0, V3 v1, V3 v2, V3& nOut) {
+PD_HDN bool box_tri_contact(V3 c, V3 A0, V3 A1, V3 A2, V3 h, V3 v0, V3 v1, V3 v2, V3& nOut, float* depthOut = nullptr) {
     const V3 E0 = v1 - v0, E1 = v2 - v1, E2 = v0 - v2;
     const V3 P0 = v0 - c, P1 = v1 - c, P2 = v2 - c;
     const V3 N = cross(E0, v2 - v0);
@@ -71,6 +70,7 @@ PD_HDN bool box_tri_contact(V3 c, V3 A0, V3 A1, V3 A2, V3 h, V3 v0, V3 v1, V3 v2
         }
     }
     nOut = bestN;
+    if (depthOut) *depthOut = bestDepth;
     return true;
 }
 

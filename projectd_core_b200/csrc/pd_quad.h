@@ -38,7 +38,7 @@ PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
 }
 
 template <int STRIDE, int STRIDE_D, class Ex, class SVX>
-PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD, int collPre = -1, volatile uint32_t* collWait = nullptr) {
+PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD, int collPre = -1, volatile uint32_t* collWait = nullptr, const float* cont = nullptr) {
     const int lane = ex.lane;
     const bool front = lane < 2;
     /* Car-level state: with a stride-1 view (the shared-memory staging copy) the four lanes work IN PLACE on the
@@ -187,6 +187,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
         else if (collWait) collDeferred = true;
         else { const bool hit = car_collide(P, T, C, lane, 4); if (!ex.all(!hit)) c.collisionFlag = 1; }
     }
+    const bool freshContacts = (c.physFrame & 1) != 0;
     c.physFrame++;
     /* ---------------- dWorldStep: one joint group per lane ---------------- */
     PD_PHASE(X, 8);
@@ -216,7 +217,15 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     for (int k = 0; k < 6; ++k) b6[k] = ex.sum(b6[k]);
     schur_add_chassis(S21, C);
     float z[6];
-    solve6(S21, b6, z);
+    if (cont && reinterpret_cast<const int*>(cont)[0] > 0) {      /* live contact joints (rare): every lane of the quad solves the same small system */
+        float life = c.lifeLeft;
+        float dmg[5] = {c.damageZone0, c.damageZone1, c.damageZone2, c.damageZone3, c.damageZone4};
+        contacts_solve(P, cont, C, dC, S21, b6, h, freshContacts, life, dmg, z);
+        X.newDamage = fabsf(dmg[0] - c.damageZone0) > 0.001f || fabsf(dmg[1] - c.damageZone1) > 0.001f || fabsf(dmg[2] - c.damageZone2) > 0.001f || fabsf(dmg[3] - c.damageZone3) > 0.001f || fabsf(dmg[4] - c.damageZone4) > 0.001f;
+        ex.sync();
+        c.lifeLeft = life; c.damageZone0 = dmg[0]; c.damageZone1 = dmg[1]; c.damageZone2 = dmg[2]; c.damageZone3 = dmg[3]; c.damageZone4 = dmg[4];
+        ex.sync();
+    } else solve6(S21, b6, z);
     PD_PHASE(X, 11);
     float cfA[6], cfB[6];
     if (front) strut_backsolve(GS, z, cfA, cfB); else single_backsolve(G1, z, cfA);

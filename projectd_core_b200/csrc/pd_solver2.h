@@ -381,7 +381,8 @@ PD_HD void single_backsolve(const SingleSys& G, const float* z, float* cfA) {
 }
 
 /* dWorldStep for the car's island, one thread doing the four groups one after the other (thread-per-car kernel, host build) */
-PD_HDN void world_step2(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h) {
+PD_HDN void contacts_solve(const PdCarParams& P, const float* __restrict__ cont, const Body& C, const BodyDyn& dC, const float* __restrict__ S21, const float* __restrict__ b6, float h, bool fresh, float& lifeLeft, float* __restrict__ dmg, float* __restrict__ z);   /* pd_contacts.h */
+PD_HDN void world_step2(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h, const float* cont, bool freshContacts, float& lifeLeft, float* dmg) {
     const float hinv = 1.0f / h;
     BodyDyn dyn[PD_NUM_BODIES];
     for (int i = 0; i < PD_NUM_BODIES; ++i) body_dyn(b[i], P.gravityY, h, dyn[i]);
@@ -401,7 +402,8 @@ PD_HDN void world_step2(const PdCarParams& P, Body* b, const V3* steerAnchor1, c
     { SingleSys GA; GA.R = RA; single_rows_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, GA, cfm); single_factor(GA, cfm, dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6); }
     schur_add_chassis(S21, C);
     float z[6];
-    solve6(S21, b6, z);
+    if (cont && reinterpret_cast<const int*>(cont)[0] > 0) contacts_solve(P, cont, C, dyn[PD_BODY_CHASSIS], S21, b6, h, freshContacts, lifeLeft, dmg, z);   /* live contact joints: rows on the chassis */
+    else solve6(S21, b6, z);
     float cfA[6], cfB[6];
     { SingleSys GT; GT.R = RT; single_backsolve(GT, z, cfA); apply_update(b[PD_BODY_TANK], dyn[PD_BODY_TANK], cfA, h); }
     PD_NOUNROLL

@@ -5,7 +5,7 @@
  */
 #pragma once
 #include "pd_solver2.h"
-#include "pd_collide.h"
+#include "pd_contacts.h"
 #include "../../include/pd_batch.h"
 
 namespace pd {
@@ -107,6 +107,7 @@ template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, con
     Tk.fr.ax = C.fr.ax; Tk.fr.ay = C.fr.ay; Tk.fr.az = C.fr.az; Tk.q = C.q;
     /* Car::reset (Car.cpp:385-410) */
     c.waterT = 60; c.fuel = P.requestedFuel;
+    c.damageZone0 = 0; c.damageZone1 = 0; c.damageZone2 = 0; c.damageZone3 = 0; c.damageZone4 = 0;      /* Car.cpp:403-407 */
     c.collisionFlag = 0; c.outOfTrackFlag = 0;
     c.lastTrackPointTimestamp = (float)physicsTime;
     c.nearestTrackPointId = 0; c.oldTrackPointId = 0; c.splinePointId = 0; c.trackLocation = 0; c.oldTrackLocation = 0;
@@ -209,7 +210,7 @@ PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, 
         /* validateDrift */
         bool bInvalid = true; int nDirty = 0;
         for (int w = 0; w < 4; ++w) { const int s = X.wl[w].surfaceId; if (s >= 0 && T.surfaces[s].dirtAdditiveK > 0.001f) nDirty++; }
-        if (nDirty <= 2) { if ((c.speed * 3.6f) >= 20.0f) { if (c.currentGear) bInvalid = false; } }
+        if (nDirty <= 2) { if ((c.speed * 3.6f) >= 20.0f) { if (!X.newDamage && c.currentGear) bInvalid = false; } }      /* bDamage: a damage zone rose this tick (ScoringSystem.cpp:359-368) */
         if (bInvalid) c.driftInvalid = 1;
         const float fBeta = fabsf(beta_rad(C));
         const float fSpeedKmh = c.speed * 3.6f;
@@ -275,7 +276,7 @@ PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, 
 }
 
 /* the tick */
-template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch, float* scratchD, int collPre = -1) {
+template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch, float* scratchD, int collPre = -1, const float* cont = nullptr) {
     CarS cLocal; CarS* cp = &cLocal;
     if constexpr (sv_traits<SVX>::in_place) cp = car_in_place(sv); else load_car(sv, cLocal);
     CarCtx X(*cp); X.dt = dt; X.time = physicsTime;
@@ -385,9 +386,13 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
     /* ---------------- physics->step(dt): collisionStep (odd frames: car vs static meshes), then dWorldStep ---------------- */
     /* collPre: the answer of k_collide for this tick's start pose (0 / 1), or -1 = not computed: test here */
     if (c.physFrame & 1) { if (collPre >= 0 ? (collPre != 0) : car_collide(P, T, C, 0, 1)) c.collisionFlag = 1; }
+    const bool freshContacts = (c.physFrame & 1) != 0;       /* contact joints made by this frame's collisionStep (odd) or left over from the last one (even) */
     c.physFrame++;
 #if PD_SOLVER2
-    world_step2(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt);
+    float dmg[5] = {c.damageZone0, c.damageZone1, c.damageZone2, c.damageZone3, c.damageZone4};
+    world_step2(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, cont, freshContacts, c.lifeLeft, dmg);
+    X.newDamage = fabsf(dmg[0] - c.damageZone0) > 0.001f || fabsf(dmg[1] - c.damageZone1) > 0.001f || fabsf(dmg[2] - c.damageZone2) > 0.001f || fabsf(dmg[3] - c.damageZone3) > 0.001f || fabsf(dmg[4] - c.damageZone4) > 0.001f;
+    c.damageZone0 = dmg[0]; c.damageZone1 = dmg[1]; c.damageZone2 = dmg[2]; c.damageZone3 = dmg[3]; c.damageZone4 = dmg[4];
 #else
     world_step<STRIDE, STRIDE_D>(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, scratch, scratchD);
 #endif

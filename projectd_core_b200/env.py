@@ -22,6 +22,7 @@ def configure_like_env(batch, car_model="ks_toyota_ae86_drift", auto_clutch=True
     """Configure a Batch the way ProjectDEnv.__init__ configures its simulator (projectd_env.py:118-136): assists, the
     car's tune table, the scoring variables."""
     batch.set_assists(auto_clutch, auto_shift, auto_blip)
+    batch.set_collision_response(not BatchedProjectDEnv.terminate_on_hit)        # as BatchedProjectDEnv does for an env that terminates on hit
     for name, value in BatchedProjectDEnv.car_tunes.get(car_model, {}).items():
         batch.set_tune(name, value)
     for name, value in BatchedProjectDEnv.scoring_vars.items():
@@ -55,6 +56,7 @@ class BatchedProjectDEnv:
     terminate_low_reward = -200.0
     stuck_timeout = 5.0
 
+    collision_response = None   # None: on unless terminate_on_hit (the terminal tick then shows the flag but not the bounce); True / False: forced
     teleport_mode = 0   # 0:Start, 1:Nearest, 2:Random
     autoreset_mode = 0  # 0: a finished env is reset inside the step that finished it (SB3-style VecEnv, 3 launches per step);
                         # 1: at the following step, whose action is ignored (gymnasium >= 1.0 VectorEnv; 1 launch per step)
@@ -100,6 +102,9 @@ class BatchedProjectDEnv:
                          terminate_on_hit=int(self.terminate_on_hit), terminate_off_track=int(self.terminate_off_track),
                          terminate_when_stuck=int(self.terminate_when_stuck), smooth_controls=int(self.smooth_controls),
                          clutch=0.0 if self.auto_clutch else 1.0, requested_gear=-1 if self.auto_shift else 2)
+        # collision response (contact joints): needed when an env lives on after a hit; an env that terminates on hit only needs
+        # the flag, and the detection then rides inside the tick kernel (one launch per step)
+        b.set_collision_response(self.collision_response if self.collision_response is not None else not self.terminate_on_hit)
         import torch
         self.device = torch.device("cuda", device)
         # stream ordering: the batch launches on its own non-blocking stream; every step makes that stream wait for the caller's

@@ -36,7 +36,7 @@ def scripted(t):
 def main():
     assert pdref.available(), "build the oracle first: make -C oracle && make -C oracle content"
     out = {}
-    r = pdref.RefSim()
+    r = pdref.RefSim(); r.set_collision_response(False)     # fixtures of the CPU tier: detection only (the host build of the kernels has no contact generator; the response is tested on the GPU, live against the oracle)
     out["params"] = r.params_bytes()
     ti = np.zeros(12, np.uint32); r.L.pdref_get_track_info(r.h, ti.ctypes.data); out["track_info"] = ti
 
@@ -56,7 +56,7 @@ def main():
     rng = np.random.default_rng(20261017)
     before, after, ptime = [], [], []
     for drive in range(6):
-        s = pdref.RefSim(); s.teleport_spline(drive / 6.0)
+        s = pdref.RefSim(); s.set_collision_response(False); s.teleport_spline(drive / 6.0)
         keep = set(rng.choice(1500, 40, replace=False).tolist()) | {0, 1, 2}
         for t in range(1500):
             steer = 0.5 * math.sin(2 * math.pi * t / (400.0 + 100 * drive) + drive)
@@ -111,7 +111,7 @@ def main():
     lay = pdref.Layout()
     bodies = ["chassis", "tank", "hub0", "strut0", "hub1", "strut1", "axle"]
     cb, cf, ct = [], [], []
-    s = pdref.RefSim()
+    s = pdref.RefSim(); s.set_collision_response(False)
     for case in range(600):
         if case % 20 == 0:
             s.teleport_spline(float(rng.uniform(0, 1)))

@@ -19,6 +19,7 @@ _BODIES = ["chassis", "tank", "hub0", "strut0", "hub1", "strut1", "axle"]
 def make_env_like(batch):
     """Configure a Batch the way pyprojectd/projectd_env.py:118-136 configures its simulator."""
     batch.set_assists(True, True, True)
+    batch.set_collision_response(True)
     for k, v in pdref.ENV_TUNES.items():
         batch.set_tune(k, v)
     for k, v in pdref.ENV_SCORING.items():

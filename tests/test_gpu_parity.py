@@ -1,6 +1,7 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI (libpd_b200.so), against the oracle
 (the reference's own Car/Sim/Core sources + restated ODE) on identical states and inputs."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -603,13 +604,15 @@ def test_tunes_raw_and_unsupported(oracle):
     """setCarTune clamps / scales through the spinner, setCarRawTune writes the raw value (SetupManager.cpp:276-288,394-399);
     per-wheel front suspension tunes are live; reference variables this build cannot honour fail loudly."""
     from projectd_core_b200 import Batch, PdError
-    b = Batch(oracle.BASE_PATH, n_envs=2, device=0)
-    r = oracle.RefSim(env_setup=False)
+    b = _batch(oracle, 2)
+    r = oracle.RefSim()                 # same env-style set-up on both sides (the reference's scoring variables are process-global)
+    before = b.params_bytes().copy()
     for name, val in (("FRONT_BIAS", 55.0), ("SPRING_RATE_LF", 30.0), ("DAMP_BUMP_RF", 2500.0), ("CAMBER_LF", -20.0), ("TOE_OUT_RF", 12.0),
                       ("ROD_LENGTH_LF", 50.0), ("ARB_FRONT", 12000.0), ("INTERNAL_GEAR_2", 3.2), ("WING_1", 3.0)):
         b.set_tune(name, val); r.L.pdref_set_tune(r.h, name.encode(), val)
     ref = r.params_bytes(); mine = b.params_bytes()[: len(ref)]
     assert np.array_equal(mine, ref), np.nonzero(mine != ref)[0][:20]
+    assert (b.params_bytes() != before).sum() >= 20, "the tunes must really have changed the parameter block"
     b3 = Batch(oracle.BASE_PATH, n_envs=2, device=0); b3.set_raw_tune("FRONT_BIAS", 0.61)
     b4 = Batch(oracle.BASE_PATH, n_envs=2, device=0); b4.set_tune("FRONT_BIAS", 61.0)
     assert np.array_equal(b3.params_bytes(), b4.params_bytes())
@@ -617,3 +620,142 @@ def test_tunes_raw_and_unsupported(oracle):
         with pytest.raises(PdError):
             b.set_tune(name, 1.0)
     b.set_tune("NO_SUCH_VARIABLE", 1.0)        # unknown to the reference as well: ignored there, ignored here
+
+
+def _wall_approach_states(oracle, lay, n):
+    """n oracle states a few ticks before a car first touches a wall (different start points / steering), found by driving."""
+    key = ("wall", n)
+    if key in _WALL_CACHE:
+        return _WALL_CACHE[key]
+    out = []
+    k = 0
+    while len(out) < n and k < 4 * n:
+        r = oracle.RefSim(); r.set_collision_response(True)
+        r.teleport_spline(0.05 + 0.9 * ((k * 0.37) % 1.0))
+        steer = (0.25 if k % 2 else -0.25) * (1 + 0.2 * (k % 3)); gas = 0.7 + 0.1 * (k % 3)
+        hist = []
+        for t in range(2200):
+            r.set_controls(steer=steer, gas=gas)
+            hist.append((r.state().copy(), r.time()))
+            r.step()
+            if lay.get(r.state(), "car.collisionFlag") and len(r.contacts()) > 0:
+                rec, tm = hist[max(0, len(hist) - 12)]
+                out.append((rec, tm, steer, gas))
+                break
+        r.close(); k += 1
+    _WALL_CACHE[key] = out
+    return out
+
+
+_WALL_CACHE = {}
+
+
+@pytest.mark.parametrize("kernel", ["k_tick_quad<4>", "k_tick"])
+def test_collision_response_tracks_oracle(oracle, lay, kernel, monkeypatch):
+    """SURVEY.md A14 response: cars that run into walls with auto-teleport off.  (a) single tick from identical states on the odd
+    frames where the contact joints are made: same contact set (count, kind; positions / normals / depths to 1e-4) and the
+    state within the single-tick rule; (b) one second free running through the impact and the slide along the wall: the GPU car
+    stays with the oracle's (bound 15 cm / 3 deg after the impact; the oracle's car bounces off instead of driving through)."""
+    _select_kernel(monkeypatch, kernel)
+    n = 16
+    starts = _wall_approach_states(oracle, lay, n)
+    assert len(starts) == n
+    b = _batch(oracle, n)
+    assert b.tick_kernel_instance() == kernel
+    refs = [oracle.RefSim() for _ in range(n)]
+    for r, (rec, tm, steer, gas) in zip(refs, starts):
+        r.set_collision_response(True); r.set_state(rec); r.set_time(0.0); r.set_controls(steer=steer, gas=gas)
+    # (a) identical states, 60 ticks around the first impact
+    ncont = 0; nodd = 0
+    for t in range(60):
+        before = [r.state() for r in refs]
+        tb = refs[0].time()
+        b.restore(np.stack(before, axis=1)); b.set_time(tb)
+        b.step(DT, 1)
+        out = b.snapshot()
+        for i, r in enumerate(refs):
+            odd = lay.get(before[i], "car.physFrame") & 1
+            live = r.contacts() if not odd else None          # joints that stay alive for this (even) frame in the free-running oracle
+            r.step()
+            ref = r.state()
+            if odd:
+                nodd += 1
+                want = r.contacts(); got = b.contacts(i)
+                assert len(got) == min(len(want), 8), (t, i, got, want)
+                if len(want):
+                    ncont += 1
+                    assert np.array_equal(got[:, 7], want[:len(got), 7])
+                    assert np.abs(got[:, :7] - want[:len(got), :7]).max() <= 1e-4 * max(1.0, float(np.abs(want[:, :3]).max())), (t, i, got, want)
+                bad, w = compare_records(lay, out[:, i], ref, tol=1e-4)
+                if bad:
+                    left = arbitrate(oracle, lay, "driftplayground", before[i], tb, ref, bad)
+                    # the arbiter's oracle run starts without live joints too (a restored state has none), as the GPU's does
+                    assert not left, (t, i, left[:4])
+    assert ncont >= n, "the approach states must lead into contacts (%d contact frames of %d odd frames)" % (ncont, nodd)
+    # (b) one second free running from the approach states
+    for r, (rec, tm, steer, gas) in zip(refs, starts):
+        r.set_state(rec); r.set_time(0.0); r.set_controls(steer=steer, gas=gas)
+    b.restore(np.stack([s[0] for s in starts], axis=1)); b.set_time(0.0)
+    ctl = np.zeros((n, 5), np.float32)
+    for i, s in enumerate(starts):
+        ctl[i, 0] = s[2]; ctl[i, 4] = s[3]
+    hit_ticks = 0
+    for t in range(333):
+        for r in refs:
+            r.step()
+        b.set_controls(ctl, None, smooth=True)
+        b.step(DT, 1)
+        hit_ticks += sum(1 for r in refs if len(r.contacts()) > 0)
+    out = b.snapshot()
+    assert hit_ticks >= 20 * n, "the cars must really spend time in contact (%d car-ticks)" % hit_ticks
+    worst_p = worst_a = 0.0
+    for i, r in enumerate(refs):
+        ref = r.state()
+        dp = [lay.get(out[:, i], "chassis." + k) - lay.get(ref, "chassis." + k) for k in ("px", "py", "pz")]
+        dq = [lay.get(out[:, i], "chassis." + k) - lay.get(ref, "chassis." + k) for k in ("qw", "qx", "qy", "qz")]
+        worst_p = max(worst_p, math.sqrt(sum(d * d for d in dp))); worst_a = max(worst_a, 2 * math.sqrt(sum(d * d for d in dq)))
+    print("collision response, 1 s free run: worst position %.4f m, heading %.3f deg" % (worst_p, math.degrees(worst_a)))
+    # measured on B200: 9.5 cm / 2.3 deg worst over 16 impacts (a wall impact amplifies round-off like any stiff event)
+    assert worst_p <= 0.15 and worst_a <= math.radians(3.0), (worst_p, math.degrees(worst_a))
+
+
+@pytest.mark.parametrize("track", ["driftplayground", "yamanashi_short", "ebisu_touge", "euphoria_hillside_park"])
+def test_compute_fat_points_matches_shipped_spline_cache(oracle, track):
+    """SURVEY.md N2: Track::computeFatPoints + computeSideLocation (Sim/Track.cpp:366-467) as batch ray casting on the GPU,
+    against the reference-held spline.cache of every track that ships surfaces.bin -- a known-answer test for the general
+    (slanted) rays of the side traces (up to 1000 dependent rays per point and side), not just the vertical ones."""
+    from projectd_core_b200.binding import compute_fat_points
+    base = oracle.BASE_PATH + "/content/tracks/%s/" % track
+    want = np.fromfile(base + "spline.cache", dtype=np.float32).reshape(-1, 15)
+    got = compute_fat_points(oracle.BASE_PATH, track)
+    assert got.shape == want.shape
+    err_best = np.abs(got[:, 0:3] - want[:, 0:3]).max(axis=1)
+    err_side = np.maximum(np.abs(got[:, 3:6] - want[:, 3:6]).max(axis=1), np.abs(got[:, 6:9] - want[:, 6:9]).max(axis=1))
+    err_dir = np.abs(got[:, 12:15] - want[:, 12:15]).max(axis=1)
+    print("%s: %d points; best max %.2e; sides: max %.3f m, %d of %d points beyond 2 cm; forwardDir max %.2e" % (track, len(want), err_best.max(), err_side.max(), int((err_side > 0.02).sum()), len(want), err_dir.max()))
+    # forwardDir: identical except at the LAST point, where the shipped caches hold the wrap-around direction of an older
+    # computeFatPoints (the commented-out variant at Track.cpp:397-400): a few 1e-3 there
+    assert err_best.max() <= 1e-4 and err_dir[:-1].max() <= 1e-5 and err_dir[-1] <= 2e-2
+    # a side trace stops at the first ray whose hit breaks the continuity rules: one trace step (1 cm) of slack, and a few points
+    # where ODE's any-hit-per-mesh ray and the closest-hit ray used here see different triangles at an overlap of meshes
+    assert (err_side > 0.02).mean() <= 0.02, (int((err_side > 0.02).sum()), len(want))
+    assert np.abs(got[:, 9:12] - 0.5 * (got[:, 3:6] + got[:, 6:9])).max() <= 1e-5
+
+
+def test_track_without_spline_cache_loads(oracle, tmp_path):
+    """A track whose spline.cache is missing loads anyway: pd_create regenerates the fat points on the GPU."""
+    import shutil
+    from projectd_core_b200 import Batch
+    base = tmp_path / "base"
+    shutil.copytree(oracle.BASE_PATH, base)
+    os.remove(base / "content" / "tracks" / "driftplayground" / "spline.cache")
+    b = make_env_like(Batch(str(base), n_envs=8, device=0))
+    ref = _batch(oracle, 8)
+    assert b.track_info()["nFatPoints"] == ref.track_info()["nFatPoints"]
+    b.teleport_spline(np.linspace(0, 0.9, 8)); ref.teleport_spline(np.linspace(0, 0.9, 8))
+    b.step(DT, 50); ref.step(DT, 50)
+    sa, sb = b.snapshot(), ref.snapshot()
+    lay = oracle.Layout()
+    for i in range(8):
+        bad, w = compare_records(lay, sa[:, i], sb[:, i], tol=1e-3)
+        assert not [x for x in bad if math.isinf(x[3])], bad[:5]

@@ -14,7 +14,7 @@ DT = 1.0 / 333.0
 
 
 def test_golden_file_shape(golden):
-    lay_words = 628
+    lay_words = 634
     assert golden["traj_state"].shape == (41, lay_words)
     assert golden["pair_before"].shape == golden["pair_after"].shape and golden["pair_before"].shape[1] == lay_words
     assert golden["params"].size == 13464
