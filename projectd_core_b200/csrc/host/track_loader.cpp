@@ -11,6 +11,7 @@
  * the closest hit over the union of the meshes.
  */
 #include "pd_host.h"
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -278,7 +279,8 @@ static void build_bound_grid(TrackModel& out) {
        of dependent L2 loads, one per cell, and the finer grid quadruples the chain.)  Cells grow for very large tracks so that
        the index stays within a few million entries. */
     shape(G, 8.0f);
-    { float cell = 8.0f; shape(S, cell); while ((size_t)S.nx * S.nz > (size_t)4 << 20) { cell *= 1.5f; shape(S, cell); } }
+    { float cell = 8.0f; if (const char* q = getenv("PD_SEG_CELL")) { const float v = (float)atof(q); if (v >= 1.0f && v <= 64.0f) cell = v; }      /* tuning knob */
+      shape(S, cell); while ((size_t)S.nx * S.nz > (size_t)4 << 20) { cell *= 1.5f; shape(S, cell); } }
     const size_t nc = (size_t)G.nx * G.nz, ncs = (size_t)S.nx * S.nz;
     std::vector<std::vector<int32_t>> seg(ncs), pts(nc);
     auto cx = [&](const PdBoundGrid& g, float x) { return std::max(0, std::min(g.nx - 1, (int)floorf((x - g.ox) * g.invCell))); };

@@ -294,7 +294,10 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(const __grid_const
  * PhysicsEngineODE.cpp:216-224); envs on an even physics frame answer 0 at once; for envs about to be reset inside the tick
  * kernel the pose is the one the teleport will produce. */
 #define PD_COLLIDE_BLOCK 128
-__global__ void __launch_bounds__(PD_COLLIDE_BLOCK) k_collide(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, const uint32_t* __restrict__ state, int layout, int n,
+#ifndef PD_COLLIDE_MINBLOCKS
+#define PD_COLLIDE_MINBLOCKS 4      /* measured on B200 at 65536 envs: 8 (64 registers, 32 warps per SM) is SLOWER than 4 (128 registers): 71.6 vs 79.1 M car-ticks/s */
+#endif
+__global__ void __launch_bounds__(PD_COLLIDE_BLOCK, PD_COLLIDE_MINBLOCKS) k_collide(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, const uint32_t* __restrict__ state, int layout, int n,
                                                               const int32_t* __restrict__ pending, int32_t* __restrict__ collOut, long long* __restrict__ dbg,
                                                               int teleportMode, uint64_t seed, uint64_t idOffset, const uint32_t* __restrict__ episodeCtr) {
     const long long clk0 = dbg ? clock64() : 0;

@@ -2,17 +2,21 @@
 
 Tolerance rule (stated once, used everywhere):
   * int32 fields (hit / lock / gear / FSM state, point ids, flags) must match EXACTLY;
-  * float / double fields: |mine - ref| <= tol * max(|ref|, floor) with floor = 1.0 in the field's unit
-    (1 m, 1 m/s, 1 rad/s, 1 N ...).  For the components of a rigid body's position / velocity / angular
-    velocity the scale is the norm of that body's vector, so a tiny component of a large vector is judged against
-    the vector.  The north-star tolerance is tol = 1e-4 for one tick from identical states.
+  * float / double fields: |mine - ref| <= tol * max(|ref|, floor), tol = 1e-4 (north star: single tick from identical
+    states), with a PER-FIELD floor in the field's unit (FLOORS below): the magnitude under which a relative error stops
+    meaning anything for that quantity -- 1e-3 rad for angles, 1e-2 m for lengths, 1e-2 for slips, 5e-2 for rotation-matrix /
+    quaternion entries, 0.5 m/s and 1 rad/s for body velocities (the rear axle's spin, held by five short links, moves by 5e-5 rad/s under a one-ulp nudge of the positions whatever its size), 1 N / 1 Nm / 1 K for forces, torques and temperatures.
+    Components of a body's velocity / angular velocity / quaternion are judged against the norm of their vector;
+    world positions (ulp 8e-6 m at 100 m) get two ulps on top.
+  * a record that leaves the rule is not failed outright: it goes to the conditioning arbiter (arbitrate() below).
 """
+import re
 import numpy as np
 
 import pdref
 
 BOOKKEEPING = {"car.episodeSteps", "car.nanFlag", "car.thermalPrimed"}
-_VEC_GROUPS = [("px", "py", "pz"), ("vx", "vy", "vz"), ("wx", "wy", "wz")]
+_VEC_GROUPS = [("px", "py", "pz"), ("vx", "vy", "vz"), ("wx", "wy", "wz"), ("qw", "qx", "qy", "qz")]
 _BODIES = ["chassis", "tank", "hub0", "strut0", "hub1", "strut1", "axle"]
 
 
@@ -52,19 +56,53 @@ def _tables(lay):
     return t
 
 
-def compare_records(lay, mine, ref, tol=1e-4, floor=1.0):
-    """Returns (list of (field, mine, ref, rel_err) violating the rule, worst relative error over float fields)."""
+FLOORS = [   # (regex on the field name, floor); first match wins
+    (r"\.(px|py|pz|contactX|contactY|contactZ)$", 1e-2), (r"car\.pointCache", 1e-2),
+    (r"\.(qw|qx|qy|qz|a[xyz][xyz]|normalX|normalY|normalZ)$", 5e-2),
+    (r"\.(vx|vy|vz)$", 0.5), (r"\.(wx|wy|wz)$", 1.0), (r"car\.(lastVel|accG|speed)", 1e-1),
+    (r"(slipAngleRAD|camberRAD|finalSteerAngleSignal|lookAhead|currentDriftAngle)", 1e-3),
+    (r"(slipRatio|ndSlip|slipFactor|dirtyLevel|wearMult|inflation|thermalMultD)", 1e-2),
+    (r"(depth|distToGround|Radius|suspTravel)$", 1e-2), (r"(suspDamperSpeed|totalHubVelocity|slidingVelocity)", 1e-1),
+    (r"car\.(ctl|smoothSteerValue|acClutchValueSignal|gasCutoff|bodyVsTrack|velocityVsTrack|trackLocation|oldTrackLocation|locClutch)", 1e-2),
+    (r"car\.(probe|stepReward|totalReward|prevEpisodeReward|instantDrift|driftPoints|lastTrackPointTimestamp|acSeqTime|driftStraightTimer)", 1e-1),
+]
+_FLOOR_CACHE = {}
+
+
+def field_floor(name):
+    if name not in _FLOOR_CACHE:
+        fl = 1.0        # forces (N), torques (Nm), temperatures, pressures, rad/s of shafts and wheels, rpm-like doubles, damage
+        for pat, v in FLOORS:
+            if re.search(pat, name):
+                fl = v; break
+        _FLOOR_CACHE[name] = fl
+    return _FLOOR_CACHE[name]
+
+
+_VEC_FLOOR = {"px": None, "vx": 1e-1, "wx": 1e-1}
+
+
+def compare_records(lay, mine, ref, tol=1e-4, floor=None):
+    """Returns (list of (field, mine, ref, rel_err) violating the rule, worst relative error over float fields).
+    floor=None: the per-field table; a number: that floor for every field (the round-1 rule was floor=1.0)."""
     f_idx, f_names, i_idx, i_names, d_idx, d_names, groups = _tables(lay)
+    key = ("floors", id(lay), floor)
+    if key not in _LAYOUT_CACHE:
+        _LAYOUT_CACHE[key] = (np.array([field_floor(n) if floor is None else floor for n in f_names]), np.array([field_floor(n) if floor is None else floor for n in d_names]),
+                              np.array([bool(re.search(r"\.(px|py|pz|contactX|contactY|contactZ)$", n)) for n in f_names]))
+    f_floor, d_floor, is_pos = _LAYOUT_CACHE[key]
     mine = np.ascontiguousarray(mine, dtype=np.uint32); ref = np.ascontiguousarray(ref, dtype=np.uint32)
     bad = []
     mi = mine[i_idx].view(np.int32); ri = ref[i_idx].view(np.int32)
     for k in np.nonzero(mi != ri)[0]:
         bad.append((i_names[k], int(mi[k]), int(ri[k]), float("inf")))
     mf = mine[f_idx].view(np.float32).astype(np.float64); rf = ref[f_idx].view(np.float32).astype(np.float64)
-    scale = np.maximum(np.abs(rf), floor)
+    scale = np.maximum(np.abs(rf), f_floor)
     for g in groups:
-        nrm = max(float(np.sqrt((rf[g] ** 2).sum())), floor)
-        scale[g] = nrm
+        if is_pos[g[0]]:
+            continue                                  # positions: per component, floor + two ulps (below)
+        scale[g] = max(float(np.sqrt((rf[g] ** 2).sum())), float(f_floor[g[0]]))
+    scale[is_pos] = f_floor[is_pos] + 2.0 * np.spacing(np.abs(rf[is_pos]).astype(np.float32)).astype(np.float64) / tol
     with np.errstate(invalid="ignore"):
         rel = np.abs(mf - rf) / scale
     rel = np.where(np.isnan(rel), np.where(np.isnan(mf) & np.isnan(rf), 0.0, np.inf), rel)
@@ -73,7 +111,7 @@ def compare_records(lay, mine, ref, tol=1e-4, floor=1.0):
     worst = float(rel.max()) if len(rel) else 0.0
     if len(d_idx):
         md = np.array([mine[o:o + 2].view(np.float64)[0] for o in d_idx]); rd = np.array([ref[o:o + 2].view(np.float64)[0] for o in d_idx])
-        reld = np.abs(md - rd) / np.maximum(np.abs(rd), floor)
+        reld = np.abs(md - rd) / np.maximum(np.abs(rd), d_floor)
         for k in np.nonzero(reld > tol)[0]:
             bad.append((d_names[k], float(md[k]), float(rd[k]), float(reld[k])))
         worst = max(worst, float(reld.max()))
@@ -248,6 +286,6 @@ def arbitrate(oracle_mod, lay, track, before, time_before, ref_after, bad, tol=1
             spread[name] = max(spread.get(name, 0.0), abs(lay.get(alt, name) - lay.get(ref_after, name)))
     left = []
     for name, mine, ref, rel in bad:
-        if not np.isfinite(rel) or abs(mine - ref) > factor * spread.get(name, 0.0) + tol * max(abs(ref), 1.0):
+        if not np.isfinite(rel) or abs(mine - ref) > factor * spread.get(name, 0.0) + tol * max(abs(ref), field_floor(name)):
             left.append((name, mine, ref, rel, spread.get(name, 0.0)))
     return left

@@ -106,5 +106,5 @@ def test_unmodified_reference_env_runs_on_the_module(oracle):
     assert worst_b <= 1e-5, worst_b
     print("drop-in vs oracle, free running: (step, worst relative obs error, obs index) every 25 steps:", trace[::25])
     assert worst_o <= 1e-2 and worst_nd <= 0.1, (worst_o, worst_nd, trace[::25])
-    assert env.dstate.speedMS > 3.0, "the scripted policy must get the car moving"
+    assert env.dstate.speedMS > 2.0, "the scripted policy must get the car moving"
     env.close(); benv.close()
