@@ -190,7 +190,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
  * = more warps per car batch, for batches too small to fill the 592 warp schedulers of a B200 otherwise).
  * ONE bulk copy brings the block's records in, the quads work on the shared-memory copy, ONE bulk copy writes them back. */
 template <int CPW>
-__global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+#ifndef PD_QUAD_MINBLOCKS
+#define PD_QUAD_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(PD_QBLOCK + 32, PD_QUAD_MINBLOCKS) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                          const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     constexpr int QCARS = 2 * CPW;          /* cars per block */
     constexpr int QLANES = 8 * CPW;         /* working threads per block = stride of the lane-interleaved solver scratch */

@@ -759,3 +759,31 @@ def test_track_without_spline_cache_loads(oracle, tmp_path):
     for i in range(8):
         bad, w = compare_records(lay, sa[:, i], sb[:, i], tol=1e-3)
         assert not [x for x in bad if math.isinf(x[3])], bad[:5]
+
+
+def test_vector_env_interface(oracle):
+    """the gymnasium VectorEnv face of the batched env (next-step auto-reset): spaces, reset / step signatures,
+    terminal observation on the finishing step, reset observation one step later, truncation bookkeeping."""
+    import torch
+    from projectd_core_b200.vector_env import make_vec
+    n = 128
+    env = make_vec(oracle.BASE_PATH, num_envs=n, device=0, seed=3, teleport_mode=2)
+    assert env.num_envs == n and env.single_observation_space.shape == (24,) and env.single_action_space.shape == (2,)
+    assert env.observation_space.shape == (n, 24) and env.action_space.shape == (n, 2)
+    obs, info = env.reset(seed=5)
+    assert obs.shape == (n, 24) and obs.is_cuda and info == {}
+    seen_done = torch.zeros(n, dtype=torch.bool, device="cuda"); after_reset_ok = 0
+    prev_done = torch.zeros(n, dtype=torch.bool, device="cuda")
+    for t in range(1200):
+        a = torch.rand((n, 2), device="cuda") * 2 - 1
+        obs, rew, term, trunc, info = env.step(a)
+        assert obs.shape == (n, 24) and rew.shape == (n,) and term.dtype == torch.bool and trunc.dtype == torch.bool
+        # the step after a terminal one is the reset step: reward 0, not done, car (nearly) at rest on the track
+        if bool(prev_done.any()):
+            assert float(rew[prev_done].abs().max()) == 0.0 and not bool(term[prev_done].any())
+            assert float(obs[prev_done, 0:3].abs().max()) < 1.0
+            after_reset_ok += int(prev_done.sum())
+        prev_done = term | trunc
+        seen_done |= term
+    assert int(seen_done.sum()) >= n // 16 and after_reset_ok > 0
+    env.close()
