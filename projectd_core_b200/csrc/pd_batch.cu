@@ -190,10 +190,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
  * = more warps per car batch, for batches too small to fill the 592 warp schedulers of a B200 otherwise).
  * ONE bulk copy brings the block's records in, the quads work on the shared-memory copy, ONE bulk copy writes them back. */
 template <int CPW>
-#ifndef PD_QUAD_MINBLOCKS
-#define PD_QUAD_MINBLOCKS 1
+/* registers: left to ptxas (168 with the plain bound).  Measured on B200: capping at 128 (5 blocks per SM) is slower everywhere
+ * (4096 envs 23.7 vs 26.4 M car-ticks/s, 65536 envs 33 vs 52 M); an explicit minimum of 1 block makes ptxas take 255 registers. */
+#ifdef PD_QUAD_MINBLOCKS
+__global__ void __launch_bounds__(PD_QBLOCK + 32, PD_QUAD_MINBLOCKS) k_tick_quad(
+#else
+__global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(
 #endif
-__global__ void __launch_bounds__(PD_QBLOCK + 32, PD_QUAD_MINBLOCKS) k_tick_quad(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+                                                         const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                          const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     constexpr int QCARS = 2 * CPW;          /* cars per block */
     constexpr int QLANES = 8 * CPW;         /* working threads per block = stride of the lane-interleaved solver scratch */

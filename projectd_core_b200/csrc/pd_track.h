@@ -225,8 +225,9 @@ PD_HDN bool probe_walk(const TrackDev& T, float ax, float az, float bx, float bz
     float tmz = dz != 0.0f ? ((G.oz + (iz + (sz > 0 ? 1 : 0)) * G.cell) - az) / dz : FLT_MAX;
     float best = FLT_MAX;
     const float margin = 0.1f;   /* metres: cells are padded by 0.05 m, rounding is far below that */
-    /* (Measured on B200, round 2: fetching the headers of the next 8 cells of the walk in one batch, so that their L2 round trips
-       overlap, changed nothing -- 37.6 k vs 36.3 k cycles for the probe phase; the plain cell-by-cell loop stays.) */
+    /* (Measured on B200, round 2, both without effect on the probe phase -- it is a chain of dependent L2 round trips, one per
+       cell, not arithmetic: (1) fetching the headers of the next 8 cells of the walk in one batch; (2) one padded box per cell and
+       boundary side with a slab test in front of the side's segments, which removes ~3/4 of the segment tests.  The plain loop stays.) */
     for (int guard = 0; guard < 4096; ++guard) {
         const int c = iz * G.nx + ix;
         const int s0 = T.segStart[c], s1 = T.segStart[c + 1];

@@ -7,7 +7,7 @@ import numpy as np, torch
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import pdref
 from projectd_core_b200 import Batch
-from parity_util import make_env_like
+from projectd_core_b200.env import configure_like_env as make_env_like      # the bench configuration: env that terminates on hit -> detection only, collision warp inside the tick kernel
 n = 4096; pre = 2001
 dev = torch.device("cuda", 0)
 b = make_env_like(Batch(pdref.BASE_PATH, n_envs=n, device=0)); b.set_seed(1234, 0); b.teleport_mode(2); b.set_autoreset(1)
