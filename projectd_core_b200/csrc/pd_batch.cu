@@ -530,6 +530,7 @@ struct pd_batch {
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     long long* dClk = nullptr; int nClk = 0;
     int serialSmemPad = 0;            /* tuning knob (env PD_SERIAL_SMEM_PAD, bytes): unused dynamic shared memory per block of k_tick, caps the resident blocks per SM */
+    bool inlineCollide = false;       /* thread-per-car kernel: test collisions inside the tick (env PD_SERIAL_INLINE_COLLIDE=1) instead of k_collide ahead of it */
     bool collWarp = true;             /* quad kernel: collision warp inside the tick kernel (env PD_COLL_WARP=0: k_collide ahead of it instead) */
     bool zeroCopy = true; const void* zcKey[4] = {nullptr, nullptr, nullptr, nullptr}; void* zcDev[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* dColl = nullptr;         /* k_collide's answers for the coming tick */
@@ -620,6 +621,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_QUAD_MAX_ENVS")) b->quadMax = atoi(q);
     if (const char* q = getenv("PD_E2E_ZEROCOPY")) b->zeroCopy = atoi(q) != 0;
     if (const char* q = getenv("PD_COLL_WARP")) b->collWarp = atoi(q) != 0;
+    if (const char* q = getenv("PD_SERIAL_INLINE_COLLIDE")) b->inlineCollide = atoi(q) != 0;
     if (const char* q = getenv("PD_SERIAL_SMEM_PAD")) { b->serialSmemPad = atoi(q); cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); }
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->ownStream = b->stream;
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
@@ -724,6 +726,7 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
         /* with the collision response on, k_collide also GENERATES the contact joints of cars that touch something (it knows the
            start pose, resets included); the tick kernels pick the live joints up at the solve */
         if (oddPossible && b->layout == PD_LAYOUT_RECORDS && b->collWarp && !b->response) collWarp = true;
+        else if (oddPossible && b->layout == PD_LAYOUT_TILED && b->inlineCollide && !b->response) { /* experiment: every thread tests its own car inside k_tick */ }
         else if (oddPossible) {
             k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr,
                                                                                                       io.teleportMode, io.seed, io.idOffset, io.episodeCtr); b->launches++;
