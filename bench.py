@@ -185,7 +185,7 @@ def ours(args):
     n_envs = args.envs if args.envs else (4096 if world == 1 else 65536)
     K, W = args.steps, args.warmup
 
-    b = configure_like_env(Batch(default_base(), n_envs=n_envs, device=dev.index, synthetic_tris=args.synthetic_tris))
+    b = configure_like_env(Batch(default_base(), n_envs=n_envs, device=dev.index, synthetic_tris=args.synthetic_tris, car=args.car))
     env_offset, _ = pdist.shard_range(world * n_envs, rank, world)
     b.set_seed(1234, env_offset)             # RNG keyed by global env id: results do not depend on the sharding
     b.teleport_mode(2)                        # random start positions u ~ U[0,1)
@@ -344,6 +344,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: 4096 at N=1, 65536 at N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--car", default="ks_toyota_ae86_drift", help="car model (BASELINE's configs all use the demo car; the other four bundled cars run the double-wishbone kernel instances)")
     ap.add_argument("--synthetic-tris", type=int, default=0, help="BASELINE configs[3]: generated 20.8 km circuit of about this many triangles instead of driftplayground")
     ap.add_argument("--preroll", type=int, default=1998, help="untimed ticks before the warm-up (brings the rollout to its steady state)")
     args = ap.parse_args()

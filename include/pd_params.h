@@ -20,7 +20,7 @@
 #include "pd_state.h"
 
 #define PD_CURVE_MAX 24
-#define PD_MAX_WINGS 4
+#define PD_MAX_WINGS 6       /* bundled cars: 3 wings + up to 2 fins */
 #define PD_MAX_GEARS 10
 #define PD_AXLE_LINKS 5      /* SuspensionAxle.cpp:50 LINK_COUNT (demo car: 5) */
 #define PD_NUM_SCORING_VARS 21
@@ -73,6 +73,33 @@ typedef struct PdAxle { /* SuspensionAxle x2 sharing Car::rigidAxle (rear of the
     float axleMass, axleInertia[3];
     float torqueReaction;     /* Car::axleTorqueReaction */
 } PdAxle;
+
+/* SuspensionDW (Car/SuspensionDW.cpp:18-195): one hub body held by five distance joints (upper wishbone rear / front, lower
+ * wishbone rear / front, steering or toe rod), spring + damper along the chassis' up axis at the reference point */
+#define PD_DW_LINKS 5
+typedef struct PdDW {
+    float refPoint[3];        /* dataRelToWheel.refPoint == basePosition (chassis frame) */
+    float baseCarSteer[3];    /* baseCarSteerPosition (chassis frame) */
+    float tyreSteer[3];       /* dataRelToWheel.tyreSteer (hub frame) */
+    float rodLength, k, progressiveK, packerRange, bumpStopRate, bumpStopProgressive, bumpStopUp, bumpStopDn;
+    float toeOutLinear, staticCamber, baseCFM;
+    PdDamper damper;
+    PdDBall link[PD_DW_LINKS]; /* joints[0..4]: top rear, top front, bottom rear, bottom front, steer rod (chassis <-> hub) */
+    float hubMass, hubInertia[3];
+} PdDW;
+
+/* Turbo (Car/Turbo.h, Engine.cpp:69-94) */
+#define PD_MAX_TURBOS 3
+typedef struct PdTurbo {
+    float lagDN, lagUP, maxBoost, wastegate, rpmRef, gamma, userSetting;
+    int32_t isAdjustable;
+} PdTurbo;
+
+/* suspension topology = (front == DWB) * 2 + (rear == DWB); front otherwise STRUT, rear otherwise AXLE */
+#define PD_TOPO_STRUT_AXLE 0
+#define PD_TOPO_STRUT_DW   1
+#define PD_TOPO_DW_AXLE    2
+#define PD_TOPO_DW_DW      3
 
 typedef struct PdTyre { /* TyreData + TyreModelData + SCTM + thermal patch data of the active compound */
     /* TyreData */
@@ -145,8 +172,8 @@ enum {
     PD_SV_OffTrackPenalty, PD_SV_GearGrindPenalty, PD_SV_StallPenalty
 };
 
-#define PD_MAX_COLLIDER_VERTS 64
-#define PD_MAX_COLLIDER_TRIS 128
+#define PD_MAX_COLLIDER_VERTS 128     /* bundled cars: 50 .. 113 vertices, 96 .. 178 triangles (indices fit a byte) */
+#define PD_MAX_COLLIDER_TRIS 192
 
 typedef struct PdCarParams {
     /* Car (car.ini) */
@@ -190,6 +217,11 @@ typedef struct PdCarParams {
     uint8_t colliderTris[PD_MAX_COLLIDER_TRIS][4];         /* vertex indices i0, i1, i2, 0 */
     float colliderTriBounds[PD_MAX_COLLIDER_TRIS][6];      /* chassis-local box of each hull triangle, grown by 1e-4: min xyz, max xyz (a filter only) */
     float colliderTriSphere[PD_MAX_COLLIDER_TRIS][4];      /* bounding sphere of each hull triangle: centre xyz, radius grown by 1e-4 (a filter only) */
+    /* the other bundled cars: double-wishbone axles and turbochargers.  dw[w] is filled for the wheels of a DWB
+     * axle (strut[] / axle stay zero for that axle), topology = PD_TOPO_* */
+    int32_t topology, nTurbos;
+    PdDW dw[PD_NUM_WHEELS];
+    PdTurbo turbo[PD_MAX_TURBOS];
 } PdCarParams;
 
 /* ---- track (Sim/Track.cpp) ---- */

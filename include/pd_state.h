@@ -20,7 +20,7 @@
 
 #include <stdint.h>
 
-#define PD_NUM_BODIES   7
+#define PD_NUM_BODIES   8
 #define PD_BODY_CHASSIS 0  /* Car::body              Car/Car.cpp:38        */
 #define PD_BODY_TANK    1  /* Car::fuelTankBody      Car/Car.cpp:39,49-51  */
 #define PD_BODY_HUB0    2  /* SuspensionStrut::hub   (LF)  SuspensionStrut.cpp:132 */
@@ -28,6 +28,11 @@
 #define PD_BODY_HUB1    4  /* (RF) */
 #define PD_BODY_STRUT1  5  /* (RF) */
 #define PD_BODY_AXLE    6  /* Car::rigidAxle         Car/Car.cpp:66, SuspensionAxle.cpp:46 */
+/* cars with double-wishbone suspensions (SuspensionDW::hub, SuspensionDW.cpp:143): a DWB front axle keeps its hubs in the
+ * HUB0 / HUB1 slots (the strut-body slots stay zero), a DWB rear axle keeps its two hubs in slot 6 (instead of the rigid
+ * axle) and slot 7.  Slots a topology does not have are zero in every record and are never touched by its kernels. */
+#define PD_BODY_HUB2    6  /* (LR, DWB rear) */
+#define PD_BODY_HUB3    7  /* (RR, DWB rear) */
 
 #define PD_NUM_WHEELS   4   /* LF, RF, LR, RR (Car/Car.cpp:72) */
 #define PD_THERMAL_STRIPES  3   /* Tyre.cpp:41 thermalModel->init(car, 12, 3) */
@@ -114,7 +119,9 @@
     X(I, physFrame) \
     /* Car::damageZoneLevel[5] (Car.h:204; front, rear, left, right, max): raised by wall contacts in Car::onCollisionCallback \
      * (Car.cpp:980-999), read by ScoringSystem::validateDrift (a tick with new damage invalidates the drift); + 1 pad word */ \
-    X(F, damageZone0) X(F, damageZone1) X(F, damageZone2) X(F, damageZone3) X(F, damageZone4) X(I, carPad)
+    X(F, damageZone0) X(F, damageZone1) X(F, damageZone2) X(F, damageZone3) X(F, damageZone4) X(I, carPad) \
+    /* Turbo::rotation of up to three turbochargers (Turbo.h, Turbo.cpp:11-40) and Engine::status.turboBoost (Engine.cpp:368-384) */ \
+    X(F, turboRot0) X(F, turboRot1) X(F, turboRot2) X(F, turboBoost)
 
 /* ---------------------------------------------------------------------------------------- */
 #define PD__W_F 1
@@ -138,7 +145,7 @@
 #define PD_STATE_WORDS   (PD_OFF_CAR + PD_CAR_WORDS)
 /* record stride of the array-of-records device layout: a multiple of 4 words (16-byte bulk copies) whose value
  * mod 32 (= 20) spreads the same word of 8 consecutive records over 8 different shared-memory bank groups */
-#define PD_STATE_STRIDE  636
+#define PD_STATE_STRIDE  660
 
 /* per-field word offsets inside their group: PD_BODY_o_px, PD_TYRE_o_load, PD_CAR_o_fuel ... */
 #define PD__ENUM_B(kind, name) PD_BODY_o_##name, PD_BODY_e_##name = PD_BODY_o_##name + PD__W_##kind - 1,

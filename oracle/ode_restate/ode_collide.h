@@ -33,6 +33,7 @@
  */
 #pragma once
 #include <cmath>
+#include <vector>
 
 namespace oder {
 
@@ -114,7 +115,7 @@ static inline void contact_offer(ContactPoint* slot, bool* used, int key, CV3 po
 }
 /* the `maxOut` deepest used slots, deepest first, ties by lower key */
 static inline int contact_select(const ContactPoint* slot, const bool* used, int nSlots, ContactPoint* out, int maxOut) {
-    int n = 0; bool taken[64] = {false};
+    int n = 0; std::vector<char> taken((size_t)(nSlots > 0 ? nSlots : 1), 0);
     for (int r = 0; r < maxOut; ++r) {
         int best = -1;
         for (int k = 0; k < nSlots; ++k) if (used[k] && !taken[k] && (best < 0 || slot[k].depth > slot[best].depth)) best = k;

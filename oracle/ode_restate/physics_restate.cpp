@@ -443,9 +443,9 @@ struct RestateEngine : public IPhysicsEngine, std::enable_shared_from_this<Resta
                 if (hit) fire(rb, &cm, &m, oder::cv(b.pos[0], b.pos[1], b.pos[2]));     /* one callback per mesh pair is enough for the flag */
             }
             if (responseEnabled && firstWall) {
-                bool usedArr[64]; for (size_t j = 0; j < 64; ++j) usedArr[j] = j < nv && vusedC[j] != 0;
+                std::unique_ptr<bool[]> usedArr(new bool[nv ? nv : 1]); for (size_t j = 0; j < nv; ++j) usedArr[j] = vusedC[j] != 0;      /* every hull vertex is a slot (bundled cars: 50 .. 113 vertices) */
                 oder::ContactPoint out[4];
-                const int nOut = oder::contact_select(vslot.data(), usedArr, (int)std::min<size_t>(nv, 64), out, 4);
+                const int nOut = oder::contact_select(vslot.data(), usedArr.get(), (int)nv, out, 4);
                 addContacts(rb, out, nOut, &cm, firstWall);
             }
         }

@@ -152,7 +152,7 @@ class Layout:
         self.car = _parse_fields(text, "PD_CAR_FIELDS")
         self.fields = {}  # name -> (offset, kind)
         off = 0
-        bnames = ["chassis", "tank", "hub0", "strut0", "hub1", "strut1", "axle"]
+        bnames = ["chassis", "tank", "hub0", "strut0", "hub1", "strut1", "axle", "hub3"]      # slot 6 = rigid axle or the LR hub of a DWB rear axle, slot 7 = its RR hub
         for b in bnames:
             for k, n in self.body:
                 self.fields["%s.%s" % (b, n)] = (off, k); off += W[k]

@@ -41,16 +41,22 @@ struct RefSim {
     std::string err;
 };
 
+static bool front_dw(Car* c) { return c->suspensionTypeF == SuspensionType::DoubleWishbone; }
+static bool rear_dw(Car* c) { return c->suspensionTypeR == SuspensionType::DoubleWishbone; }
+/* the body kept in slot b of the record (include/pd_state.h), or null when this car's topology has none there */
 static oder::Body* body_of(RefSim* h, int b) {
     Car* c = h->car;
     switch (b) {
     case PD_BODY_CHASSIS: return pdref_body(c->body.get());
     case PD_BODY_TANK: return pdref_body(c->fuelTankBody.get());
-    case PD_BODY_HUB0: return pdref_body(static_cast<SuspensionStrut*>(c->suspensions[0])->hub.get());
-    case PD_BODY_STRUT0: return pdref_body(static_cast<SuspensionStrut*>(c->suspensions[0])->strutBody.get());
-    case PD_BODY_HUB1: return pdref_body(static_cast<SuspensionStrut*>(c->suspensions[1])->hub.get());
-    case PD_BODY_STRUT1: return pdref_body(static_cast<SuspensionStrut*>(c->suspensions[1])->strutBody.get());
-    case PD_BODY_AXLE: return pdref_body(c->rigidAxle.get());
+    case PD_BODY_HUB0: case PD_BODY_HUB1: {
+        ISuspension* s = c->suspensions[(b - PD_BODY_HUB0) / 2];
+        return front_dw(c) ? pdref_body(static_cast<SuspensionDW*>(s)->hub.get()) : pdref_body(static_cast<SuspensionStrut*>(s)->hub.get());
+    }
+    case PD_BODY_STRUT0: case PD_BODY_STRUT1:
+        return front_dw(c) ? nullptr : pdref_body(static_cast<SuspensionStrut*>(c->suspensions[(b - PD_BODY_STRUT0) / 2])->strutBody.get());
+    case PD_BODY_AXLE: return rear_dw(c) ? pdref_body(static_cast<SuspensionDW*>(c->suspensions[2])->hub.get()) : pdref_body(c->rigidAxle.get());
+    case PD_BODY_HUB3: return rear_dw(c) ? pdref_body(static_cast<SuspensionDW*>(c->suspensions[3])->hub.get()) : nullptr;
     }
     return nullptr;
 }
@@ -147,6 +153,7 @@ void pdref_get_state(void* hv, uint32_t* r) {
     memset(r, 0, sizeof(uint32_t) * PD_STATE_WORDS);
     for (int b = 0; b < PD_NUM_BODIES; ++b) {
         oder::Body* ob = body_of(h, b); int o = PD_OFF_BODY(b);
+        if (!ob) continue;
         putF(r, o + PD_BODY_o_px, ob->pos[0]); putF(r, o + PD_BODY_o_py, ob->pos[1]); putF(r, o + PD_BODY_o_pz, ob->pos[2]);
         putF(r, o + PD_BODY_o_qw, ob->q[0]); putF(r, o + PD_BODY_o_qx, ob->q[1]); putF(r, o + PD_BODY_o_qy, ob->q[2]); putF(r, o + PD_BODY_o_qz, ob->q[3]);
         putF(r, o + PD_BODY_o_vx, ob->lvel[0]); putF(r, o + PD_BODY_o_vy, ob->lvel[1]); putF(r, o + PD_BODY_o_vz, ob->lvel[2]);
@@ -230,6 +237,7 @@ void pdref_get_state(void* hv, uint32_t* r) {
         CI(episodeSteps, 0); CI(nanFlag, 0);
         CI(thermalPrimed, c->tyres[0]->thermalModel->patches[5].inputT == 0.0f ? 1 : 0);
         CI(physFrame, (int)pdref_get_frame(h->sim->physics.get()));
+        { const auto& tb = e->turbos; if (tb.size() > 0) CF(turboRot0, tb[0]->rotation); if (tb.size() > 1) CF(turboRot1, tb[1]->rotation); if (tb.size() > 2) CF(turboRot2, tb[2]->rotation); CF(turboBoost, e->status.turboBoost); }
         CF(damageZone0, c->damageZoneLevel[0]); CF(damageZone1, c->damageZoneLevel[1]); CF(damageZone2, c->damageZoneLevel[2]); CF(damageZone3, c->damageZoneLevel[3]); CF(damageZone4, c->damageZoneLevel[4]);
         for (size_t i = 0; i < c->probeHits.size() && i < PD_MAX_PROBES; ++i) putF(r, PD_OFF_PROBES + (int)i, c->probeHits[i]);
         for (size_t i = 0; i < c->lookAhead.size() && i < PD_LOOKAHEAD; ++i) putF(r, PD_OFF_LOOKAHEAD + (int)i, c->lookAhead[i]);
@@ -245,6 +253,7 @@ void pdref_set_state(void* hv, const uint32_t* r) {
     pdref_engine_clear_contacts(h->sim->physics.get());     /* contact joints are not part of the record: a restored state has none alive */
     for (int b = 0; b < PD_NUM_BODIES; ++b) {
         oder::Body* ob = body_of(h, b); int o = PD_OFF_BODY(b);
+        if (!ob) continue;
         for (int k = 0; k < 3; ++k) ob->pos[k] = getF(r, o + PD_BODY_o_px + k);
         for (int k = 0; k < 4; ++k) ob->q[k] = getF(r, o + PD_BODY_o_qw + k);
         ob->R[0] = getF(r, o + PD_BODY_o_axx); ob->R[3] = getF(r, o + PD_BODY_o_axy); ob->R[6] = getF(r, o + PD_BODY_o_axz);
@@ -292,6 +301,7 @@ void pdref_set_state(void* hv, const uint32_t* r) {
         c->fuel = CD(fuel); c->sleepingFrames = CI(sleepingFrames); c->water->t = CF(waterT); c->speed.value = CF(speed);
         c->collisionFlag = CI(collisionFlag) != 0; c->outOfTrackFlag = CI(outOfTrackFlag) != 0;
         pdref_set_frame(h->sim->physics.get(), (unsigned int)CI(physFrame));
+        { auto& tb = e->turbos; if (tb.size() > 0) tb[0]->rotation = CF(turboRot0); if (tb.size() > 1) tb[1]->rotation = CF(turboRot1); if (tb.size() > 2) tb[2]->rotation = CF(turboRot2); e->status.turboBoost = CF(turboBoost); }
         c->damageZoneLevel[0] = CF(damageZone0); c->damageZoneLevel[1] = CF(damageZone1); c->damageZoneLevel[2] = CF(damageZone2); c->damageZoneLevel[3] = CF(damageZone3); c->damageZoneLevel[4] = CF(damageZone4);
         for (int i = 0; i < 5; ++i) c->oldDamageZoneLevel[i] = c->damageZoneLevel[i];        /* Car::postStep leaves them equal (Car.cpp:706-707) */
         c->nearestTrackPointId = CI(nearestTrackPointId); c->oldTrackPointId = CI(oldTrackPointId); c->splinePointId = CI(splinePointId);
@@ -343,7 +353,20 @@ void pdref_get_params(void* hv, PdCarParams* P) {
     P->waterTmass = c->water->tmass; P->waterCoolSpeedK = c->water->coolSpeedK; P->waterCoolFactor = c->water->coolFactor; P->waterHeatFactor = c->water->heatFactor;
     P->baseCarHeight = c->getBaseCarHeight();
     { oder::Joint* j = pdref_joint(c->fuelTankJoint.get()); for (int k = 0; k < 3; ++k) P->tankOffset[k] = j->offset[k]; for (int k = 0; k < 4; ++k) P->tankQrel[k] = j->qrel[k]; }
-    for (int i = 0; i < 2; ++i) {
+    P->topology = (front_dw(c) ? 2 : 0) + (rear_dw(c) ? 1 : 0);
+    for (int i = 0; i < 4; ++i) {
+        if (!(i < 2 ? front_dw(c) : rear_dw(c))) continue;
+        SuspensionDW* s = static_cast<SuspensionDW*>(c->suspensions[i]); PdDW& d = P->dw[i];
+        v3(d.refPoint, s->dataRelToWheel.refPoint); v3(d.baseCarSteer, s->baseCarSteerPosition); v3(d.tyreSteer, s->dataRelToWheel.tyreSteer);
+        d.rodLength = s->rodLength; d.k = s->k; d.progressiveK = s->progressiveK; d.packerRange = s->packerRange; d.bumpStopRate = s->bumpStopRate;
+        d.bumpStopProgressive = s->bumpStopProgressive; d.bumpStopUp = s->bumpStopUp; d.bumpStopDn = s->bumpStopDn;
+        d.toeOutLinear = s->toeOUT_Linear; d.staticCamber = s->staticCamber; d.baseCFM = s->baseCFM;
+        copy_damper(d.damper, s->damper);
+        for (int l = 0; l < PD_DW_LINKS; ++l) copy_dball(d.link[l], s->joints[l].get(), pdref_joint(s->joints[l].get())->targetDistance);
+        { oder::Body* b = pdref_body(s->hub.get()); d.hubMass = b->mass; for (int k = 0; k < 3; ++k) d.hubInertia[k] = b->I[k]; }
+        if (s->useActiveActuator) fprintf(stderr, "[oracle] DWB active actuator present: not exported\n");
+    }
+    for (int i = 0; i < 2 && !front_dw(c); ++i) {
         SuspensionStrut* s = static_cast<SuspensionStrut*>(c->suspensions[i]); PdStrut& d = P->strut[i];
         v3(d.refPoint, s->dataRelToWheel.refPoint); v3(d.carStrut, s->dataRelToBody.carStrut); v3(d.tyreStrut, s->dataRelToWheel.tyreStrut);
         v3(d.baseCarSteer, s->baseCarSteerPosition); v3(d.tyreSteer, s->dataRelToWheel.tyreSteer);
@@ -357,7 +380,7 @@ void pdref_get_params(void* hv, PdCarParams* P) {
         { oder::Body* b = pdref_body(s->hub.get()); d.hubMass = b->mass; for (int k = 0; k < 3; ++k) d.hubInertia[k] = b->I[k]; }
         { oder::Body* b = pdref_body(s->strutBody.get()); d.strutMass = b->mass; for (int k = 0; k < 3; ++k) d.strutInertia[k] = b->I[k]; }
     }
-    {
+    if (!rear_dw(c)) {
         SuspensionAxle* s = static_cast<SuspensionAxle*>(c->suspensions[2]); PdAxle& d = P->axle;
         d.track = s->track; d.referenceY = s->referenceY; d.attachRelativePos = s->attachRelativePos; v3(d.axleBasePos, s->axleBasePos); d.leafSpringKx = s->leafSpringK.x;
         d.rodLength = s->rodLength; d.k = s->k; d.progressiveK = s->progressiveK; d.bumpStopUp = s->bumpStopUp; d.bumpStopDn = s->bumpStopDn; d.bumpStopRate = s->bumpStopRate; d.baseCFM = s->baseCFM;
@@ -414,7 +437,13 @@ void pdref_get_params(void* hv, PdCarParams* P) {
         d.gasCoastOffset = e->gasCoastOffset; d.coastEntryRpm = e->coastEntryRpm;
         d.overlapFreq = e->data.overlapFreq; d.overlapGain = e->data.overlapGain; d.overlapIdealRPM = e->data.overlapIdealRPM;
         d.isEngineStallEnabled = e->isEngineStallEnabled ? 1 : 0; d.maxPowerRPM = e->maxPowerRPM; d.maxTorqueRPM = e->maxTorqueRPM;
-        if (!e->turbos.empty() || e->throttleResponseCurveMax.getCount()) fprintf(stderr, "[oracle] turbos / throttle max curve present: not exported\n");
+        P->nTurbos = (int)e->turbos.size();
+        for (int i = 0; i < P->nTurbos && i < PD_MAX_TURBOS; ++i) {
+            const Turbo& t = *e->turbos[i]; PdTurbo& u = P->turbo[i];
+            u.lagDN = t.data.lagDN; u.lagUP = t.data.lagUP; u.maxBoost = t.data.maxBoost; u.wastegate = t.data.wastegate; u.rpmRef = t.data.rpmRef; u.gamma = t.data.gamma;
+            u.userSetting = t.userSetting; u.isAdjustable = t.data.isAdjustable ? 1 : 0;
+        }
+        if (!e->turboControllers.empty() || e->throttleResponseCurveMax.getCount()) fprintf(stderr, "[oracle] turbo controllers / throttle max curve present: not exported\n");
     }
     {
         Drivetrain* t = c->drivetrain.get(); PdDrivetrain& d = P->drivetrain;

@@ -83,6 +83,7 @@ def load_library():
         "pd_env_step_host": (i, [vp, vp, f, vp, vp, vp]),
         "pd_tick_kernel": (ctypes.c_char_p, [vp]),
         "pd_tick_kernel_instance": (ctypes.c_char_p, [vp]),
+        "pd_topology": (ctypes.c_int, [vp]),
         "pd_env_stats": (i, [vp, vp, i]),
         "pd_set_autoreset": (i, [vp, i]),
         "pd_debug_read_clocks": (i, [vp, vp, i]),
@@ -303,6 +304,10 @@ class Batch:
 
     def tick_kernel_instance(self):
         return self.L.pd_tick_kernel_instance(self.h).decode()
+
+    def topology(self):
+        """(front == DWB) * 2 + (rear == DWB)"""
+        return int(self.L.pd_topology(self.h))
 
     def launch_count(self):
         return int(self.L.pd_launch_count(self.h))

@@ -178,6 +178,57 @@ static void load_strut(const Ini& ini, int index, const HBody& car, PdStrut& S, 
     S.strutBaseLength = lenv(vTyreStrut - vCarStrut);
 }
 
+/* SuspensionDW::init + attach (SuspensionDW.cpp:18-195) for wheel `index` */
+static void load_dw(const Ini& ini, int index, const HBody& car, PdDW& D) {
+    memset(&D, 0, sizeof(D));
+    D.k = 90000.0f; D.baseCFM = 0.0000001f;
+    const int iVer = ini.getInt("HEADER", "VERSION");
+    const std::string id = index < 2 ? "FRONT" : "REAR";
+    const float fWheelBase = ini.getFloat("BASIC", "WHEELBASE"), fCg = ini.getFloat("BASIC", "CG_LOCATION");
+    const float fFrontBaseY = ini.getFloat("FRONT", "BASEY"), fFrontTrack = ini.getFloat("FRONT", "TRACK") * 0.5f;
+    const float fRearBaseY = ini.getFloat("REAR", "BASEY"), fRearTrack = ini.getFloat("REAR", "TRACK") * 0.5f;
+    V ref[4] = {{fFrontTrack, fFrontBaseY, (1.0f - fCg) * fWheelBase}, {-fFrontTrack, fFrontBaseY, (1.0f - fCg) * fWheelBase},
+                {fRearTrack, fRearBaseY, -(fCg * fWheelBase)}, {-fRearTrack, fRearBaseY, -(fCg * fWheelBase)}};
+    const V refPoint = ref[index];
+    float t[3];
+    auto g3 = [&](const char* k) { ini.getFloat3(id, k, t); return V{t[0], t[1], t[2]}; };
+    V carTopF = g3("WBCAR_TOP_FRONT"), carTopR = g3("WBCAR_TOP_REAR"), carBotF = g3("WBCAR_BOTTOM_FRONT"), carBotR = g3("WBCAR_BOTTOM_REAR");
+    V tyreTop = g3("WBTYRE_TOP"), tyreBot = g3("WBTYRE_BOTTOM"), tyreSteer = g3("WBTYRE_STEER"), carSteer = g3("WBCAR_STEER");
+    if (iVer >= 2) {
+        const float rim = -ini.getFloat(id, "RIM_OFFSET");
+        if (rim != 0.0f) { carTopF.x += rim; carTopR.x += rim; carBotF.x += rim; carBotR.x += rim; tyreTop.x += rim; tyreBot.x += rim; tyreSteer.x += rim; carSteer.x += rim; }
+    }
+    const float hubMass = ini.getFloat(id, "HUB_MASS");
+    D.bumpStopUp = ini.getFloat(id, "BUMPSTOP_UP"); D.bumpStopDn = -ini.getFloat(id, "BUMPSTOP_DN");
+    D.rodLength = ini.getFloat(id, "ROD_LENGTH"); D.toeOutLinear = ini.getFloat(id, "TOE_OUT");
+    D.k = ini.getFloat(id, "SPRING_RATE"); D.progressiveK = ini.getFloat(id, "PROGRESSIVE_SPRING_RATE");
+    load_damper(ini, id, D.damper);
+    D.bumpStopRate = ini.getFloat(id, "BUMP_STOP_RATE"); if (D.bumpStopRate == 0.0f) D.bumpStopRate = 500000.0f;
+    if (ini.hasKey(id, "BUMP_STOP_PROGRESSIVE")) D.bumpStopProgressive = ini.getFloat(id, "BUMP_STOP_PROGRESSIVE");
+    D.staticCamber = -ini.getFloat(id, "STATIC_CAMBER") * 0.017453f; if (index % 2) D.staticCamber *= -1.0f;
+    D.packerRange = ini.getFloat(id, "PACKER_RANGE");
+    if (refPoint.x > 0.0f) { carBotF.x *= -1.0f; carBotR.x *= -1.0f; carSteer.x *= -1.0f; carTopF.x *= -1.0f; carTopR.x *= -1.0f; tyreBot.x *= -1.0f; tyreSteer.x *= -1.0f; tyreTop.x *= -1.0f; }
+    float fMass = hubMass; if (fMass <= 0.0f) fMass = 20.0f;
+    D.hubMass = fMass; box_inertia(fMass, 0.2f, 0.6f, 0.6f, D.hubInertia);      /* hubInertiaBox is never read from the ini: the default box */
+    put(D.refPoint, refPoint); put(D.tyreSteer, tyreSteer);
+    /* attach(): hub at the reference point with the chassis' rotation; dataRelToBody.x = carBody->localToWorld(relToWheel.x + refPoint) */
+    HBody hub;
+    hub.setRotationAxes({car.R[0], car.R[3], car.R[6]}, {car.R[1], car.R[4], car.R[7]}, {car.R[2], car.R[5], car.R[8]});
+    hub.setPos(car.toWorld(refPoint));
+    const V bCarBotF = car.toWorld(carBotF + refPoint), bCarBotR = car.toWorld(carBotR + refPoint), bCarTopF = car.toWorld(carTopF + refPoint), bCarTopR = car.toWorld(carTopR + refPoint);
+    const V bTyreBot = car.toWorld(tyreBot + refPoint), bTyreTop = car.toWorld(tyreTop + refPoint), bCarSteer = car.toWorld(carSteer + refPoint), bTyreSteer = car.toWorld(tyreSteer + refPoint);
+    make_dball(D.link[0], car, hub, bCarTopR, bTyreTop);
+    make_dball(D.link[1], car, hub, bCarTopF, bTyreTop);
+    make_dball(D.link[2], car, hub, bCarBotR, bTyreBot);
+    make_dball(D.link[3], car, hub, bCarBotF, bTyreBot);
+    make_dball(D.link[4], car, hub, bCarSteer, bTyreSteer);
+    put(D.baseCarSteer, bCarSteer);
+    { /* init ends with setSteerLengthOffset(0): the steer rod is re-seated with the toe offset, target distance kept */
+        const V cs = {bCarSteer.x + (0.0f + 0.0f + (sgn(refPoint.x) * D.toeOutLinear)), bCarSteer.y, bCarSteer.z};
+        put(D.link[4].anchor1, car.toLocal(car.toWorld(cs))); put(D.link[4].anchor2, hub.toLocal(hub.toWorld(tyreSteer)));
+    }
+}
+
 static void load_axle(const Ini& ini, const HBody& car, PdAxle& A) {
     memset(&A, 0, sizeof(A));
     A.baseCFM = 0.0000001f; A.attachRelativePos = 1.0f;
@@ -287,7 +338,7 @@ static void load_tyre(const std::string& dataPath, int index, float ambient, PdT
     T.sctmLsMultX = T.lsMultX; T.sctmLsExpX = T.lsExpX;
 }
 
-static void load_engine(const std::string& dataPath, PdEngine& E) {
+static void load_engine(const std::string& dataPath, PdEngine& E, PdCarParams& P) {
     memset(&E, 0, sizeof(E));
     Ini ini(dataPath + "engine.ini");
     if (!ini.ready) throw Error("cannot read engine.ini");
@@ -312,10 +363,30 @@ static void load_engine(const std::string& dataPath, PdEngine& E) {
         if (def >= 0 && def < lut.n) E.gasCoastOffset = curve_value(lut, (float)def);
         E.coastEntryRpm = E.minimum + ini.getInt("COAST_SETTINGS", "ACTIVATION_RPM");
     }
-    if (ini.hasSection("TURBO_0")) throw Error("turbocharged engines are not supported yet (SURVEY.md N1)");
+    { /* Engine.cpp:69-94: TURBO_n sections, cockpit adjustment */
+        bool adjustable = false;
+        for (int id = 0;; ++id) {
+            const std::string sec = "TURBO_" + std::to_string(id);
+            if (!ini.hasSection(sec)) break;
+            if (id >= PD_MAX_TURBOS) throw Error("more than PD_MAX_TURBOS turbochargers");
+            PdTurbo& U = P.turbo[id]; memset(&U, 0, sizeof(U));
+            U.lagDN = (1.0f - ini.getFloat(sec, "LAG_DN")) * 1.333333f * 333.3333f;
+            U.lagUP = (1.0f - ini.getFloat(sec, "LAG_UP")) * 1.333333f * 333.3333f;
+            U.maxBoost = ini.getFloat(sec, "MAX_BOOST"); U.wastegate = ini.getFloat(sec, "WASTEGATE");
+            U.rpmRef = ini.getFloat(sec, "REFERENCE_RPM"); U.gamma = ini.getFloat(sec, "GAMMA");
+            U.isAdjustable = ini.getInt(sec, "COCKPIT_ADJUSTABLE") != 0; U.userSetting = 1.0f;      /* Turbo::userSetting = 1 (Turbo.h) */
+            if (U.isAdjustable) adjustable = true;
+            P.nTurbos = id + 1;
+        }
+        if (adjustable) { const float boost = ini.getFloat("ENGINE_DATA", "DEFAULT_TURBO_ADJUSTMENT"); for (int i = 0; i < P.nTurbos; ++i) P.turbo[i].userSetting = P.turbo[i].isAdjustable ? boost : 1.0f; }
+        for (int i = 0; i < P.nTurbos; ++i) if (file_exists(dataPath + "ctrl_turbo" + std::to_string(i) + ".ini") || file_exists(dataPath + "ctrl_wastegate" + std::to_string(i) + ".ini")) throw Error("turbo dynamic controllers are not supported yet");
+    }
     if (ini.hasSection("OVERLAP")) { E.overlapFreq = ini.getFloat("OVERLAP", "FREQUENCY"); E.overlapGain = ini.getFloat("OVERLAP", "GAIN"); E.overlapIdealRPM = ini.getFloat("OVERLAP", "IDEAL_RPM"); }
     load_curve(dataPath + "throttle.lut", E.throttleResponseCurve);
-    if (ini.hasSection("DAMAGE")) { E.rpmDamageThreshold = ini.getFloat("DAMAGE", "RPM_THRESHOLD"); E.rpmDamageK = ini.getFloat("DAMAGE", "RPM_DAMAGE_K"); }
+    if (ini.hasSection("DAMAGE")) {
+        E.rpmDamageThreshold = ini.getFloat("DAMAGE", "RPM_THRESHOLD"); E.rpmDamageK = ini.getFloat("DAMAGE", "RPM_DAMAGE_K");
+        if (P.nTurbos > 0) { E.turboBoostDamageThreshold = ini.getFloat("DAMAGE", "TURBO_BOOST_THRESHOLD"); E.turboBoostDamageK = ini.getFloat("DAMAGE", "TURBO_DAMAGE_K"); }
+    }
     if (ini.hasSection("BOV")) E.bovThreshold = ini.getFloat("BOV", "PRESSURE_THRESHOLD");
     if (ini.hasSection("THROTTLE_RESPONSE")) throw Error("THROTTLE_RESPONSE max curve is not supported yet");
     /* precalculatePowerAndTorque */
@@ -523,19 +594,25 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
     /* ---- suspensions ---- */
     Ini susp(dataPath + "suspensions.ini");
     if (!susp.ready) throw Error("cannot read suspensions.ini");
-    if (susp.getString("FRONT", "TYPE") != "STRUT" || susp.getString("REAR", "TYPE") != "AXLE")
-        throw Error("only the demo-car topology (FRONT TYPE=STRUT, REAR TYPE=AXLE) is implemented; DWB / ML are SURVEY.md N1");
+    const std::string frontType = susp.getString("FRONT", "TYPE"), rearType = susp.getString("REAR", "TYPE");
+    if ((frontType != "STRUT" && frontType != "DWB") || (rearType != "AXLE" && rearType != "DWB"))
+        throw Error("suspension types other than STRUT / DWB (front) and AXLE / DWB (rear) are not implemented (ML: SURVEY.md N4)");
+    if (susp.hasSection("HEAVE_FRONT") || susp.hasSection("HEAVE_REAR")) throw Error("heave springs are not supported yet (SURVEY.md N4)");
+    const bool frontDW = frontType == "DWB", rearDW = rearType == "DWB";
+    P.topology = (frontDW ? 2 : 0) + (rearDW ? 1 : 0);
+    if (P.topology == PD_TOPO_DW_AXLE) throw Error("DWB front with a rigid rear axle: no kernel instance is built for this pair");
     float hubMass[2];
-    load_strut(susp, 0, chassis, P.strut[0], hubMass[0]);
-    load_strut(susp, 1, chassis, P.strut[1], hubMass[1]);
-    load_axle(susp, chassis, P.axle);
+    if (frontDW) { load_dw(susp, 0, chassis, P.dw[0]); load_dw(susp, 1, chassis, P.dw[1]); }
+    else { load_strut(susp, 0, chassis, P.strut[0], hubMass[0]); load_strut(susp, 1, chassis, P.strut[1], hubMass[1]); }
+    if (rearDW) { load_dw(susp, 2, chassis, P.dw[2]); load_dw(susp, 3, chassis, P.dw[3]); }
+    else load_axle(susp, chassis, P.axle);
     P.arbK[0] = susp.getFloat("ARB", "FRONT"); P.arbK[1] = susp.getFloat("ARB", "REAR");
     if (file_exists(dataPath + "ctrl_arb_front.ini") || file_exists(dataPath + "ctrl_arb_rear.ini")) throw Error("ARB dynamic controllers are not supported yet");
     /* ---- tyres ---- */
     for (int w = 0; w < 4; ++w) load_tyre(dataPath, w, P.ambientTemperature, P.tyre[w]);
     /* Car::getBaseCarHeight */
     {
-        const float t0 = fabsf(P.strut[0].refPoint[1] - P.tyre[0].rimRadius), t2 = fabsf(P.axle.axleBasePos[1] - P.tyre[2].rimRadius);
+        const float t0 = fabsf((frontDW ? P.dw[0].refPoint[1] : P.strut[0].refPoint[1]) - P.tyre[0].rimRadius), t2 = fabsf((rearDW ? P.dw[2].refPoint[1] : P.axle.axleBasePos[1]) - P.tyre[2].rimRadius);
         P.baseCarHeight = t0 > t2 ? t0 : t2;
     }
     /* ---- components ---- */
@@ -550,7 +627,7 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
         Ini s(dataPath + "setup.ini");
         if (s.ready && s.hasSection("FRONT_BIAS")) { P.brakes.biasMin = s.getFloat("FRONT_BIAS", "MIN") * 0.01f; P.brakes.biasMax = s.getFloat("FRONT_BIAS", "MAX") * 0.01f; }
     }
-    load_engine(dataPath, P.engine);
+    load_engine(dataPath, P.engine, P);
     load_drivetrain(dataPath, P, P.drivetrain, P.assists);
     /* tyres[].driven */
     for (int w = 0; w < 4; ++w) P.tyre[w].driven = (P.drivetrain.tractionType == 0) ? (w >= 2) : (w < 2);
@@ -561,7 +638,9 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
     }
     /* ---- Car::updateBodyMass (Car.cpp:589-620) at init ---- */
     {
-        const float suspMass = (P.strut[0].hubMass + P.strut[1].hubMass) + (P.axle.axleMass * 0.5f) + (P.axle.axleMass * 0.5f);
+        /* Car::calcBodyMass: fSuspMass += suspensions[i]->getMass() for i = 0..3, in that order */
+        float suspMass = 0.0f;
+        for (int w = 0; w < 4; ++w) suspMass += (w < 2) ? (frontDW ? P.dw[w].hubMass : P.strut[w].hubMass) : (rearDW ? P.dw[w].hubMass : (P.axle.axleMass * 0.5f));
         P.chassisMass = (P.mass - suspMass) + 0.0f;
         box_inertia(P.chassisMass, bodyInertia[0], bodyInertia[1], bodyInertia[2], P.chassisInertia);
         const float fuelMass = (P.fuelKG * (float)fuel) > 0.1f ? (P.fuelKG * (float)fuel) : 0.1f;
@@ -575,17 +654,35 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
     addD("FINAL_RATIO", 1.0, &P.drivetrain.finalRatio);
     addF("ARB_FRONT", 1.0, &P.arbK[0]); addF("ARB_REAR", 1.0, &P.arbK[1]);
     addF("ENGINE_LIMITER", 0.01, &P.engine.limiterMultiplier);
+    for (int i = 0; i < P.nTurbos; ++i) { /* SetupManager.cpp:94-107: TURBO_n -> Turbo::userSetting, tunable 0..1 in steps of 0.1 */
+        static char nm[PD_MAX_TURBOS][16]; snprintf(nm[i], sizeof(nm[i]), "TURBO_%d", i); addF(nm[i], 0.01, &P.turbo[i].userSetting);
+        SetupVar& v = out.setupVars.back(); v.minV = 0.0f; v.maxV = 1.0f; v.step = 0.1f; v.tunable = true;
+    }
     for (int i = 0; i < P.drivetrain.nGears && i < PD_MAX_GEARS; ++i) { static char nm[PD_MAX_GEARS][32]; snprintf(nm[i], sizeof(nm[i]), "INTERNAL_GEAR_%d", i); addD(nm[i], 1.0, &P.drivetrain.gears[i]); }
     {   /* front struts: the per-wheel variables of SetupManager.cpp:62-83 */
         static const char* kSide[2] = {"LF", "RF"}; static const double kSign[2] = {-1, 1};
         static char nm[2][11][40];
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < 2 && !frontDW; ++w) {
             PdStrut& S = P.strut[w]; int q = 0;
             auto reg = [&](const char* base, double mult, float* ptr) { snprintf(nm[w][q], sizeof(nm[w][q]), "%s_%s", base, kSide[w]); addF(nm[w][q], mult, ptr); ++q; };
             reg("DAMP_FAST_BUMP", 1.0, &S.damper.bumpFast); reg("DAMP_BUMP", 1.0, &S.damper.bumpSlow);
             reg("DAMP_FAST_REBOUND", 1.0, &S.damper.reboundFast); reg("DAMP_REBOUND", 1.0, &S.damper.reboundSlow);
             reg("BUMP_STOP_RATE", 1000.0, &S.bumpStopRate); reg("SPRING_RATE", 1000.0, &S.k); reg("PROGRESSIVE_SPRING_RATE", 1000.0, &S.progressiveK);
             reg("ROD_LENGTH", 0.0001, &S.rodLength); reg("CAMBER", 0.0017453292 * kSign[w], &S.staticCamber);
+            reg("TOE_OUT", 0.00001, &S.toeOutLinear); reg("PACKER_RANGE", 0.001, &S.packerRange);
+        }
+    }
+    {   /* double-wishbone corners: the same per-wheel variables (SetupManager.cpp:62-83), all four wheels where the axle is DWB */
+        static const char* kSide4[4] = {"LF", "RF", "LR", "RR"}; static const double kSign4[4] = {-1, 1, -1, 1};
+        static char nm4[4][11][40];
+        for (int w = 0; w < 4; ++w) {
+            if (!(w < 2 ? frontDW : rearDW)) continue;
+            PdDW& S = P.dw[w]; int q = 0;
+            auto reg = [&](const char* base, double mult, float* ptr) { snprintf(nm4[w][q], sizeof(nm4[w][q]), "%s_%s", base, kSide4[w]); addF(nm4[w][q], mult, ptr); ++q; };
+            reg("DAMP_FAST_BUMP", 1.0, &S.damper.bumpFast); reg("DAMP_BUMP", 1.0, &S.damper.bumpSlow);
+            reg("DAMP_FAST_REBOUND", 1.0, &S.damper.reboundFast); reg("DAMP_REBOUND", 1.0, &S.damper.reboundSlow);
+            reg("BUMP_STOP_RATE", 1000.0, &S.bumpStopRate); reg("SPRING_RATE", 1000.0, &S.k); reg("PROGRESSIVE_SPRING_RATE", 1000.0, &S.progressiveK);
+            reg("ROD_LENGTH", 0.0001, &S.rodLength); reg("CAMBER", 0.0017453292 * kSign4[w], &S.staticCamber);
             reg("TOE_OUT", 0.00001, &S.toeOutLinear); reg("PACKER_RANGE", 0.001, &S.packerRange);
         }
     }
@@ -652,7 +749,9 @@ void CarModel::setRawTune(const std::string& name, float v) {
     if (known_but_unsupported(name)) throw Error("setup variable '" + name + "' exists in the reference but is not supported by this build (per-wheel rear-axle / AWD / turbo tune)");
 }
 void CarModel::setTune(const std::string& name, float v) {
-    if (known_but_unsupported(name)) throw Error("setup variable '" + name + "' exists in the reference but is not supported by this build (per-wheel rear-axle / AWD / turbo tune)");
+    bool registered = false;
+    for (auto& var : setupVars) if (var.name == name) registered = true;
+    if (!registered && known_but_unsupported(name)) throw Error("setup variable '" + name + "' exists in the reference but is not supported by this build (per-wheel rear-axle / AWD tune)");
     for (auto& var : setupVars) {
         if (var.name != name) continue;
         float smin = 0, smax = 0;

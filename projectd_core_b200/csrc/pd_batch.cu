@@ -108,6 +108,7 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
 #ifndef PD_SERIAL_MINBLOCKS
 #define PD_SERIAL_MINBLOCKS 8
 #endif
+template <int TOPO>       /* suspension topology (PD_TOPO_*): one compile-time instance per (front, rear) pair of the bundled cars */
 __global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                    const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     const long long clk0 = io.clk ? clock64() : 0;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __
         if (resetNow) env_reset_in_kernel(P, T, sv, e, io, time);
         else if (io.act) env_apply_action(sv, io.act[e * 2 + 0], io.act[e * 2 + 1], io.cfg);
 #if PD_SOLVER2
-        car_tick<1, 1>(P, T, sv, dt, time, pd_rows, pd_rows, collPre, io.contacts ? io.contacts + (size_t)e * PD_CONTACT_WORDS : nullptr);
+        car_tick<1, 1, TOPO>(P, T, sv, dt, time, pd_rows, pd_rows, collPre, io.contacts ? io.contacts + (size_t)e * PD_CONTACT_WORDS : nullptr);
 #elif PD_SERIAL_SMEM_SCRATCH
         car_tick<1, PD_BLOCK>(P, T, sv, dt, time, pd_rows, pd_scrD + threadIdx.x, collPre);
 #else
@@ -622,7 +623,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_E2E_ZEROCOPY")) b->zeroCopy = atoi(q) != 0;
     if (const char* q = getenv("PD_COLL_WARP")) b->collWarp = atoi(q) != 0;
     if (const char* q = getenv("PD_SERIAL_INLINE_COLLIDE")) b->inlineCollide = atoi(q) != 0;
-    if (const char* q = getenv("PD_SERIAL_SMEM_PAD")) { b->serialSmemPad = atoi(q); cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); }
+    if (const char* q = getenv("PD_SERIAL_SMEM_PAD")) { b->serialSmemPad = atoi(q); cudaFuncSetAttribute(k_tick<PD_TOPO_STRUT_AXLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); cudaFuncSetAttribute(k_tick<PD_TOPO_STRUT_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); cudaFuncSetAttribute(k_tick<PD_TOPO_DW_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); }
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->ownStream = b->stream;
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
     CK(cudaFuncSetAttribute(k_tick_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
@@ -633,6 +634,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
       b->quadCpw = (n_envs <= sms * 6 * 4) ? 2 : (n_envs <= sms * 4 * 8) ? 4 : 8;
       if (const char* q = getenv("PD_QUAD_CPW")) { const int v = atoi(q); if (v == 2 || v == 4 || v == 8) b->quadCpw = v; } }
     b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
+    if (b->car.P.topology != PD_TOPO_STRUT_AXLE) b->layout = PD_LAYOUT_TILED;      /* double-wishbone cars: the thread-per-car kernel has the instances (k_tick<PD_TOPO_STRUT_DW>, <PD_TOPO_DW_DW>); the 4-lanes-per-car kernel is laid out for strut + rigid axle */
     int rc;
     if (b->track.needFat) { b->launches++; if ((rc = fat_points_on_device(b->track, b->stream, b->err))) return rc; }      /* no usable spline.cache: Track::computeFatPoints, on the GPU */
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
@@ -745,7 +747,11 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
         default: k_tick_quad<8><<<grid(b->n, 16), threads, PD_QUAD_SMEM_BYTES_(8), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
         }
     } else
-        k_tick<<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+        switch (b->car.P.topology) {
+        case PD_TOPO_STRUT_DW: k_tick<PD_TOPO_STRUT_DW><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        case PD_TOPO_DW_DW: k_tick<PD_TOPO_DW_DW><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        default: k_tick<PD_TOPO_STRUT_AXLE><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        }
     b->launches++;
 }
 
@@ -1116,7 +1122,9 @@ int pd_get_car_state(pd_batch* b, int env, void* outv) {
     s.angularVelocity[0] = C.w.x; s.angularVelocity[1] = C.w.y; s.angularVelocity[2] = C.w.z;
     for (int w = 0; w < 4; ++w) {
         Frame hf;
-        if (w < 2) { Body H; load_body(sv, PD_BODY_HUB0 + 2 * w, H); hf = strut_hub_frame(b->car.P.strut[w], H); }
+        const int topo = b->car.P.topology;
+        if (w < 2) { Body H; load_body(sv, PD_BODY_HUB0 + 2 * w, H); hf = PD_TOPO_FRONT_DW(topo) ? dw_hub_frame(b->car.P.dw[w], H) : strut_hub_frame(b->car.P.strut[w], H); }
+        else if (PD_TOPO_REAR_DW(topo)) { Body H; load_body(sv, PD_BODY_HUB2 + (w - 2), H); hf = dw_hub_frame(b->car.P.dw[w], H); }
         else { Body A; load_body(sv, PD_BODY_AXLE, A); hf = axle_hub_frame(b->car.P.axle, A, w - 2); }
         put_matrix(s.hubMatrix[w], hf);
         const int o = PD_OFF_TYRE(w);
@@ -1147,9 +1155,10 @@ int pd_raycast(pd_batch* b, int n, const float* rays, float* out) {
 int pd_sync(pd_batch* b) { if (!b) return PD_ERR_ARG; CK(cudaStreamSynchronize(b->stream)); CK(cudaGetLastError()); return PD_OK; }
 void* pd_stream(pd_batch* b) { return b ? (void*)b->stream : nullptr; }
 const char* pd_tick_kernel(const pd_batch* b) { return !b ? "" : (b->layout == PD_LAYOUT_RECORDS ? "k_tick_quad" : "k_tick"); }
+int pd_topology(const pd_batch* b) { return b ? b->car.P.topology : -1; }
 const char* pd_tick_kernel_instance(const pd_batch* b) {
     if (!b) return "";
-    if (b->layout != PD_LAYOUT_RECORDS) return "k_tick";
+    if (b->layout != PD_LAYOUT_RECORDS) return b->car.P.topology == PD_TOPO_STRUT_DW ? "k_tick<strut,dwb>" : (b->car.P.topology == PD_TOPO_DW_DW ? "k_tick<dwb,dwb>" : "k_tick");
     return b->quadCpw == 2 ? "k_tick_quad<2>" : b->quadCpw == 4 ? "k_tick_quad<4>" : "k_tick_quad<8>";
 }
 uint64_t pd_launch_count(const pd_batch* b) { return b ? b->launches : 0; }

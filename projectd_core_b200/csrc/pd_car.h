@@ -46,6 +46,13 @@ PD_HD Frame strut_hub_frame(const PdStrut& P, const Body& hub) { /* SuspensionSt
     f.az = hub.fr.az; f.p = hub.fr.p;
     return f;
 }
+PD_HD Frame dw_hub_frame(const PdDW& P, const Body& hub) { /* SuspensionDW.cpp:333-336: rotate(hub world matrix, z, staticCamber) */
+    Frame f; const float s = m_sin(P.staticCamber), c = m_cos(P.staticCamber);
+    f.ax = v3(c * hub.fr.ax.x + s * hub.fr.ay.x, c * hub.fr.ax.y + s * hub.fr.ay.y, c * hub.fr.ax.z + s * hub.fr.ay.z);
+    f.ay = v3(-s * hub.fr.ax.x + c * hub.fr.ay.x, -s * hub.fr.ax.y + c * hub.fr.ay.y, -s * hub.fr.ax.z + c * hub.fr.ay.z);
+    f.az = hub.fr.az; f.p = hub.fr.p;
+    return f;
+}
 PD_HD Frame axle_hub_frame(const PdAxle& P, const Body& axle, int side) { /* SuspensionAxle.cpp:224-232 */
     Frame f = axle.fr; const float t = side ? -P.track : P.track;
     f.p.x += f.ax.x * t; f.p.y += f.ax.y * t; f.p.z += f.ax.z * t;
@@ -150,6 +157,41 @@ PD_HD void axle_step(const PdAxle& P, Body& C, Body& A, int side, float& travelO
     const V3 vForce = vDelta * fDamperForce;
     add_force_at_pos(A, vForce, vAxleWorld);
     add_force_at_pos(C, vForce * -1.0f, vBaseWorld);
+}
+
+/* SuspensionDW::step (SuspensionDW.cpp:202-272), passive branch (useActiveActuator is never set) */
+PD_HD void dw_step(const PdDW& P, Body& C, Body& H, float& travelOut, float& damperSpeedOut) {
+    const V3 vBodyM2 = C.fr.ay;
+    const V3 vRef = v3(P.refPoint[0], P.refPoint[1], P.refPoint[2]);
+    const V3 vHubWorldPos = H.fr.p;
+    const V3 vHubLocalPos = to_local(C.fr, vHubWorldPos);
+    const float fHubDeltaY = vHubLocalPos.y - P.refPoint[1];
+    const float fTravel = fHubDeltaY + P.rodLength;
+    travelOut = fTravel;
+    float fForce = ((fTravel * P.progressiveK) + P.k) * fTravel;
+    if (P.packerRange != 0.0f && fTravel > P.packerRange && P.k != 0.0f)
+        fForce += (((fTravel - P.packerRange) * P.bumpStopProgressive) + P.bumpStopRate) * (fTravel - P.packerRange);
+    if (fForce > 0.0f) {
+        add_force_at_pos(H, vBodyM2 * -fForce, vHubWorldPos);
+        add_rel_force_at_rel_pos(C, v3(0, fForce, 0), vRef);
+    }
+    const V3 vDeltaVel = H.v - body_rel_point_vel(C, vRef);
+    const float fDamperSpeed = dot(vDeltaVel, vBodyM2);
+    damperSpeedOut = fDamperSpeed;
+    const float fDamperForce = damper_force(P.damper, fDamperSpeed);
+    const V3 vForce = vBodyM2 * fDamperForce;
+    add_force_at_pos(H, vForce, vHubWorldPos);
+    add_force_at_rel_pos(C, vForce * -1.0f, vRef);
+    if (P.bumpStopUp != 0.0f && fHubDeltaY > P.bumpStopUp && 0.0f != P.k) {
+        const float f = (((fHubDeltaY - P.bumpStopUp) * P.bumpStopProgressive) + P.bumpStopRate) * (fHubDeltaY - P.bumpStopUp);
+        add_force_at_pos(H, vBodyM2 * -f, vHubWorldPos);
+        add_rel_force_at_rel_pos(C, v3(0, f, 0), vHubLocalPos);
+    }
+    if (P.bumpStopDn != 0.0f && fHubDeltaY < P.bumpStopDn && 0.0f != P.k) {
+        const float f = (((fHubDeltaY - P.bumpStopDn) * P.bumpStopProgressive) + P.bumpStopRate) * (fHubDeltaY - P.bumpStopDn);
+        add_force_at_pos(H, vBodyM2 * -f, vHubWorldPos);
+        add_rel_force_at_rel_pos(C, v3(0, f, 0), vHubLocalPos);
+    }
 }
 
 /* AntirollBar::step (AntirollBar.cpp:19-47) */
@@ -797,9 +839,25 @@ PD_HD void engine_step(const PdCarParams& PP, CarCtx& X, float gasInput, float r
     float fPower = curve_value(E.powerCurve, rpm);
     float fCoastTorq = 0;
     if (E.coast1 != 0.0f) fCoastTorq = (rpm - (float)E.minimum) * E.coast1;
+    if (PP.nTurbos > 0) { /* Engine::stepTurbos (Engine.cpp:368-384) + Turbo::step (Turbo.cpp:11-40; the reference passes dt = 0.003) */
+        float boost = 0.0f;
+        for (int i = 0; i < PP.nTurbos && i < PD_MAX_TURBOS; ++i) {
+            const PdTurbo& U = PP.turbo[i];
+            float& rotation = (i == 0) ? c.turboRot0 : ((i == 1) ? c.turboRot1 : c.turboRot2);
+            float fNewRotation = 0.0f, fLag;
+            if (rpm > 0.0f && fGas > 0.0f) fNewRotation = m_pow(tclampf(((fGas * rpm) / U.rpmRef), 0.0f, 1.0f), U.gamma);
+            if (fNewRotation <= rotation) fLag = tclampf((0.003f * U.lagDN), 0.0f, 1.0f); else fLag = tclampf((0.003f * U.lagUP), 0.0f, 1.0f);
+            rotation += ((fNewRotation - rotation) * fLag);
+            if (U.wastegate != 0.0f) { const float fUserWG = U.wastegate * U.userSetting; if ((U.maxBoost * rotation) > fUserWG) rotation = fUserWG / U.maxBoost; }
+            boost += ((U.maxBoost * rotation) * c.fuelPressure);
+        }
+        c.turboBoost = boost;
+        if (boost != 0.0f) fPower *= (boost + 1.0f);
+    }
     if (E.coast2 != 0.0f) { const float d = rpm - (float)E.minimum; fCoastTorq -= (((d * d) * E.coast2) * signf_(rpm)); }
     fCoastTorq += 0.0f; /* externalCoastTorque */
     if (rpm <= (float)E.minimum) fCoastTorq = 0;
+    if (E.turboBoostDamageThreshold != 0.0f && c.turboBoost > E.turboBoostDamageThreshold) c.lifeLeft -= ((((c.turboBoost - E.turboBoostDamageThreshold) * E.turboBoostDamageK) * 0.003f) * PP.mechanicalDamageRate);
     if (E.rpmDamageThreshold != 0.0f && rpm > E.rpmDamageThreshold) c.lifeLeft -= ((((rpm - E.rpmDamageThreshold) * E.rpmDamageK) * 0.003f) * PP.mechanicalDamageRate);
     const float fAirAmount = PP.airDensity * 0.82630974f;
     const float fOutTorq = ((((fPower - fCoastTorq) * fGas) + fCoastTorq) * fAirAmount);

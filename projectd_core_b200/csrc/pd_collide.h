@@ -302,7 +302,7 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
 #define PD_HULLS_BOUNDS (PD_HULLS_SPHERE + PD_MAX_COLLIDER_TRIS * 4)
 #define PD_HULLS_TRIS   (PD_HULLS_BOUNDS + PD_MAX_COLLIDER_TRIS * 6)
 #define PD_HULLS_VERTS  (PD_HULLS_TRIS + PD_MAX_COLLIDER_TRIS)
-#define PD_HULLS_WORDS  (PD_HULLS_VERTS + PD_MAX_COLLIDER_VERTS * 3)      /* 1600 words = 6.4 KB per warp */
+#define PD_HULLS_WORDS  (PD_HULLS_VERTS + PD_MAX_COLLIDER_VERTS * 3)      /* 2496 words = 10 KB per warp */
 template <bool SMEM> __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackDev& T, const Body& C, int lane, float* hullS, int* stats = nullptr) {
     const unsigned FULL = 0xffffffffu;
     bool staged = false;
@@ -334,12 +334,12 @@ template <bool SMEM> __device__ __noinline__ bool car_collide_warp(const PdCarPa
         const long long tc0 = stats ? clock64() : 0;
                         const long long ts0 = stats ? clock64() : 0;
                         if (SMEM && !staged) {      /* first survivor of this car: the hull's filter data and vertices move to this warp's shared memory */
-                            for (int i = lane; i < PD_MAX_COLLIDER_TRIS; i += 32) {
+                            for (int i = lane; i < P.nColliderTris; i += 32) {
                                 PD_UNROLL for (int q = 0; q < 4; ++q) hullS[PD_HULLS_SPHERE + i * 4 + q] = P.colliderTriSphere[i][q];
                                 PD_UNROLL for (int q = 0; q < 6; ++q) hullS[PD_HULLS_BOUNDS + i * 6 + q] = P.colliderTriBounds[i][q];
                                 hullS[PD_HULLS_TRIS + i] = __int_as_float((int)P.colliderTris[i][0] | ((int)P.colliderTris[i][1] << 8) | ((int)P.colliderTris[i][2] << 16));
                             }
-                            for (int i = lane; i < PD_MAX_COLLIDER_VERTS; i += 32) { PD_UNROLL for (int q = 0; q < 3; ++q) hullS[PD_HULLS_VERTS + i * 3 + q] = P.colliderVerts[i][q]; }
+                            for (int i = lane; i < P.nColliderVerts; i += 32) { PD_UNROLL for (int q = 0; q < 3; ++q) hullS[PD_HULLS_VERTS + i * 3 + q] = P.colliderVerts[i][q]; }
                             __syncwarp(FULL);
                             staged = true;
                             if (stats && lane == 0) stats[5] += (int)((clock64() - ts0) >> 4);

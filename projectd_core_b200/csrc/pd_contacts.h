@@ -29,7 +29,9 @@ namespace pd {
 
 #define PD_MAX_CONTACTS 8
 #define PD_CONTACT_WORDS 68          /* per env: count | 8 x {pos3, normal3, depth, kind} | pad */
-#define PD_CONTACT_SLOTS 59          /* 8 box corners | 50 hull vertices | the floor fallback */
+#define PD_CONTACT_HULL_SLOTS PD_MAX_COLLIDER_VERTS
+#define PD_CONTACT_SLOTS (8 + PD_CONTACT_HULL_SLOTS + 1)          /* 8 box corners | one per hull vertex | the floor fallback */
+#define PD_CONTACT_FALLBACK (PD_CONTACT_SLOTS - 1)
 
 struct ContactSlot { float depth, nx, ny, nz, px, py, pz; };
 /* total order of ode_collide.h contact_offer: deeper wins, ties by larger normal.y, then .x, then .z */
@@ -99,7 +101,7 @@ __device__ __noinline__ void car_contacts_warp(const PdCarParams& P, const Track
                 V3 n; float satDepth = 0.0f;
                 if (!box_tri_contact(bc, f.ax, f.ay, f.az, bh, t0, t1, t2, n, &satDepth)) continue;
                 if (dot(f.ay, n) < 0.9f) continue;
-                contact_offer(slot[58], v3(0, 0, 0), n, satDepth);                      /* fallback: the deepest accepted triangle */
+                contact_offer(slot[PD_CONTACT_FALLBACK], v3(0, 0, 0), n, satDepth);                      /* fallback: the deepest accepted triangle */
                 const V3 N = cross(t1 - t0, t2 - t0);
                 const float len = sqrtf(dot(N, N));
                 if (!(len > 1e-12f)) continue;
@@ -139,7 +141,7 @@ __device__ __noinline__ void car_contacts_warp(const PdCarParams& P, const Track
                 V3 nl = v3(N.x * inv, N.y * inv, N.z * inv);
                 if (dot(v3(0, 0, 0) - b0, nl) < 0.0f) nl = v3(-nl.x, -nl.y, -nl.z);
                 const V3 nw = rot(f, nl);
-                for (int j = 0; j < P.nColliderVerts && j < 50; ++j) {
+                for (int j = 0; j < P.nColliderVerts && j < PD_CONTACT_HULL_SLOTS; ++j) {
                     const V3 hv = v3(P.colliderVerts[j][0], P.colliderVerts[j][1], P.colliderVerts[j][2]);
                     const float sdist = dot(hv - b0, nl);
                     if (!(sdist < 0.0f) || !(sdist > -0.5f)) continue;
@@ -172,19 +174,19 @@ __device__ __noinline__ void car_contacts_warp(const PdCarParams& P, const Track
             taken[best] = true; ++nf;
             float* o = out + 1 + n * 8; o[0] = slot[best].px; o[1] = slot[best].py; o[2] = slot[best].pz; o[3] = slot[best].nx; o[4] = slot[best].ny; o[5] = slot[best].nz; o[6] = slot[best].depth; o[7] = 0.0f; ++n;
         }
-        if (nf == 0 && slot[58].depth >= 0.0f) {
-            const V3 fbN = v3(slot[58].nx, slot[58].ny, slot[58].nz);
+        if (nf == 0 && slot[PD_CONTACT_FALLBACK].depth >= 0.0f) {
+            const V3 fbN = v3(slot[PD_CONTACT_FALLBACK].nx, slot[PD_CONTACT_FALLBACK].ny, slot[PD_CONTACT_FALLBACK].nz);
             int bestK = 0; float bestS = 3.4e38f;
             for (int k = 0; k < 8; ++k) { const float sdot = dot(corner[k], fbN); if (sdot < bestS) { bestS = sdot; bestK = k; } }
-            float* o = out + 1 + n * 8; o[0] = corner[bestK].x; o[1] = corner[bestK].y; o[2] = corner[bestK].z; o[3] = fbN.x; o[4] = fbN.y; o[5] = fbN.z; o[6] = slot[58].depth; o[7] = 0.0f; ++n;
+            float* o = out + 1 + n * 8; o[0] = corner[bestK].x; o[1] = corner[bestK].y; o[2] = corner[bestK].z; o[3] = fbN.x; o[4] = fbN.y; o[5] = fbN.z; o[6] = slot[PD_CONTACT_FALLBACK].depth; o[7] = 0.0f; ++n;
         }
     }
     {   /* walls: the 4 deepest hull vertices, ties by lower vertex index */
-        bool taken[50];
-        for (int k = 0; k < 50; ++k) taken[k] = false;
+        bool taken[PD_CONTACT_HULL_SLOTS];
+        for (int k = 0; k < PD_CONTACT_HULL_SLOTS; ++k) taken[k] = false;
         for (int r = 0; r < 4; ++r) {
             int best = -1;
-            for (int k = 0; k < 50; ++k) if (slot[8 + k].depth >= 0.0f && !taken[k] && (best < 0 || slot[8 + k].depth > slot[8 + best].depth)) best = k;
+            for (int k = 0; k < PD_CONTACT_HULL_SLOTS; ++k) if (slot[8 + k].depth >= 0.0f && !taken[k] && (best < 0 || slot[8 + k].depth > slot[8 + best].depth)) best = k;
             if (best < 0) break;
             taken[best] = true;
             const ContactSlot& s = slot[8 + best];

@@ -304,15 +304,18 @@ PD_HD void single_rows_tank(const PdCarParams& P, const Body& T, const Body& C, 
     PD_UNROLL
     for (int i = 0; i < 6; ++i) cfm[i] = P.worldCFM;
 }
-/* dball links chassis (b0) <-> axle (b1, own); rows beyond nLinks are identity padding */
-PD_HD void single_rows_axle(const PdCarParams& P, const Body& C, const Body& Ax, float hinv, float dballErp, float dballCfm, const SingleSys& G, float* cfm) {
-    const int n = P.axle.nLinks;
+/* dball links chassis (b0) <-> own body (b1: rigid axle, or the hub of a double-wishbone corner); rows beyond n are identity
+ * padding.  steer != null: link 4's anchors are the re-seated steering rod (SuspensionDW::setSteerLengthOffset) */
+PD_HD void single_rows_links(const PdDBall* links, int n, const Body& C, const Body& Ax, float hinv, float dballErp, float dballCfm, const SingleSys& G, float* cfm,
+                             const V3* steer = nullptr) {
     PD_UNROLL
     for (int l = 0; l < 6; ++l) {
         if (l < PD_AXLE_LINKS && l < n) {
-            const PdDBall& K = P.axle.link[l];
+            const PdDBall& K = links[l];
             float J0[6], J1[6], c;
-            row_dball(C, Ax, v3(K.anchor1[0], K.anchor1[1], K.anchor1[2]), v3(K.anchor2[0], K.anchor2[1], K.anchor2[2]), K.distance, hinv * dballErp, J0, J1, c);
+            V3 a1 = v3(K.anchor1[0], K.anchor1[1], K.anchor1[2]), a2 = v3(K.anchor2[0], K.anchor2[1], K.anchor2[2]);
+            if (steer && l == 4) { a1 = steer[0]; a2 = steer[1]; }
+            row_dball(C, Ax, a1, a2, K.distance, hinv * dballErp, J0, J1, c);
             single_row(G, l, v3(J1[0], J1[1], J1[2]), v3(J1[3], J1[4], J1[5]), v3(J0[0], J0[1], J0[2]), v3(J0[3], J0[4], J0[5]), c);
             cfm[l] = dballCfm;
         } else {
@@ -320,6 +323,9 @@ PD_HD void single_rows_axle(const PdCarParams& P, const Body& C, const Body& Ax,
             cfm[l] = 1.0f / hinv;       /* pad row: diagonal cfm / h = 1, nothing else */
         }
     }
+}
+PD_HD void single_rows_axle(const PdCarParams& P, const Body& C, const Body& Ax, float hinv, float dballErp, float dballCfm, const SingleSys& G, float* cfm) {
+    single_rows_links(P.axle.link, P.axle.nLinks, C, Ax, hinv, dballErp, dballCfm, G, cfm);
 }
 PD_HD void single_factor(const SingleSys& G, const float* cfm, const BodyDyn& dA, const BodyDyn& dC, float hinv, float* S21, float* b6) {
     float MJ[6][6], A[21], r[6], dinv[6], Yu[6][6];
@@ -382,24 +388,47 @@ PD_HD void single_backsolve(const SingleSys& G, const float* z, float* cfA) {
 
 /* dWorldStep for the car's island, one thread doing the four groups one after the other (thread-per-car kernel, host build) */
 PD_HDN void contacts_solve(const PdCarParams& P, const float* __restrict__ cont, const Body& C, const BodyDyn& dC, const float* __restrict__ S21, const float* __restrict__ b6, float h, bool fresh, float& lifeLeft, float* __restrict__ dmg, float* __restrict__ z);   /* pd_contacts.h */
+#define PD_TOPO_FRONT_DW(T) (((T) & 2) != 0)
+#define PD_TOPO_REAR_DW(T) (((T) & 1) != 0)
+/* body slots a topology owns (include/pd_state.h): chassis, tank, the two front hubs and slot 6 always; the strut bodies with a
+ * strut front axle; slot 7 with a double-wishbone rear axle */
+template <int TOPO> PD_HD constexpr bool topo_has_body(int i) { return (i == PD_BODY_STRUT0 || i == PD_BODY_STRUT1) ? !PD_TOPO_FRONT_DW(TOPO) : (i == PD_BODY_HUB3 ? PD_TOPO_REAR_DW(TOPO) : true); }
+PD_HD bool topo_has_body_rt(int topo, int i) { return (i == PD_BODY_STRUT0 || i == PD_BODY_STRUT1) ? !PD_TOPO_FRONT_DW(topo) : (i == PD_BODY_HUB3 ? PD_TOPO_REAR_DW(topo) : true); }
+/* a double-wishbone corner as a single-body group: hub w held by its five links */
+PD_HD void dw_factor(const PdDW& D, const Body& C, const Body& H, const V3* steer, const BodyDyn& dH, const BodyDyn& dC, float hinv, float dballErp, float dballCfm, float* R, float* S21, float* b6) {
+    SingleSys G; G.R = R; float cfm[6];
+    single_rows_links(D.link, PD_DW_LINKS, C, H, hinv, dballErp, dballCfm, G, cfm, steer);
+    single_factor(G, cfm, dH, dC, hinv, S21, b6);
+}
+template <int TOPO = 0>
 PD_HDN void world_step2(const PdCarParams& P, Body* b, const V3* steerAnchor1, const V3* steerAnchor2, float dballErp, float dballCfm, float h, const float* cont, bool freshContacts, float& lifeLeft, float* dmg) {
+    constexpr bool FDW = PD_TOPO_FRONT_DW(TOPO), RDW = PD_TOPO_REAR_DW(TOPO);
     const float hinv = 1.0f / h;
     BodyDyn dyn[PD_NUM_BODIES];
-    for (int i = 0; i < PD_NUM_BODIES; ++i) body_dyn(b[i], P.gravityY, h, dyn[i]);
+    PD_UNROLL
+    for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body<TOPO>(i)) body_dyn(b[i], P.gravityY, h, dyn[i]);
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
     const Body& C = b[PD_BODY_CHASSIS];
-    float RS[2][PD_GSYS_WORDS], RT[105], RA[105];
+    float RS[2][FDW ? 105 : PD_GSYS_WORDS], RT[105], RA[RDW ? 2 : 1][105];
     float cfm[6];
     { SingleSys GT; GT.R = RT; single_rows_tank(P, b[PD_BODY_TANK], C, hinv, GT, cfm); single_factor(GT, cfm, dyn[PD_BODY_TANK], dyn[PD_BODY_CHASSIS], hinv, S21, b6); }
     PD_NOUNROLL
     for (int s = 0; s < 2; ++s) {
-        StrutSys GS; GS.R = RS[s];
-        strut_factor(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s],
-                     dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, GS, S21, b6);
+        if constexpr (FDW) {
+            const V3 st[2] = {steerAnchor1[s], steerAnchor2[s]};
+            dw_factor(P.dw[s], C, b[PD_BODY_HUB0 + 2 * s], st, dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, RS[s], S21, b6);
+        } else {
+            StrutSys GS; GS.R = RS[s];
+            strut_factor(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s],
+                         dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, GS, S21, b6);
+        }
     }
-    { SingleSys GA; GA.R = RA; single_rows_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, GA, cfm); single_factor(GA, cfm, dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6); }
+    if constexpr (RDW) {
+        PD_NOUNROLL
+        for (int s = 0; s < 2; ++s) dw_factor(P.dw[2 + s], C, b[PD_BODY_HUB2 + s], nullptr, dyn[PD_BODY_HUB2 + s], dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, RA[s], S21, b6);
+    } else { SingleSys GA; GA.R = RA[0]; single_rows_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, GA, cfm); single_factor(GA, cfm, dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6); }
     schur_add_chassis(S21, C);
     float z[6];
     if (cont && reinterpret_cast<const int*>(cont)[0] > 0) contacts_solve(P, cont, C, dyn[PD_BODY_CHASSIS], S21, b6, h, freshContacts, lifeLeft, dmg, z);   /* live contact joints: rows on the chassis */
@@ -408,14 +437,22 @@ PD_HDN void world_step2(const PdCarParams& P, Body* b, const V3* steerAnchor1, c
     { SingleSys GT; GT.R = RT; single_backsolve(GT, z, cfA); apply_update(b[PD_BODY_TANK], dyn[PD_BODY_TANK], cfA, h); }
     PD_NOUNROLL
     for (int s = 0; s < 2; ++s) {
-        StrutSys GS; GS.R = RS[s];
-        strut_backsolve(GS, z, cfA, cfB);
-        apply_update(b[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_HUB0 + 2 * s], cfA, h);
-        apply_update(b[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], cfB, h);
+        if constexpr (FDW) {
+            SingleSys GH; GH.R = RS[s]; single_backsolve(GH, z, cfA); apply_update(b[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_HUB0 + 2 * s], cfA, h);
+        } else {
+            StrutSys GS; GS.R = RS[s];
+            strut_backsolve(GS, z, cfA, cfB);
+            apply_update(b[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_HUB0 + 2 * s], cfA, h);
+            apply_update(b[PD_BODY_STRUT0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s], cfB, h);
+        }
     }
-    { SingleSys GA; GA.R = RA; single_backsolve(GA, z, cfA); apply_update(b[PD_BODY_AXLE], dyn[PD_BODY_AXLE], cfA, h); }
+    if constexpr (RDW) {
+        PD_NOUNROLL
+        for (int s = 0; s < 2; ++s) { SingleSys GH; GH.R = RA[s]; single_backsolve(GH, z, cfA); apply_update(b[PD_BODY_HUB2 + s], dyn[PD_BODY_HUB2 + s], cfA, h); }
+    } else { SingleSys GA; GA.R = RA[0]; single_backsolve(GA, z, cfA); apply_update(b[PD_BODY_AXLE], dyn[PD_BODY_AXLE], cfA, h); }
     chassis_update(b[PD_BODY_CHASSIS], dyn[PD_BODY_CHASSIS], z, h);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) { integrate_body(b[i], h); b[i].F = v3(0, 0, 0); b[i].T = v3(0, 0, 0); }
+    PD_UNROLL
+    for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body<TOPO>(i)) { integrate_body(b[i], h); b[i].F = v3(0, 0, 0); b[i].T = v3(0, 0, 0); }
 }
 
 } // namespace pd

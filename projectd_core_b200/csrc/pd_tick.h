@@ -10,14 +10,23 @@
 
 namespace pd {
 
-PD_HD void set_body_mass(Body* b, const PdCarParams& P) {
+/* topo: the car's suspension topology (PD_TOPO_*; a compile-time constant inside the tick kernels) */
+PD_HD void set_body_mass(Body* b, const PdCarParams& P, int topo) {
     b[PD_BODY_CHASSIS].mass = P.chassisMass; b[PD_BODY_CHASSIS].I = v3(P.chassisInertia[0], P.chassisInertia[1], P.chassisInertia[2]);
     b[PD_BODY_TANK].mass = P.tankMass; b[PD_BODY_TANK].I = v3(P.tankInertia[0], P.tankInertia[1], P.tankInertia[2]);
     for (int s = 0; s < 2; ++s) {
+        if (PD_TOPO_FRONT_DW(topo)) { b[PD_BODY_HUB0 + 2 * s].mass = P.dw[s].hubMass; b[PD_BODY_HUB0 + 2 * s].I = v3(P.dw[s].hubInertia[0], P.dw[s].hubInertia[1], P.dw[s].hubInertia[2]); continue; }
         b[PD_BODY_HUB0 + 2 * s].mass = P.strut[s].hubMass; b[PD_BODY_HUB0 + 2 * s].I = v3(P.strut[s].hubInertia[0], P.strut[s].hubInertia[1], P.strut[s].hubInertia[2]);
         b[PD_BODY_STRUT0 + 2 * s].mass = P.strut[s].strutMass; b[PD_BODY_STRUT0 + 2 * s].I = v3(P.strut[s].strutInertia[0], P.strut[s].strutInertia[1], P.strut[s].strutInertia[2]);
     }
-    b[PD_BODY_AXLE].mass = P.axle.axleMass; b[PD_BODY_AXLE].I = v3(P.axle.axleInertia[0], P.axle.axleInertia[1], P.axle.axleInertia[2]);
+    if (PD_TOPO_REAR_DW(topo)) {
+        for (int s = 0; s < 2; ++s) { b[PD_BODY_HUB2 + s].mass = P.dw[2 + s].hubMass; b[PD_BODY_HUB2 + s].I = v3(P.dw[2 + s].hubInertia[0], P.dw[2 + s].hubInertia[1], P.dw[2 + s].hubInertia[2]); }
+    } else { b[PD_BODY_AXLE].mass = P.axle.axleMass; b[PD_BODY_AXLE].I = v3(P.axle.axleInertia[0], P.axle.axleInertia[1], P.axle.axleInertia[2]); }
+}
+/* SuspensionDW::attach (SuspensionDW.cpp:157-161): hub rotation = the chassis' world matrix, hub at the reference point */
+PD_HD void dw_attach(const PdDW& D, const Body& C, Body& H) {
+    set_rotation(C.fr.ax, C.fr.ay, C.fr.az, H.fr.ax, H.fr.ay, H.fr.az, H.q);
+    H.fr.p = to_world(C.fr, v3(D.refPoint[0], D.refPoint[1], D.refPoint[2]));
 }
 
 /* Car::getBetaRad (Car.cpp:1472-1484) */
@@ -33,7 +42,8 @@ PD_HD float beta_rad(const Body& C) {
  * origin with identity rotation, suspension bodies attached, everything else at its default */
 template <class SVX> PD_HDN void car_init_state(const PdCarParams& P, const SVX& sv) {
     for (int w = 0; w < PD_STATE_WORDS; ++w) sv.i(w, 0);
-    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
+    const int topo = P.topology;
+    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P, topo);
     for (int i = 0; i < PD_NUM_BODIES; ++i) {
         Body& b = bod[i]; b.fr.p = v3(0, 0, 0); b.fr.ax = v3(1, 0, 0); b.fr.ay = v3(0, 1, 0); b.fr.az = v3(0, 0, 1);
         b.q.w = 1; b.q.x = b.q.y = b.q.z = 0; b.v = v3(0, 0, 0); b.w = v3(0, 0, 0);
@@ -41,6 +51,7 @@ template <class SVX> PD_HDN void car_init_state(const PdCarParams& P, const SVX&
     Body& C = bod[PD_BODY_CHASSIS];
     bod[PD_BODY_TANK].fr.p = v3(P.fuelTankPos[0], P.fuelTankPos[1], P.fuelTankPos[2]);
     for (int s = 0; s < 2; ++s) {
+        if (PD_TOPO_FRONT_DW(topo)) { bod[PD_BODY_HUB0 + 2 * s].fr.p = to_world(C.fr, v3(P.dw[s].refPoint[0], P.dw[s].refPoint[1], P.dw[s].refPoint[2])); continue; }
         const PdStrut& S = P.strut[s]; Body& H = bod[PD_BODY_HUB0 + 2 * s]; Body& B = bod[PD_BODY_STRUT0 + 2 * s];
         H.fr.p = to_world(C.fr, v3(S.refPoint[0], S.refPoint[1], S.refPoint[2]));
         const V3 vCarStrut = to_world(C.fr, v3(S.carStrut[0], S.carStrut[1], S.carStrut[2]));
@@ -52,8 +63,9 @@ template <class SVX> PD_HDN void car_init_state(const PdCarParams& P, const SVX&
         set_rotation(vM3NN, vM3N * -1.0f, vNorm * -1.0f, B.fr.ax, B.fr.ay, B.fr.az, B.q);
         B.fr.p = (vNorm * S.strutBodyLength) * 0.5f + vCarStrut;
     }
-    bod[PD_BODY_AXLE].fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
-    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, bod[i]);
+    if (PD_TOPO_REAR_DW(topo)) { for (int s = 0; s < 2; ++s) bod[PD_BODY_HUB2 + s].fr.p = to_world(C.fr, v3(P.dw[2 + s].refPoint[0], P.dw[2 + s].refPoint[1], P.dw[2 + s].refPoint[2])); }
+    else bod[PD_BODY_AXLE].fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
+    for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body_rt(topo, i)) store_body(sv, i, bod[i]);
     for (int w = 0; w < PD_NUM_WHEELS; ++w) { /* Tyre::Tyre + setCompound(0) + reset (Tyre.cpp:15-26,343-425) */
         const int o = PD_OFF_TYRE(w);
         sv.f(o + PD_TYRE_o_pressureStatic, P.tyre[w].pressureStaticDefault); sv.f(o + PD_TYRE_o_pressureDynamic, P.tyre[w].pressureRef);
@@ -98,8 +110,9 @@ PD_HD void teleport_chassis_pose(const PdCarParams& P, const TrackDev& T, int po
 
 /* teleport: Car::teleportToSpline -> forceRotation + forcePosition (Car.cpp:1325-1340,1275-1308,1240-1273) */
 template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, const TrackDev& T, const SVX& sv, int pointId, double physicsTime) {
-    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
+    const int topo = P.topology;
+    Body bod[PD_NUM_BODIES]; set_body_mass(bod, P, topo);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body_rt(topo, i)) load_body(sv, i, bod[i]);
     CarS c; load_car(sv, c);
     Body& C = bod[PD_BODY_CHASSIS]; Body& Tk = bod[PD_BODY_TANK];
     V3 bodyPos;
@@ -117,6 +130,7 @@ template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, con
     Tk.fr.p = to_world(C.fr, v3(P.fuelTankPos[0], P.fuelTankPos[1], P.fuelTankPos[2]));
     /* susp->stop(); susp->attach() */
     for (int s = 0; s < 2; ++s) { /* SuspensionStrut::setPositions (SuspensionStrut.cpp:188-223) */
+        if (PD_TOPO_FRONT_DW(topo)) { Body& H = bod[PD_BODY_HUB0 + 2 * s]; body_stop(H); dw_attach(P.dw[s], C, H); continue; }
         const PdStrut& S = P.strut[s]; Body& H = bod[PD_BODY_HUB0 + 2 * s]; Body& B = bod[PD_BODY_STRUT0 + 2 * s];
         body_stop(H);
         set_rotation(C.fr.ax, C.fr.ay, C.fr.az, H.fr.ax, H.fr.ay, H.fr.az, H.q);   /* hub->setRotation(mxBody) */
@@ -131,7 +145,8 @@ template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, con
         B.fr.p = (vNorm * S.strutBodyLength) * 0.5f + vCarStrut;
         /* NB SuspensionStrut::stop() stops only the hub; the strut body keeps its velocity (reference behaviour) */
     }
-    {
+    if (PD_TOPO_REAR_DW(topo)) { for (int s = 0; s < 2; ++s) { Body& H = bod[PD_BODY_HUB2 + s]; body_stop(H); dw_attach(P.dw[2 + s], C, H); } }
+    else {
         Body& A = bod[PD_BODY_AXLE]; body_stop(A);
         set_rotation(C.fr.ax, C.fr.ay, C.fr.az, A.fr.ax, A.fr.ay, A.fr.az, A.q);
         A.fr.p = to_world(C.fr, v3(P.axle.axleBasePos[0], P.axle.axleBasePos[1], P.axle.axleBasePos[2]));
@@ -139,6 +154,7 @@ template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, con
     /* drivetrain->reset() (Drivetrain.cpp:154-167) */
     c.clutchOpenState = 1; c.rootVel = 0; c.engineVel = 0; c.shaftLVel = 0; c.shaftRVel = 0; c.driveVel = 0;
     c.reqRequest = 0; c.validShiftRPMWindow = P.drivetrain.orgRpmWindow; c.lifeLeft = 1000.0f;
+    c.turboRot0 = 0; c.turboRot1 = 0; c.turboRot2 = 0;          /* Engine::reset -> Turbo::reset (Engine.cpp:160-166); status.turboBoost keeps its last value */
     /* tyres reset (Tyre.cpp:393-425) */
     for (int w = 0; w < PD_NUM_WHEELS; ++w) {
         const int o = PD_OFF_TYRE(w);
@@ -152,7 +168,7 @@ template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, con
     /* drivetrain->setCurrentGear(1, true) */
     c.isGearGrinding = 0; c.currentGear = 1;
     body_stop(C); body_stop(Tk);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, bod[i]);
+    for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body_rt(topo, i)) store_body(sv, i, bod[i]);
     store_car(sv, c);
 }
 
@@ -276,13 +292,15 @@ PD_HD void post_scoring(const PdCarParams& P, const TrackDev& T, const Body& C, 
 }
 
 /* the tick */
-template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch, float* scratchD, int collPre = -1, const float* cont = nullptr) {
+template <int STRIDE, int STRIDE_D, int TOPO = 0, class SVX> PD_HDN void car_tick(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, float* scratch, float* scratchD, int collPre = -1, const float* cont = nullptr) {
     CarS cLocal; CarS* cp = &cLocal;
     if constexpr (sv_traits<SVX>::in_place) cp = car_in_place(sv); else load_car(sv, cLocal);
     CarCtx X(*cp); X.dt = dt; X.time = physicsTime;
+    constexpr bool FDW = PD_TOPO_FRONT_DW(TOPO), RDW = PD_TOPO_REAR_DW(TOPO);
     Body bod[PD_NUM_BODIES]; V3 steerAnchor1[2], steerAnchor2[2];
-    set_body_mass(bod, P);
-    for (int i = 0; i < PD_NUM_BODIES; ++i) load_body(sv, i, bod[i]);
+    set_body_mass(bod, P, TOPO);
+    PD_UNROLL
+    for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body<TOPO>(i)) load_body(sv, i, bod[i]);
     CarS& c = X.c;
     Body& C = bod[PD_BODY_CHASSIS];
 
@@ -292,7 +310,7 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
     { /* Car.cpp:426-451 (car id 0): DBall ERP by speed; CFM = baseCFM = 1e-7 in both branches */
         const float fVelSq = sqlen(C.v);
         X.dballErp = (fVelSq >= 1.0f) ? 0.3f : 0.9f;
-        X.dballCfm = (fVelSq >= 1.0f) ? P.strut[0].baseCFM : 0.0000001f;
+        X.dballCfm = (fVelSq >= 1.0f) ? (FDW ? P.dw[0].baseCFM : P.strut[0].baseCFM) : 0.0000001f;
     }
     c.ctlSteer = tclampf(c.ctlSteer, -1.0f, 1.0f); c.ctlClutch = tclampf(c.ctlClutch, 0.0f, 1.0f); c.ctlBrake = tclampf(c.ctlBrake, 0.0f, 1.0f);
     c.ctlHandBrake = tclampf(c.ctlHandBrake, 0.0f, 1.0f); c.ctlGas = tclampf(c.ctlGas, 0.0f, 1.0f);
@@ -303,7 +321,7 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
     }
     { /* fuel (Car.cpp:476-489) */
         const float fRpmAbs = fabsf(engine_rpm(c));
-        const double fNewFuel = c.fuel - (fRpmAbs * dt * c.gasUsage) * (0.0f + 1.0) * P.fuelConsumptionK * 0.001 * P.fuelConsumptionRate;
+        const double fNewFuel = c.fuel - (fRpmAbs * dt * c.gasUsage) * (tmaxf(0.0f, c.turboBoost) + 1.0) * P.fuelConsumptionK * 0.001 * P.fuelConsumptionRate;
         c.fuel = fNewFuel;
         if (fNewFuel > 0.0f) c.fuelPressure = 1.0f; else { c.fuel = 0; c.fuelPressure = 0; }
     }
@@ -344,40 +362,44 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
     float brakeT[4], handT[4];
     brakes_step(P.brakes, c, brakeT, handT);
     float travel[4], dspeed[4];
-    strut_step(P.strut[0], C, bod[PD_BODY_HUB0], travel[0], dspeed[0]);
-    strut_step(P.strut[1], C, bod[PD_BODY_HUB1], travel[1], dspeed[1]);
-    axle_step(P.axle, C, bod[PD_BODY_AXLE], 0, travel[2], dspeed[2]);
-    axle_step(P.axle, C, bod[PD_BODY_AXLE], 1, travel[3], dspeed[3]);
+    if constexpr (FDW) { dw_step(P.dw[0], C, bod[PD_BODY_HUB0], travel[0], dspeed[0]); dw_step(P.dw[1], C, bod[PD_BODY_HUB1], travel[1], dspeed[1]); }
+    else { strut_step(P.strut[0], C, bod[PD_BODY_HUB0], travel[0], dspeed[0]); strut_step(P.strut[1], C, bod[PD_BODY_HUB1], travel[1], dspeed[1]); }
+    if constexpr (RDW) { dw_step(P.dw[2], C, bod[PD_BODY_HUB2], travel[2], dspeed[2]); dw_step(P.dw[3], C, bod[PD_BODY_HUB3], travel[3], dspeed[3]); }
+    else { axle_step(P.axle, C, bod[PD_BODY_AXLE], 0, travel[2], dspeed[2]); axle_step(P.axle, C, bod[PD_BODY_AXLE], 1, travel[3], dspeed[3]); }
     for (int w = 0; w < 4; ++w) {
         sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspTravel, travel[w]); sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_suspDamperSpeed, dspeed[w]);
     }
     for (int w = 0; w < 4; ++w) {
-        if (w < 2) { Body& H = bod[PD_BODY_HUB0 + 2 * w]; const Frame hf = strut_hub_frame(P.strut[w], H); tyre_step(P, T, w, X, sv, H, hf, C, brakeT[w], handT[w], X.wl[w]); }
+        if (w < 2) { Body& H = bod[PD_BODY_HUB0 + 2 * w]; const Frame hf = FDW ? dw_hub_frame(P.dw[w], H) : strut_hub_frame(P.strut[w], H); tyre_step(P, T, w, X, sv, H, hf, C, brakeT[w], handT[w], X.wl[w]); }
+        else if constexpr (RDW) { Body& H = bod[PD_BODY_HUB2 + (w - 2)]; const Frame hf = dw_hub_frame(P.dw[w], H); tyre_step(P, T, w, X, sv, H, hf, C, brakeT[w], handT[w], X.wl[w]); }
         else { Body& A = bod[PD_BODY_AXLE]; const Frame hf = axle_hub_frame(P.axle, A, w - 2); tyre_step(P, T, w, X, sv, A, hf, C, brakeT[w], handT[w], X.wl[w]); }
     }
     aero_step(P, C);
     { /* SteeringSystem::step -> setSteerLengthOffset -> reseatDistanceJointLocal (incl. its local->world->local round trip) */
         const float steer = -c.finalSteerAngleSignal * P.steerLinearRatio;
         for (int s = 0; s < 2; ++s) {
-            const PdStrut& S = P.strut[s];
-            const float sx = signf_(S.refPoint[0]);
-            const float offx = 0.0f + steer + (sx * S.toeOutLinear);
-            const V3 carSteer = v3(S.baseCarSteer[0] + offx, S.baseCarSteer[1], S.baseCarSteer[2]);
+            const float* refPoint = FDW ? P.dw[s].refPoint : P.strut[s].refPoint;
+            const float* baseCarSteer = FDW ? P.dw[s].baseCarSteer : P.strut[s].baseCarSteer;
+            const float* tyreSteer = FDW ? P.dw[s].tyreSteer : P.strut[s].tyreSteer;
+            const float sx = signf_(refPoint[0]);
+            const float offx = 0.0f + steer + (sx * (FDW ? P.dw[s].toeOutLinear : P.strut[s].toeOutLinear));
+            const V3 carSteer = v3(baseCarSteer[0] + offx, baseCarSteer[1], baseCarSteer[2]);
             const Body& H = bod[PD_BODY_HUB0 + 2 * s];
             steerAnchor1[s] = to_local(C.fr, to_world(C.fr, carSteer));
-            steerAnchor2[s] = to_local(H.fr, to_world(H.fr, v3(S.tyreSteer[0], S.tyreSteer[1], S.tyreSteer[2])));
+            steerAnchor2[s] = to_local(H.fr, to_world(H.fr, v3(tyreSteer[0], tyreSteer[1], tyreSteer[2])));
         }
     }
     autoblip_step(P, X);
     autoshift_step(P, X);
     gearchanger_step(P, X);
-    { const float fAxleTorq = drivetrain_step(P, X); add_rel_torque(C, v3(0, 0, fAxleTorq)); add_rel_torque(bod[PD_BODY_AXLE], v3(0, 0, -fAxleTorq)); }
+    { const float fAxleTorq = drivetrain_step(P, X); if constexpr (!RDW) { add_rel_torque(C, v3(0, 0, fAxleTorq)); add_rel_torque(bod[PD_BODY_AXLE], v3(0, 0, -fAxleTorq)); } }   /* Drivetrain.cpp:547-553: only with a rigid rear axle */
     { /* driven wheels: angular velocity / lock state written by the drivetrain */
         const int dl = (P.drivetrain.tractionType == 1) ? 0 : 2;
         for (int w = dl; w < dl + 2; ++w) { sv.f(PD_OFF_TYRE(w) + PD_TYRE_o_angularVelocity, X.wl[w].angularVelocity); sv.i(PD_OFF_TYRE(w) + PD_TYRE_o_isLocked, X.wl[w].isLocked); }
     }
     arb_step(P.arbK[0], C, bod[PD_BODY_HUB0], bod[PD_BODY_HUB0].fr.p, bod[PD_BODY_HUB1], bod[PD_BODY_HUB1].fr.p);
-    {
+    if constexpr (RDW) arb_step(P.arbK[1], C, bod[PD_BODY_HUB2], bod[PD_BODY_HUB2].fr.p, bod[PD_BODY_HUB3], bod[PD_BODY_HUB3].fr.p);
+    else {
         Body& A = bod[PD_BODY_AXLE];
         const Frame f0 = axle_hub_frame(P.axle, A, 0), f1 = axle_hub_frame(P.axle, A, 1);
         arb_step(P.arbK[1], C, A, f0.p, A, f1.p);
@@ -390,7 +412,7 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
     c.physFrame++;
 #if PD_SOLVER2
     float dmg[5] = {c.damageZone0, c.damageZone1, c.damageZone2, c.damageZone3, c.damageZone4};
-    world_step2(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, cont, freshContacts, c.lifeLeft, dmg);
+    world_step2<TOPO>(P, bod, steerAnchor1, steerAnchor2, X.dballErp, X.dballCfm, dt, cont, freshContacts, c.lifeLeft, dmg);
     X.newDamage = fabsf(dmg[0] - c.damageZone0) > 0.001f || fabsf(dmg[1] - c.damageZone1) > 0.001f || fabsf(dmg[2] - c.damageZone2) > 0.001f || fabsf(dmg[3] - c.damageZone3) > 0.001f || fabsf(dmg[4] - c.damageZone4) > 0.001f;
     c.damageZone0 = dmg[0]; c.damageZone1 = dmg[1]; c.damageZone2 = dmg[2]; c.damageZone3 = dmg[3]; c.damageZone4 = dmg[4];
 #else
@@ -468,10 +490,12 @@ template <int STRIDE, int STRIDE_D, class SVX> PD_HDN void car_tick(const PdCarP
     c.episodeSteps++; c.thermalPrimed = 1;
     {
         int bad = 0;
-        for (int i = 0; i < PD_NUM_BODIES; ++i) { const Body& b = bod[i]; if (!(finitef(b.fr.p.x) && finitef(b.fr.p.y) && finitef(b.fr.p.z) && finitef(b.v.x) && finitef(b.v.y) && finitef(b.v.z) && finitef(b.w.x) && finitef(b.w.y) && finitef(b.w.z) && finitef(b.q.w))) bad = 1; }
+        PD_UNROLL
+        for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body<TOPO>(i)) { const Body& b = bod[i]; if (!(finitef(b.fr.p.x) && finitef(b.fr.p.y) && finitef(b.fr.p.z) && finitef(b.v.x) && finitef(b.v.y) && finitef(b.v.z) && finitef(b.w.x) && finitef(b.w.y) && finitef(b.w.z) && finitef(b.q.w))) bad = 1; }
         if (bad) c.nanFlag = 1;
     }
-    for (int i = 0; i < PD_NUM_BODIES; ++i) store_body(sv, i, bod[i]);
+    PD_UNROLL
+    for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body<TOPO>(i)) store_body(sv, i, bod[i]);
     if constexpr (!sv_traits<SVX>::in_place) store_car(sv, c);
 }
 

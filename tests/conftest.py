@@ -65,6 +65,7 @@ def hostsim():
     H.hs_tick_quad.argtypes = [vp, vp, f, d]
     H.hs_probe_compare.argtypes = [vp, i, vp, vp, vp]
     H.hs_params_bytes.restype = i
+    H.hs_offset_autoshift_rpm.restype = i
     H.hs_teleport_point.argtypes = [vp, vp, i, d]
     H.hs_point_id_at_distance.argtypes = [vp, f]
     H.hs_raycast.argtypes = [vp, i, vp, vp]

@@ -57,11 +57,19 @@ void hs_set_tune(void* h, const char* name, float v) { ((HS*)h)->car.setTune(nam
 void hs_set_scoring_var(void* h, const char* name, float v) { ((HS*)h)->car.setScoringVar(name, v); }
 void hs_set_assists(void* hv, int ac, int as, int ab) { auto& A = ((HS*)hv)->car.P.assists; A.acUseAutoOnStart = ac; A.acUseAutoOnChange = ac; A.asIsActive = as; A.blipIsActive = ab; }
 int hs_params_bytes() { return (int)sizeof(PdCarParams); }
+int hs_offset_autoshift_rpm() { return (int)offsetof(PdCarParams, assists.asChangeUpRpm); }   /* asChangeUpRpm, asChangeDnRpm: resolved lazily by the reference (AutoShifter.cpp:38-53), at load by the loader */
 void hs_get_params(void* h, PdCarParams* out) { *out = ((HS*)h)->car.P; }
 void hs_set_params(void* h, const PdCarParams* in) { ((HS*)h)->car.P = *in; }
 void hs_get_track_info(void* h, PdTrackInfo* out) { *out = ((HS*)h)->track.info; }
 void hs_get_spline_nodes(void* hv, float* xyz, float* dist) { HS* h = (HS*)hv; memcpy(xyz, h->track.splineXYZ.data(), h->track.splineXYZ.size() * 4); memcpy(dist, h->track.splineDist.data(), h->track.splineDist.size() * 4); }
-void hs_tick(void* hv, uint32_t* rec, float dt, double time) { HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS]; pd::car_tick<1, 1>(h->car.P, h->dev, sv, dt, time, scr, scr + PD_GSCR_ROWS_WORDS); }
+void hs_tick(void* hv, uint32_t* rec, float dt, double time) {
+    HS* h = (HS*)hv; pd::SVFlat sv = pd::sv_flat(rec); float scr[PD_GSCR_WORDS];
+    switch (h->car.P.topology) {      /* the same compile-time instances the thread-per-car kernel has */
+    case PD_TOPO_STRUT_DW: pd::car_tick<1, 1, PD_TOPO_STRUT_DW>(h->car.P, h->dev, sv, dt, time, scr, scr + PD_GSCR_ROWS_WORDS); break;
+    case PD_TOPO_DW_DW: pd::car_tick<1, 1, PD_TOPO_DW_DW>(h->car.P, h->dev, sv, dt, time, scr, scr + PD_GSCR_ROWS_WORDS); break;
+    default: pd::car_tick<1, 1>(h->car.P, h->dev, sv, dt, time, scr, scr + PD_GSCR_ROWS_WORDS); break;
+    }
+}
 void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
     /* the GPU lanes of a quad share one record and run converged; host threads do not, so every "lane" gets a private
        copy of the record and the parts each lane owns are merged afterwards:
