@@ -159,8 +159,16 @@ typedef struct PdAssists { /* AutoClutch / AutoBlip / AutoShifter */
     int32_t asChangeUpRpm, asChangeDnRpm; float asSlipThreshold, asGasCutoffTime; int32_t asIsActive, pad0;
 } PdAssists;
 
+typedef struct PdBrakeDisc { /* Car/BrakeSystem.h:15-25 */
+    PdCurve perfCurve;
+    float torqueK, coolTransfer, coolSpeedFactor;
+} PdBrakeDisc;
 typedef struct PdBrakes { /* Car/BrakeSystem.h:43-66 */
     float brakePower, brakePowerMultiplier, handBrakeTorque, frontBias, biasMin, biasMax;
+    int32_t ebbInternal;          /* brakes.ini [EBB]: EBBMode::Internal -- front share follows the load distribution (BrakeSystem.cpp:95-118) */
+    float ebbFrontMultiplier;
+    int32_t hasTemps;             /* brakes.ini [TEMPS_FRONT] + [TEMPS_REAR]: disc temperatures scale the brake torque (BrakeSystem.cpp:151-168) */
+    PdBrakeDisc disc[PD_NUM_WHEELS];
 } PdBrakes;
 
 /* indices into PdCarParams::scoring (Car/ScoringSystem.cpp:50-73, same order) */

@@ -121,7 +121,9 @@
      * (Car.cpp:980-999), read by ScoringSystem::validateDrift (a tick with new damage invalidates the drift); + 1 pad word */ \
     X(F, damageZone0) X(F, damageZone1) X(F, damageZone2) X(F, damageZone3) X(F, damageZone4) X(I, carPad) \
     /* Turbo::rotation of up to three turbochargers (Turbo.h, Turbo.cpp:11-40) and Engine::status.turboBoost (Engine.cpp:368-384) */ \
-    X(F, turboRot0) X(F, turboRot1) X(F, turboRot2) X(F, turboBoost)
+    X(F, turboRot0) X(F, turboRot1) X(F, turboRot2) X(F, turboBoost) \
+    /* BrakeDisc::t of the four discs (BrakeSystem.h:15-25, BrakeSystem.cpp:151-168): only cars with [TEMPS_FRONT] / [TEMPS_REAR] move them */ \
+    X(F, brakeDiscT0) X(F, brakeDiscT1) X(F, brakeDiscT2) X(F, brakeDiscT3)
 
 /* ---------------------------------------------------------------------------------------- */
 #define PD__W_F 1
@@ -144,8 +146,8 @@
 #define PD_OFF_LOOKAHEAD (PD_OFF_PROBES + PD_MAX_PROBES)
 #define PD_STATE_WORDS   (PD_OFF_CAR + PD_CAR_WORDS)
 /* record stride of the array-of-records device layout: a multiple of 4 words (16-byte bulk copies) whose value
- * mod 32 (= 20) spreads the same word of 8 consecutive records over 8 different shared-memory bank groups */
-#define PD_STATE_STRIDE  660
+ * mod 32 (= 28: its multiples run through 0, 28, 24, 20, 16, 12, 8, 4) spreads the same word of 8 consecutive records over 8 different shared-memory bank groups */
+#define PD_STATE_STRIDE  668
 
 /* per-field word offsets inside their group: PD_BODY_o_px, PD_TYRE_o_load, PD_CAR_o_fuel ... */
 #define PD__ENUM_B(kind, name) PD_BODY_o_##name, PD_BODY_e_##name = PD_BODY_o_##name + PD__W_##kind - 1,

@@ -238,6 +238,7 @@ void pdref_get_state(void* hv, uint32_t* r) {
         CI(thermalPrimed, c->tyres[0]->thermalModel->patches[5].inputT == 0.0f ? 1 : 0);
         CI(physFrame, (int)pdref_get_frame(h->sim->physics.get()));
         { const auto& tb = e->turbos; if (tb.size() > 0) CF(turboRot0, tb[0]->rotation); if (tb.size() > 1) CF(turboRot1, tb[1]->rotation); if (tb.size() > 2) CF(turboRot2, tb[2]->rotation); CF(turboBoost, e->status.turboBoost); }
+        { BrakeSystem* bs = c->brakeSystem.get(); CF(brakeDiscT0, bs->discs[0].t); CF(brakeDiscT1, bs->discs[1].t); CF(brakeDiscT2, bs->discs[2].t); CF(brakeDiscT3, bs->discs[3].t); }
         CF(damageZone0, c->damageZoneLevel[0]); CF(damageZone1, c->damageZoneLevel[1]); CF(damageZone2, c->damageZoneLevel[2]); CF(damageZone3, c->damageZoneLevel[3]); CF(damageZone4, c->damageZoneLevel[4]);
         for (size_t i = 0; i < c->probeHits.size() && i < PD_MAX_PROBES; ++i) putF(r, PD_OFF_PROBES + (int)i, c->probeHits[i]);
         for (size_t i = 0; i < c->lookAhead.size() && i < PD_LOOKAHEAD; ++i) putF(r, PD_OFF_LOOKAHEAD + (int)i, c->lookAhead[i]);
@@ -302,6 +303,7 @@ void pdref_set_state(void* hv, const uint32_t* r) {
         c->collisionFlag = CI(collisionFlag) != 0; c->outOfTrackFlag = CI(outOfTrackFlag) != 0;
         pdref_set_frame(h->sim->physics.get(), (unsigned int)CI(physFrame));
         { auto& tb = e->turbos; if (tb.size() > 0) tb[0]->rotation = CF(turboRot0); if (tb.size() > 1) tb[1]->rotation = CF(turboRot1); if (tb.size() > 2) tb[2]->rotation = CF(turboRot2); e->status.turboBoost = CF(turboBoost); }
+        { BrakeSystem* bs = c->brakeSystem.get(); bs->discs[0].t = CF(brakeDiscT0); bs->discs[1].t = CF(brakeDiscT1); bs->discs[2].t = CF(brakeDiscT2); bs->discs[3].t = CF(brakeDiscT3); }
         c->damageZoneLevel[0] = CF(damageZone0); c->damageZoneLevel[1] = CF(damageZone1); c->damageZoneLevel[2] = CF(damageZone2); c->damageZoneLevel[3] = CF(damageZone3); c->damageZoneLevel[4] = CF(damageZone4);
         for (int i = 0; i < 5; ++i) c->oldDamageZoneLevel[i] = c->damageZoneLevel[i];        /* Car::postStep leaves them equal (Car.cpp:706-707) */
         c->nearestTrackPointId = CI(nearestTrackPointId); c->oldTrackPointId = CI(oldTrackPointId); c->splinePointId = CI(splinePointId);
@@ -392,7 +394,11 @@ void pdref_get_params(void* hv, PdCarParams* P) {
     }
     P->arbK[0] = c->antirollBars[0]->k; P->arbK[1] = c->antirollBars[1]->k;
     { BrakeSystem* b = c->brakeSystem.get(); P->brakes.brakePower = b->brakePower; P->brakes.brakePowerMultiplier = b->brakePowerMultiplier;
-      P->brakes.handBrakeTorque = b->handBrakeTorque; P->brakes.frontBias = b->frontBias; P->brakes.biasMin = b->biasMin; P->brakes.biasMax = b->biasMax; }
+      P->brakes.handBrakeTorque = b->handBrakeTorque; P->brakes.frontBias = b->frontBias; P->brakes.biasMin = b->biasMin; P->brakes.biasMax = b->biasMax;
+      P->brakes.ebbInternal = b->ebbMode == EBBMode::Internal ? 1 : 0; P->brakes.ebbFrontMultiplier = P->brakes.ebbInternal ? b->ebbFrontMultiplier : 0.0f;
+      P->brakes.hasTemps = b->hasBrakeTempsData ? 1 : 0;
+      if (b->hasBrakeTempsData) for (int i = 0; i < 4; ++i) { copy_curve(P->brakes.disc[i].perfCurve, b->discs[i].perfCurve); P->brakes.disc[i].torqueK = b->discs[i].torqueK; P->brakes.disc[i].coolTransfer = b->discs[i].coolTransfer; P->brakes.disc[i].coolSpeedFactor = b->discs[i].coolSpeedFactor; }
+      if (b->ebbMode == EBBMode::DynamicController || b->steerBrake.isActive) fprintf(stderr, "[oracle] brake controllers present: not exported\n"); }
     for (int w = 0; w < 4; ++w) {
         Tyre* t = c->tyres[w].get(); PdTyre& d = P->tyre[w]; SCTM* m = t->tyreModel.get();
         d.width = t->data.width; d.radius = t->data.radius; d.rimRadius = t->data.rimRadius; d.k = t->data.k; d.d = t->data.d; d.angularInertia = t->data.angularInertia;

@@ -622,8 +622,18 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
         P.brakes.brakePower = b.getFloat("DATA", "MAX_TORQUE"); P.brakes.frontBias = b.getFloat("DATA", "FRONT_SHARE");
         P.brakes.handBrakeTorque = b.getFloat("DATA", "HANDBRAKE_TORQUE"); P.brakes.brakePowerMultiplier = 1.0f;
         P.brakes.biasMin = 0; P.brakes.biasMax = 1.0f;
-        if (b.hasSection("EBB") || file_exists(dataPath + "ctrl_ebb.ini") || file_exists(dataPath + "steer_brake_controller.ini") || (b.hasSection("TEMPS_FRONT") && b.hasSection("TEMPS_REAR")))
-            throw Error("EBB / steer-brake / brake-disc temperatures are not supported yet (SURVEY.md N1)");
+        if (file_exists(dataPath + "ctrl_ebb.ini") || file_exists(dataPath + "steer_brake_controller.ini"))
+            throw Error("brake dynamic controllers (ctrl_ebb.ini, steer_brake_controller.ini) are not supported yet (SURVEY.md N4)");
+        if (b.hasSection("EBB")) { P.brakes.ebbInternal = 1; const float m = b.getFloat("EBB", "FRONT_SHARE_MULTIPLIER"); P.brakes.ebbFrontMultiplier = m > 1.1f ? m : 1.1f; }
+        if (b.hasSection("TEMPS_FRONT") && b.hasSection("TEMPS_REAR")) { /* BrakeSystem.cpp:41-54 */
+            P.brakes.hasTemps = 1;
+            for (int id = 0; id < 4; ++id) {
+                const std::string sec = id < 2 ? "TEMPS_FRONT" : "TEMPS_REAR";
+                PdBrakeDisc& D = P.brakes.disc[id];
+                D.perfCurve = b.getCurve(sec, "PERF_CURVE"); D.torqueK = b.getFloat(sec, "TORQUE_K");
+                D.coolTransfer = b.getFloat(sec, "COOL_TRANSFER"); D.coolSpeedFactor = b.getFloat(sec, "COOL_SPEED_FACTOR");
+            }
+        }
         Ini s(dataPath + "setup.ini");
         if (s.ready && s.hasSection("FRONT_BIAS")) { P.brakes.biasMin = s.getFloat("FRONT_BIAS", "MIN") * 0.01f; P.brakes.biasMax = s.getFloat("FRONT_BIAS", "MAX") * 0.01f; }
     }

@@ -209,9 +209,17 @@ PD_HD void arb_step(float k, Body& C, Body& H0, V3 hubWorld0, Body& H1, V3 hubWo
     }
 }
 
-/* BrakeSystem::step (BrakeSystem.cpp:82-149); EBB / steer-brake / disc temps are absent on the demo car */
-PD_HD void brakes_step(const PdBrakes& P, const CarS& c, float* brakeTorque, float* handBrakeTorque) {
-    float fFrontBias = tclampf(P.frontBias, P.biasMin, P.biasMax);
+/* BrakeSystem::step (BrakeSystem.cpp:82-168): front share (fixed or EBBMode::Internal), torques, disc temperatures; the dynamic
+ * controllers (ctrl_ebb.ini, steer_brake_controller.ini) are rejected by the loader.  sv: the tyres' state of the last tick */
+template <class SVX> PD_HD void brakes_step(const PdBrakes& P, CarS& c, const SVX& sv, float ambient, float dt, float* brakeTorque, float* handBrakeTorque) {
+    float fFrontBias = P.frontBias;
+    if (P.ebbInternal) {
+        const float fLoadFront = sv.f(PD_OFF_TYRE(1) + PD_TYRE_o_load) + sv.f(PD_OFF_TYRE(0) + PD_TYRE_o_load);
+        const float fLoadAWD = (sv.f(PD_OFF_TYRE(3) + PD_TYRE_o_load) + sv.f(PD_OFF_TYRE(2) + PD_TYRE_o_load)) + fLoadFront;
+        const bool bFlag = fLoadAWD != 0.0f && (c.speed * 3.6f) > 10.0f;
+        fFrontBias = bFlag ? tclampf(((fLoadFront / fLoadAWD) * P.ebbFrontMultiplier), 0.0f, 1.0f) : P.frontBias;
+    }
+    fFrontBias = tclampf(fFrontBias, P.biasMin, P.biasMax);
     const float fBrakeInput = tmaxf(c.ctlBrake, 0.0f /* brakeOverride */);
     const float fBrakeTorq = (P.brakePower * P.brakePowerMultiplier) * fBrakeInput;
     brakeTorque[0] = fBrakeTorq * fFrontBias;
@@ -222,6 +230,19 @@ PD_HD void brakes_step(const PdBrakes& P, const CarS& c, float* brakeTorque, flo
     handBrakeTorque[0] = 0; handBrakeTorque[1] = 0;
     handBrakeTorque[2] = c.ctlHandBrake * P.handBrakeTorque;
     handBrakeTorque[3] = c.ctlHandBrake * P.handBrakeTorque;
+    if (P.hasTemps) { /* BrakeSystem::stepTemps (BrakeSystem.cpp:151-168) */
+        const float fSpeed = c.speed * 3.6f;
+        float* T[4] = {&c.brakeDiscT0, &c.brakeDiscT1, &c.brakeDiscT2, &c.brakeDiscT3};
+        for (int i = 0; i < 4; ++i) {
+            const PdBrakeDisc& D = P.disc[i];
+            float t = *T[i];
+            brakeTorque[i] = curve_value(D.perfCurve, t) * brakeTorque[i];
+            const float fCool = ((fSpeed * D.coolSpeedFactor) + 1.0f) * D.coolTransfer;
+            t += (((ambient - t) * fCool) * dt);
+            t += (((fabsf(sv.f(PD_OFF_TYRE(i) + PD_TYRE_o_angularVelocity)) * (brakeTorque[i] * D.torqueK)) * 0.001f) * dt);
+            *T[i] = t;
+        }
+    }
 }
 
 /* ================================ tyre ================================ */

@@ -116,9 +116,9 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
 
     /* ---------------- stepComponents: one wheel per lane ---------------- */
     float brakeT[4], handT[4];
-    brakes_step(P.brakes, c, brakeT, handT);
+    brakes_step(P.brakes, c, sv, P.ambientTemperature, dt, brakeT, handT);      /* all lanes, identical (reads the four tyres' state of the last tick before any lane's tyre step writes) */
     PD_PHASE(X, 1);
-    const float myBrake = front ? brakeT[0] : brakeT[2], myHand = front ? handT[0] : handT[2];
+    const float myBrake = brakeT[lane], myHand = handT[lane];          /* per wheel: disc temperatures (cars with [TEMPS_*]) scale each wheel's torque */
     float travel, dspeed;
     Frame hf;
     if (front) { strut_step(P.strut[lane], C, W, travel, dspeed); hf = strut_hub_frame(P.strut[lane], W); }

@@ -154,6 +154,7 @@ template <class SVX> PD_HDN void car_teleport_to_point(const PdCarParams& P, con
     /* drivetrain->reset() (Drivetrain.cpp:154-167) */
     c.clutchOpenState = 1; c.rootVel = 0; c.engineVel = 0; c.shaftLVel = 0; c.shaftRVel = 0; c.driveVel = 0;
     c.reqRequest = 0; c.validShiftRPMWindow = P.drivetrain.orgRpmWindow; c.lifeLeft = 1000.0f;
+    c.brakeDiscT0 = P.ambientTemperature; c.brakeDiscT1 = P.ambientTemperature; c.brakeDiscT2 = P.ambientTemperature; c.brakeDiscT3 = P.ambientTemperature;   /* brakeSystem->reset() (BrakeSystem.cpp:73-80) */
     c.turboRot0 = 0; c.turboRot1 = 0; c.turboRot2 = 0;          /* Engine::reset -> Turbo::reset (Engine.cpp:160-166); status.turboBoost keeps its last value */
     /* tyres reset (Tyre.cpp:393-425) */
     for (int w = 0; w < PD_NUM_WHEELS; ++w) {
@@ -360,7 +361,7 @@ template <int STRIDE, int STRIDE_D, int TOPO = 0, class SVX> PD_HDN void car_tic
 
     /* ---------------- stepComponents ---------------- */
     float brakeT[4], handT[4];
-    brakes_step(P.brakes, c, brakeT, handT);
+    brakes_step(P.brakes, c, sv, P.ambientTemperature, dt, brakeT, handT);
     float travel[4], dspeed[4];
     if constexpr (FDW) { dw_step(P.dw[0], C, bod[PD_BODY_HUB0], travel[0], dspeed[0]); dw_step(P.dw[1], C, bod[PD_BODY_HUB1], travel[1], dspeed[1]); }
     else { strut_step(P.strut[0], C, bod[PD_BODY_HUB0], travel[0], dspeed[0]); strut_step(P.strut[1], C, bod[PD_BODY_HUB1], travel[1], dspeed[1]); }

@@ -283,11 +283,11 @@ def _nudged(lay, rec, mode):
     return out
 
 
-def arbitrate(oracle_mod, lay, track, before, time_before, ref_after, bad, tol=1e-4, factor=4.0, dt=1.0 / 333.0, car=None):
+def arbitrate(oracle_mod, lay, track, before, time_before, ref_after, bad, tol=1e-4, factor=4.0, dt=1.0 / 333.0, car=None, base=None):
     """bad: list of (field, mine, ref, rel) from compare_records.  Returns the entries that remain bad after arbitration."""
-    r = _ARB_SIMS.get((track, car))
+    r = _ARB_SIMS.get((track, car, base))
     if r is None:
-        r = _ARB_SIMS[(track, car)] = oracle_mod.RefSim(track=track, **({"car": car} if car else {}))
+        r = _ARB_SIMS[(track, car, base)] = oracle_mod.RefSim(track=track, **({"car": car} if car else {}), **({"base": base} if base else {}))
     spread = {}
     for mode in (0, 1, 2):
         r.set_state(_nudged(lay, before, mode)); r.set_time(time_before); r.step(dt)
@@ -301,3 +301,24 @@ def arbitrate(oracle_mod, lay, track, before, time_before, ref_after, bad, tol=1
         if not np.isfinite(rel) or abs(mine - ref) > factor * spread.get(name, 0.0) + tol * max(abs(ref), field_floor(name)):
             left.append((name, mine, ref, rel, spread.get(name, 0.0)))
     return left
+
+
+def make_brake_temps_base(tmp_dir, base, car="ks_toyota_ae86_drift", new_name="ae86_brake_temps"):
+    """A content tree (symlinks into `base`) with one extra car: `car` plus [TEMPS_FRONT] / [TEMPS_REAR] / [EBB] in its brakes.ini
+    -- the optional BrakeSystem parts no bundled car ships data for (BrakeSystem.cpp:28-54: 'cars: F40').  Returns (base, car)."""
+    import os, shutil
+    root = os.path.join(str(tmp_dir), "base")
+    os.makedirs(os.path.join(root, "content", "cars"), exist_ok=True)
+    for d in ("cfg",):
+        if not os.path.exists(os.path.join(root, d)):
+            os.symlink(os.path.join(base, d), os.path.join(root, d))
+    if not os.path.exists(os.path.join(root, "content", "tracks")):
+        os.symlink(os.path.join(base, "content", "tracks"), os.path.join(root, "content", "tracks"))
+    dst = os.path.join(root, "content", "cars", new_name)
+    if not os.path.isdir(dst):
+        shutil.copytree(os.path.join(base, "content", "cars", car), dst)
+        with open(os.path.join(dst, "data", "brakes.ini"), "a") as f:
+            f.write("\n[EBB]\nFRONT_SHARE_MULTIPLIER=1.25\n\n"
+                    "[TEMPS_FRONT]\nPERF_CURVE=(|0=0.85|150=0.95|300=1.0|600=1.0|800=0.7|)\nTORQUE_K=0.12\nCOOL_TRANSFER=0.006\nCOOL_SPEED_FACTOR=0.0015\n\n"
+                    "[TEMPS_REAR]\nPERF_CURVE=(|0=0.8|200=1.0|500=1.0|700=0.75|)\nTORQUE_K=0.09\nCOOL_TRANSFER=0.004\nCOOL_SPEED_FACTOR=0.001\n")
+    return root, new_name

@@ -47,7 +47,7 @@ def test_layout_constants_agree():
     from projectd_core_b200 import load_library
     import pdref
     L = load_library()
-    assert L.pd_state_words() == pdref.Layout().words == 660
+    assert L.pd_state_words() == pdref.Layout().words == 664
     assert L.pd_obs_dim() == 24
     assert L.pd_car_state_bytes() == 664
     from projectd_core_b200.pyprojectd import CAR_STATE_DTYPE

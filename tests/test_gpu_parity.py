@@ -819,3 +819,36 @@ def test_vector_env_interface(oracle):
         seen_done |= term
     assert int(seen_done.sum()) >= n // 16 and after_reset_ok > 0
     env.close()
+
+
+@pytest.mark.parametrize("kernel", ["k_tick_quad<4>", "k_tick"])
+def test_brake_disc_temperatures_and_ebb(oracle, lay, kernel, monkeypatch, tmp_path, hostsim):
+    """BrakeSystem's optional parts on the GPU (disc temperatures BrakeSystem.cpp:151-168, EBBMode::Internal :95-118), on a derived
+    car whose brakes.ini carries [TEMPS_*] / [EBB] (no bundled car ships that data): single-tick rule on both tick kernels."""
+    from projectd_core_b200 import Batch
+    from parity_util import make_brake_temps_base, params_equal
+    _select_kernel(monkeypatch, kernel)
+    base, car = make_brake_temps_base(tmp_path, oracle.BASE_PATH)
+    n = 32
+    b = make_env_like(Batch(base, n_envs=n, device=0, car=car))
+    refs = [oracle.RefSim(car=car, base=base) for _ in range(n)]
+    assert params_equal(b.params_bytes(), refs[0].params_bytes(), hostsim)
+    for i, r in enumerate(refs):
+        r.teleport_spline(i / n)
+    hot = 0.0
+    for t in range(500):
+        for i, r in enumerate(refs):
+            brake = 0.3 + 0.02 * i if (t % 250) > 170 else 0.0
+            r.set_controls(steer=0.2 * math.sin(0.01 * t + i), gas=0.0 if brake else 1.0, brake=brake)
+        before = [r.state() for r in refs]; tb = refs[0].time()
+        b.restore(np.stack(before, axis=1)); b.set_time(tb); b.step(DT, 1)
+        out = b.snapshot()
+        for i, r in enumerate(refs):
+            r.set_state(before[i]); r.step()
+            ref = r.state()
+            bad, w = compare_records(lay, out[:, i], ref, tol=1e-4)
+            if bad:
+                left = arbitrate(oracle, lay, "driftplayground", before[i], tb, ref, bad, car=car, base=base)
+                assert not left, (t, i, left[:5])
+            hot = max(hot, lay.get(out[:, i], "car.brakeDiscT0"))
+    assert hot > 20.01

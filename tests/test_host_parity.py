@@ -198,3 +198,41 @@ def test_other_cars_loader_and_single_tick(hostsim, oracle, content_base, car):
         boost = max(boost, lay.get(rec, "car.turboBoost"))
     assert boost > 0.01
     hostsim.hs_destroy(h)
+
+
+def test_brake_disc_temperatures_and_ebb(hostsim, oracle, content_base, tmp_path):
+    """BrakeSystem's optional parts (disc temperatures BrakeSystem.cpp:151-168, EBBMode::Internal :95-118) on a derived car whose
+    brakes.ini carries [TEMPS_*] / [EBB]: loader block = reference init, and the braking ticks follow the oracle (disc temperatures
+    rise, per-wheel brake torques follow the performance curves)."""
+    from parity_util import compare_records, make_brake_temps_base, params_equal
+    base, car = make_brake_temps_base(tmp_path, content_base)
+    r = oracle.RefSim(car=car, base=base); r.set_collision_response(False)
+    h = hostsim.hs_create(base.encode(), b"driftplayground", car.encode())
+    assert h
+    hostsim.hs_set_assists(h, 1, 1, 1)
+    for k, v in oracle.ENV_TUNES.items():
+        hostsim.hs_set_tune(h, k.encode(), v)
+    for k, v in oracle.ENV_SCORING.items():
+        hostsim.hs_set_scoring_var(h, k.encode(), v)
+    mine = np.zeros(hostsim.hs_params_bytes(), np.uint8); hostsim.hs_get_params(h, mine.ctypes.data)
+    assert params_equal(mine, r.params_bytes(), hostsim)
+    lay = oracle.Layout()
+    r.teleport_spline(0.1)
+    hot = 0.0
+    for t in range(700):
+        brake = 0.8 if (t % 350) > 250 else 0.0
+        r.set_controls(steer=0.1 * math.sin(0.01 * t), gas=0.0 if brake else 1.0, brake=brake)
+        rec = r.state().copy(); tb = r.time()
+        forms = (hostsim.hs_tick, hostsim.hs_tick_quad) if t % 7 == 0 else (hostsim.hs_tick,)      # thread-per-car form every tick, the 4-lane form every 7th
+        outs = []
+        for fn in forms:
+            mine = rec.copy(); fn(h, mine.ctypes.data, DT, tb); outs.append(mine)
+        first = outs[0]
+        r.step()
+        for mine in outs:
+            bad, worst = compare_records(lay, mine, r.state(), tol=1e-4)
+            bad = [x for x in bad if not (x[0].endswith(".wz") and x[3] < 5e-4)]
+            assert not bad, (t, bad[:6])
+        hot = max(hot, lay.get(first, "car.brakeDiscT0"))
+    assert hot > 20.01, "the discs never warmed up"      # 2 s of simulated time: a few hundredths of a kelvin above the 20 C ambient
+    hostsim.hs_destroy(h)

@@ -14,10 +14,10 @@ DT = 1.0 / 333.0
 
 
 def test_golden_file_shape(golden):
-    lay_words = 660
+    lay_words = 664
     assert golden["traj_state"].shape == (41, lay_words)
     assert golden["pair_before"].shape == golden["pair_after"].shape and golden["pair_before"].shape[1] == lay_words
-    assert golden["params"].size == 19056
+    assert golden["params"].size == 19904
 
 
 def test_spline_cache_known_answers_oracle(oracle):
