@@ -48,7 +48,12 @@ struct Builder {
         for (int k = 0; k < 3; ++k) { mn[k] = 3.4e38f; mx[k] = -3.4e38f; }
         for (uint32_t i = lo; i < hi; ++i) { uint32_t t = order[i]; for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], tmin[t * 3 + k]); mx[k] = std::max(mx[k], tmax[t * 3 + k]); } }
     }
-    void build(int nodeIdx, uint32_t lo, uint32_t hi) {
+    int maxDepth = 0;
+    /* median split on the widest centroid axis, leaves of <= 4 triangles: the tree is balanced, depth <= ceil(log2(n / 4)) + 1
+       (21 for a million triangles).  The traversal (pd_track.h ray_cast) pushes both children of an interior node after popping it,
+       so its stack never holds more than depth + 1 entries: PD_RAY_STACK (48) cannot overflow; build_bvh checks it. */
+    void build(int nodeIdx, uint32_t lo, uint32_t hi, int depth = 0) {
+        if (depth > maxDepth) maxDepth = depth;
         float mn[3], mx[3]; bounds(lo, hi, mn, mx);
         for (int k = 0; k < 3; ++k) {   /* conservative padding: the box test is only a filter */
             float pad = 1e-4f * std::max(1.0f, std::max(fabsf(mn[k]), fabsf(mx[k])));
@@ -67,7 +72,7 @@ struct Builder {
         const int left = (int)nodes.size();
         nodes.push_back(BvhNodeH{}); nodes.push_back(BvhNodeH{});
         nodes[nodeIdx].left = left; nodes[nodeIdx].count = 0;
-        build(left, lo, mid); build(left + 1, mid, hi);
+        build(left, lo, mid, depth + 1); build(left + 1, mid, hi, depth + 1);
     }
 };
 }
@@ -87,6 +92,7 @@ void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& sur
     }
     B.nodes.reserve(nt); B.nodes.push_back(BvhNodeH{});
     if (nt > 0) B.build(0, 0, nt);
+    if (B.maxDepth + 1 > 46) throw Error("BVH deeper than the ray caster's stack allows");      /* cannot happen with the median split; guards a future builder */
     out.nodes = B.nodes;
     out.tris.assign((size_t)nt * PD_TRI_STRIDE, 0.0f); out.triSurf.resize(nt);
     for (uint32_t i = 0; i < nt; ++i) {

@@ -94,7 +94,7 @@ PD_HDN RayHit ray_cast(const TrackDev& T, V3 o, V3 d, float length) {
         if (d.z != 0.0f) { float a = (nd.bmin[2] - o.z) * inv.z, b = (nd.bmax[2] - o.z) * inv.z; t0 = tmaxf(t0, tminf(a, b)); t1 = tminf(t1, tmaxf(a, b)); } else if (o.z < nd.bmin[2] || o.z > nd.bmax[2]) miss = true;
         if (miss || t0 > t1) continue;
         if (nd.count == 0) {
-            if (sp + 2 <= 48) { stack[sp++] = nd.left; stack[sp++] = nd.left + 1; }
+            if (sp + 2 <= 48) { stack[sp++] = nd.left; stack[sp++] = nd.left + 1; }      /* always true: the builder's trees are balanced (depth <= 46 checked at load, track_loader.cpp build_bvh), the stack holds <= depth + 1 */
             continue;
         }
         for (int k = 0; k < nd.count; ++k) {
