@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(
         }
         __syncthreads();      /* poses and frame parities are in the collision warp's registers: the tick may start changing the records */
         if (warp == 2) {
+            /* (a lane per car for the floor test, as k_collide2 does, was measured SLOWER here: 22.4 vs 25.8 M car-ticks/s at 4096 envs -- the serial
+               lane's chain of dependent loads ends later than eight warp-wide tests, and the quads wait for the answer) */
             for (int k = 0; k < ncars; ++k) {
                 if (!__shfl_sync(0xffffffffu, need, k)) continue;
                 Body Cc;
@@ -327,6 +329,52 @@ __global__ void __launch_bounds__(PD_COLLIDE_BLOCK, PD_COLLIDE_MINBLOCKS) k_coll
     const bool any = car_collide_warp<true>(P, T, C, lane, hullS + (threadIdx.x >> 5) * PD_HULLS_WORDS, dbg ? stats : nullptr);
     if (lane == 0) collOut[e] = any ? 1 : 0;
     if (dbg && lane == 0) { dbg[4096 + (size_t)n * 12 + (size_t)e * 4] = clock64() - clk0; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 1] = ((long long)stats[0] << 32) | (unsigned)stats[1]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 2] = ((long long)stats[2] << 32) | (unsigned)stats[3]; dbg[4096 + (size_t)n * 12 + (size_t)e * 4 + 3] = (long long)any | ((long long)stats[4] << 8) | ((long long)stats[5] << 36); }
+}
+
+/* The same answers, with the work where it is (measured on B200, tools/collide_tail.py: 93 % of the cars in a steady-state rollout only ever reach
+ * the floor-box x TRACK-triangle loop, where a warp per car spends 17 k cycles on 5 rounds of at most 32 entries; 7 % have WALL triangles in the
+ * hull's height range, 0.3 % reach the narrow phase): ONE THREAD PER CAR runs the floor test (car_collide, walls left out) and notes whether the
+ * footprint holds wall triangles at hull height; the warp then takes those cars one after the other through the hull x WALL test with all
+ * 32 lanes (car_collide_warp, floor left out).  Same predicates on the same data as k_collide, any-hit: identical flags. */
+template <int LPC>      /* lanes per car of the floor test: the cells of the footprint are dealt to them (car_collide's cellPart / cellParts) */
+__global__ void __launch_bounds__(PD_COLLIDE_BLOCK, PD_COLLIDE_MINBLOCKS) k_collide2(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, const uint32_t* __restrict__ state, int layout, int n,
+                                                              const int32_t* __restrict__ pending, int32_t* __restrict__ collOut,
+                                                              int teleportMode, uint64_t seed, uint64_t idOffset, const uint32_t* __restrict__ episodeCtr) {
+    const int lane = threadIdx.x & 31, sub = lane % LPC;
+    const int e = (blockIdx.x * PD_COLLIDE_BLOCK + threadIdx.x) / LPC;
+    const unsigned FULL = 0xffffffffu;
+    __shared__ __align__(16) float hullS[(PD_COLLIDE_BLOCK / 32) * PD_HULLS_WORDS];
+    Body C; C.fr.p = v3(0, 0, 0); C.fr.ax = v3(1, 0, 0); C.fr.ay = v3(0, 1, 0); C.fr.az = v3(0, 0, 1);
+    bool hit = false, walls = false;
+    if (e < n) {
+        SVR sv = sv_env(layout, const_cast<uint32_t*>(state), (size_t)e);
+        if (sv.i(PD_OFF_CAR + PD_CAR_o_physFrame) & 1) {
+            load_body(sv, PD_BODY_CHASSIS, C);
+            if (pending && pending[e]) {       /* reset inside the coming tick kernel, before its collision step: the pose the teleport will give (see k_collide) */
+                float u = 0.0f;
+                if (teleportMode == PD_TELEPORT_NEAREST) u = sv.f(PD_OFF_CAR + PD_CAR_o_trackLocation);
+                else if (teleportMode == PD_TELEPORT_RANDOM) u = pd_uniform(seed, idOffset + (uint64_t)e, episodeCtr[e]);
+                Quat q; teleport_chassis_pose(P, T, point_id_at_distance(T, u), C.fr.ax, C.fr.ay, C.fr.az, q, C.fr.p);
+            }
+            hit = car_collide(P, T, C, 0, 1, sub, LPC, 1, &walls);
+        }
+    }
+    PD_UNROLL
+    for (int off = 1; off < LPC; off <<= 1) { hit = __shfl_xor_sync(FULL, (int)hit, off) || hit; walls = __shfl_xor_sync(FULL, (int)walls, off) || walls; }
+    if (hit) walls = false;
+    unsigned m = __ballot_sync(FULL, walls && sub == 0);
+    while (m) {
+        const int k = __ffs(m) - 1; m &= m - 1;
+        Body Cc;
+        Cc.fr.p = v3(__shfl_sync(FULL, C.fr.p.x, k), __shfl_sync(FULL, C.fr.p.y, k), __shfl_sync(FULL, C.fr.p.z, k));
+        Cc.fr.ax = v3(__shfl_sync(FULL, C.fr.ax.x, k), __shfl_sync(FULL, C.fr.ax.y, k), __shfl_sync(FULL, C.fr.ax.z, k));
+        Cc.fr.ay = v3(__shfl_sync(FULL, C.fr.ay.x, k), __shfl_sync(FULL, C.fr.ay.y, k), __shfl_sync(FULL, C.fr.ay.z, k));
+        Cc.fr.az = v3(__shfl_sync(FULL, C.fr.az.x, k), __shfl_sync(FULL, C.fr.az.y, k), __shfl_sync(FULL, C.fr.az.z, k));
+        const bool wh = car_collide_warp<true, false>(P, T, Cc, lane, hullS + (threadIdx.x >> 5) * PD_HULLS_WORDS, nullptr);
+        if (lane == k && wh) hit = true;
+        __syncwarp(FULL);        /* the next car re-stages the hull tables of this warp's slot only after every lane is done with them */
+    }
+    if (e < n && sub == 0) collOut[e] = hit ? 1 : 0;
 }
 
 /* Collision response: the contact joints of this odd frame (PhysicsEngineODE.cpp:230-236: the frame's contact group is emptied, then
@@ -531,6 +579,8 @@ struct pd_batch {
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     long long* dClk = nullptr; int nClk = 0;
     int serialSmemPad = 0;            /* tuning knob (env PD_SERIAL_SMEM_PAD, bytes): unused dynamic shared memory per block of k_tick, caps the resident blocks per SM */
+    int collideLpc = 4;               /* env PD_COLLIDE_LPC: lanes per car of k_collide2's floor test (1 / 4 / 8 / 16); measured at 65536 envs: 79.4 / 81.1 / 80.2 / 78.2 M car-ticks/s (warp per car, k_collide: 75.3 M) */
+    bool collideV1 = false;           /* env PD_COLLIDE_V1=1: k_collide (a warp per car) instead of k_collide2 (a thread per car for the floor, a warp for the walls) */
     bool inlineCollide = false;       /* thread-per-car kernel: test collisions inside the tick (env PD_SERIAL_INLINE_COLLIDE=1) instead of k_collide ahead of it */
     bool collWarp = true;             /* quad kernel: collision warp inside the tick kernel (env PD_COLL_WARP=0: k_collide ahead of it instead) */
     bool zeroCopy = true; const void* zcKey[4] = {nullptr, nullptr, nullptr, nullptr}; void* zcDev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -623,6 +673,8 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_E2E_ZEROCOPY")) b->zeroCopy = atoi(q) != 0;
     if (const char* q = getenv("PD_COLL_WARP")) b->collWarp = atoi(q) != 0;
     if (const char* q = getenv("PD_SERIAL_INLINE_COLLIDE")) b->inlineCollide = atoi(q) != 0;
+    if (const char* q = getenv("PD_COLLIDE_V1")) b->collideV1 = atoi(q) != 0;
+    if (const char* q = getenv("PD_COLLIDE_LPC")) b->collideLpc = atoi(q);
     if (const char* q = getenv("PD_SERIAL_SMEM_PAD")) { b->serialSmemPad = atoi(q); cudaFuncSetAttribute(k_tick<PD_TOPO_STRUT_AXLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); cudaFuncSetAttribute(k_tick<PD_TOPO_STRUT_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); cudaFuncSetAttribute(k_tick<PD_TOPO_DW_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); }
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->ownStream = b->stream;
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
@@ -730,8 +782,17 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
         if (oddPossible && b->layout == PD_LAYOUT_RECORDS && b->collWarp && !b->response) collWarp = true;
         else if (oddPossible && b->layout == PD_LAYOUT_TILED && b->inlineCollide && !b->response) { /* experiment: every thread tests its own car inside k_tick */ }
         else if (oddPossible) {
-            k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr,
-                                                                                                      io.teleportMode, io.seed, io.idOffset, io.episodeCtr); b->launches++;
+            if (b->collideV1 || b->dClk)   /* the warp-per-car form (round 1; keeps the per-car clocks of the profiling tools) */
+                k_collide<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, (b->dClk && b->nClk >= 4096 + b->n * 16) ? b->dClk : nullptr,
+                                                                                                          io.teleportMode, io.seed, io.idOffset, io.episodeCtr);
+            else
+                switch (b->collideLpc) {
+                case 1: k_collide2<1><<<grid(b->n, PD_COLLIDE_BLOCK), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, io.teleportMode, io.seed, io.idOffset, io.episodeCtr); break;
+                default: k_collide2<4><<<grid(b->n, PD_COLLIDE_BLOCK / 4), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, io.teleportMode, io.seed, io.idOffset, io.episodeCtr); break;
+                case 16: k_collide2<16><<<grid(b->n, PD_COLLIDE_BLOCK / 16), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, io.teleportMode, io.seed, io.idOffset, io.episodeCtr); break;
+                case 8: k_collide2<8><<<grid(b->n, PD_COLLIDE_BLOCK / 8), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, io.teleportMode, io.seed, io.idOffset, io.episodeCtr); break;
+                }
+            b->launches++;
             io.collIn = b->dColl;
             if (b->response) { k_contacts<<<grid(b->n, PD_COLLIDE_BLOCK / 32), PD_COLLIDE_BLOCK, 0, b->stream>>>(b->car.P, b->dev, b->dState, b->layout, b->n, io.pending, b->dColl, b->dContacts,
                                                                                                                         io.teleportMode, io.seed, io.idOffset, io.episodeCtr); b->launches++; }

@@ -184,8 +184,11 @@ PD_HD void obb_bounds(const Frame& f, V3 c, V3 h, V3& lo, V3& hi) {
 /* Does the chassis touch the static world?  The work is shared by cellParts x nparts callers that OR their answers:
  * caller (cellPart, part) visits the cells number cellPart, cellPart + cellParts, ... of the car's footprint and, in each,
  * the entries part, part + nparts, ... of the cell's lists.  (1 x 1: thread-per-car kernel; 1 x 4: a quad inside the tick
- * kernel; 4 x 8: a warp per car in k_collide.) */
-PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, int part, int nparts, int cellPart = 0, int cellParts = 1) {
+ * kernel; 4 x 8: a warp per car in k_collide.)
+ * what: bit 0 = floor box vs TRACK triangles, bit 1 = hull vs WALL triangles.  With the walls left out, *wallsPossible tells whether any
+ * cell of the footprint holds WALL triangles in the hull's height range (k_collide: the floor test runs one thread per car, the rare car
+ * near a wall then gets a whole warp for the hull test). */
+PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, int part, int nparts, int cellPart = 0, int cellParts = 1, int what = 3, bool* wallsPossible = nullptr) {
     const PdBoundGrid& G = T.collGrid;
     if (G.nx <= 0 || G.nz <= 0) return false;
     const Frame& f = C.fr;
@@ -222,7 +225,7 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
             const float tY0 = cq[0], tY1 = cq[1], wY0 = cq[2], wY1 = cq[3];
             int kT, kW, kE; memcpy(&kT, &cq[4], 4); memcpy(&kW, &cq[5], 4); memcpy(&kE, &cq[6], 4);
 #endif
-            if (hasBox && !(tY0 > bhi.y || tY1 < blo.y)) {           /* C_CATEGORY_TRACK triangles x floor box */
+            if (hasBox && (what & 1) && !(tY0 > bhi.y || tY1 < blo.y)) {           /* C_CATEGORY_TRACK triangles x floor box */
                 const int k0 = kT, k1 = kW;
                 /* four entries of this lane's share are fetched together (the loop is bound by load latency, not by arithmetic) */
                 bool stop = false;
@@ -244,7 +247,8 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
                     }
                 }
             }
-            if (hasHull && !(wY0 > hhi.y || wY1 < hlo.y)) {          /* C_CATEGORY_WALL triangles x hull mesh */
+            if (hasHull && !(what & 2) && wallsPossible && kE > kW && !(wY0 > hhi.y || wY1 < hlo.y)) *wallsPossible = true;
+            if (hasHull && (what & 2) && !(wY0 > hhi.y || wY1 < hlo.y)) {          /* C_CATEGORY_WALL triangles x hull mesh */
                 const int k0 = kW, k1 = kE;
                 bool stop = false;
                 for (int k = k0 + part; k < k1 && !stop; k += 4 * nparts) {
@@ -303,7 +307,7 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
 #define PD_HULLS_TRIS   (PD_HULLS_BOUNDS + PD_MAX_COLLIDER_TRIS * 6)
 #define PD_HULLS_VERTS  (PD_HULLS_TRIS + PD_MAX_COLLIDER_TRIS)
 #define PD_HULLS_WORDS  (PD_HULLS_VERTS + PD_MAX_COLLIDER_VERTS * 3)      /* 2496 words = 10 KB per warp */
-template <bool SMEM> __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackDev& T, const Body& C, int lane, float* hullS, int* stats = nullptr) {
+template <bool SMEM, bool FLOOR = true> __device__ __noinline__ bool car_collide_warp(const PdCarParams& P, const TrackDev& T, const Body& C, int lane, float* hullS, int* stats = nullptr) {
     const unsigned FULL = 0xffffffffu;
     bool staged = false;
     const PdBoundGrid& G = T.collGrid;
@@ -415,7 +419,7 @@ template <bool SMEM> __device__ __noinline__ bool car_collide_warp(const PdCarPa
         for (int i = 0; i < nhere; ++i) {
             const float tY0 = __shfl_sync(FULL, hy.x, i), tY1 = __shfl_sync(FULL, hy.y, i), wY0 = __shfl_sync(FULL, hy.z, i), wY1 = __shfl_sync(FULL, hy.w, i);
             const int kT = __float_as_int(__shfl_sync(FULL, hk.x, i)), kW = __float_as_int(__shfl_sync(FULL, hk.y, i)), kE = __float_as_int(__shfl_sync(FULL, hk.z, i));
-            if (hasBox && !(tY0 > bhi.y || tY1 < blo.y)) {           /* TRACK triangles x floor box: one entry per lane and round */
+            if (FLOOR && hasBox && !(tY0 > bhi.y || tY1 < blo.y)) {           /* TRACK triangles x floor box: one entry per lane and round */
                 for (int kb = kT; kb < kW; kb += 32) {
                     if (stats && lane == 0) stats[1]++;
                     const int k = kb + lane;

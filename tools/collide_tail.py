@@ -30,3 +30,10 @@ for e in np.argsort(-cyc)[:12]:
     pos = [lay.get(r, "chassis.p" + k) for k in "xyz"]; v = np.linalg.norm([lay.get(r, "chassis.v" + k) for k in "xyz"])
     hullc = ((int(d[e, 3]) >> 8) & 0xfffffff) * 16 / 1e3; stagec = (int(d[e, 3]) >> 36) * 16 / 1e3
     print("env %d: %.0f kcycles (hull loops %.0f k, of which staging %.0f k), cells %d, track rounds %d, wall rounds %d, candidates %d, hit %d | pos %.1f %.1f %.1f v %.1f frame %d oot %d" % (e, cyc[e] / 1e3, hullc, stagec, ncell, tr, wr, cand, int(d[e, 3]) & 1, pos[0], pos[1], pos[2], v, lay.get(r, "car.physFrame"), lay.get(r, "car.outOfTrackFlag")))
+# distribution over all cars (what a thread-per-car pre-filter could discard)
+ncell = (d[:, 1] >> 32).astype(np.int64); tr = (d[:, 1] & 0xffffffff).astype(np.int64); wr = (d[:, 2] >> 32).astype(np.int64); cand = (d[:, 2] & 0xffffffff).astype(np.int64)
+odd = np.array([lay.get(before[:, e], "car.physFrame") & 1 for e in range(n)])
+print("odd-frame cars %d of %d; cells mean %.1f; track rounds: 0 -> %.1f%%, mean %.2f; wall rounds: 0 -> %.1f%%, mean %.2f; candidates: 0 -> %.1f%%, mean %.2f" % (
+    odd.sum(), n, ncell.mean(), 100 * (tr == 0).mean(), tr.mean(), 100 * (wr == 0).mean(), wr.mean(), 100 * (cand == 0).mean(), cand.mean()))
+for name, m in (("no rounds at all", (tr == 0) & (wr == 0)), ("track rounds only", (tr > 0) & (wr == 0)), ("wall rounds, no candidate", (wr > 0) & (cand == 0)), ("candidates", cand > 0)):
+    if m.any(): print("  %-28s %5.1f%% of cars, mean %.1f kcycles, share of total cycles %.1f%%" % (name, 100 * m.mean(), cyc[m].mean() / 1e3, 100 * cyc[m].sum() / cyc.sum()))
