@@ -190,7 +190,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
  * block = 64 threads = 2 warps, CPW cars per warp (8: every lane busy, throughput; 4 or 2: half / quarter-filled warps
  * = more warps per car batch, for batches too small to fill the 592 warp schedulers of a B200 otherwise).
  * ONE bulk copy brings the block's records in, the quads work on the shared-memory copy, ONE bulk copy writes them back. */
-template <int CPW>
+template <int CPW, int TOPO = 0>
 /* registers: left to ptxas (168 with the plain bound).  Measured on B200: capping at 128 (5 blocks per SM) is slower everywhere
  * (4096 envs 23.7 vs 26.4 M car-ticks/s, 65536 envs 33 vs 52 M); an explicit minimum of 1 block makes ptxas take 255 registers. */
 #ifdef PD_QUAD_MINBLOCKS
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(
         float lrows[PD_GSCR_ROWS_WORDS];                     /* JA | JB in local memory, Y | D | dg in shared memory */
         car_tick_quad<1, QLANES>(P, T, sv, dt, time, ex, lrows, scratch + cid, collPre, collWait);
 #else
-        car_tick_quad<QLANES, QLANES>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid, collPre, collWait, io.contacts ? io.contacts + (size_t)e * PD_CONTACT_WORDS : nullptr);
+        car_tick_quad<QLANES, QLANES, TOPO>(P, T, sv, dt, time, ex, scratch + cid, scratch + PD_GSCR_ROWS_WORDS * QLANES + cid, collPre, collWait, io.contacts ? io.contacts + (size_t)e * PD_CONTACT_WORDS : nullptr);
 #endif
     }
     if (io.clk && wl == 0 && warp < 2) io.clk[blockIdx.x * 2 + warp] = clock64() - clk0;
@@ -680,13 +680,17 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     CK(cudaFuncSetAttribute(k_tick_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
     CK(cudaFuncSetAttribute(k_tick_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
     CK(cudaFuncSetAttribute(k_tick_quad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(2)));
+    CK(cudaFuncSetAttribute((k_tick_quad<8, PD_TOPO_STRUT_DW>), cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
+    CK(cudaFuncSetAttribute((k_tick_quad<4, PD_TOPO_STRUT_DW>), cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
+    CK(cudaFuncSetAttribute((k_tick_quad<8, PD_TOPO_DW_DW>), cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(8)));
+    CK(cudaFuncSetAttribute((k_tick_quad<4, PD_TOPO_DW_DW>), cudaFuncAttributeMaxDynamicSharedMemorySize, PD_QUAD_SMEM_BYTES_(4)));
     /* cars per warp of the quad kernel: as few as still fit the batch into ONE wave of resident blocks
        (168 registers x 64 threads -> 6 blocks per SM; shared memory allows 2 / 4 / 8 blocks for 8 / 4 / 2 cars per warp) */
     { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); const int sms = prop.multiProcessorCount;
       b->quadCpw = (n_envs <= sms * 6 * 4) ? 2 : (n_envs <= sms * 4 * 8) ? 4 : 8;
       if (const char* q = getenv("PD_QUAD_CPW")) { const int v = atoi(q); if (v == 2 || v == 4 || v == 8) b->quadCpw = v; } }
     b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
-    if (b->car.P.topology != PD_TOPO_STRUT_AXLE) b->layout = PD_LAYOUT_TILED;      /* double-wishbone cars: the thread-per-car kernel has the instances (k_tick<PD_TOPO_STRUT_DW>, <PD_TOPO_DW_DW>); the 4-lanes-per-car kernel is laid out for strut + rigid axle */
+    if (b->car.P.topology != PD_TOPO_STRUT_AXLE && b->quadCpw == 2) b->quadCpw = 4;      /* double-wishbone cars: the 4-lanes-per-car kernel is instantiated for 4 and 8 cars per warp */
     int rc;
     if (b->track.needFat) { b->launches++; if ((rc = fat_points_on_device(b->track, b->stream, b->err))) return rc; }      /* no usable spline.cache: Track::computeFatPoints, on the GPU */
     if ((rc = dalloc(b, &b->dP, 1))) return rc;
@@ -802,10 +806,14 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
     } else { b->frameKnown = -1; if (b->response) io.contacts = b->dContacts; }          /* a masked tick advances only some envs: frames are no longer in lock step */
     if (b->layout == PD_LAYOUT_RECORDS) {
         const int threads = collWarp ? PD_QBLOCK + 32 : PD_QBLOCK;
-        switch (b->quadCpw) {
-        case 2: k_tick_quad<2><<<grid(b->n, 4), threads, PD_QUAD_SMEM_BYTES_(2), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
-        case 4: k_tick_quad<4><<<grid(b->n, 8), threads, PD_QUAD_SMEM_BYTES_(4), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
-        default: k_tick_quad<8><<<grid(b->n, 16), threads, PD_QUAD_SMEM_BYTES_(8), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+#define PD_LAUNCH_QUAD(CPW_, ...) k_tick_quad<CPW_, ##__VA_ARGS__><<<grid(b->n, 2 * CPW_), threads, PD_QUAD_SMEM_BYTES_(CPW_), b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io)
+        const int topo = b->car.P.topology;
+        if (topo == PD_TOPO_STRUT_DW) { if (b->quadCpw == 4) PD_LAUNCH_QUAD(4, PD_TOPO_STRUT_DW); else PD_LAUNCH_QUAD(8, PD_TOPO_STRUT_DW); }
+        else if (topo == PD_TOPO_DW_DW) { if (b->quadCpw == 4) PD_LAUNCH_QUAD(4, PD_TOPO_DW_DW); else PD_LAUNCH_QUAD(8, PD_TOPO_DW_DW); }
+        else switch (b->quadCpw) {
+        case 2: PD_LAUNCH_QUAD(2); break;
+        case 4: PD_LAUNCH_QUAD(4); break;
+        default: PD_LAUNCH_QUAD(8); break;
         }
     } else
         switch (b->car.P.topology) {
@@ -1220,6 +1228,8 @@ int pd_topology(const pd_batch* b) { return b ? b->car.P.topology : -1; }
 const char* pd_tick_kernel_instance(const pd_batch* b) {
     if (!b) return "";
     if (b->layout != PD_LAYOUT_RECORDS) return b->car.P.topology == PD_TOPO_STRUT_DW ? "k_tick<strut,dwb>" : (b->car.P.topology == PD_TOPO_DW_DW ? "k_tick<dwb,dwb>" : "k_tick");
+    if (b->car.P.topology == PD_TOPO_STRUT_DW) return b->quadCpw == 4 ? "k_tick_quad<4,strut,dwb>" : "k_tick_quad<8,strut,dwb>";
+    if (b->car.P.topology == PD_TOPO_DW_DW) return b->quadCpw == 4 ? "k_tick_quad<4,dwb,dwb>" : "k_tick_quad<8,dwb,dwb>";
     return b->quadCpw == 2 ? "k_tick_quad<2>" : b->quadCpw == 4 ? "k_tick_quad<4>" : "k_tick_quad<8>";
 }
 uint64_t pd_launch_count(const pd_batch* b) { return b ? b->launches : 0; }

@@ -27,7 +27,9 @@
 
 namespace pd {
 
-PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
+PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b, int topo = 0) {
+    if (PD_TOPO_FRONT_DW(topo) && (bodyIdx == PD_BODY_HUB0 || bodyIdx == PD_BODY_HUB1)) { const PdDW& D = P.dw[(bodyIdx - PD_BODY_HUB0) >> 1]; b.mass = D.hubMass; b.I = v3(D.hubInertia[0], D.hubInertia[1], D.hubInertia[2]); return; }
+    if (PD_TOPO_REAR_DW(topo) && (bodyIdx == PD_BODY_HUB2 || bodyIdx == PD_BODY_HUB3)) { const PdDW& D = P.dw[2 + (bodyIdx - PD_BODY_HUB2)]; b.mass = D.hubMass; b.I = v3(D.hubInertia[0], D.hubInertia[1], D.hubInertia[2]); return; }
     switch (bodyIdx) {
     case PD_BODY_CHASSIS: b.mass = P.chassisMass; b.I = v3(P.chassisInertia[0], P.chassisInertia[1], P.chassisInertia[2]); break;
     case PD_BODY_TANK: b.mass = P.tankMass; b.I = v3(P.tankInertia[0], P.tankInertia[1], P.tankInertia[2]); break;
@@ -37,10 +39,16 @@ PD_HD void lane_body_mass(const PdCarParams& P, int bodyIdx, Body& b) {
     }
 }
 
-template <int STRIDE, int STRIDE_D, class Ex, class SVX>
+/* TOPO (PD_TOPO_*): with a double-wishbone axle the lane's wheel body is the corner's own hub and its joint group the hub's five
+ * links (a single-body group, the code path of the rigid axle); the fuel tank's group stays on lane 3, which then factors two small
+ * groups; nothing is sent between the rear lanes (each owns its hub). */
+template <int STRIDE, int STRIDE_D, int TOPO = 0, class Ex, class SVX>
 PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv, float dt, double physicsTime, Ex& ex, float* scratch, float* scratchD, int collPre = -1, volatile uint32_t* collWait = nullptr, const float* cont = nullptr) {
     const int lane = ex.lane;
     const bool front = lane < 2;
+    constexpr bool FDW = PD_TOPO_FRONT_DW(TOPO), RDW = PD_TOPO_REAR_DW(TOPO);
+    const bool laneDW = front ? FDW : RDW;          /* this lane's corner is a double-wishbone one */
+    const bool hasStrutBody = front && !FDW;
     /* Car-level state: with a stride-1 view (the shared-memory staging copy) the four lanes work IN PLACE on the
      * record's car part.  They execute the car-level code converged (ex.sync() below re-joins them after every
      * lane-dependent section) and from identical inputs, so every store is four identical stores and every
@@ -55,11 +63,11 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     PD_PHASE(X, 0);
     ex.sync();
     Body C, W, S;
-    const int wIdx = front ? (PD_BODY_HUB0 + 2 * lane) : PD_BODY_AXLE;
-    const int sIdx = front ? (PD_BODY_STRUT0 + 2 * lane) : PD_BODY_TANK;
+    const int wIdx = front ? (PD_BODY_HUB0 + 2 * lane) : (RDW ? PD_BODY_HUB2 + (lane - 2) : PD_BODY_AXLE);
+    const int sIdx = hasStrutBody ? (PD_BODY_STRUT0 + 2 * lane) : PD_BODY_TANK;      /* second body: the strut body, or the tank (owned by lane 3, read-only elsewhere) */
     load_body(sv, PD_BODY_CHASSIS, C); lane_body_mass(P, PD_BODY_CHASSIS, C);
-    load_body(sv, wIdx, W); lane_body_mass(P, wIdx, W);
-    load_body(sv, sIdx, S); lane_body_mass(P, sIdx, S);
+    load_body(sv, wIdx, W); lane_body_mass(P, wIdx, W, TOPO);
+    load_body(sv, sIdx, S); lane_body_mass(P, sIdx, S, TOPO);
 
     /* ---------------- Car::step prologue (all lanes, identical) ---------------- */
     c.speed = len(C.v);
@@ -67,7 +75,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     {
         const float fVelSq = sqlen(C.v);
         X.dballErp = (fVelSq >= 1.0f) ? 0.3f : 0.9f;
-        X.dballCfm = (fVelSq >= 1.0f) ? P.strut[0].baseCFM : 0.0000001f;
+        X.dballCfm = (fVelSq >= 1.0f) ? (FDW ? P.dw[0].baseCFM : P.strut[0].baseCFM) : 0.0000001f;
     }
     c.ctlSteer = tclampf(c.ctlSteer, -1.0f, 1.0f); c.ctlClutch = tclampf(c.ctlClutch, 0.0f, 1.0f); c.ctlBrake = tclampf(c.ctlBrake, 0.0f, 1.0f);
     c.ctlHandBrake = tclampf(c.ctlHandBrake, 0.0f, 1.0f); c.ctlGas = tclampf(c.ctlGas, 0.0f, 1.0f);
@@ -78,7 +86,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     }
     {
         const float fRpmAbs = fabsf(engine_rpm(c));
-        const double fNewFuel = c.fuel - (fRpmAbs * dt * c.gasUsage) * (0.0f + 1.0) * P.fuelConsumptionK * 0.001 * P.fuelConsumptionRate;
+        const double fNewFuel = c.fuel - (fRpmAbs * dt * c.gasUsage) * (tmaxf(0.0f, c.turboBoost) + 1.0) * P.fuelConsumptionK * 0.001 * P.fuelConsumptionRate;
         c.fuel = fNewFuel;
         if (fNewFuel > 0.0f) c.fuelPressure = 1.0f; else { c.fuel = 0; c.fuelPressure = 0; }
     }
@@ -121,7 +129,8 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     const float myBrake = brakeT[lane], myHand = handT[lane];          /* per wheel: disc temperatures (cars with [TEMPS_*]) scale each wheel's torque */
     float travel, dspeed;
     Frame hf;
-    if (front) { strut_step(P.strut[lane], C, W, travel, dspeed); hf = strut_hub_frame(P.strut[lane], W); }
+    if (laneDW) { dw_step(P.dw[lane], C, W, travel, dspeed); hf = dw_hub_frame(P.dw[lane], W); }
+    else if (front) { strut_step(P.strut[lane], C, W, travel, dspeed); hf = strut_hub_frame(P.strut[lane], W); }
     else { axle_step(P.axle, C, W, lane - 2, travel, dspeed); hf = axle_hub_frame(P.axle, W, lane - 2); }
     sv.f(PD_OFF_TYRE(lane) + PD_TYRE_o_suspTravel, travel); sv.f(PD_OFF_TYRE(lane) + PD_TYRE_o_suspDamperSpeed, dspeed);
     WheelLink my;
@@ -138,12 +147,14 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     V3 steerA1 = v3(0, 0, 0), steerA2 = v3(0, 0, 0);
     if (front) { /* SteeringSystem::step */
         const float steer = -c.finalSteerAngleSignal * P.steerLinearRatio;
-        const PdStrut& St = P.strut[lane];
-        const float sx = signf_(St.refPoint[0]);
-        const float offx = 0.0f + steer + (sx * St.toeOutLinear);
-        const V3 carSteer = v3(St.baseCarSteer[0] + offx, St.baseCarSteer[1], St.baseCarSteer[2]);
+        const float* refPoint = FDW ? P.dw[lane].refPoint : P.strut[lane].refPoint;
+        const float* baseCarSteer = FDW ? P.dw[lane].baseCarSteer : P.strut[lane].baseCarSteer;
+        const float* tyreSteer = FDW ? P.dw[lane].tyreSteer : P.strut[lane].tyreSteer;
+        const float sx = signf_(refPoint[0]);
+        const float offx = 0.0f + steer + (sx * (FDW ? P.dw[lane].toeOutLinear : P.strut[lane].toeOutLinear));
+        const V3 carSteer = v3(baseCarSteer[0] + offx, baseCarSteer[1], baseCarSteer[2]);
         steerA1 = to_local(C.fr, to_world(C.fr, carSteer));
-        steerA2 = to_local(W.fr, to_world(W.fr, v3(St.tyreSteer[0], St.tyreSteer[1], St.tyreSteer[2])));
+        steerA2 = to_local(W.fr, to_world(W.fr, v3(tyreSteer[0], tyreSteer[1], tyreSteer[2])));
     }
     ex.sync();
     PD_PHASE(X, 6);
@@ -153,17 +164,18 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     const float fAxleTorq = drivetrain_step(P, X);
     PD_PHASE(X, 7);
     if (P.tyre[lane].driven) { sv.f(PD_OFF_TYRE(lane) + PD_TYRE_o_angularVelocity, X.wl[lane].angularVelocity); sv.i(PD_OFF_TYRE(lane) + PD_TYRE_o_isLocked, X.wl[lane].isLocked); }
-    if (lane == 2) { add_rel_torque(C, v3(0, 0, fAxleTorq)); add_rel_torque(W, v3(0, 0, -fAxleTorq)); }
+    if (!RDW && lane == 2) { add_rel_torque(C, v3(0, 0, fAxleTorq)); add_rel_torque(W, v3(0, 0, -fAxleTorq)); }       /* Drivetrain.cpp:547-553: only with a rigid rear axle */
     { /* anti-roll bars */
         const V3 partner = ex.get(W.fr.p, lane ^ 1);
-        if (front) {
-            const float k = P.arbK[0];
+        if (front || RDW) {       /* two hubs: each lane applies its own half of AntirollBar::step */
+            const float k = P.arbK[front ? 0 : 1];
             if (k > 0.0f) {
-                const V3 hubWorld0 = (lane == 0) ? W.fr.p : partner, hubWorld1 = (lane == 0) ? partner : W.fr.p;
+                const bool first = (lane & 1) == 0;
+                const V3 hubWorld0 = first ? W.fr.p : partner, hubWorld1 = first ? partner : W.fr.p;
                 const V3 vHubLoc0 = to_local(C.fr, hubWorld0), vHubLoc1 = to_local(C.fr, hubWorld1);
                 const float fDeltaK = (vHubLoc1.y - vHubLoc0.y) * k;
                 const V3 vForce = norm(C.fr.ay) * fDeltaK;
-                if (lane == 0) { add_force_at_pos(W, vForce, hubWorld0); add_rel_force_at_rel_pos(C, v3(0, -fDeltaK, 0), vHubLoc0); }
+                if (first) { add_force_at_pos(W, vForce, hubWorld0); add_rel_force_at_rel_pos(C, v3(0, -fDeltaK, 0), vHubLoc0); }
                 else { add_force_at_pos(W, vForce * -1.0f, hubWorld1); add_rel_force_at_rel_pos(C, v3(0, fDeltaK, 0), vHubLoc1); }
             }
         } else if (lane == 2) {
@@ -173,7 +185,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     }
     /* chassis force / torque: sum of the four lanes' partials; the axle collects lane 3's wheel forces */
     C.F = ex.sum(C.F); C.T = ex.sum(C.T);
-    {
+    if constexpr (!RDW) {
         const V3 f3 = ex.get(W.F, 3), t3 = ex.get(W.T, 3);
         if (lane == 2) { W.F += f3; W.T += t3; }
     }
@@ -194,22 +206,26 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     const float h = dt, hinv = 1.0f / dt;
     BodyDyn dC, dA, dB;
     body_dyn(C, P.gravityY, h, dC);
-    Body& A = (lane == 3) ? S : W;        /* lane 3 owns the tank, the other lanes their wheel body */
+    Body& A = (!RDW && lane == 3) ? S : W;        /* rigid rear axle: lane 3 owns the tank, the other lanes their wheel body; double-wishbone rear: every lane its hub */
     body_dyn(A, P.gravityY, h, dA);
-    if (front) body_dyn(S, P.gravityY, h, dB); else dB = dA;
+    if (hasStrutBody || (RDW && lane == 3)) body_dyn(S, P.gravityY, h, dB); else dB = dA;       /* dB: the strut body, or (DWB rear, lane 3) the tank */
     float S21[21], b6[6];
     for (int k = 0; k < 21; ++k) S21[k] = 0;
     for (int k = 0; k < 6; ++k) b6[k] = 0;
 #if PD_SOLVER2
     /* one group per lane, register-resident (pd_solver2.h): lanes 0 / 1 the strut groups, lanes 2 / 3 the single-body groups
        (axle, tank) through one shared code path */
-    float GR[PD_GSYS_WORDS];
-    StrutSys GS; GS.R = GR; SingleSys G1; G1.R = GR;
-    if (front) strut_factor(P, P.strut[lane], C, W, S, steerA1, steerA2, dA, dB, dC, hinv, X.dballErp, X.dballCfm, GS, S21, b6);
+    float GR[FDW ? 105 : PD_GSYS_WORDS];
+    float GT[RDW ? 105 : 1];                  /* DWB rear: the tank's group, on lane 3 beside its hub's */
+    StrutSys GS; GS.R = GR; SingleSys G1; G1.R = GR; SingleSys G2; G2.R = GT;
+    if (hasStrutBody) strut_factor(P, P.strut[lane], C, W, S, steerA1, steerA2, dA, dB, dC, hinv, X.dballErp, X.dballCfm, GS, S21, b6);
     else {
         float cfm[6];
-        if (lane == 2) single_rows_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G1, cfm); else single_rows_tank(P, S, C, hinv, G1, cfm);
+        if (laneDW) { const V3 st[2] = {steerA1, steerA2}; single_rows_links(P.dw[lane].link, PD_DW_LINKS, C, W, hinv, X.dballErp, X.dballCfm, G1, cfm, front ? st : nullptr); }
+        else if (lane == 2) single_rows_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G1, cfm);
+        else single_rows_tank(P, S, C, hinv, G1, cfm);
         single_factor(G1, cfm, dA, dC, hinv, S21, b6);
+        if constexpr (RDW) { if (lane == 3) { single_rows_tank(P, S, C, hinv, G2, cfm); single_factor(G2, cfm, dB, dC, hinv, S21, b6); } }
     }
     PD_PHASE(X, 9);
     PD_PHASE(X, 10);
@@ -228,7 +244,8 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     } else solve6(S21, b6, z);
     PD_PHASE(X, 11);
     float cfA[6], cfB[6];
-    if (front) strut_backsolve(GS, z, cfA, cfB); else single_backsolve(G1, z, cfA);
+    if (hasStrutBody) strut_backsolve(GS, z, cfA, cfB);
+    else { single_backsolve(G1, z, cfA); if constexpr (RDW) { if (lane == 3) single_backsolve(G2, z, cfB); } }
 #else
     GScr<STRIDE, STRIDE_D> G; G.bind(scratch, scratchD);
     if (front) build_strut(P, P.strut[lane], C, W, S, steerA1, steerA2, hinv, X.dballErp, X.dballCfm, G);
@@ -249,19 +266,20 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     float cfA[6], cfB[6];
     backsolve_group(G, z, cfA, cfB);
 #endif
+    const bool hasB = hasStrutBody || (RDW && lane == 3);        /* a second own body: the strut body / the tank beside a DWB rear hub */
     apply_update(A, dA, cfA, h);
-    if (front) apply_update(S, dB, cfB, h);
+    if (hasB) apply_update(S, dB, cfB, h);
     chassis_update(C, dC, z, h);
     integrate_body(C, h); integrate_body(A, h);
-    if (front) integrate_body(S, h);
+    if (hasB) integrate_body(S, h);
     int bad = !(finitef(A.fr.p.x) && finitef(A.fr.p.y) && finitef(A.fr.p.z) && finitef(A.v.x) && finitef(A.v.y) && finitef(A.v.z) && finitef(A.w.x) && finitef(A.w.y) && finitef(A.w.z) && finitef(A.q.w));
-    if (front) bad |= !(finitef(S.fr.p.x) && finitef(S.fr.p.y) && finitef(S.fr.p.z) && finitef(S.v.x) && finitef(S.v.y) && finitef(S.v.z) && finitef(S.w.x) && finitef(S.w.y) && finitef(S.w.z) && finitef(S.q.w));
+    if (hasB) bad |= !(finitef(S.fr.p.x) && finitef(S.fr.p.y) && finitef(S.fr.p.z) && finitef(S.v.x) && finitef(S.v.y) && finitef(S.v.z) && finitef(S.w.x) && finitef(S.w.y) && finitef(S.w.z) && finitef(S.q.w));
     bad |= !(finitef(C.fr.p.x) && finitef(C.fr.p.y) && finitef(C.fr.p.z) && finitef(C.v.x) && finitef(C.v.y) && finitef(C.v.z) && finitef(C.w.x) && finitef(C.w.y) && finitef(C.w.z) && finitef(C.q.w));
     bad = ex.all(!bad) ? 0 : 1;
     /* own bodies back to the state */
     if (lane == 0) store_body(sv, PD_BODY_CHASSIS, C);
-    if (lane != 3) store_body(sv, wIdx, W);
-    if (lane != 2) store_body(sv, sIdx, S);
+    if (RDW || lane != 3) store_body(sv, wIdx, W);
+    if (hasStrutBody || lane == 3) store_body(sv, sIdx, S);
 
     /* ---------------- Car::postStep ---------------- */
     ex.sync();

@@ -78,13 +78,21 @@ void hs_tick_quad(void* hv, uint32_t* rec, float dt, double time) {
     std::vector<uint32_t> copy[4];
     for (int l = 0; l < 4; ++l) copy[l].assign(rec, rec + PD_STATE_WORDS);
     std::thread th[4];
-    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() { QuadHost ex{l, &sh}; pd::SVFlat sv = pd::sv_flat(copy[l].data()); float scr[PD_GSCR_WORDS]; pd::car_tick_quad<1, 1>(h->car.P, h->dev, sv, dt, time, ex, scr, scr + PD_GSCR_ROWS_WORDS); });
+    const int topo = h->car.P.topology;
+    for (int l = 0; l < 4; ++l) th[l] = std::thread([&, l]() {
+        QuadHost ex{l, &sh}; pd::SVFlat sv = pd::sv_flat(copy[l].data()); float scr[PD_GSCR_WORDS];
+        if (topo == PD_TOPO_STRUT_DW) pd::car_tick_quad<1, 1, PD_TOPO_STRUT_DW>(h->car.P, h->dev, sv, dt, time, ex, scr, scr + PD_GSCR_ROWS_WORDS);
+        else if (topo == PD_TOPO_DW_DW) pd::car_tick_quad<1, 1, PD_TOPO_DW_DW>(h->car.P, h->dev, sv, dt, time, ex, scr, scr + PD_GSCR_ROWS_WORDS);
+        else pd::car_tick_quad<1, 1>(h->car.P, h->dev, sv, dt, time, ex, scr, scr + PD_GSCR_ROWS_WORDS);
+    });
     for (int l = 0; l < 4; ++l) th[l].join();
     pthread_barrier_destroy(&sh.bar);
     auto take = [&](int lane, int off, int words) { memcpy(rec + off, copy[lane].data() + off, (size_t)words * 4); };
-    take(0, PD_OFF_BODY(PD_BODY_CHASSIS), PD_BODY_WORDS); take(0, PD_OFF_BODY(PD_BODY_HUB0), PD_BODY_WORDS); take(0, PD_OFF_BODY(PD_BODY_STRUT0), PD_BODY_WORDS);
-    take(1, PD_OFF_BODY(PD_BODY_HUB1), PD_BODY_WORDS); take(1, PD_OFF_BODY(PD_BODY_STRUT1), PD_BODY_WORDS);
-    take(2, PD_OFF_BODY(PD_BODY_AXLE), PD_BODY_WORDS); take(3, PD_OFF_BODY(PD_BODY_TANK), PD_BODY_WORDS);
+    take(0, PD_OFF_BODY(PD_BODY_CHASSIS), PD_BODY_WORDS); take(0, PD_OFF_BODY(PD_BODY_HUB0), PD_BODY_WORDS); take(1, PD_OFF_BODY(PD_BODY_HUB1), PD_BODY_WORDS);
+    if (!PD_TOPO_FRONT_DW(topo)) { take(0, PD_OFF_BODY(PD_BODY_STRUT0), PD_BODY_WORDS); take(1, PD_OFF_BODY(PD_BODY_STRUT1), PD_BODY_WORDS); }
+    take(2, PD_OFF_BODY(PD_BODY_AXLE), PD_BODY_WORDS);          /* the rigid axle, or the LR hub of a double-wishbone rear axle */
+    if (PD_TOPO_REAR_DW(topo)) take(3, PD_OFF_BODY(PD_BODY_HUB3), PD_BODY_WORDS);
+    take(3, PD_OFF_BODY(PD_BODY_TANK), PD_BODY_WORDS);
     for (int l = 0; l < 4; ++l) take(l, PD_OFF_TYRE(l), PD_TYRE_WORDS);
     take(0, PD_OFF_CAR, PD_CAR_WORDS);
 }
