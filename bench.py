@@ -257,7 +257,7 @@ def ours(args):
     kernel = b.tick_kernel()
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s@%d" % (kernel, n_envs))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("%s@%d" % (kernel, n_envs))      # dram bytes of one launch of this kernel at this batch size, from the committed ncu capture
     except Exception:
         pass
 

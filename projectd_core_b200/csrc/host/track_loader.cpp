@@ -140,10 +140,36 @@ void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& sur
                 const float* p = &out.triRaw[(size_t)i * 9];
                 const float y0 = std::min(p[1], std::min(p[4], p[7])), y1 = std::max(p[1], std::max(p[4], p[7]));
                 int a2, b2, c2, d2; range(i, a2, b2, c2, d2);
+                /* TRACK triangles that face up: the top of the cell's height range is the triangle's highest point INSIDE the cell's column
+                   (the triangle clipped to the cell square), not its highest vertex -- a large road triangle on a slope reaches the floor
+                   box's height only in cells the box does not stand on, and its entry in those cells is tested there.  The floor test's
+                   triangle-normal axis is one-sided (box_tri_contact), so a triangle facing down keeps its full range. */
+                const float nY = (p[5] - p[2]) * (p[6] - p[0]) - (p[3] - p[0]) * (p[8] - p[2]);       /* y of (v1 - v0) x (v2 - v0) */
+                const bool clipTop = cat == 1u && nY > 0.0f && !getenv("PD_COLL_NO_CLIP");
                 for (int iz = c2; iz <= d2; ++iz) for (int ix = a2; ix <= b2; ++ix) {
                     const size_t c = (size_t)iz * G.nx + ix;
                     count[2 * c + (cat - 1) + 1]++;
-                    float* yr = &out.collY[4 * c + 2 * (cat - 1)]; yr[0] = std::min(yr[0], y0); yr[1] = std::max(yr[1], y1);
+                    float top = y1;
+                    if (clipTop && (a2 != b2 || c2 != d2)) {
+                        /* Sutherland-Hodgman against the four sides of the cell square (x, z), grown by 1 mm; y interpolated along the edges */
+                        float px[8][3], qx[8][3]; int np = 3;
+                        for (int v = 0; v < 3; ++v) { px[v][0] = p[3 * v]; px[v][1] = p[3 * v + 1]; px[v][2] = p[3 * v + 2]; }
+                        const float lim[4] = {G.ox + ix * G.cell - 1e-3f, G.ox + (ix + 1) * G.cell + 1e-3f, G.oz + iz * G.cell - 1e-3f, G.oz + (iz + 1) * G.cell + 1e-3f};
+                        for (int side = 0; side < 4 && np > 0; ++side) {
+                            const int ax = side < 2 ? 0 : 2; const float L = lim[side]; const bool keepGreater = (side & 1) == 0;
+                            int nq = 0;
+                            for (int v = 0; v < np; ++v) {
+                                const float* A = px[v]; const float* B = px[(v + 1) % np];
+                                const bool inA = keepGreater ? A[ax] >= L : A[ax] <= L, inB = keepGreater ? B[ax] >= L : B[ax] <= L;
+                                if (inA) { memcpy(qx[nq++], A, 12); }
+                                if (inA != inB) { const float t = (L - A[ax]) / (B[ax] - A[ax]); for (int d = 0; d < 3; ++d) qx[nq][d] = A[d] + t * (B[d] - A[d]); ++nq; }
+                            }
+                            np = nq; memcpy(px, qx, sizeof(float) * 3 * (size_t)np);
+                        }
+                        if (np > 0) { top = -3.4e38f; for (int v = 0; v < np; ++v) top = std::max(top, px[v][1]); top = std::min(y1, top + 1e-3f + 1e-5f * fabsf(top)); }
+                        else top = y0;        /* the triangle's box reaches the cell, the triangle does not: it cannot be met here */
+                    }
+                    float* yr = &out.collY[4 * c + 2 * (cat - 1)]; yr[0] = std::min(yr[0], y0); yr[1] = std::max(yr[1], top);
                 }
             }
             for (size_t c = 0; c < 2 * nc; ++c) count[c + 1] += count[c];

@@ -257,8 +257,42 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(
         }
         __syncthreads();      /* poses and frame parities are in the collision warp's registers: the tick may start changing the records */
         if (warp == 2) {
-            /* (a lane per car for the floor test, as k_collide2 does, was measured SLOWER here: 22.4 vs 25.8 M car-ticks/s at 4096 envs -- the serial
-               lane's chain of dependent loads ends later than eight warp-wide tests, and the quads wait for the answer) */
+#ifndef PD_COLL_WARP_SEQ
+#define PD_COLL_WARP_SEQ 1      /* measured on B200 (30-step bench runs): sequential 23.6 / side by side 23.7 M car-ticks/s at 4096 envs, 8.65 / 8.53 M at 1024, 14.6 / 14.3 M at 2048, 36.6 / 37.0 M at 8192: no difference worth the code; the odd-frame cost is not the collision warp's own duration */
+#endif
+#if !PD_COLL_WARP_SEQ
+            /* The block's cars side by side: 32 / QCARS lanes per car run the floor-box test (the cells of the footprint dealt to them, as in
+               k_collide2) -- 93 % of the cars need nothing else (tools/collide_tail.py) -- then the whole warp takes the cars whose footprint holds
+               WALL triangles at hull height through the hull test, one after the other.  (Round 1 tested the cars one after the other with all
+               32 lanes: 8 x 15 k cycles, and a block with two or three kerb-straddling cars kept its quads waiting: odd frames 198-221 us
+               against 167 us for even ones under ncu.  ONE lane per car was slower still: 22.4 vs 25.8 M car-ticks/s.) */
+            constexpr int LPC = 32 / QCARS;
+            const unsigned FULLW = 0xffffffffu;
+            const int kc = wl / LPC, sub = wl % LPC;
+            Body Cc;
+            Cc.fr.p = v3(__shfl_sync(FULLW, fr[0], kc), __shfl_sync(FULLW, fr[1], kc), __shfl_sync(FULLW, fr[2], kc));
+            Cc.fr.ax = v3(__shfl_sync(FULLW, fr[3], kc), __shfl_sync(FULLW, fr[4], kc), __shfl_sync(FULLW, fr[5], kc));
+            Cc.fr.ay = v3(__shfl_sync(FULLW, fr[6], kc), __shfl_sync(FULLW, fr[7], kc), __shfl_sync(FULLW, fr[8], kc));
+            Cc.fr.az = v3(__shfl_sync(FULLW, fr[9], kc), __shfl_sync(FULLW, fr[10], kc), __shfl_sync(FULLW, fr[11], kc));
+            const bool needK = __shfl_sync(FULLW, need, kc) != 0;
+            bool hitK = false, walls = false;
+            if (needK) hitK = car_collide(P, T, Cc, 0, 1, sub, LPC, 1, &walls);
+            PD_UNROLL
+            for (int off = 1; off < LPC; off <<= 1) { hitK = __shfl_xor_sync(FULLW, (int)hitK, off) || hitK; walls = __shfl_xor_sync(FULLW, (int)walls, off) || walls; }
+            if (hitK) walls = false;
+            if (needK && !walls && sub == 0) { *reinterpret_cast<volatile uint32_t*>(recs + kc * PD_STATE_STRIDE + collSlot) = hitK ? 2u : 1u; __threadfence_block(); }      /* answered: this car's quad need not wait for the others */
+            unsigned m = __ballot_sync(FULLW, walls && sub == 0);
+            while (m) {
+                const int k = (__ffs(m) - 1) / LPC; m &= m - 1;
+                Body Cw;
+                Cw.fr.p = v3(__shfl_sync(FULLW, fr[0], k), __shfl_sync(FULLW, fr[1], k), __shfl_sync(FULLW, fr[2], k));
+                Cw.fr.ax = v3(__shfl_sync(FULLW, fr[3], k), __shfl_sync(FULLW, fr[4], k), __shfl_sync(FULLW, fr[5], k));
+                Cw.fr.ay = v3(__shfl_sync(FULLW, fr[6], k), __shfl_sync(FULLW, fr[7], k), __shfl_sync(FULLW, fr[8], k));
+                Cw.fr.az = v3(__shfl_sync(FULLW, fr[9], k), __shfl_sync(FULLW, fr[10], k), __shfl_sync(FULLW, fr[11], k));
+                const bool hit = car_collide_warp<false, false>(P, T, Cw, wl, nullptr);
+                if (wl == 0) { *reinterpret_cast<volatile uint32_t*>(recs + k * PD_STATE_STRIDE + collSlot) = hit ? 2u : 1u; __threadfence_block(); }
+            }
+#else
             for (int k = 0; k < ncars; ++k) {
                 if (!__shfl_sync(0xffffffffu, need, k)) continue;
                 Body Cc;
@@ -269,6 +303,7 @@ __global__ void __launch_bounds__(PD_QBLOCK + 32) k_tick_quad(
                 const bool hit = car_collide_warp<false>(P, T, Cc, wl, nullptr);
                 if (wl == 0) { *reinterpret_cast<volatile uint32_t*>(recs + k * PD_STATE_STRIDE + collSlot) = hit ? 2u : 1u; __threadfence_block(); }
             }
+#endif
         }
     }
     if (on) {
@@ -580,6 +615,7 @@ struct pd_batch {
     long long* dClk = nullptr; int nClk = 0;
     int serialSmemPad = 0;            /* tuning knob (env PD_SERIAL_SMEM_PAD, bytes): unused dynamic shared memory per block of k_tick, caps the resident blocks per SM */
     int collideLpc = 4;               /* env PD_COLLIDE_LPC: lanes per car of k_collide2's floor test (1 / 4 / 8 / 16); measured at 65536 envs: 79.4 / 81.1 / 80.2 / 78.2 M car-ticks/s (warp per car, k_collide: 75.3 M) */
+    bool debugSkipCollision = false;  /* env PD_DEBUG_SKIP_COLLISION=1: MEASUREMENT ONLY -- no collision test at all (wrong flags), to see what the detection costs a tick */
     bool collideV1 = false;           /* env PD_COLLIDE_V1=1: k_collide (a warp per car) instead of k_collide2 (a thread per car for the floor, a warp for the walls) */
     bool inlineCollide = false;       /* thread-per-car kernel: test collisions inside the tick (env PD_SERIAL_INLINE_COLLIDE=1) instead of k_collide ahead of it */
     bool collWarp = true;             /* quad kernel: collision warp inside the tick kernel (env PD_COLL_WARP=0: k_collide ahead of it instead) */
@@ -674,6 +710,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if (const char* q = getenv("PD_COLL_WARP")) b->collWarp = atoi(q) != 0;
     if (const char* q = getenv("PD_SERIAL_INLINE_COLLIDE")) b->inlineCollide = atoi(q) != 0;
     if (const char* q = getenv("PD_COLLIDE_V1")) b->collideV1 = atoi(q) != 0;
+    if (const char* q = getenv("PD_DEBUG_SKIP_COLLISION")) b->debugSkipCollision = atoi(q) != 0;
     if (const char* q = getenv("PD_COLLIDE_LPC")) b->collideLpc = atoi(q);
     if (const char* q = getenv("PD_SERIAL_SMEM_PAD")) { b->serialSmemPad = atoi(q); cudaFuncSetAttribute(k_tick<PD_TOPO_STRUT_AXLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); cudaFuncSetAttribute(k_tick<PD_TOPO_STRUT_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); cudaFuncSetAttribute(k_tick<PD_TOPO_DW_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->serialSmemPad); }
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->ownStream = b->stream;
@@ -780,7 +817,8 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
     if (!mask) {
         /* collision detection (odd physics frames): the quad kernel brings its own collision warp per block; the thread-per-car
            kernel is preceded by k_collide (a warp per car) on the same stream */
-        const bool oddPossible = b->frameKnown < 0 || (b->frameKnown & 1);
+        const bool oddPossible = (b->frameKnown < 0 || (b->frameKnown & 1)) && !b->debugSkipCollision;
+        if (b->debugSkipCollision) { cudaMemsetAsync(b->dColl, 0, (size_t)b->n * 4, b->stream); io.collIn = b->dColl; }       /* "no contact" for every car: measurement only */
         /* with the collision response on, k_collide also GENERATES the contact joints of cars that touch something (it knows the
            start pose, resets included); the tick kernels pick the live joints up at the solve */
         if (oddPossible && b->layout == PD_LAYOUT_RECORDS && b->collWarp && !b->response) collWarp = true;

@@ -272,9 +272,9 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     chassis_update(C, dC, z, h);
     integrate_body(C, h); integrate_body(A, h);
     if (hasB) integrate_body(S, h);
-    int bad = !(finitef(A.fr.p.x) && finitef(A.fr.p.y) && finitef(A.fr.p.z) && finitef(A.v.x) && finitef(A.v.y) && finitef(A.v.z) && finitef(A.w.x) && finitef(A.w.y) && finitef(A.w.z) && finitef(A.q.w));
-    if (hasB) bad |= !(finitef(S.fr.p.x) && finitef(S.fr.p.y) && finitef(S.fr.p.z) && finitef(S.v.x) && finitef(S.v.y) && finitef(S.v.z) && finitef(S.w.x) && finitef(S.w.y) && finitef(S.w.z) && finitef(S.q.w));
-    bad |= !(finitef(C.fr.p.x) && finitef(C.fr.p.y) && finitef(C.fr.p.z) && finitef(C.v.x) && finitef(C.v.y) && finitef(C.v.z) && finitef(C.w.x) && finitef(C.w.y) && finitef(C.w.z) && finitef(C.q.w));
+    float nf = body_nonfinite_acc(A) + body_nonfinite_acc(C);
+    if (hasB) nf += body_nonfinite_acc(S);
+    int bad = (nf == 0.0f) ? 0 : 1;
     bad = ex.all(!bad) ? 0 : 1;
     /* own bodies back to the state */
     if (lane == 0) store_body(sv, PD_BODY_CHASSIS, C);

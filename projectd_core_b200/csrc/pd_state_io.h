@@ -191,6 +191,12 @@ template <class SVX> PD_HD void store_body(const SVX& sv, int b, const Body& B) 
     sv.f(o + PD_BODY_o_azx, B.fr.az.x); sv.f(o + PD_BODY_o_azy, B.fr.az.y); sv.f(o + PD_BODY_o_azz, B.fr.az.z);
 }
 
+/* 0 when position, velocities and q.w of the body are all finite, NaN otherwise: x - x is 0 for a finite x and NaN for an infinity or a NaN, and
+ * NaN survives the sum -- the same predicate as ten finitef() tests, without their ten dependent branches */
+PD_HD float body_nonfinite_acc(const Body& b) {
+    return ((b.fr.p.x - b.fr.p.x) + (b.fr.p.y - b.fr.p.y)) + ((b.fr.p.z - b.fr.p.z) + (b.v.x - b.v.x)) + ((b.v.y - b.v.y) + (b.v.z - b.v.z)) + ((b.w.x - b.w.x) + (b.w.y - b.w.y)) + ((b.w.z - b.w.z) + (b.q.w - b.q.w));
+}
+
 /* ---- body force API (RigidBodyODE.cpp:184-270 -> ODE dBody*) ---- */
 PD_HD V3 body_point_vel(const Body& b, V3 p) { return b.v + cross(b.w, p - b.fr.p); }            /* dBodyGetPointVel */
 PD_HD V3 body_rel_point_vel(const Body& b, V3 prel) { return b.v + cross(b.w, rot(b.fr, prel)); } /* dBodyGetRelPointVel */

@@ -491,8 +491,10 @@ template <int STRIDE, int STRIDE_D, int TOPO = 0, class SVX> PD_HDN void car_tic
     c.episodeSteps++; c.thermalPrimed = 1;
     {
         int bad = 0;
+        float acc = 0.0f;
         PD_UNROLL
-        for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body<TOPO>(i)) { const Body& b = bod[i]; if (!(finitef(b.fr.p.x) && finitef(b.fr.p.y) && finitef(b.fr.p.z) && finitef(b.v.x) && finitef(b.v.y) && finitef(b.v.z) && finitef(b.w.x) && finitef(b.w.y) && finitef(b.w.z) && finitef(b.q.w))) bad = 1; }
+        for (int i = 0; i < PD_NUM_BODIES; ++i) if (topo_has_body<TOPO>(i)) acc += body_nonfinite_acc(bod[i]);
+        bad = (acc == 0.0f) ? 0 : 1;
         if (bad) c.nanFlag = 1;
     }
     PD_UNROLL
