@@ -105,6 +105,7 @@ struct TrackModel {
     std::vector<float> triRaw;                 /* 9 floats per triangle (leaf order): v0, v1, v2 as stored in surfaces.bin */
     PdBoundGrid collGrid;                      /* x-z grid over all triangles for collision detection */
     std::vector<int32_t> collStart, collItems; /* CSR, two lists per cell: [2c] TRACK triangles, [2c+1] WALL triangles */
+    std::vector<float> collPlane;              /* per collItems entry, 16 B: unit normal of the triangle + its plane offset (normal . v0); zero for a degenerate triangle */
     std::vector<float> collRec;                /* per collItems entry, 32 B: box min xyz, triangle index bits, box max xyz, 0; lists sorted by descending ymax */
     std::vector<float> collCell;               /* per cell, 32 B: track y min / max, wall y min / max, then (int bits) first TRACK entry, first WALL entry, end */
     std::vector<float> collY;                  /* per cell: y range of its TRACK triangles, y range of its WALL triangles */

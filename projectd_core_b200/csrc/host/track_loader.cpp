@@ -185,10 +185,17 @@ void build_bvh(const std::vector<float>& verts9, const std::vector<int32_t>& sur
             auto ymax_of = [&](int32_t i) { const float* p = &out.triRaw[(size_t)i * 9]; return std::max(p[1], std::max(p[4], p[7])); };
             for (size_t l = 0; l < 2 * nc; ++l) std::stable_sort(out.collItems.begin() + count[l], out.collItems.begin() + count[l + 1], [&](int32_t x, int32_t y) { return ymax_of(x) > ymax_of(y); });
             out.collRec.assign(out.collItems.size() * 8, 0.0f);
+            out.collPlane.assign(out.collItems.size() * 4, 0.0f);
             for (size_t k = 0; k < out.collItems.size(); ++k) {
                 const int32_t i = out.collItems[k]; const float* p = &out.triRaw[(size_t)i * 9]; float* q = &out.collRec[k * 8];
                 for (int d = 0; d < 3; ++d) { q[d] = std::min(p[d], std::min(p[3 + d], p[6 + d])); q[4 + d] = std::max(p[d], std::max(p[3 + d], p[6 + d])); }
                 memcpy(&q[3], &i, 4);
+                /* the triangle's plane, for the one-sided plane test ahead of everything else (pd_collide.h): N = (v1 - v0) x (v2 - v0) as box_tri_contact forms it */
+                const double e1[3] = {(double)p[3] - p[0], (double)p[4] - p[1], (double)p[5] - p[2]}, e2[3] = {(double)p[6] - p[0], (double)p[7] - p[1], (double)p[8] - p[2]};
+                const double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+                const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                float* pl = &out.collPlane[k * 4];
+                if (len > 1e-9) { pl[0] = (float)(n[0] / len); pl[1] = (float)(n[1] / len); pl[2] = (float)(n[2] / len); pl[3] = (float)((n[0] * p[0] + n[1] * p[1] + n[2] * p[2]) / len); }
             }
             /* one 32-byte header per cell: y ranges of its two lists and their bounds in collRec */
             out.collCell.assign(nc * 8, 0.0f);

@@ -753,6 +753,7 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
     if ((rc = upload(b, &b->dev.collItems, b->track.collItems))) return rc;
     if ((rc = upload(b, &b->dev.collCell, b->track.collCell))) return rc;
     if ((rc = upload(b, &b->dev.collRec, b->track.collRec))) return rc;
+    if ((rc = upload(b, &b->dev.collPlane, b->track.collPlane))) return rc;
     b->dev.collGrid = b->track.collGrid;
     {   /* the hull's tables in car_collide_warp's layout */
         std::vector<float> ht(PD_HULLS_WORDS, 0.0f); const PdCarParams& Pc = b->car.P;

@@ -181,6 +181,22 @@ PD_HD void obb_bounds(const Frame& f, V3 c, V3 h, V3& lo, V3& hi) {
     lo = c - e; hi = c + e;
 }
 
+/* The floor box entirely in FRONT of the triangle's plane (by more than 0.1 mm): box_tri_contact's first axis -- the triangle's normal, one-sided:
+ * depth = r + (v0 - c) . N < 0 -- answers "no contact" for such a triangle whatever the other twelve axes say, so the entry needs neither its box
+ * tests nor the triangle itself.  (The road under a car: the floor box rides a few centimetres above it, and nearly every entry that reaches the
+ * separating-axis test is rejected by exactly this axis.)  The margin keeps the early answer on the safe side of box_tri_contact's own rounding. */
+PD_HD bool box_clear_of_plane(const float* __restrict__ planes, int k, const Frame& f, V3 bc, V3 bh) {
+#if defined(__CUDA_ARCH__)
+    const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + k);
+    const V3 n = v3(pl.x, pl.y, pl.z); const float d = pl.w;
+#else
+    const float* q = planes + (size_t)k * 4; const V3 n = v3(q[0], q[1], q[2]); const float d = q[3];
+#endif
+    if (n.x == 0.0f && n.y == 0.0f && n.z == 0.0f) return false;
+    const float r = bh.x * fabsf(dot(f.ax, n)) + bh.y * fabsf(dot(f.ay, n)) + bh.z * fabsf(dot(f.az, n));
+    return r + (d - dot(bc, n)) < -1e-4f;
+}
+
 /* Does the chassis touch the static world?  The work is shared by cellParts x nparts callers that OR their answers:
  * caller (cellPart, part) visits the cells number cellPart, cellPart + cellParts, ... of the car's footprint and, in each,
  * the entries part, part + nparts, ... of the cell's lists.  (1 x 1: thread-per-car kernel; 1 x 4: a quad inside the tick
@@ -236,6 +252,7 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
                         if (stop) break;
                         const float* mn = R.mn[u]; const float* mx = R.mx[u];
                         if (mx[1] < blo.y) { stop = true; break; }   /* sorted by descending top: nothing further reaches the box (also ends a short group) */
+                        if (box_clear_of_plane(T.collPlane, k + u * nparts, f, bc, bh)) continue;
                         if (mn[1] > bhi.y || mn[0] > bhi.x || mx[0] < blo.x || mn[2] > bhi.z || mx[2] < blo.z) continue;
                         if (aabb_outside_obb(mn, mx, bc, f, bh)) continue;       /* the entry's box misses the collider along one of its axes */
                         const float* q = T.triRaw + (size_t)R.tri[u] * 9;
@@ -428,7 +445,7 @@ template <bool SMEM, bool FLOOR = true> __device__ __noinline__ bool car_collide
                         float mn[3], mx[3]; int t;
                         load_coll_rec(T.collRec, k, mn, mx, t);
                         below = mx[1] < blo.y;
-                        if (!below && !(mn[1] > bhi.y || mn[0] > bhi.x || mx[0] < blo.x || mn[2] > bhi.z || mx[2] < blo.z) && !aabb_outside_obb(mn, mx, bc, f, bh)) {
+                        if (!below && !box_clear_of_plane(T.collPlane, k, f, bc, bh) && !(mn[1] > bhi.y || mn[0] > bhi.x || mx[0] < blo.x || mn[2] > bhi.z || mx[2] < blo.z) && !aabb_outside_obb(mn, mx, bc, f, bh)) {
                             const float* q = T.triRaw + (size_t)t * 9;
                             V3 n;
                             if (box_tri_contact(bc, f.ax, f.ay, f.az, bh, v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), v3(q[6], q[7], q[8]), n) && !(dot(f.ay, n) < 0.9f)) hit = true;

@@ -62,6 +62,7 @@ struct TrackDev {
     const float* triRaw;      /* 9 floats per triangle: v0, v1, v2 (collision detection, pd_collide.h) */
     const int32_t* collStart; const int32_t* collItems;  /* collision grid CSR, two lists per cell: TRACK triangles, WALL triangles */
     const float* collRec;     /* per entry, 32 B: box min xyz, triangle index bits | box max xyz, 0 (lists sorted by descending ymax) */
+    const float* collPlane;   /* per entry, 16 B: the triangle's unit normal and plane offset (zeros: degenerate triangle, no early answer) */
     const float* collCell;    /* per cell, 32 B: track y min / max, wall y min / max | first TRACK entry, first WALL entry, end (int bits), 0 */
     PdBoundGrid collGrid;
     const float* hullTables;  /* the car hull's triangle / vertex tables in car_collide_warp's layout (PD_HULLS_*): read-only global copy */

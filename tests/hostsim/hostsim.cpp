@@ -22,7 +22,7 @@ struct HS {
         dev.surfaces = track.surfaces.data(); dev.fat = track.fat.data(); dev.splineXYZ = track.splineXYZ.data(); dev.splineDist = track.splineDist.data();
         dev.segStart = track.segStart.data(); dev.segItems = track.segItems.data(); dev.ptStart = track.ptStart.data(); dev.ptItems = track.ptItems.data(); dev.segRec = track.segRec.data(); dev.ptRec = track.ptRec.data(); dev.grid = track.grid; dev.segGrid = track.segGrid;
         dev.colStart = track.colStart.data(); dev.colItems = track.colItems.data(); dev.colGrid = track.colGrid;
-        dev.triRaw = track.triRaw.data(); dev.collStart = track.collStart.data(); dev.collItems = track.collItems.data(); dev.collCell = track.collCell.data(); dev.collRec = track.collRec.data(); dev.collGrid = track.collGrid; dev.hullTables = nullptr;
+        dev.triRaw = track.triRaw.data(); dev.collStart = track.collStart.data(); dev.collItems = track.collItems.data(); dev.collPlane = track.collPlane.data(); dev.collCell = track.collCell.data(); dev.collRec = track.collRec.data(); dev.collGrid = track.collGrid; dev.hullTables = nullptr;
         dev.info = track.info;
     }
 };
