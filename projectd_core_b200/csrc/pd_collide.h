@@ -185,16 +185,20 @@ PD_HD void obb_bounds(const Frame& f, V3 c, V3 h, V3& lo, V3& hi) {
  * depth = r + (v0 - c) . N < 0 -- answers "no contact" for such a triangle whatever the other twelve axes say, so the entry needs neither its box
  * tests nor the triangle itself.  (The road under a car: the floor box rides a few centimetres above it, and nearly every entry that reaches the
  * separating-axis test is rejected by exactly this axis.)  The margin keeps the early answer on the safe side of box_tri_contact's own rounding. */
-PD_HD bool box_clear_of_plane(const float* __restrict__ planes, int k, const Frame& f, V3 bc, V3 bh) {
+struct Plane4 { float x, y, z, w; };
+PD_HD Plane4 load_plane(const float* __restrict__ planes, int k) {      /* issued together with the entry's box: the two loads overlap */
 #if defined(__CUDA_ARCH__)
     const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + k);
-    const V3 n = v3(pl.x, pl.y, pl.z); const float d = pl.w;
+    Plane4 r; r.x = pl.x; r.y = pl.y; r.z = pl.z; r.w = pl.w; return r;
 #else
-    const float* q = planes + (size_t)k * 4; const V3 n = v3(q[0], q[1], q[2]); const float d = q[3];
+    const float* q = planes + (size_t)k * 4; Plane4 r; r.x = q[0]; r.y = q[1]; r.z = q[2]; r.w = q[3]; return r;
 #endif
+}
+PD_HD bool box_clear_of_plane(const Plane4& pl, const Frame& f, V3 bc, V3 bh) {
+    const V3 n = v3(pl.x, pl.y, pl.z);
     if (n.x == 0.0f && n.y == 0.0f && n.z == 0.0f) return false;
     const float r = bh.x * fabsf(dot(f.ax, n)) + bh.y * fabsf(dot(f.ay, n)) + bh.z * fabsf(dot(f.az, n));
-    return r + (d - dot(bc, n)) < -1e-4f;
+    return r + (pl.w - dot(bc, n)) < -1e-4f;
 }
 
 /* Does the chassis touch the static world?  The work is shared by cellParts x nparts callers that OR their answers:
@@ -247,13 +251,16 @@ PD_HDN bool car_collide(const PdCarParams& P, const TrackDev& T, const Body& C, 
                 bool stop = false;
                 for (int k = k0 + part; k < k1 && !stop; k += 4 * nparts) {
                     CollRec4 R; load_coll_rec4(T.collRec, k, nparts, k1, R);
+                    Plane4 PL[4];
+                    PD_UNROLL
+                    for (int u = 0; u < 4; ++u) PL[u] = load_plane(T.collPlane, (k + u * nparts < k1) ? k + u * nparts : k);
                     PD_UNROLL
                     for (int u = 0; u < 4; ++u) {
                         if (stop) break;
                         const float* mn = R.mn[u]; const float* mx = R.mx[u];
                         if (mx[1] < blo.y) { stop = true; break; }   /* sorted by descending top: nothing further reaches the box (also ends a short group) */
-                        if (box_clear_of_plane(T.collPlane, k + u * nparts, f, bc, bh)) continue;
                         if (mn[1] > bhi.y || mn[0] > bhi.x || mx[0] < blo.x || mn[2] > bhi.z || mx[2] < blo.z) continue;
+                        if (box_clear_of_plane(PL[u], f, bc, bh)) continue;
                         if (aabb_outside_obb(mn, mx, bc, f, bh)) continue;       /* the entry's box misses the collider along one of its axes */
                         const float* q = T.triRaw + (size_t)R.tri[u] * 9;
                         const V3 v0 = v3(q[0], q[1], q[2]), v1 = v3(q[3], q[4], q[5]), v2 = v3(q[6], q[7], q[8]);
@@ -444,8 +451,9 @@ template <bool SMEM, bool FLOOR = true> __device__ __noinline__ bool car_collide
                     if (k < kW) {
                         float mn[3], mx[3]; int t;
                         load_coll_rec(T.collRec, k, mn, mx, t);
+                        const Plane4 pl = load_plane(T.collPlane, k);
                         below = mx[1] < blo.y;
-                        if (!below && !box_clear_of_plane(T.collPlane, k, f, bc, bh) && !(mn[1] > bhi.y || mn[0] > bhi.x || mx[0] < blo.x || mn[2] > bhi.z || mx[2] < blo.z) && !aabb_outside_obb(mn, mx, bc, f, bh)) {
+                        if (!below && !(mn[1] > bhi.y || mn[0] > bhi.x || mx[0] < blo.x || mn[2] > bhi.z || mx[2] < blo.z) && !box_clear_of_plane(pl, f, bc, bh) && !aabb_outside_obb(mn, mx, bc, f, bh)) {
                             const float* q = T.triRaw + (size_t)t * 9;
                             V3 n;
                             if (box_tri_contact(bc, f.ax, f.ay, f.az, bh, v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), v3(q[6], q[7], q[8]), n) && !(dot(f.ay, n) < 0.9f)) hit = true;

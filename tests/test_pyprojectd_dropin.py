@@ -108,3 +108,46 @@ def test_unmodified_reference_env_runs_on_the_module(oracle):
     assert worst_o <= 1e-2 and worst_nd <= 0.1, (worst_o, worst_nd, trace[::25])
     assert env.dstate.speedMS > 2.0, "the scripted policy must get the car moving"
     env.close(); benv.close()
+
+
+@pytest.mark.gpu
+def test_reference_env_with_the_supra(oracle):
+    """The reference's env file names a second car (`#car_model = 'ks_toyota_supra_mkiv_drift'`, projectd_env.py:25: double
+    wishbones all round, two turbochargers).  A subclass that only switches `car_model` runs on the compiled module; its
+    observations follow the oracle driven through the same call sequence (free running; no `car_tunes` entry exists for this
+    car, so none are applied on either side)."""
+    Env = _reference_env_class(oracle.BASE_PATH)
+
+    class SupraEnv(Env):
+        car_model = "ks_toyota_supra_mkiv_drift"
+
+    env = SupraEnv()
+    r = oracle.RefSim(car="ks_toyota_supra_mkiv_drift", env_setup=False)
+    r.L.pdref_teleport_mode(r.h, 0); r.L.pdref_set_auto_teleport(r.h, 0, 0, 0); r.L.pdref_set_assists(r.h, 1, 1, 1)
+    for k, v in oracle.ENV_SCORING.items():
+        r.L.pdref_set_scoring_var(r.h, k.encode(), v)
+
+    def ref_obs():
+        st = np.zeros(664, np.uint8); r.L.pdref_get_car_state(r.h, st.ctypes.data)
+        from projectd_core_b200.pyprojectd import CAR_STATE_DTYPE
+        s = np.frombuffer(st, dtype=CAR_STATE_DTYPE)[0]
+        o = np.concatenate([s["localVelocity"], s["localAngularVelocity"], s["tyreNdSlip"], [s["bodyVsTrack"], s["velocityVsTrack"]], s["lookAhead"], s["probes"][:7]])
+        return o.astype(np.float32), float(s["stepReward"])
+
+    obs0 = env.reset()
+    r.L.pdref_teleport_mode(r.h, 0); r.set_controls(steer=0.0, gas=0.55); r.step()
+    assert np.abs(obs0 - ref_obs()[0]).max() <= 1e-4
+    worst = 0.0
+    for t in range(650):      # the auto-shifter leaves neutral after ~1 s, the car is rolling at ~2 m/s after 1.5 s
+        a = np.array([0.3 * math.sin(t / 80.0), min(1.0, -0.4 + t / 150.0)], np.float32)
+        obs, rew, term, trunc, _ = env.step(a)
+        r.set_controls(steer=float(a[0]), gas=float(0.1 + 0.9 * (a[1] + 1) * 0.5)); r.step()
+        ro, rr = ref_obs()
+        if t < 250:
+            e = np.abs(obs - ro) / np.maximum(np.abs(obs), 1.0); e[6:10] = 0.0          # tyreNdSlip of the spinning rear tyres: chaotic, not bounded here
+            worst = max(worst, float(e.max()))
+            assert abs(rew - rr) <= 1e-3, t
+        assert not term, t
+    assert worst <= 1e-2, worst
+    assert env.dstate.speedMS > 2.0 and env.dstate.engineRPM > 1500.0
+    env.close()
