@@ -187,7 +187,7 @@ int pd_sync(pd_batch* b);
 void* pd_stream(pd_batch* b);                        /* the cudaStream_t every kernel of this batch runs on */
 /* number of kernels launched by this batch since creation (bench.py's gpu_launches) */
 uint64_t pd_launch_count(const pd_batch* b);
-/* name of the tick kernel this batch dispatches to ("k_tick_quad": <= 8192 envs, "k_tick": larger batches) */
+/* name of the tick kernel this batch dispatches to ("k_tick_quad": <= 20480 envs, "k_tick": larger batches) */
 const char* pd_tick_kernel(const pd_batch* b);
 /* the exact kernel instance: "k_tick_quad<2>" / "<4>" / "<8>" (cars per warp), "k_tick", or for the double-wishbone cars
  * "k_tick<strut,dwb>" / "k_tick<dwb,dwb>"; the parity tests run on every one */

@@ -599,7 +599,7 @@ static_assert(sizeof(PdCarStateOut) == 664, "CarState is 664 bytes");
 
 /* batches up to PD_QUAD_MAX_ENVS: four lanes per car (latency-bound regime, more warps per car);
  * larger batches: one thread per car (throughput regime, no redundant scalar work) */
-#define PD_QUAD_MAX_ENVS 8192
+#define PD_QUAD_MAX_ENVS 20480     /* measured crossover on B200 (round 2, k_tick_quad<8> against k_tick + k_collide2, M car-ticks/s): 12288 envs 37.2 / 26.7, 16384: 41.9 / 33.0, 24576: 43.8 / 47.8, 32768: 48.8 / 56.4 */
 
 struct pd_batch {
     int n = 0, device = 0;
