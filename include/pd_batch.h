@@ -189,8 +189,9 @@ void* pd_stream(pd_batch* b);                        /* the cudaStream_t every k
 uint64_t pd_launch_count(const pd_batch* b);
 /* name of the tick kernel this batch dispatches to ("k_tick_quad": <= 20480 envs, "k_tick": larger batches) */
 const char* pd_tick_kernel(const pd_batch* b);
-/* the exact kernel instance: "k_tick_quad<2>" / "<4>" / "<8>" (cars per warp), "k_tick", or for the double-wishbone cars
- * "k_tick<strut,dwb>" / "k_tick<dwb,dwb>"; the parity tests run on every one */
+/* the exact kernel instance: "k_tick_quad<2>" / "<4>" / "<8>" (cars per warp; "<4,strut,dwb>" ... for the double-wishbone cars), "k_tick" (128
+ * registers: batches beyond 37888 envs), "k_tick/255" (255 registers: thread-per-car batches that fit one wave at 4 blocks per SM), "k_tick<strut,dwb>" /
+ * "k_tick<dwb,dwb>"; the parity tests run on every one */
 const char* pd_tick_kernel_instance(const pd_batch* b);
 /* suspension topology of the loaded car: (front == DWB) * 2 + (rear == DWB)  (Car.cpp:74-117: SuspensionStrut / SuspensionDW /
  * SuspensionAxle chosen from suspensions.ini [FRONT] / [REAR] TYPE) */

@@ -108,8 +108,11 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
 #ifndef PD_SERIAL_MINBLOCKS
 #define PD_SERIAL_MINBLOCKS 8
 #endif
-template <int TOPO>       /* suspension topology (PD_TOPO_*): one compile-time instance per (front, rear) pair of the bundled cars */
-__global__ void __launch_bounds__(PD_BLOCK, PD_SERIAL_MINBLOCKS) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+/* MB = resident blocks per SM the register budget is set for: 8 (128 registers) lets a 65536-env batch sit in ONE wave (1024 blocks of 64 threads on
+ * 148 x 8 slots); a batch of at most 148 x 4 x 64 = 37888 envs fits one wave at 4 blocks per SM, where ptxas may take 255 registers and keeps more of the
+ * tick out of local memory: measured +7.7 % at 24576 envs, +10.5 % at 32768 (and -45 % at 65536, where it means two waves). */
+template <int TOPO, int MB = PD_SERIAL_MINBLOCKS>       /* TOPO: suspension topology (PD_TOPO_*), one compile-time instance per (front, rear) pair of the bundled cars */
+__global__ void __launch_bounds__(PD_BLOCK, MB) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                    const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     const long long clk0 = io.clk ? clock64() : 0;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,6 +618,7 @@ struct pd_batch {
     float* dReward = nullptr; float* dTotal = nullptr; int32_t* dFlags = nullptr; int32_t* dDone = nullptr;
     float* dEnvReturn = nullptr; int32_t* dEnvLen = nullptr; double* dStats = nullptr;
     long long* dClk = nullptr; int nClk = 0;
+    bool serialWide = false;          /* thread-per-car kernel with the 255-register budget (batches that fit one wave at 4 blocks per SM; env PD_SERIAL_WIDE overrides) */
     int serialSmemPad = 0;            /* tuning knob (env PD_SERIAL_SMEM_PAD, bytes): unused dynamic shared memory per block of k_tick, caps the resident blocks per SM */
     int collideLpc = 4;               /* env PD_COLLIDE_LPC: lanes per car of k_collide2's floor test (1 / 4 / 8 / 16); measured at 65536 envs: 79.4 / 81.1 / 80.2 / 78.2 M car-ticks/s (warp per car, k_collide: 75.3 M) */
     bool debugSkipCollision = false;  /* env PD_DEBUG_SKIP_COLLISION=1: MEASUREMENT ONLY -- no collision test at all (wrong flags), to see what the detection costs a tick */
@@ -727,7 +731,9 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
        (168 registers x 64 threads -> 6 blocks per SM; shared memory allows 2 / 4 / 8 blocks for 8 / 4 / 2 cars per warp) */
     { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); const int sms = prop.multiProcessorCount;
       b->quadCpw = (n_envs <= sms * 6 * 4) ? 2 : (n_envs <= sms * 4 * 8) ? 4 : 8;
-      if (const char* q = getenv("PD_QUAD_CPW")) { const int v = atoi(q); if (v == 2 || v == 4 || v == 8) b->quadCpw = v; } }
+      if (const char* q = getenv("PD_QUAD_CPW")) { const int v = atoi(q); if (v == 2 || v == 4 || v == 8) b->quadCpw = v; }
+      b->serialWide = n_envs <= sms * 4 * PD_BLOCK;
+      if (const char* q = getenv("PD_SERIAL_WIDE")) b->serialWide = atoi(q) != 0; }
     b->layout = (n_envs <= b->quadMax) ? PD_LAYOUT_RECORDS : PD_LAYOUT_TILED;
     if (b->car.P.topology != PD_TOPO_STRUT_AXLE && b->quadCpw == 2) b->quadCpw = 4;      /* double-wishbone cars: the 4-lanes-per-car kernel is instantiated for 4 and 8 cars per warp */
     int rc;
@@ -860,7 +866,10 @@ static void launch_tick(pd_batch* b, float dt, const int32_t* mask, const EnvIO&
         switch (b->car.P.topology) {
         case PD_TOPO_STRUT_DW: k_tick<PD_TOPO_STRUT_DW><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
         case PD_TOPO_DW_DW: k_tick<PD_TOPO_DW_DW><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
-        default: k_tick<PD_TOPO_STRUT_AXLE><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io); break;
+        default:
+            if (b->serialWide) k_tick<PD_TOPO_STRUT_AXLE, 4><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+            else k_tick<PD_TOPO_STRUT_AXLE><<<grid(b->n, PD_BLOCK), PD_BLOCK, b->serialSmemPad, b->stream>>>(b->car.P, b->dev, b->dState, b->n, dt, b->time, mask, io);
+            break;
         }
     b->launches++;
 }
@@ -1268,7 +1277,7 @@ const char* pd_tick_kernel(const pd_batch* b) { return !b ? "" : (b->layout == P
 int pd_topology(const pd_batch* b) { return b ? b->car.P.topology : -1; }
 const char* pd_tick_kernel_instance(const pd_batch* b) {
     if (!b) return "";
-    if (b->layout != PD_LAYOUT_RECORDS) return b->car.P.topology == PD_TOPO_STRUT_DW ? "k_tick<strut,dwb>" : (b->car.P.topology == PD_TOPO_DW_DW ? "k_tick<dwb,dwb>" : "k_tick");
+    if (b->layout != PD_LAYOUT_RECORDS) return b->car.P.topology == PD_TOPO_STRUT_DW ? "k_tick<strut,dwb>" : (b->car.P.topology == PD_TOPO_DW_DW ? "k_tick<dwb,dwb>" : (b->serialWide ? "k_tick/255" : "k_tick"));
     if (b->car.P.topology == PD_TOPO_STRUT_DW) return b->quadCpw == 4 ? "k_tick_quad<4,strut,dwb>" : "k_tick_quad<8,strut,dwb>";
     if (b->car.P.topology == PD_TOPO_DW_DW) return b->quadCpw == 4 ? "k_tick_quad<4,dwb,dwb>" : "k_tick_quad<8,dwb,dwb>";
     return b->quadCpw == 2 ? "k_tick_quad<2>" : b->quadCpw == 4 ? "k_tick_quad<4>" : "k_tick_quad<8>";

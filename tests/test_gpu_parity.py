@@ -93,7 +93,8 @@ KERNELS = {
     "k_tick_quad<2>": {"PD_QUAD_MAX_ENVS": "20480", "PD_QUAD_CPW": "2"},
     "k_tick_quad<4>": {"PD_QUAD_MAX_ENVS": "20480", "PD_QUAD_CPW": "4"},
     "k_tick_quad<8>": {"PD_QUAD_MAX_ENVS": "20480", "PD_QUAD_CPW": "8"},
-    "k_tick": {"PD_QUAD_MAX_ENVS": "0"},
+    "k_tick": {"PD_QUAD_MAX_ENVS": "0", "PD_SERIAL_WIDE": "0"},          # the 128-register instance: what batches beyond 37888 envs (the 65536-env bench) run
+    "k_tick/255": {"PD_QUAD_MAX_ENVS": "0", "PD_SERIAL_WIDE": "1"},      # the 255-register instance: thread-per-car batches that fit one wave at 4 blocks per SM
 }
 
 
@@ -364,7 +365,7 @@ def test_autoreset_next_step_equals_same_step(oracle, kernel, monkeypatch):
     the reset observation PD_AUTORESET_SAME_STEP produces (teleport + zero-action tick, projectd_env.py:216-227), with
     the same done / reward on the finishing step and (0, 0) on the reset step."""
     import torch
-    monkeypatch.setenv("PD_QUAD_MAX_ENVS", "20480" if kernel == "k_tick_quad" else "0")
+    monkeypatch.setenv("PD_QUAD_MAX_ENVS", "20480" if kernel == "k_tick_quad" else "0"); monkeypatch.setenv("PD_SERIAL_WIDE", "0")
     n = 64
     a = _batch(oracle, n); a.set_seed(5, 0); a.teleport_spline(np.linspace(0, 0.9, n))
     c = _batch(oracle, n); c.set_seed(5, 0); c.teleport_spline(np.linspace(0, 0.9, n)); c.set_autoreset(1)
@@ -398,7 +399,7 @@ def test_autoreset_next_step_equals_same_step(oracle, kernel, monkeypatch):
 def test_collision_flag_matches_oracle(oracle, lay, golden, kernel, monkeypatch):
     """SURVEY.md A14 on the GPU: collisionFlag after one tick on an odd physics frame for the golden collision cases
     (whole car translated towards walls / into the ground) and for fresh random cases checked against the oracle live."""
-    monkeypatch.setenv("PD_QUAD_MAX_ENVS", "20480" if kernel == "k_tick_quad" else "0")
+    monkeypatch.setenv("PD_QUAD_MAX_ENVS", "20480" if kernel == "k_tick_quad" else "0"); monkeypatch.setenv("PD_SERIAL_WIDE", "0")
     flags = golden["coll_flag"]; n = len(flags)
     b = _batch(oracle, n)
     assert b.tick_kernel() == kernel
