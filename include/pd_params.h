@@ -86,7 +86,18 @@ typedef struct PdDW {
     PdDamper damper;
     PdDBall link[PD_DW_LINKS]; /* joints[0..4]: top rear, top front, bottom rear, bottom front, steer rod (chassis <-> hub) */
     float hubMass, hubInertia[3];
+    /* 1: SuspensionML (Car/SuspensionML.cpp:15-137) -- the same hub + five distance joints (JOINTn_CAR / JOINTn_TYRE), spring force applied
+     * whatever its sign, plain packer, no bump stops, joints left at the world's ERP / CFM (its setERPCFM is empty) */
+    int32_t multilink, pad0;
 } PdDW;
+
+/* HeaveSpring (Car/HeaveSpring.cpp:11-149): a third spring + damper between the chassis and the MEAN travel of the two hubs of a double-wishbone
+ * axle, suspensions.ini [HEAVE_FRONT] / [HEAVE_REAR] */
+typedef struct PdHeave {
+    int32_t present, pad0;
+    float bumpStopUp, bumpStopDn, rodLength, k, progressiveK, bumpStopRate, packerRange;
+    PdDamper damper;
+} PdHeave;
 
 /* Turbo (Car/Turbo.h, Engine.cpp:69-94) */
 #define PD_MAX_TURBOS 3
@@ -230,6 +241,7 @@ typedef struct PdCarParams {
     int32_t topology, nTurbos;
     PdDW dw[PD_NUM_WHEELS];
     PdTurbo turbo[PD_MAX_TURBOS];
+    PdHeave heave[2];          /* front, rear (only between two double-wishbone corners, Car.cpp:131-146) */
 } PdCarParams;
 
 /* ---- track (Sim/Track.cpp) ---- */

@@ -41,8 +41,10 @@ struct RefSim {
     std::string err;
 };
 
-static bool front_dw(Car* c) { return c->suspensionTypeF == SuspensionType::DoubleWishbone; }
-static bool rear_dw(Car* c) { return c->suspensionTypeR == SuspensionType::DoubleWishbone; }
+/* "hub on five distance joints": SuspensionDW or SuspensionML (the record and the kernels treat them alike, PdDW::multilink tells them apart) */
+static bool front_dw(Car* c) { return c->suspensionTypeF == SuspensionType::DoubleWishbone || c->suspensionTypeF == SuspensionType::Multilink; }
+static bool rear_dw(Car* c) { return c->suspensionTypeR == SuspensionType::DoubleWishbone || c->suspensionTypeR == SuspensionType::Multilink; }
+static IRigidBody* dw_hub(ISuspension* s) { return s->getType() == SuspensionType::Multilink ? static_cast<SuspensionML*>(s)->hub.get() : static_cast<SuspensionDW*>(s)->hub.get(); }
 /* the body kept in slot b of the record (include/pd_state.h), or null when this car's topology has none there */
 static oder::Body* body_of(RefSim* h, int b) {
     Car* c = h->car;
@@ -51,12 +53,12 @@ static oder::Body* body_of(RefSim* h, int b) {
     case PD_BODY_TANK: return pdref_body(c->fuelTankBody.get());
     case PD_BODY_HUB0: case PD_BODY_HUB1: {
         ISuspension* s = c->suspensions[(b - PD_BODY_HUB0) / 2];
-        return front_dw(c) ? pdref_body(static_cast<SuspensionDW*>(s)->hub.get()) : pdref_body(static_cast<SuspensionStrut*>(s)->hub.get());
+        return front_dw(c) ? pdref_body(dw_hub(s)) : pdref_body(static_cast<SuspensionStrut*>(s)->hub.get());
     }
     case PD_BODY_STRUT0: case PD_BODY_STRUT1:
         return front_dw(c) ? nullptr : pdref_body(static_cast<SuspensionStrut*>(c->suspensions[(b - PD_BODY_STRUT0) / 2])->strutBody.get());
-    case PD_BODY_AXLE: return rear_dw(c) ? pdref_body(static_cast<SuspensionDW*>(c->suspensions[2])->hub.get()) : pdref_body(c->rigidAxle.get());
-    case PD_BODY_HUB3: return rear_dw(c) ? pdref_body(static_cast<SuspensionDW*>(c->suspensions[3])->hub.get()) : nullptr;
+    case PD_BODY_AXLE: return rear_dw(c) ? pdref_body(dw_hub(c->suspensions[2])) : pdref_body(c->rigidAxle.get());
+    case PD_BODY_HUB3: return rear_dw(c) ? pdref_body(dw_hub(c->suspensions[3])) : nullptr;
     }
     return nullptr;
 }
@@ -358,6 +360,18 @@ void pdref_get_params(void* hv, PdCarParams* P) {
     P->topology = (front_dw(c) ? 2 : 0) + (rear_dw(c) ? 1 : 0);
     for (int i = 0; i < 4; ++i) {
         if (!(i < 2 ? front_dw(c) : rear_dw(c))) continue;
+        if (c->suspensions[i]->getType() == SuspensionType::Multilink) {
+            SuspensionML* s = static_cast<SuspensionML*>(c->suspensions[i]); PdDW& d = P->dw[i];
+            d.multilink = 1;
+            v3(d.refPoint, s->basePosition); v3(d.baseCarSteer, s->baseCarSteerPosition); v3(d.tyreSteer, s->joints[4].ballTyre.relToTyre);
+            d.rodLength = s->rodLength; d.k = s->k; d.progressiveK = s->progressiveK; d.packerRange = s->packerRange; d.bumpStopRate = s->bumpStopRate;
+            d.bumpStopProgressive = s->bumpStopProgressive; d.bumpStopUp = s->bumpStopUp; d.bumpStopDn = s->bumpStopDn;
+            d.toeOutLinear = s->toeOUT_Linear; d.staticCamber = s->staticCamber; d.baseCFM = s->baseCFM;
+            copy_damper(d.damper, s->damper);
+            for (int l = 0; l < PD_DW_LINKS; ++l) copy_dball(d.link[l], s->joints[l].joint.get(), pdref_joint(s->joints[l].joint.get())->targetDistance);
+            { oder::Body* b = pdref_body(s->hub.get()); d.hubMass = b->mass; for (int k = 0; k < 3; ++k) d.hubInertia[k] = b->I[k]; }
+            continue;
+        }
         SuspensionDW* s = static_cast<SuspensionDW*>(c->suspensions[i]); PdDW& d = P->dw[i];
         v3(d.refPoint, s->dataRelToWheel.refPoint); v3(d.baseCarSteer, s->baseCarSteerPosition); v3(d.tyreSteer, s->dataRelToWheel.tyreSteer);
         d.rodLength = s->rodLength; d.k = s->k; d.progressiveK = s->progressiveK; d.packerRange = s->packerRange; d.bumpStopRate = s->bumpStopRate;
@@ -391,6 +405,12 @@ void pdref_get_params(void* hv, PdCarParams* P) {
         for (int l = 0; l < d.nLinks && l < PD_AXLE_LINKS; ++l) copy_dball(d.link[l], s->joints[l].ballAxle.joint.get(), pdref_joint(s->joints[l].ballAxle.joint.get())->targetDistance);
         { oder::Body* b = pdref_body(c->rigidAxle.get()); d.axleMass = b->mass; for (int k = 0; k < 3; ++k) d.axleInertia[k] = b->I[k]; }
         d.torqueReaction = c->axleTorqueReaction;
+    }
+    for (auto& hs : c->heaveSprings) {
+        if (!hs->isPresent) continue;
+        PdHeave& d = P->heave[hs->isFront ? 0 : 1];
+        d.present = 1; d.bumpStopUp = hs->bumpStopUp; d.bumpStopDn = hs->bumpStopDn; d.rodLength = hs->rodLength; d.k = hs->k; d.progressiveK = hs->progressiveK;
+        d.bumpStopRate = hs->bumpStopRate; d.packerRange = hs->packerRange; copy_damper(d.damper, hs->damper);
     }
     P->arbK[0] = c->antirollBars[0]->k; P->arbK[1] = c->antirollBars[1]->k;
     { BrakeSystem* b = c->brakeSystem.get(); P->brakes.brakePower = b->brakePower; P->brakes.brakePowerMultiplier = b->brakePowerMultiplier;

@@ -229,6 +229,53 @@ static void load_dw(const Ini& ini, int index, const HBody& car, PdDW& D) {
     }
 }
 
+/* SuspensionML::init (SuspensionML.cpp:15-99) for wheel `index`: kept in a PdDW (same bodies, joints and solver group), multilink = 1 */
+static void load_ml(const Ini& ini, int index, const HBody& car, PdDW& D) {
+    memset(&D, 0, sizeof(D));
+    D.multilink = 1; D.baseCFM = 0.0000001f;      /* SuspensionML::SuspensionML; unused by its joints (setERPCFM is empty) */
+    const std::string id = index < 2 ? "FRONT" : "REAR";
+    const float fWheelBase = ini.getFloat("BASIC", "WHEELBASE"), fCg = ini.getFloat("BASIC", "CG_LOCATION");
+    const float fFrontBaseY = ini.getFloat("FRONT", "BASEY"), fFrontTrack = ini.getFloat("FRONT", "TRACK") * 0.5f;
+    const float fRearBaseY = ini.getFloat("REAR", "BASEY"), fRearTrack = ini.getFloat("REAR", "TRACK") * 0.5f;
+    V ref[4] = {{fFrontTrack, fFrontBaseY, (1.0f - fCg) * fWheelBase}, {-fFrontTrack, fFrontBaseY, (1.0f - fCg) * fWheelBase},
+                {fRearTrack, fRearBaseY, -(fCg * fWheelBase)}, {-fRearTrack, fRearBaseY, -(fCg * fWheelBase)}};
+    const V basePosition = ref[index];
+    put(D.refPoint, basePosition);
+    D.hubMass = ini.getFloat(id, "HUB_MASS"); box_inertia(D.hubMass, 0.2f, 0.6f, 0.6f, D.hubInertia);
+    HBody hub;
+    hub.setRotationAxes({car.R[0], car.R[3], car.R[6]}, {car.R[1], car.R[4], car.R[7]}, {car.R[2], car.R[5], car.R[8]});
+    hub.setPos(car.toWorld(basePosition));
+    V tyre4 = {0, 0, 0};
+    for (int i = 0; i < 5; ++i) {
+        float t[3];
+        ini.getFloat3(id, "JOINT" + std::to_string(i) + "_CAR", t); V ballCar = {t[0], t[1], t[2]};
+        ini.getFloat3(id, "JOINT" + std::to_string(i) + "_TYRE", t); V ballTyre = {t[0], t[1], t[2]};
+        if (basePosition.x > 0.0f) { ballCar.x *= -1.0f; ballTyre.x *= -1.0f; }
+        const V carRel = car.toLocal(hub.toWorld(ballCar)), tyreRel = car.toLocal(hub.toWorld(ballTyre));
+        make_dball(D.link[i], car, hub, car.toWorld(carRel), car.toWorld(tyreRel));
+        if (i == 4) { put(D.baseCarSteer, carRel); tyre4 = ballTyre; }
+    }
+    put(D.tyreSteer, tyre4);
+    D.rodLength = ini.getFloat(id, "ROD_LENGTH"); D.toeOutLinear = ini.getFloat(id, "TOE_OUT");
+    D.k = ini.getFloat(id, "SPRING_RATE"); D.progressiveK = ini.getFloat(id, "PROGRESSIVE_SPRING_RATE");
+    D.damper.bumpSlow = ini.getFloat(id, "DAMP_BUMP"); D.damper.reboundSlow = ini.getFloat(id, "DAMP_REBOUND");
+    D.damper.bumpFast = ini.getFloat(id, "DAMP_FAST_BUMP"); D.damper.reboundFast = ini.getFloat(id, "DAMP_FAST_REBOUND");
+    D.damper.fastThresholdBump = ini.getFloat(id, "DAMP_FAST_BUMPTHRESHOLD"); D.damper.fastThresholdRebound = ini.getFloat(id, "DAMP_FAST_REBOUNDTHRESHOLD");     /* no defaults here (SuspensionML.cpp:80-85) */
+    D.staticCamber = -ini.getFloat(id, "STATIC_CAMBER") * 0.017453f; if (index % 2) D.staticCamber *= -1.0f;
+}
+/* HeaveSpring::init (HeaveSpring.cpp:11-54) */
+static void load_heave(const Ini& ini, bool front, PdHeave& H) {
+    memset(&H, 0, sizeof(H));
+    const std::string id = front ? "HEAVE_FRONT" : "HEAVE_REAR";
+    if (!ini.hasSection(id)) return;
+    H.present = 1;
+    H.bumpStopUp = ini.getFloat(id, "BUMPSTOP_UP"); H.bumpStopDn = -ini.getFloat(id, "BUMPSTOP_DN");
+    H.rodLength = ini.getFloat(id, "ROD_LENGTH"); H.k = ini.getFloat(id, "SPRING_RATE"); H.progressiveK = ini.getFloat(id, "PROGRESSIVE_SPRING_RATE");
+    load_damper(ini, id, H.damper);
+    H.bumpStopRate = ini.getFloat(id, "BUMP_STOP_RATE"); if (H.bumpStopRate == 0.0f) H.bumpStopRate = 500000.0f;
+    H.packerRange = ini.getFloat(id, "PACKER_RANGE");
+}
+
 static void load_axle(const Ini& ini, const HBody& car, PdAxle& A) {
     memset(&A, 0, sizeof(A));
     A.baseCFM = 0.0000001f; A.attachRelativePos = 1.0f;
@@ -595,16 +642,19 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
     Ini susp(dataPath + "suspensions.ini");
     if (!susp.ready) throw Error("cannot read suspensions.ini");
     const std::string frontType = susp.getString("FRONT", "TYPE"), rearType = susp.getString("REAR", "TYPE");
-    if ((frontType != "STRUT" && frontType != "DWB") || (rearType != "AXLE" && rearType != "DWB"))
-        throw Error("suspension types other than STRUT / DWB (front) and AXLE / DWB (rear) are not implemented (ML: SURVEY.md N4)");
-    if (susp.hasSection("HEAVE_FRONT") || susp.hasSection("HEAVE_REAR")) throw Error("heave springs are not supported yet (SURVEY.md N4)");
-    const bool frontDW = frontType == "DWB", rearDW = rearType == "DWB";
+    if ((frontType != "STRUT" && frontType != "DWB" && frontType != "ML") || (rearType != "AXLE" && rearType != "DWB" && rearType != "ML"))
+        throw Error("unknown suspension TYPE (STRUT / DWB / ML front, AXLE / DWB / ML rear)");
+    /* a multilink corner (SuspensionML) is a hub on five distance joints like a double-wishbone one: same kernels, PdDW::multilink = 1 */
+    const bool frontML = frontType == "ML", rearML = rearType == "ML";
+    const bool frontDW = frontType == "DWB" || frontML, rearDW = rearType == "DWB" || rearML;
     P.topology = (frontDW ? 2 : 0) + (rearDW ? 1 : 0);
     if (P.topology == PD_TOPO_DW_AXLE) throw Error("DWB front with a rigid rear axle: no kernel instance is built for this pair");
     float hubMass[2];
-    if (frontDW) { load_dw(susp, 0, chassis, P.dw[0]); load_dw(susp, 1, chassis, P.dw[1]); }
+    if (frontML) { load_ml(susp, 0, chassis, P.dw[0]); load_ml(susp, 1, chassis, P.dw[1]); }
+    else if (frontDW) { load_dw(susp, 0, chassis, P.dw[0]); load_dw(susp, 1, chassis, P.dw[1]); load_heave(susp, true, P.heave[0]); }
     else { load_strut(susp, 0, chassis, P.strut[0], hubMass[0]); load_strut(susp, 1, chassis, P.strut[1], hubMass[1]); }
-    if (rearDW) { load_dw(susp, 2, chassis, P.dw[2]); load_dw(susp, 3, chassis, P.dw[3]); }
+    if (rearML) { load_ml(susp, 2, chassis, P.dw[2]); load_ml(susp, 3, chassis, P.dw[3]); }
+    else if (rearDW) { load_dw(susp, 2, chassis, P.dw[2]); load_dw(susp, 3, chassis, P.dw[3]); load_heave(susp, false, P.heave[1]); }
     else load_axle(susp, chassis, P.axle);
     P.arbK[0] = susp.getFloat("ARB", "FRONT"); P.arbK[1] = susp.getFloat("ARB", "REAR");
     if (file_exists(dataPath + "ctrl_arb_front.ini") || file_exists(dataPath + "ctrl_arb_rear.ini")) throw Error("ARB dynamic controllers are not supported yet");

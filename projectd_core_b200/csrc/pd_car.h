@@ -169,11 +169,17 @@ PD_HD void dw_step(const PdDW& P, Body& C, Body& H, float& travelOut, float& dam
     const float fTravel = fHubDeltaY + P.rodLength;
     travelOut = fTravel;
     float fForce = ((fTravel * P.progressiveK) + P.k) * fTravel;
+    if (P.multilink) { /* SuspensionML::step (SuspensionML.cpp:105-137): plain packer, the force acts whatever its sign, no bump stops */
+        if (P.packerRange != 0.0f && fTravel > P.packerRange && P.k != 0.0f) fForce += ((fTravel - P.packerRange) * P.bumpStopRate);
+        add_force_at_pos(H, vBodyM2 * -fForce, vHubWorldPos);
+        add_rel_force_at_rel_pos(C, v3(0.0f, fForce, 0.0f), vRef);
+    } else {
     if (P.packerRange != 0.0f && fTravel > P.packerRange && P.k != 0.0f)
         fForce += (((fTravel - P.packerRange) * P.bumpStopProgressive) + P.bumpStopRate) * (fTravel - P.packerRange);
     if (fForce > 0.0f) {
         add_force_at_pos(H, vBodyM2 * -fForce, vHubWorldPos);
         add_rel_force_at_rel_pos(C, v3(0, fForce, 0), vRef);
+    }
     }
     const V3 vDeltaVel = H.v - body_rel_point_vel(C, vRef);
     const float fDamperSpeed = dot(vDeltaVel, vBodyM2);
@@ -182,6 +188,7 @@ PD_HD void dw_step(const PdDW& P, Body& C, Body& H, float& travelOut, float& dam
     const V3 vForce = vBodyM2 * fDamperForce;
     add_force_at_pos(H, vForce, vHubWorldPos);
     add_force_at_rel_pos(C, vForce * -1.0f, vRef);
+    if (P.multilink) return;
     if (P.bumpStopUp != 0.0f && fHubDeltaY > P.bumpStopUp && 0.0f != P.k) {
         const float f = (((fHubDeltaY - P.bumpStopUp) * P.bumpStopProgressive) + P.bumpStopRate) * (fHubDeltaY - P.bumpStopUp);
         add_force_at_pos(H, vBodyM2 * -f, vHubWorldPos);
@@ -192,6 +199,34 @@ PD_HD void dw_step(const PdDW& P, Body& C, Body& H, float& travelOut, float& dam
         add_force_at_pos(H, vBodyM2 * -f, vHubWorldPos);
         add_rel_force_at_rel_pos(C, v3(0, f, 0), vHubLocalPos);
     }
+}
+
+/* HeaveSpring::step (HeaveSpring.cpp:56-149) between the hubs H0 (left) / H1 (right) of a double-wishbone axle.  `mine`: 0 / 1 = apply only what
+ * acts on hub 0 / hub 1 and the chassis share at its reference point (one lane per corner), -1 = everything (one thread per car). */
+PD_HD void heave_step(const PdHeave& Hv, const PdDW& D0, const PdDW& D1, Body& C, Body& H0, V3 hubPos0, V3 hubVel0, Body& H1, V3 hubPos1, V3 hubVel1, int mine) {
+    const V3 vM2 = C.fr.ay;
+    const V3 vRefPoint0 = v3(D0.refPoint[0], D0.refPoint[1], D0.refPoint[2]), vRefPoint1 = v3(D1.refPoint[0], D1.refPoint[1], D1.refPoint[2]);
+    const V3 vHubLoc0 = to_local(C.fr, hubPos0), vHubLoc1 = to_local(C.fr, hubPos1);
+    float rodLength = Hv.rodLength;
+    if (D0.k != 0.0f || D1.k != 0.0f) rodLength = (D1.rodLength + D0.rodLength) * 0.5f;
+    const float fAvgY = (vHubLoc0.y + vHubLoc1.y) * 0.5f;
+    const float fTravel = (fAvgY - D0.refPoint[1]) + rodLength;
+    auto apply = [&](V3 hubForce, V3 bodyLocalForce) {
+        if (mine != 1) { add_force_at_pos(H0, hubForce, hubPos0); add_rel_force_at_rel_pos(C, bodyLocalForce, vRefPoint0); }
+        if (mine != 0) { add_force_at_pos(H1, hubForce, hubPos1); add_rel_force_at_rel_pos(C, bodyLocalForce, vRefPoint1); }
+    };
+    float v12 = ((fTravel * Hv.progressiveK) + Hv.k) * fTravel;
+    if (Hv.packerRange != 0.0f && fTravel > Hv.packerRange) v12 += ((fTravel - Hv.packerRange) * Hv.bumpStopRate);
+    apply(vM2 * -v12, v3(0.0f, v12, 0.0f));
+    const float fDeltaY0 = fAvgY - D0.refPoint[1];
+    if (Hv.bumpStopUp != 0.0f && fDeltaY0 > Hv.bumpStopUp) { const float f = (fDeltaY0 - Hv.bumpStopUp) * 500000.0f; apply(vM2 * -f, v3(0.0f, f, 0.0f)); }
+    if (Hv.bumpStopDn != 0.0f && fDeltaY0 < Hv.bumpStopDn) { const float f = (fDeltaY0 - Hv.bumpStopDn) * 500000.0f; apply(vM2 * -f, v3(0.0f, f, 0.0f)); }
+    const V3 vHubVel = (hubVel0 + hubVel1) * 0.5f;
+    const V3 vLpv = (body_rel_point_vel(C, vRefPoint0) + body_rel_point_vel(C, vRefPoint1)) * 0.5f;
+    const float fDamperForce = damper_force(Hv.damper, dot(vHubVel - vLpv, vM2));
+    V3 vForce = vM2 * fDamperForce;
+    /* the reference hands the damper's chassis share to addLocalForceAtLocalPos although it is a world vector (HeaveSpring.cpp:145-148): kept as is */
+    apply(vForce, vForce * -1.0f);
 }
 
 /* AntirollBar::step (AntirollBar.cpp:19-47) */

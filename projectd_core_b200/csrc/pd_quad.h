@@ -75,7 +75,7 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     {
         const float fVelSq = sqlen(C.v);
         X.dballErp = (fVelSq >= 1.0f) ? 0.3f : 0.9f;
-        X.dballCfm = (fVelSq >= 1.0f) ? (FDW ? P.dw[0].baseCFM : P.strut[0].baseCFM) : 0.0000001f;
+        X.dballCfm = (fVelSq >= 1.0f) ? susp_base_cfm<TOPO>(P) : 0.0000001f;
     }
     c.ctlSteer = tclampf(c.ctlSteer, -1.0f, 1.0f); c.ctlClutch = tclampf(c.ctlClutch, 0.0f, 1.0f); c.ctlBrake = tclampf(c.ctlBrake, 0.0f, 1.0f);
     c.ctlHandBrake = tclampf(c.ctlHandBrake, 0.0f, 1.0f); c.ctlGas = tclampf(c.ctlGas, 0.0f, 1.0f);
@@ -142,6 +142,15 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
         L.load = ex.get(my.load, w); L.feedbackTorque = ex.get(my.feedbackTorque, w); L.angularVelocity = ex.get(my.angularVelocity, w);
         L.brakeTorque = ex.get(my.brakeTorque, w); L.handBrakeTorque = ex.get(my.handBrakeTorque, w); L.ndSlip = ex.get(my.ndSlip, w);
         L.slipRatio = ex.get(my.slipRatio, w); L.isLocked = ex.get(my.isLocked, w); L.surfaceId = ex.get(my.surfaceId, w);
+    }
+    if constexpr (FDW || RDW) if (P.heave[0].present || P.heave[1].present) {      /* heave springs (uniform condition: every lane of the quad takes part in the exchange) */
+        const V3 pp = ex.get(W.fr.p, lane ^ 1), pv = ex.get(W.v, lane ^ 1);
+        if (laneDW && P.heave[front ? 0 : 1].present && P.heave[front ? 0 : 1].k != 0.0f) {      /* this axle's spring: each lane applies what acts on its own hub */
+        const int a = front ? 0 : 2;
+        Body dummy = W;
+        if ((lane & 1) == 0) heave_step(P.heave[front ? 0 : 1], P.dw[a], P.dw[a + 1], C, W, W.fr.p, W.v, dummy, pp, pv, 0);
+        else heave_step(P.heave[front ? 0 : 1], P.dw[a], P.dw[a + 1], C, dummy, pp, pv, W, W.fr.p, W.v, 1);
+        }
     }
     if (lane == 0) aero_step(P, C);          /* all wings on one lane: the chassis force is then accumulated in the reference's order (a per-lane split is ~2 % faster but re-associates the sum, and the 1 s free-running divergence test is sensitive to that) */
     V3 steerA1 = v3(0, 0, 0), steerA2 = v3(0, 0, 0);
@@ -221,7 +230,11 @@ PD_HDN void car_tick_quad(const PdCarParams& P, const TrackDev& T, const SVX& sv
     if (hasStrutBody) strut_factor(P, P.strut[lane], C, W, S, steerA1, steerA2, dA, dB, dC, hinv, X.dballErp, X.dballCfm, GS, S21, b6);
     else {
         float cfm[6];
-        if (laneDW) { const V3 st[2] = {steerA1, steerA2}; single_rows_links(P.dw[lane].link, PD_DW_LINKS, C, W, hinv, X.dballErp, X.dballCfm, G1, cfm, front ? st : nullptr); }
+        if (laneDW) {
+            const V3 st[2] = {steerA1, steerA2};
+            const bool ml = P.dw[lane].multilink != 0;       /* SuspensionML's joints keep the world's ERP / CFM */
+            single_rows_links(P.dw[lane].link, PD_DW_LINKS, C, W, hinv, ml ? P.worldERP : X.dballErp, ml ? P.worldCFM : X.dballCfm, G1, cfm, front ? st : nullptr);
+        }
         else if (lane == 2) single_rows_axle(P, C, W, hinv, X.dballErp, X.dballCfm, G1, cfm);
         else single_rows_tank(P, S, C, hinv, G1, cfm);
         single_factor(G1, cfm, dA, dC, hinv, S21, b6);

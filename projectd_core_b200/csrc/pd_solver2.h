@@ -395,8 +395,9 @@ PD_HDN void contacts_solve(const PdCarParams& P, const float* __restrict__ cont,
 template <int TOPO> PD_HD constexpr bool topo_has_body(int i) { return (i == PD_BODY_STRUT0 || i == PD_BODY_STRUT1) ? !PD_TOPO_FRONT_DW(TOPO) : (i == PD_BODY_HUB3 ? PD_TOPO_REAR_DW(TOPO) : true); }
 PD_HD bool topo_has_body_rt(int topo, int i) { return (i == PD_BODY_STRUT0 || i == PD_BODY_STRUT1) ? !PD_TOPO_FRONT_DW(topo) : (i == PD_BODY_HUB3 ? PD_TOPO_REAR_DW(topo) : true); }
 /* a double-wishbone corner as a single-body group: hub w held by its five links */
-PD_HD void dw_factor(const PdDW& D, const Body& C, const Body& H, const V3* steer, const BodyDyn& dH, const BodyDyn& dC, float hinv, float dballErp, float dballCfm, float* R, float* S21, float* b6) {
+PD_HD void dw_factor(const PdCarParams& P, const PdDW& D, const Body& C, const Body& H, const V3* steer, const BodyDyn& dH, const BodyDyn& dC, float hinv, float dballErp, float dballCfm, float* R, float* S21, float* b6) {
     SingleSys G; G.R = R; float cfm[6];
+    if (D.multilink) { dballErp = P.worldERP; dballCfm = P.worldCFM; }      /* SuspensionML::setERPCFM is empty: its joints keep the world's values */
     single_rows_links(D.link, PD_DW_LINKS, C, H, hinv, dballErp, dballCfm, G, cfm, steer);
     single_factor(G, cfm, dH, dC, hinv, S21, b6);
 }
@@ -418,7 +419,7 @@ PD_HDN void world_step2(const PdCarParams& P, Body* b, const V3* steerAnchor1, c
     for (int s = 0; s < 2; ++s) {
         if constexpr (FDW) {
             const V3 st[2] = {steerAnchor1[s], steerAnchor2[s]};
-            dw_factor(P.dw[s], C, b[PD_BODY_HUB0 + 2 * s], st, dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, RS[s], S21, b6);
+            dw_factor(P, P.dw[s], C, b[PD_BODY_HUB0 + 2 * s], st, dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, RS[s], S21, b6);
         } else {
             StrutSys GS; GS.R = RS[s];
             strut_factor(P, P.strut[s], C, b[PD_BODY_HUB0 + 2 * s], b[PD_BODY_STRUT0 + 2 * s], steerAnchor1[s], steerAnchor2[s], dyn[PD_BODY_HUB0 + 2 * s], dyn[PD_BODY_STRUT0 + 2 * s],
@@ -427,7 +428,7 @@ PD_HDN void world_step2(const PdCarParams& P, Body* b, const V3* steerAnchor1, c
     }
     if constexpr (RDW) {
         PD_NOUNROLL
-        for (int s = 0; s < 2; ++s) dw_factor(P.dw[2 + s], C, b[PD_BODY_HUB2 + s], nullptr, dyn[PD_BODY_HUB2 + s], dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, RA[s], S21, b6);
+        for (int s = 0; s < 2; ++s) dw_factor(P, P.dw[2 + s], C, b[PD_BODY_HUB2 + s], nullptr, dyn[PD_BODY_HUB2 + s], dyn[PD_BODY_CHASSIS], hinv, dballErp, dballCfm, RA[s], S21, b6);
     } else { SingleSys GA; GA.R = RA[0]; single_rows_axle(P, C, b[PD_BODY_AXLE], hinv, dballErp, dballCfm, GA, cfm); single_factor(GA, cfm, dyn[PD_BODY_AXLE], dyn[PD_BODY_CHASSIS], hinv, S21, b6); }
     schur_add_chassis(S21, C);
     float z[6];

@@ -10,6 +10,9 @@
 
 namespace pd {
 
+/* SuspensionBase::baseCFM of the corners that follow Car::step's ERP / CFM switch (Car.cpp:426-451): 1e-7 in every suspension class that sets it;
+ * a multilink corner ignores the switch (its setERPCFM is empty), so it is not asked */
+template <int TOPO> PD_HD float susp_base_cfm(const PdCarParams& P) { return PD_TOPO_FRONT_DW(TOPO) ? P.dw[0].baseCFM : P.strut[0].baseCFM; }
 /* topo: the car's suspension topology (PD_TOPO_*; a compile-time constant inside the tick kernels) */
 PD_HD void set_body_mass(Body* b, const PdCarParams& P, int topo) {
     b[PD_BODY_CHASSIS].mass = P.chassisMass; b[PD_BODY_CHASSIS].I = v3(P.chassisInertia[0], P.chassisInertia[1], P.chassisInertia[2]);
@@ -311,7 +314,7 @@ template <int STRIDE, int STRIDE_D, int TOPO = 0, class SVX> PD_HDN void car_tic
     { /* Car.cpp:426-451 (car id 0): DBall ERP by speed; CFM = baseCFM = 1e-7 in both branches */
         const float fVelSq = sqlen(C.v);
         X.dballErp = (fVelSq >= 1.0f) ? 0.3f : 0.9f;
-        X.dballCfm = (fVelSq >= 1.0f) ? (FDW ? P.dw[0].baseCFM : P.strut[0].baseCFM) : 0.0000001f;
+        X.dballCfm = (fVelSq >= 1.0f) ? susp_base_cfm<TOPO>(P) : 0.0000001f;
     }
     c.ctlSteer = tclampf(c.ctlSteer, -1.0f, 1.0f); c.ctlClutch = tclampf(c.ctlClutch, 0.0f, 1.0f); c.ctlBrake = tclampf(c.ctlBrake, 0.0f, 1.0f);
     c.ctlHandBrake = tclampf(c.ctlHandBrake, 0.0f, 1.0f); c.ctlGas = tclampf(c.ctlGas, 0.0f, 1.0f);
@@ -375,6 +378,9 @@ template <int STRIDE, int STRIDE_D, int TOPO = 0, class SVX> PD_HDN void car_tic
         else if constexpr (RDW) { Body& H = bod[PD_BODY_HUB2 + (w - 2)]; const Frame hf = dw_hub_frame(P.dw[w], H); tyre_step(P, T, w, X, sv, H, hf, C, brakeT[w], handT[w], X.wl[w]); }
         else { Body& A = bod[PD_BODY_AXLE]; const Frame hf = axle_hub_frame(P.axle, A, w - 2); tyre_step(P, T, w, X, sv, A, hf, C, brakeT[w], handT[w], X.wl[w]); }
     }
+    /* heave springs (Car.cpp:655-659: after the tyres, only when their rate is non-zero) */
+    if constexpr (FDW) { if (P.heave[0].present && P.heave[0].k != 0.0f) heave_step(P.heave[0], P.dw[0], P.dw[1], C, bod[PD_BODY_HUB0], bod[PD_BODY_HUB0].fr.p, bod[PD_BODY_HUB0].v, bod[PD_BODY_HUB1], bod[PD_BODY_HUB1].fr.p, bod[PD_BODY_HUB1].v, -1); }
+    if constexpr (RDW) { if (P.heave[1].present && P.heave[1].k != 0.0f) heave_step(P.heave[1], P.dw[2], P.dw[3], C, bod[PD_BODY_HUB2], bod[PD_BODY_HUB2].fr.p, bod[PD_BODY_HUB2].v, bod[PD_BODY_HUB3], bod[PD_BODY_HUB3].fr.p, bod[PD_BODY_HUB3].v, -1); }
     aero_step(P, C);
     { /* SteeringSystem::step -> setSteerLengthOffset -> reseatDistanceJointLocal (incl. its local->world->local round trip) */
         const float steer = -c.finalSteerAngleSignal * P.steerLinearRatio;

@@ -322,3 +322,41 @@ def make_brake_temps_base(tmp_dir, base, car="ks_toyota_ae86_drift", new_name="a
                     "[TEMPS_FRONT]\nPERF_CURVE=(|0=0.85|150=0.95|300=1.0|600=1.0|800=0.7|)\nTORQUE_K=0.12\nCOOL_TRANSFER=0.006\nCOOL_SPEED_FACTOR=0.0015\n\n"
                     "[TEMPS_REAR]\nPERF_CURVE=(|0=0.8|200=1.0|500=1.0|700=0.75|)\nTORQUE_K=0.09\nCOOL_TRANSFER=0.004\nCOOL_SPEED_FACTOR=0.001\n")
     return root, new_name
+
+
+def make_variant_car_base(tmp_dir, base, kind, car="ks_mazda_rx7_tuned"):
+    """A content tree (symlinks into `base`) with one car derived from the double-wishbone `car` for the suspension parts no bundled
+    car ships data for.  kind "ml": the REAR axle becomes TYPE=ML (SuspensionML: JOINTn_CAR / JOINTn_TYRE taken from the wishbone
+    points, so the geometry stays a sane one); kind "heave": [HEAVE_FRONT] / [HEAVE_REAR] third springs are added.  Returns (base, car)."""
+    import os, re, shutil
+    root = os.path.join(str(tmp_dir), "base_" + kind)
+    os.makedirs(os.path.join(root, "content", "cars"), exist_ok=True)
+    if not os.path.exists(os.path.join(root, "cfg")):
+        os.symlink(os.path.join(base, "cfg"), os.path.join(root, "cfg"))
+    if not os.path.exists(os.path.join(root, "content", "tracks")):
+        os.symlink(os.path.join(base, "content", "tracks"), os.path.join(root, "content", "tracks"))
+    new_name = "rx7_" + kind
+    dst = os.path.join(root, "content", "cars", new_name)
+    if os.path.isdir(dst):
+        return root, new_name
+    shutil.copytree(os.path.join(base, "content", "cars", car), dst)
+    path = os.path.join(dst, "data", "suspensions.ini")
+    text = open(path, newline="").read()
+    nl = "\r\n" if "\r\n" in text else "\n"
+    if kind == "heave":
+        text += nl + nl.join(["[HEAVE_FRONT]", "BUMPSTOP_UP=0.05", "BUMPSTOP_DN=0.04", "ROD_LENGTH=0.0", "SPRING_RATE=30000", "PROGRESSIVE_SPRING_RATE=2000", "DAMP_BUMP=1500", "DAMP_REBOUND=2500",
+                              "DAMP_FAST_BUMP=900", "DAMP_FAST_REBOUND=1400", "DAMP_FAST_BUMPTHRESHOLD=0.1", "DAMP_FAST_REBOUNDTHRESHOLD=0.1", "BUMP_STOP_RATE=0", "PACKER_RANGE=0.06", "",
+                              "[HEAVE_REAR]", "BUMPSTOP_UP=0.06", "BUMPSTOP_DN=0.03", "ROD_LENGTH=0.0", "SPRING_RATE=25000", "PROGRESSIVE_SPRING_RATE=0", "DAMP_BUMP=1200", "DAMP_REBOUND=2000",
+                              "DAMP_FAST_BUMP=0", "DAMP_FAST_REBOUND=0", "DAMP_FAST_BUMPTHRESHOLD=0", "DAMP_FAST_REBOUNDTHRESHOLD=0", "BUMP_STOP_RATE=120000", "PACKER_RANGE=0.08", ""]) + nl
+    elif kind == "ml":
+        m = re.search(r"\[REAR\](.*?)(?=\r?\n\[|\Z)", text, re.S)
+        sec = m.group(1)
+        get = lambda k: re.search(r"^%s=(.*?)\s*$" % k, sec, re.M).group(1)
+        joints = [("WBCAR_TOP_REAR", "WBTYRE_TOP"), ("WBCAR_TOP_FRONT", "WBTYRE_TOP"), ("WBCAR_BOTTOM_REAR", "WBTYRE_BOTTOM"), ("WBCAR_BOTTOM_FRONT", "WBTYRE_BOTTOM"), ("WBCAR_STEER", "WBTYRE_STEER")]
+        extra = nl.join("JOINT%d_CAR=%s%sJOINT%d_TYRE=%s" % (i, get(a), nl, i, get(b)) for i, (a, b) in enumerate(joints))
+        sec2 = re.sub(r"^TYPE=DWB", "TYPE=ML", sec, flags=re.M).rstrip() + nl + extra + nl
+        text = text[:m.start(1)] + sec2 + text[m.end(1):]
+    else:
+        raise ValueError(kind)
+    open(path, "w", newline="").write(text)
+    return root, new_name

@@ -856,3 +856,34 @@ def test_brake_disc_temperatures_and_ebb(oracle, lay, kernel, monkeypatch, tmp_p
                 assert not left, (t, i, left[:5])
             hot = max(hot, lay.get(out[:, i], "car.brakeDiscT0"))
     assert hot > 20.01
+
+
+@pytest.mark.parametrize("kind,kernel", [("ml", "k_tick_quad<4>"), ("ml", "k_tick"), ("heave", "k_tick_quad<8>"), ("heave", "k_tick")])
+def test_multilink_and_heave_spring_variants(oracle, lay, kind, kernel, monkeypatch, tmp_path, hostsim):
+    """SuspensionML (SuspensionML.cpp:15-137) and HeaveSpring (HeaveSpring.cpp:11-149) on the GPU, on cars derived from ks_mazda_rx7_tuned (no bundled
+    car ships such data; parity_util.make_variant_car_base): parameter block = reference init, single-tick rule on a 4-lanes-per-car instance and on
+    the thread-per-car instance."""
+    from projectd_core_b200 import Batch
+    from parity_util import make_variant_car_base, params_equal
+    _select_kernel(monkeypatch, kernel)
+    base, car = make_variant_car_base(tmp_path, oracle.BASE_PATH, kind)
+    n = 32
+    b = make_env_like(Batch(base, n_envs=n, device=0, car=car))
+    assert b.tick_kernel_instance() == ("k_tick<dwb,dwb>" if kernel == "k_tick" else kernel[:-1] + ",dwb,dwb>")
+    refs = [oracle.RefSim(car=car, base=base) for _ in range(n)]
+    assert params_equal(b.params_bytes(), refs[0].params_bytes(), hostsim)
+    for i, r in enumerate(refs):
+        r.teleport_spline(i / n)
+    for t in range(260):
+        for i, r in enumerate(refs):
+            r.set_controls(**drive_controls(t, i + 16 * (i % 3), lay, r.state()))
+        before = [r.state() for r in refs]; tb = refs[0].time()
+        b.restore(np.stack(before, axis=1)); b.set_time(tb); b.step(DT, 1)
+        out = b.snapshot()
+        for i, r in enumerate(refs):
+            r.set_state(before[i]); r.step()
+            ref = r.state()
+            bad, w = compare_records(lay, out[:, i], ref, tol=1e-4)
+            if bad:
+                left = arbitrate(oracle, lay, "driftplayground", before[i], tb, ref, bad, car=car, base=base)
+                assert not left, (t, i, left[:5])

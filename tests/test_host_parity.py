@@ -242,3 +242,38 @@ def test_brake_disc_temperatures_and_ebb(hostsim, oracle, content_base, tmp_path
         hot = max(hot, lay.get(first, "car.brakeDiscT0"))
     assert hot > 20.01, "the discs never warmed up"      # 2 s of simulated time: a few hundredths of a kelvin above the 20 C ambient
     hostsim.hs_destroy(h)
+
+
+@pytest.mark.parametrize("kind", ["ml", "heave"])
+def test_multilink_and_heave_spring_variants(hostsim, oracle, content_base, tmp_path, kind):
+    """SuspensionML (SuspensionML.cpp:15-137: a hub on five distance joints with the world's ERP / CFM, spring force of either sign) and
+    HeaveSpring (HeaveSpring.cpp:11-149: third spring on the mean travel of an axle's two hubs), on cars derived from ks_mazda_rx7_tuned
+    (no bundled car ships such data): loader block = reference init, then tick by tick against the oracle in the thread-per-car form and
+    (every 4th tick) the 4-lanes-per-car form."""
+    from parity_util import compare_records, make_variant_car_base, params_equal
+    base, car = make_variant_car_base(tmp_path, content_base, kind)
+    r = oracle.RefSim(car=car, base=base); r.set_collision_response(False)
+    h = hostsim.hs_create(base.encode(), b"driftplayground", car.encode())
+    assert h, "loader rejected the %s variant" % kind
+    hostsim.hs_set_assists(h, 1, 1, 1)
+    for k, v in oracle.ENV_TUNES.items():
+        hostsim.hs_set_tune(h, k.encode(), v)
+    for k, v in oracle.ENV_SCORING.items():
+        hostsim.hs_set_scoring_var(h, k.encode(), v)
+    mine = np.zeros(hostsim.hs_params_bytes(), np.uint8); hostsim.hs_get_params(h, mine.ctypes.data)
+    ref = r.params_bytes()
+    assert params_equal(mine, ref, hostsim), np.nonzero(mine != ref)[0][:12]
+    lay = oracle.Layout()
+    r.teleport_spline(0.3)
+    for t in range(320):
+        r.set_controls(steer=0.4 * math.sin(0.01 * t), gas=min(1.0, 0.2 + t / 150.0) if t < 240 else 0.0, brake=0.0 if t < 240 else 0.6)
+        before = r.state().copy(); tb = r.time()
+        outs = []
+        for fn in ((hostsim.hs_tick, hostsim.hs_tick_quad) if t % 4 == 0 else (hostsim.hs_tick,)):
+            rec = before.copy(); fn(h, rec.ctypes.data, DT, tb); outs.append(rec)
+        r.step()
+        for rec in outs:
+            bad, worst = compare_records(lay, rec, r.state(), tol=1e-4)
+            bad = [x for x in bad if not (x[0].endswith(".wz") and x[3] < 5e-4)]
+            assert not bad, (t, bad[:6])
+    hostsim.hs_destroy(h)
