@@ -151,6 +151,8 @@ typedef struct PdEngine { /* Car/Engine.h:9-115 */
     float overlapFreq, overlapGain, overlapIdealRPM;
     int32_t isEngineStallEnabled;
     float maxPowerRPM, maxTorqueRPM;
+    /* engine.ini [THROTTLE_RESPONSE]: a second throttle map blended in with rpm / RPM_REFERENCE (Engine::getThrottleResponseGas, Engine.cpp:344-366) */
+    PdCurve throttleResponseCurveMax; float throttleResponseCurveMaxRef; int32_t pad0;
 } PdEngine;
 
 typedef struct PdDrivetrain { /* Car/Drivetrain.h:75-96 */

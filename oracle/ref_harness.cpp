@@ -469,7 +469,8 @@ void pdref_get_params(void* hv, PdCarParams* P) {
             u.lagDN = t.data.lagDN; u.lagUP = t.data.lagUP; u.maxBoost = t.data.maxBoost; u.wastegate = t.data.wastegate; u.rpmRef = t.data.rpmRef; u.gamma = t.data.gamma;
             u.userSetting = t.userSetting; u.isAdjustable = t.data.isAdjustable ? 1 : 0;
         }
-        if (!e->turboControllers.empty() || e->throttleResponseCurveMax.getCount()) fprintf(stderr, "[oracle] turbo controllers / throttle max curve present: not exported\n");
+        copy_curve(d.throttleResponseCurveMax, e->throttleResponseCurveMax); d.throttleResponseCurveMaxRef = e->throttleResponseCurveMax.getCount() ? e->throttleResponseCurveMaxRef : 0.0f;
+        if (!e->turboControllers.empty()) fprintf(stderr, "[oracle] turbo controllers present: not exported\n");
     }
     {
         Drivetrain* t = c->drivetrain.get(); PdDrivetrain& d = P->drivetrain;

@@ -435,7 +435,7 @@ static void load_engine(const std::string& dataPath, PdEngine& E, PdCarParams& P
         if (P.nTurbos > 0) { E.turboBoostDamageThreshold = ini.getFloat("DAMAGE", "TURBO_BOOST_THRESHOLD"); E.turboBoostDamageK = ini.getFloat("DAMAGE", "TURBO_DAMAGE_K"); }
     }
     if (ini.hasSection("BOV")) E.bovThreshold = ini.getFloat("BOV", "PRESSURE_THRESHOLD");
-    if (ini.hasSection("THROTTLE_RESPONSE")) throw Error("THROTTLE_RESPONSE max curve is not supported yet");
+    if (ini.hasSection("THROTTLE_RESPONSE")) { E.throttleResponseCurveMaxRef = ini.getFloat("THROTTLE_RESPONSE", "RPM_REFERENCE"); E.throttleResponseCurveMax = ini.getCurve("THROTTLE_RESPONSE", "LUT"); }
     /* precalculatePowerAndTorque */
     const float fMaxRef = E.powerCurve.n ? E.powerCurve.ref[E.powerCurve.n - 1] : 0.0f;
     float maxTorqueNM = 0, maxPowerW = 0;
@@ -569,7 +569,9 @@ void load_car(const std::string& basePathIn, const std::string& model, CarModel&
     Ini car(dataPath + "car.ini");
     if (!car.ready) throw Error("cannot read " + dataPath + "car.ini");
     P.mass = car.getFloat("BASIC", "TOTALMASS");
-    if (car.hasSection("EXPLICIT_INERTIA")) throw Error("EXPLICIT_INERTIA cars are not supported yet");
+    /* the reference writes the three explicit moments into slots [0], [4], [8] of ODE's 3 x 4 inertia matrix (RigidBodyODE.cpp:80-89, its own "TODO: why not
+       [0] [5] [10]?"): the tensor it hands to dBodySetMass is singular, such a car cannot be simulated by the reference itself */
+    if (car.hasSection("EXPLICIT_INERTIA")) throw Error("EXPLICIT_INERTIA cars are not supported (the reference builds a singular inertia tensor for them, RigidBodyODE.cpp:80-89)");
     float bodyInertia[3]; car.getFloat3("BASIC", "INERTIA", bodyInertia);
     P.fuelKG = 0.74f; if (car.hasSection("FUEL_EXT")) P.fuelKG = car.getFloat("FUEL_EXT", "KG_PER_LITER");
     P.steerLock = car.getFloat("CONTROLS", "STEER_LOCK"); P.steerRatio = car.getFloat("CONTROLS", "STEER_RATIO");

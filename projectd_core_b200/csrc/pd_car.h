@@ -882,7 +882,12 @@ PD_HD void gearchanger_step(const PdCarParams& PP, CarCtx& X) {
 PD_HD void engine_step(const PdCarParams& PP, CarCtx& X, float gasInput, float rpm) {
     CarS& c = X.c; const PdEngine& E = PP.engine;
     float gas;
-    if (E.throttleResponseCurve.n) gas = tclampf(curve_value(E.throttleResponseCurve, gasInput * 100.0f) * 0.01f, 0.0f, 1.0f); else gas = gasInput;
+    if (E.throttleResponseCurve.n && E.throttleResponseCurveMax.n) {       /* Engine::getThrottleResponseGas (Engine.cpp:344-366) */
+        const float fTrc = tclampf(curve_value(E.throttleResponseCurve, gasInput * 100.0f) * 0.01f, 0.0f, 1.0f);
+        const float fTrcMax = tclampf(curve_value(E.throttleResponseCurveMax, gasInput * 100.0f) * 0.01f, 0.0f, 1.0f);
+        const float fTrcScale = tclampf(rpm / E.throttleResponseCurveMaxRef, 0.0f, 1.0f);
+        gas = ((fTrcMax - fTrc) * fTrcScale) + fTrc;
+    } else if (E.throttleResponseCurve.n) gas = tclampf(curve_value(E.throttleResponseCurve, gasInput * 100.0f) * 0.01f, 0.0f, 1.0f); else gas = gasInput;
     if (E.gasCoastOffset > 0.0f) {
         float g1 = tclampf((rpm - (float)E.minimum) / (float)E.coastEntryRpm, 0.0f, 1.0f);
         gas = tclampf(((1.0f - (E.gasCoastOffset * g1)) * gas) + (E.gasCoastOffset * g1), 0.0f, 1.0f);

@@ -327,7 +327,8 @@ def make_brake_temps_base(tmp_dir, base, car="ks_toyota_ae86_drift", new_name="a
 def make_variant_car_base(tmp_dir, base, kind, car="ks_mazda_rx7_tuned"):
     """A content tree (symlinks into `base`) with one car derived from the double-wishbone `car` for the suspension parts no bundled
     car ships data for.  kind "ml": the REAR axle becomes TYPE=ML (SuspensionML: JOINTn_CAR / JOINTn_TYRE taken from the wishbone
-    points, so the geometry stays a sane one); kind "heave": [HEAVE_FRONT] / [HEAVE_REAR] third springs are added.  Returns (base, car)."""
+    points, so the geometry stays a sane one); kind "heave": [HEAVE_FRONT] / [HEAVE_REAR] third springs are added; kind "throttle": engine.ini gets a
+    [THROTTLE_RESPONSE] section (second throttle map blended in with rpm).  Returns (base, car)."""
     import os, re, shutil
     root = os.path.join(str(tmp_dir), "base_" + kind)
     os.makedirs(os.path.join(root, "content", "cars"), exist_ok=True)
@@ -356,6 +357,11 @@ def make_variant_car_base(tmp_dir, base, kind, car="ks_mazda_rx7_tuned"):
         extra = nl.join("JOINT%d_CAR=%s%sJOINT%d_TYRE=%s" % (i, get(a), nl, i, get(b)) for i, (a, b) in enumerate(joints))
         sec2 = re.sub(r"^TYPE=DWB", "TYPE=ML", sec, flags=re.M).rstrip() + nl + extra + nl
         text = text[:m.start(1)] + sec2 + text[m.end(1):]
+    elif kind == "throttle":
+        epath = os.path.join(dst, "data", "engine.ini")
+        etext = open(epath, newline="").read()
+        enl = "\r\n" if "\r\n" in etext else "\n"
+        open(epath, "w", newline="").write(etext + enl + enl.join(["[THROTTLE_RESPONSE]", "RPM_REFERENCE=6000", "LUT=(|0=0|30=55|60=85|100=100|)", ""]) + enl)
     else:
         raise ValueError(kind)
     open(path, "w", newline="").write(text)

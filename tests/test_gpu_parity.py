@@ -858,7 +858,7 @@ def test_brake_disc_temperatures_and_ebb(oracle, lay, kernel, monkeypatch, tmp_p
     assert hot > 20.01
 
 
-@pytest.mark.parametrize("kind,kernel", [("ml", "k_tick_quad<4>"), ("ml", "k_tick"), ("heave", "k_tick_quad<8>"), ("heave", "k_tick")])
+@pytest.mark.parametrize("kind,kernel", [("ml", "k_tick_quad<4>"), ("ml", "k_tick"), ("heave", "k_tick_quad<8>"), ("heave", "k_tick"), ("throttle", "k_tick_quad<4>")])
 def test_multilink_and_heave_spring_variants(oracle, lay, kind, kernel, monkeypatch, tmp_path, hostsim):
     """SuspensionML (SuspensionML.cpp:15-137) and HeaveSpring (HeaveSpring.cpp:11-149) on the GPU, on cars derived from ks_mazda_rx7_tuned (no bundled
     car ships such data; parity_util.make_variant_car_base): parameter block = reference init, single-tick rule on a 4-lanes-per-car instance and on

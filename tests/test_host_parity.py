@@ -244,7 +244,7 @@ def test_brake_disc_temperatures_and_ebb(hostsim, oracle, content_base, tmp_path
     hostsim.hs_destroy(h)
 
 
-@pytest.mark.parametrize("kind", ["ml", "heave"])
+@pytest.mark.parametrize("kind", ["ml", "heave", "throttle"])
 def test_multilink_and_heave_spring_variants(hostsim, oracle, content_base, tmp_path, kind):
     """SuspensionML (SuspensionML.cpp:15-137: a hub on five distance joints with the world's ERP / CFM, spring force of either sign) and
     HeaveSpring (HeaveSpring.cpp:11-149: third spring on the mean travel of an axle's two hubs), on cars derived from ks_mazda_rx7_tuned

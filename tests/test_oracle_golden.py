@@ -17,7 +17,7 @@ def test_golden_file_shape(golden):
     lay_words = 664
     assert golden["traj_state"].shape == (41, lay_words)
     assert golden["pair_before"].shape == golden["pair_after"].shape and golden["pair_before"].shape[1] == lay_words
-    assert golden["params"].size == 20056
+    assert golden["params"].size == 20256
 
 
 def test_spline_cache_known_answers_oracle(oracle):
