@@ -8,6 +8,11 @@ want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_active.avg.per_cycle_active",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
+        # divergence / branch efficiency and LOCAL-memory traffic (the share of the DRAM bytes that is not state: spilled bodies / solver groups)
+        "smsp__branch_targets_threads_divergent", "smsp__sass_branch_targets.sum", "smsp__sass_branch_targets_threads_divergent.sum", "smsp__sass_branch_targets_threads_uniform.sum",
+        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "sass__inst_executed_global_loads", "sass__inst_executed_global_stores",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
         "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum", "smsp__sass_inst_executed_op_shared_ld.sum", "smsp__sass_inst_executed_op_shared_st.sum",
         "smsp__sass_inst_executed_op_global_ld.sum", "smsp__sass_inst_executed_op_global_st.sum", "derived__smsp__sass_thread_inst_executed_op_ffma_pred_on_x2", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"]
