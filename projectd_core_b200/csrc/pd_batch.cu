@@ -112,7 +112,12 @@ template <class SVX> __device__ __forceinline__ void env_epilogue(const SVX& sv,
  * 148 x 8 slots); a batch of at most 148 x 4 x 64 = 37888 envs fits one wave at 4 blocks per SM, where ptxas may take 255 registers and keeps more of the
  * tick out of local memory: measured +7.7 % at 24576 envs, +10.5 % at 32768 (and -45 % at 65536, where it means two waves). */
 template <int TOPO, int MB = PD_SERIAL_MINBLOCKS>       /* TOPO: suspension topology (PD_TOPO_*), one compile-time instance per (front, rear) pair of the bundled cars */
-__global__ void __launch_bounds__(PD_BLOCK, MB) k_tick(const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
+#if defined(PD_SERIAL_MAXNREG)
+__global__ void __maxnreg__(PD_SERIAL_MAXNREG) k_tick(      /* experiment: an explicit register cap instead of the launch bound.  144 registers (7 blocks of 64 threads per SM on paper) measured 62.4 vs 83.1 M car-ticks/s at 65536 envs: the allocation granularity leaves room for 6 blocks only, i.e. two waves */
+#else
+__global__ void __launch_bounds__(PD_BLOCK, MB) k_tick(
+#endif
+                                                   const __grid_constant__ PdCarParams P, const __grid_constant__ TrackDev T, uint32_t* state, int n, float dt, double time,
                                                    const int32_t* __restrict__ mask, const __grid_constant__ EnvIO io) {
     const long long clk0 = io.clk ? clock64() : 0;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
