@@ -196,6 +196,10 @@ const char* pd_tick_kernel_instance(const pd_batch* b);
 /* suspension topology of the loaded car: (front == DWB) * 2 + (rear == DWB)  (Car.cpp:74-117: SuspensionStrut / SuspensionDW /
  * SuspensionAxle chosen from suspensions.ini [FRONT] / [REAR] TYPE) */
 int pd_topology(const pd_batch* b);
+/* the ray caster's triangle tree (general rays: Track::computeFatPoints' traces, pd_raycast; the reference's rays go through ODE / OPCODE,
+ * Physics/ODE/RayCasterODE.cpp): built on the host at load (median splits) or ON THE DEVICE as a linear BVH -- automatically for tracks of
+ * 400 000 triangles and more, or with PD_DEVICE_BVH=1 in the environment.  *depth is reported for the device-built tree. */
+int pd_bvh_info(const pd_batch* b, int* built_on_device, int* n_nodes, int* depth);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,7 @@ def load_library():
         "pd_tick_kernel": (ctypes.c_char_p, [vp]),
         "pd_tick_kernel_instance": (ctypes.c_char_p, [vp]),
         "pd_topology": (ctypes.c_int, [vp]),
+        "pd_bvh_info": (i, [vp, vp, vp, vp]),
         "pd_env_stats": (i, [vp, vp, i]),
         "pd_set_autoreset": (i, [vp, i]),
         "pd_debug_read_clocks": (i, [vp, vp, i]),
@@ -304,6 +305,12 @@ class Batch:
 
     def tick_kernel_instance(self):
         return self.L.pd_tick_kernel_instance(self.h).decode()
+
+    def bvh_info(self):
+        """(built on the device?, number of nodes, depth of the device-built tree)"""
+        a, b_, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        self._ck(self.L.pd_bvh_info(self.h, ctypes.byref(a), ctypes.byref(b_), ctypes.byref(c)))
+        return bool(a.value), b_.value, c.value
 
     def topology(self):
         """(front == DWB) * 2 + (rear == DWB)"""

@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include "pd_quad.h"
+#include "pd_lbvh.h"
 #include "host/pd_host.h"
 #include "../../include/pd_batch.h"
 
@@ -627,6 +628,7 @@ struct pd_batch {
     int serialSmemPad = 0;            /* tuning knob (env PD_SERIAL_SMEM_PAD, bytes): unused dynamic shared memory per block of k_tick, caps the resident blocks per SM */
     int collideLpc = 4;               /* env PD_COLLIDE_LPC: lanes per car of k_collide2's floor test (1 / 4 / 8 / 16); measured at 65536 envs: 79.4 / 81.1 / 80.2 / 78.2 M car-ticks/s (warp per car, k_collide: 75.3 M) */
     bool debugSkipCollision = false;  /* env PD_DEBUG_SKIP_COLLISION=1: MEASUREMENT ONLY -- no collision test at all (wrong flags), to see what the detection costs a tick */
+    int bvhOnDevice = 0, bvhDepth = 0; /* the ray caster's tree was built by pd_lbvh.h (and its depth) */
     bool collideV1 = false;           /* env PD_COLLIDE_V1=1: k_collide (a warp per car) instead of k_collide2 (a thread per car for the floor, a warp for the walls) */
     bool inlineCollide = false;       /* thread-per-car kernel: test collisions inside the tick (env PD_SERIAL_INLINE_COLLIDE=1) instead of k_collide ahead of it */
     bool collWarp = true;             /* quad kernel: collision warp inside the tick kernel (env PD_COLL_WARP=0: k_collide ahead of it instead) */
@@ -692,6 +694,19 @@ static int fat_points_on_device(pdh::TrackModel& track, cudaStream_t stream, std
     float* dFat = (float*)up(nullptr, (size_t)n * 15 * 4);
     int rc = PD_OK;
     if (!T.nodes || !T.tris || !T.triSurf || !T.surfaces || !T.colStart || !T.colItems || !dSlim || !dFat) { err = "cudaMalloc failed (fat points)"; rc = PD_ERR_CUDA; }
+    if (rc == PD_OK) {      /* the traces through the device-built tree where pd_create would use it (same rule: PD_DEVICE_BVH, or >= 400 000 triangles) */
+        const char* q = getenv("PD_DEVICE_BVH");
+        const int nt = track.info.nTris;
+        if ((q ? atoi(q) != 0 : nt >= 400000) && nt >= 2) {
+            float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+            for (size_t i = 0; i < track.triRaw.size(); ++i) { const int k = (int)(i % 3); lo[k] = std::min(lo[k], track.triRaw[i]); hi[k] = std::max(hi[k], track.triRaw[i]); }
+            const float* dRaw = (const float*)up(track.triRaw.data(), track.triRaw.size() * 4);
+            BvhNode* nodes = nullptr; int count = 0, depth = 0;
+            const char* e = dRaw ? lbvh_build_on_device(dRaw, nt, lo, hi, stream, &nodes, &count, &depth) : "cudaMalloc failed";
+            if (!e) { tmp.push_back(nodes); T.nodes = nodes; T.info.nNodes = count; }
+            else if (q) { err = std::string("device BVH build failed: ") + e; rc = PD_ERR_CUDA; }
+        }
+    }
     if (rc == PD_OK) {
         FatCfg cfg{}; const pdh::TraceConfig& tc = track.trace;
         cfg.traceSides = tc.traceSides; cfg.offY = tc.rayOffsetY; cfg.rayLen = tc.rayLength; cfg.sideMax = tc.sideMax; cfg.diffH = tc.diffHeightMax; cfg.diffGrip = tc.diffGripMax; cfg.step = tc.step;
@@ -780,6 +795,21 @@ static int finish_create(pd_batch* b, int n_envs, int device) {
         if ((rc = upload(b, &b->dev.hullTables, ht))) return rc;
     }
     b->dev.info = b->track.info;
+    {   /* the ray caster's tree built ON THE DEVICE (pd_lbvh.h) for very large tracks (>= 400 000 triangles: BASELINE configs[3]) or on request
+           (PD_DEVICE_BVH=1; =0 keeps the host-built tree).  Closest-hit rays do not depend on which tree they walk. */
+        const char* q = getenv("PD_DEVICE_BVH");
+        const bool want = q ? atoi(q) != 0 : b->track.info.nTris >= 400000;
+        const int nt = b->track.info.nTris;
+        if (want && nt >= 2) {
+            float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+            for (size_t i = 0; i < b->track.triRaw.size(); ++i) { const int k = (int)(i % 3); lo[k] = std::min(lo[k], b->track.triRaw[i]); hi[k] = std::max(hi[k], b->track.triRaw[i]); }
+            pd::BvhNode* nodes = nullptr; int count = 0, depth = 0;
+            const char* e = pd::lbvh_build_on_device(b->dev.triRaw, nt, lo, hi, b->stream, &nodes, &count, &depth);
+            b->launches += 8;
+            if (!e) { b->allocs.push_back(nodes); b->dev.nodes = nodes; b->dev.info.nNodes = count; b->bvhOnDevice = 1; b->bvhDepth = depth; }
+            else if (q) { b->err = std::string("device BVH build failed: ") + e; return PD_ERR_CUDA; }      /* an explicit request does not fall back silently */
+        }
+    }
     const size_t n = (size_t)n_envs;
     const size_t nAlloc = state_alloc_words(b->layout, n);
     if ((rc = dalloc(b, &b->dState, nAlloc))) return rc;
@@ -1280,6 +1310,13 @@ int pd_sync(pd_batch* b) { if (!b) return PD_ERR_ARG; CK(cudaStreamSynchronize(b
 void* pd_stream(pd_batch* b) { return b ? (void*)b->stream : nullptr; }
 const char* pd_tick_kernel(const pd_batch* b) { return !b ? "" : (b->layout == PD_LAYOUT_RECORDS ? "k_tick_quad" : "k_tick"); }
 int pd_topology(const pd_batch* b) { return b ? b->car.P.topology : -1; }
+int pd_bvh_info(const pd_batch* b, int* built_on_device, int* n_nodes, int* depth) {
+    if (!b) return PD_ERR_ARG;
+    if (built_on_device) *built_on_device = b->bvhOnDevice;
+    if (n_nodes) *n_nodes = b->dev.info.nNodes;
+    if (depth) *depth = b->bvhDepth;
+    return PD_OK;
+}
 const char* pd_tick_kernel_instance(const pd_batch* b) {
     if (!b) return "";
     if (b->layout != PD_LAYOUT_RECORDS) return b->car.P.topology == PD_TOPO_STRUT_DW ? "k_tick<strut,dwb>" : (b->car.P.topology == PD_TOPO_DW_DW ? "k_tick<dwb,dwb>" : (b->serialWide ? "k_tick/255" : "k_tick"));

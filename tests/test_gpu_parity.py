@@ -887,3 +887,37 @@ def test_multilink_and_heave_spring_variants(oracle, lay, kind, kernel, monkeypa
             if bad:
                 left = arbitrate(oracle, lay, "driftplayground", before[i], tb, ref, bad, car=car, base=base)
                 assert not left, (t, i, left[:5])
+
+
+def test_device_bvh_rays_equal_host_bvh_rays(oracle, monkeypatch):
+    """SURVEY.md N2: the ray caster's tree built on the device (linear BVH: Morton keys, radix sort, Karras' internal nodes, bottom-up refit;
+    csrc/pd_lbvh.h).  Closest-hit rays must not depend on the tree they walk: 60 000 general rays (slanted, vertical, long, missing) give the
+    same hit flags, surfaces and distances on the device-built and on the host-built tree, and the reference-held spline.cache is regenerated
+    bit for bit through the device-built one (Track::computeFatPoints, the KAT of test_compute_fat_points_matches_shipped_spline_cache)."""
+    from projectd_core_b200 import Batch
+    rng = np.random.default_rng(17)
+    fat = np.fromfile(oracle.BASE_PATH + "/content/tracks/driftplayground/spline.cache", dtype=np.float32).reshape(-1, 15)
+    n = 60000
+    idx = rng.integers(0, len(fat), n)
+    rays = np.zeros((n, 7), np.float32)
+    rays[:, 0:3] = fat[idx, 0:3] + rng.uniform(-15, 15, (n, 3)).astype(np.float32) * np.array([1, 0.2, 1], np.float32) + np.array([0, 3.0, 0], np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d[:, 1] = -np.abs(d[:, 1]) - 0.2; d[: n // 4] = np.array([0, -1, 0], np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 3:6] = d; rays[:, 6] = rng.uniform(0.5, 60.0, n).astype(np.float32)
+    monkeypatch.setenv("PD_DEVICE_BVH", "0")
+    bh = make_env_like(Batch(oracle.BASE_PATH, n_envs=1, device=0))
+    assert bh.bvh_info()[0] is False
+    host = bh.raycast(rays)
+    monkeypatch.setenv("PD_DEVICE_BVH", "1")
+    bd = make_env_like(Batch(oracle.BASE_PATH, n_envs=1, device=0))
+    on_dev, nodes, depth = bd.bvh_info()
+    assert on_dev and nodes == 2 * bd.track_info()["nTris"] - 1 and 10 < depth <= 45, (on_dev, nodes, depth)
+    dev = bd.raycast(rays)
+    assert np.array_equal(dev[:, 0], host[:, 0]) and 0.2 < host[:, 0].mean() < 0.98, host[:, 0].mean()
+    hit = host[:, 0] == 1
+    assert np.array_equal(dev[hit, 7], host[hit, 7]), "surface ids differ"
+    assert np.array_equal(dev[hit, 1:7], host[hit, 1:7]), "hit positions / normals differ"
+    # the reference-held known answers through the device-built tree
+    from projectd_core_b200.binding import compute_fat_points
+    mine = compute_fat_points(oracle.BASE_PATH, "driftplayground", device=0)
+    assert np.array_equal(mine[:, 0:3], fat[:, 0:3])
