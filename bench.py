@@ -303,6 +303,12 @@ def ours(args):
         except Exception as ex:  # the baseline is a reported figure, not part of the measurement
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference", "sample": "failed: %s" % ex}
 
+    # ---- like-for-like anchor of the weak-scaling curve (N=1 default run only): the per-GPU load of configs[2], 65536 envs,
+    #      on this one GPU, same pre-roll / warm-up / event timing as above, in this process ----
+    anchor = None
+    if world == 1 and n_envs == 4096 and not args.no_anchor and not args.synthetic_tris:
+        anchor = _anchor_65536(args, dev, gen)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -323,6 +329,7 @@ def ours(args):
                          "peak_source": peak_kind, "algorithmic_bytes_per_car_tick": alg_bytes / n_envs, "kernel_ms": tick_ms,
                          "fp32_issue_frac_of_74TFLOPs_at_50kflop_per_car_tick": flop_frac},
             "cpu_baseline": cpu,
+            "extras": {"weak_scaling_anchor": anchor},
             "episode_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None, "mean_length": (stats[2] / stats[0]) if stats[0] else None,
                               "collisions": stats[3], "offtrack": stats[4], "stuck": stats[5], "lowreward": stats[6], "nan": stats[7]},
         }
@@ -336,6 +343,46 @@ def ours(args):
     torch.cuda.synchronize()
 
 
+def _anchor_65536(args, dev, gen, n_envs=65536):
+    """Device-resident car-ticks/s of ONE GPU at the per-GPU load the N>1 runs use (65536 envs): the like-for-like first
+    point of the weak-scaling curve, measured by the same rules as the headline (pre-roll, >= 3 warm-up steps, CUDA events
+    on the batch's stream; the state, 175 MB, is larger than L2)."""
+    import torch
+    from projectd_core_b200 import Batch
+    from projectd_core_b200.assets import default_base
+    from projectd_core_b200.env import configure_like_env
+    K, W = min(args.steps, 10), 3
+    b = configure_like_env(Batch(default_base(), n_envs=n_envs, device=dev.index, car=args.car))
+    b.set_seed(1234, 0); b.teleport_mode(2); b.set_autoreset(1)
+    stream = torch.cuda.ExternalStream(b.stream(), device=dev)
+    acts = (torch.rand((args.preroll // TICKS_PER_STEP + 1 + W + K, n_envs, 2), device=dev, generator=gen) * 2 - 1).contiguous()
+    rew = torch.zeros(n_envs, device=dev); done = torch.zeros(n_envs, device=dev, dtype=torch.int32)
+    torch.cuda.synchronize()
+    for t in range(args.preroll):
+        b.env_step(acts[t // TICKS_PER_STEP], DT, None, rew, done)
+    base = args.preroll // TICKS_PER_STEP + 1
+    for s in range(W):
+        for _ in range(TICKS_PER_STEP):
+            b.env_step(acts[base + s], DT, None, rew, done)
+    torch.cuda.synchronize()
+    l0 = b.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for s in range(W, W + K):
+            for _ in range(TICKS_PER_STEP):
+                b.env_step(acts[base + s], DT, None, rew, done)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"envs_per_gpu": n_envs, "value": n_envs * K * TICKS_PER_STEP / (ms * 1e-3), "unit": UNIT, "steps": K, "warmup": W,
+           "ms_per_step": ms / K, "gpu_launches": b.launch_count() - l0, "kernel": b.tick_kernel(),
+           "note": "one GPU at the per-GPU load of configs[2]; divide the N-GPU value by N times this for the like-for-like weak-scaling efficiency"}
+    del e0, e1, stream
+    b.sync(); b.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,6 +391,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: 4096 at N=1, 65536 at N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-anchor", action="store_true", help="skip the 65536-env single-GPU anchor the default N=1 run adds under extras")
     ap.add_argument("--car", default="ks_toyota_ae86_drift", help="car model (BASELINE's configs all use the demo car; the other four bundled cars run the double-wishbone kernel instances)")
     ap.add_argument("--synthetic-tris", type=int, default=0, help="BASELINE configs[3]: generated 20.8 km circuit of about this many triangles instead of driftplayground")
     ap.add_argument("--preroll", type=int, default=1998, help="untimed ticks before the warm-up (brings the rollout to its steady state)")
