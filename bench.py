@@ -67,7 +67,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(n)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set(); self.join(timeout=2)
@@ -229,7 +229,6 @@ def ours(args):
         run_steps(W, W + K)
         e1.record(stream)
     barrier()
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = b.launch_count() - l0
     ms = pdist.max_over_ranks(ms, dev)
@@ -285,6 +284,7 @@ def ours(args):
             e2e_tick(acts_host[s])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()                   # sampled across the three timed regions (device-resident steps, per-launch events, end to end)
     e2e_s = pdist.max_over_ranks(e2e_s, dev)
     e2e_value = world * n_envs * e2e_steps * TICKS_PER_STEP / e2e_s
 

@@ -921,3 +921,65 @@ def test_device_bvh_rays_equal_host_bvh_rays(oracle, monkeypatch):
     from projectd_core_b200.binding import compute_fat_points
     mine = compute_fat_points(oracle.BASE_PATH, "driftplayground", device=0)
     assert np.array_equal(mine[:, 0:3], fat[:, 0:3])
+
+
+def test_full_size_batch_65536_envs(oracle, lay, monkeypatch):
+    """BASELINE configs[2]'s per-GPU load (65536 envs, the bench configuration: random actions, next-step auto-reset, an env
+    terminates on a hit) through size-independent properties: (1) the rollout stays finite and the episode counters add up;
+    (2) sharding: the first and the last 4096 envs of the batch equal, bit for bit, 4096-env batches seeded at the same global
+    env ids (env-id keyed RNG, the same kernel instance); (3) sampled oracle parity at full size: after the rollout, one more
+    tick of 64 envs picked across the batch against the oracle started from those envs' records (single-tick rule)."""
+    import torch
+    from projectd_core_b200 import Batch
+    from projectd_core_b200.env import configure_like_env
+    N, S, T = 65536, 4096, 500
+    monkeypatch.setenv("PD_QUAD_MAX_ENVS", "0"); monkeypatch.setenv("PD_SERIAL_WIDE", "0")     # the shards run what the full batch runs
+
+    def make(n, off):
+        b = configure_like_env(Batch(oracle.BASE_PATH, n_envs=n, device=0))
+        b.set_seed(1234, off); b.teleport_mode(2); b.set_autoreset(1)
+        return b
+    full = make(N, 0); lo = make(S, 0); hi = make(S, N - S)
+    assert full.tick_kernel_instance() == "k_tick" and lo.tick_kernel_instance() == "k_tick"
+    gen = torch.Generator(device="cuda"); gen.manual_seed(7)
+    rew = torch.zeros(N, device="cuda"); done = torch.zeros(N, device="cuda", dtype=torch.int32)
+    rs = torch.zeros(S, device="cuda"); ds = torch.zeros(S, device="cuda", dtype=torch.int32)
+    ndone = torch.zeros((), device="cuda", dtype=torch.int64)
+    for t in range(T):
+        if t % 33 == 0:
+            act = (torch.rand((N, 2), device="cuda", generator=gen) * 2 - 1).contiguous()
+            a_lo = act[:S].contiguous(); a_hi = act[N - S:].contiguous()
+        full.env_step(act, DT, None, rew, done); lo.env_step(a_lo, DT, None, rs, ds); hi.env_step(a_hi, DT, None, rs, ds)
+        full.sync(); lo.sync(); hi.sync()
+        ndone += (done != 0).sum()
+    st = full.env_stats(reset=False)
+    assert st[7] == 0, "non-finite cars"                      # nan counter
+    assert int(st[0]) == int(ndone.item()) and st[0] == st[3] + st[4] + st[5] + st[6] + st[7], st
+    assert st[0] > N * 0.02, "the rollout never reached episode ends"
+    before = full.snapshot()
+    assert np.isfinite(before[lay.fields["chassis.px"][0]].view(np.float32)).all()
+    assert np.array_equal(before[:, :S], lo.snapshot()) and np.array_equal(before[:, N - S:], hi.snapshot())
+    # sampled oracle parity: restore (drops nothing but live contact joints, which the bench configuration never has), one plain tick
+    tb = full.time()
+    full.restore(before); full.set_time(tb); full.step(DT, 1)
+    after = full.snapshot()
+    rng = np.random.default_rng(3)
+    pick = sorted(set([0, 63, 64, N - 1] + rng.integers(0, N, 60).tolist()))
+    cf = lay.fields["car.collisionFlag"][0]
+    worst = 0.0; hits = 0; failures = []
+    r = oracle.RefSim()
+    for i in pick:
+        r.set_state(before[:, i]); r.set_time(tb); r.step()
+        ref = r.state()
+        assert int(after[cf, i]) == int(ref[cf]), ("collision flag", i)
+        if int(ref[cf]):            # the oracle answers a hit with contact joints, the env configuration with termination
+            hits += 1; continue
+        bad, w = compare_records(lay, after[:, i], ref, tol=1e-4)
+        if bad:
+            left = arbitrate(oracle, lay, "driftplayground", before[:, i], tb, ref, bad)
+            if left:
+                failures.append((i, left[:4]))
+        else:
+            worst = max(worst, w)
+    assert not failures, failures
+    assert hits < len(pick) // 2
