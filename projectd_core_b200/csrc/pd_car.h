@@ -352,9 +352,16 @@ PD_HD TmOut sctm_solve(const PdTyre& P, const TmIn& tmi) {
     return tmo;
 }
 
+/* where the 12 x 3 thermal grid of a tyre lives while the tick works on it: in the TyreS copy (or the in-place record), or --
+ * thread-per-car kernel on the tiled global state, sv_traits::grid_in_place -- in the state words themselves.  A warp's accesses
+ * to one patch word are one 128-byte line either way; the local copy cost a local store + load per patch on the way in and again
+ * on the way out (profiles/r02_local_memory_attribution.md: 16 % of the kernel's local-memory sectors). */
+struct GridLocal { float* T; PD_HD float get(int p) const { return T[p]; } PD_HD void set(int p, float v) const { T[p] = v; } };
+template <class SVX> struct GridSV { const SVX& sv; int base; PD_HD float get(int p) const { return sv.f(base + p); } PD_HD void set(int p, float v) const { sv.f(base + p, v); } };
+
 /* thermal grid neighbours in the reference's connection order (TyreThermalModel.cpp:28-58, buildTyre):
  * patch index p = element + stripe * 12 */
-PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, float in0, float in1, float in2, float coreTInput, float dt, float angularSpeed, float camberRAD, float ambient, float carSpeed) {
+template <class GRID> PD_HD void thermal_step(const PdTyre& P, TyreS& t, const GRID g, float inBase, int inElem, float in0, float in1, float in2, float coreTInput, float dt, float angularSpeed, float camberRAD, float ambient, float carSpeed) {
     /* TyreThermalModel::step (TyreThermalModel.cpp:60-110) */
     float fPhase = (float)t.phase + (angularSpeed * dt);
     if (fPhase > 100000.0) fPhase = (float)(fPhase - 100000.0); else if (fPhase < 0.0) fPhase = (float)(fPhase + 100000.0);
@@ -371,25 +378,25 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, flo
     PD_UNROLL
     for (int i = 0; i < PD_THERMAL_STRIPES; ++i) {
         const float inj = inBase + (i == 0 ? in0 : (i == 1 ? in1 : in2));
-        float* Ti = t.T + i * PD_THERMAL_ELEMENTS;
+        const int pi = i * PD_THERMAL_ELEMENTS;
         PD_NOUNROLL
         for (int j = 0; j < PD_THERMAL_ELEMENTS; ++j) {
             const float fInputT = (j == inElem) ? inj : inBase;
-            float fPatchT = Ti[j];
+            float fPatchT = g.get(pi + j);
             if (fInputT <= ambient) fPatchT += ((ambient - fPatchT) * fAmbientFactor);
             else fPatchT += ((fInputT - fPatchT) * kSurf);
-            if (i > 0) fPatchT += (Ti[j - PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
+            if (i > 0) fPatchT += (g.get(pi + j - PD_THERMAL_ELEMENTS) - fPatchT) * kPatch;
             if (j == 0) {
-                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (Ti[PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
-                fPatchT += (Ti[1] - fPatchT) * kPatch;
-                fPatchT += (Ti[PD_THERMAL_ELEMENTS - 1] - fPatchT) * kPatch;
+                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (g.get(pi + PD_THERMAL_ELEMENTS) - fPatchT) * kPatch;
+                fPatchT += (g.get(pi + 1) - fPatchT) * kPatch;
+                fPatchT += (g.get(pi + PD_THERMAL_ELEMENTS - 1) - fPatchT) * kPatch;
             } else {
-                fPatchT += (Ti[j - 1] - fPatchT) * kPatch;
-                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (Ti[j + PD_THERMAL_ELEMENTS] - fPatchT) * kPatch;
-                fPatchT += (Ti[(j + 1 < PD_THERMAL_ELEMENTS) ? j + 1 : 0] - fPatchT) * kPatch;
+                fPatchT += (g.get(pi + j - 1) - fPatchT) * kPatch;
+                if (i + 1 < PD_THERMAL_STRIPES) fPatchT += (g.get(pi + j + PD_THERMAL_ELEMENTS) - fPatchT) * kPatch;
+                fPatchT += (g.get(pi + ((j + 1 < PD_THERMAL_ELEMENTS) ? j + 1 : 0)) - fPatchT) * kPatch;
             }
             fPatchT += (coreTemp - fPatchT) * fPctDt;
-            Ti[j] = fPatchT;
+            g.set(pi + j, fPatchT);
             coreTemp += ((fPatchT - coreTemp) * fPctDt);
         }
     }
@@ -400,7 +407,7 @@ PD_HD void thermal_step(const PdTyre& P, TyreS& t, float inBase, int inElem, flo
         const float ph = (float)(t.phase * 0.1591549430964443);
         const int iElemY = ((int)(ph * PD_THERMAL_ELEMENTS)) % PD_THERMAL_ELEMENTS;
         float t0 = 0, t1 = 0, t2 = 0;
-        if (iElemY >= 0 && iElemY < PD_THERMAL_ELEMENTS) { t0 = t.T[iElemY]; t1 = t.T[iElemY + PD_THERMAL_ELEMENTS]; t2 = t.T[iElemY + 2 * PD_THERMAL_ELEMENTS]; }
+        if (iElemY >= 0 && iElemY < PD_THERMAL_ELEMENTS) { t0 = g.get(iElemY); t1 = g.get(iElemY + PD_THERMAL_ELEMENTS); t2 = g.get(iElemY + 2 * PD_THERMAL_ELEMENTS); }
         const float cp = ((((fNormCsk + 1.0f) * t0) + t1) + ((1.0f - fNormCsk) * t2)) * 0.33333334f;
         const float fPracT = ((cp - coreTemp) * 0.25f) + coreTemp;
         t.practicalTemp = fPracT;
@@ -562,7 +569,7 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
             if (PP.mechanicalDamageRate > 0.0f) { /* stepPuncture (TyreForces.cpp:235-247) */
                 bool expl = false;
                 PD_UNROLL
-                for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) s += t.T[j + i * 12]; if (s / 12.0f > P.explosionTemperature) expl = true; }
+                for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) { if constexpr (sv_traits<SVX>::grid_in_place) s += sv.f(PD_OFF_TYRE_PATCH(w) + j + i * 12); else s += t.T[j + i * 12]; } if (s / 12.0f > P.explosionTemperature) expl = true; }
                 if (expl) t.inflation = 0;
             }
             t.Mz = tmo.Mz;
@@ -663,7 +670,8 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
             }
             float coreTInput = 0.0f;
             if (P.version >= 5) coreTInput += (((fThermalRollingK * t.angularVelocity) * t.load) * 0.001f);
-            thermal_step(P, t, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
+            if constexpr (sv_traits<SVX>::grid_in_place) thermal_step(P, t, GridSV<SVX>{sv, PD_OFF_TYRE_PATCH(w)}, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
+            else thermal_step(P, t, GridLocal{t.T}, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
         }
     }
     t.pressureDynamic = ((t.coreTemp - 26.0f) * P.pressureTemperatureGain) + t.pressureStatic;

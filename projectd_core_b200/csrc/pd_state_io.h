@@ -117,8 +117,12 @@ PD_CAR_FIELDS(PD__CHK_C)
 static_assert(offsetof(TyreS, T) == 4 * PD_TYRE_SCALAR_WORDS && sizeof(TyreS) == 4 * PD_TYRE_WORDS, "TyreS size");
 static_assert(offsetof(CarS, probes) == 4 * PD_CAR_SCALAR_WORDS && offsetof(CarS, lookAhead) == 4 * (PD_CAR_SCALAR_WORDS + PD_MAX_PROBES), "CarS arrays");
 static_assert(PD_OFF_TYRE(0) % 2 == 0 && PD_TYRE_WORDS % 2 == 0 && PD_OFF_CAR % 2 == 0 && PD_STATE_STRIDE % 2 == 0, "8-byte alignment of the double fields");
-template <class SVX> struct sv_traits { static constexpr bool in_place = false; };
-template <> struct sv_traits<SVT<1> > { static constexpr bool in_place = true; };
+#ifndef PD_GRID_IN_PLACE
+#define PD_GRID_IN_PLACE 1      /* tiled view: the tyres' thermal grids are swept in the state buffer, not in a local copy (pd_car.h GridSV) */
+#endif
+template <class SVX> struct sv_traits { static constexpr bool in_place = false; static constexpr bool grid_in_place = false; };
+template <> struct sv_traits<SVT<1> > { static constexpr bool in_place = true; static constexpr bool grid_in_place = false; };
+template <> struct sv_traits<SVT<PD_TILE> > { static constexpr bool in_place = false; static constexpr bool grid_in_place = PD_GRID_IN_PLACE != 0; };
 PD_HD TyreS* tyre_in_place(const SVT<1>& sv, int w) { return reinterpret_cast<TyreS*>(sv.s + PD_OFF_TYRE(w)); }
 PD_HD CarS* car_in_place(const SVT<1>& sv) { return reinterpret_cast<CarS*>(sv.s + PD_OFF_CAR); }
 template <class SVX> PD_HD TyreS* tyre_in_place(const SVX&, int) { return nullptr; }
@@ -138,14 +142,18 @@ template <class SVX> PD_HD CarS* car_in_place(const SVX&) { return nullptr; }
 template <class SVX> PD_HD void load_tyre(const SVX& sv, int w, TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__LDT)
-    PD_UNROLL4
-    for (int p = 0; p < PD_THERMAL_PATCHES; ++p) t.T[p] = sv.f(PD_OFF_TYRE_PATCH(w) + p);
+    if constexpr (!sv_traits<SVX>::grid_in_place) {
+        PD_UNROLL4
+        for (int p = 0; p < PD_THERMAL_PATCHES; ++p) t.T[p] = sv.f(PD_OFF_TYRE_PATCH(w) + p);
+    }
 }
 template <class SVX> PD_HD void store_tyre(const SVX& sv, int w, const TyreS& t) {
     const int o = PD_OFF_TYRE(w);
     PD_TYRE_FIELDS(PD__STT)
-    PD_UNROLL4
-    for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, t.T[p]);
+    if constexpr (!sv_traits<SVX>::grid_in_place) {
+        PD_UNROLL4
+        for (int p = 0; p < PD_THERMAL_PATCHES; ++p) sv.f(PD_OFF_TYRE_PATCH(w) + p, t.T[p]);
+    }
 }
 template <class SVX> PD_HD void load_car(const SVX& sv, CarS& t) {
     const int o = PD_OFF_CAR;
