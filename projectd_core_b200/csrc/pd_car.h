@@ -358,11 +358,25 @@ PD_HD TmOut sctm_solve(const PdTyre& P, const TmIn& tmi) {
  * on the way out (profiles/r02_local_memory_attribution.md: 16 % of the kernel's local-memory sectors). */
 struct GridLocal { float* T; PD_HD float get(int p) const { return T[p]; } PD_HD void set(int p, float v) const { T[p] = v; } };
 template <class SVX> struct GridSV { const SVX& sv; int base; PD_HD float get(int p) const { return sv.f(base + p); } PD_HD void set(int p, float v) const { sv.f(base + p, v); } };
+/* the grid words of a batch larger than L2 come from HBM; the sweep is a rolled loop with a loop-carried dependency, so its first touch of every line would be
+ * exposed latency: ask for the 36 lines (one 128-byte line per word and warp) when the tyre's step begins, a ray cast and the force model ahead of the sweep */
+#ifndef PD_GRID_PREFETCH
+#define PD_GRID_PREFETCH 1
+#endif
+template <class SVX> PD_HD void grid_prefetch(const SVX& sv, int base) {
+#if defined(__CUDA_ARCH__) && PD_GRID_PREFETCH
+    PD_UNROLL
+    for (int p = 0; p < PD_THERMAL_PATCHES; ++p) asm volatile("prefetch.global.L1 [%0];" ::"l"(sv.s + (base + p) * SVX::stride));
+#else
+    (void)sv; (void)base;
+#endif
+}
 
 /* thermal grid neighbours in the reference's connection order (TyreThermalModel.cpp:28-58, buildTyre):
  * patch index p = element + stripe * 12 */
-template <class GRID> PD_HD void thermal_step(const PdTyre& P, TyreS& t, const GRID g, float inBase, int inElem, float in0, float in1, float in2, float coreTInput, float dt, float angularSpeed, float camberRAD, float ambient, float carSpeed) {
-    /* TyreThermalModel::step (TyreThermalModel.cpp:60-110) */
+template <class GRID> PD_HD void thermal_step(const PdTyre& P, TyreS& t, const GRID g, float inBase, int inElem, float in0, float in1, float in2, float coreTInput, float dt, float angularSpeed, float camberRAD, float ambient, float carSpeed, float* preSum = nullptr) {
+    /* TyreThermalModel::step (TyreThermalModel.cpp:60-110).  preSum (optional, 3 floats): per stripe, the sum of the patch temperatures BEFORE this step
+     * in element order -- what stepPuncture averages -- so that a grid that lives in the global state is read once per tick, not twice */
     float fPhase = (float)t.phase + (angularSpeed * dt);
     if (fPhase > 100000.0) fPhase = (float)(fPhase - 100000.0); else if (fPhase < 0.0) fPhase = (float)(fPhase + 100000.0);
     t.phase = fPhase;
@@ -379,10 +393,12 @@ template <class GRID> PD_HD void thermal_step(const PdTyre& P, TyreS& t, const G
     for (int i = 0; i < PD_THERMAL_STRIPES; ++i) {
         const float inj = inBase + (i == 0 ? in0 : (i == 1 ? in1 : in2));
         const int pi = i * PD_THERMAL_ELEMENTS;
+        float sPre = 0;
         PD_NOUNROLL
         for (int j = 0; j < PD_THERMAL_ELEMENTS; ++j) {
             const float fInputT = (j == inElem) ? inj : inBase;
             float fPatchT = g.get(pi + j);
+            sPre += fPatchT;
             if (fInputT <= ambient) fPatchT += ((ambient - fPatchT) * fAmbientFactor);
             else fPatchT += ((fInputT - fPatchT) * kSurf);
             if (i > 0) fPatchT += (g.get(pi + j - PD_THERMAL_ELEMENTS) - fPatchT) * kPatch;
@@ -399,6 +415,7 @@ template <class GRID> PD_HD void thermal_step(const PdTyre& P, TyreS& t, const G
             g.set(pi + j, fPatchT);
             coreTemp += ((fPatchT - coreTemp) * fPctDt);
         }
+        if (preSum) preSum[i] = sPre;
     }
     t.coreTemp = coreTemp;
     if (P.performanceCurve.n > 0) {
@@ -425,6 +442,7 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
     TyreS tLocal; TyreS* tp = &tLocal;
     if constexpr (sv_traits<SVX>::in_place) tp = tyre_in_place(sv, w); else load_tyre(sv, w, tLocal);
     TyreS& t = *tp;
+    if constexpr (sv_traits<SVX>::grid_in_place) grid_prefetch(sv, PD_OFF_TYRE_PATCH(w));
     t.brakeTorque = brakeTorqueIn; t.handBrakeTorque = handBrakeIn;
     t.feedbackTorque = 0; t.Fx = 0; t.Mz = 0; t.slipFactor = 0; t.rollingResistence = 0;
     t.slidingVelocityY = 0; t.slidingVelocityX = 0; t.totalHubVelocity = 0;
@@ -436,6 +454,7 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
     const RayHit hit = ray_cast_down(T, v3(worldPosition.x, worldPosition.y + 2.0f, worldPosition.z), 3.0f);
     PD_PHASE(X, 3);
     float gripMod = 0, dirtAdditiveK = 0;
+    bool punctureCheck = false;
     bool contact = hit.hit && !(hubFrame.ay.y <= 0.35f);
     if (!contact) {
         t.ndSlip = 0; t.Fy = 0;
@@ -567,10 +586,13 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
                 t.Fy *= fM; t.Fx *= fM; t.Mz *= fM;
             }
             if (PP.mechanicalDamageRate > 0.0f) { /* stepPuncture (TyreForces.cpp:235-247) */
-                bool expl = false;
-                PD_UNROLL
-                for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) { if constexpr (sv_traits<SVX>::grid_in_place) s += sv.f(PD_OFF_TYRE_PATCH(w) + j + i * 12); else s += t.T[j + i * 12]; } if (s / 12.0f > P.explosionTemperature) expl = true; }
-                if (expl) t.inflation = 0;
+                if constexpr (sv_traits<SVX>::grid_in_place) punctureCheck = true;       /* deferred to the thermal sweep below, which reads the same 36 words (inflation is not read again this tick) */
+                else {
+                    bool expl = false;
+                    PD_UNROLL
+                    for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) s += t.T[j + i * 12]; if (s / 12.0f > P.explosionTemperature) expl = true; }
+                    if (expl) t.inflation = 0;
+                }
             }
             t.Mz = tmo.Mz;
             V3 vForce = (roadHeading * t.Fx) + (roadRight * t.Fy);
@@ -670,8 +692,19 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
             }
             float coreTInput = 0.0f;
             if (P.version >= 5) coreTInput += (((fThermalRollingK * t.angularVelocity) * t.load) * 0.001f);
-            if constexpr (sv_traits<SVX>::grid_in_place) thermal_step(P, t, GridSV<SVX>{sv, PD_OFF_TYRE_PATCH(w)}, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
-            else thermal_step(P, t, GridLocal{t.T}, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
+            if constexpr (sv_traits<SVX>::grid_in_place) {
+                float ss[3];
+                thermal_step(P, t, GridSV<SVX>{sv, PD_OFF_TYRE_PATCH(w)}, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed, ss);
+                if (punctureCheck) { punctureCheck = false; if (ss[0] / 12.0f > P.explosionTemperature || ss[1] / 12.0f > P.explosionTemperature || ss[2] / 12.0f > P.explosionTemperature) t.inflation = 0; }
+            } else thermal_step(P, t, GridLocal{t.T}, inBase, inElem, in0, in1, in2, coreTInput, dt, t.angularVelocity, t.camberRAD, PP.ambientTemperature, X.c.speed);
+        }
+        if constexpr (sv_traits<SVX>::grid_in_place) {
+            if (punctureCheck) {        /* no thermal sweep this tick (non-finite thermal input): stepPuncture (TyreForces.cpp:235-247) on its own */
+                bool expl = false;
+                PD_UNROLL
+                for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) s += sv.f(PD_OFF_TYRE_PATCH(w) + j + i * 12); if (s / 12.0f > P.explosionTemperature) expl = true; }
+                if (expl) t.inflation = 0;
+            }
         }
     }
     t.pressureDynamic = ((t.coreTemp - 26.0f) * P.pressureTemperatureGain) + t.pressureStatic;
