@@ -360,6 +360,10 @@ struct GridLocal { float* T; PD_HD float get(int p) const { return T[p]; } PD_HD
 template <class SVX> struct GridSV { const SVX& sv; int base; PD_HD float get(int p) const { return sv.f(base + p); } PD_HD void set(int p, float v) const { sv.f(base + p, v); } };
 /* the grid words of a batch larger than L2 come from HBM; the sweep is a rolled loop with a loop-carried dependency, so its first touch of every line would be
  * exposed latency: ask for the 36 lines (one 128-byte line per word and warp) when the tyre's step begins, a ray cast and the force model ahead of the sweep */
+#ifndef PD_PUNCTURE_FUSED
+#define PD_PUNCTURE_FUSED 1      /* in-place grid: stepPuncture's stripe sums come out of the thermal sweep (0: read the grid on the spot, as the other layouts do).
+                                  * A/B on one B200, M car-ticks/s, fused / on the spot (both with the L1 prefetch): 65536 envs 87.3 / 86.0, 32768 envs (255-register instance) 64.2 / 65.9 */
+#endif
 #ifndef PD_GRID_PREFETCH
 #define PD_GRID_PREFETCH 1
 #endif
@@ -600,11 +604,11 @@ template <class SVX> PD_HDN void tyre_step(const PdCarParams& PP, const TrackDev
                 t.Fy *= fM; t.Fx *= fM; t.Mz *= fM;
             }
             if (PP.mechanicalDamageRate > 0.0f) { /* stepPuncture (TyreForces.cpp:235-247) */
-                if constexpr (sv_traits<SVX>::grid_in_place) punctureCheck = true;       /* deferred to the thermal sweep below, which reads the same 36 words (inflation is not read again this tick) */
+                if constexpr (sv_traits<SVX>::grid_in_place && PD_PUNCTURE_FUSED) punctureCheck = true;       /* deferred to the thermal sweep below, which reads the same 36 words (inflation is not read again this tick) */
                 else {
                     bool expl = false;
                     PD_UNROLL
-                    for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) s += t.T[j + i * 12]; if (s / 12.0f > P.explosionTemperature) expl = true; }
+                    for (int i = 0; i < 3; ++i) { float s = 0; PD_UNROLL for (int j = 0; j < 12; ++j) { if constexpr (sv_traits<SVX>::grid_in_place) s += sv.f(PD_OFF_TYRE_PATCH(w) + j + i * 12); else s += t.T[j + i * 12]; } if (s / 12.0f > P.explosionTemperature) expl = true; }
                     if (expl) t.inflation = 0;
                 }
             }
